@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors from the REAL reference (oracle/_ref, the mechanically
+py3-translated copy of /root/reference/src written by oracle/make_ref.py).
+
+Runs only in the build container (needs /root/reference).  Output: tests/golden/*.npz, small on
+purpose.  Inputs are stored next to the expected outputs so the GPU box (which has neither
+/root/reference nor oracle/_ref) can replay them.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import make_ref  # noqa: E402
+
+sys.path.insert(0, make_ref.build())
+warnings.simplefilter('ignore')
+import magphase as mp  # noqa: E402  (the reference)
+import libaudio as la  # noqa: E402
+
+from magphase_b200.synth import synth_utterance  # noqa: E402
+
+REF_DATA = '/root/reference/demos/data_48k'
+BIN_STEP = 32
+FULL_ROWS = [0, 3, 17, 40, -1]
+
+
+def lossless():
+    fs = 48000
+    sig, pm, voi = synth_utterance(7, fs=fs, dur_s=0.4)
+    m_fft, v_shift = mp.analysis_with_del_comp_from_pm(sig, fs, pm)
+    m_mag, m_real, m_imag, v_f0 = mp.compute_lossless_feats(m_fft, v_shift, voi, fs)
+    y = mp.synthesis_from_lossless(m_mag.copy(), m_real.copy(), m_imag.copy(), v_f0.copy(), fs)
+    minph = la.build_min_phase_from_mag_spec(m_mag[FULL_ROWS].copy())
+    np.savez_compressed(
+        os.path.join(HERE, 'lossless_synth48k.npz'),
+        sig_i16=np.round(sig * 32768.0).astype(np.int16), pm=pm, voi=voi, fs=fs,
+        v_shift=v_shift.astype(np.int64), v_f0=v_f0,
+        full_rows=np.array(FULL_ROWS), bin_step=BIN_STEP,
+        mag_rows=m_mag[FULL_ROWS], real_rows=m_real[FULL_ROWS], imag_rows=m_imag[FULL_ROWS],
+        mag_cols=m_mag[:, ::BIN_STEP], real_cols=m_real[:, ::BIN_STEP], imag_cols=m_imag[:, ::BIN_STEP],
+        syn=y, minph_rows=minph)
+    print('lossless: %d frames, syn %d samples' % (v_shift.size, y.size))
+
+
+def compressed():
+    fs = 48000
+    d = os.path.join(REF_DATA, 'params_predicted')
+    n = 64
+    rd = lambda ext, dim: np.fromfile(os.path.join(d, 'hvd_704' + ext), dtype=np.float32).reshape(-1, dim)[40:40 + n]
+    mag, real, imag, lf0 = rd('.mag', 60), rd('.real', 45), rd('.imag', 45), rd('.lf0', 1)[:, 0]
+    f64 = lambda a: a.astype(np.float64)
+    out = {}
+    for name, kw in (('var_nohpf', dict(b_out_hpf=False)), ('var_hpf', dict(b_out_hpf=True)),
+                     ('const_nohpf', dict(b_out_hpf=False, b_const_rate=True)),
+                     ('minph_nohpf', dict(b_out_hpf=False, per_phase_type='min_phase'))):
+        np.random.seed(1234)
+        out['syn_' + name] = mp.synthesis_from_compressed(f64(mag), f64(real), f64(imag), f64(lf0), fs, **kw)
+    np.random.seed(1234)
+    out['syn_16k_const_hpf'] = mp.synthesis_from_compressed(f64(mag), f64(real), f64(imag), f64(lf0), 16000,
+                                                            b_const_rate=True)
+    pf48 = mp.post_filter(f64(mag), 48000)
+    pf16 = mp.post_filter(f64(mag), 16000)
+    unw = la.sp_mel_unwarp(f64(mag)[:4], 2049, alpha=0.77, in_type='log')
+    r_unw, i_unw = mp.phase_uncompress_type1_mcep(f64(real)[:4], f64(imag)[:4], 0.77, 4096, fs)
+    np.savez_compressed(os.path.join(HERE, 'compressed_hvd704.npz'),
+                        mag=mag, real=real, imag=imag, lf0=lf0, fs=fs, seed=1234,
+                        post_filter_48k=pf48, post_filter_16k=pf16,
+                        mag_unwarp4=unw, real_unwarp4=r_unw, imag_unwarp4=i_unw, **out)
+    print('compressed:', {k: v.shape for k, v in out.items()})
+
+
+if __name__ == '__main__':
+    lossless()
+    compressed()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith('.npz'):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

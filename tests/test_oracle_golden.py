@@ -1,0 +1,104 @@
+"""The numpy oracle against the committed golden vectors (generated from the real reference by
+tests/golden/make_golden.py).  No /root/reference needed: this is what pins the oracle on the GPU box."""
+import os
+import warnings
+
+import numpy as np
+
+import magphase_oracle as orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def test_lossless_analysis_golden():
+    g = load('lossless_synth48k.npz')
+    sig = g['sig_i16'].astype(np.float64) / 32768.0
+    mag, real, imag, f0, fs, v_shift = orc.analysis_lossless_from_pm(sig, int(g['fs']), g['pm'], g['voi'])
+    assert np.array_equal(v_shift, g['v_shift'])
+    assert np.array_equal(f0, g['v_f0'])
+    rows, st = g['full_rows'], int(g['bin_step'])
+    np.testing.assert_allclose(mag[rows], g['mag_rows'], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(real[rows], g['real_rows'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(imag[rows], g['imag_rows'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(mag[:, ::st], g['mag_cols'], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(real[:, ::st], g['real_cols'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(imag[:, ::st], g['imag_cols'], rtol=0, atol=1e-9)
+    y = orc.synthesis_from_lossless(mag, real, imag, f0, fs)
+    assert y.shape == g['syn'].shape
+    np.testing.assert_allclose(y, g['syn'], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(orc.build_min_phase_from_mag_spec(mag[rows]), g['minph_rows'], rtol=1e-11, atol=1e-12)
+
+
+def test_compressed_synthesis_golden():
+    g = load('compressed_hvd704.npz')
+    f64 = lambda k: g[k].astype(np.float64)
+    mag, real, imag, lf0 = f64('mag'), f64('real'), f64('imag'), f64('lf0')
+    cases = {'syn_var_nohpf': dict(b_out_hpf=False), 'syn_var_hpf': dict(b_out_hpf=True),
+             'syn_const_nohpf': dict(b_out_hpf=False, b_const_rate=True),
+             'syn_minph_nohpf': dict(b_out_hpf=False, per_phase_type='min_phase')}
+    for k, kw in cases.items():
+        np.random.seed(int(g['seed']))
+        y = orc.synthesis_from_compressed(mag, real, imag, lf0, 48000, **kw)
+        assert y.shape == g[k].shape, k
+        # HPF: direct-form IIR rounding noise ~1e-8 (see tests/test_oracle_vs_ref.py)
+        np.testing.assert_allclose(y, g[k], rtol=0, atol=1e-6 if kw.get('b_out_hpf') else 1e-12, err_msg=k)
+    np.random.seed(int(g['seed']))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        y = orc.synthesis_from_compressed(mag, real, imag, lf0, 16000, b_const_rate=True)
+    assert y.shape == g['syn_16k_const_hpf'].shape
+    np.testing.assert_allclose(y, g['syn_16k_const_hpf'], rtol=0, atol=1e-6)
+
+
+def test_post_filter_and_unwarp_golden():
+    g = load('compressed_hvd704.npz')
+    mag = g['mag'].astype(np.float64)
+    np.testing.assert_allclose(orc.post_filter(mag, 48000), g['post_filter_48k'], rtol=0, atol=1e-13)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        np.testing.assert_allclose(orc.post_filter(mag, 16000), g['post_filter_16k'], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(orc.sp_mel_unwarp(mag[:4], 2049, 0.77), g['mag_unwarp4'], rtol=0, atol=1e-12)
+    r, i = orc.phase_uncompress(g['real'][:4].astype(np.float64), g['imag'][:4].astype(np.float64), 0.77, 4096, 48000)
+    np.testing.assert_allclose(r, g['real_unwarp4'], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(i, g['imag_unwarp4'], rtol=0, atol=1e-12)
+
+
+def test_freqt_matrix_matches_scalar_recursion():
+    """The vectorised freqt matrix against a literal scalar run of the published SPTK recursion."""
+    rng = np.random.default_rng(1)
+    c = rng.normal(size=40) * np.exp(-np.arange(40) / 8.0)
+    a, m2 = 0.77, 11
+    g = np.zeros(m2 + 1)
+    d = np.zeros(m2 + 1)
+    b = 1 - a * a
+    for i in range(-(c.size - 1), 1):
+        d[0] = g[0]
+        g[0] = c[-i] + a * d[0]
+        d[1] = g[1]
+        g[1] = b * d[0] + a * d[1]
+        for j in range(2, m2 + 1):
+            d[j] = g[j]
+            g[j] = d[j - 1] + a * (d[j] - g[j - 1])
+    np.testing.assert_allclose(orc.freqt_matrix(m2 + 1, c.size, a) @ c, g, rtol=1e-12, atol=1e-13)
+
+
+def test_mel_warp_unwarp_roundtrip_sane():
+    """sp_mel_warp (SPTK restatement, parity unpinned) followed by the pinned sp_mel_unwarp must give back a
+    smoothed version of the input log spectrum."""
+    g = load('lossless_synth48k.npz')
+    sig = g['sig_i16'].astype(np.float64) / 32768.0
+    mag, real, imag, f0, fs, v_shift = orc.analysis_lossless_from_pm(sig, 48000, g['pm'], g['voi'])
+    mel = orc.sp_mel_warp(mag, 60, alpha=0.77, in_type=3)
+    back = orc.sp_mel_unwarp(np.log(mel), 2049, alpha=0.77, in_type='log')
+    voiced = g['voi'] > 0
+    lm = np.log(mag[voiced][:, :400])
+    cc = np.corrcoef(lm.ravel(), back[voiced][:, :400].ravel())[0, 1]
+    assert cc > 0.9
+    mm, rr, ii, lf0 = orc.format_for_modelling(mag, real, imag, f0, fs)
+    assert mm.shape == (mag.shape[0], 60) and rr.shape == (mag.shape[0], 45) and ii.shape == rr.shape
+    assert np.all(np.abs(rr) <= 1) and np.all(rr[~voiced] == 0)
+    assert np.all(lf0[~voiced] == orc.MAGIC)

@@ -1,0 +1,158 @@
+"""Pin the numpy oracle (oracle/magphase_oracle.py) against the real reference (oracle/_ref, the
+mechanically py3-translated copy of /root/reference/src).  Runs only where /root/reference exists."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import magphase_oracle as orc
+from magphase_b200.synth import synth_marks_for_wav, synth_utterance
+
+from conftest import REF_DATA
+
+
+def _wav(name):
+    from scipy.io import wavfile
+    fs, d = wavfile.read(os.path.join(REF_DATA, 'wavs_nat', name + '.wav'))
+    return d.astype(np.float64) / 32768.0, fs
+
+
+def _pred(tok):
+    d = os.path.join(REF_DATA, 'params_predicted')
+    rd = lambda ext, dim: np.fromfile(os.path.join(d, tok + ext), dtype=np.float32).reshape(-1, dim).astype(np.float64)
+    return rd('.mag', 60), rd('.real', 45), rd('.imag', 45), rd('.lf0', 1)[:, 0]
+
+
+@pytest.mark.parametrize('wav', ['hvd_593', 'hvd_577'])
+def test_lossless_analysis_matches_reference(ref_modules, wav):
+    mp, la, lu = ref_modules
+    sig, fs = _wav(wav)
+    pm, voi = synth_marks_for_wav(sig.size, fs, seed=3)
+    m_fft_r, v_shift_r = mp.analysis_with_del_comp_from_pm(sig, fs, pm)
+    mag_r, real_r, imag_r, f0_r = mp.compute_lossless_feats(m_fft_r, v_shift_r, voi, fs)
+    mag, real, imag, f0, _, v_shift = orc.analysis_lossless_from_pm(sig, fs, pm, voi)
+    assert np.array_equal(v_shift, v_shift_r)
+    assert np.array_equal(f0, f0_r)
+    np.testing.assert_allclose(mag, mag_r, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(real, real_r, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(imag, imag_r, rtol=0, atol=1e-9)
+
+
+def test_lossless_analysis_fractional_and_edge_marks(ref_modules):
+    mp, la, lu = ref_modules
+    rng = np.random.default_rng(5)
+    sig = rng.uniform(-0.5, 0.5, 30000)
+    # marks include pm[0]=0, a shift of 1, half-integers (half-to-even) and a frame longer than fft_len
+    pm = np.array([0.0, 1.0, 240.5, 241.5, 700.49, 1200.0, 6000.0, 6300.5, 9000.0, 29990.0])
+    voi = (np.arange(pm.size) % 2).astype(float)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m_fft_r, v_shift_r = mp.analysis_with_del_comp_from_pm(sig, 48000, pm)
+        m_fft, v_shift = orc.analysis_fft_from_pm(sig, 48000, pm)
+    assert np.array_equal(v_shift, v_shift_r)
+    np.testing.assert_allclose(m_fft, m_fft_r, rtol=0, atol=1e-11)
+
+
+def test_lossless_synthesis_matches_reference(ref_modules):
+    mp, la, lu = ref_modules
+    sig, pm, voi = synth_utterance(2, dur_s=1.0)
+    mag, real, imag, f0, fs, _ = orc.analysis_lossless_from_pm(sig, 48000, pm, voi)
+    y_r = mp.synthesis_from_lossless(mag.copy(), real.copy(), imag.copy(), f0.copy(), fs)
+    y = orc.synthesis_from_lossless(mag, real, imag, f0, fs)
+    assert y.shape == y_r.shape
+    np.testing.assert_allclose(y, y_r, rtol=0, atol=1e-13)
+
+
+def test_tables_match_reference(ref_modules):
+    mp, la, lu = ref_modules
+    for fs in (48000, 16000):
+        assert orc.define_alpha(fs) == mp.define_alpha(fs)
+        assert orc.define_fft_len(fs) == mp.define_fft_len(fs)
+        assert orc.define_crossfade_params(fs) == mp.define_crossfade_params(fs)
+    for fs, pd, al in ((48000, 45, 0.77), (48000, 10, 0.77), (16000, 45, 0.58), (48000, 10, 0.0)):
+        cf = mp.define_crossfade_params(fs)[0]
+        assert orc.n_full_mel_coeffs(cf, pd, al, fs) == mp.get_num_full_mel_coeffs_from_num_phase_coeffs(cf, pd, al, fs)
+    H = 2049
+    ones, zeros = np.ones((1, H)), np.zeros((1, H))
+    ref_curve = la.spectral_crossfade(ones, zeros, 5000, 2000, 48000, freq_scale='hz', win_func=np.hanning)[0]
+    np.testing.assert_array_equal(orc.crossfade_curve(H, 5000, 2000, 48000), ref_curve)
+    np.testing.assert_array_equal(orc.build_mel_curve(0.77, H, amp=3.5), la.build_mel_curve(0.77, H, amp=3.5))
+    for (l, r) in ((0, 5), (7, 0), (240, 371), (1, 1)):
+        np.testing.assert_array_equal(orc.asym_window(l, r), la.gen_non_symmetric_win(l, r, np.hanning))
+        np.testing.assert_array_equal(orc.asym_window(l, r, 'bartlett2.5'),
+                                      la.gen_non_symmetric_win(l, r, mp.voi_noise_window))
+    np.testing.assert_array_equal(orc.centred_window(480, 611, 4096),
+                                  la.gen_centr_win(480, 611, 4096, win_func=mp.raised_hanning, b_fill_w_bound_val=True))
+
+
+def test_mel_unwarp_and_minphase_match_reference(ref_modules):
+    mp, la, lu = ref_modules
+    mag_mel, real_mel, imag_mel, lf0 = _pred('hvd_704')
+    a = la.sp_mel_unwarp(mag_mel[:40].copy(), 2049, alpha=0.77, in_type='log')
+    b = orc.sp_mel_unwarp(mag_mel[:40], 2049, alpha=0.77, in_type='log')
+    np.testing.assert_allclose(b, a, rtol=0, atol=1e-12)
+    m_mag = np.exp(b)
+    np.testing.assert_allclose(orc.build_min_phase_from_mag_spec(m_mag), la.build_min_phase_from_mag_spec(m_mag.copy()),
+                               rtol=1e-11, atol=1e-12)
+    r1, i1 = mp.phase_uncompress_type1_mcep(real_mel[:30].copy(), imag_mel[:30].copy(), 0.77, 4096, 48000)
+    r2, i2 = orc.phase_uncompress(real_mel[:30], imag_mel[:30], 0.77, 4096, 48000)
+    np.testing.assert_allclose(r2, r1, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(i2, i1, rtol=0, atol=1e-12)
+
+
+def test_post_filter_matches_reference(ref_modules):
+    mp, la, lu = ref_modules
+    mag_mel = _pred('hvd_705')[0]
+    np.testing.assert_allclose(orc.post_filter(mag_mel, 48000), mp.post_filter(mag_mel.copy(), 48000), rtol=0, atol=1e-13)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        np.testing.assert_allclose(orc.post_filter(mag_mel, 16000), mp.post_filter(mag_mel.copy(), 16000), rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize('tok,hpf,ptype', [('hvd_704', True, 'magphase'), ('hvd_708', False, 'magphase'),
+                                           ('hvd_706', False, 'min_phase')])
+def test_compressed_synthesis_matches_reference(ref_modules, tok, hpf, ptype):
+    mp, la, lu = ref_modules
+    mag_mel, real_mel, imag_mel, lf0 = _pred(tok)
+    np.random.seed(11)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        y_r = mp.synthesis_from_compressed(mag_mel.copy(), real_mel.copy(), imag_mel.copy(), lf0.copy(), 48000,
+                                           b_out_hpf=hpf, per_phase_type=ptype)
+    np.random.seed(11)
+    y = orc.synthesis_from_compressed(mag_mel, real_mel, imag_mel, lf0, 48000, b_out_hpf=hpf, per_phase_type=ptype)
+    assert y.shape == y_r.shape
+    # Without the HPF the two agree to ~1e-15.  The reference's 4th-order 40 Hz Butterworth runs as a
+    # direct-form lfilter (src/magphase.py:990-995) whose poles sit at |z|~0.995: its own rounding noise is
+    # ~1e-8, so two float64 evaluations whose inputs differ in the last bit already differ by ~3e-8.
+    np.testing.assert_allclose(y, y_r, rtol=0, atol=1e-6 if hpf else 1e-12)
+    # ('linear' is not cross-checked: the reference raises TypeError under numpy>=2 at src/magphase.py:951.)
+
+
+def test_compressed_synthesis_const_rate_16k_matches_reference(ref_modules):
+    mp, la, lu = ref_modules
+    mag_mel, real_mel, imag_mel, lf0 = _pred('hvd_705')
+    # plumbing input for the 16 kHz constant-rate configuration (BASELINE config 4): same features, lf0 shifted
+    lf0_16 = lf0
+    np.random.seed(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        y_r = mp.synthesis_from_compressed(mag_mel.copy(), real_mel.copy(), imag_mel.copy(), lf0_16.copy(), 16000,
+                                           b_const_rate=True)
+    np.random.seed(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        y = orc.synthesis_from_compressed(mag_mel, real_mel, imag_mel, lf0_16, 16000, b_const_rate=True)
+    assert y.shape == y_r.shape
+    np.testing.assert_allclose(y, y_r, rtol=0, atol=1e-6)   # HPF on (default): see note above
+
+
+def test_var_to_const_rate_matches_reference(ref_modules):
+    mp, la, lu = ref_modules
+    rng = np.random.default_rng(0)
+    v_shift = rng.integers(200, 600, 50)
+    pm = np.cumsum(v_shift)
+    m = rng.normal(size=(50, 7))
+    np.testing.assert_allclose(orc.interp_from_variable_to_const_frm_rate(m, pm, 5.0, 48000),
+                               mp.interp_from_variable_to_const_frm_rate(m.copy(), pm, 5.0, 48000), rtol=0, atol=1e-14)
