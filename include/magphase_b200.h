@@ -1,0 +1,143 @@
+/*
+ * magphase_b200 -- C ABI of the B200-native MagPhase analysis/synthesis hot path.
+ *
+ * The reference (CSTR-Edinburgh/magphase) has no FFI: its boundary is the Python module API of
+ * src/magphase.py.  This header is what a ctypes binding in that module would bind instead of the
+ * NumPy loops; each entry point names the reference interface it replaces (file:line, relative to
+ * the reference root).  See INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *   - every function returns an int status: MPB_OK (0) or a negative MPB_ERR_* code; nothing throws.
+ *     mpb_last_error() gives the message for the last failure on the calling thread.
+ *   - the caller allocates and owns every buffer.  Functions ending in _dev take DEVICE pointers and
+ *     enqueue on `stream` (a cudaStream_t passed as void*; NULL = default stream) without
+ *     synchronising.  Functions ending in _host take HOST pointers (NumPy arrays), stage through
+ *     pinned memory, run the same kernels and return after the results are back on the host.
+ *   - matrices are C-contiguous, row = frame, exactly like the reference's NumPy arrays
+ *     (nfrms x (fft_len/2+1) for mag/real/imag).
+ *   - integer frame bookkeeping (rounding / truncation of pitch marks, cumsum) is done by the host
+ *     mirror in float64 NumPy with the reference's expression order and handed over as int arrays.
+ */
+#ifndef MAGPHASE_B200_H
+#define MAGPHASE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPB_OK 0
+#define MPB_ERR_BAD_ARG (-1)      /* NULL pointer, negative size, unknown dtype ...   -> ValueError */
+#define MPB_ERR_FFT_LEN (-2)      /* fft_len not one of 1024 / 2048 / 4096            -> ValueError */
+#define MPB_ERR_FRAME_GEOM (-3)   /* a frame's left length >= fft_len, marks not increasing ...     */
+#define MPB_ERR_CUDA (-4)         /* CUDA runtime failure (message has the cudaError string)        */
+#define MPB_ERR_NO_DEVICE (-5)    /* no usable CUDA device: there is NO CPU fallback                */
+#define MPB_ERR_DIM (-6)          /* mel dimensions exceed the compiled limits                      */
+
+/* element types of caller buffers */
+#define MPB_F32 0
+#define MPB_F64 1
+
+/* window applied to each side of a pitch-synchronous frame (mpb_frames_*) */
+#define MPB_WIN_HANN 0            /* np.hanning halves               src/libaudio.py:70-84 */
+#define MPB_WIN_BARTLETT25 1      /* np.bartlett(.)**2.5 halves      src/magphase.py:67-69 */
+
+typedef struct mpb_ctx mpb_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* Creates the per-device context: twiddle tables, mel/unwarp matrices cache, pinned staging.      */
+int mpb_create(int device, mpb_ctx** out_ctx);
+int mpb_destroy(mpb_ctx* ctx);
+const char* mpb_last_error(void);
+const char* mpb_version(void);
+/* number of kernels this library has launched since the context was created (bench accounting)   */
+int64_t mpb_launch_count(const mpb_ctx* ctx);
+
+/* ---- lossless analysis --------------------------------------------------------------------- */
+/*
+ * Replaces windowing() + the pad/rotate loop + np.fft.fft + remove_hermitian_half of
+ * analysis_with_del_comp_from_pm (src/magphase.py:74-119, :266-334) and compute_lossless_feats
+ * (:457-476) for a batch of frames.
+ *
+ *   sig        concatenated signals of all utterances in the batch (sig_dtype)
+ *   n_sig      total samples in sig
+ *   centre[f]  absolute index into sig of frame f's pitch mark  (P[f+1] + utterance base)
+ *   left[f]    P[f+1]-P[f]   (= v_shift[f]);   right[f] = P[f+2]-P[f+1]
+ *   win[f]     MPB_WIN_* per frame, or NULL for all-Hann
+ *   out_*      nfrm x (fft_len/2+1), out_dtype; mag=|X|, real=Re X/|X|, imag=Im X/|X| (0 where |X|==0)
+ *   compute_dtype  MPB_F64: float64 butterflies (needed for 1e-5 on real/imag of near-silent bins)
+ *                  MPB_F32: float32 butterflies
+ */
+int mpb_analysis_lossless_dev(mpb_ctx* ctx, void* stream,
+                              const void* sig, int sig_dtype, int64_t n_sig,
+                              const int64_t* centre, const int32_t* left, const int32_t* right,
+                              const uint8_t* win, int64_t nfrm, int fft_len, int compute_dtype,
+                              void* out_mag, void* out_real, void* out_imag, int out_dtype);
+
+int mpb_analysis_lossless_host(mpb_ctx* ctx,
+                               const double* sig, int64_t n_sig,
+                               const int64_t* centre, const int32_t* left, const int32_t* right,
+                               const uint8_t* win, int64_t nfrm, int fft_len, int compute_dtype,
+                               double* out_mag, double* out_real, double* out_imag);
+
+/* Complex half spectra only (m_fft of analysis_with_del_comp_from_pm, src/magphase.py:325-332):
+ * out_fft is nfrm x (fft_len/2+1) x 2 (re, im interleaved == complex64/complex128).              */
+int mpb_frames_fft_dev(mpb_ctx* ctx, void* stream,
+                       const void* sig, int sig_dtype, int64_t n_sig,
+                       const int64_t* centre, const int32_t* left, const int32_t* right,
+                       const uint8_t* win, int64_t nfrm, int fft_len, int compute_dtype,
+                       void* out_fft, int out_dtype);
+
+/* Host variant of mpb_frames_fft_dev: out_fft is nfrm x (fft_len/2+1) complex128.                */
+int mpb_frames_fft_host(mpb_ctx* ctx,
+                        const double* sig, int64_t n_sig,
+                        const int64_t* centre, const int32_t* left, const int32_t* right,
+                        const uint8_t* win, int64_t nfrm, int fft_len, int compute_dtype,
+                        double* out_fft);
+
+/* ---- lossless synthesis -------------------------------------------------------------------- */
+/*
+ * Host-side planner for the overlap-add: splits every utterance's frames into "runs" of about
+ * target_frames consecutive frames, each spanning at least fft_len samples (so that at most two runs
+ * ever touch the same output sample and the result is bit-reproducible).  All pointers are HOST
+ * pointers.  A run is 4 x int32: {first frame (global index), frame count, utterance, flags
+ * (bit0: has a previous run in the utterance, bit1: has a next run)}.  Call with out_runs = NULL
+ * to get the count.  Also validates that pm is strictly increasing inside every utterance.
+ */
+int mpb_plan_ola_runs(const int32_t* pm, const int64_t* utt_frm_off, int32_t n_utt, int fft_len,
+                      int32_t target_frames, int32_t* out_runs, int64_t capacity, int64_t* n_runs);
+
+/*
+ * Replaces synthesis_from_lossless (src/magphase.py:1759-1776): normalise real+j*imag, scale by mag,
+ * Hermitian inverse FFT (la.add_hermitian_half src/libaudio.py:369-388 + np.fft.ifft), fftshift and
+ * ola() (src/magphase.py:34-62) for a batch of utterances.
+ *
+ *   mag/real/imag  nfrm_total x (fft_len/2+1), feat_dtype, frames of all utterances concatenated
+ *   pm[f]          integer pitch-mark position of frame f inside its utterance: trunc(cumsum(shift))
+ *   utt_out_off    [n_utt+1] first output sample of each utterance in `out`
+ *   utt_t0[u]      position (same axis as pm) of the utterance's first output sample:
+ *                  out[utt_out_off[u] + j] = sum_i frame_i[(t0 + j) - pm_i + N/2]
+ *                  (the reference's cut v_sig[(N/2 - pm[0]):][:pm[-1]+shift[-1]+1] is t0 = 0)
+ *   runs, n_runs   the plan from mpb_plan_ola_runs, uploaded by the caller (device pointer)
+ *   out            n_out = utt_out_off[n_utt] samples, out_dtype; fully overwritten
+ */
+int mpb_synthesis_lossless_dev(mpb_ctx* ctx, void* stream,
+                               const void* mag, const void* real, const void* imag, int feat_dtype,
+                               const int32_t* pm, int64_t nfrm_total,
+                               const int64_t* utt_out_off, const int32_t* utt_t0, int32_t n_utt,
+                               const int32_t* runs, int32_t n_runs, int fft_len, int compute_dtype,
+                               void* out, int out_dtype, int64_t n_out);
+
+/* Host variant: plans the runs itself; utt_frm_off is [n_utt+1] first frame of each utterance.     */
+int mpb_synthesis_lossless_host(mpb_ctx* ctx,
+                                const double* mag, const double* real, const double* imag,
+                                const int32_t* pm, int64_t nfrm_total,
+                                const int64_t* utt_frm_off, const int64_t* utt_out_off, const int32_t* utt_t0,
+                                int32_t n_utt, int fft_len, int compute_dtype,
+                                double* out, int64_t n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGPHASE_B200_H */

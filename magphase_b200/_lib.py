@@ -1,0 +1,108 @@
+"""ctypes binding of libmagphase_b200.so (the C ABI declared in include/magphase_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is usable, every compute
+entry point raises.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmagphase_b200.so')
+
+MPB_F32, MPB_F64 = 0, 1
+WIN_HANN, WIN_BARTLETT25 = 0, 1
+_VALUE_ERRORS = (-1, -2, -3, -6)
+
+_lib = None
+_lock = threading.Lock()
+_ctx = {}
+
+_vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/magphase_b200.h
+SIGNATURES = {
+    'mpb_create': [C.c_int, C.POINTER(_vp)],
+    'mpb_destroy': [_vp],
+    'mpb_last_error': [],
+    'mpb_version': [],
+    'mpb_launch_count': [_vp],
+    'mpb_analysis_lossless_dev': [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int,
+                                  _vp, _vp, _vp, C.c_int],
+    'mpb_analysis_lossless_host': [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp],
+    'mpb_frames_fft_dev': [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_int],
+    'mpb_frames_fft_host': [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp],
+    'mpb_plan_ola_runs': [_vp, _vp, _i32, C.c_int, _i32, _vp, _i64, C.POINTER(_i64)],
+    'mpb_synthesis_lossless_dev': [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _vp, _i32, _vp, _i32,
+                                   C.c_int, C.c_int, _vp, C.c_int, _i64],
+    'mpb_synthesis_lossless_host': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, C.c_int, C.c_int, _vp, _i64],
+}
+_RESTYPES = {'mpb_last_error': C.c_char_p, 'mpb_version': C.c_char_p, 'mpb_launch_count': _i64}
+
+
+def lib():
+    """The loaded shared library (raises if it has not been built: run __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError('magphase_b200: %s is missing -- build it with '
+                                       '`python -c "import __graft_entry__ as g; g.build()"`. '
+                                       'There is no CPU fallback.' % LIB_PATH)
+                l = C.CDLL(LIB_PATH)
+                for name, args in SIGNATURES.items():
+                    fn = getattr(l, name)
+                    fn.argtypes = args
+                    fn.restype = _RESTYPES.get(name, C.c_int)
+                _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = lib().mpb_last_error().decode('utf-8', 'replace')
+    if rc in _VALUE_ERRORS:
+        raise ValueError('magphase_b200: %s' % msg)
+    raise RuntimeError('magphase_b200 (code %d): %s' % (rc, msg))
+
+
+def default_device():
+    for k in ('MPB_DEVICE', 'LOCAL_RANK'):
+        if os.environ.get(k, '') != '':
+            return int(os.environ[k])
+    return 0
+
+
+def ctx(device=None):
+    """Per-device context handle (created on first use)."""
+    device = default_device() if device is None else int(device)
+    with _lock:
+        h = _ctx.get(device)
+    if h is None:
+        l = lib()
+        p = _vp()
+        check(l.mpb_create(device, C.byref(p)))
+        with _lock:
+            _ctx.setdefault(device, p)
+            h = _ctx[device]
+    return h
+
+
+def launch_count(device=None):
+    return int(lib().mpb_launch_count(ctx(device)))
+
+
+def ptr(a):
+    """Host pointer of a C-contiguous numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags['C_CONTIGUOUS']
+    return a.ctypes.data_as(_vp)
+
+
+def as_c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)

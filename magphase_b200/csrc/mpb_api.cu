@@ -1,0 +1,339 @@
+// C-ABI layer of libmagphase_b200.so: context, tables, argument checks, host staging.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "mpb_kernels.h"
+
+using namespace mpb;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return fail(MPB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+struct DevBuf {   // grow-only device scratch
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t need(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct mpb_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;                 // used by the *_host entry points
+    std::map<int, void*> tw32, tw64;               // fft_len -> twiddle table exp(-2 pi i j / N), j < N/2
+    std::mutex mu;                                 // serialises the *_host entry points (shared scratch)
+    std::mutex tw_mu;
+    int64_t launches = 0;
+    DevBuf scratch[12];
+};
+
+static bool fft_len_ok(int n) { return n == 1024 || n == 2048 || n == 4096; }
+static bool dtype_ok(int d) { return d == MPB_F32 || d == MPB_F64; }
+
+static int get_twiddles(mpb_ctx* ctx, int fft_len, int dtype, const void** out) {
+    std::lock_guard<std::mutex> lk(ctx->tw_mu);
+    auto& tab = dtype == MPB_F64 ? ctx->tw64 : ctx->tw32;
+    auto it = tab.find(fft_len);
+    if (it != tab.end()) { *out = it->second; return MPB_OK; }
+    const int n = fft_len / 2;
+    std::vector<double> h64(2 * n);
+    for (int j = 0; j < n; ++j) {
+        const long double a = 2.0L * 3.141592653589793238462643383279502884L * (long double)j / (long double)fft_len;
+        h64[2 * j] = (double)cosl(a);
+        h64[2 * j + 1] = (double)(-sinl(a));
+    }
+    void* d = nullptr;
+    if (dtype == MPB_F64) {
+        CU(cudaMalloc(&d, sizeof(double) * 2 * n));
+        CU(cudaMemcpy(d, h64.data(), sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> h32(2 * n);
+        for (int j = 0; j < 2 * n; ++j) h32[j] = (float)h64[j];
+        CU(cudaMalloc(&d, sizeof(float) * 2 * n));
+        CU(cudaMemcpy(d, h32.data(), sizeof(float) * 2 * n, cudaMemcpyHostToDevice));
+    }
+    tab[fft_len] = d;
+    *out = d;
+    return MPB_OK;
+}
+
+extern "C" {
+
+const char* mpb_last_error(void) { return g_err.c_str(); }
+const char* mpb_version(void) { return "magphase_b200 0.1 (sm_100a)"; }
+
+int mpb_create(int device, mpb_ctx** out_ctx) {
+    if (!out_ctx) return fail(MPB_ERR_BAD_ARG, "out_ctx is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(MPB_ERR_NO_DEVICE, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                           cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(MPB_ERR_BAD_ARG, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    mpb_ctx* c = new mpb_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out_ctx = c;
+    return MPB_OK;
+}
+
+int mpb_destroy(mpb_ctx* ctx) {
+    if (!ctx) return MPB_OK;
+    cudaSetDevice(ctx->device);
+    for (auto& kv : ctx->tw32) cudaFree(kv.second);
+    for (auto& kv : ctx->tw64) cudaFree(kv.second);
+    for (auto& b : ctx->scratch) b.release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MPB_OK;
+}
+
+int64_t mpb_launch_count(const mpb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+static int analysis_common(mpb_ctx* ctx, void* stream, const void* sig, int sig_dtype, int64_t n_sig,
+                           const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* win,
+                           int64_t nfrm, int fft_len, int compute_dtype, void* out_a, void* out_b, void* out_c,
+                           int out_dtype, int mode) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (nfrm < 0 || n_sig < 0) return fail(MPB_ERR_BAD_ARG, "negative size");
+    if (!fft_len_ok(fft_len)) return fail(MPB_ERR_FFT_LEN, "fft_len must be 1024, 2048 or 4096");
+    if (!dtype_ok(sig_dtype) || !dtype_ok(compute_dtype) || !dtype_ok(out_dtype))
+        return fail(MPB_ERR_BAD_ARG, "unknown dtype");
+    if (nfrm == 0) return MPB_OK;
+    if (!sig || !centre || !left || !right || !out_a || (mode == MODE_FEATS && (!out_b || !out_c)))
+        return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    AnalysisArgs a;
+    a.sig = sig; a.sig_dtype = sig_dtype; a.n_sig = n_sig;
+    a.centre = centre; a.left = left; a.right = right; a.win = win;
+    a.nfrm = nfrm; a.fft_len = fft_len; a.compute_dtype = compute_dtype;
+    int rc = get_twiddles(ctx, fft_len, compute_dtype, &a.tw);
+    if (rc != MPB_OK) return rc;
+    a.out_a = out_a; a.out_b = out_b; a.out_c = out_c; a.out_dtype = out_dtype;
+    a.mode = mode; a.num_sms = ctx->num_sms;
+    CU(launch_analysis(a, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return MPB_OK;
+}
+
+int mpb_analysis_lossless_dev(mpb_ctx* ctx, void* stream, const void* sig, int sig_dtype, int64_t n_sig,
+                              const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* win,
+                              int64_t nfrm, int fft_len, int compute_dtype, void* out_mag, void* out_real,
+                              void* out_imag, int out_dtype) {
+    return analysis_common(ctx, stream, sig, sig_dtype, n_sig, centre, left, right, win, nfrm, fft_len, compute_dtype,
+                           out_mag, out_real, out_imag, out_dtype, MODE_FEATS);
+}
+
+int mpb_frames_fft_dev(mpb_ctx* ctx, void* stream, const void* sig, int sig_dtype, int64_t n_sig,
+                       const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* win,
+                       int64_t nfrm, int fft_len, int compute_dtype, void* out_fft, int out_dtype) {
+    return analysis_common(ctx, stream, sig, sig_dtype, n_sig, centre, left, right, win, nfrm, fft_len, compute_dtype,
+                           out_fft, nullptr, nullptr, out_dtype, MODE_FFT);
+}
+
+// Host-side geometry check shared by the *_host entry points (the *_dev ones trust the caller's plan).
+static int check_frames_host(const int64_t* centre, const int32_t* left, const int32_t* right, int64_t nfrm,
+                             int64_t n_sig, int fft_len) {
+    for (int64_t f = 0; f < nfrm; ++f) {
+        if (left[f] < 0 || right[f] < 0) return fail(MPB_ERR_FRAME_GEOM, "negative frame side length");
+        if (left[f] >= fft_len)
+            return fail(MPB_ERR_FRAME_GEOM, "a frame's left length (pitch period) is >= fft_len");
+        if (centre[f] - left[f] < 0 || centre[f] + right[f] >= n_sig)
+            return fail(MPB_ERR_FRAME_GEOM, "frame reaches outside the signal");
+    }
+    return MPB_OK;
+}
+
+static int frames_host(mpb_ctx* ctx, const double* sig, int64_t n_sig, const int64_t* centre, const int32_t* left,
+                       const int32_t* right, const uint8_t* win, int64_t nfrm, int fft_len, int compute_dtype,
+                       double* o0, double* o1, double* o2, int mode) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (nfrm == 0) return MPB_OK;
+    if (!fft_len_ok(fft_len)) return fail(MPB_ERR_FFT_LEN, "fft_len must be 1024, 2048 or 4096");
+    if (!sig || !centre || !left || !right || !o0) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    int rc = check_frames_host(centre, left, right, nfrm, n_sig, fft_len);
+    if (rc != MPB_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int64_t H = fft_len / 2 + 1;
+    const size_t osz = sizeof(double) * (size_t)nfrm * H * (mode == MODE_FFT ? 2 : 1);
+    DevBuf* b = ctx->scratch;
+    CU(b[0].need(sizeof(double) * n_sig));
+    CU(b[1].need(sizeof(int64_t) * nfrm));
+    CU(b[2].need(sizeof(int32_t) * nfrm));
+    CU(b[3].need(sizeof(int32_t) * nfrm));
+    CU(b[4].need(win ? (size_t)nfrm : 1));
+    CU(b[5].need(osz));
+    if (mode == MODE_FEATS) { CU(b[6].need(osz)); CU(b[7].need(osz)); }
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(b[0].p, sig, sizeof(double) * n_sig, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[1].p, centre, sizeof(int64_t) * nfrm, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[2].p, left, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[3].p, right, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
+    if (win) CU(cudaMemcpyAsync(b[4].p, win, (size_t)nfrm, cudaMemcpyHostToDevice, st));
+    rc = analysis_common(ctx, st, b[0].p, MPB_F64, n_sig, (const int64_t*)b[1].p, (const int32_t*)b[2].p,
+                         (const int32_t*)b[3].p, win ? (const uint8_t*)b[4].p : nullptr, nfrm, fft_len, compute_dtype,
+                         b[5].p, b[6].p, b[7].p, MPB_F64, mode);
+    if (rc != MPB_OK) return rc;
+    CU(cudaMemcpyAsync(o0, b[5].p, osz, cudaMemcpyDeviceToHost, st));
+    if (mode == MODE_FEATS) {
+        CU(cudaMemcpyAsync(o1, b[6].p, osz, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(o2, b[7].p, osz, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return MPB_OK;
+}
+
+int mpb_analysis_lossless_host(mpb_ctx* ctx, const double* sig, int64_t n_sig, const int64_t* centre,
+                               const int32_t* left, const int32_t* right, const uint8_t* win, int64_t nfrm,
+                               int fft_len, int compute_dtype, double* out_mag, double* out_real, double* out_imag) {
+    if (nfrm > 0 && (!out_real || !out_imag)) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    return frames_host(ctx, sig, n_sig, centre, left, right, win, nfrm, fft_len, compute_dtype, out_mag, out_real,
+                       out_imag, MODE_FEATS);
+}
+
+int mpb_frames_fft_host(mpb_ctx* ctx, const double* sig, int64_t n_sig, const int64_t* centre, const int32_t* left,
+                        const int32_t* right, const uint8_t* win, int64_t nfrm, int fft_len, int compute_dtype,
+                        double* out_fft) {
+    return frames_host(ctx, sig, n_sig, centre, left, right, win, nfrm, fft_len, compute_dtype, out_fft, nullptr,
+                       nullptr, MODE_FFT);
+}
+
+// ---------------------------------------------------------------------------------------------
+int mpb_plan_ola_runs(const int32_t* pm, const int64_t* utt_frm_off, int32_t n_utt, int fft_len,
+                      int32_t target_frames, int32_t* out_runs, int64_t capacity, int64_t* n_runs) {
+    if (!pm || !utt_frm_off || !n_runs || n_utt < 0) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    if (!fft_len_ok(fft_len)) return fail(MPB_ERR_FFT_LEN, "fft_len must be 1024, 2048 or 4096");
+    if (target_frames < 1) target_frames = 32;
+    int64_t nr = 0;
+    for (int32_t u = 0; u < n_utt; ++u) {
+        const int64_t a = utt_frm_off[u], b = utt_frm_off[u + 1];
+        if (b < a) return fail(MPB_ERR_BAD_ARG, "utt_frm_off not non-decreasing");
+        for (int64_t f = a + 1; f < b; ++f)
+            if (pm[f] <= pm[f - 1]) return fail(MPB_ERR_FRAME_GEOM, "pitch marks must be strictly increasing");
+        int64_t s = a;
+        const int64_t first_run = nr;
+        while (s < b) {
+            int64_t e = s + target_frames < b ? s + target_frames : b;
+            while (e < b && pm[e - 1] - pm[s] < fft_len) ++e;             // every run spans >= fft_len samples
+            if (e < b && pm[b - 1] - pm[e] < fft_len) e = b;              // ... including the last one
+            if (out_runs) {
+                if (nr >= capacity) return fail(MPB_ERR_BAD_ARG, "run buffer too small");
+                out_runs[4 * nr + 0] = (int32_t)s;
+                out_runs[4 * nr + 1] = (int32_t)(e - s);
+                out_runs[4 * nr + 2] = u;
+                out_runs[4 * nr + 3] = (nr > first_run ? 1 : 0) | (e < b ? 2 : 0);
+            }
+            ++nr;
+            s = e;
+        }
+    }
+    *n_runs = nr;
+    return MPB_OK;
+}
+
+int mpb_synthesis_lossless_dev(mpb_ctx* ctx, void* stream, const void* mag, const void* real, const void* imag,
+                               int feat_dtype, const int32_t* pm, int64_t nfrm_total, const int64_t* utt_out_off,
+                               const int32_t* utt_t0, int32_t n_utt, const int32_t* runs, int32_t n_runs, int fft_len,
+                               int compute_dtype, void* out, int out_dtype, int64_t n_out) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (!fft_len_ok(fft_len)) return fail(MPB_ERR_FFT_LEN, "fft_len must be 1024, 2048 or 4096");
+    if (!dtype_ok(feat_dtype) || !dtype_ok(compute_dtype) || !dtype_ok(out_dtype))
+        return fail(MPB_ERR_BAD_ARG, "unknown dtype");
+    if (nfrm_total < 0 || n_out < 0 || n_utt < 0 || n_runs < 0) return fail(MPB_ERR_BAD_ARG, "negative size");
+    if (n_out == 0) return MPB_OK;
+    if (!out) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    if (nfrm_total > 0 && (!mag || !real || !imag || !pm || !utt_out_off || !utt_t0 || !runs))
+        return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    SynthArgs a;
+    a.mag = mag; a.real = real; a.imag = imag; a.feat_dtype = feat_dtype;
+    a.pm = pm; a.nfrm_total = nfrm_total;
+    a.utt_frm_off = nullptr; a.utt_out_off = utt_out_off; a.utt_t0 = utt_t0; a.n_utt = n_utt;
+    a.runs = (const OlaRun*)runs; a.n_runs = n_runs;
+    a.fft_len = fft_len; a.compute_dtype = compute_dtype;
+    int rc = get_twiddles(ctx, fft_len, compute_dtype, &a.tw);
+    if (rc != MPB_OK) return rc;
+    a.out = out; a.out_dtype = out_dtype; a.n_out = n_out; a.num_sms = ctx->num_sms;
+    CU(launch_synthesis_lossless(a, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return MPB_OK;
+}
+
+int mpb_synthesis_lossless_host(mpb_ctx* ctx, const double* mag, const double* real, const double* imag,
+                                const int32_t* pm, int64_t nfrm_total, const int64_t* utt_frm_off,
+                                const int64_t* utt_out_off, const int32_t* utt_t0, int32_t n_utt, int fft_len,
+                                int compute_dtype, double* out, int64_t n_out) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (!fft_len_ok(fft_len)) return fail(MPB_ERR_FFT_LEN, "fft_len must be 1024, 2048 or 4096");
+    if (n_out == 0) return MPB_OK;
+    if (!mag || !real || !imag || !pm || !utt_frm_off || !utt_out_off || !utt_t0 || !out)
+        return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    int64_t n_runs = 0;
+    int target = 32;
+    {   // fewer frames per run when the batch is too small to fill the GPU
+        const int64_t want = (int64_t)ctx->num_sms * 4;
+        if (nfrm_total / target < want) target = (int)(nfrm_total / want > 1 ? nfrm_total / want : 1);
+    }
+    int rc = mpb_plan_ola_runs(pm, utt_frm_off, n_utt, fft_len, target, nullptr, 0, &n_runs);
+    if (rc != MPB_OK) return rc;
+    std::vector<int32_t> runs(4 * (size_t)(n_runs > 0 ? n_runs : 1));
+    rc = mpb_plan_ola_runs(pm, utt_frm_off, n_utt, fft_len, target, runs.data(), n_runs, &n_runs);
+    if (rc != MPB_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    const int64_t H = fft_len / 2 + 1;
+    const size_t fsz = sizeof(double) * (size_t)nfrm_total * H;
+    DevBuf* b = ctx->scratch;
+    CU(b[5].need(fsz)); CU(b[6].need(fsz)); CU(b[7].need(fsz));
+    CU(b[1].need(sizeof(int32_t) * nfrm_total));
+    CU(b[2].need(sizeof(int64_t) * (n_utt + 1)));
+    CU(b[3].need(sizeof(int32_t) * (n_utt + 1)));
+    CU(b[8].need(sizeof(int32_t) * 4 * (size_t)n_runs));
+    CU(b[0].need(sizeof(double) * n_out));
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(b[5].p, mag, fsz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[6].p, real, fsz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[7].p, imag, fsz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[1].p, pm, sizeof(int32_t) * nfrm_total, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[2].p, utt_out_off, sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[3].p, utt_t0, sizeof(int32_t) * n_utt, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[8].p, runs.data(), sizeof(int32_t) * 4 * (size_t)n_runs, cudaMemcpyHostToDevice, st));
+    rc = mpb_synthesis_lossless_dev(ctx, st, b[5].p, b[6].p, b[7].p, MPB_F64, (const int32_t*)b[1].p, nfrm_total,
+                                    (const int64_t*)b[2].p, (const int32_t*)b[3].p, n_utt, (const int32_t*)b[8].p,
+                                    (int32_t)n_runs, fft_len, compute_dtype, b[0].p, MPB_F64, n_out);
+    if (rc != MPB_OK) return rc;
+    CU(cudaMemcpyAsync(out, b[0].p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MPB_OK;
+}
+
+}  // extern "C"

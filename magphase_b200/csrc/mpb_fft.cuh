@@ -1,0 +1,209 @@
+// In-shared-memory FFT engine for pitch-synchronous frames (sm_100a, no cuFFT).
+//
+// A frame of N real samples (N = fft_len = 1024 / 2048 / 4096) is transformed through one complex FFT of
+// M = N/2 points on z[m] = b[2m] + i b[2m+1] followed by the usual real-FFT split.  The M-point FFT is a
+// three-pass Stockham-style decomposition M = 16 x 16 x R3 (R3 = M/256) executed by TPB = M/16 threads:
+// every thread owns 16 points in registers, does a radix-16 butterfly per pass (radix-R3 in the last
+// pass) and exchanges through ONE padded shared-memory buffer:
+//
+//   pass 1  thread t         reads  z[n1*S1 + t]              (registers <- caller)      S1 = M/16
+//           radix-16 over n1, twiddle W_M^(k1*t), writes A[k1*S1 + t]
+//   pass 2  thread (k1,m2)   reads  A[k1*S1 + m1*R3 + m2], radix-16 over m1,
+//           twiddle W_S1^(k2*m2), writes back IN PLACE (same 16 slots, no barrier needed)
+//   pass 3  butterfly (k1,k2) reads A[k1*S1 + k2*R3 + m2], radix-R3 over m2 -> Z[k1 + 16*k2 + 256*k3]
+//
+// "A" is stored with one pad element after every R3 (phys = i + i/R3) so that passes 1, 2 and 3 are all
+// bank-conflict free; the natural-order result is stored with one pad after every 16 (phys = k + k/16).
+// All twiddles come from one table tw[j] = exp(-2*pi*i*j/N), j in [0, N/2), in the compute precision.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mpb {
+
+template <typename T> struct Vec2;
+template <> struct Vec2<float>  { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+
+template <typename T> using cx = typename Vec2<T>::type;
+
+template <typename T> __device__ __forceinline__ cx<T> mk(T x, T y) { cx<T> r; r.x = x; r.y = y; return r; }
+template <typename T2> __device__ __forceinline__ T2 cadd(T2 a, T2 b) { a.x += b.x; a.y += b.y; return a; }
+template <typename T2> __device__ __forceinline__ T2 csub(T2 a, T2 b) { a.x -= b.x; a.y -= b.y; return a; }
+template <typename T2> __device__ __forceinline__ T2 cmul(T2 a, T2 b) {
+    T2 r;
+    r.x = a.x * b.x - a.y * b.y;
+    r.y = a.x * b.y + a.y * b.x;
+    return r;
+}
+template <typename T2> __device__ __forceinline__ T2 cconj(T2 a) { a.y = -a.y; return a; }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV, typename T2> __device__ __forceinline__ T2 rot90(T2 a) {
+    T2 r;
+    if (INV) { r.x = -a.y; r.y = a.x; } else { r.x = a.y; r.y = -a.x; }
+    return r;
+}
+
+// tw table: exp(-2 pi i j / N) for j in [0, N/2).  k may be any value in [0, N).
+template <typename T, int N, bool INV>
+__device__ __forceinline__ cx<T> twiddle(const cx<T>* __restrict__ tw, int k) {
+    cx<T> w = __ldg(&tw[k & (N / 2 - 1)]);
+    if (k & (N / 2)) { w.x = -w.x; w.y = -w.y; }
+    if (INV) w.y = -w.y;
+    return w;
+}
+
+// ---- register butterflies -------------------------------------------------------------------
+template <bool INV, typename T2>
+__device__ __forceinline__ void dft2(T2& a0, T2& a1) {
+    T2 s = cadd(a0, a1), d = csub(a0, a1);
+    a0 = s; a1 = d;
+}
+
+template <bool INV, typename T2>
+__device__ __forceinline__ void dft4(T2& a0, T2& a1, T2& a2, T2& a3) {
+    T2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = rot90<INV>(csub(a1, a3));
+    a0 = cadd(s02, s13);
+    a2 = csub(s02, s13);
+    a1 = cadd(d02, d13);
+    a3 = csub(d02, d13);
+}
+
+// slot -> output index maps of the in-place butterflies below
+__host__ __device__ constexpr int perm2(int s) { return s; }
+__host__ __device__ constexpr int perm4(int s) { return s; }
+__host__ __device__ constexpr int perm8(int s) { return (s >> 1) + 4 * (s & 1); }
+__host__ __device__ constexpr int perm16(int s) { return (s >> 2) + 4 * (s & 3); }
+template <int R> __host__ __device__ constexpr int perm(int s) {
+    return R == 16 ? perm16(s) : (R == 8 ? perm8(s) : s);
+}
+
+// 8-point DFT, in place; output k sits in slot s with k = perm8(s)
+template <bool INV, typename T, typename T2>
+__device__ __forceinline__ void dft8(T2* v) {
+    dft4<INV>(v[0], v[2], v[4], v[6]);   // E[k] -> slot 2k
+    dft4<INV>(v[1], v[3], v[5], v[7]);   // O[k] -> slot 2k+1
+    const T h = (T)0.70710678118654752440;
+    // W8^1, W8^2, W8^3 (forward: exp(-i pi k/4))
+    T2 o1, o2, o3;
+    if (INV) {
+        o1 = mk<T>(h * (v[3].x - v[3].y), h * (v[3].x + v[3].y));
+        o2 = mk<T>(-v[5].y, v[5].x);
+        o3 = mk<T>(-h * (v[7].x + v[7].y), h * (v[7].x - v[7].y));
+    } else {
+        o1 = mk<T>(h * (v[3].x + v[3].y), h * (v[3].y - v[3].x));
+        o2 = mk<T>(v[5].y, -v[5].x);
+        o3 = mk<T>(h * (v[7].y - v[7].x), -h * (v[7].x + v[7].y));
+    }
+    T2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+    v[0] = cadd(e0, o0); v[1] = csub(e0, o0);
+    v[2] = cadd(e1, o1); v[3] = csub(e1, o1);
+    v[4] = cadd(e2, o2); v[5] = csub(e2, o2);
+    v[6] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+// 16-point DFT as 4 x 4, in place; input n = 4*n1 + n2 in slot n; output k in slot s, k = perm16(s)
+template <bool INV, typename T, typename T2>
+__device__ __forceinline__ void dft16(T2* v) {
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) dft4<INV>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+    // v[4*k1 + n2] *= W16^(n2*k1)
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, h = (T)0.70710678118654752440;
+    auto mulw = [&](T2 a, T wr, T wi) {   // a * (wr - i*wi) forward, a * (wr + i*wi) inverse
+        T2 r;
+        if (INV) { r.x = a.x * wr - a.y * wi; r.y = a.y * wr + a.x * wi; }
+        else     { r.x = a.x * wr + a.y * wi; r.y = a.y * wr - a.x * wi; }
+        return r;
+    };
+    v[5]  = mulw(v[5], c1, s1);                        // W16^1
+    v[6]  = mulw(v[6], h, h);                          // W16^2
+    v[7]  = mulw(v[7], s1, c1);                        // W16^3
+    v[9]  = mulw(v[9], h, h);                          // W16^2
+    v[10] = rot90<INV>(v[10]);                         // W16^4 = -i
+    v[11] = mulw(v[11], -h, h);                        // W16^6
+    v[13] = mulw(v[13], s1, c1);                       // W16^3
+    v[14] = mulw(v[14], -h, h);                        // W16^6
+    v[15] = mulw(v[15], -c1, -s1);                     // W16^9
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) dft4<INV>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+}
+
+template <int R, bool INV, typename T, typename T2>
+__device__ __forceinline__ void dftR(T2* v) {
+    if (R == 16) dft16<INV, T>(v);
+    else if (R == 8) dft8<INV, T>(v);
+    else if (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
+    else dft2<INV>(v[0], v[1]);
+}
+
+// ---- geometry -------------------------------------------------------------------------------
+template <int N> struct FftGeom {
+    static constexpr int M = N / 2;           // complex points
+    static constexpr int TPB = M / 16;        // threads per frame
+    static constexpr int S1 = M / 16;         // stride of pass 1
+    static constexpr int R3 = M / 256;        // radix of pass 3 (2, 4, 8 or 16)
+    static constexpr int NB3 = 16 / R3;       // pass-3 butterflies per thread
+    static constexpr int A_ELEMS = M + M / R3;        // padded exchange layout
+    static constexpr int NAT_ELEMS = M + M / 16 + 1;  // padded natural-order layout (+1: slot for index M)
+    static constexpr int BUF_ELEMS = (A_ELEMS > NAT_ELEMS ? A_ELEMS : NAT_ELEMS);
+    __host__ __device__ static constexpr int aphys(int i) { return i + i / R3; }
+    __host__ __device__ static constexpr int nphys(int k) { return k + (k >> 4); }
+};
+
+// M-point complex FFT of the 16 values per thread in v (v[n1] = z[n1*S1 + t]).
+// On return the natural-order spectrum Z[k] is in buf[nphys(k)], k in [0, M), and the CTA is synchronised.
+// INV=true computes the un-normalised inverse transform (sum with exp(+...)).
+template <typename T, int N, bool INV>
+__device__ __forceinline__ void fft_m(cx<T>* v, cx<T>* __restrict__ buf, const cx<T>* __restrict__ tw, int t) {
+    using G = FftGeom<N>;
+    using T2 = cx<T>;
+    constexpr int S1 = G::S1, R3 = G::R3;
+
+    // pass 1
+    dft16<INV, T>(v);
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int k1 = perm16(s);
+        T2 x = v[s];
+        if (k1 != 0) x = cmul(x, twiddle<T, N, INV>(tw, 2 * k1 * t));
+        buf[G::aphys(k1 * S1 + t)] = x;
+    }
+    __syncthreads();
+
+    // pass 2 (in place)
+    {
+        const int k1 = t / R3, m2 = t % R3;
+        const int base = k1 * S1 + m2;
+#pragma unroll
+        for (int m1 = 0; m1 < 16; ++m1) v[m1] = buf[G::aphys(base + m1 * R3)];
+        dft16<INV, T>(v);
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+            const int k2 = perm16(s);
+            T2 x = v[s];
+            if (k2 != 0) x = cmul(x, twiddle<T, N, INV>(tw, 32 * k2 * m2));
+            buf[G::aphys(base + k2 * R3)] = x;
+        }
+    }
+    __syncthreads();
+
+    // pass 3: NB3 butterflies of radix R3 per thread; results kept in v[i*R3 + slot]
+#pragma unroll
+    for (int i = 0; i < G::NB3; ++i) {
+        const int b = t + i * G::TPB;        // b = k1*16 + k2
+#pragma unroll
+        for (int m2 = 0; m2 < R3; ++m2) v[i * R3 + m2] = buf[G::aphys(b * R3 + m2)];
+        dftR<R3, INV, T>(v + i * R3);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < G::NB3; ++i) {
+        const int b = t + i * G::TPB;
+        const int k12 = (b >> 4) + 16 * (b & 15);   // k1 + 16*k2
+#pragma unroll
+        for (int s = 0; s < R3; ++s) buf[G::nphys(k12 + 256 * perm<R3>(s))] = v[i * R3 + s];
+    }
+    __syncthreads();
+}
+
+}  // namespace mpb

@@ -1,0 +1,43 @@
+// Internal launch interfaces between the C-ABI layer (mpb_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/magphase_b200.h"
+
+namespace mpb {
+
+enum { MODE_FEATS = 0, MODE_FFT = 1 };
+
+struct AnalysisArgs {
+    const void* sig; int sig_dtype; int64_t n_sig;
+    const int64_t* centre; const int32_t* left; const int32_t* right; const uint8_t* win;
+    int64_t nfrm; int fft_len; int compute_dtype;
+    const void* tw;                 // twiddle table in the compute precision
+    void* out_a; void* out_b; void* out_c; int out_dtype;
+    int mode;                       // MODE_FEATS: a=mag b=real c=imag;  MODE_FFT: a=interleaved complex
+    int num_sms;
+};
+cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st);
+
+// One OLA run = consecutive frames of one utterance handled by one CTA (see mpb_synthesis.cu).
+struct OlaRun {
+    int32_t first;      // global index of the first frame
+    int32_t count;      // frames in the run
+    int32_t utt;        // utterance index
+    int32_t flags;      // bit0: a previous run of the same utterance exists, bit1: a next run exists
+};
+
+struct SynthArgs {
+    const void* mag; const void* real; const void* imag; int feat_dtype;
+    const int32_t* pm; int64_t nfrm_total;
+    const int64_t* utt_frm_off; const int64_t* utt_out_off; const int32_t* utt_t0; int32_t n_utt;
+    const OlaRun* runs; int32_t n_runs;
+    int fft_len; int compute_dtype;
+    const void* tw;
+    void* out; int out_dtype; int64_t n_out;
+    int num_sms;
+};
+cudaError_t launch_synthesis_lossless(const SynthArgs& a, cudaStream_t st);
+
+}  // namespace mpb

@@ -1,0 +1,178 @@
+// Lossless synthesis kernel: features -> Hermitian inverse FFT -> pitch-synchronous overlap-add.
+//
+// Work unit = an "OLA run": a stretch of consecutive frames of one utterance (host-chosen, each run
+// spans >= fft_len samples).  One CTA of M/16 threads walks its run frame by frame:
+//   load mag/real/imag rows (coalesced) -> X = mag * u/|u| -> pack the Hermitian spectrum into the
+//   half-size complex spectrum Z -> inverse FFT (mpb_fft.cuh) -> add the N samples (fftshift is index
+//   math) into a circular N-sample accumulator in shared memory -> flush the samples no later frame
+//   of the run can touch (everything left of pm[i+1] - N/2) to HBM.
+// Frames are added in index order like the reference's loop (src/magphase.py:43-56).  Output samples
+// that a neighbouring run also touches (within N/2 of the run boundary) are combined with a float
+// atomicAdd onto the zero-initialised output: there are at most TWO contributors per sample (runs span
+// >= N samples), and a+b == b+a, so the result is bit-reproducible run to run.
+// Reference: synthesis_from_lossless src/magphase.py:1759-1776, la.add_hermitian_half
+// src/libaudio.py:369-388 (imag of DC/Nyquist dropped), ola() src/magphase.py:34-62.
+#include "mpb_fft.cuh"
+#include "mpb_kernels.h"
+
+namespace mpb {
+
+template <typename T, typename TF>
+__device__ __forceinline__ cx<T> feat_to_spec(TF mag, TF re, TF im) {
+    // (real + j imag) / |.| with |.| == 0 -> 1, times mag          src/magphase.py:1761-1766
+    const T r = (T)re, i = (T)im;
+    T a = hypot(r, i);
+    if (a == (T)0) a = (T)1;
+    const T s = (T)mag / a;
+    return mk<T>(r * s, i * s);
+}
+
+template <typename T, int N> struct SynthCfg {
+    static constexpr int MINB = (sizeof(T) == 8 ? 384 : 768) / FftGeom<N>::TPB;
+};
+
+template <typename T, typename TF, typename TO, int N>
+__global__ void __launch_bounds__(FftGeom<N>::TPB, SynthCfg<T, N>::MINB)
+k_synthesis_lossless(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __restrict__ imag,
+                     const int32_t* __restrict__ pm, const int64_t* __restrict__ utt_out_off,
+                     const int32_t* __restrict__ utt_t0, const OlaRun* __restrict__ runs, int32_t n_runs,
+                     const cx<T>* __restrict__ tw, TO* __restrict__ out) {
+    using G = FftGeom<N>;
+    using T2 = cx<T>;
+    constexpr int M = G::M, H = M + 1, TPB = G::TPB, HALF = N / 2;
+    constexpr int NP = (M / 2) / TPB;            // spectrum pairs (k, M-k) per thread, k in [0, M/2)
+    constexpr int NPB = NP / 2;                  // pairs per load batch
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T2* buf = reinterpret_cast<T2*>(smem_raw);
+    T* acc = reinterpret_cast<T*>(buf + G::BUF_ELEMS);
+    const int t = threadIdx.x;
+    const T scale = (T)1 / (T)N;
+
+    for (int r = blockIdx.x; r < n_runs; r += gridDim.x) {
+        const OlaRun run = runs[r];
+        const int64_t out_off = utt_out_off[run.utt];
+        const int64_t out_len = utt_out_off[run.utt + 1] - out_off;
+        const int t0 = utt_t0[run.utt];
+        // positions (pm axis) outside [own_lo, own_hi) may also be written by the neighbouring runs
+        const int own_lo = (run.flags & 1) ? pm[run.first - 1] + HALF : INT32_MIN;
+        const int own_hi = (run.flags & 2) ? pm[run.first + run.count] - HALF : INT32_MAX;
+
+        for (int n = t; n < N; n += TPB) acc[n] = (T)0;
+        __syncthreads();
+
+        for (int fr = 0; fr < run.count; ++fr) {
+            const int64_t g = (int64_t)run.first + fr;
+            const int p = pm[g];
+            const int64_t row = g * (int64_t)H;
+
+            // ---- load the half spectrum, build Z (natural padded layout) ----
+            // (two batches of NP/2 pairs: 6*NP/2 independent loads in flight per thread)
+#pragma unroll 1
+            for (int jb = 0; jb < NP; jb += NPB) {
+                TF fa[NPB][3], fb[NPB][3];
+#pragma unroll
+                for (int j = 0; j < NPB; ++j) {
+                    const int k = t + (jb + j) * TPB;
+                    fa[j][0] = mag[row + k];       fa[j][1] = real[row + k];       fa[j][2] = imag[row + k];
+                    fb[j][0] = mag[row + M - k];   fb[j][1] = real[row + M - k];   fb[j][2] = imag[row + M - k];
+                }
+#pragma unroll
+                for (int j = 0; j < NPB; ++j) {
+                    const int k = t + (jb + j) * TPB;
+                    T2 a = feat_to_spec<T, TF>(fa[j][0], fa[j][1], fa[j][2]);
+                    T2 b = feat_to_spec<T, TF>(fb[j][0], fb[j][1], fb[j][2]);
+                    if (k == 0) { a.y = (T)0; b.y = (T)0; }          // Im X[0] = Im X[M] = 0
+                    b.y = -b.y;                                       // B = conj(X[M-k])
+                    const T2 e = cadd(a, b);
+                    const T2 o = cmul(csub(a, b), twiddle<T, N, true>(tw, k));
+                    buf[G::nphys(k)] = mk<T>(e.x - o.y, e.y + o.x);   // Z[k] = E + iO
+                    if (k != 0) buf[G::nphys(M - k)] = mk<T>(e.x + o.y, -e.y + o.x);   // conj(E) + i conj(O)
+                }
+            }
+            if (t == 0) {                                         // k = M/2 pairs with itself
+                T2 a = feat_to_spec<T, TF>(mag[row + M / 2], real[row + M / 2], imag[row + M / 2]);
+                buf[G::nphys(M / 2)] = mk<T>((T)2 * a.x, (T)-2 * a.y);
+            }
+            __syncthreads();
+            T2 v[16];
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) v[n1] = buf[G::nphys(n1 * G::S1 + t)];
+            __syncthreads();
+            fft_m<T, N, true>(v, buf, tw, t);
+
+            // ---- overlap-add: sample n of the frame sits at p + (n < N/2 ? n : n - N) ----
+            const T* bufT = reinterpret_cast<const T*>(buf);
+#pragma unroll 8
+            for (int n = t; n < N; n += TPB) {
+                const T x = bufT[2 * G::nphys(n >> 1) + (n & 1)] * scale;
+                const int pos = p + (n < HALF ? n : n - N);
+                acc[pos & (N - 1)] += x;
+            }
+            __syncthreads();
+
+            // ---- flush what no later frame of this run can touch ----
+            const int lo = p - HALF;
+            int hi = p + HALF;
+            if (fr + 1 < run.count) { const int nx = pm[g + 1] - HALF; hi = nx < hi ? nx : hi; }
+            for (int pos = lo + t; pos < hi; pos += TPB) {
+                const int ai = pos & (N - 1);
+                const T x = acc[ai];
+                acc[ai] = (T)0;
+                const int64_t j = (int64_t)pos - t0;
+                if (j >= 0 && j < out_len) {
+                    if (pos >= own_lo && pos < own_hi) out[out_off + j] = (TO)x;
+                    else atomicAdd(&out[out_off + j], (TO)x);
+                }
+            }
+            // the next frame's first write to acc happens after two more barriers: no barrier needed here
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, typename TF, typename TO, int N>
+static cudaError_t launch_synth_t(const SynthArgs& a, cudaStream_t st) {
+    using G = FftGeom<N>;
+    const size_t smem = sizeof(cx<T>) * G::BUF_ELEMS + sizeof(T) * N;
+    auto kern = k_synthesis_lossless<T, TF, TO, N>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G::TPB, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)a.num_sms * per_sm;
+    if (grid > a.n_runs) grid = a.n_runs;
+    if (grid < 1) return cudaSuccess;
+    kern<<<(unsigned)grid, G::TPB, smem, st>>>((const TF*)a.mag, (const TF*)a.real, (const TF*)a.imag, a.pm,
+                                               a.utt_out_off, a.utt_t0, a.runs, a.n_runs, (const cx<T>*)a.tw,
+                                               (TO*)a.out);
+    return cudaGetLastError();
+}
+
+template <typename T, typename TF, typename TO>
+static cudaError_t launch_synth_n(const SynthArgs& a, cudaStream_t st) {
+    switch (a.fft_len) {
+        case 1024: return launch_synth_t<T, TF, TO, 1024>(a, st);
+        case 2048: return launch_synth_t<T, TF, TO, 2048>(a, st);
+        case 4096: return launch_synth_t<T, TF, TO, 4096>(a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <typename T>
+static cudaError_t launch_synth_io(const SynthArgs& a, cudaStream_t st) {
+    if (a.feat_dtype == MPB_F32 && a.out_dtype == MPB_F32) return launch_synth_n<T, float, float>(a, st);
+    if (a.feat_dtype == MPB_F32 && a.out_dtype == MPB_F64) return launch_synth_n<T, float, double>(a, st);
+    if (a.feat_dtype == MPB_F64 && a.out_dtype == MPB_F32) return launch_synth_n<T, double, float>(a, st);
+    return launch_synth_n<T, double, double>(a, st);
+}
+
+cudaError_t launch_synthesis_lossless(const SynthArgs& a, cudaStream_t st) {
+    const size_t esz = a.out_dtype == MPB_F64 ? 8 : 4;
+    cudaError_t e = cudaMemsetAsync(a.out, 0, esz * (size_t)a.n_out, st);
+    if (e != cudaSuccess) return e;
+    return a.compute_dtype == MPB_F64 ? launch_synth_io<double>(a, st) : launch_synth_io<float>(a, st);
+}
+
+}  // namespace mpb

@@ -1,0 +1,93 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol the header declares,
+fails loudly without a GPU, and the host bookkeeping is bit-exact against the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import magphase_oracle as orc
+from conftest import ROOT, have_cuda
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, 'include', 'magphase_b200.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(mpb_[a-z0-9_]+)\s*\(', txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from magphase_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _header_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), n
+    # and the ctypes table binds exactly the declared entry points
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_error_strings():
+    from magphase_b200 import _lib
+    assert b'magphase_b200' in _lib.lib().mpb_version()
+
+
+@pytest.mark.skipif(have_cuda(), reason='only meaningful without a GPU')
+def test_no_cpu_fallback():
+    import magphase_b200.magphase as mp
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        mp.analysis_lossless_from_pm(np.zeros(2000), 48000, np.array([300.0, 700.0]), np.array([0.0, 1.0]))
+
+
+def test_plan_ola_runs_host():
+    from magphase_b200 import _lib
+    rng = np.random.default_rng(0)
+    pm_a = np.cumsum(rng.integers(120, 900, 500)).astype(np.int32)
+    pm_b = np.cumsum(rng.integers(120, 900, 7)).astype(np.int32)
+    pm = np.concatenate((pm_a, pm_b))
+    off = np.array([0, 500, 507], dtype=np.int64)
+    n = ctypes.c_int64()
+    lib = _lib.lib()
+    _lib.check(lib.mpb_plan_ola_runs(_lib.ptr(pm), _lib.ptr(off), 2, 4096, 16, None, 0, ctypes.byref(n)))
+    runs = np.zeros((n.value, 4), dtype=np.int32)
+    _lib.check(lib.mpb_plan_ola_runs(_lib.ptr(pm), _lib.ptr(off), 2, 4096, 16, _lib.ptr(runs), n.value, ctypes.byref(n)))
+    # runs tile the frames of each utterance in order; every run of a multi-run utterance spans >= fft_len
+    assert runs[0, 0] == 0 and np.all(runs[1:, 0] == runs[:-1, 0] + runs[:-1, 1])
+    assert runs[-1, 0] + runs[-1, 1] == 507
+    for first, cnt, utt, flags in runs:
+        assert off[utt] <= first and first + cnt <= off[utt + 1]
+        if flags != 0:
+            assert pm[first + cnt - 1] - pm[first] >= 4096
+        assert bool(flags & 1) == (first > off[utt]) and bool(flags & 2) == (first + cnt < off[utt + 1])
+    assert runs[-1, 2] == 1 and runs[-1, 3] == 0
+    # non-increasing marks are refused
+    bad = pm.copy()
+    bad[10] = bad[9]
+    with pytest.raises(ValueError):
+        _lib.check(lib.mpb_plan_ola_runs(_lib.ptr(bad), _lib.ptr(off), 2, 4096, 16, None, 0, ctypes.byref(n)))
+
+
+def test_host_bookkeeping_bit_exact():
+    import magphase_b200.magphase as mp
+    rng = np.random.default_rng(1)
+    pm = np.cumsum(rng.uniform(100, 700, 300))
+    pm[5] = np.floor(pm[5]) + 0.5      # half-to-even cases
+    pm[6] = np.floor(pm[6]) + 0.5
+    P, s, r = mp.frame_geometry(pm, int(pm[-1]) + 500)
+    P2, s2, r2 = orc.frame_limits(pm, int(pm[-1]) + 500)
+    assert np.array_equal(P, P2) and np.array_equal(s, s2) and np.array_equal(r, r2)
+    voi = (rng.uniform(size=300) > 0.4).astype(float)
+    f0 = mp.shift_to_f0(s, voi, 48000, b_smooth=False)
+    assert np.array_equal(f0, orc.shift_to_f0(s2, voi, 48000))
+    assert np.array_equal(mp.f0_to_shift(f0, 48000), orc.f0_to_shift(f0, 48000))
+    # ola geometry against the oracle's literal slicing
+    v_pm = np.cumsum(mp.f0_to_shift(f0, 48000))
+    pm_int, t0, n_out = mp.ola_geometry(v_pm, 4096)
+    y = orc.ola(np.zeros((300, 4096)), v_pm)
+    assert t0 == 0 and n_out == y.size and np.array_equal(pm_int, v_pm.astype(int))
+    for fs in (16000, 22050, 44100, 48000):
+        assert mp.define_alpha(fs) == orc.define_alpha(fs)
+        assert mp.define_fft_len(fs) == orc.define_fft_len(fs)
+    with pytest.raises(ValueError):
+        mp.define_alpha(8000)
