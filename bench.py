@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the MagPhase analysis+synthesis hot path (BASELINE.json metric: frames/sec at 48 kHz, FFT 4096).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One *step* = one pass of analysis -> synthesis over one batch of synthetic 48 kHz utterances ("synth48k-v1",
+magphase_b200/synth.py).  `value` is device-timed with signals, descriptors and features resident in HBM;
+`e2e` goes through the public host API (NumPy in, NumPy out, H2D/D2H inside the timed region).
+Under torchrun every rank runs its own shard of utterances (weak scaling, no data-path collective: the only
+NCCL traffic is the scattered work list and the final counters).
+"""
+import argparse
+import json
+import multiprocessing
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'analysis+synthesis frames/sec at 48 kHz FFT=4096'
+FS = 48000
+FFT_LEN = 4096
+DISTINCT = 16          # distinct synthetic utterances generated per rank (tiled up to --utts)
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref, py3 translation) or the numpy oracle port
+# --------------------------------------------------------------------------------------------
+_CPU_INPUTS = None
+_CPU_KIND = None
+
+
+def _cpu_impl():
+    """Returns (kind, analysis_fn, synthesis_fn).  The ONLY place bench.py touches oracle/."""
+    odir = os.path.join(ROOT, 'oracle')
+    ref_dir = os.path.join(odir, '_ref')
+    import warnings
+    warnings.simplefilter('ignore')
+    if os.path.exists(os.path.join(ref_dir, 'magphase.py')):
+        for p in (odir, ref_dir):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        import magphase as ref_mp
+
+        def ana(sig, pm, voi):
+            m_fft, v_shift = ref_mp.analysis_with_del_comp_from_pm(sig, FS, pm)
+            return ref_mp.compute_lossless_feats(m_fft, v_shift, voi, FS)
+
+        def syn(mag, real, imag, f0):
+            return ref_mp.synthesis_from_lossless(mag, real, imag, f0, FS)
+        return 'reference', ana, syn
+    if odir not in sys.path:
+        sys.path.insert(0, odir)
+    import magphase_oracle as orc
+
+    def ana(sig, pm, voi):
+        return orc.analysis_lossless_from_pm(sig, FS, pm, voi)[:4]
+
+    def syn(mag, real, imag, f0):
+        return orc.synthesis_from_lossless(mag, real, imag, f0, FS)
+    return 'port', ana, syn
+
+
+def _cpu_worker(i):
+    kind, ana, syn = _cpu_impl()
+    sig, pm, voi = _CPU_INPUTS[i]
+    mag, real, imag, f0 = ana(sig, pm, voi)
+    y = syn(mag, real, imag, f0)
+    return int(mag.shape[0]), float(y[0])
+
+
+def cpu_pass(pool, n_utts):
+    t = time.perf_counter()
+    res = pool.map(_cpu_worker, range(n_utts), chunksize=1)
+    dt = time.perf_counter() - t
+    return sum(r[0] for r in res), dt
+
+
+def make_cpu_inputs(n_utts, dur_s):
+    from magphase_b200.synth import synth_utterance
+    global _CPU_INPUTS
+    base = [synth_utterance(u, fs=FS, dur_s=dur_s) for u in range(min(n_utts, DISTINCT))]
+    _CPU_INPUTS = [base[i % len(base)] for i in range(n_utts)]
+
+
+def run_cpu_arm(n_utts, dur_s, steps, warmup):
+    """K timed steps (after W warm-ups), each a Pool.map over n_utts utterances on all host cores --
+    the reference's own fan-out (src/libutils.py:32-63)."""
+    for k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
+        os.environ[k] = '1'
+    kind = _cpu_impl()[0]
+    make_cpu_inputs(n_utts, dur_s)
+    cores = os.cpu_count() or 1
+    ctx = multiprocessing.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        for _ in range(warmup):
+            cpu_pass(pool, n_utts)
+        frames, secs = 0, 0.0
+        for _ in range(steps):
+            f, dt = cpu_pass(pool, n_utts)
+            frames += f
+            secs += dt
+    return dict(kind=kind, cores=cores, frames_per_step=frames // max(steps, 1), value=frames / secs,
+                ms_per_step=1e3 * secs / max(steps, 1),
+                sample='%d x %.1f s synth48k-v1 utterances per step (analysis_with_del_comp_from_pm + '
+                       'compute_lossless_feats + synthesis_from_lossless), Pool(%d)' % (n_utts, dur_s, cores))
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
+                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower() == 'active':
+                    reasons.add(n)
+        if not sm:
+            return None
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def lpt_assign(sizes, n_bins):
+    """Longest-processing-time greedy assignment of utterances to GPUs."""
+    order = np.argsort(-np.asarray(sizes), kind='stable')
+    load = np.zeros(n_bins)
+    owner = np.zeros(len(sizes), dtype=np.int64)
+    for i in order:
+        b = int(np.argmin(load))
+        owner[i] = b
+        load[b] += sizes[i]
+    return owner
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--utts', type=int, default=128, help='utterances per GPU per step (device-timed arm)')
+    ap.add_argument('--dur', type=float, default=5.0, help='utterance length in seconds')
+    ap.add_argument('--e2e-utts', type=int, default=8, help='utterances per GPU per step (host-API arm)')
+    ap.add_argument('--cpu-utts', type=int, default=32, help='utterances per step of the CPU arm')
+    ap.add_argument('--feat-dtype', default='f32', choices=['f32', 'f64'], help='feature storage in HBM')
+    ap.add_argument('--analysis-compute', default='f64', choices=['f32', 'f64'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    workload = 'lossless chain: analysis_lossless -> synthesis_from_lossless, %d x %.0f s synth48k-v1 utterances per GPU' \
+               % (a.utts, a.dur)
+
+    if a.impl == 'reference':
+        if rank != 0:
+            return
+        r = run_cpu_arm(a.cpu_utts, a.dur, a.steps, a.warmup)
+        print(json.dumps({
+            'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': 'frames/s', 'n_gpus': a.gpus,
+            'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': workload, 'fs': FS, 'fft_len': FFT_LEN},
+            'cpu_baseline': {'value': r['value'], 'unit': 'frames/s', 'cores': r['cores'], 'kind': r['kind'],
+                             'sample': r['sample']},
+            'e2e': {'value': r['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}))
+        return
+
+    # ---- CPU baseline first (fork before CUDA is initialised), rank 0 at N=1 only ----
+    cpu = None
+    if world == 1 and a.gpus == 1 and not a.no_cpu_baseline:
+        cpu = run_cpu_arm(a.cpu_utts, a.dur, 2, 1)
+
+    import torch
+    import torch.distributed as dist
+    from magphase_b200 import _lib
+    from magphase_b200 import magphase as mp
+    from magphase_b200.device import LosslessPlan
+    from magphase_b200.synth import synth_utterance
+
+    os.environ.setdefault('MPB_DEVICE', str(local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    # ---- work list: rank 0 enumerates utterances, LPT-assigns them, NCCL broadcasts the assignment ----
+    n_total = a.utts * world
+    owner = torch.zeros(n_total, dtype=torch.int64, device=dev)
+    if rank == 0:
+        sizes = np.full(n_total, int(round(a.dur * FS)))
+        owner = torch.from_numpy(lpt_assign(sizes, world)).to(dev)
+    if world > 1:
+        dist.broadcast(owner, src=0)
+    my_ids = torch.nonzero(owner == rank).flatten().cpu().numpy()
+
+    base = {}
+    for u in my_ids[:DISTINCT]:
+        base[int(u)] = synth_utterance(int(u), fs=FS, dur_s=a.dur)
+    keys = list(base)
+    utts = [base[keys[i % len(keys)]] for i in range(len(my_ids))]
+
+    F32, F64 = _lib.MPB_F32, _lib.MPB_F64
+    feat_dt = F64 if a.feat_dtype == 'f64' else F32
+    ana_compute = F64 if a.analysis_compute == 'f64' else F32
+    plan = LosslessPlan([u[0].size for u in utts], [u[1] for u in utts], [u[2] for u in utts], FS, FFT_LEN,
+                        device=local_rank)
+    d_sig = torch.from_numpy(np.concatenate([u[0] for u in utts]).astype(np.float32)).to(dev)   # PCM16/32768: exact in f32
+    feats = plan.alloc_features(feat_dt)
+    d_out = plan.alloc_output(F32)
+
+    def step(evs=None):
+        if evs:
+            evs[0].record()
+        plan.analysis(d_sig, feats, compute=ana_compute)
+        if evs:
+            evs[1].record()
+        plan.synthesis(feats, d_out, compute=F32)
+        if evs:
+            evs[2].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    launches0 = _lib.launch_count(local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for k in range(a.steps):
+        step(ev[k])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = _lib.launch_count(local_rank) - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    ana_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / a.steps
+    syn_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / a.steps
+
+    # ---- e2e through the public host API (NumPy in / NumPy out; H2D + D2H inside the timed region) ----
+    e_utts = utts[:max(1, min(a.e2e_utts, len(utts)))]
+    e_sig, e_pm, e_voi = [u[0] for u in e_utts], [u[1] for u in e_utts], [u[2] for u in e_utts]
+
+    def e2e_step():
+        outs = mp.analysis_lossless_batch(e_sig, FS, e_pm, e_voi, fft_len=FFT_LEN)
+        ys = mp.synthesis_from_lossless_batch([o[:4] for o in outs], FS)
+        return sum(o[5].size for o in outs), outs, ys
+    for _ in range(2):
+        e_frames, outs, ys = e2e_step()
+    e_steps = max(2, min(a.steps, 5))
+    barrier()
+    t = time.perf_counter()
+    for _ in range(e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e_secs = time.perf_counter() - t
+    feat_bytes = 3 * 8 * sum(o[0].size for o in outs)
+    h2d = 8 * sum(s.size for s in e_sig) + 16 * e_frames + feat_bytes + 4 * e_frames
+    d2h = feat_bytes + 8 * sum(y.size for y in ys)
+
+    # ---- reduce over ranks: max time, summed frames ----
+    stats = torch.tensor([total_ms, e_secs, ana_ms, syn_ms], dtype=torch.float64, device=dev)
+    counts = torch.tensor([plan.nfrm, e_frames], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    total_ms, e_secs, ana_ms, syn_ms = [float(x) for x in stats.cpu()]
+    frames_all, e_frames_all = [float(x) for x in counts.cpu()]
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    k_ana = dict(name='k_analysis', ms=ana_ms, bytes=plan.analysis_bytes(F32, feat_dt))
+    k_syn = dict(name='k_synthesis_lossless', ms=syn_ms, bytes=plan.synthesis_bytes(feat_dt, F32))
+    for k in (k_ana, k_syn):
+        k['gbs'] = k['bytes'] / (k['ms'] * 1e-3) / 1e9
+        k['frac'] = k['gbs'] / peak
+    dom = k_ana if ana_ms >= syn_ms else k_syn
+    ms_per_step = total_ms / a.steps
+    value = frames_all / (ms_per_step * 1e-3)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64 analysis butterflies / f32 synthesis; %s feature storage' % a.feat_dtype,
+        'data': 'synthetic',
+        'config': {'workload': workload, 'fs': FS, 'fft_len': FFT_LEN, 'frames_per_gpu_per_step': plan.nfrm,
+                   'mean_shift_samples': round(plan.mean_shift, 1), 'l2_note': 'per-step working set %.1f GB >> 126 MB L2'
+                   % ((k_ana['bytes']) / 1e9), 'parallelism': 'utterance-sharded x%d' % world},
+        'e2e': {'value': e_frames_all / (e_secs / e_steps), 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d),
+                'd2h_bytes_per_step': int(d2h), 'utts_per_gpu_per_step': len(e_utts),
+                'api': 'analysis_lossless_batch -> synthesis_from_lossless_batch (float64 NumPy in/out)'},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s',
+                     'frac': dom['frac'], 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': int(dom['bytes']), 'ms_per_launch': dom['ms']},
+        'kernels': [k_ana, k_syn],
+        'clocks': clocks,
+    }
+    if cpu is not None:
+        line['cpu_baseline'] = {'value': cpu['value'], 'unit': 'frames/s', 'cores': cpu['cores'], 'kind': cpu['kind'],
+                                'sample': cpu['sample']}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

@@ -30,7 +30,7 @@ extern "C" {
 #define MPB_OK 0
 #define MPB_ERR_BAD_ARG (-1)      /* NULL pointer, negative size, unknown dtype ...   -> ValueError */
 #define MPB_ERR_FFT_LEN (-2)      /* fft_len not one of 1024 / 2048 / 4096            -> ValueError */
-#define MPB_ERR_FRAME_GEOM (-3)   /* a frame's left length >= fft_len, marks not increasing ...     */
+#define MPB_ERR_FRAME_GEOM (-3)   /* frame outside the signal, marks not increasing ... -> ValueError */
 #define MPB_ERR_CUDA (-4)         /* CUDA runtime failure (message has the cudaError string)        */
 #define MPB_ERR_NO_DEVICE (-5)    /* no usable CUDA device: there is NO CPU fallback                */
 #define MPB_ERR_DIM (-6)          /* mel dimensions exceed the compiled limits                      */

@@ -34,18 +34,22 @@ __device__ __forceinline__ void load_frame(const TS* __restrict__ sig, int64_t n
                                            cx<T>* __restrict__ buf, cx<T>* v, int t) {
     using G = FftGeom<N>;
     T* bufT = reinterpret_cast<T*>(buf);
-    const int q_eff = min(q, N - l - 1);
-    const int total = l + q_eff + 1;
+    // l >= N (pitch period longer than the FFT): the reference keeps the first N samples of the frame and its
+    // hstack((v[l:], v[:l])) rotation degenerates to the identity -> b[k] = sig[c-l+k] * w(l-k, l)
+    const bool whole = l >= N;
+    const int q_eff = whole ? -1 : min(q, N - l - 1);
+    const int total = whole ? N : l + q_eff + 1;
     for (int idx = t; idx < total; idx += G::TPB) {
         int k, dist, side;
-        if (idx < l) { dist = l - idx; side = l; k = N - dist; }
-        else         { dist = idx - l; side = q; k = dist; }
+        if (whole)        { dist = l - idx; side = l; k = idx; }
+        else if (idx < l) { dist = l - idx; side = l; k = N - dist; }
+        else              { dist = idx - l; side = q; k = dist; }
         const int64_t i = c - l + idx;
         const T x = (i >= 0 && i < n_sig) ? (T)sig[i] * side_window<T>(dist, side, kind) : (T)0;
         bufT[2 * G::nphys(k >> 1) + (k & 1)] = x;
     }
     // complete the two complex elements that straddle the edges of the non-zero ranges
-    if (t == 0) {
+    if (t == 0 && !whole) {
         const int ke = q_eff + 1;                 // first zero after the right part
         if ((ke & 1) && ke < N - l) bufT[2 * G::nphys(ke >> 1) + 1] = (T)0;
         const int ks = N - l;                     // first sample of the left part
@@ -55,7 +59,7 @@ __device__ __forceinline__ void load_frame(const TS* __restrict__ sig, int64_t n
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
         const int m = n1 * G::S1 + t;
-        const bool nz = (2 * m <= q_eff) || (2 * m + 1 >= N - l);
+        const bool nz = whole || (2 * m <= q_eff) || (2 * m + 1 >= N - l);
         v[n1] = nz ? buf[G::nphys(m)] : mk<T>((T)0, (T)0);
     }
     __syncthreads();

@@ -164,8 +164,6 @@ static int check_frames_host(const int64_t* centre, const int32_t* left, const i
                              int64_t n_sig, int fft_len) {
     for (int64_t f = 0; f < nfrm; ++f) {
         if (left[f] < 0 || right[f] < 0) return fail(MPB_ERR_FRAME_GEOM, "negative frame side length");
-        if (left[f] >= fft_len)
-            return fail(MPB_ERR_FRAME_GEOM, "a frame's left length (pitch period) is >= fft_len");
         if (centre[f] - left[f] < 0 || centre[f] + right[f] >= n_sig)
             return fail(MPB_ERR_FRAME_GEOM, "frame reaches outside the signal");
     }
