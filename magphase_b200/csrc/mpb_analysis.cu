@@ -23,6 +23,36 @@ __device__ __forceinline__ T side_window(int j, int S, int kind) {
     return (T)(b * b * sqrt(b));
 }
 
+// mag = |X|, re = Re X/|X|, im = Im X/|X|, all 0 where |X| == 0 (src/magphase.py:459-470).  One reciprocal
+// square root instead of hypot + divide: float seed refined by a Newton step in the compute precision.
+__device__ __forceinline__ void normalise(double x, double y, double& mag, double& re, double& im) {
+    const double p = x * x + y * y;
+    if (p > 1e-30 && p < 1e30) {
+        double r = (double)rsqrtf((float)p);
+        r = r * fma(-0.5 * p, r * r, 1.5);
+        r = r * fma(-0.5 * p, r * r, 1.5);
+        mag = p * r; re = x * r; im = y * r;
+    } else if (p == 0.0 && x == 0.0 && y == 0.0) {
+        mag = re = im = 0.0;
+    } else {                                  // out-of-range magnitudes: slow exact path
+        mag = hypot(x, y);
+        re = x / mag; im = y / mag;
+    }
+}
+__device__ __forceinline__ void normalise(float x, float y, float& mag, float& re, float& im) {
+    const float p = x * x + y * y;
+    if (p > 1e-30f && p < 1e30f) {
+        float r = rsqrtf(p);
+        r = r * fmaf(-0.5f * p, r * r, 1.5f);
+        mag = p * r; re = x * r; im = y * r;
+    } else if (x == 0.0f && y == 0.0f) {
+        mag = re = im = 0.0f;
+    } else {
+        mag = hypotf(x, y);
+        re = x / mag; im = y / mag;
+    }
+}
+
 // Stage the windowed, un-delayed frame b[k] into shared memory as the packed complex
 // sequence z[m] = b[2m] + i b[2m+1] (natural padded layout) and pull this thread's 16 points into registers.
 //   b[N-j] = sig[c-j] * w(j, l)   j = 1..l          (left part; has priority, which also reproduces the
@@ -32,7 +62,7 @@ __device__ __forceinline__ T side_window(int j, int S, int kind) {
 template <typename T, typename TS, int N>
 __device__ __forceinline__ void load_frame(const TS* __restrict__ sig, int64_t n_sig, int64_t c, int l, int q, int kind,
                                            cx<T>* __restrict__ buf, cx<T>* v, int t) {
-    using G = FftGeom<N>;
+    using G = FftGeom<T, N>;
     T* bufT = reinterpret_cast<T*>(buf);
     // l >= N (pitch period longer than the FFT): the reference keeps the first N samples of the frame and its
     // hstack((v[l:], v[:l])) rotation degenerates to the identity -> b[k] = sig[c-l+k] * w(l-k, l)
@@ -57,31 +87,37 @@ __device__ __forceinline__ void load_frame(const TS* __restrict__ sig, int64_t n
     }
     __syncthreads();
 #pragma unroll
+    const cx<T>* pk = buf + G::nphys(t);
     for (int n1 = 0; n1 < 16; ++n1) {
         const int m = n1 * G::S1 + t;
         const bool nz = whole || (2 * m <= q_eff) || (2 * m + 1 >= N - l);
-        v[n1] = nz ? buf[G::nphys(m)] : mk<T>((T)0, (T)0);
+        v[n1] = nz ? pk[n1 * (G::S1 + G::S1 / 16)] : mk<T>((T)0, (T)0);
     }
     __syncthreads();
 }
 
 template <typename T, int N> struct KernelCfg {
     // register budget: 128 regs/thread for float64 butterflies, ~85 for float32
-    static constexpr int MINB = (sizeof(T) == 8 ? 512 : 768) / FftGeom<N>::TPB;
+    static constexpr int MINB = (sizeof(T) == 8 ? 512 : 768) / FftGeom<T, N>::TPB;
 };
 
 template <typename T, typename TS, typename TO, int N, int MODE>
-__global__ void __launch_bounds__(FftGeom<N>::TPB, KernelCfg<T, N>::MINB)
+__global__ void __launch_bounds__(FftGeom<T, N>::TPB, KernelCfg<T, N>::MINB)
 k_analysis(const TS* __restrict__ sig, int64_t n_sig,
            const int64_t* __restrict__ centre, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
            const uint8_t* __restrict__ win, int64_t nfrm, const cx<T>* __restrict__ tw,
            TO* __restrict__ out_a, TO* __restrict__ out_b, TO* __restrict__ out_c) {
-    using G = FftGeom<N>;
+    using G = FftGeom<T, N>;
     using T2 = cx<T>;
     constexpr int M = G::M, H = M + 1, TPB = G::TPB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T2* buf = reinterpret_cast<T2*>(smem_raw);
     const int t = threadIdx.x;
+    FftCtx<T> fc;
+    fft_setup<T, N, false>(fc, buf + G::BUF_ELEMS, tw, t);
+    constexpr int STEP = TPB + TPB / 16;          // nphys(k + TPB) - nphys(k)
+    const T2* pk = buf + G::nphys(t);
+    const T2* pmk = buf + G::nphys(M - t);
 
     for (int64_t f = blockIdx.x; f < nfrm; f += gridDim.x) {
         const int64_t c = centre[f];
@@ -90,18 +126,25 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
 
         T2 v[16];
         load_frame<T, TS, N>(sig, n_sig, c, l, q, kind, buf, v, t);
-        fft_m<T, N, false>(v, buf, tw, t);
+        fft_m<T, N, false>(v, buf, fc, t);
 
         // real-FFT split:  X[k] = E + W_N^k O,  X[M-k] = conj(E - W_N^k O),
-        //                  E = (Z[k] + conj Z[M-k]) / 2,  O = -i (Z[k] - conj Z[M-k]) / 2
-        const int64_t row = f * (int64_t)H;
-        for (int k = t; k <= M / 2; k += TPB) {
-            const T2 zk = buf[G::nphys(k)];
-            const T2 zm = cconj(buf[G::nphys((M - k) & (M - 1))]);
-            T2 e = mk<T>((T)0.5 * (zk.x + zm.x), (T)0.5 * (zk.y + zm.y));
-            T2 d = mk<T>((T)0.5 * (zk.x - zm.x), (T)0.5 * (zk.y - zm.y));
-            T2 o = mk<T>(d.y, -d.x);
-            T2 wo = cmul(o, twiddle<T, N, false>(tw, k));
+        //                  E = (Z[k] + conj Z[M-k]) / 2,  O = -i (Z[k] - conj Z[M-k]) / 2,   k = t + j*TPB
+        TO* oa = out_a + f * (int64_t)H * (MODE == MODE_FFT ? 2 : 1);
+        TO* ob = out_b + f * (int64_t)H;
+        TO* oc = out_c + f * (int64_t)H;
+        T2 w = fc.wp;
+        constexpr int NJ = (M / 2) / TPB;
+#pragma unroll 2
+        for (int j = 0; j <= NJ; ++j) {
+            const int k = t + j * TPB;
+            if (j == NJ && t != 0) break;          // k == M/2 is handled by thread 0 only
+            const T2 zk = pk[j * STEP];
+            const T2 zm = cconj(k == 0 ? buf[0] : pmk[-j * STEP]);
+            const T2 e = mk<T>((T)0.5 * (zk.x + zm.x), (T)0.5 * (zk.y + zm.y));
+            const T2 d = mk<T>((T)0.5 * (zk.x - zm.x), (T)0.5 * (zk.y - zm.y));
+            const T2 wo = cmul(mk<T>(d.y, -d.x), w);
+            w = cmul(w, fc.wstep);
             T2 x1 = cadd(e, wo);            // X[k]
             T2 x2 = cconj(csub(e, wo));     // X[M-k]
             if (k == 0) { x1.y = (T)0; x2.y = (T)0; }
@@ -111,15 +154,14 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
                 const int kk = h ? (M - k) : k;
                 if (h && kk == k) break;    // k == M/2 pairs with itself
                 if (MODE == MODE_FFT) {
-                    out_a[2 * (row + kk)] = (TO)x.x;
-                    out_a[2 * (row + kk) + 1] = (TO)x.y;
+                    __stcs(&oa[2 * kk], (TO)x.x);
+                    __stcs(&oa[2 * kk + 1], (TO)x.y);
                 } else {
-                    // mag = |X|; real = Re/|X|, imag = Im/|X| with 0 where |X| == 0   (src/magphase.py:459-470)
-                    const T mag = hypot(x.x, x.y);
-                    const T inv = mag == (T)0 ? (T)0 : (T)1 / mag;
-                    out_a[row + kk] = (TO)mag;
-                    out_b[row + kk] = (TO)(x.x * inv);
-                    out_c[row + kk] = (TO)(x.y * inv);
+                    T mag, re, im;
+                    normalise(x.x, x.y, mag, re, im);
+                    __stcs(&oa[kk], (TO)mag);
+                    __stcs(&ob[kk], (TO)re);
+                    __stcs(&oc[kk], (TO)im);
                 }
             }
         }
@@ -129,8 +171,8 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
 
 template <typename T, typename TS, typename TO, int N, int MODE>
 static cudaError_t launch_analysis_t(const AnalysisArgs& a, cudaStream_t st) {
-    using G = FftGeom<N>;
-    const size_t smem = sizeof(cx<T>) * G::BUF_ELEMS;
+    using G = FftGeom<T, N>;
+    const size_t smem = sizeof(cx<T>) * (G::BUF_ELEMS + G::TW2_ELEMS);
     auto kern = k_analysis<T, TS, TO, N, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -7,14 +7,16 @@
 // pass) and exchanges through ONE padded shared-memory buffer:
 //
 //   pass 1  thread t         reads  z[n1*S1 + t]              (registers <- caller)      S1 = M/16
-//           radix-16 over n1, twiddle W_M^(k1*t), writes A[k1*S1 + t]
-//   pass 2  thread (k1,m2)   reads  A[k1*S1 + m1*R3 + m2], radix-16 over m1,
+//           radix-16 over n1, twiddle W_M^(k1*t), writes A[k1][t]
+//   pass 2  thread (k1,m2)   reads  A[k1][m1*R3 + m2], radix-16 over m1,
 //           twiddle W_S1^(k2*m2), writes back IN PLACE (same 16 slots, no barrier needed)
-//   pass 3  butterfly (k1,k2) reads A[k1*S1 + k2*R3 + m2], radix-R3 over m2 -> Z[k1 + 16*k2 + 256*k3]
+//   pass 3  butterfly (k1,k2) reads A[k1][k2*R3 + m2], radix-R3 over m2 -> Z[k1 + 16*k2 + 256*k3]
 //
-// "A" is stored with one pad element after every R3 (phys = i + i/R3) so that passes 1, 2 and 3 are all
-// bank-conflict free; the natural-order result is stored with one pad after every 16 (phys = k + k/16).
-// All twiddles come from one table tw[j] = exp(-2*pi*i*j/N), j in [0, N/2), in the compute precision.
+// "A" is stored with one pad element after every R3 so that passes 1, 2 and 3 are all bank-conflict free;
+// the natural-order result is stored with one pad after every 16 (phys = k + k/16).
+// Twiddles never touch global memory inside the frame loop: pass 1 uses powers of one per-thread register
+// value (product tree), pass 2 a 16 x R3 table in shared memory, the real-FFT split a per-thread recurrence.
+// They are seeded once per kernel from tw[j] = exp(-2*pi*i*j/N), j in [0, N/2), in the compute precision.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -137,71 +139,114 @@ __device__ __forceinline__ void dftR(T2* v) {
 }
 
 // ---- geometry -------------------------------------------------------------------------------
-template <int N> struct FftGeom {
+template <typename T, int N> struct FftGeom {
     static constexpr int M = N / 2;           // complex points
     static constexpr int TPB = M / 16;        // threads per frame
     static constexpr int S1 = M / 16;         // stride of pass 1
     static constexpr int R3 = M / 256;        // radix of pass 3 (2, 4, 8 or 16)
     static constexpr int NB3 = 16 / R3;       // pass-3 butterflies per thread
-    static constexpr int A_ELEMS = M + M / R3;        // padded exchange layout
-    static constexpr int NAT_ELEMS = M + M / 16 + 1;  // padded natural-order layout (+1: slot for index M)
+    // Exchange layout "A": element (k1, x), x in [0, S1), lives at k1*ROW + x + x/R3 (one pad after every R3
+    // elements).  When the R3 consecutive elements a pass-2 thread group touches are narrower than 128 bytes, the
+    // rows are additionally skewed by R3 elements so that the k1-rows one warp touches in pass 2 tile the 32 banks
+    // instead of starting on the same bank.
+    static constexpr int SKEW = (R3 * 2 * (int)sizeof(T) < 128) ? R3 : 0;
+    static constexpr int ROW = S1 + S1 / R3 + SKEW;
+    static constexpr int A_ELEMS = 16 * ROW;
+    // natural-order layout: index k lives at k + k/16
+    static constexpr int NAT_ELEMS = M + M / 16 + 1;  // (+1: slot for index M)
     static constexpr int BUF_ELEMS = (A_ELEMS > NAT_ELEMS ? A_ELEMS : NAT_ELEMS);
-    __host__ __device__ static constexpr int aphys(int i) { return i + i / R3; }
+    static constexpr int TW2_ELEMS = 16 * R3;         // pass-2 twiddle table W_S1^(k2*m2), [k2][m2]
     __host__ __device__ static constexpr int nphys(int k) { return k + (k >> 4); }
 };
+
+// Per-thread, frame-independent twiddle state (set up once per kernel).
+template <typename T> struct FftCtx {
+    cx<T> w1;            // W_M^t: pass-1 twiddle base; W_M^(k1 t) are its powers
+    cx<T> wp;            // W_N^t: base of the real-FFT split twiddles, advanced by W_N^TPB per step
+    cx<T> wstep;         // W_N^TPB
+    const cx<T>* tw2;    // shared-memory pass-2 table, pre-offset by m2 = t % R3
+};
+
+template <typename T, int N, bool INV>
+__device__ __forceinline__ void fft_setup(FftCtx<T>& c, cx<T>* __restrict__ tw2_smem, const cx<T>* __restrict__ tw, int t) {
+    using G = FftGeom<T, N>;
+    for (int i = t; i < G::TW2_ELEMS; i += G::TPB)
+        tw2_smem[i] = twiddle<T, N, INV>(tw, 32 * (i / G::R3) * (i % G::R3));
+    c.w1 = twiddle<T, N, INV>(tw, 2 * t);
+    c.wp = twiddle<T, N, INV>(tw, t);
+    c.wstep = twiddle<T, N, INV>(tw, G::TPB);
+    c.tw2 = tw2_smem + (t % G::R3);
+    __syncthreads();
+}
+
+template <typename T2> __device__ __forceinline__ T2 csqr(T2 a) {
+    T2 r;
+    r.x = a.x * a.x - a.y * a.y;
+    r.y = (a.x + a.x) * a.y;
+    return r;
+}
 
 // M-point complex FFT of the 16 values per thread in v (v[n1] = z[n1*S1 + t]).
 // On return the natural-order spectrum Z[k] is in buf[nphys(k)], k in [0, M), and the CTA is synchronised.
 // INV=true computes the un-normalised inverse transform (sum with exp(+...)).
 template <typename T, int N, bool INV>
-__device__ __forceinline__ void fft_m(cx<T>* v, cx<T>* __restrict__ buf, const cx<T>* __restrict__ tw, int t) {
-    using G = FftGeom<N>;
+__device__ __forceinline__ void fft_m(cx<T>* v, cx<T>* __restrict__ buf, const FftCtx<T>& c, int t) {
+    using G = FftGeom<T, N>;
     using T2 = cx<T>;
-    constexpr int S1 = G::S1, R3 = G::R3;
+    constexpr int R3 = G::R3, ROW = G::ROW, TPB = G::TPB;
 
-    // pass 1
+    // pass 1: radix-16 over n1, twiddle by powers of w1 = W_M^t (generated by a depth-4 product tree)
     dft16<INV, T>(v);
-#pragma unroll
-    for (int s = 0; s < 16; ++s) {
-        const int k1 = perm16(s);
-        T2 x = v[s];
-        if (k1 != 0) x = cmul(x, twiddle<T, N, INV>(tw, 2 * k1 * t));
-        buf[G::aphys(k1 * S1 + t)] = x;
-    }
-    __syncthreads();
-
-    // pass 2 (in place)
     {
-        const int k1 = t / R3, m2 = t % R3;
-        const int base = k1 * S1 + m2;
-#pragma unroll
-        for (int m1 = 0; m1 < 16; ++m1) v[m1] = buf[G::aphys(base + m1 * R3)];
-        dft16<INV, T>(v);
+        T2 w[16];
+        w[1] = c.w1;
+        w[2] = csqr(w[1]);  w[3] = cmul(w[2], w[1]);   w[4] = csqr(w[2]);    w[5] = cmul(w[4], w[1]);
+        w[6] = csqr(w[3]);  w[7] = cmul(w[4], w[3]);   w[8] = csqr(w[4]);    w[9] = cmul(w[8], w[1]);
+        w[10] = csqr(w[5]); w[11] = cmul(w[8], w[3]);  w[12] = csqr(w[6]);   w[13] = cmul(w[8], w[5]);
+        w[14] = csqr(w[7]); w[15] = cmul(w[8], w[7]);
+        T2* pa = buf + t + t / R3;
 #pragma unroll
         for (int s = 0; s < 16; ++s) {
-            const int k2 = perm16(s);
-            T2 x = v[s];
-            if (k2 != 0) x = cmul(x, twiddle<T, N, INV>(tw, 32 * k2 * m2));
-            buf[G::aphys(base + k2 * R3)] = x;
+            const int k1 = perm16(s);
+            pa[k1 * ROW] = k1 == 0 ? v[s] : cmul(v[s], w[k1]);
         }
     }
     __syncthreads();
 
-    // pass 3: NB3 butterflies of radix R3 per thread; results kept in v[i*R3 + slot]
+    // pass 2 (in place): thread (k1, m2) owns x = m1*R3 + m2  ->  phys = k1*ROW + m2 + m1*(R3+1)
+    {
+        T2* pa = buf + (t / R3) * ROW + (t % R3);
 #pragma unroll
-    for (int i = 0; i < G::NB3; ++i) {
-        const int b = t + i * G::TPB;        // b = k1*16 + k2
+        for (int m1 = 0; m1 < 16; ++m1) v[m1] = pa[m1 * (R3 + 1)];
+        dft16<INV, T>(v);
 #pragma unroll
-        for (int m2 = 0; m2 < R3; ++m2) v[i * R3 + m2] = buf[G::aphys(b * R3 + m2)];
-        dftR<R3, INV, T>(v + i * R3);
+        for (int s = 0; s < 16; ++s) {
+            const int k2 = perm16(s);
+            pa[k2 * (R3 + 1)] = k2 == 0 ? v[s] : cmul(v[s], c.tw2[k2 * R3]);
+        }
     }
     __syncthreads();
+
+    // pass 3: NB3 butterflies of radix R3 per thread, b = k1*16 + k2 = t + i*TPB; results kept in v[i*R3 + slot]
+    {
+        const T2* pa = buf + (t >> 4) * ROW + (t & 15) * (R3 + 1);
 #pragma unroll
-    for (int i = 0; i < G::NB3; ++i) {
-        const int b = t + i * G::TPB;
-        const int k12 = (b >> 4) + 16 * (b & 15);   // k1 + 16*k2
+        for (int i = 0; i < G::NB3; ++i) {
 #pragma unroll
-        for (int s = 0; s < R3; ++s) buf[G::nphys(k12 + 256 * perm<R3>(s))] = v[i * R3 + s];
+            for (int m2 = 0; m2 < R3; ++m2) v[i * R3 + m2] = pa[i * (TPB / 16) * ROW + m2];
+            dftR<R3, INV, T>(v + i * R3);
+        }
+    }
+    __syncthreads();
+    {
+        const int k12 = (t >> 4) + 16 * (t & 15);            // k1 + 16*k2 of butterfly b = t
+        T2* pn = buf + G::nphys(k12);
+#pragma unroll
+        for (int i = 0; i < G::NB3; ++i) {
+            // butterfly t + i*TPB has k1 larger by i*TPB/16  ->  natural index larger by the same amount
+#pragma unroll
+            for (int s = 0; s < R3; ++s) pn[i * (TPB / 16) + 272 * perm<R3>(s)] = v[i * R3 + s];
+        }
     }
     __syncthreads();
 }

@@ -17,27 +17,45 @@
 
 namespace mpb {
 
-template <typename T, typename TF>
-__device__ __forceinline__ cx<T> feat_to_spec(TF mag, TF re, TF im) {
-    // (real + j imag) / |.| with |.| == 0 -> 1, times mag          src/magphase.py:1761-1766
-    const T r = (T)re, i = (T)im;
-    T a = hypot(r, i);
-    if (a == (T)0) a = (T)1;
-    const T s = (T)mag / a;
-    return mk<T>(r * s, i * s);
+// (real + j imag) / |.| with |.| == 0 -> 1, times mag          src/magphase.py:1761-1766
+// |u| == 0 means u == 0, so the quotient is 0 either way: one reciprocal square root does it.
+__device__ __forceinline__ float2 feat_to_spec(float mag, float re, float im, float) {
+    const float p = re * re + im * im;
+    if (p > 1e-30f && p < 1e30f) {
+        float r = rsqrtf(p);
+        r = r * fmaf(-0.5f * p, r * r, 1.5f);
+        const float s = mag * r;
+        return make_float2(re * s, im * s);
+    }
+    if (re == 0.0f && im == 0.0f) return make_float2(0.0f, 0.0f);
+    const float s = mag / hypotf(re, im);
+    return make_float2(re * s, im * s);
+}
+__device__ __forceinline__ double2 feat_to_spec(double mag, double re, double im, double) {
+    const double p = re * re + im * im;
+    if (p > 1e-30 && p < 1e30) {
+        double r = (double)rsqrtf((float)p);
+        r = r * fma(-0.5 * p, r * r, 1.5);
+        r = r * fma(-0.5 * p, r * r, 1.5);
+        const double s = mag * r;
+        return make_double2(re * s, im * s);
+    }
+    if (re == 0.0 && im == 0.0) return make_double2(0.0, 0.0);
+    const double s = mag / hypot(re, im);
+    return make_double2(re * s, im * s);
 }
 
 template <typename T, int N> struct SynthCfg {
-    static constexpr int MINB = (sizeof(T) == 8 ? 384 : 768) / FftGeom<N>::TPB;
+    static constexpr int MINB = (sizeof(T) == 8 ? 384 : 768) / FftGeom<T, N>::TPB;
 };
 
 template <typename T, typename TF, typename TO, int N>
-__global__ void __launch_bounds__(FftGeom<N>::TPB, SynthCfg<T, N>::MINB)
+__global__ void __launch_bounds__(FftGeom<T, N>::TPB, SynthCfg<T, N>::MINB)
 k_synthesis_lossless(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __restrict__ imag,
                      const int32_t* __restrict__ pm, const int64_t* __restrict__ utt_out_off,
                      const int32_t* __restrict__ utt_t0, const OlaRun* __restrict__ runs, int32_t n_runs,
                      const cx<T>* __restrict__ tw, TO* __restrict__ out) {
-    using G = FftGeom<N>;
+    using G = FftGeom<T, N>;
     using T2 = cx<T>;
     constexpr int M = G::M, H = M + 1, TPB = G::TPB, HALF = N / 2;
     constexpr int NP = (M / 2) / TPB;            // spectrum pairs (k, M-k) per thread, k in [0, M/2)
@@ -47,6 +65,11 @@ k_synthesis_lossless(const TF* __restrict__ mag, const TF* __restrict__ real, co
     T* acc = reinterpret_cast<T*>(buf + G::BUF_ELEMS);
     const int t = threadIdx.x;
     const T scale = (T)1 / (T)N;
+    FftCtx<T> fc;
+    fft_setup<T, N, true>(fc, reinterpret_cast<T2*>(acc + N), tw, t);
+    constexpr int STEP = TPB + TPB / 16;          // nphys(k + TPB) - nphys(k)
+    T2* pk = buf + G::nphys(t);
+    T2* pmk = buf + G::nphys(M - t);
 
     for (int r = blockIdx.x; r < n_runs; r += gridDim.x) {
         const OlaRun run = runs[r];
@@ -67,38 +90,42 @@ k_synthesis_lossless(const TF* __restrict__ mag, const TF* __restrict__ real, co
 
             // ---- load the half spectrum, build Z (natural padded layout) ----
             // (two batches of NP/2 pairs: 6*NP/2 independent loads in flight per thread)
+            const TF* ga = mag + row + t;  const TF* gb = real + row + t;  const TF* gc = imag + row + t;
+            const TF* ha = mag + row + M - t;  const TF* hb = real + row + M - t;  const TF* hc = imag + row + M - t;
+            T2 w = fc.wp;                                         // conj(W_N^k), k = t + j*TPB
 #pragma unroll 1
             for (int jb = 0; jb < NP; jb += NPB) {
                 TF fa[NPB][3], fb[NPB][3];
 #pragma unroll
                 for (int j = 0; j < NPB; ++j) {
-                    const int k = t + (jb + j) * TPB;
-                    fa[j][0] = mag[row + k];       fa[j][1] = real[row + k];       fa[j][2] = imag[row + k];
-                    fb[j][0] = mag[row + M - k];   fb[j][1] = real[row + M - k];   fb[j][2] = imag[row + M - k];
+                    const int o = (jb + j) * TPB;
+                    fa[j][0] = __ldcs(ga + o);   fa[j][1] = __ldcs(gb + o);   fa[j][2] = __ldcs(gc + o);
+                    fb[j][0] = __ldcs(ha - o);   fb[j][1] = __ldcs(hb - o);   fb[j][2] = __ldcs(hc - o);
                 }
 #pragma unroll
                 for (int j = 0; j < NPB; ++j) {
                     const int k = t + (jb + j) * TPB;
-                    T2 a = feat_to_spec<T, TF>(fa[j][0], fa[j][1], fa[j][2]);
-                    T2 b = feat_to_spec<T, TF>(fb[j][0], fb[j][1], fb[j][2]);
+                    T2 a = feat_to_spec((T)fa[j][0], (T)fa[j][1], (T)fa[j][2], (T)0);
+                    T2 b = feat_to_spec((T)fb[j][0], (T)fb[j][1], (T)fb[j][2], (T)0);
                     if (k == 0) { a.y = (T)0; b.y = (T)0; }          // Im X[0] = Im X[M] = 0
                     b.y = -b.y;                                       // B = conj(X[M-k])
                     const T2 e = cadd(a, b);
-                    const T2 o = cmul(csub(a, b), twiddle<T, N, true>(tw, k));
-                    buf[G::nphys(k)] = mk<T>(e.x - o.y, e.y + o.x);   // Z[k] = E + iO
-                    if (k != 0) buf[G::nphys(M - k)] = mk<T>(e.x + o.y, -e.y + o.x);   // conj(E) + i conj(O)
+                    const T2 o = cmul(csub(a, b), w);
+                    w = cmul(w, fc.wstep);
+                    pk[(jb + j) * STEP] = mk<T>(e.x - o.y, e.y + o.x);                     // Z[k] = E + iO
+                    if (k != 0) pmk[-(jb + j) * STEP] = mk<T>(e.x + o.y, -e.y + o.x);       // conj(E) + i conj(O)
                 }
             }
             if (t == 0) {                                         // k = M/2 pairs with itself
-                T2 a = feat_to_spec<T, TF>(mag[row + M / 2], real[row + M / 2], imag[row + M / 2]);
+                T2 a = feat_to_spec((T)mag[row + M / 2], (T)real[row + M / 2], (T)imag[row + M / 2], (T)0);
                 buf[G::nphys(M / 2)] = mk<T>((T)2 * a.x, (T)-2 * a.y);
             }
             __syncthreads();
             T2 v[16];
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) v[n1] = buf[G::nphys(n1 * G::S1 + t)];
+            for (int n1 = 0; n1 < 16; ++n1) v[n1] = pk[n1 * (G::S1 + G::S1 / 16)];
             __syncthreads();
-            fft_m<T, N, true>(v, buf, tw, t);
+            fft_m<T, N, true>(v, buf, fc, t);
 
             // ---- overlap-add: sample n of the frame sits at p + (n < N/2 ? n : n - N) ----
             const T* bufT = reinterpret_cast<const T*>(buf);
@@ -132,8 +159,8 @@ k_synthesis_lossless(const TF* __restrict__ mag, const TF* __restrict__ real, co
 
 template <typename T, typename TF, typename TO, int N>
 static cudaError_t launch_synth_t(const SynthArgs& a, cudaStream_t st) {
-    using G = FftGeom<N>;
-    const size_t smem = sizeof(cx<T>) * G::BUF_ELEMS + sizeof(T) * N;
+    using G = FftGeom<T, N>;
+    const size_t smem = sizeof(cx<T>) * (G::BUF_ELEMS + G::TW2_ELEMS) + sizeof(T) * N;
     auto kern = k_synthesis_lossless<T, TF, TO, N>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
