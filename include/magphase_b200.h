@@ -137,6 +137,43 @@ int mpb_synthesis_lossless_host(mpb_ctx* ctx,
                                 int32_t n_utt, int fft_len, int compute_dtype,
                                 double* out, int64_t n_out);
 
+/* ---- low-dimensional compression (analysis side) --------------------------------------------- */
+typedef struct mpb_mel mpb_mel;
+/*
+ * Plan for format_for_modelling (src/magphase.py:2490-2544): la.sp_mel_warp (src/libaudio.py:643-661) of the
+ * three lossless streams, i.e. SPTK `mcep -a alpha -m n-1 -l fft_len -e 1.0E-8 -j 0 -f 0.0 -q {3,2,2}`
+ * (src/libaudio.py:589) followed by la.mcep_to_sp_cosmat(alpha=0) (:605-631), voicing mask and clip.
+ *   alpha_mag, n_mag      warping factor and size of the log-magnitude stream          (0.77, 60 @ 48 kHz)
+ *   alpha_ph, n_ph        warping factor and FULL mel size of the phase streams (get_num_full_mel_coeffs_...)
+ *   phase_dim             phase coefficients kept (first phase_dim of n_ph)
+ *   cos_mag               HOST float64 [n_mag][n_mag]  : cos(j * w~_o), the matrix of mcep_to_sp_cosmat(alpha=0)
+ *   cos_ph                HOST float64 [n_ph][phase_dim]
+ * The warping matrices themselves are built on the device.
+ */
+int mpb_mel_create(mpb_ctx* ctx, int fft_len, double alpha_mag, int n_mag, double alpha_ph, int n_ph,
+                   int phase_dim, const double* cos_mag, const double* cos_ph, mpb_mel** out);
+int mpb_mel_destroy(mpb_mel* plan);
+/* test hook: W^T of stream 0 (mag) / 1 (phase) as HOST float32 [fft_len/2+1][n]                         */
+int mpb_mel_get_warp_matrix(mpb_mel* plan, int which, float* out_host);
+
+/* mag/real/imag: nfrm x (fft_len/2+1) lossless features (feat_dtype); voi[f] != 0 for voiced frames.
+ * out_mag_mel: nfrm x n_mag (log); out_real_mel / out_imag_mel: nfrm x phase_dim, masked and clipped.      */
+int mpb_mel_compress_dev(mpb_mel* plan, void* stream,
+                         const void* mag, const void* real, const void* imag, int feat_dtype,
+                         const uint8_t* voi, int64_t nfrm,
+                         void* out_mag_mel, void* out_real_mel, void* out_imag_mel, int out_dtype);
+int mpb_mel_compress_host(mpb_mel* plan,
+                          const double* mag, const double* real, const double* imag,
+                          const uint8_t* voi, int64_t nfrm,
+                          double* out_mag_mel, double* out_real_mel, double* out_imag_mel);
+/* analysis_compressed (src/magphase.py:2947-2988) minus wav reading / REAPER / lf0: signal + frame geometry
+ * in, low-dimensional features out; the lossless features stay in HBM (float32 scratch).                */
+int mpb_analysis_compressed_host(mpb_mel* plan,
+                                 const double* sig, int64_t n_sig,
+                                 const int64_t* centre, const int32_t* left, const int32_t* right,
+                                 const uint8_t* voi, int64_t nfrm, int compute_dtype,
+                                 double* out_mag_mel, double* out_real_mel, double* out_imag_mel);
+
 #ifdef __cplusplus
 }
 #endif

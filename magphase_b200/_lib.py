@@ -38,6 +38,12 @@ SIGNATURES = {
     'mpb_synthesis_lossless_dev': [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _vp, _i32, _vp, _i32,
                                    C.c_int, C.c_int, _vp, C.c_int, _i64],
     'mpb_synthesis_lossless_host': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, C.c_int, C.c_int, _vp, _i64],
+    'mpb_mel_create': [_vp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, C.POINTER(_vp)],
+    'mpb_mel_destroy': [_vp],
+    'mpb_mel_get_warp_matrix': [_vp, C.c_int, _vp],
+    'mpb_mel_compress_dev': [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _vp, _vp, C.c_int],
+    'mpb_mel_compress_host': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    'mpb_analysis_compressed_host': [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp],
 }
 _RESTYPES = {'mpb_last_error': C.c_char_p, 'mpb_version': C.c_char_p, 'mpb_launch_count': _i64}
 

@@ -53,13 +53,16 @@ def build(force=False, verbose=False):
         return s, r
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(8, len(jobs)))) as ex:
+        failed = []
         for s, r in ex.map(compile_one, jobs):
+            with open(os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + '.ptxas.log'), 'w') as f:
+                f.write(r.stderr)
             if verbose or r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)
             if r.returncode != 0:
-                raise RuntimeError('nvcc failed on %s' % s)
-            with open(os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + '.ptxas.log'), 'w') as f:
-                f.write(r.stderr)
+                failed.append(s)
+        if failed:
+            raise RuntimeError('nvcc failed on %s' % ', '.join(failed))
     objs = [os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + '.o') for s in srcs]
     if force or jobs or _stale(OUT, objs):
         cmd = [_nvcc(), '-shared', '-o', OUT] + objs + ['-lcudart']

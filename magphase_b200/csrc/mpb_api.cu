@@ -8,52 +8,20 @@
 #include <string>
 #include <vector>
 
-#include "mpb_kernels.h"
+#include "mpb_ctx.h"
 
 using namespace mpb;
 
 static thread_local std::string g_err;
 
-static int fail(int code, const std::string& msg) {
+namespace mpb {
+int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
-#define CU(call)                                                                               \
-    do {                                                                                       \
-        cudaError_t _e = (call);                                                               \
-        if (_e != cudaSuccess)                                                                 \
-            return fail(MPB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));     \
-    } while (0)
+}  // namespace mpb
 
-struct DevBuf {   // grow-only device scratch
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t need(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, n);
-        if (e == cudaSuccess) cap = n;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct mpb_ctx {
-    int device = 0;
-    int num_sms = 0;
-    cudaStream_t stream = nullptr;                 // used by the *_host entry points
-    std::map<int, void*> tw32, tw64;               // fft_len -> twiddle table exp(-2 pi i j / N), j < N/2
-    std::mutex mu;                                 // serialises the *_host entry points (shared scratch)
-    std::mutex tw_mu;
-    int64_t launches = 0;
-    DevBuf scratch[12];
-};
-
-static bool fft_len_ok(int n) { return n == 1024 || n == 2048 || n == 4096; }
-static bool dtype_ok(int d) { return d == MPB_F32 || d == MPB_F64; }
-
-static int get_twiddles(mpb_ctx* ctx, int fft_len, int dtype, const void** out) {
+int mpb::get_twiddles(mpb_ctx* ctx, int fft_len, int dtype, const void** out) {
     std::lock_guard<std::mutex> lk(ctx->tw_mu);
     auto& tab = dtype == MPB_F64 ? ctx->tw64 : ctx->tw32;
     auto it = tab.find(fft_len);
@@ -117,8 +85,10 @@ int mpb_destroy(mpb_ctx* ctx) {
 
 int64_t mpb_launch_count(const mpb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+}  // extern "C"
+
 // ---------------------------------------------------------------------------------------------
-static int analysis_common(mpb_ctx* ctx, void* stream, const void* sig, int sig_dtype, int64_t n_sig,
+int mpb::analysis_common(mpb_ctx* ctx, void* stream, const void* sig, int sig_dtype, int64_t n_sig,
                            const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* win,
                            int64_t nfrm, int fft_len, int compute_dtype, void* out_a, void* out_b, void* out_c,
                            int out_dtype, int mode) {
@@ -144,6 +114,8 @@ static int analysis_common(mpb_ctx* ctx, void* stream, const void* sig, int sig_
     return MPB_OK;
 }
 
+extern "C" {
+
 int mpb_analysis_lossless_dev(mpb_ctx* ctx, void* stream, const void* sig, int sig_dtype, int64_t n_sig,
                               const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* win,
                               int64_t nfrm, int fft_len, int compute_dtype, void* out_mag, void* out_real,
@@ -159,8 +131,10 @@ int mpb_frames_fft_dev(mpb_ctx* ctx, void* stream, const void* sig, int sig_dtyp
                            out_fft, nullptr, nullptr, out_dtype, MODE_FFT);
 }
 
+}  // extern "C"
+
 // Host-side geometry check shared by the *_host entry points (the *_dev ones trust the caller's plan).
-static int check_frames_host(const int64_t* centre, const int32_t* left, const int32_t* right, int64_t nfrm,
+int mpb::check_frames_host(const int64_t* centre, const int32_t* left, const int32_t* right, int64_t nfrm,
                              int64_t n_sig, int fft_len) {
     for (int64_t f = 0; f < nfrm; ++f) {
         if (left[f] < 0 || right[f] < 0) return fail(MPB_ERR_FRAME_GEOM, "negative frame side length");
@@ -169,6 +143,8 @@ static int check_frames_host(const int64_t* centre, const int32_t* left, const i
     }
     return MPB_OK;
 }
+
+extern "C" {
 
 static int frames_host(mpb_ctx* ctx, const double* sig, int64_t n_sig, const int64_t* centre, const int32_t* left,
                        const int32_t* right, const uint8_t* win, int64_t nfrm, int fft_len, int compute_dtype,

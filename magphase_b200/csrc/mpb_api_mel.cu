@@ -1,0 +1,193 @@
+// C-ABI: mel-compression plan (format_for_modelling) and the fused host entry point of analysis_compressed.
+#include "mpb_ctx.h"
+
+using namespace mpb;
+
+struct mpb_mel {
+    mpb_ctx* ctx = nullptr;
+    int fft_len = 0, n_mag = 0, n_ph = 0, phase_dim = 0, ld_mag = 0, ld_ph = 0;
+    double alpha_mag = 0, alpha_ph = 0;
+    float* wt_mag = nullptr;     // [kpad][ld_mag]
+    float* wt_ph = nullptr;      // [kpad][ld_ph]
+    double* cos_mag = nullptr;   // [n_mag][n_mag]
+    double* cos_ph = nullptr;    // [n_ph][phase_dim]
+    DevBuf partial, feats[3], small[8];
+    std::mutex mu;
+};
+
+static constexpr int64_t MEL_CHUNK = 16384;   // frames per pass: bounds the K-slice partial-sum scratch (~210 MB)
+
+static int pad64(int n) { return ((n + 63) / 64) * 64; }
+
+extern "C" {
+
+int mpb_mel_create(mpb_ctx* ctx, int fft_len, double alpha_mag, int n_mag, double alpha_ph, int n_ph, int phase_dim,
+                   const double* cos_mag, const double* cos_ph, mpb_mel** out) {
+    if (!ctx || !out || !cos_mag || !cos_ph) return fail(MPB_ERR_BAD_ARG, "NULL argument");
+    if (!fft_len_ok(fft_len)) return fail(MPB_ERR_FFT_LEN, "fft_len must be 1024, 2048 or 4096");
+    if (n_mag < 2 || n_ph < 2 || phase_dim < 1 || phase_dim > n_ph || n_mag > MEL_MAX_COEFFS || n_ph > MEL_MAX_COEFFS)
+        return fail(MPB_ERR_DIM, "mel dimensions must satisfy 2 <= mag_dim, nmel <= 128 and 1 <= phase_dim <= nmel");
+    CU(cudaSetDevice(ctx->device));
+    mpb_mel* m = new mpb_mel();
+    m->ctx = ctx; m->fft_len = fft_len; m->n_mag = n_mag; m->n_ph = n_ph; m->phase_dim = phase_dim;
+    m->alpha_mag = alpha_mag; m->alpha_ph = alpha_ph;
+    m->ld_mag = pad64(n_mag); m->ld_ph = pad64(n_ph);
+    const int H = fft_len / 2 + 1;
+    const size_t kpad = (size_t)((H + MEL_KSLICE - 1) / MEL_KSLICE) * MEL_KSLICE;
+    double* scratch = nullptr;
+    CU(cudaMalloc(&scratch, sizeof(double) * kpad * MEL_MAX_COEFFS));
+    CU(cudaMalloc(&m->wt_mag, sizeof(float) * kpad * m->ld_mag));
+    CU(cudaMalloc(&m->wt_ph, sizeof(float) * kpad * m->ld_ph));
+    CU(cudaMalloc(&m->cos_mag, sizeof(double) * n_mag * n_mag));
+    CU(cudaMalloc(&m->cos_ph, sizeof(double) * n_ph * phase_dim));
+    CU(cudaMemcpy(m->cos_mag, cos_mag, sizeof(double) * n_mag * n_mag, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m->cos_ph, cos_ph, sizeof(double) * n_ph * phase_dim, cudaMemcpyHostToDevice));
+    CU(build_warp_matrix(fft_len, n_mag, alpha_mag, m->wt_mag, scratch, m->ld_mag, ctx->stream));
+    CU(build_warp_matrix(fft_len, n_ph, alpha_ph, m->wt_ph, scratch, m->ld_ph, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(scratch));
+    ctx->launches += 4;
+    *out = m;
+    return MPB_OK;
+}
+
+int mpb_mel_destroy(mpb_mel* m) {
+    if (!m) return MPB_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaFree(m->wt_mag); cudaFree(m->wt_ph); cudaFree(m->cos_mag); cudaFree(m->cos_ph);
+    m->partial.release();
+    for (auto& b : m->feats) b.release();
+    for (auto& b : m->small) b.release();
+    delete m;
+    return MPB_OK;
+}
+
+// debugging / tests: copies W^T (float32, [fft_len/2+1][n]) of stream 0 (mag) or 1 (phase) to the host
+int mpb_mel_get_warp_matrix(mpb_mel* m, int which, float* out_host) {
+    if (!m || !out_host) return fail(MPB_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(m->ctx->device));
+    const int H = m->fft_len / 2 + 1;
+    const int n = which == 0 ? m->n_mag : m->n_ph, ld = which == 0 ? m->ld_mag : m->ld_ph;
+    const float* src = which == 0 ? m->wt_mag : m->wt_ph;
+    CU(cudaMemcpy2D(out_host, sizeof(float) * n, src, sizeof(float) * ld, sizeof(float) * n, H, cudaMemcpyDeviceToHost));
+    return MPB_OK;
+}
+
+int mpb_mel_compress_dev(mpb_mel* m, void* stream, const void* mag, const void* real, const void* imag, int feat_dtype,
+                         const uint8_t* voi, int64_t nfrm, void* out_mag_mel, void* out_real_mel, void* out_imag_mel,
+                         int out_dtype) {
+    if (!m) return fail(MPB_ERR_BAD_ARG, "plan is NULL");
+    if (!dtype_ok(feat_dtype) || !dtype_ok(out_dtype)) return fail(MPB_ERR_BAD_ARG, "unknown dtype");
+    if (nfrm < 0) return fail(MPB_ERR_BAD_ARG, "negative size");
+    if (nfrm == 0) return MPB_OK;
+    if (!mag || !real || !imag || !voi || !out_mag_mel || !out_real_mel || !out_imag_mel)
+        return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(m->ctx->device));
+    std::lock_guard<std::mutex> lk(m->mu);
+    const int H = m->fft_len / 2 + 1;
+    const int n_slices = (H + MEL_KSLICE - 1) / MEL_KSLICE;
+    const int ncp = m->ld_mag > m->ld_ph ? m->ld_mag : m->ld_ph;
+    const int64_t chunk = nfrm < MEL_CHUNK ? nfrm : MEL_CHUNK;
+    CU(m->partial.need(sizeof(float) * 3 * (size_t)n_slices * (size_t)chunk * ncp));
+    const size_t fes = feat_dtype == MPB_F64 ? 8 : 4, oes = out_dtype == MPB_F64 ? 8 : 4;
+    for (int64_t f0 = 0; f0 < nfrm; f0 += chunk) {
+        const int64_t n = nfrm - f0 < chunk ? nfrm - f0 : chunk;
+        MelArgs a;
+        a.mag = (const char*)mag + fes * f0 * H; a.real = (const char*)real + fes * f0 * H;
+        a.imag = (const char*)imag + fes * f0 * H; a.feat_dtype = feat_dtype;
+        a.voi = voi + f0; a.nfrm = n; a.fft_len = m->fft_len;
+        a.wt_mag = m->wt_mag; a.ld_mag = m->ld_mag; a.wt_ph = m->wt_ph; a.ld_ph = m->ld_ph;
+        a.cos_mag = m->cos_mag; a.n_mag = m->n_mag; a.cos_ph = m->cos_ph; a.n_ph = m->n_ph; a.phase_dim = m->phase_dim;
+        a.partial = (float*)m->partial.p; a.ncp_max = ncp;
+        a.out_mag = (char*)out_mag_mel + oes * f0 * m->n_mag;
+        a.out_real = (char*)out_real_mel + oes * f0 * m->phase_dim;
+        a.out_imag = (char*)out_imag_mel + oes * f0 * m->phase_dim;
+        a.out_dtype = out_dtype;
+        CU(launch_mel_compress(a, (cudaStream_t)stream));
+        m->ctx->launches += 2;
+    }
+    return MPB_OK;
+}
+
+int mpb_mel_compress_host(mpb_mel* m, const double* mag, const double* real, const double* imag, const uint8_t* voi,
+                          int64_t nfrm, double* out_mag_mel, double* out_real_mel, double* out_imag_mel) {
+    if (!m) return fail(MPB_ERR_BAD_ARG, "plan is NULL");
+    if (nfrm == 0) return MPB_OK;
+    if (!mag || !real || !imag || !voi || !out_mag_mel || !out_real_mel || !out_imag_mel)
+        return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    mpb_ctx* ctx = m->ctx;
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int H = m->fft_len / 2 + 1;
+    const size_t fsz = sizeof(double) * (size_t)nfrm * H;
+    cudaStream_t st = ctx->stream;
+    for (int i = 0; i < 3; ++i) CU(m->feats[i].need(fsz));
+    CU(m->small[0].need((size_t)nfrm));
+    CU(m->small[1].need(sizeof(double) * nfrm * m->n_mag));
+    CU(m->small[2].need(sizeof(double) * nfrm * m->phase_dim));
+    CU(m->small[3].need(sizeof(double) * nfrm * m->phase_dim));
+    CU(cudaMemcpyAsync(m->feats[0].p, mag, fsz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->feats[1].p, real, fsz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->feats[2].p, imag, fsz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->small[0].p, voi, (size_t)nfrm, cudaMemcpyHostToDevice, st));
+    int rc = mpb_mel_compress_dev(m, st, m->feats[0].p, m->feats[1].p, m->feats[2].p, MPB_F64, (const uint8_t*)m->small[0].p,
+                                  nfrm, m->small[1].p, m->small[2].p, m->small[3].p, MPB_F64);
+    if (rc != MPB_OK) return rc;
+    CU(cudaMemcpyAsync(out_mag_mel, m->small[1].p, sizeof(double) * nfrm * m->n_mag, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_real_mel, m->small[2].p, sizeof(double) * nfrm * m->phase_dim, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_imag_mel, m->small[3].p, sizeof(double) * nfrm * m->phase_dim, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MPB_OK;
+}
+
+// analysis_lossless + format_for_modelling fused on the device: host signal in, low-dimensional features out.
+// The lossless features only ever exist as a float32 scratch in HBM (frame-chunked).
+int mpb_analysis_compressed_host(mpb_mel* m, const double* sig, int64_t n_sig, const int64_t* centre,
+                                 const int32_t* left, const int32_t* right, const uint8_t* voi, int64_t nfrm,
+                                 int compute_dtype, double* out_mag_mel, double* out_real_mel, double* out_imag_mel) {
+    if (!m) return fail(MPB_ERR_BAD_ARG, "plan is NULL");
+    if (nfrm == 0) return MPB_OK;
+    if (!sig || !centre || !left || !right || !voi || !out_mag_mel || !out_real_mel || !out_imag_mel)
+        return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    mpb_ctx* ctx = m->ctx;
+    int rc = check_frames_host(centre, left, right, nfrm, n_sig, m->fft_len);
+    if (rc != MPB_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int H = m->fft_len / 2 + 1;
+    cudaStream_t st = ctx->stream;
+    const int64_t chunk = nfrm < MEL_CHUNK ? nfrm : MEL_CHUNK;
+    for (int i = 0; i < 3; ++i) CU(m->feats[i].need(sizeof(float) * (size_t)chunk * H));
+    CU(m->small[0].need((size_t)nfrm));
+    CU(m->small[1].need(sizeof(double) * nfrm * m->n_mag));
+    CU(m->small[2].need(sizeof(double) * nfrm * m->phase_dim));
+    CU(m->small[3].need(sizeof(double) * nfrm * m->phase_dim));
+    CU(m->small[4].need(sizeof(double) * n_sig));
+    CU(m->small[5].need(sizeof(int64_t) * nfrm));
+    CU(m->small[6].need(sizeof(int32_t) * nfrm));
+    CU(m->small[7].need(sizeof(int32_t) * nfrm));
+    CU(cudaMemcpyAsync(m->small[4].p, sig, sizeof(double) * n_sig, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->small[5].p, centre, sizeof(int64_t) * nfrm, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->small[6].p, left, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->small[7].p, right, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->small[0].p, voi, (size_t)nfrm, cudaMemcpyHostToDevice, st));
+    for (int64_t f0 = 0; f0 < nfrm; f0 += chunk) {
+        const int64_t n = nfrm - f0 < chunk ? nfrm - f0 : chunk;
+        rc = analysis_common(ctx, st, m->small[4].p, MPB_F64, n_sig, (const int64_t*)m->small[5].p + f0,
+                             (const int32_t*)m->small[6].p + f0, (const int32_t*)m->small[7].p + f0, nullptr, n,
+                             m->fft_len, compute_dtype, m->feats[0].p, m->feats[1].p, m->feats[2].p, MPB_F32, MODE_FEATS);
+        if (rc != MPB_OK) return rc;
+        rc = mpb_mel_compress_dev(m, st, m->feats[0].p, m->feats[1].p, m->feats[2].p, MPB_F32,
+                                  (const uint8_t*)m->small[0].p + f0, n, (double*)m->small[1].p + f0 * m->n_mag,
+                                  (double*)m->small[2].p + f0 * m->phase_dim, (double*)m->small[3].p + f0 * m->phase_dim,
+                                  MPB_F64);
+        if (rc != MPB_OK) return rc;
+    }
+    CU(cudaMemcpyAsync(out_mag_mel, m->small[1].p, sizeof(double) * nfrm * m->n_mag, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_real_mel, m->small[2].p, sizeof(double) * nfrm * m->phase_dim, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_imag_mel, m->small[3].p, sizeof(double) * nfrm * m->phase_dim, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// Shared internals of the C-ABI translation units: context, scratch buffers, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "mpb_kernels.h"
+
+namespace mpb {
+int fail(int code, const std::string& msg);
+}
+using mpb::fail;
+
+#define CU(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return fail(MPB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+struct DevBuf {   // grow-only device scratch
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t need(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct mpb_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;                 // used by the *_host entry points
+    std::map<int, void*> tw32, tw64;               // fft_len -> twiddle table exp(-2 pi i j / N), j < N/2
+    std::mutex mu;                                 // serialises the *_host entry points (shared scratch)
+    std::mutex tw_mu;
+    int64_t launches = 0;
+    DevBuf scratch[16];
+};
+
+namespace mpb {
+inline bool fft_len_ok(int n) { return n == 1024 || n == 2048 || n == 4096; }
+inline bool dtype_ok(int d) { return d == MPB_F32 || d == MPB_F64; }
+int get_twiddles(mpb_ctx* ctx, int fft_len, int dtype, const void** out);
+int analysis_common(mpb_ctx* ctx, void* stream, const void* sig, int sig_dtype, int64_t n_sig,
+                    const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* win,
+                    int64_t nfrm, int fft_len, int compute_dtype, void* out_a, void* out_b, void* out_c,
+                    int out_dtype, int mode);
+int check_frames_host(const int64_t* centre, const int32_t* left, const int32_t* right, int64_t nfrm,
+                      int64_t n_sig, int fft_len);
+}

@@ -40,4 +40,20 @@ struct SynthArgs {
 };
 cudaError_t launch_synthesis_lossless(const SynthArgs& a, cudaStream_t st);
 
+// ---- mel compression (mpb_mel.cu) ----
+constexpr int MEL_KSLICE = 128;        // spectral bins per K-slice of the tile product
+constexpr int MEL_MAX_COEFFS = 128;    // largest supported mag_dim / nmel
+
+struct MelArgs {
+    const void* mag; const void* real; const void* imag; int feat_dtype;   // nfrm x (fft_len/2+1)
+    const uint8_t* voi; int64_t nfrm; int fft_len;
+    const float* wt_mag; int ld_mag; const float* wt_ph; int ld_ph;         // W^T, [kpad][ld] float32
+    const double* cos_mag; int n_mag; const double* cos_ph; int n_ph; int phase_dim;
+    float* partial; int ncp_max;                                            // [3][slices][nfrm][ncp_max]
+    void* out_mag; void* out_real; void* out_imag; int out_dtype;
+};
+cudaError_t build_warp_matrix(int fft_len, int n_out, double alpha, float* wt32, double* scratch64, int ld,
+                              cudaStream_t st);
+cudaError_t launch_mel_compress(const MelArgs& a, cudaStream_t st);
+
 }  // namespace mpb

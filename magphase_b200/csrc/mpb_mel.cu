@@ -1,0 +1,229 @@
+// Low-dimensional mel compression of the lossless features (analysis side of format_for_modelling).
+//
+// Reference: format_for_modelling src/magphase.py:2490-2544 -> la.sp_mel_warp src/libaudio.py:643-661 ->
+// la.sp_to_mcep :575-601 (SPTK `mcep -a alpha -m n-1 -l N -e 1.0E-8 -j 0 -f 0.0 -q in_type`, float32 file I/O)
+// -> la.mcep_to_sp_cosmat(alpha=0) :605-631.
+//
+// With `-j 0` SPTK's output is its initial estimate, which is LINEAR in the log periodogram:
+//     mc = freqt_alpha( halve_ends( irfft( log(amp(x)^2 + 1e-8) ) ) )  =  W . logp,    W = A_alpha . C
+// (C: the cosine IFFT matrix with the halved c[0], c[N/2]; A_alpha: SPTK freqt as a matrix).  So the hot
+// loop is  MC[F x n] = log-periodogram[F x H] . W^T[H x n]  per stream (mag: in_type 3, real/imag: in_type 2)
+// -- a tall-skinny product with K = H = N/2+1.  There is no cepstrum / IFFT left in the path.
+//   k_build_warp : builds W^T (H x n, float64 -> float32) on the GPU: one thread per spectral bin runs the
+//                  freqt recursion on that bin's cosine column.
+//   k_mel_gemm   : CUDA-core FMA tile kernel, split over K in slices of 128 bins; float32 products and
+//                  accumulation inside a slice (the operands are float32 data anyway), partial sums to HBM.
+//   k_mel_finish : float64 sum over the K-slices -> float32 rounding (SPTK's float32 output file) ->
+//                  cosine matrix in float64 -> voicing mask / clip / log.
+#include "mpb_kernels.h"
+
+namespace mpb {
+
+// ---- W^T builder ------------------------------------------------------------------------------
+// thread k: sequence c_k[n] = C[n][k] = wk/N * cos(2 pi k n / N) * (n == 0 || n == N/2 ? 0.5 : 1), n = 0..H-1
+// pushed through the all-pass recursion (SPTK freqt: inputs consumed from n = H-1 down to 0).
+__global__ void k_build_warp(int fft_len, int n_out, double alpha, double* __restrict__ wt64, int ld) {
+    const int H = fft_len / 2 + 1;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= H) return;
+    double g[MEL_MAX_COEFFS], d[MEL_MAX_COEFFS];
+    for (int j = 0; j < n_out; ++j) g[j] = 0.0;
+    const double wk = (k == 0 || k == H - 1) ? 1.0 : 2.0;
+    const double b = 1.0 - alpha * alpha;
+    for (int n = H - 1; n >= 0; --n) {
+        const int r = (int)(((long long)k * n) % fft_len);
+        double c = wk / (double)fft_len * cospi(2.0 * (double)r / (double)fft_len);
+        if (n == 0 || n == H - 1) c *= 0.5;
+        for (int j = 0; j < n_out; ++j) d[j] = g[j];
+        g[0] = c + alpha * d[0];
+        if (n_out > 1) g[1] = b * d[0] + alpha * d[1];
+        for (int j = 2; j < n_out; ++j) g[j] = d[j - 1] + alpha * (d[j] - g[j - 1]);
+    }
+    for (int j = 0; j < n_out; ++j) wt64[(size_t)k * ld + j] = g[j];
+}
+
+__global__ void k_f64_to_f32(const double* __restrict__ a, float* __restrict__ b, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = (float)a[i];
+}
+
+cudaError_t build_warp_matrix(int fft_len, int n_out, double alpha, float* wt32, double* scratch64, int ld,
+                              cudaStream_t st) {
+    const int H = fft_len / 2 + 1;
+    const int kpad = ((H + MEL_KSLICE - 1) / MEL_KSLICE) * MEL_KSLICE;
+    cudaError_t e = cudaMemsetAsync(scratch64, 0, sizeof(double) * (size_t)kpad * ld, st);
+    if (e != cudaSuccess) return e;
+    k_build_warp<<<(H + 63) / 64, 64, 0, st>>>(fft_len, n_out, alpha, scratch64, ld);
+    const size_t n = (size_t)kpad * ld;
+    k_f64_to_f32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scratch64, wt32, n);
+    return cudaGetLastError();
+}
+
+// ---- tile product -----------------------------------------------------------------------------
+// log periodogram of one feature value as SPTK sees it (float32 input file):
+//   in_type 3 (|X|):   log(x^2 + 1e-8)            in_type 2 (ln|X|):  log(exp(2x) + 1e-8)
+template <int IN_TYPE>
+__device__ __forceinline__ float log_periodogram(float x) {
+    if (IN_TYPE == 3) return logf(fmaf(x, x, 1.0e-8f));
+    // 2x + log1p(1e-8 * exp(-2x)): exact to float precision for the |x| <= ~1 phase features, safe elsewhere
+    const float e = 1.0e-8f * expf(-2.0f * x);
+    return (e < 1.0e-3f) ? fmaf(2.0f, x, e - 0.5f * e * e) : logf(expf(2.0f * x) + 1.0e-8f);
+}
+
+constexpr int GEMM_FT = 128;          // frames per CTA tile
+constexpr int GEMM_CT = 64;           // coefficients per CTA tile
+constexpr int GEMM_LDL = GEMM_FT + 4; // pitch of the transposed log-periodogram tile (floats)
+
+// grid: (frame tiles, K slices * coefficient tiles, 3 streams)
+template <typename TF>
+__global__ void __launch_bounds__(128, 2)
+k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __restrict__ imag, int64_t nfrm, int H,
+           const float* __restrict__ wt_mag, int ld_mag, const float* __restrict__ wt_ph, int ld_ph,
+           float* __restrict__ partial, int n_slices, int ncp_max) {
+    extern __shared__ __align__(16) float smem_f[];
+    float* Ls = smem_f;                                  // [MEL_KSLICE][GEMM_LDL]
+    float* Bs = smem_f + MEL_KSLICE * GEMM_LDL;          // [MEL_KSLICE][GEMM_CT]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int stream = blockIdx.z;
+    const int slice = blockIdx.y % n_slices, ctile = blockIdx.y / n_slices;
+    const TF* __restrict__ src = stream == 0 ? mag : (stream == 1 ? real : imag);
+    const float* __restrict__ wt = stream == 0 ? wt_mag : wt_ph;
+    const int ld = stream == 0 ? ld_mag : ld_ph;
+    if (ctile * GEMM_CT >= ld) return;
+    const int64_t f0 = (int64_t)blockIdx.x * GEMM_FT;
+    const int k0 = slice * MEL_KSLICE;
+
+    // ---- stage the W^T slice: rows k0..k0+127, columns ctile*64..+63 (zero padded on the host side) ----
+    for (int i = tid; i < MEL_KSLICE * (GEMM_CT / 4); i += 128) {
+        const int kk = i / (GEMM_CT / 4), c4 = i % (GEMM_CT / 4);
+        reinterpret_cast<float4*>(Bs)[i] =
+            __ldg(reinterpret_cast<const float4*>(wt + (size_t)(k0 + kk) * ld + ctile * GEMM_CT) + c4);
+    }
+    // ---- stage the log-periodogram tile transposed: Ls[kk][f]; a warp takes 4 frames x 32 bins per step ----
+    for (int fb = warp * 4; fb < GEMM_FT; fb += 16) {
+#pragma unroll
+        for (int kc = 0; kc < MEL_KSLICE; kc += 32) {
+            const int k = k0 + kc + lane;
+            float4 v;
+            float* pv = &v.x;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int64_t f = f0 + fb + r;
+                float x = 0.0f;
+                if (f < nfrm && k < H) {
+                    const float raw = (float)__ldcs(src + f * (int64_t)H + k);
+                    x = stream == 0 ? log_periodogram<3>(raw) : log_periodogram<2>(raw);
+                }
+                pv[r] = x;
+            }
+            *reinterpret_cast<float4*>(Ls + (kc + lane) * GEMM_LDL + fb) = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- 8 x 8 outputs per thread: frames {tf*4.., 64+tf*4..}, coefficients {tc*4.., 32+tc*4..} ----
+    const int tf = tid >> 3, tc = tid & 7;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    const float* pl = Ls + tf * 4;
+    const float* pb = Bs + tc * 4;
+#pragma unroll 4
+    for (int kk = 0; kk < MEL_KSLICE; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(pl + kk * GEMM_LDL);
+        const float4 a1 = *reinterpret_cast<const float4*>(pl + kk * GEMM_LDL + 64);
+        const float4 b0 = *reinterpret_cast<const float4*>(pb + kk * GEMM_CT);
+        const float4 b1 = *reinterpret_cast<const float4*>(pb + kk * GEMM_CT + 32);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    // ---- partial[stream][slice][f][ncp_max] ----
+    float* out = partial + ((size_t)stream * n_slices + slice) * (size_t)nfrm * ncp_max;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t f = f0 + (i < 4 ? tf * 4 + i : 64 + tf * 4 + (i - 4));
+        if (f >= nfrm) continue;
+        float* po = out + (size_t)f * ncp_max + ctile * GEMM_CT;
+        *reinterpret_cast<float4*>(po + tc * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(po + 32 + tc * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+}
+
+// ---- finish -------------------------------------------------------------------------------------
+// one warp per (frame, stream): mc[j] = float32(sum over slices), out[o] = sum_j mc[j] cos_tab[j][o]
+template <typename TO>
+__global__ void __launch_bounds__(128)
+k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64_t nfrm,
+             const double* __restrict__ cos_mag, int n_mag, const double* __restrict__ cos_ph, int n_ph, int phase_dim,
+             const uint8_t* __restrict__ voi, TO* __restrict__ out_mag, TO* __restrict__ out_real, TO* __restrict__ out_imag) {
+    __shared__ double mc[4][MEL_MAX_COEFFS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t f = (int64_t)blockIdx.x * 4 + warp;
+    const int stream = blockIdx.y;
+    if (f >= nfrm) return;
+    const int n_in = stream == 0 ? n_mag : n_ph;
+    const int n_out = stream == 0 ? n_mag : phase_dim;
+    const double* __restrict__ ct = stream == 0 ? cos_mag : cos_ph;      // [n_in][n_out]
+    for (int j = lane; j < n_in; j += 32) {
+        double s = 0.0;
+        for (int sl = 0; sl < n_slices; ++sl)
+            s += (double)partial[(((size_t)stream * n_slices + sl) * (size_t)nfrm + f) * ncp_max + j];
+        mc[warp][j] = (double)(float)s;                                    // SPTK writes float32 (src/libaudio.py:593)
+    }
+    __syncwarp();
+    const bool voiced = voi[f] != 0;
+    TO* __restrict__ dst = (stream == 0 ? out_mag : (stream == 1 ? out_real : out_imag)) + f * (int64_t)n_out;
+    for (int o = lane; o < n_out; o += 32) {
+        double s = 0.0;
+        for (int j = 0; j < n_in; ++j) s = fma(mc[warp][j], ct[j * n_out + o], s);
+        if (stream == 0) {
+            // m_mag_mel = exp(s); la.log(m_mag_mel) = s up to 1 ulp, except the protected -inf (src/libaudio.py:241-248)
+            if (s < -745.0) s = -1.0e10;
+        } else {
+            s = voiced ? fmin(fmax(s, -1.0), 1.0) : 0.0;                   // mask, clip (src/magphase.py:2527-2542)
+        }
+        dst[o] = (TO)s;
+    }
+}
+
+cudaError_t launch_mel_compress(const MelArgs& a, cudaStream_t st) {
+    const int H = a.fft_len / 2 + 1;
+    const int n_slices = (H + MEL_KSLICE - 1) / MEL_KSLICE;
+    const int ctiles = (a.ncp_max + GEMM_CT - 1) / GEMM_CT;
+    const size_t smem = sizeof(float) * (MEL_KSLICE * GEMM_LDL + MEL_KSLICE * GEMM_CT);
+    dim3 grid((unsigned)((a.nfrm + GEMM_FT - 1) / GEMM_FT), (unsigned)(n_slices * ctiles), 3);
+    cudaError_t e;
+    if (a.feat_dtype == MPB_F64) {
+        e = cudaFuncSetAttribute(k_mel_gemm<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_mel_gemm<double><<<grid, 128, smem, st>>>((const double*)a.mag, (const double*)a.real, (const double*)a.imag,
+                                                    a.nfrm, H, a.wt_mag, a.ld_mag, a.wt_ph, a.ld_ph, a.partial, n_slices,
+                                                    a.ncp_max);
+    } else {
+        e = cudaFuncSetAttribute(k_mel_gemm<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_mel_gemm<float><<<grid, 128, smem, st>>>((const float*)a.mag, (const float*)a.real, (const float*)a.imag,
+                                                   a.nfrm, H, a.wt_mag, a.ld_mag, a.wt_ph, a.ld_ph, a.partial, n_slices,
+                                                   a.ncp_max);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dim3 g2((unsigned)((a.nfrm + 3) / 4), 3);
+    if (a.out_dtype == MPB_F64)
+        k_mel_finish<double><<<g2, 128, 0, st>>>(a.partial, n_slices, a.ncp_max, a.nfrm, a.cos_mag, a.n_mag, a.cos_ph,
+                                                 a.n_ph, a.phase_dim, a.voi, (double*)a.out_mag, (double*)a.out_real,
+                                                 (double*)a.out_imag);
+    else
+        k_mel_finish<float><<<g2, 128, 0, st>>>(a.partial, n_slices, a.ncp_max, a.nfrm, a.cos_mag, a.n_mag, a.cos_ph,
+                                                a.n_ph, a.phase_dim, a.voi, (float*)a.out_mag, (float*)a.out_real,
+                                                (float*)a.out_imag);
+    return cudaGetLastError();
+}
+
+}  // namespace mpb

@@ -317,3 +317,207 @@ def synthesis_from_lossless_batch(l_feats, fs):
         l_t0.append(t0)
         l_n.append(n_out)
     return _synthesis_lossless_call(l_feats, l_pm, l_t0, l_n, fft_len)
+
+
+# ----------------------------------------------------------------------------------------------
+# low-dimensional compression (analysis side)
+# ----------------------------------------------------------------------------------------------
+def warped_axis(alpha, nbins):
+    """All-pass warped frequency axis on [0, pi] (src/libaudio.py:611-613, :711-718)."""
+    w = np.linspace(0, np.pi, num=nbins)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        wt = np.arctan((1 - alpha ** 2) * np.sin(w) / ((1 + alpha ** 2) * np.cos(w) - 2 * alpha))
+    wt[wt < 0] += np.pi
+    return wt
+
+
+def build_mel_curve(alpha, nbins, amp=np.pi):
+    """src/libaudio.py:711-718"""
+    return warped_axis(alpha, nbins) * (amp / np.pi)
+
+
+def get_num_full_mel_coeffs_from_num_phase_coeffs(freq_hz, phase_dim, alpha, fs):
+    """src/magphase.py:2479-2487"""
+    w = 2 * np.pi * freq_hz / float(fs)
+    m = np.arctan((1 - alpha ** 2) * np.sin(w) / ((1 + alpha ** 2) * np.cos(w) - 2 * alpha))
+    if m < 0:
+        m += np.pi
+    return int(round_to_int(1 + (np.pi * (phase_dim - 1) / float(m))))
+
+
+def medfilt3(v):
+    """scipy.signal.medfilt(v) (kernel 3, zero padded) without scipy: the median of three picks an element, so
+    this is bit-exact.  Used by format_for_modelling (src/magphase.py:2500)."""
+    v = np.asarray(v, dtype=np.float64)
+    p = np.concatenate(([0.0], v, [0.0]))
+    return np.median(np.stack((p[:-2], p[1:-1], p[2:])), axis=0)
+
+
+class _MelPlan:
+    _cache = {}
+
+    def __init__(self, fft_len, alpha_mag, mag_dim, alpha_ph, nmel, phase_dim):
+        self.key = (fft_len, alpha_mag, mag_dim, alpha_ph, nmel, phase_dim)
+        self.mag_dim, self.nmel, self.phase_dim, self.fft_len = mag_dim, nmel, phase_dim, fft_len
+        # cosine matrices of la.mcep_to_sp_cosmat(alpha=0.0)  (src/libaudio.py:605-631)
+        cos_mag = np.ascontiguousarray(np.cos(np.arange(mag_dim)[:, None] * warped_axis(0.0, mag_dim)[None, :]))
+        cos_ph = np.ascontiguousarray(
+            np.cos(np.arange(nmel)[:, None] * warped_axis(0.0, nmel)[None, :])[:, :phase_dim])
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mpb_mel_create(_lib.ctx(), fft_len, float(alpha_mag), mag_dim, float(alpha_ph), nmel,
+                                             phase_dim, _lib.ptr(cos_mag), _lib.ptr(cos_ph), C.byref(h)))
+        self.handle = h
+
+    @classmethod
+    def get(cls, fs, fft_len, mag_dim, phase_dim, alpha_phase):
+        alpha = define_alpha(fs)
+        crsf_cf, _ = define_crossfade_params(fs)
+        if alpha_phase is None:
+            alpha_phase = alpha
+        nmel = get_num_full_mel_coeffs_from_num_phase_coeffs(crsf_cf, phase_dim, alpha_phase, fs)
+        # the reference prints alpha with "%1.2f" on the SPTK command line (src/libaudio.py:589): False -> 0.00
+        a_mag, a_ph = float("%1.2f" % alpha), float("%1.2f" % alpha_phase)
+        key = (_lib.default_device(), fft_len, a_mag, mag_dim, a_ph, nmel, phase_dim)
+        if key not in cls._cache:
+            cls._cache[key] = cls(fft_len, a_mag, mag_dim, a_ph, nmel, phase_dim)
+        return cls._cache[key]
+
+
+def _lf0_smoothed(v_f0):
+    """src/magphase.py:2499-2501"""
+    v_f0 = np.asarray(v_f0, dtype=np.float64)
+    v_voi = (v_f0 > 0).astype('float')
+    return v_voi, f0_to_lf0(v_voi * medfilt3(v_f0))
+
+
+def format_for_modelling(m_mag, m_real, m_imag, v_f0, fs, mag_dim=60, phase_dim=45, b_mag_fbank_mel=False,
+                         alpha_phase=None):
+    """Lossless features -> (m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0_smth).  src/magphase.py:2490-2544"""
+    if b_mag_fbank_mel:
+        raise ValueError('b_mag_fbank_mel=True (experimental filter-bank warping) is outside the CUDA hot path')
+    m_mag = np.ascontiguousarray(m_mag, dtype=np.float64)
+    m_real = np.ascontiguousarray(m_real, dtype=np.float64)
+    m_imag = np.ascontiguousarray(m_imag, dtype=np.float64)
+    fft_len = 2 * (m_mag.shape[1] - 1)
+    plan = _MelPlan.get(fs, fft_len, mag_dim, phase_dim, alpha_phase)
+    v_voi, v_lf0 = _lf0_smoothed(v_f0)
+    n = m_mag.shape[0]
+    voi8 = np.ascontiguousarray(v_voi > 0, dtype=np.uint8)
+    o_mag = np.empty((n, mag_dim)); o_real = np.empty((n, phase_dim)); o_imag = np.empty((n, phase_dim))
+    _lib.check(_lib.lib().mpb_mel_compress_host(plan.handle, _lib.ptr(m_mag), _lib.ptr(m_real), _lib.ptr(m_imag),
+                                                _lib.ptr(voi8), n, _lib.ptr(o_mag), _lib.ptr(o_real), _lib.ptr(o_imag)))
+    return o_mag, o_real, o_imag, v_lf0
+
+
+def interp_from_variable_to_const_frm_rate(m_data, v_pm_smpls, const_rate_ms, fs, interp_type='linear'):
+    """Linear resampling of per-frame data onto a constant frame-rate grid.  src/magphase.py:2219-2239
+    (host NumPy for now: SURVEY.md 8(f) rank 1 moves it onto the device)."""
+    if interp_type != 'linear':
+        raise ValueError('only linear interpolation is supported')
+    m = np.asarray(m_data, dtype=np.float64)
+    one_d = m.ndim == 1
+    if one_d:
+        m = m[:, None]
+    step = fs * const_rate_ms / 1000
+    centres = np.arange(step, v_pm_smpls[-1], step)
+    x = np.asarray(v_pm_smpls, dtype=np.float64)
+    if x[0] > 0:
+        x = np.r_[0, x]
+        m = np.vstack((m[0, :], m))
+    j = np.clip(np.searchsorted(x, centres, side='right') - 1, 0, x.size - 2)
+    # scipy.interpolate.interp1d(kind='linear'): slope * (x_new - x_lo) + y_lo
+    slope = (m[j + 1] - m[j]) / (x[j + 1] - x[j])[:, None]
+    out = slope * (centres - x[j])[:, None] + m[j]
+    return out[:, 0] if one_d else out
+
+
+def analysis_compressed_from_pm(v_sig, fs, v_pm_smpls, v_voi, fft_len=None, mag_dim=60, phase_dim=10,
+                                b_const_rate=False, b_mag_fbank_mel=False, alpha_phase=None):
+    """analysis_compressed (src/magphase.py:2947-2988) minus file reading and epoch detection.
+    Variable-rate output runs fused on the device (the lossless features never leave HBM)."""
+    return analysis_compressed_batch([v_sig], fs, [v_pm_smpls], [v_voi], fft_len=fft_len, mag_dim=mag_dim,
+                                     phase_dim=phase_dim, b_const_rate=b_const_rate,
+                                     b_mag_fbank_mel=b_mag_fbank_mel, alpha_phase=alpha_phase)[0]
+
+
+def analysis_compressed_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None, mag_dim=60, phase_dim=10,
+                              b_const_rate=False, b_mag_fbank_mel=False, alpha_phase=None):
+    """Batched analysis_compressed_from_pm.  Returns a list of
+    (m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0_smth, v_shift, fs, fft_len)."""
+    if b_mag_fbank_mel:
+        raise ValueError('b_mag_fbank_mel=True (experimental filter-bank warping) is outside the CUDA hot path')
+    if fft_len is None:
+        fft_len = define_fft_len(fs)
+    if b_const_rate:
+        out = []
+        for sig, pm, voi in zip(l_sig, l_pm_smpls, l_voi):
+            m_mag, m_real, m_imag, v_f0, _, v_shift = analysis_lossless_from_pm(sig, fs, pm, voi, fft_len=fft_len)
+            v_pm = np.cumsum(v_shift)                               # la.shift_to_pm (src/magphase.py:2970)
+            m_mag = interp_from_variable_to_const_frm_rate(m_mag, v_pm, 5.0, fs)
+            m_real = interp_from_variable_to_const_frm_rate(m_real, v_pm, 5.0, fs)
+            m_imag = interp_from_variable_to_const_frm_rate(m_imag, v_pm, 5.0, fs)
+            vv = v_f0 > 1.0
+            v_f0c = interp_from_variable_to_const_frm_rate(np.r_[v_f0[vv][0], v_f0[vv], v_f0[vv][-1]],
+                                                           np.r_[0, v_pm[vv], v_pm[-1]], 5.0, fs)
+            vvc = interp_from_variable_to_const_frm_rate(vv.astype(float), v_pm, 5.0, fs) > 0.5
+            v_f0c = v_f0c * vvc
+            feats = format_for_modelling(m_mag, m_real, m_imag, v_f0c, fs, mag_dim=mag_dim, phase_dim=phase_dim,
+                                         alpha_phase=alpha_phase)
+            out.append(feats + (v_shift, fs, fft_len))
+        return out
+    plan = _MelPlan.get(fs, fft_len, mag_dim, phase_dim, alpha_phase)
+    sig_off = np.zeros(len(l_sig) + 1, dtype=np.int64)
+    centres, lefts, rights, vois, lf0s = [], [], [], [], []
+    for u, (sig, pm, voi) in enumerate(zip(l_sig, l_pm_smpls, l_voi)):
+        sig = np.asarray(sig)
+        P, v_shift, v_rights = frame_geometry(pm, sig.size)
+        _check_frames(v_shift, v_rights, fft_len)
+        sig_off[u + 1] = sig_off[u] + sig.size
+        centres.append(P[1:-1] + sig_off[u]); lefts.append(v_shift); rights.append(v_rights)
+        v_f0 = shift_to_f0(v_shift.astype(int), np.asarray(voi, dtype=np.float64), fs, out='f0', b_smooth=False)
+        v_voi, v_lf0 = _lf0_smoothed(v_f0)
+        vois.append(v_voi > 0); lf0s.append(v_lf0)
+    centre = np.ascontiguousarray(np.concatenate(centres), dtype=np.int64)
+    left = np.ascontiguousarray(np.concatenate(lefts), dtype=np.int32)
+    right = np.ascontiguousarray(np.concatenate(rights), dtype=np.int32)
+    voi8 = np.ascontiguousarray(np.concatenate(vois), dtype=np.uint8)
+    sig_all = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.float64) for s in l_sig]))
+    n = centre.size
+    o_mag = np.empty((n, mag_dim)); o_real = np.empty((n, phase_dim)); o_imag = np.empty((n, phase_dim))
+    _lib.check(_lib.lib().mpb_analysis_compressed_host(
+        plan.handle, _lib.ptr(sig_all), sig_all.size, _lib.ptr(centre), _lib.ptr(left), _lib.ptr(right),
+        _lib.ptr(voi8), n, ANALYSIS_COMPUTE, _lib.ptr(o_mag), _lib.ptr(o_real), _lib.ptr(o_imag)))
+    out, a = [], 0
+    for u in range(len(l_sig)):
+        b = a + lefts[u].size
+        out.append((o_mag[a:b], o_real[a:b], o_imag[a:b], lf0s[u], lefts[u].astype(int), fs, fft_len))
+        a = b
+    return out
+
+
+def analysis_compressed(wav_file, fft_len=None, mag_dim=60, phase_dim=10, b_const_rate=False, b_mag_fbank_mel=False,
+                        alpha_phase=None, est_file=None, pm=None):
+    """src/magphase.py:2947-2988.  Returns (m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0_smth, v_shift, fs, fft_len)."""
+    v_sig, fs = io.read_audio_file(wav_file)
+    v_pm_sec, v_voi = get_pitch_marks_and_voicing(wav_file, len(v_sig), fs, est_file=est_file, pm=pm)
+    return analysis_compressed_from_pm(v_sig, fs, v_pm_sec * fs, v_voi, fft_len=fft_len, mag_dim=mag_dim,
+                                       phase_dim=phase_dim, b_const_rate=b_const_rate,
+                                       b_mag_fbank_mel=b_mag_fbank_mel, alpha_phase=alpha_phase)
+
+
+def analysis_for_acoustic_modelling(wav_file, out_dir, fft_len=None, mag_dim=60, phase_dim=10, b_const_rate=False,
+                                    b_mag_fbank_mel=False, alpha_phase=None, est_file=None, pm=None):
+    """Writes .mag/.real/.imag/.lf0 (+ .shift when variable rate) float32 files.  src/magphase.py:2992-3022.
+    NB the reference passes ``alpha_phase=b_mag_fbank_mel`` (=False, i.e. 0.0) at :3010 -- replicated."""
+    feats = analysis_compressed(wav_file, fft_len=fft_len, mag_dim=mag_dim, phase_dim=phase_dim,
+                                b_const_rate=b_const_rate, b_mag_fbank_mel=b_mag_fbank_mel,
+                                alpha_phase=b_mag_fbank_mel, est_file=est_file, pm=pm)
+    m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0_smth, v_shift = feats[:5]
+    file_id = os.path.basename(wav_file).split(".")[0]
+    io.write_binfile(m_mag_mel_log, os.path.join(out_dir, file_id + '.mag'))
+    io.write_binfile(m_real_mel, os.path.join(out_dir, file_id + '.real'))
+    io.write_binfile(m_imag_mel, os.path.join(out_dir, file_id + '.imag'))
+    io.write_binfile(v_lf0_smth, os.path.join(out_dir, file_id + '.lf0'))
+    if not b_const_rate:
+        io.write_binfile(v_shift, os.path.join(out_dir, file_id + '.shift'))
+    return

@@ -1,0 +1,95 @@
+"""GPU parity of the low-dimensional compression (format_for_modelling / analysis_compressed) against the oracle.
+
+The oracle's SPTK `mcep -j 0` restatement is itself unpinned (no SPTK binary/source/fixture available, see
+oracle/magphase_oracle.py), so these tests prove CUDA == restatement, within 1e-5 RMS."""
+import ctypes
+import warnings
+
+import numpy as np
+import pytest
+
+import magphase_oracle as orc
+from magphase_b200.synth import synth_utterance
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rms(a, b):
+    return float(np.sqrt(np.mean(np.abs(np.asarray(a) - np.asarray(b)) ** 2)))
+
+
+@pytest.fixture(scope='module')
+def mp():
+    import magphase_b200.magphase as m
+    return m
+
+
+def test_warp_matrix_matches_freqt_recursion(mp):
+    """The device-built W^T = (freqt . cosine-IFFT)^T against the oracle's matrices."""
+    from magphase_b200 import _lib
+    plan = mp._MelPlan.get(48000, 4096, 60, 45, None)
+    H, N = 2049, 4096
+    k = np.arange(H)
+    w = np.full(H, 2.0); w[0] = w[-1] = 1.0
+    Cm = np.cos(2 * np.pi * np.outer(k, k) / N) * w[None, :] / N
+    Cm[0] *= 0.5; Cm[-1] *= 0.5
+    for which, n in ((0, 60), (1, plan.nmel)):
+        got = np.zeros((H, n), dtype=np.float32)
+        _lib.check(_lib.lib().mpb_mel_get_warp_matrix(plan.handle, which, _lib.ptr(got)))
+        ref = (orc.freqt_matrix(n, H, 0.77) @ Cm).T
+        assert np.max(np.abs(got - ref)) < 1e-9 + 1e-6 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize('fs,phase_dim,alpha_phase', [(48000, 45, None), (48000, 10, 0.0), (16000, 45, None)])
+def test_format_for_modelling_vs_oracle(mp, fs, phase_dim, alpha_phase):
+    sig, pm, voi = synth_utterance(6, fs=fs, dur_s=0.8)
+    mag, real, imag, f0, _, _ = orc.analysis_lossless_from_pm(sig, fs, pm, voi)
+    ref = orc.format_for_modelling(mag, real, imag, f0, fs, mag_dim=60, phase_dim=phase_dim, alpha_phase=alpha_phase)
+    got = mp.format_for_modelling(mag, real, imag, f0, fs, mag_dim=60, phase_dim=phase_dim, alpha_phase=alpha_phase)
+    for name, a, b in zip(('mag_mel_log', 'real_mel', 'imag_mel'), got[:3], ref[:3]):
+        assert a.shape == b.shape and a.dtype == np.float64
+        assert rms(a, b) < TOL, (name, rms(a, b))
+        assert np.max(np.abs(a - b)) < 1e-4, (name, np.max(np.abs(a - b)))
+    assert np.array_equal(got[3], ref[3]), 'lf0 (host float64 bookkeeping) must be bit-exact'
+    unv = f0 == 0
+    assert np.all(got[1][unv] == 0) and np.all(np.abs(got[1]) <= 1) and np.all(np.abs(got[2]) <= 1)
+
+
+def test_analysis_compressed_fused_vs_oracle(mp):
+    sig, pm, voi = synth_utterance(8, fs=48000, dur_s=1.0)
+    ref = orc.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45)
+    got = mp.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45)
+    assert np.array_equal(got[4], ref[4]) and got[5] == 48000 and got[6] == 4096
+    assert np.array_equal(got[3], ref[3])
+    for name, a, b in zip(('mag_mel_log', 'real_mel', 'imag_mel'), got[:3], ref[:3]):
+        assert a.shape == b.shape
+        assert rms(a, b) < TOL, (name, rms(a, b))
+
+
+def test_analysis_compressed_batch_and_mag_dim_100(mp):
+    """mag_dim=100 is what the shipped low-dim demo uses (demos/demo_copy_synthesis_low_dim.py:63)."""
+    utts = [synth_utterance(u, fs=48000, dur_s=0.4) for u in (20, 21)]
+    outs = mp.analysis_compressed_batch([u[0] for u in utts], 48000, [u[1] for u in utts], [u[2] for u in utts],
+                                        mag_dim=100, phase_dim=45)
+    for (sig, pm, voi), got in zip(utts, outs):
+        ref = orc.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=100, phase_dim=45)
+        for a, b in zip(got[:3], ref[:3]):
+            assert a.shape == b.shape and rms(a, b) < TOL
+        assert np.array_equal(got[3], ref[3])
+
+
+def test_analysis_compressed_const_rate(mp):
+    sig, pm, voi = synth_utterance(9, fs=48000, dur_s=0.8)
+    ref = orc.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45, b_const_rate=True)
+    got = mp.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45, b_const_rate=True)
+    for a, b in zip(got[:4], ref[:4]):
+        assert a.shape == b.shape and rms(a, b) < TOL
+
+
+def test_dim_errors(mp):
+    sig, pm, voi = synth_utterance(9, fs=48000, dur_s=0.3)
+    with pytest.raises(ValueError):
+        mp.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=300, phase_dim=45)
+    with pytest.raises(ValueError):
+        mp.analysis_compressed_from_pm(sig, 8000, pm, voi)
