@@ -174,6 +174,56 @@ int mpb_analysis_compressed_host(mpb_mel* plan,
                                  const uint8_t* voi, int64_t nfrm, int compute_dtype,
                                  double* out_mag_mel, double* out_real_mel, double* out_imag_mel);
 
+/* ---- compressed synthesis ------------------------------------------------------------------- */
+typedef struct mpb_syn mpb_syn;
+/*
+ * Plan for synthesis_from_compressed (src/magphase.py:825-997).  The host mirror builds, in float64, the fixed
+ * linear maps of la.sp_mel_unwarp (src/libaudio.py:667-684) and the per-bin tables:
+ *   u_mag  HOST [n_mag][fft_len/2+1]   log|X| = mag_mel_log . u_mag
+ *   u_ph   HOST [n_ph][hb]             real/imag = {real,imag}_mel . u_ph  (the nearest-extrapolation padding of
+ *                                      phase_uncompress_type1_mcep, src/magphase.py:1219-1235, folded in);
+ *                                      hb = bins below the upper edge of the crossfade band (<= fft_len/4)
+ *   tab    HOST [3][fft_len/2+1]       P  = sqrt(mask) * voiced tilt       (src/magphase.py:873-875, 940-946)
+ *                                      Av = sqrt(1 - mask)                 (:947)
+ *                                      Au = unvoiced aperiodic tilt        (:917-918)
+ */
+int mpb_syn_create(mpb_ctx* ctx, int fft_len, int n_mag, int n_ph, int hb,
+                   const double* u_mag, const double* u_ph, const double* tab, mpb_syn** out);
+int mpb_syn_destroy(mpb_syn* plan);
+
+/* Per-frame / per-utterance bookkeeping of a batch (all arrays host pointers for *_host, device for *_dev). */
+typedef struct mpb_syn_frames {
+    int64_t nfrm;
+    const int32_t* pm;        /* cumsum(trunc(shift)) inside the utterance                 (:879-880)           */
+    const int64_t* ncentre;   /* noise frame geometry, as in mpb_analysis_lossless_*        (:886-896)           */
+    const int32_t* nleft;
+    const int32_t* nright;
+    const uint8_t* voi;       /* voiced flag                                                                    */
+    const uint8_t* nkind;     /* MPB_WIN_* of the noise frame (Bartlett^2.5 for voiced when b_voi_ap_win)      */
+    const int32_t* win_a;     /* anti-ringing window half lengths                           (:968-973)           */
+    const int32_t* win_b;
+    const int32_t* row0;      /* feature row of the frame; with constant-rate input the frame is               */
+    const int32_t* row1;      /*   (1-roww)*row0 + roww*row1 of the UN-WARPED features (:861-870); NULL = none  */
+    const float* roww;
+    int32_t n_utt;
+    const int64_t* utt_frm_off;   /* [n_utt+1] */
+    const int64_t* utt_out_off;   /* [n_utt+1] */
+    const int32_t* utt_t0;        /* [n_utt]   see mpb_synthesis_lossless_dev */
+} mpb_syn_frames;
+
+/* mag_mel: n_rows x n_mag; real_mel/imag_mel: n_rows x n_ph (in_dtype); need_ph[row] != 0 where the phase rows
+ * are needed; noise: uniform(-1,1) samples (float32) of all utterances; runs from mpb_plan_ola_runs.
+ * per_linear != 0 selects per_phase_type='linear'.  Launches un-warp, noise statistics, gains, synthesis.      */
+int mpb_synthesis_compressed_dev(mpb_syn* plan, void* stream,
+                                 const void* mag_mel, const void* real_mel, const void* imag_mel, int in_dtype,
+                                 int64_t n_rows, const uint8_t* need_ph, const float* noise, int64_t n_noise,
+                                 const mpb_syn_frames* frames, const int32_t* runs, int32_t n_runs, int per_linear,
+                                 void* out, int out_dtype, int64_t n_out);
+int mpb_synthesis_compressed_host(mpb_syn* plan,
+                                  const double* mag_mel, const double* real_mel, const double* imag_mel,
+                                  int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
+                                  const mpb_syn_frames* frames, int per_linear, double* out, int64_t n_out);
+
 #ifdef __cplusplus
 }
 #endif

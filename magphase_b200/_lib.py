@@ -44,8 +44,20 @@ SIGNATURES = {
     'mpb_mel_compress_dev': [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _vp, _vp, C.c_int],
     'mpb_mel_compress_host': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     'mpb_analysis_compressed_host': [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp],
+    'mpb_syn_create': [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(_vp)],
+    'mpb_syn_destroy': [_vp],
+    'mpb_synthesis_compressed_dev': [_vp, _vp, _vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _i64, _vp, _vp, _i32, C.c_int,
+                                     _vp, C.c_int, _i64],
+    'mpb_synthesis_compressed_host': [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, C.c_int, _vp, _i64],
 }
 _RESTYPES = {'mpb_last_error': C.c_char_p, 'mpb_version': C.c_char_p, 'mpb_launch_count': _i64}
+
+
+class SynFrames(C.Structure):
+    """mpb_syn_frames of include/magphase_b200.h"""
+    _fields_ = [('nfrm', _i64), ('pm', _vp), ('ncentre', _vp), ('nleft', _vp), ('nright', _vp), ('voi', _vp),
+                ('nkind', _vp), ('win_a', _vp), ('win_b', _vp), ('row0', _vp), ('row1', _vp), ('roww', _vp),
+                ('n_utt', _i32), ('utt_frm_off', _vp), ('utt_out_off', _vp), ('utt_t0', _vp)]
 
 
 def lib():

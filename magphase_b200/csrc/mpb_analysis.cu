@@ -6,95 +6,9 @@
 // Reference: windowing() src/magphase.py:74-119, analysis_with_del_comp_from_pm :266-334 (pad :311-315,
 // rotate :323, fft :325, half :330-332), compute_lossless_feats :457-476, la.gen_non_symmetric_win
 // src/libaudio.py:70-84, voi_noise_window src/magphase.py:67-69.
-#include "mpb_fft.cuh"
-#include "mpb_kernels.h"
+#include "mpb_frame.cuh"
 
 namespace mpb {
-
-// value of the side window at distance j from the peak, side length S (j <= S):
-//   Hann       : 0.5 + 0.5 cos(pi j / S)        (np.hanning(2S+1) halves; hanning(1) = [1])
-//   Bartlett2.5: (1 - j/S)^2.5                  (np.bartlett(2S+1)**2.5 halves)
-template <typename T>
-__device__ __forceinline__ T side_window(int j, int S, int kind) {
-    if (j == 0) return (T)1;
-    const double x = (double)j / (double)S;
-    if (kind == MPB_WIN_HANN) return (T)(0.5 + 0.5 * cospi(x));
-    const double b = 1.0 - x;
-    return (T)(b * b * sqrt(b));
-}
-
-// mag = |X|, re = Re X/|X|, im = Im X/|X|, all 0 where |X| == 0 (src/magphase.py:459-470).  One reciprocal
-// square root instead of hypot + divide: float seed refined by a Newton step in the compute precision.
-__device__ __forceinline__ void normalise(double x, double y, double& mag, double& re, double& im) {
-    const double p = x * x + y * y;
-    if (p > 1e-30 && p < 1e30) {
-        double r = (double)rsqrtf((float)p);
-        r = r * fma(-0.5 * p, r * r, 1.5);
-        r = r * fma(-0.5 * p, r * r, 1.5);
-        mag = p * r; re = x * r; im = y * r;
-    } else if (p == 0.0 && x == 0.0 && y == 0.0) {
-        mag = re = im = 0.0;
-    } else {                                  // out-of-range magnitudes: slow exact path
-        mag = hypot(x, y);
-        re = x / mag; im = y / mag;
-    }
-}
-__device__ __forceinline__ void normalise(float x, float y, float& mag, float& re, float& im) {
-    const float p = x * x + y * y;
-    if (p > 1e-30f && p < 1e30f) {
-        float r = rsqrtf(p);
-        r = r * fmaf(-0.5f * p, r * r, 1.5f);
-        mag = p * r; re = x * r; im = y * r;
-    } else if (x == 0.0f && y == 0.0f) {
-        mag = re = im = 0.0f;
-    } else {
-        mag = hypotf(x, y);
-        re = x / mag; im = y / mag;
-    }
-}
-
-// Stage the windowed, un-delayed frame b[k] into shared memory as the packed complex
-// sequence z[m] = b[2m] + i b[2m+1] (natural padded layout) and pull this thread's 16 points into registers.
-//   b[N-j] = sig[c-j] * w(j, l)   j = 1..l          (left part; has priority, which also reproduces the
-//   b[k]   = sig[c+k] * w(k, q)   k = 0..q_eff       truncation branch src/magphase.py:313-315)
-// Only the l + q_eff + 1 non-zero samples are touched (~18 % of N for speech); everything else is known
-// to be zero from the frame geometry and never goes through shared memory.
-template <typename T, typename TS, int N>
-__device__ __forceinline__ void load_frame(const TS* __restrict__ sig, int64_t n_sig, int64_t c, int l, int q, int kind,
-                                           cx<T>* __restrict__ buf, cx<T>* v, int t) {
-    using G = FftGeom<T, N>;
-    T* bufT = reinterpret_cast<T*>(buf);
-    // l >= N (pitch period longer than the FFT): the reference keeps the first N samples of the frame and its
-    // hstack((v[l:], v[:l])) rotation degenerates to the identity -> b[k] = sig[c-l+k] * w(l-k, l)
-    const bool whole = l >= N;
-    const int q_eff = whole ? -1 : min(q, N - l - 1);
-    const int total = whole ? N : l + q_eff + 1;
-    for (int idx = t; idx < total; idx += G::TPB) {
-        int k, dist, side;
-        if (whole)        { dist = l - idx; side = l; k = idx; }
-        else if (idx < l) { dist = l - idx; side = l; k = N - dist; }
-        else              { dist = idx - l; side = q; k = dist; }
-        const int64_t i = c - l + idx;
-        const T x = (i >= 0 && i < n_sig) ? (T)sig[i] * side_window<T>(dist, side, kind) : (T)0;
-        bufT[2 * G::nphys(k >> 1) + (k & 1)] = x;
-    }
-    // complete the two complex elements that straddle the edges of the non-zero ranges
-    if (t == 0 && !whole) {
-        const int ke = q_eff + 1;                 // first zero after the right part
-        if ((ke & 1) && ke < N - l) bufT[2 * G::nphys(ke >> 1) + 1] = (T)0;
-        const int ks = N - l;                     // first sample of the left part
-        if ((ks & 1) && ks - 1 > q_eff) bufT[2 * G::nphys(ks >> 1)] = (T)0;
-    }
-    __syncthreads();
-#pragma unroll
-    const cx<T>* pk = buf + G::nphys(t);
-    for (int n1 = 0; n1 < 16; ++n1) {
-        const int m = n1 * G::S1 + t;
-        const bool nz = whole || (2 * m <= q_eff) || (2 * m + 1 >= N - l);
-        v[n1] = nz ? pk[n1 * (G::S1 + G::S1 / 16)] : mk<T>((T)0, (T)0);
-    }
-    __syncthreads();
-}
 
 template <typename T, int N> struct KernelCfg {
     // register budget: 128 regs/thread for float64 butterflies, ~85 for float32
@@ -130,11 +44,12 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
 
         // real-FFT split:  X[k] = E + W_N^k O,  X[M-k] = conj(E - W_N^k O),
         //                  E = (Z[k] + conj Z[M-k]) / 2,  O = -i (Z[k] - conj Z[M-k]) / 2,   k = t + j*TPB
-        TO* oa = out_a + f * (int64_t)H * (MODE == MODE_FFT ? 2 : 1);
-        TO* ob = out_b + f * (int64_t)H;
-        TO* oc = out_c + f * (int64_t)H;
+        TO* oa = out_a + (MODE == MODE_LOGSQ ? 0 : f * (int64_t)H * (MODE == MODE_FFT ? 2 : 1));
+        TO* ob = out_b + (MODE == MODE_LOGSQ ? 0 : f * (int64_t)H);
+        TO* oc = out_c + (MODE == MODE_LOGSQ ? 0 : f * (int64_t)H);
         T2 w = fc.wp;
         constexpr int NJ = (M / 2) / TPB;
+        double lsum = 0.0;                         // MODE_LOGSQ: sum over bins 1..H-2 of (log|X|)^2
 #pragma unroll 2
         for (int j = 0; j <= NJ; ++j) {
             const int k = t + j * TPB;
@@ -153,7 +68,13 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
                 const T2 x = h ? x2 : x1;
                 const int kk = h ? (M - k) : k;
                 if (h && kk == k) break;    // k == M/2 pairs with itself
-                if (MODE == MODE_FFT) {
+                if (MODE == MODE_LOGSQ) {
+                    if (kk != 0 && kk != M) {
+                        const T p = x.x * x.x + x.y * x.y;
+                        const double lg = p > (T)0 ? 0.5 * (double)log(p) : -1.0e10;   // la.log floor (src/libaudio.py:241-248)
+                        lsum = fma(lg, lg, lsum);
+                    }
+                } else if (MODE == MODE_FFT) {
                     __stcs(&oa[2 * kk], (TO)x.x);
                     __stcs(&oa[2 * kk + 1], (TO)x.y);
                 } else {
@@ -163,6 +84,18 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
                     __stcs(&ob[kk], (TO)re);
                     __stcs(&oc[kk], (TO)im);
                 }
+            }
+        }
+        if (MODE == MODE_LOGSQ) {                  // deterministic block reduction -> out_a[f]
+            __shared__ double red[32];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+            if ((t & 31) == 0) red[t >> 5] = lsum;
+            __syncthreads();
+            if (t == 0) {
+                double s = 0.0;
+                for (int i = 0; i < TPB / 32; ++i) s += red[i];
+                out_a[f] = (TO)s;
             }
         }
         __syncthreads();   // buf is rewritten by the next frame's staging
@@ -210,6 +143,16 @@ static cudaError_t launch_analysis_io(const AnalysisArgs& a, cudaStream_t st) {
     if (a.sig_dtype == MPB_F32 && a.out_dtype == MPB_F64) return launch_analysis_n<T, float, double>(a, st);
     if (a.sig_dtype == MPB_F64 && a.out_dtype == MPB_F32) return launch_analysis_n<T, double, float>(a, st);
     return launch_analysis_n<T, double, double>(a, st);
+}
+
+// sum over bins 1..H-2 of (log|N|)^2 per frame (float32 butterflies, float32 signal, float64 sums)
+cudaError_t launch_noise_stats(const AnalysisArgs& a, cudaStream_t st) {
+    switch (a.fft_len) {
+        case 1024: return launch_analysis_t<float, float, double, 1024, MODE_LOGSQ>(a, st);
+        case 2048: return launch_analysis_t<float, float, double, 2048, MODE_LOGSQ>(a, st);
+        case 4096: return launch_analysis_t<float, float, double, 4096, MODE_LOGSQ>(a, st);
+    }
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st) {

@@ -1,0 +1,113 @@
+// Device functions shared by the analysis-type kernels: side windows, frame staging, normalisation,
+// and the overlap-add flush shared by the synthesis kernels.
+#pragma once
+#include "mpb_fft.cuh"
+#include "mpb_kernels.h"
+
+namespace mpb {
+
+// value of the side window at distance j from the peak, side length S (j <= S):
+//   Hann       : 0.5 + 0.5 cos(pi j / S)        (np.hanning(2S+1) halves; hanning(1) = [1])
+//   Bartlett2.5: (1 - j/S)^2.5                  (np.bartlett(2S+1)**2.5 halves)
+template <typename T>
+__device__ __forceinline__ T side_window(int j, int S, int kind) {
+    if (j == 0) return (T)1;
+    const double x = (double)j / (double)S;
+    if (kind == MPB_WIN_HANN) return (T)(0.5 + 0.5 * cospi(x));
+    const double b = 1.0 - x;
+    return (T)(b * b * sqrt(b));
+}
+
+// mag = |X|, re = Re X/|X|, im = Im X/|X|, all 0 where |X| == 0 (src/magphase.py:459-470).  One reciprocal
+// square root instead of hypot + divide: float seed refined by a Newton step in the compute precision.
+__device__ __forceinline__ void normalise(double x, double y, double& mag, double& re, double& im) {
+    const double p = x * x + y * y;
+    if (p > 1e-30 && p < 1e30) {
+        double r = (double)rsqrtf((float)p);
+        r = r * fma(-0.5 * p, r * r, 1.5);
+        r = r * fma(-0.5 * p, r * r, 1.5);
+        mag = p * r; re = x * r; im = y * r;
+    } else if (p == 0.0 && x == 0.0 && y == 0.0) {
+        mag = re = im = 0.0;
+    } else {                                  // out-of-range magnitudes: slow exact path
+        mag = hypot(x, y);
+        re = x / mag; im = y / mag;
+    }
+}
+__device__ __forceinline__ void normalise(float x, float y, float& mag, float& re, float& im) {
+    const float p = x * x + y * y;
+    if (p > 1e-30f && p < 1e30f) {
+        float r = rsqrtf(p);
+        r = r * fmaf(-0.5f * p, r * r, 1.5f);
+        mag = p * r; re = x * r; im = y * r;
+    } else if (x == 0.0f && y == 0.0f) {
+        mag = re = im = 0.0f;
+    } else {
+        mag = hypotf(x, y);
+        re = x / mag; im = y / mag;
+    }
+}
+
+// Stage the windowed, un-delayed frame b[k] into shared memory as the packed complex
+// sequence z[m] = b[2m] + i b[2m+1] (natural padded layout) and pull this thread's 16 points into registers.
+//   b[N-j] = sig[c-j] * w(j, l)   j = 1..l          (left part; has priority, which also reproduces the
+//   b[k]   = sig[c+k] * w(k, q)   k = 0..q_eff       truncation branch src/magphase.py:313-315)
+// Only the l + q_eff + 1 non-zero samples are touched (~18 % of N for speech); everything else is known
+// to be zero from the frame geometry and never goes through shared memory.
+template <typename T, typename TS, int N>
+__device__ __forceinline__ void load_frame(const TS* __restrict__ sig, int64_t n_sig, int64_t c, int l, int q, int kind,
+                                           cx<T>* __restrict__ buf, cx<T>* v, int t) {
+    using G = FftGeom<T, N>;
+    T* bufT = reinterpret_cast<T*>(buf);
+    // l >= N (pitch period longer than the FFT): the reference keeps the first N samples of the frame and its
+    // hstack((v[l:], v[:l])) rotation degenerates to the identity -> b[k] = sig[c-l+k] * w(l-k, l)
+    const bool whole = l >= N;
+    const int q_eff = whole ? -1 : min(q, N - l - 1);
+    const int total = whole ? N : l + q_eff + 1;
+    for (int idx = t; idx < total; idx += G::TPB) {
+        int k, dist, side;
+        if (whole)        { dist = l - idx; side = l; k = idx; }
+        else if (idx < l) { dist = l - idx; side = l; k = N - dist; }
+        else              { dist = idx - l; side = q; k = dist; }
+        const int64_t i = c - l + idx;
+        const T x = (i >= 0 && i < n_sig) ? (T)sig[i] * side_window<T>(dist, side, kind) : (T)0;
+        bufT[2 * G::nphys(k >> 1) + (k & 1)] = x;
+    }
+    // complete the two complex elements that straddle the edges of the non-zero ranges
+    if (t == 0 && !whole) {
+        const int ke = q_eff + 1;                 // first zero after the right part
+        if ((ke & 1) && ke < N - l) bufT[2 * G::nphys(ke >> 1) + 1] = (T)0;
+        const int ks = N - l;                     // first sample of the left part
+        if ((ks & 1) && ks - 1 > q_eff) bufT[2 * G::nphys(ks >> 1)] = (T)0;
+    }
+    __syncthreads();
+#pragma unroll
+    const cx<T>* pk = buf + G::nphys(t);
+    for (int n1 = 0; n1 < 16; ++n1) {
+        const int m = n1 * G::S1 + t;
+        const bool nz = whole || (2 * m <= q_eff) || (2 * m + 1 >= N - l);
+        v[n1] = nz ? pk[n1 * (G::S1 + G::S1 / 16)] : mk<T>((T)0, (T)0);
+    }
+    __syncthreads();
+}
+
+
+// Flush the finished part [lo, hi) of the circular overlap-add accumulator to HBM (and clear it).  Samples a
+// neighbouring run may also write (outside [own_lo, own_hi)) are combined with atomicAdd on the zero-initialised
+// output; everything else is a plain store.  t0 / out_len map the pitch-mark axis to the utterance's output.
+template <typename T, typename TO, int N, int TPB>
+__device__ __forceinline__ void ola_flush(T* __restrict__ acc, int lo, int hi, int own_lo, int own_hi, int t0,
+                                          int64_t out_len, TO* __restrict__ out_utt, int t) {
+    for (int pos = lo + t; pos < hi; pos += TPB) {
+        const int ai = pos & (N - 1);
+        const T x = acc[ai];
+        acc[ai] = (T)0;
+        const int64_t j = (int64_t)pos - t0;
+        if (j >= 0 && j < out_len) {
+            if (pos >= own_lo && pos < own_hi) out_utt[j] = (TO)x;
+            else atomicAdd(&out_utt[j], (TO)x);
+        }
+    }
+}
+
+}  // namespace mpb

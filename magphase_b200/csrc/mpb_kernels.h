@@ -7,7 +7,7 @@
 
 namespace mpb {
 
-enum { MODE_FEATS = 0, MODE_FFT = 1 };
+enum { MODE_FEATS = 0, MODE_FFT = 1, MODE_LOGSQ = 2 };
 
 struct AnalysisArgs {
     const void* sig; int sig_dtype; int64_t n_sig;
@@ -19,6 +19,7 @@ struct AnalysisArgs {
     int num_sms;
 };
 cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st);
+cudaError_t launch_noise_stats(const AnalysisArgs& a, cudaStream_t st);   // out_a: double[nfrm]
 
 // One OLA run = consecutive frames of one utterance handled by one CTA (see mpb_synthesis.cu).
 struct OlaRun {
@@ -55,5 +56,33 @@ struct MelArgs {
 cudaError_t build_warp_matrix(int fft_len, int n_out, double alpha, float* wt32, double* scratch64, int ld,
                               cudaStream_t st);
 cudaError_t launch_mel_compress(const MelArgs& a, cudaStream_t st);
+
+// ---- mel un-warping + compressed synthesis (mpb_unwarp.cu, mpb_synth_comp.cu) ----
+struct UnwarpArgs {
+    const void* mag_mel; const void* real_mel; const void* imag_mel; int in_dtype;   // [nfrm][n_mag], [nfrm][n_ph]
+    const uint8_t* need_ph; int64_t nfrm; int n_mag; int n_ph;
+    const float* u_mag; int H; const float* u_ph; int HB;                           // [n_mag][H], [n_ph][HB]
+    float* out_mag; float* out_real; float* out_imag;                               // [nfrm][H], [nfrm][HB] x2
+};
+cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st);
+
+struct SynthCompArgs {
+    const float* m_mag; const float* m_real; const float* m_imag; int H; int HB;
+    const float* noise; int64_t n_noise;
+    const int32_t* pm; const int64_t* ncentre; const int32_t* nleft; const int32_t* nright;
+    const uint8_t* voi; const uint8_t* nkind; const int32_t* win_a; const int32_t* win_b;
+    const int32_t* row0; const int32_t* row1; const float* roww;                    // row1/roww NULL: no interpolation
+    const double* logsq; const int64_t* utt_frm_off;                                // noise statistics per frame
+    double* inv_gain;                                                               // [n_utt][2] scratch
+    const float* tab;                                                               // [3][H]: P, Av, Au
+    const int64_t* utt_out_off; const int32_t* utt_t0; int32_t n_utt;
+    const OlaRun* runs; int32_t n_runs; int64_t nfrm;
+    int fft_len; int per_linear;
+    const void* tw;                                                                 // float32 twiddles
+    void* out; int out_dtype; int64_t n_out;
+    int num_sms;
+};
+cudaError_t launch_noise_gain(const SynthCompArgs& a, cudaStream_t st);
+cudaError_t launch_synthesis_compressed(const SynthCompArgs& a, cudaStream_t st);
 
 }  // namespace mpb

@@ -1,0 +1,229 @@
+// Compressed synthesis: un-warped features + windowed noise -> periodic/aperiodic mix -> IFFT -> PSOLA.
+//
+// Reference: synthesis_from_compressed src/magphase.py:825-997.  Per frame (one CTA walks an OLA run):
+//   1. noise frame: windowing() with per-voicing window (:886-892), frm_list_to_matrix + fftshift (:895-896,
+//      src/libaudio.py:122-140) == the analysis buffer layout -> forward real FFT
+//   2. aperiodic = noise_spec / gain(voicing class) * mag [* unvoiced tilt]                    (:905-918)
+//      periodic  = mag * (real + j imag)/|.| * voiced tilt                                      (:922-941)
+//      mix with sqrt(mask), sqrt(1 - mask); DC and Nyquist become |.|                           (:944-961)
+//      -- all folded into three per-bin tables P = sqrt(mask) * tilt_voi, Av = sqrt(1 - mask), Au = tilt_unv
+//   3. Hermitian inverse FFT, fftshift (index math), anti-ringing window (:968-973, la.gen_centr_win
+//      src/libaudio.py:90-103), ola() (:976, :34-62)
+// The noise gains need the mean of (log|N|)^2 over ALL voiced / unvoiced frames of the utterance (:902-903):
+// k_analysis<MODE_LOGSQ> produces per-frame sums, k_noise_gain reduces them per utterance, and this kernel
+// recomputes the noise FFT instead of storing the noise spectra (16 KB/frame of HBM traffic saved).
+#include "mpb_frame.cuh"
+
+namespace mpb {
+
+// one warp per utterance, fixed summation order -> bit-reproducible gains
+__global__ void k_noise_gain(const double* __restrict__ logsq, const uint8_t* __restrict__ voi,
+                             const int64_t* __restrict__ utt_frm_off, int n_utt, int H, double* __restrict__ inv_gain) {
+    const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (u >= n_utt) return;
+    double sv = 0.0, su = 0.0;
+    long long nv = 0, nu = 0;
+    for (int64_t f = utt_frm_off[u] + lane; f < utt_frm_off[u + 1]; f += 32) {
+        if (voi[f]) { sv += logsq[f]; ++nv; } else { su += logsq[f]; ++nu; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        su += __shfl_xor_sync(0xffffffffu, su, o);
+        nv += __shfl_xor_sync(0xffffffffu, nv, o);
+        nu += __shfl_xor_sync(0xffffffffu, nu, o);
+    }
+    if (lane == 0) {
+        // gain = sqrt(exp(mean((log|N|)^2)));  an empty class gives NaN like np.mean([]) and is never used
+        inv_gain[2 * u + 0] = 1.0 / sqrt(exp(sv / ((double)nv * (double)(H - 2))));
+        inv_gain[2 * u + 1] = 1.0 / sqrt(exp(su / ((double)nu * (double)(H - 2))));
+    }
+}
+
+cudaError_t launch_noise_gain(const SynthCompArgs& a, cudaStream_t st) {
+    if (a.n_utt < 1) return cudaSuccess;
+    k_noise_gain<<<(a.n_utt + 3) / 4, 128, 0, st>>>(a.logsq, a.voi, a.utt_frm_off, a.n_utt, a.fft_len / 2 + 1, a.inv_gain);
+    return cudaGetLastError();
+}
+
+__device__ __forceinline__ float lerp_row(const float* __restrict__ r0, const float* __restrict__ r1, float w, int k) {
+    const float a = __ldg(r0 + k);
+    return r1 ? fmaf(w, __ldg(r1 + k) - a, a) : a;
+}
+
+template <typename TO, int N>
+__global__ void __launch_bounds__(FftGeom<float, N>::TPB, 640 / FftGeom<float, N>::TPB)
+k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
+    using T = float;
+    using G = FftGeom<T, N>;
+    using T2 = float2;
+    constexpr int M = G::M, TPB = G::TPB, HALF = N / 2;
+    constexpr int NJ = (M / 2) / TPB;
+    constexpr int STEP = TPB + TPB / 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T2* buf = reinterpret_cast<T2*>(smem_raw);
+    T* acc = reinterpret_cast<T*>(buf + G::BUF_ELEMS);
+    T2* tw2f = reinterpret_cast<T2*>(acc + N);
+    T2* tw2i = tw2f + G::TW2_ELEMS;
+    const int t = threadIdx.x;
+    const T scale = (T)1 / (T)N;
+    FftCtx<T> ff, fi;
+    fft_setup<T, N, false>(ff, tw2f, (const T2*)a.tw, t);
+    fft_setup<T, N, true>(fi, tw2i, (const T2*)a.tw, t);
+    T2* pk = buf + G::nphys(t);
+    T2* pmk = buf + G::nphys(M - t);
+    const int H = a.H, HB = a.HB;
+    const float* __restrict__ tabP = a.tab;
+    const float* __restrict__ tabAv = a.tab + H;
+    const float* __restrict__ tabAu = a.tab + 2 * H;
+
+    for (int r = blockIdx.x; r < a.n_runs; r += gridDim.x) {
+        const OlaRun run = a.runs[r];
+        const int64_t out_off = a.utt_out_off[run.utt];
+        const int64_t out_len = a.utt_out_off[run.utt + 1] - out_off;
+        const int t0 = a.utt_t0[run.utt];
+        const int own_lo = (run.flags & 1) ? a.pm[run.first - 1] + HALF : INT32_MIN;
+        const int own_hi = (run.flags & 2) ? a.pm[run.first + run.count] - HALF : INT32_MAX;
+        const float giv = (float)a.inv_gain[2 * run.utt + 0], giu = (float)a.inv_gain[2 * run.utt + 1];
+
+        for (int n = t; n < N; n += TPB) acc[n] = (T)0;
+        __syncthreads();
+
+        for (int fr = 0; fr < run.count; ++fr) {
+            const int64_t g = (int64_t)run.first + fr;
+            const int p = a.pm[g];
+            const bool voiced = a.voi[g] != 0;
+
+            // ---- 1. noise frame -> spectrum (natural padded layout in buf) ----
+            T2 v[16];
+            load_frame<T, float, N>(a.noise, a.n_noise, a.ncentre[g], a.nleft[g], a.nright[g], (int)a.nkind[g], buf, v, t);
+            fft_m<T, N, false>(v, buf, ff, t);
+
+            // ---- 2. mix periodic + aperiodic per bin pair (k, M-k), pack for the inverse transform ----
+            const float* __restrict__ mag0 = a.m_mag + (int64_t)a.row0[g] * H;
+            const float* __restrict__ mag1 = a.row1 ? a.m_mag + (int64_t)a.row1[g] * H : nullptr;
+            const float* __restrict__ re0 = a.m_real + (int64_t)a.row0[g] * HB;
+            const float* __restrict__ re1 = a.row1 ? a.m_real + (int64_t)a.row1[g] * HB : nullptr;
+            const float* __restrict__ im0 = a.m_imag + (int64_t)a.row0[g] * HB;
+            const float* __restrict__ im1 = a.row1 ? a.m_imag + (int64_t)a.row1[g] * HB : nullptr;
+            const float rw = a.roww ? a.roww[g] : 0.0f;
+            const float gi = voiced ? giv : giu;
+            const float* __restrict__ tabA = voiced ? tabAv : tabAu;
+            T2 znk[NJ + 1], znm[NJ + 1];
+            T2 wf = ff.wp, wi = fi.wp;
+#pragma unroll
+            for (int j = 0; j <= NJ; ++j) {
+                const int k = t + j * TPB;
+                if (j == NJ && t != 0) break;                  // k == M/2: thread 0 only
+                const T2 zk = pk[j * STEP];
+                const T2 zm = cconj(k == 0 ? buf[0] : pmk[-j * STEP]);
+                const T2 e = mk<T>(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
+                const T2 d = mk<T>(0.5f * (zk.x - zm.x), 0.5f * (zk.y - zm.y));
+                const T2 wo = cmul(mk<T>(d.y, -d.x), wf);
+                wf = cmul(wf, ff.wstep);
+                T2 n1 = cadd(e, wo);                           // noise spectrum N[k]
+                T2 n2 = cconj(csub(e, wo));                    // N[M-k]
+                if (k == 0) { n1.y = 0.0f; n2.y = 0.0f; }
+                const int km = M - k;
+                const float magk = lerp_row(mag0, mag1, rw, k), magm = lerp_row(mag0, mag1, rw, km);
+                const float sk = gi * magk * __ldg(tabA + k), sm = gi * magm * __ldg(tabA + km);
+                T2 xk = mk<T>(n1.x * sk, n1.y * sk);
+                T2 xm = mk<T>(n2.x * sm, n2.y * sm);
+                if (voiced && k < HB) {                        // periodic part lives below the crossfade band only
+                    float ur = 1.0f, ui = 0.0f;                // per_phase_type 'linear': zero phase
+                    if (!a.per_linear) { ur = lerp_row(re0, re1, rw, k); ui = lerp_row(im0, im1, rw, k); }
+                    const float pw = ur * ur + ui * ui;
+                    float s = 0.0f;                            // |u| == 0 -> u / 1 = 0
+                    if (pw > 1e-30f && pw < 1e30f) { s = rsqrtf(pw); s = s * fmaf(-0.5f * pw, s * s, 1.5f); }
+                    else if (pw > 0.0f) s = 1.0f / hypotf(ur, ui);
+                    s *= magk * __ldg(tabP + k);
+                    xk.x = fmaf(ur, s, xk.x);
+                    xk.y = fmaf(ui, s, xk.y);
+                }
+                if (k == 0) {                                  // DC and Nyquist: Re = |.|, Im = 0    (:958-961)
+                    xk = mk<T>(hypotf(xk.x, xk.y), 0.0f);
+                    xm = mk<T>(hypotf(xm.x, xm.y), 0.0f);
+                }
+                if (j == NJ) {                                 // k == M/2 pairs with itself: Z = 2 conj(X)
+                    znk[j] = mk<T>(2.0f * xk.x, -2.0f * xk.y);
+                    znm[j] = znk[j];
+                } else {
+                    xm.y = -xm.y;                              // conj(X[M-k])
+                    const T2 e2 = cadd(xk, xm);
+                    const T2 o2 = cmul(csub(xk, xm), wi);
+                    wi = cmul(wi, fi.wstep);
+                    znk[j] = mk<T>(e2.x - o2.y, e2.y + o2.x);
+                    znm[j] = mk<T>(e2.x + o2.y, -e2.y + o2.x);
+                }
+            }
+            __syncthreads();                                   // every thread is done reading the noise spectrum
+#pragma unroll
+            for (int j = 0; j <= NJ; ++j) {
+                const int k = t + j * TPB;
+                if (j == NJ && t != 0) break;
+                pk[j * STEP] = znk[j];
+                if (k != 0 && j != NJ) pmk[-j * STEP] = znm[j];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) v[n1] = pk[n1 * (G::S1 + G::S1 / 16)];
+            __syncthreads();
+            fft_m<T, N, true>(v, buf, fi, t);
+
+            // ---- 3. anti-ringing window + overlap-add: sample d in [-A, B] around the pitch mark ----
+            const int A = a.win_a[g], B = a.win_b[g];
+            const T* bufT = reinterpret_cast<const T*>(buf);
+            const float ia = A > 0 ? 1.0f / (float)A : 0.0f, ib = B > 0 ? 1.0f / (float)B : 0.0f;
+            for (int d = -A + t; d <= B; d += TPB) {
+                const int n = d & (N - 1);
+                const float w = d == 0 ? 1.0f : 0.5f + 0.5f * cospif(d < 0 ? (float)(-d) * ia : (float)d * ib);
+                acc[(p + d) & (N - 1)] += bufT[2 * G::nphys(n >> 1) + (n & 1)] * scale * w;
+            }
+            __syncthreads();
+
+            const int lo = p - HALF;
+            int hi = p + HALF;
+            if (fr + 1 < run.count) { const int nx = a.pm[g + 1] - HALF; hi = nx < hi ? nx : hi; }
+            ola_flush<T, TO, N, TPB>(acc, lo, hi, own_lo, own_hi, t0, out_len, out + out_off, t);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename TO, int N>
+static cudaError_t launch_sc_t(const SynthCompArgs& a, cudaStream_t st) {
+    using G = FftGeom<float, N>;
+    const size_t smem = sizeof(float2) * (G::BUF_ELEMS + 2 * G::TW2_ELEMS) + sizeof(float) * N;
+    auto kern = k_synthesis_compressed<TO, N>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G::TPB, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)a.num_sms * per_sm;
+    if (grid > a.n_runs) grid = a.n_runs;
+    if (grid < 1) return cudaSuccess;
+    kern<<<(unsigned)grid, G::TPB, smem, st>>>(a, (TO*)a.out);
+    return cudaGetLastError();
+}
+
+template <typename TO>
+static cudaError_t launch_sc_n(const SynthCompArgs& a, cudaStream_t st) {
+    switch (a.fft_len) {
+        case 1024: return launch_sc_t<TO, 1024>(a, st);
+        case 2048: return launch_sc_t<TO, 2048>(a, st);
+        case 4096: return launch_sc_t<TO, 4096>(a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_synthesis_compressed(const SynthCompArgs& a, cudaStream_t st) {
+    const size_t esz = a.out_dtype == MPB_F64 ? 8 : 4;
+    cudaError_t e = cudaMemsetAsync(a.out, 0, esz * (size_t)a.n_out, st);
+    if (e != cudaSuccess) return e;
+    return a.out_dtype == MPB_F64 ? launch_sc_n<double>(a, st) : launch_sc_n<float>(a, st);
+}
+
+}  // namespace mpb

@@ -12,8 +12,7 @@
 // >= N samples), and a+b == b+a, so the result is bit-reproducible run to run.
 // Reference: synthesis_from_lossless src/magphase.py:1759-1776, la.add_hermitian_half
 // src/libaudio.py:369-388 (imag of DC/Nyquist dropped), ola() src/magphase.py:34-62.
-#include "mpb_fft.cuh"
-#include "mpb_kernels.h"
+#include "mpb_frame.cuh"
 
 namespace mpb {
 
@@ -141,16 +140,7 @@ k_synthesis_lossless(const TF* __restrict__ mag, const TF* __restrict__ real, co
             const int lo = p - HALF;
             int hi = p + HALF;
             if (fr + 1 < run.count) { const int nx = pm[g + 1] - HALF; hi = nx < hi ? nx : hi; }
-            for (int pos = lo + t; pos < hi; pos += TPB) {
-                const int ai = pos & (N - 1);
-                const T x = acc[ai];
-                acc[ai] = (T)0;
-                const int64_t j = (int64_t)pos - t0;
-                if (j >= 0 && j < out_len) {
-                    if (pos >= own_lo && pos < own_hi) out[out_off + j] = (TO)x;
-                    else atomicAdd(&out[out_off + j], (TO)x);
-                }
-            }
+            ola_flush<T, TO, N, TPB>(acc, lo, hi, own_lo, own_hi, t0, out_len, out + out_off, t);
             // the next frame's first write to acc happens after two more barriers: no barrier needed here
         }
         __syncthreads();

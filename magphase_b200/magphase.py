@@ -521,3 +521,190 @@ def analysis_for_acoustic_modelling(wav_file, out_dir, fft_len=None, mag_dim=60,
     if not b_const_rate:
         io.write_binfile(v_shift, os.path.join(out_dir, file_id + '.shift'))
     return
+
+
+# ----------------------------------------------------------------------------------------------
+# compressed synthesis
+# ----------------------------------------------------------------------------------------------
+def mel_unwarp_matrix(n_c, nbins_out, alpha):
+    """la.sp_mel_unwarp (src/libaudio.py:667-684) as one matrix: out = in @ U, U is n_c x nbins_out.
+    Hermitian-extend, ifft.real, double cepstral indices 1..n_c-3 (index n_c-2 is NOT doubled, :679),
+    cosine matrix of the warped axis (src/libaudio.py:605-631)."""
+    eye = np.eye(n_c)
+    ceps = np.fft.ifft(np.hstack((eye, eye[:, -2:0:-1])), axis=1).real
+    ceps[:, 1:(n_c - 2)] *= 2
+    T = np.cos(np.arange(n_c)[:, None] * warped_axis(alpha, nbins_out)[None, :])
+    return ceps[:, :n_c] @ T
+
+
+def crossfade_curve(nbins, cut_off, bw, fs):
+    """Left weight of la.spectral_crossfade (src/libaudio.py:160-186) and the last bin it can be non-zero at."""
+    n_fft = (nbins - 1) * 2
+    bin_l = int(round_to_int((cut_off - bw / 2.0) * n_fft / float(fs)))
+    bin_r = int(round_to_int((cut_off + bw / 2.0) * n_fft / float(fs)))
+    B = bin_r - bin_l
+    return np.hstack((np.ones(bin_l), np.hanning(2 * B + 1)[B:], np.zeros(nbins - bin_r - 1))), bin_r
+
+
+class _SynPlan:
+    _cache = {}
+
+    def __init__(self, fs, fft_len, mag_dim, phase_dim, alpha, alpha_phase):
+        H = fft_len // 2 + 1
+        crsf_cf, crsf_bw = define_crossfade_params(fs)
+        curve, bin_r = crossfade_curve(H, crsf_cf, crsf_bw, fs)
+        self.HB = bin_r + 1
+        u_mag = mel_unwarp_matrix(mag_dim, H, alpha)
+        nmel = get_num_full_mel_coeffs_from_num_phase_coeffs(crsf_cf, phase_dim, alpha_phase, fs)
+        u_full = mel_unwarp_matrix(nmel, H, alpha_phase)[:, :self.HB]
+        # nearest-extrapolation padding phase_dim -> nmel = repeat the last column (src/magphase.py:1225-1229)
+        u_ph = np.zeros((phase_dim, self.HB))
+        np.add.at(u_ph, np.minimum(np.arange(nmel), phase_dim - 1), u_full)
+        tab = np.vstack((np.sqrt(curve) * 10 ** (build_mel_curve(0.6, H, amp=2.0) / 20),          # :940-946
+                         np.sqrt(1 - curve),                                                      # :947
+                         10 ** ((build_mel_curve(alpha, H, amp=3.5) - 3.5) / 20)))                # :917-918
+        self.fft_len, self.mag_dim, self.phase_dim = fft_len, mag_dim, phase_dim
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mpb_syn_create(_lib.ctx(), fft_len, mag_dim, phase_dim, self.HB,
+                                             _lib.ptr(np.ascontiguousarray(u_mag)), _lib.ptr(np.ascontiguousarray(u_ph)),
+                                             _lib.ptr(np.ascontiguousarray(tab)), C.byref(h)))
+        self.handle = h
+
+    @classmethod
+    def get(cls, fs, fft_len, mag_dim, phase_dim, alpha_phase):
+        alpha = define_alpha(fs)
+        if alpha_phase is None:
+            alpha_phase = alpha
+        key = (_lib.default_device(), fs, fft_len, mag_dim, phase_dim, float(alpha_phase))
+        if key not in cls._cache:
+            cls._cache[key] = cls(fs, fft_len, mag_dim, phase_dim, alpha, alpha_phase)
+        return cls._cache[key]
+
+
+def get_shifts_and_frm_locs_from_const_shifts(v_shift_c_rate, frm_rate_ms, fs, interp_type='linear'):
+    """Host reverse scan (sequential, data dependent): walk back from the last constant-rate centre, subtracting
+    the interpolated shift, until the position leaves the interpolation range.  src/magphase.py:1426-1449"""
+    n = np.size(v_shift_c_rate, 0)
+    centres = (fs * frm_rate_ms / 1000) * np.arange(1, n + 1)
+    shifts, locs = [], []
+    pos = centres[-1]
+    for _ in range(2 * n - 1):
+        if pos < centres[0] or pos > centres[-1]:
+            break
+        s = float(np.interp(pos, centres, v_shift_c_rate))
+        locs.append(pos)
+        shifts.append(s)
+        pos = pos - s
+    return np.array(shifts[::-1]), np.array(locs[::-1])
+
+
+def _const_rate_rows(v_locs, n_c, step):
+    """Row pairs + weights of interp_from_const_to_variable_rate (src/magphase.py:2242-2252), linear."""
+    centres = step * np.arange(1, n_c + 1)
+    j = np.clip(np.searchsorted(centres, v_locs, side='right') - 1, 0, n_c - 2)
+    w = (v_locs - centres[j]) / (centres[j + 1] - centres[j])
+    return j.astype(np.int32), (j + 1).astype(np.int32), w
+
+
+def synthesis_from_compressed(m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0, fs, fft_len=None, b_voi_ap_win=True,
+                              b_fbank_mel=False, b_const_rate=False, per_phase_type='magphase', alpha_phase=None,
+                              b_out_hpf=True):
+    """src/magphase.py:825-997.  The aperiodic noise is drawn from NumPy's global legacy stream with
+    np.random.uniform(-1, 1, ns_len) exactly where the reference draws it (:883): seed it for reproducibility."""
+    return synthesis_from_compressed_batch([(m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0)], fs, fft_len=fft_len,
+                                           b_voi_ap_win=b_voi_ap_win, b_fbank_mel=b_fbank_mel,
+                                           b_const_rate=b_const_rate, per_phase_type=per_phase_type,
+                                           alpha_phase=alpha_phase, b_out_hpf=b_out_hpf)[0]
+
+
+def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True, b_fbank_mel=False, b_const_rate=False,
+                                    per_phase_type='magphase', alpha_phase=None, b_out_hpf=True, l_noise=None):
+    """Batched synthesis_from_compressed; l_feats is a list of (m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0).
+    l_noise: optional list of per-utterance noise vectors (else drawn from np.random, utterance by utterance)."""
+    if b_fbank_mel:
+        raise ValueError('b_fbank_mel=True (experimental filter-bank warping) is outside the CUDA hot path')
+    if per_phase_type not in ('magphase', 'linear'):
+        raise NotImplementedError("per_phase_type=%r: only 'magphase' and 'linear' run on the CUDA path" % (per_phase_type,))
+    if fft_len is None:
+        fft_len = define_fft_len(fs)
+    mag_dim = np.shape(l_feats[0][0])[1]
+    phase_dim = np.shape(l_feats[0][1])[1]
+    plan = _SynPlan.get(fs, fft_len, mag_dim, phase_dim, alpha_phase)
+    half = fft_len // 2
+    n_utt = len(l_feats)
+    frm_off = np.zeros(n_utt + 1, dtype=np.int64)
+    out_off = np.zeros(n_utt + 1, dtype=np.int64)
+    row_off, noise_off = 0, 0
+    acc = {k: [] for k in ('pm', 'ncentre', 'nleft', 'nright', 'voi', 'nkind', 'win_a', 'win_b', 'row0', 'row1', 'roww',
+                           'need', 'noise', 'mag', 'real', 'imag', 't0')}
+    for u, (m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0) in enumerate(l_feats):
+        m_mag_mel_log = np.asarray(m_mag_mel_log, dtype=np.float64)
+        if m_mag_mel_log.shape[1] != mag_dim or np.shape(m_real_mel)[1] != phase_dim or np.shape(m_imag_mel)[1] != phase_dim:
+            raise ValueError('all utterances of a batch must share mag_dim / phase_dim')
+        n_c = m_mag_mel_log.shape[0]
+        v_f0 = np.exp(np.asarray(v_lf0, dtype=np.float64))
+        v_voi = v_f0 > 1.0                                        # :847
+        v_shift = f0_to_shift(v_f0, fs)
+        if b_const_rate:
+            v_shift, v_locs = get_shifts_and_frm_locs_from_const_shifts(v_shift, 5.0, fs)
+            r0, r1, w = _const_rate_rows(v_locs, n_c, fs * 5.0 / 1000)
+            vf = v_voi.astype(np.float64)
+            v_voi = (vf[r0] + (vf[r1] - vf[r0]) * w) > 0.5        # :868
+            need = np.ones(n_c, dtype=np.uint8)
+        else:
+            r0, r1, w = np.arange(n_c, dtype=np.int32), None, None
+            need = v_voi.astype(np.uint8)
+        n = v_shift.size
+        if n < 2:
+            raise IndexError('synthesis_from_compressed needs at least two frames (src/magphase.py:882)')
+        v_shift = v_shift.astype(int)                             # truncation BEFORE the cumsum (:879-880)
+        v_pm = np.cumsum(v_shift)
+        ns_len = int(v_pm[-1] + (v_pm[-1] - v_pm[-2]))
+        if l_noise is None:
+            v_ns = np.random.uniform(-1, 1, ns_len)               # :883
+        else:
+            v_ns = np.asarray(l_noise[u], dtype=np.float64)
+            if v_ns.size != ns_len:
+                raise ValueError('noise length %d != %d' % (v_ns.size, ns_len))
+        P, n_left, n_right = frame_geometry(v_pm, ns_len)
+        if np.any(n_left > half) or np.any(n_right >= half):      # frame_shift() would get a negative pad (src/libaudio.py:137-140)
+            raise ValueError('negative dimensions are not allowed')
+        se = np.r_[v_shift[0], v_shift, v_shift[-1], v_shift[-1]]
+        pm_int, t0, n_out = ola_geometry(v_pm, fft_len)
+        frm_off[u + 1] = frm_off[u] + n
+        out_off[u + 1] = out_off[u] + n_out
+        acc['pm'].append(pm_int); acc['ncentre'].append(P[1:-1] + noise_off)
+        acc['nleft'].append(n_left); acc['nright'].append(n_right)
+        acc['voi'].append(v_voi.astype(np.uint8))
+        acc['nkind'].append(np.where(v_voi & bool(b_voi_ap_win), WIN_BARTLETT25, WIN_HANN).astype(np.uint8))
+        acc['win_a'].append(se[:-3] + se[1:-2]); acc['win_b'].append(se[2:-1] + se[3:])
+        acc['row0'].append(r0 + row_off)
+        if b_const_rate:
+            acc['row1'].append(r1 + row_off); acc['roww'].append(w)
+        acc['need'].append(need); acc['noise'].append(v_ns); acc['t0'].append(t0)
+        acc['mag'].append(m_mag_mel_log)
+        acc['real'].append(np.asarray(m_real_mel, dtype=np.float64)); acc['imag'].append(np.asarray(m_imag_mel, dtype=np.float64))
+        row_off += n_c
+        noise_off += ns_len
+    cat = lambda k, dt: np.ascontiguousarray(np.concatenate(acc[k]), dtype=dt)
+    arrs = dict(pm=cat('pm', np.int32), ncentre=cat('ncentre', np.int64), nleft=cat('nleft', np.int32),
+                nright=cat('nright', np.int32), voi=cat('voi', np.uint8), nkind=cat('nkind', np.uint8),
+                win_a=cat('win_a', np.int32), win_b=cat('win_b', np.int32), row0=cat('row0', np.int32),
+                row1=cat('row1', np.int32) if b_const_rate else None,
+                roww=cat('roww', np.float32) if b_const_rate else None,
+                utt_frm_off=frm_off, utt_out_off=out_off, utt_t0=np.ascontiguousarray(acc['t0'], dtype=np.int32))
+    fr = _lib.SynFrames(nfrm=int(frm_off[-1]), n_utt=n_utt, **{k: _lib.ptr(v) for k, v in arrs.items()})
+    mag, real, imag = cat('mag', np.float64), cat('real', np.float64), cat('imag', np.float64)
+    need, noise = cat('need', np.uint8), cat('noise', np.float64)
+    out = np.empty(int(out_off[-1]), dtype=np.float64)
+    _lib.check(_lib.lib().mpb_synthesis_compressed_host(
+        plan.handle, _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), mag.shape[0], _lib.ptr(need), _lib.ptr(noise),
+        noise.size, C.byref(fr), 1 if per_phase_type == 'linear' else 0, _lib.ptr(out), out.size))
+    l_out = [out[out_off[u]:out_off[u + 1]] for u in range(n_utt)]
+    if b_out_hpf:
+        # 4th-order 40 Hz Butterworth high-pass (src/magphase.py:981-995); sequential IIR, host for now
+        # (SURVEY.md 8(f) rank 1 moves it onto the device as a blocked state-space scan)
+        from scipy import signal
+        v_b, v_a = signal.butter(4, 40 / (fs / 2.0), btype='highpass')
+        l_out = [signal.lfilter(v_b, v_a, y) for y in l_out]
+    return l_out

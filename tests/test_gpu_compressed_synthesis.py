@@ -1,0 +1,122 @@
+"""GPU parity of synthesis_from_compressed against the oracle and the golden vectors generated from the real
+reference, with identical host-generated noise (np.random legacy stream, same seed)."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import magphase_oracle as orc
+from magphase_b200.synth import synth_utterance
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+TOL = 1e-5
+
+
+def rms(a, b):
+    return float(np.sqrt(np.mean(np.abs(np.asarray(a) - np.asarray(b)) ** 2)))
+
+
+@pytest.fixture(scope='module')
+def mp():
+    import magphase_b200.magphase as m
+    return m
+
+
+@pytest.fixture(scope='module')
+def gold():
+    g = np.load(os.path.join(GOLD, 'compressed_hvd704.npz'))
+    f64 = lambda k: g[k].astype(np.float64)
+    return g, (f64('mag'), f64('real'), f64('imag'), f64('lf0'))
+
+
+@pytest.mark.parametrize('key,kw', [('syn_var_nohpf', dict(b_out_hpf=False)), ('syn_var_hpf', dict(b_out_hpf=True)),
+                                    ('syn_const_nohpf', dict(b_out_hpf=False, b_const_rate=True))])
+def test_vs_reference_golden_48k(mp, gold, key, kw):
+    g, feats = gold
+    np.random.seed(int(g['seed']))
+    y = mp.synthesis_from_compressed(*feats, 48000, **kw)
+    assert y.shape == g[key].shape and y.dtype == np.float64
+    assert rms(y, g[key]) < TOL, rms(y, g[key])
+    assert np.max(np.abs(y - g[key])) < 1e-4
+
+
+def test_vs_reference_golden_16k_const_rate_hpf(mp, gold):
+    g, feats = gold
+    np.random.seed(int(g['seed']))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        y = mp.synthesis_from_compressed(*feats, 16000, b_const_rate=True)
+    assert y.shape == g['syn_16k_const_hpf'].shape
+    assert rms(y, g['syn_16k_const_hpf']) < TOL
+
+
+def test_linear_phase_and_plain_noise_window_vs_oracle(mp, gold):
+    g, feats = gold
+    for kw in (dict(per_phase_type='linear'), dict(b_voi_ap_win=False)):
+        np.random.seed(5)
+        y = mp.synthesis_from_compressed(*feats, 48000, b_out_hpf=False, **kw)
+        np.random.seed(5)
+        y_ref = orc.synthesis_from_compressed(*feats, 48000, b_out_hpf=False, **kw)
+        assert y.shape == y_ref.shape and rms(y, y_ref) < TOL
+
+
+def test_copy_synthesis_low_dim_chain(mp):
+    """BASELINE config 2: analysis_compressed (60/45/45) -> synthesis_from_compressed on the same utterance,
+    CUDA chain against the oracle chain."""
+    sig, pm, voi = synth_utterance(12, fs=48000, dur_s=1.0)
+    got = mp.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45)
+    ref = orc.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45)
+    np.random.seed(3)
+    y = mp.synthesis_from_compressed(got[0], got[1], got[2], got[3], 48000, b_out_hpf=False)
+    np.random.seed(3)
+    y_ref = orc.synthesis_from_compressed(ref[0], ref[1], ref[2], ref[3], 48000, b_out_hpf=False)
+    assert y.shape == y_ref.shape
+    assert rms(y, y_ref) < TOL, rms(y, y_ref)
+
+
+def test_batch_equals_single_and_is_deterministic(mp, gold):
+    g, feats = gold
+    a_feats = tuple(f[:30] for f in feats)
+    b_feats = tuple(f[20:64] for f in feats)
+    rng = np.random.RandomState(1)
+    lens = []
+    for f in (a_feats, b_feats):
+        sh = mp.f0_to_shift(np.exp(f[3]), 48000).astype(int)
+        pmv = np.cumsum(sh)
+        lens.append(int(pmv[-1] + (pmv[-1] - pmv[-2])))
+    noises = [rng.uniform(-1, 1, n) for n in lens]
+    y = mp.synthesis_from_compressed_batch([a_feats, b_feats], 48000, b_out_hpf=False, l_noise=noises)
+    y2 = mp.synthesis_from_compressed_batch([a_feats, b_feats], 48000, b_out_hpf=False, l_noise=noises)
+    for u, f in enumerate((a_feats, b_feats)):
+        assert np.array_equal(y[u], y2[u])
+        single = mp.synthesis_from_compressed_batch([f], 48000, b_out_hpf=False, l_noise=[noises[u]])[0]
+        assert np.array_equal(single, y[u])
+        ref = orc.synthesis_from_compressed(*f, 48000, b_out_hpf=False, v_noise=noises[u])
+        assert rms(y[u], ref) < TOL
+
+
+def test_all_unvoiced_and_all_voiced(mp, gold):
+    """Empty voicing class: the reference takes np.mean of an empty selection (NaN gain, RuntimeWarning) that is
+    never applied to any frame."""
+    g, feats = gold
+    mag, real, imag, lf0 = (f[:20].copy() for f in feats)
+    for lf in (np.full(20, -1.0e10), np.full(20, np.log(120.0))):
+        np.random.seed(2)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            y = mp.synthesis_from_compressed(mag, real, imag, lf, 48000, b_out_hpf=False)
+            np.random.seed(2)
+            y_ref = orc.synthesis_from_compressed(mag, real, imag, lf, 48000, b_out_hpf=False)
+        assert np.all(np.isfinite(y)) and y.shape == y_ref.shape and rms(y, y_ref) < TOL
+
+
+def test_errors(mp, gold):
+    g, feats = gold
+    with pytest.raises(NotImplementedError):
+        mp.synthesis_from_compressed(*feats, 48000, per_phase_type='min_phase')
+    with pytest.raises(ValueError):
+        mp.synthesis_from_compressed(*feats, 48000, b_fbank_mel=True)
+    with pytest.raises(ValueError):        # f0 of 20 Hz: frames longer than fft_len/2
+        mp.synthesis_from_compressed(feats[0][:5], feats[1][:5], feats[2][:5], np.full(5, np.log(20.0)), 48000)
