@@ -33,7 +33,7 @@ DISTINCT = 16          # distinct synthetic utterances generated per rank (tiled
 # CPU arm: the reference's own implementation (oracle/_ref, py3 translation) or the numpy oracle port
 # --------------------------------------------------------------------------------------------
 _CPU_INPUTS = None
-_CPU_KIND = None
+_CPU_WORKLOAD = 'compressed'
 
 
 def _cpu_impl():
@@ -67,9 +67,33 @@ def _cpu_impl():
     return 'port', ana, syn
 
 
+def _cpu_impl_compressed():
+    """(kind, fn) for the compressed chain: reference lossless analysis -> format_for_modelling with the numpy
+    restatement of SPTK `mcep -j 0` (the binary is not available anywhere) -> reference synthesis_from_compressed."""
+    kind, ana, _ = _cpu_impl()
+    odir = os.path.join(ROOT, 'oracle')
+    if odir not in sys.path:
+        sys.path.insert(0, odir)
+    import magphase_oracle as orc
+    if kind == 'reference':
+        import magphase as ref_mp
+        syn_c = lambda a, b, c, d: ref_mp.synthesis_from_compressed(a, b, c, d, FS, b_out_hpf=False)
+    else:
+        syn_c = lambda a, b, c, d: orc.synthesis_from_compressed(a, b, c, d, FS, b_out_hpf=False)
+
+    def chain(sig, pm, voi):
+        mag, real, imag, f0 = ana(sig, pm, voi)
+        mm, rr, ii, lf0 = orc.format_for_modelling(mag, real, imag, f0, FS, mag_dim=60, phase_dim=45)
+        return mag.shape[0], syn_c(mm, rr, ii, lf0)
+    return kind, chain
+
+
 def _cpu_worker(i):
-    kind, ana, syn = _cpu_impl()
     sig, pm, voi = _CPU_INPUTS[i]
+    if _CPU_WORKLOAD == 'compressed':
+        n, y = _cpu_impl_compressed()[1](sig, pm, voi)
+        return int(n), float(y[0])
+    kind, ana, syn = _cpu_impl()
     mag, real, imag, f0 = ana(sig, pm, voi)
     y = syn(mag, real, imag, f0)
     return int(mag.shape[0]), float(y[0])
@@ -89,11 +113,13 @@ def make_cpu_inputs(n_utts, dur_s):
     _CPU_INPUTS = [base[i % len(base)] for i in range(n_utts)]
 
 
-def run_cpu_arm(n_utts, dur_s, steps, warmup):
+def run_cpu_arm(n_utts, dur_s, steps, warmup, workload='compressed'):
     """K timed steps (after W warm-ups), each a Pool.map over n_utts utterances on all host cores --
     the reference's own fan-out (src/libutils.py:32-63)."""
     for k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
         os.environ[k] = '1'
+    global _CPU_WORKLOAD
+    _CPU_WORKLOAD = workload
     kind = _cpu_impl()[0]
     make_cpu_inputs(n_utts, dur_s)
     cores = os.cpu_count() or 1
@@ -108,8 +134,11 @@ def run_cpu_arm(n_utts, dur_s, steps, warmup):
             secs += dt
     return dict(kind=kind, cores=cores, frames_per_step=frames // max(steps, 1), value=frames / secs,
                 ms_per_step=1e3 * secs / max(steps, 1),
-                sample='%d x %.1f s synth48k-v1 utterances per step (analysis_with_del_comp_from_pm + '
-                       'compute_lossless_feats + synthesis_from_lossless), Pool(%d)' % (n_utts, dur_s, cores))
+                sample=('%d x %.1f s synth48k-v1 utterances per step, Pool(%d): ' % (n_utts, dur_s, cores)) + (
+                    'analysis_with_del_comp_from_pm + compute_lossless_feats + format_for_modelling(60/45/45; SPTK mcep '
+                    'step = numpy restatement, binary unavailable) + synthesis_from_compressed(b_out_hpf=False)'
+                    if workload == 'compressed' else
+                    'analysis_with_del_comp_from_pm + compute_lossless_feats + synthesis_from_lossless'))
 
 
 # --------------------------------------------------------------------------------------------
@@ -171,26 +200,38 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='compressed', choices=['compressed', 'lossless'],
+                    help="compressed = BASELINE config 2 (analysis_compressed 60/45/45 -> synthesis_from_compressed); "
+                         "lossless = config 1 chain (analysis_lossless -> synthesis_from_lossless)")
     ap.add_argument('--utts', type=int, default=128, help='utterances per GPU per step (device-timed arm)')
     ap.add_argument('--dur', type=float, default=5.0, help='utterance length in seconds')
-    ap.add_argument('--e2e-utts', type=int, default=8, help='utterances per GPU per step (host-API arm)')
-    ap.add_argument('--cpu-utts', type=int, default=32, help='utterances per step of the CPU arm')
-    ap.add_argument('--feat-dtype', default='f32', choices=['f32', 'f64'], help='feature storage in HBM')
+    ap.add_argument('--e2e-utts', type=int, default=0, help='utterances per GPU per step (host-API arm); 0 = auto')
+    ap.add_argument('--cpu-utts', type=int, default=0, help='utterances per step of the CPU arm; 0 = auto')
+    ap.add_argument('--cpu-dur', type=float, default=0.0, help='utterance length of the CPU arm sample; 0 = auto')
+    ap.add_argument('--feat-dtype', default='f32', choices=['f32', 'f64'], help='lossless feature storage in HBM')
     ap.add_argument('--analysis-compute', default='f64', choices=['f32', 'f64'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
+    comp = a.workload == 'compressed'
+    if a.cpu_utts == 0:
+        a.cpu_utts = 16 if comp else 32
+    if a.cpu_dur == 0.0:
+        a.cpu_dur = 2.0 if comp else a.dur     # the reference's compressed synthesis runs at ~70 frames/s/core
+    if a.e2e_utts == 0:
+        a.e2e_utts = 32 if comp else 8
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    workload = 'lossless chain: analysis_lossless -> synthesis_from_lossless, %d x %.0f s synth48k-v1 utterances per GPU' \
-               % (a.utts, a.dur)
+    chain = ('analysis_compressed(mag=60, real=45, imag=45) -> synthesis_from_compressed(b_out_hpf=False)' if comp
+             else 'analysis_lossless -> synthesis_from_lossless')
+    workload = '%s chain: %s, %d x %.0f s synth48k-v1 utterances per GPU per step' % (a.workload, chain, a.utts, a.dur)
 
     if a.impl == 'reference':
         if rank != 0:
             return
-        r = run_cpu_arm(a.cpu_utts, a.dur, a.steps, a.warmup)
+        r = run_cpu_arm(a.cpu_utts, a.cpu_dur, a.steps, a.warmup, a.workload)
         print(json.dumps({
             'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': 'frames/s', 'n_gpus': a.gpus,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
@@ -205,16 +246,16 @@ def main():
     # ---- CPU baseline first (fork before CUDA is initialised), rank 0 at N=1 only ----
     cpu = None
     if world == 1 and a.gpus == 1 and not a.no_cpu_baseline:
-        cpu = run_cpu_arm(a.cpu_utts, a.dur, 2, 1)
+        cpu = run_cpu_arm(a.cpu_utts, a.cpu_dur, 2, 1, a.workload)
 
     import torch
     import torch.distributed as dist
+    os.environ.setdefault('MPB_DEVICE', str(local_rank))
     from magphase_b200 import _lib
     from magphase_b200 import magphase as mp
-    from magphase_b200.device import LosslessPlan
+    from magphase_b200.device import CompressedPlan, LosslessPlan
     from magphase_b200.synth import synth_utterance
 
-    os.environ.setdefault('MPB_DEVICE', str(local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
@@ -239,21 +280,36 @@ def main():
     F32, F64 = _lib.MPB_F32, _lib.MPB_F64
     feat_dt = F64 if a.feat_dtype == 'f64' else F32
     ana_compute = F64 if a.analysis_compute == 'f64' else F32
-    plan = LosslessPlan([u[0].size for u in utts], [u[1] for u in utts], [u[2] for u in utts], FS, FFT_LEN,
-                        device=local_rank)
     d_sig = torch.from_numpy(np.concatenate([u[0] for u in utts]).astype(np.float32)).to(dev)   # PCM16/32768: exact in f32
-    feats = plan.alloc_features(feat_dt)
-    d_out = plan.alloc_output(F32)
+    geom = ([u[0].size for u in utts], [u[1] for u in utts], [u[2] for u in utts])
+    if comp:
+        plan = CompressedPlan(*geom, FS, FFT_LEN, mag_dim=60, phase_dim=45, device=local_rank)
 
-    def step(evs=None):
-        if evs:
-            evs[0].record()
-        plan.analysis(d_sig, feats, compute=ana_compute)
-        if evs:
-            evs[1].record()
-        plan.synthesis(feats, d_out, compute=F32)
-        if evs:
-            evs[2].record()
+        def step(evs=None):
+            if evs:
+                evs[0].record()
+            plan.analysis(d_sig, compute=ana_compute)
+            if evs:
+                evs[1].record()
+            plan.synthesis()
+            if evs:
+                evs[2].record()
+        bytes_ana, bytes_syn = plan.analysis_bytes(), plan.synthesis_bytes()
+    else:
+        plan = LosslessPlan(*geom, FS, FFT_LEN, device=local_rank)
+        feats = plan.alloc_features(feat_dt)
+        d_out = plan.alloc_output(F32)
+
+        def step(evs=None):
+            if evs:
+                evs[0].record()
+            plan.analysis(d_sig, feats, compute=ana_compute)
+            if evs:
+                evs[1].record()
+            plan.synthesis(feats, d_out, compute=F32)
+            if evs:
+                evs[2].record()
+        bytes_ana, bytes_syn = plan.analysis_bytes(F32, feat_dt), plan.synthesis_bytes(feat_dt, F32)
 
     def barrier():
         if world > 1:
@@ -279,14 +335,28 @@ def main():
     ana_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / a.steps
     syn_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / a.steps
 
+    # ---- per-kernel device times: extra steps with the library's CUDA-event brackets switched on ----
+    prof_steps = 3
+    _lib.profile_begin(local_rank)
+    for _ in range(prof_steps):
+        step()
+    prof = _lib.profile_end(local_rank)
+
     # ---- e2e through the public host API (NumPy in / NumPy out; H2D + D2H inside the timed region) ----
     e_utts = utts[:max(1, min(a.e2e_utts, len(utts)))]
     e_sig, e_pm, e_voi = [u[0] for u in e_utts], [u[1] for u in e_utts], [u[2] for u in e_utts]
-
-    def e2e_step():
-        outs = mp.analysis_lossless_batch(e_sig, FS, e_pm, e_voi, fft_len=FFT_LEN)
-        ys = mp.synthesis_from_lossless_batch([o[:4] for o in outs], FS)
-        return sum(o[5].size for o in outs), outs, ys
+    if comp:
+        def e2e_step():
+            outs = mp.analysis_compressed_batch(e_sig, FS, e_pm, e_voi, fft_len=FFT_LEN, mag_dim=60, phase_dim=45)
+            ys = mp.synthesis_from_compressed_batch([o[:4] for o in outs], FS, b_out_hpf=False)
+            return sum(o[4].size for o in outs), outs, ys
+        api = 'analysis_compressed_batch -> synthesis_from_compressed_batch (float64 NumPy in/out, np.random noise)'
+    else:
+        def e2e_step():
+            outs = mp.analysis_lossless_batch(e_sig, FS, e_pm, e_voi, fft_len=FFT_LEN)
+            ys = mp.synthesis_from_lossless_batch([o[:4] for o in outs], FS)
+            return sum(o[5].size for o in outs), outs, ys
+        api = 'analysis_lossless_batch -> synthesis_from_lossless_batch (float64 NumPy in/out)'
     for _ in range(2):
         e_frames, outs, ys = e2e_step()
     e_steps = max(2, min(a.steps, 5))
@@ -296,9 +366,16 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e_secs = time.perf_counter() - t
-    feat_bytes = 3 * 8 * sum(o[0].size for o in outs)
-    h2d = 8 * sum(s.size for s in e_sig) + 16 * e_frames + feat_bytes + 4 * e_frames
-    d2h = feat_bytes + 8 * sum(y.size for y in ys)
+    n_smp = sum(s.size for s in e_sig)
+    if comp:
+        feat_bytes = 8 * sum(o[0].size + o[1].size + o[2].size for o in outs)
+        n_noise = sum(y.size for y in ys)      # ~ one noise sample per output sample
+        h2d = 8 * n_smp + 17 * e_frames + feat_bytes + e_frames + 4 * n_noise + 45 * e_frames
+        d2h = feat_bytes + 8 * sum(y.size for y in ys)
+    else:
+        feat_bytes = 3 * 8 * sum(o[0].size for o in outs)
+        h2d = 8 * n_smp + 16 * e_frames + feat_bytes + 4 * e_frames
+        d2h = feat_bytes + 8 * sum(y.size for y in ys)
 
     # ---- reduce over ranks: max time, summed frames ----
     stats = torch.tensor([total_ms, e_secs, ana_ms, syn_ms], dtype=torch.float64, device=dev)
@@ -318,30 +395,50 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-    k_ana = dict(name='k_analysis', ms=ana_ms, bytes=plan.analysis_bytes(F32, feat_dt))
-    k_syn = dict(name='k_synthesis_lossless', ms=syn_ms, bytes=plan.synthesis_bytes(feat_dt, F32))
-    for k in (k_ana, k_syn):
-        k['gbs'] = k['bytes'] / (k['ms'] * 1e-3) / 1e9
-        k['frac'] = k['gbs'] / peak
-    dom = k_ana if ana_ms >= syn_ms else k_syn
+    # algorithmic HBM bytes per launch of each kernel = what its own contract must move
+    H, nf = FFT_LEN // 2 + 1, plan.nfrm
+    kbytes = {
+        'k_analysis': plan.n_sig * 4 + nf * 16 + 3 * nf * H * (8 if (not comp and feat_dt == F64) else 4),
+        'k_synthesis_lossless': 3 * nf * H * (8 if feat_dt == F64 else 4) + nf * 4 + getattr(plan, 'n_out', 0) * 4,
+        'k_mel_gemm': 3 * nf * H * 4 + nf * 150 * 4,
+        'k_mel_finish': nf * 150 * 4,
+        'k_mel_unwarp': nf * 150 * 4 + nf * H * 4 + 0.4 * nf * 2 * 513 * 4,
+        'k_analysis<noise_logsq>': getattr(plan, 'n_noise', 0) * 4 + nf * 25,
+        'k_noise_gain': nf * 9,
+        'k_synthesis_compressed': nf * H * 4 + 0.4 * nf * 2 * 513 * 4 + getattr(plan, 'n_noise', 0) * 4 + nf * 45
+                                  + getattr(plan, 'n_out', 0) * 4,
+    }
+    kernels = []
+    for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        per_step_ms = ms / prof_steps
+        kb = float(kbytes.get(name, 0))
+        gbs = kb / (per_step_ms * 1e-3) / 1e9 if per_step_ms > 0 else 0.0
+        kernels.append(dict(name=name, launches_per_step=cnt // prof_steps, ms_per_step=per_step_ms,
+                            algorithmic_bytes_per_step=int(kb), gbs=gbs, frac=gbs / peak))
+    dom = kernels[0]
     ms_per_step = total_ms / a.steps
     value = frames_all / (ms_per_step * 1e-3)
+    chain_bytes = bytes_ana + bytes_syn
     line = {
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64 analysis butterflies / f32 synthesis; %s feature storage' % a.feat_dtype,
+        'dtype': 'f64 analysis butterflies, f32 elsewhere; f32 storage',
         'data': 'synthetic',
         'config': {'workload': workload, 'fs': FS, 'fft_len': FFT_LEN, 'frames_per_gpu_per_step': plan.nfrm,
-                   'mean_shift_samples': round(plan.mean_shift, 1), 'l2_note': 'per-step working set %.1f GB >> 126 MB L2'
-                   % ((k_ana['bytes']) / 1e9), 'parallelism': 'utterance-sharded x%d' % world},
+                   'mean_shift_samples': round(plan.mean_shift, 1),
+                   'l2_note': 'per-step intermediates %.1f GB in HBM >> 126 MB L2' % (3 * nf * H * 4 / 1e9),
+                   'parallelism': 'utterance-sharded x%d' % world},
         'e2e': {'value': e_frames_all / (e_secs / e_steps), 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d),
-                'd2h_bytes_per_step': int(d2h), 'utts_per_gpu_per_step': len(e_utts),
-                'api': 'analysis_lossless_batch -> synthesis_from_lossless_batch (float64 NumPy in/out)'},
+                'd2h_bytes_per_step': int(d2h), 'utts_per_gpu_per_step': len(e_utts), 'api': api},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s',
                      'frac': dom['frac'], 'traffic': None, 'peak_source': peak_src,
-                     'algorithmic_bytes_per_launch': int(dom['bytes']), 'ms_per_launch': dom['ms']},
-        'kernels': [k_ana, k_syn],
+                     'algorithmic_bytes_per_launch': int(dom['algorithmic_bytes_per_step'] / max(dom['launches_per_step'], 1)),
+                     'ms_per_launch': dom['ms_per_step'] / max(dom['launches_per_step'], 1)},
+        'halves': {'analysis_ms': ana_ms, 'synthesis_ms': syn_ms,
+                   'chain_algorithmic_bytes_per_step': int(chain_bytes),
+                   'chain_gbs': chain_bytes / (ms_per_step * 1e-3) / 1e9},
+        'kernels': kernels,
         'clocks': clocks,
     }
     if cpu is not None:

@@ -53,6 +53,10 @@ const char* mpb_last_error(void);
 const char* mpb_version(void);
 /* number of kernels this library has launched since the context was created (bench accounting)   */
 int64_t mpb_launch_count(const mpb_ctx* ctx);
+/* Optional per-kernel device timing: between begin and end every kernel launch of this context is bracketed
+ * by CUDA events on its own stream; end synchronises and writes "name count total_ms\n" lines into buf.     */
+int mpb_profile_begin(mpb_ctx* ctx);
+int mpb_profile_end(mpb_ctx* ctx, char* buf, int64_t buf_len);
 
 /* ---- lossless analysis --------------------------------------------------------------------- */
 /*

@@ -29,6 +29,8 @@ SIGNATURES = {
     'mpb_last_error': [],
     'mpb_version': [],
     'mpb_launch_count': [_vp],
+    'mpb_profile_begin': [_vp],
+    'mpb_profile_end': [_vp, C.c_char_p, _i64],
     'mpb_analysis_lossless_dev': [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int,
                                   _vp, _vp, _vp, C.c_int],
     'mpb_analysis_lossless_host': [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp],
@@ -112,6 +114,21 @@ def ctx(device=None):
 
 def launch_count(device=None):
     return int(lib().mpb_launch_count(ctx(device)))
+
+
+def profile_begin(device=None):
+    check(lib().mpb_profile_begin(ctx(device)))
+
+
+def profile_end(device=None):
+    """{kernel name: (launch count, total device ms)} since profile_begin."""
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().mpb_profile_end(ctx(device), buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(' ', 2)
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def ptr(a):

@@ -85,6 +85,37 @@ int mpb_destroy(mpb_ctx* ctx) {
 
 int64_t mpb_launch_count(const mpb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int mpb_profile_begin(mpb_ctx* ctx) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    for (auto& r : ctx->timer.recs) { ctx->timer.pool.push_back(r.a); ctx->timer.pool.push_back(r.b); }
+    ctx->timer.recs.clear();
+    ctx->timer.on = true;
+    return MPB_OK;
+}
+
+int mpb_profile_end(mpb_ctx* ctx, char* buf, int64_t buf_len) {
+    if (!ctx || !buf || buf_len < 1) return fail(MPB_ERR_BAD_ARG, "NULL argument");
+    ctx->timer.on = false;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    std::map<std::string, std::pair<int, double>> agg;
+    for (auto& r : ctx->timer.recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto& e = agg[r.name]; e.first += 1; e.second += ms; }
+        ctx->timer.pool.push_back(r.a); ctx->timer.pool.push_back(r.b);
+    }
+    ctx->timer.recs.clear();
+    std::string out;
+    char line[256];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof(line), "%s %d %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if ((int64_t)out.size() + 1 > buf_len) return fail(MPB_ERR_BAD_ARG, "profile buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return MPB_OK;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
@@ -109,8 +140,7 @@ int mpb::analysis_common(mpb_ctx* ctx, void* stream, const void* sig, int sig_dt
     if (rc != MPB_OK) return rc;
     a.out_a = out_a; a.out_b = out_b; a.out_c = out_c; a.out_dtype = out_dtype;
     a.mode = mode; a.num_sms = ctx->num_sms;
-    CU(launch_analysis(a, (cudaStream_t)stream));
-    ctx->launches += 1;
+    LAUNCH(ctx, (cudaStream_t)stream, mode == MODE_FFT ? "k_analysis<fft>" : "k_analysis", launch_analysis(a, (cudaStream_t)stream));
     return MPB_OK;
 }
 
@@ -257,8 +287,7 @@ int mpb_synthesis_lossless_dev(mpb_ctx* ctx, void* stream, const void* mag, cons
     int rc = get_twiddles(ctx, fft_len, compute_dtype, &a.tw);
     if (rc != MPB_OK) return rc;
     a.out = out; a.out_dtype = out_dtype; a.n_out = n_out; a.num_sms = ctx->num_sms;
-    CU(launch_synthesis_lossless(a, (cudaStream_t)stream));
-    ctx->launches += 1;
+    LAUNCH(ctx, (cudaStream_t)stream, "k_synthesis_lossless", launch_synthesis_lossless(a, (cudaStream_t)stream));
     return MPB_OK;
 }
 

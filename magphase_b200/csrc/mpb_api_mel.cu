@@ -103,8 +103,8 @@ int mpb_mel_compress_dev(mpb_mel* m, void* stream, const void* mag, const void* 
         a.out_real = (char*)out_real_mel + oes * f0 * m->phase_dim;
         a.out_imag = (char*)out_imag_mel + oes * f0 * m->phase_dim;
         a.out_dtype = out_dtype;
-        CU(launch_mel_compress(a, (cudaStream_t)stream));
-        m->ctx->launches += 2;
+        LAUNCH(m->ctx, (cudaStream_t)stream, "k_mel_gemm", launch_mel_gemm(a, (cudaStream_t)stream));
+        LAUNCH(m->ctx, (cudaStream_t)stream, "k_mel_finish", launch_mel_finish(a, (cudaStream_t)stream));
     }
     return MPB_OK;
 }

@@ -88,7 +88,7 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
     u.need_ph = need_ph; u.nfrm = n_rows; u.n_mag = s->n_mag; u.n_ph = s->n_ph;
     u.u_mag = s->u_mag; u.H = s->H; u.u_ph = s->u_ph; u.HB = s->HB;
     u.out_mag = (float*)s->unw[0].p; u.out_real = (float*)s->unw[1].p; u.out_imag = (float*)s->unw[2].p;
-    CU(launch_mel_unwarp(u, st));
+    LAUNCH(ctx, st, "k_mel_unwarp", launch_mel_unwarp(u, st));
 
     const void* tw = nullptr;
     int rc = get_twiddles(ctx, s->fft_len, MPB_F32, &tw);
@@ -99,7 +99,7 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
     n.nfrm = fr->nfrm; n.fft_len = s->fft_len; n.compute_dtype = MPB_F32; n.tw = tw;
     n.out_a = s->logsq.p; n.out_b = nullptr; n.out_c = nullptr; n.out_dtype = MPB_F64; n.mode = MODE_LOGSQ;
     n.num_sms = ctx->num_sms;
-    CU(launch_noise_stats(n, st));
+    LAUNCH(ctx, st, "k_analysis<noise_logsq>", launch_noise_stats(n, st));
 
     SynthCompArgs a;
     a.m_mag = u.out_mag; a.m_real = u.out_real; a.m_imag = u.out_imag; a.H = s->H; a.HB = s->HB;
@@ -112,9 +112,8 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
     a.runs = (const OlaRun*)runs; a.n_runs = n_runs; a.nfrm = fr->nfrm;
     a.fft_len = s->fft_len; a.per_linear = per_linear; a.tw = tw;
     a.out = out; a.out_dtype = out_dtype; a.n_out = n_out; a.num_sms = ctx->num_sms;
-    CU(launch_noise_gain(a, st));
-    CU(launch_synthesis_compressed(a, st));
-    ctx->launches += 4;
+    LAUNCH(ctx, st, "k_noise_gain", launch_noise_gain(a, st));
+    LAUNCH(ctx, st, "k_synthesis_compressed", launch_synthesis_compressed(a, st));
     return MPB_OK;
 }
 

@@ -35,6 +35,17 @@ struct DevBuf {   // grow-only device scratch
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct KernelTimer {   // optional per-kernel CUDA-event timing (mpb_profile_begin / mpb_profile_end)
+    struct Rec { const char* name; cudaEvent_t a, b; };
+    bool on = false;
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+};
+
 struct mpb_ctx {
     int device = 0;
     int num_sms = 0;
@@ -44,7 +55,18 @@ struct mpb_ctx {
     std::mutex tw_mu;
     int64_t launches = 0;
     DevBuf scratch[16];
+    KernelTimer timer;
 };
+
+// Launch `expr` (returns cudaError_t) on stream `st`, bracketed by events when profiling is on.
+#define LAUNCH(ctx, st, kname, expr)                                                           \
+    do {                                                                                       \
+        cudaEvent_t _ea = nullptr, _eb = nullptr;                                              \
+        if ((ctx)->timer.on) { _ea = (ctx)->timer.get(); _eb = (ctx)->timer.get(); cudaEventRecord(_ea, (st)); } \
+        CU(expr);                                                                              \
+        if ((ctx)->timer.on) { cudaEventRecord(_eb, (st)); (ctx)->timer.recs.push_back({kname, _ea, _eb}); } \
+        (ctx)->launches += 1;                                                                  \
+    } while (0)
 
 namespace mpb {
 inline bool fft_len_ok(int n) { return n == 1024 || n == 2048 || n == 4096; }

@@ -55,7 +55,8 @@ struct MelArgs {
 };
 cudaError_t build_warp_matrix(int fft_len, int n_out, double alpha, float* wt32, double* scratch64, int ld,
                               cudaStream_t st);
-cudaError_t launch_mel_compress(const MelArgs& a, cudaStream_t st);
+cudaError_t launch_mel_gemm(const MelArgs& a, cudaStream_t st);
+cudaError_t launch_mel_finish(const MelArgs& a, cudaStream_t st);
 
 // ---- mel un-warping + compressed synthesis (mpb_unwarp.cu, mpb_synth_comp.cu) ----
 struct UnwarpArgs {

@@ -192,7 +192,7 @@ k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64
     }
 }
 
-cudaError_t launch_mel_compress(const MelArgs& a, cudaStream_t st) {
+cudaError_t launch_mel_gemm(const MelArgs& a, cudaStream_t st) {
     const int H = a.fft_len / 2 + 1;
     const int n_slices = (H + MEL_KSLICE - 1) / MEL_KSLICE;
     const int ctiles = (a.ncp_max + GEMM_CT - 1) / GEMM_CT;
@@ -212,8 +212,12 @@ cudaError_t launch_mel_compress(const MelArgs& a, cudaStream_t st) {
                                                    a.nfrm, H, a.wt_mag, a.ld_mag, a.wt_ph, a.ld_ph, a.partial, n_slices,
                                                    a.ncp_max);
     }
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mel_finish(const MelArgs& a, cudaStream_t st) {
+    const int H = a.fft_len / 2 + 1;
+    const int n_slices = (H + MEL_KSLICE - 1) / MEL_KSLICE;
     dim3 g2((unsigned)((a.nfrm + 3) / 4), 3);
     if (a.out_dtype == MPB_F64)
         k_mel_finish<double><<<g2, 128, 0, st>>>(a.partial, n_slices, a.ncp_max, a.nfrm, a.cos_mag, a.n_mag, a.cos_ph,

@@ -99,3 +99,90 @@ class LosslessPlan:
             self.ctx, _stream(), _dp(feats[0]), _dp(feats[1]), _dp(feats[2]), feat_dt, _dp(self.d_pm), self.nfrm,
             _dp(self.d_out_off), _dp(self.d_t0), self.n_utt, _dp(self.d_runs), self.n_runs, self.fft_len, compute,
             _dp(d_out), out_dt, self.n_out))
+
+
+class CompressedPlan:
+    """Bookkeeping for analysis_compressed -> synthesis_from_compressed (BASELINE config 2: 60/45/45, variable
+    rate, no output HPF) of a list of utterances on one GPU.  Everything the host mirror computes per call
+    (frame geometry, lf0, synthesis shifts, noise frame geometry, OLA runs) is computed once and uploaded."""
+
+    def __init__(self, l_nsmpls, l_pm_smpls, l_voi, fs, fft_len=None, mag_dim=60, phase_dim=45, device=None,
+                 ola_target_frames=32, noise_seed=1234):
+        self.fs = fs
+        self.fft_len = mp.define_fft_len(fs) if fft_len is None else fft_len
+        self.H = self.fft_len // 2 + 1
+        self.mag_dim, self.phase_dim = mag_dim, phase_dim
+        self.device = torch.device('cuda', _lib.default_device() if device is None else device)
+        self.ctx = _lib.ctx(self.device.index)
+        self.mel = mp._MelPlan.get(fs, self.fft_len, mag_dim, phase_dim, None)
+        self.syn = mp._SynPlan.get(fs, self.fft_len, mag_dim, phase_dim, None)
+        n_utt = len(l_nsmpls)
+        sig_off = np.zeros(n_utt + 1, dtype=np.int64)
+        centre, left, right, voi8, self.l_lf0 = [], [], [], [], []
+        for u in range(n_utt):
+            P, v_shift, v_rights = mp.frame_geometry(l_pm_smpls[u], l_nsmpls[u])
+            sig_off[u + 1] = sig_off[u] + l_nsmpls[u]
+            centre.append(P[1:-1] + sig_off[u]); left.append(v_shift); right.append(v_rights)
+            v_f0 = mp.shift_to_f0(v_shift, np.asarray(l_voi[u], dtype=np.float64), fs, b_smooth=False)
+            v_voi, v_lf0 = mp._lf0_smoothed(v_f0)
+            voi8.append(v_voi > 0); self.l_lf0.append(v_lf0)
+        self.n_utt, self.n_sig = n_utt, int(sig_off[-1])
+        self.nfrm = int(sum(a.size for a in left))
+        self.mean_shift = float(np.mean(np.concatenate(left)))
+        arrs, self.l_ns_len = mp.compressed_synthesis_geometry(self.l_lf0, [a.size for a in left], fs, self.fft_len)
+        self.n_noise = int(sum(self.l_ns_len))
+        self.n_out = int(arrs['utt_out_off'][-1])
+        n_runs = C.c_int64()
+        lib = _lib.lib()
+        _lib.check(lib.mpb_plan_ola_runs(_lib.ptr(arrs['pm']), _lib.ptr(arrs['utt_frm_off']), n_utt, self.fft_len,
+                                         ola_target_frames, None, 0, C.byref(n_runs)))
+        runs = np.zeros((max(n_runs.value, 1), 4), dtype=np.int32)
+        _lib.check(lib.mpb_plan_ola_runs(_lib.ptr(arrs['pm']), _lib.ptr(arrs['utt_frm_off']), n_utt, self.fft_len,
+                                         ola_target_frames, _lib.ptr(runs), n_runs.value, C.byref(n_runs)))
+        self.n_runs = int(n_runs.value)
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.device)
+        self.d_centre = up(np.concatenate(centre), np.int64)
+        self.d_left = up(np.concatenate(left), np.int32)
+        self.d_right = up(np.concatenate(right), np.int32)
+        self.d_voi_ana = up(np.concatenate(voi8), np.uint8)
+        self.d_runs = up(runs, np.int32)
+        self.d_need = up(arrs.pop('need_ph'), np.uint8)
+        self._keep = {k: (up(v, v.dtype) if v is not None else None) for k, v in arrs.items()}
+        self.frames = _lib.SynFrames(nfrm=self.nfrm, n_utt=n_utt,
+                                     **{k: (_dp(v) if v is not None else None) for k, v in self._keep.items()})
+        rs = np.random.RandomState(noise_seed)
+        self.h_noise = [rs.uniform(-1, 1, n) for n in self.l_ns_len]
+        self.d_noise = up(np.concatenate(self.h_noise), np.float32)
+        # intermediates that live in HBM between the two halves
+        self.d_lossless = tuple(torch.empty((self.nfrm, self.H), dtype=torch.float32, device=self.device) for _ in range(3))
+        self.d_mel = (torch.empty((self.nfrm, mag_dim), dtype=torch.float32, device=self.device),
+                      torch.empty((self.nfrm, phase_dim), dtype=torch.float32, device=self.device),
+                      torch.empty((self.nfrm, phase_dim), dtype=torch.float32, device=self.device))
+        self.d_out = torch.empty(self.n_out, dtype=torch.float32, device=self.device)
+
+    # algorithmic HBM bytes per pass of the two halves (SURVEY.md 8(d)): what the reference API contract moves
+    def analysis_bytes(self):
+        return self.n_sig * 4 + self.nfrm * 17 + self.nfrm * (self.mag_dim + 2 * self.phase_dim) * 4
+
+    def synthesis_bytes(self):
+        return self.nfrm * (self.mag_dim + 2 * self.phase_dim) * 4 + self.nfrm * 45 + self.n_noise * 4 + self.n_out * 4
+
+    def analysis(self, d_sig, compute=MPB_F64):
+        lib = _lib.lib()
+        sig_dt = MPB_F64 if d_sig.dtype == torch.float64 else MPB_F32
+        f = self.d_lossless
+        _lib.check(lib.mpb_analysis_lossless_dev(
+            self.ctx, _stream(), _dp(d_sig), sig_dt, self.n_sig, _dp(self.d_centre), _dp(self.d_left), _dp(self.d_right),
+            None, self.nfrm, self.fft_len, compute, _dp(f[0]), _dp(f[1]), _dp(f[2]), MPB_F32))
+        _lib.check(lib.mpb_mel_compress_dev(self.mel.handle, _stream(), _dp(f[0]), _dp(f[1]), _dp(f[2]), MPB_F32,
+                                            _dp(self.d_voi_ana), self.nfrm, _dp(self.d_mel[0]), _dp(self.d_mel[1]),
+                                            _dp(self.d_mel[2]), MPB_F32))
+        return self.d_mel
+
+    def synthesis(self, d_mel=None):
+        m = self.d_mel if d_mel is None else d_mel
+        _lib.check(_lib.lib().mpb_synthesis_compressed_dev(
+            self.syn.handle, _stream(), _dp(m[0]), _dp(m[1]), _dp(m[2]), MPB_F32, self.nfrm, _dp(self.d_need),
+            _dp(self.d_noise), self.n_noise, C.byref(self.frames), _dp(self.d_runs), self.n_runs, 0, _dp(self.d_out),
+            MPB_F32, self.n_out))
+        return self.d_out

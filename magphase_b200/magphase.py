@@ -617,32 +617,23 @@ def synthesis_from_compressed(m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0, fs, 
                                            alpha_phase=alpha_phase, b_out_hpf=b_out_hpf)[0]
 
 
-def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True, b_fbank_mel=False, b_const_rate=False,
-                                    per_phase_type='magphase', alpha_phase=None, b_out_hpf=True, l_noise=None):
-    """Batched synthesis_from_compressed; l_feats is a list of (m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0).
-    l_noise: optional list of per-utterance noise vectors (else drawn from np.random, utterance by utterance)."""
-    if b_fbank_mel:
-        raise ValueError('b_fbank_mel=True (experimental filter-bank warping) is outside the CUDA hot path')
-    if per_phase_type not in ('magphase', 'linear'):
-        raise NotImplementedError("per_phase_type=%r: only 'magphase' and 'linear' run on the CUDA path" % (per_phase_type,))
-    if fft_len is None:
-        fft_len = define_fft_len(fs)
-    mag_dim = np.shape(l_feats[0][0])[1]
-    phase_dim = np.shape(l_feats[0][1])[1]
-    plan = _SynPlan.get(fs, fft_len, mag_dim, phase_dim, alpha_phase)
+def compressed_synthesis_geometry(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win=True, b_const_rate=False):
+    """Host bookkeeping of synthesis_from_compressed for a batch (src/magphase.py:846-848, 861-870, 879-882,
+    886-896, 968-971, 34-62): everything integer / float64 that the kernels consume as arrays.
+    Returns (dict of C-contiguous arrays for mpb_syn_frames + 'need_ph', list of per-utterance noise lengths)."""
     half = fft_len // 2
-    n_utt = len(l_feats)
+    n_utt = len(l_lf0)
     frm_off = np.zeros(n_utt + 1, dtype=np.int64)
     out_off = np.zeros(n_utt + 1, dtype=np.int64)
     row_off, noise_off = 0, 0
     acc = {k: [] for k in ('pm', 'ncentre', 'nleft', 'nright', 'voi', 'nkind', 'win_a', 'win_b', 'row0', 'row1', 'roww',
-                           'need', 'noise', 'mag', 'real', 'imag', 't0')}
-    for u, (m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0) in enumerate(l_feats):
-        m_mag_mel_log = np.asarray(m_mag_mel_log, dtype=np.float64)
-        if m_mag_mel_log.shape[1] != mag_dim or np.shape(m_real_mel)[1] != phase_dim or np.shape(m_imag_mel)[1] != phase_dim:
-            raise ValueError('all utterances of a batch must share mag_dim / phase_dim')
-        n_c = m_mag_mel_log.shape[0]
-        v_f0 = np.exp(np.asarray(v_lf0, dtype=np.float64))
+                           'need', 't0')}
+    l_ns_len = []
+    for u in range(n_utt):
+        n_c = int(l_nrows[u])
+        v_f0 = np.exp(np.asarray(l_lf0[u], dtype=np.float64))
+        if v_f0.size != n_c:
+            raise ValueError('lf0 length must equal the number of feature rows')
         v_voi = v_f0 > 1.0                                        # :847
         v_shift = f0_to_shift(v_f0, fs)
         if b_const_rate:
@@ -660,12 +651,6 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
         v_shift = v_shift.astype(int)                             # truncation BEFORE the cumsum (:879-880)
         v_pm = np.cumsum(v_shift)
         ns_len = int(v_pm[-1] + (v_pm[-1] - v_pm[-2]))
-        if l_noise is None:
-            v_ns = np.random.uniform(-1, 1, ns_len)               # :883
-        else:
-            v_ns = np.asarray(l_noise[u], dtype=np.float64)
-            if v_ns.size != ns_len:
-                raise ValueError('noise length %d != %d' % (v_ns.size, ns_len))
         P, n_left, n_right = frame_geometry(v_pm, ns_len)
         if np.any(n_left > half) or np.any(n_right >= half):      # frame_shift() would get a negative pad (src/libaudio.py:137-140)
             raise ValueError('negative dimensions are not allowed')
@@ -681,9 +666,8 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
         acc['row0'].append(r0 + row_off)
         if b_const_rate:
             acc['row1'].append(r1 + row_off); acc['roww'].append(w)
-        acc['need'].append(need); acc['noise'].append(v_ns); acc['t0'].append(t0)
-        acc['mag'].append(m_mag_mel_log)
-        acc['real'].append(np.asarray(m_real_mel, dtype=np.float64)); acc['imag'].append(np.asarray(m_imag_mel, dtype=np.float64))
+        acc['need'].append(need); acc['t0'].append(t0)
+        l_ns_len.append(ns_len)
         row_off += n_c
         noise_off += ns_len
     cat = lambda k, dt: np.ascontiguousarray(np.concatenate(acc[k]), dtype=dt)
@@ -692,10 +676,41 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
                 win_a=cat('win_a', np.int32), win_b=cat('win_b', np.int32), row0=cat('row0', np.int32),
                 row1=cat('row1', np.int32) if b_const_rate else None,
                 roww=cat('roww', np.float32) if b_const_rate else None,
-                utt_frm_off=frm_off, utt_out_off=out_off, utt_t0=np.ascontiguousarray(acc['t0'], dtype=np.int32))
-    fr = _lib.SynFrames(nfrm=int(frm_off[-1]), n_utt=n_utt, **{k: _lib.ptr(v) for k, v in arrs.items()})
-    mag, real, imag = cat('mag', np.float64), cat('real', np.float64), cat('imag', np.float64)
-    need, noise = cat('need', np.uint8), cat('noise', np.float64)
+                utt_frm_off=frm_off, utt_out_off=out_off, utt_t0=np.ascontiguousarray(acc['t0'], dtype=np.int32),
+                need_ph=cat('need', np.uint8))
+    return arrs, l_ns_len
+
+
+def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True, b_fbank_mel=False, b_const_rate=False,
+                                    per_phase_type='magphase', alpha_phase=None, b_out_hpf=True, l_noise=None):
+    """Batched synthesis_from_compressed; l_feats is a list of (m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0).
+    l_noise: optional list of per-utterance noise vectors (else drawn from np.random, utterance by utterance)."""
+    if b_fbank_mel:
+        raise ValueError('b_fbank_mel=True (experimental filter-bank warping) is outside the CUDA hot path')
+    if per_phase_type not in ('magphase', 'linear'):
+        raise NotImplementedError("per_phase_type=%r: only 'magphase' and 'linear' run on the CUDA path" % (per_phase_type,))
+    if fft_len is None:
+        fft_len = define_fft_len(fs)
+    mag_dim = np.shape(l_feats[0][0])[1]
+    phase_dim = np.shape(l_feats[0][1])[1]
+    for f in l_feats:
+        if np.shape(f[0])[1] != mag_dim or np.shape(f[1])[1] != phase_dim or np.shape(f[2])[1] != phase_dim:
+            raise ValueError('all utterances of a batch must share mag_dim / phase_dim')
+    plan = _SynPlan.get(fs, fft_len, mag_dim, phase_dim, alpha_phase)
+    n_utt = len(l_feats)
+    arrs, l_ns_len = compressed_synthesis_geometry([f[3] for f in l_feats], [np.shape(f[0])[0] for f in l_feats], fs,
+                                                   fft_len, b_voi_ap_win=b_voi_ap_win, b_const_rate=b_const_rate)
+    if l_noise is None:
+        l_noise = [np.random.uniform(-1, 1, n) for n in l_ns_len]          # :883, utterance by utterance
+    for v, n in zip(l_noise, l_ns_len):
+        if np.size(v) != n:
+            raise ValueError('noise length %d != %d' % (np.size(v), n))
+    need = arrs.pop('need_ph')
+    out_off = arrs['utt_out_off']
+    fr = _lib.SynFrames(nfrm=int(arrs['utt_frm_off'][-1]), n_utt=n_utt, **{k: _lib.ptr(v) for k, v in arrs.items()})
+    cat = lambda i: np.ascontiguousarray(np.concatenate([np.asarray(f[i], dtype=np.float64) for f in l_feats], axis=0))
+    mag, real, imag = cat(0), cat(1), cat(2)
+    noise = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in l_noise]))
     out = np.empty(int(out_off[-1]), dtype=np.float64)
     _lib.check(_lib.lib().mpb_synthesis_compressed_host(
         plan.handle, _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), mag.shape[0], _lib.ptr(need), _lib.ptr(noise),
