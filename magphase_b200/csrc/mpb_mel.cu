@@ -99,25 +99,36 @@ k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __
         reinterpret_cast<float4*>(Bs)[i] =
             __ldg(reinterpret_cast<const float4*>(wt + (size_t)(k0 + kk) * ld + ctile * GEMM_CT) + c4);
     }
-    // ---- stage the log-periodogram tile transposed: Ls[kk][f]; a warp takes 4 frames x 32 bins per step ----
-    for (int fb = warp * 4; fb < GEMM_FT; fb += 16) {
+    // ---- stage the log-periodogram tile transposed: Ls[kk][f]; a warp takes 4 frames x 32 bins per step.
+    // All 64 loads of a half tile are issued before the first use (one DRAM latency per half, not per step). ----
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        float raw[4][4][4];                              // [frame group][bin chunk][frame in group]
 #pragma unroll
-        for (int kc = 0; kc < MEL_KSLICE; kc += 32) {
-            const int k = k0 + kc + lane;
-            float4 v;
-            float* pv = &v.x;
+        for (int g = 0; g < 4; ++g)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int64_t f = f0 + fb + r;
-                float x = 0.0f;
-                if (f < nfrm && k < H) {
-                    const float raw = (float)__ldcs(src + f * (int64_t)H + k);
-                    x = stream == 0 ? log_periodogram<3>(raw) : log_periodogram<2>(raw);
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int64_t f = f0 + half * 64 + g * 16 + warp * 4 + r;
+                    const int k = k0 + c * 32 + lane;
+                    raw[g][c][r] = (f < nfrm && k < H) ? (float)__ldcs(src + f * (int64_t)H + k) : 0.0f;
                 }
-                pv[r] = x;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = k0 + c * 32 + lane;
+                float4 v;
+                float* pv = &v.x;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int64_t f = f0 + half * 64 + g * 16 + warp * 4 + r;
+                    const float x = stream == 0 ? log_periodogram<3>(raw[g][c][r]) : log_periodogram<2>(raw[g][c][r]);
+                    pv[r] = (f < nfrm && k < H) ? x : 0.0f;
+                }
+                *reinterpret_cast<float4*>(Ls + (c * 32 + lane) * GEMM_LDL + half * 64 + g * 16 + warp * 4) = v;
             }
-            *reinterpret_cast<float4*>(Ls + (kc + lane) * GEMM_LDL + fb) = v;
-        }
     }
     __syncthreads();
 

@@ -47,13 +47,20 @@ cudaError_t launch_noise_gain(const SynthCompArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-__device__ __forceinline__ float lerp_row(const float* __restrict__ r0, const float* __restrict__ r1, float w, int k) {
-    const float a = __ldg(r0 + k);
-    return r1 ? fmaf(w, __ldg(r1 + k) - a, a) : a;
+__device__ __forceinline__ float lerp_row(const float* r0, const float* r1, float w, int k) {
+    const float a = r0[k];
+    return r1 ? fmaf(w, r1[k] - a, a) : a;
 }
 
+// asynchronous 4-byte global -> shared copies (rows of the un-warped features are only 4-byte aligned)
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 template <typename TO, int N>
-__global__ void __launch_bounds__(FftGeom<float, N>::TPB, 640 / FftGeom<float, N>::TPB)
+__global__ void __launch_bounds__(FftGeom<float, N>::TPB, 512 / FftGeom<float, N>::TPB)
 k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
     using T = float;
     using G = FftGeom<T, N>;
@@ -66,6 +73,11 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
     T* acc = reinterpret_cast<T*>(buf + G::BUF_ELEMS);
     T2* tw2f = reinterpret_cast<T2*>(acc + N);
     T2* tw2i = tw2f + G::TW2_ELEMS;
+    // feature rows of the current frame, prefetched with cp.async while the noise FFT runs
+    const int H = a.H, HB = a.HB;
+    const int rowlen = H + 2 * HB;
+    float* srow0 = reinterpret_cast<float*>(tw2i + G::TW2_ELEMS);      // [mag H | real HB | imag HB]
+    float* srow1 = a.row1 ? srow0 + rowlen : nullptr;
     const int t = threadIdx.x;
     const T scale = (T)1 / (T)N;
     FftCtx<T> ff, fi;
@@ -73,7 +85,6 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
     fft_setup<T, N, true>(fi, tw2i, (const T2*)a.tw, t);
     T2* pk = buf + G::nphys(t);
     T2* pmk = buf + G::nphys(M - t);
-    const int H = a.H, HB = a.HB;
     const float* __restrict__ tabP = a.tab;
     const float* __restrict__ tabAv = a.tab + H;
     const float* __restrict__ tabAu = a.tab + 2 * H;
@@ -95,18 +106,40 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
             const int p = a.pm[g];
             const bool voiced = a.voi[g] != 0;
 
+            // ---- 0. kick off the asynchronous copy of this frame's un-warped feature rows ----
+            {
+                const float* g0 = a.m_mag + (int64_t)a.row0[g] * H;
+                for (int k = t; k < H; k += TPB) cp_async4(srow0 + k, g0 + k);
+                if (voiced && !a.per_linear) {
+                    const float* gr = a.m_real + (int64_t)a.row0[g] * HB;
+                    const float* gi2 = a.m_imag + (int64_t)a.row0[g] * HB;
+                    for (int k = t; k < HB; k += TPB) { cp_async4(srow0 + H + k, gr + k); cp_async4(srow0 + H + HB + k, gi2 + k); }
+                }
+                if (srow1) {
+                    const float* g1 = a.m_mag + (int64_t)a.row1[g] * H;
+                    for (int k = t; k < H; k += TPB) cp_async4(srow1 + k, g1 + k);
+                    if (voiced && !a.per_linear) {
+                        const float* gr = a.m_real + (int64_t)a.row1[g] * HB;
+                        const float* gi2 = a.m_imag + (int64_t)a.row1[g] * HB;
+                        for (int k = t; k < HB; k += TPB) { cp_async4(srow1 + H + k, gr + k); cp_async4(srow1 + H + HB + k, gi2 + k); }
+                    }
+                }
+            }
+
             // ---- 1. noise frame -> spectrum (natural padded layout in buf) ----
             T2 v[16];
             load_frame<T, float, N>(a.noise, a.n_noise, a.ncentre[g], a.nleft[g], a.nright[g], (int)a.nkind[g], buf, v, t);
             fft_m<T, N, false>(v, buf, ff, t);
 
             // ---- 2. mix periodic + aperiodic per bin pair (k, M-k), pack for the inverse transform ----
-            const float* __restrict__ mag0 = a.m_mag + (int64_t)a.row0[g] * H;
-            const float* __restrict__ mag1 = a.row1 ? a.m_mag + (int64_t)a.row1[g] * H : nullptr;
-            const float* __restrict__ re0 = a.m_real + (int64_t)a.row0[g] * HB;
-            const float* __restrict__ re1 = a.row1 ? a.m_real + (int64_t)a.row1[g] * HB : nullptr;
-            const float* __restrict__ im0 = a.m_imag + (int64_t)a.row0[g] * HB;
-            const float* __restrict__ im1 = a.row1 ? a.m_imag + (int64_t)a.row1[g] * HB : nullptr;
+            cp_async_wait_all();
+            __syncthreads();                                   // feature rows have landed for every thread
+            const float* mag0 = srow0;
+            const float* mag1 = srow1;
+            const float* re0 = srow0 + H;
+            const float* re1 = srow1 ? srow1 + H : nullptr;
+            const float* im0 = srow0 + H + HB;
+            const float* im1 = srow1 ? srow1 + H + HB : nullptr;
             const float rw = a.roww ? a.roww[g] : 0.0f;
             const float gi = voiced ? giv : giu;
             const float* __restrict__ tabA = voiced ? tabAv : tabAu;
@@ -194,7 +227,8 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
 template <typename TO, int N>
 static cudaError_t launch_sc_t(const SynthCompArgs& a, cudaStream_t st) {
     using G = FftGeom<float, N>;
-    const size_t smem = sizeof(float2) * (G::BUF_ELEMS + 2 * G::TW2_ELEMS) + sizeof(float) * N;
+    const size_t smem = sizeof(float2) * (G::BUF_ELEMS + 2 * G::TW2_ELEMS) + sizeof(float) * N +
+                        sizeof(float) * (size_t)(a.H + 2 * a.HB) * (a.row1 ? 2 : 1);
     auto kern = k_synthesis_compressed<TO, N>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

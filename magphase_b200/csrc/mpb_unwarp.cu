@@ -18,12 +18,12 @@ constexpr int UW_BT = 128;            // bins per CTA tile
 constexpr int UW_LDX = UW_FT + 4;     // pitch of the transposed feature tile
 
 template <typename TI>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_mel_unwarp(const TI* __restrict__ mag_mel, const TI* __restrict__ real_mel, const TI* __restrict__ imag_mel,
              const uint8_t* __restrict__ need_ph, int64_t nfrm, int n_mag, int n_ph,
              const float* __restrict__ u_mag, int H, const float* __restrict__ u_ph, int HB,
              float* __restrict__ out_mag, float* __restrict__ out_real, float* __restrict__ out_imag,
-             int tiles_mag, int tiles_ph) {
+             int tiles_mag, int tiles_ph, int kmax) {
     extern __shared__ __align__(16) float smem_f[];
     const int tid = threadIdx.x;
     int stream, btile;
@@ -37,7 +37,7 @@ k_mel_unwarp(const TI* __restrict__ mag_mel, const TI* __restrict__ real_mel, co
     const int64_t f0 = (int64_t)blockIdx.x * UW_FT;
     const int b0 = btile * UW_BT;
     float* Xs = smem_f;                                   // [K][UW_LDX]  (transposed: coefficient-major)
-    float* Us = smem_f + MEL_MAX_COEFFS * UW_LDX;         // [K][UW_BT]
+    float* Us = smem_f + kmax * UW_LDX;                   // [K][UW_BT]
 
     if (stream != 0) {                                    // skip tiles where no frame needs phase
         bool any = false;
@@ -91,7 +91,8 @@ k_mel_unwarp(const TI* __restrict__ mag_mel, const TI* __restrict__ real_mel, co
 
 cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st) {
     const int tiles_mag = (a.H + UW_BT - 1) / UW_BT, tiles_ph = (a.HB + UW_BT - 1) / UW_BT;
-    const size_t smem = sizeof(float) * (MEL_MAX_COEFFS * UW_LDX + MEL_MAX_COEFFS * UW_BT);
+    const int kmax = a.n_mag > a.n_ph ? a.n_mag : a.n_ph;
+    const size_t smem = sizeof(float) * ((size_t)kmax * UW_LDX + (size_t)kmax * UW_BT);
     dim3 grid((unsigned)((a.nfrm + UW_FT - 1) / UW_FT), (unsigned)(tiles_mag + 2 * tiles_ph));
     cudaError_t e;
     if (a.in_dtype == MPB_F64) {
@@ -100,14 +101,14 @@ cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st) {
         k_mel_unwarp<double><<<grid, 128, smem, st>>>((const double*)a.mag_mel, (const double*)a.real_mel,
                                                       (const double*)a.imag_mel, a.need_ph, a.nfrm, a.n_mag, a.n_ph,
                                                       a.u_mag, a.H, a.u_ph, a.HB, a.out_mag, a.out_real, a.out_imag,
-                                                      tiles_mag, tiles_ph);
+                                                      tiles_mag, tiles_ph, kmax);
     } else {
         e = cudaFuncSetAttribute(k_mel_unwarp<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         k_mel_unwarp<float><<<grid, 128, smem, st>>>((const float*)a.mag_mel, (const float*)a.real_mel,
                                                      (const float*)a.imag_mel, a.need_ph, a.nfrm, a.n_mag, a.n_ph,
                                                      a.u_mag, a.H, a.u_ph, a.HB, a.out_mag, a.out_real, a.out_imag,
-                                                     tiles_mag, tiles_ph);
+                                                     tiles_mag, tiles_ph, kmax);
     }
     return cudaGetLastError();
 }
