@@ -12,6 +12,13 @@ namespace mpb {
 template <typename T>
 __device__ __forceinline__ T side_window(int j, int S, int kind) {
     if (j == 0) return (T)1;
+    if (sizeof(T) == 4) {
+        // float32 frames (the noise branch of compressed synthesis): float32 window arithmetic is enough
+        const float x = (float)j / (float)S;
+        if (kind == MPB_WIN_HANN) return (T)(0.5f + 0.5f * cospif(x));
+        const float b = 1.0f - x;
+        return (T)(b * b * sqrtf(b));
+    }
     const double x = (double)j / (double)S;
     if (kind == MPB_WIN_HANN) return (T)(0.5 + 0.5 * cospi(x));
     const double b = 1.0 - x;
