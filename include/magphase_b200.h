@@ -217,7 +217,8 @@ typedef struct mpb_syn_frames {
 
 /* mag_mel: n_rows x n_mag; real_mel/imag_mel: n_rows x n_ph (in_dtype); need_ph[row] != 0 where the phase rows
  * are needed; noise: uniform(-1,1) samples (float32) of all utterances; runs from mpb_plan_ola_runs.
- * per_linear != 0 selects per_phase_type='linear'.  Launches un-warp, noise statistics, gains, synthesis.      */
+ * per_linear: 0 = per_phase_type 'magphase', 1 = 'linear', 2 = 'min_phase' (then pass need_ph all zero).
+ * Launches un-warp, [min-phase], noise statistics, gains, synthesis.                                        */
 int mpb_synthesis_compressed_dev(mpb_syn* plan, void* stream,
                                  const void* mag_mel, const void* real_mel, const void* imag_mel, int in_dtype,
                                  int64_t n_rows, const uint8_t* need_ph, const float* noise, int64_t n_noise,
@@ -227,6 +228,24 @@ int mpb_synthesis_compressed_host(mpb_syn* plan,
                                   const double* mag_mel, const double* real_mel, const double* imag_mel,
                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
                                   const mpb_syn_frames* frames, int per_linear, double* out, int64_t n_out);
+
+/* ---- post-filter and minimum phase ---------------------------------------------------------- */
+/*
+ * post_filter (src/magphase.py:2300-2378): ave[b] = mean(x[centre[b]-half[b] .. centre[b]+half[b]]),
+ * out[b] = (x[b]-ave[b])*tilt[b] + ave[b], first and last bin passed through.  centre/half/tilt (dim entries) are
+ * computed by the host mirror from av_len_at_zero / av_len_at_nyq / boost_* exactly as the reference does.
+ */
+int mpb_post_filter_dev(mpb_ctx* ctx, void* stream, const void* x, int dtype, int64_t nfrm, int dim,
+                        const int32_t* centre, const int32_t* half, const double* tilt, void* out);
+int mpb_post_filter_host(mpb_ctx* ctx, const double* x, int64_t nfrm, int dim,
+                         const int32_t* centre, const int32_t* half, const double* tilt, double* out);
+/*
+ * la.build_min_phase_from_mag_spec (src/libaudio.py:920-934): log|X| -> real cepstrum -> causal lifter -> FFT ->
+ * exp, one fused float64 kernel.  mag: nfrm x (fft_len/2+1); out_cplx: nfrm x (fft_len/2+1) x 2 (re, im).
+ */
+int mpb_min_phase_dev(mpb_ctx* ctx, void* stream, const void* mag, int dtype, int64_t nfrm, int fft_len,
+                      void* out_cplx);
+int mpb_min_phase_host(mpb_ctx* ctx, const double* mag, int64_t nfrm, int fft_len, double* out_cplx);
 
 #ifdef __cplusplus
 }

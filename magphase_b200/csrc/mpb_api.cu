@@ -339,4 +339,79 @@ int mpb_synthesis_lossless_host(mpb_ctx* ctx, const double* mag, const double* r
     return MPB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+int mpb_post_filter_dev(mpb_ctx* ctx, void* stream, const void* x, int dtype, int64_t nfrm, int dim,
+                        const int32_t* centre, const int32_t* half, const double* tilt, void* out) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (!dtype_ok(dtype) || nfrm < 0) return fail(MPB_ERR_BAD_ARG, "bad dtype or size");
+    if (dim < 2 || dim > 256) return fail(MPB_ERR_DIM, "post-filter dimension must be in 2..256");
+    if (nfrm == 0) return MPB_OK;
+    if (!x || !centre || !half || !tilt || !out) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    LAUNCH(ctx, (cudaStream_t)stream, "k_post_filter",
+           launch_post_filter(x, dtype, nfrm, dim, centre, half, tilt, out, (cudaStream_t)stream));
+    return MPB_OK;
+}
+
+int mpb_post_filter_host(mpb_ctx* ctx, const double* x, int64_t nfrm, int dim, const int32_t* centre,
+                         const int32_t* half, const double* tilt, double* out) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (nfrm == 0) return MPB_OK;
+    if (!x || !centre || !half || !tilt || !out || dim < 2) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    for (int b = 0; b < dim; ++b)
+        if (half[b] < 0 || centre[b] - half[b] < 0 || centre[b] + half[b] >= dim)
+            return fail(MPB_ERR_BAD_ARG, "post-filter averaging window reaches outside the feature vector");
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevBuf* b = ctx->scratch;
+    cudaStream_t st = ctx->stream;
+    const size_t sz = sizeof(double) * (size_t)nfrm * dim;
+    CU(b[0].need(sz)); CU(b[5].need(sz));
+    CU(b[2].need(sizeof(int32_t) * dim)); CU(b[3].need(sizeof(int32_t) * dim)); CU(b[1].need(sizeof(double) * dim));
+    CU(cudaMemcpyAsync(b[0].p, x, sz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[2].p, centre, sizeof(int32_t) * dim, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[3].p, half, sizeof(int32_t) * dim, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[1].p, tilt, sizeof(double) * dim, cudaMemcpyHostToDevice, st));
+    int rc = mpb_post_filter_dev(ctx, st, b[0].p, MPB_F64, nfrm, dim, (const int32_t*)b[2].p, (const int32_t*)b[3].p,
+                                 (const double*)b[1].p, b[5].p);
+    if (rc != MPB_OK) return rc;
+    CU(cudaMemcpyAsync(out, b[5].p, sz, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MPB_OK;
+}
+
+int mpb_min_phase_dev(mpb_ctx* ctx, void* stream, const void* mag, int dtype, int64_t nfrm, int fft_len, void* out_cplx) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (!fft_len_ok(fft_len)) return fail(MPB_ERR_FFT_LEN, "fft_len must be 1024, 2048 or 4096");
+    if (!dtype_ok(dtype) || nfrm < 0) return fail(MPB_ERR_BAD_ARG, "bad dtype or size");
+    if (nfrm == 0) return MPB_OK;
+    if (!mag || !out_cplx) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    const void* tw = nullptr;
+    int rc = get_twiddles(ctx, fft_len, MPB_F64, &tw);
+    if (rc != MPB_OK) return rc;
+    LAUNCH(ctx, (cudaStream_t)stream, "k_min_phase",
+           launch_min_phase(fft_len, mag, dtype, nfrm, tw, out_cplx, ctx->num_sms, (cudaStream_t)stream));
+    return MPB_OK;
+}
+
+int mpb_min_phase_host(mpb_ctx* ctx, const double* mag, int64_t nfrm, int fft_len, double* out_cplx) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (!fft_len_ok(fft_len)) return fail(MPB_ERR_FFT_LEN, "fft_len must be 1024, 2048 or 4096");
+    if (nfrm == 0) return MPB_OK;
+    if (!mag || !out_cplx) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevBuf* b = ctx->scratch;
+    cudaStream_t st = ctx->stream;
+    const size_t sz = sizeof(double) * (size_t)nfrm * (fft_len / 2 + 1);
+    CU(b[5].need(sz)); CU(b[6].need(2 * sz));
+    CU(cudaMemcpyAsync(b[5].p, mag, sz, cudaMemcpyHostToDevice, st));
+    int rc = mpb_min_phase_dev(ctx, st, b[5].p, MPB_F64, nfrm, fft_len, b[6].p);
+    if (rc != MPB_OK) return rc;
+    CU(cudaMemcpyAsync(out_cplx, b[6].p, 2 * sz, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MPB_OK;
+}
+
 }  // extern "C"

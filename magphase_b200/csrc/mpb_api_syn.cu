@@ -57,6 +57,7 @@ int mpb_syn_destroy(mpb_syn* s) {
     return MPB_OK;
 }
 
+// per_linear: 0 = per_phase_type 'magphase', 1 = 'linear', 2 = 'min_phase' (pass need_ph all zero).
 // All pointers are DEVICE pointers (fr included: a host struct of device pointers).  Enqueues un-warp,
 // noise statistics, gains and the synthesis kernel on `stream`.
 int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, const void* real_mel,
@@ -110,7 +111,14 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
     a.logsq = (const double*)s->logsq.p; a.utt_frm_off = fr->utt_frm_off; a.inv_gain = (double*)s->gain.p;
     a.tab = s->tab; a.utt_out_off = fr->utt_out_off; a.utt_t0 = fr->utt_t0; a.n_utt = fr->n_utt;
     a.runs = (const OlaRun*)runs; a.n_runs = n_runs; a.nfrm = fr->nfrm;
-    a.fft_len = s->fft_len; a.per_linear = per_linear; a.tw = tw;
+    a.fft_len = s->fft_len; a.per_linear = per_linear == 1; a.tw = tw;
+    if (per_linear == 2) {   // per_phase_type='min_phase': Re/Im of the minimum-phase spectrum replace the phase rows
+        const void* tw64 = nullptr;
+        rc = get_twiddles(ctx, s->fft_len, MPB_F64, &tw64);
+        if (rc != MPB_OK) return rc;
+        LAUNCH(ctx, st, "k_min_phase", launch_min_phase_split(s->fft_len, u.out_mag, n_rows, tw64, u.out_real, u.out_imag,
+                                                               s->HB, ctx->num_sms, st));
+    }
     a.out = out; a.out_dtype = out_dtype; a.n_out = n_out; a.num_sms = ctx->num_sms;
     LAUNCH(ctx, st, "k_noise_gain", launch_noise_gain(a, st));
     LAUNCH(ctx, st, "k_synthesis_compressed", launch_synthesis_compressed(a, st));

@@ -1,0 +1,188 @@
+// Two small hot-path rows that reuse the FFT engine: the MagPhase post-filter and the minimum-phase builder.
+#include "mpb_frame.cuh"
+
+namespace mpb {
+
+// ---- post_filter ------------------------------------------------------------------------------
+// Reference: post_filter src/magphase.py:2300-2378.  Per frame and mel bin b:
+//   ave[b] = mean(x[c[b]-h[b] .. c[b]+h[b]])   (c, h: host-computed, boundary fill included, :2352-2360)
+//   out[b] = (x[b] - ave[b]) * tilt[b] + ave[b],   out[0] = x[0], out[D-1] = x[D-1]      (:2369-2372)
+template <typename T>
+__global__ void k_post_filter(const T* __restrict__ x, int64_t nfrm, int dim, const int32_t* __restrict__ centre,
+                              const int32_t* __restrict__ half, const double* __restrict__ tilt, T* __restrict__ out) {
+    extern __shared__ double row[];                       // [frames per CTA][dim]
+    const int fpc = blockDim.x / dim;                     // frames per CTA
+    const int lf = threadIdx.x / dim, b = threadIdx.x % dim;
+    const int64_t f = (int64_t)blockIdx.x * fpc + lf;
+    const bool on = lf < fpc && f < nfrm;
+    if (on) row[lf * dim + b] = (double)x[f * dim + b];
+    __syncthreads();
+    if (!on) return;
+    const double* r = row + lf * dim;
+    const int c = centre[b], h = half[b];
+    double s = 0.0;
+    for (int i = c - h; i <= c + h; ++i) s += r[i];
+    const double ave = s / (double)(2 * h + 1);
+    double y = (r[b] - ave) * tilt[b] + ave;
+    if (b == 0 || b == dim - 1) y = r[b];
+    out[f * dim + b] = (T)y;
+}
+
+cudaError_t launch_post_filter(const void* x, int dtype, int64_t nfrm, int dim, const int32_t* centre, const int32_t* half,
+                               const double* tilt, void* out, cudaStream_t st) {
+    if (nfrm < 1) return cudaSuccess;
+    const int fpc = 256 / dim > 0 ? 256 / dim : 1;
+    const int threads = fpc * dim;
+    const unsigned grid = (unsigned)((nfrm + fpc - 1) / fpc);
+    const size_t smem = sizeof(double) * fpc * dim;
+    if (dtype == MPB_F64)
+        k_post_filter<double><<<grid, threads, smem, st>>>((const double*)x, nfrm, dim, centre, half, tilt, (double*)out);
+    else
+        k_post_filter<float><<<grid, threads, smem, st>>>((const float*)x, nfrm, dim, centre, half, tilt, (float*)out);
+    return cudaGetLastError();
+}
+
+// ---- minimum phase ------------------------------------------------------------------------------
+// Reference: la.build_min_phase_from_mag_spec src/libaudio.py:920-934 (with la.log :241-248):
+//   log|X| -> Hermitian extend -> ifft.real (real cepstrum) -> zero n >= H, double n = 1..H-2 -> fft -> half -> exp
+// fused in one kernel, float64: one CTA per frame; inverse FFT, lifter in shared memory, forward FFT, complex exp.
+// OUT_MODE 0: complex128/complex64 rows [nfrm][H][2];  1: separate real / imag rows of `nb` leading bins (float32),
+// which the compressed synthesis kernel consumes for per_phase_type='min_phase'.
+template <typename TI, typename TO, int N, int OUT_MODE>
+__global__ void __launch_bounds__(FftGeom<double, N>::TPB, 384 / FftGeom<double, N>::TPB)
+k_min_phase(const TI* __restrict__ mag, int64_t nfrm, const double2* __restrict__ tw, TO* __restrict__ out_a,
+            TO* __restrict__ out_b, int nb) {
+    using T = double;
+    using G = FftGeom<T, N>;
+    using T2 = double2;
+    constexpr int M = G::M, H = M + 1, TPB = G::TPB;
+    constexpr int NJ = (M / 2) / TPB;
+    constexpr int STEP = TPB + TPB / 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T2* buf = reinterpret_cast<T2*>(smem_raw);
+    T2* tw2f = buf + G::BUF_ELEMS;
+    T2* tw2i = tw2f + G::TW2_ELEMS;
+    const int t = threadIdx.x;
+    FftCtx<T> ff, fi;
+    fft_setup<T, N, false>(ff, tw2f, tw, t);
+    fft_setup<T, N, true>(fi, tw2i, tw, t);
+    T2* pk = buf + G::nphys(t);
+    T2* pmk = buf + G::nphys(M - t);
+    T* bufT = reinterpret_cast<T*>(buf);
+
+    for (int64_t f = blockIdx.x; f < nfrm; f += gridDim.x) {
+        const TI* __restrict__ row = mag + f * (int64_t)H;
+        // ---- log magnitude (protected like la.log) packed for the Hermitian inverse transform ----
+        auto lg = [&](int k) {
+            const double m = (double)row[k];
+            double l = log(m);
+            if (isinf(l) || isnan(l)) l = -1.0e10;
+            return l;
+        };
+        T2 w = fi.wp;
+#pragma unroll 1
+        for (int j = 0; j < NJ; ++j) {
+            const int k = t + j * TPB;
+            const double a = lg(k), b = lg(M - k);          // X[k], conj(X[M-k]): both real
+            const T2 o = cmul(mk<T>(a - b, 0.0), w);
+            w = cmul(w, fi.wstep);
+            pk[j * STEP] = mk<T>((a + b) - o.y, o.x);
+            if (k != 0) pmk[-j * STEP] = mk<T>((a + b) + o.y, o.x);
+        }
+        if (t == 0) buf[G::nphys(M / 2)] = mk<T>(2.0 * lg(M / 2), 0.0);
+        __syncthreads();
+        T2 v[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = pk[n1 * (G::S1 + G::S1 / 16)];
+        __syncthreads();
+        fft_m<T, N, true>(v, buf, fi, t);
+        // ---- causal lifter on the real cepstrum c[n] = bufT[..] / N ----
+        for (int n = t; n < N; n += TPB) {
+            T* p = bufT + 2 * G::nphys(n >> 1) + (n & 1);
+            const double c = *p / (double)N;
+            *p = (n == 0 || n == H - 1) ? c : (n < H - 1 ? 2.0 * c : 0.0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = pk[n1 * (G::S1 + G::S1 / 16)];
+        __syncthreads();
+        fft_m<T, N, false>(v, buf, ff, t);
+        // ---- split, complex exponential, store ----
+        w = ff.wp;
+#pragma unroll 1
+        for (int j = 0; j <= NJ; ++j) {
+            const int k = t + j * TPB;
+            if (j == NJ && t != 0) break;
+            const T2 zk = pk[j * STEP];
+            const T2 zm = cconj(k == 0 ? buf[0] : pmk[-j * STEP]);
+            const T2 e = mk<T>(0.5 * (zk.x + zm.x), 0.5 * (zk.y + zm.y));
+            const T2 d = mk<T>(0.5 * (zk.x - zm.x), 0.5 * (zk.y - zm.y));
+            const T2 wo = cmul(mk<T>(d.y, -d.x), w);
+            w = cmul(w, ff.wstep);
+            T2 x1 = cadd(e, wo), x2 = cconj(csub(e, wo));
+            if (k == 0) { x1.y = 0.0; x2.y = 0.0; }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const T2 x = h ? x2 : x1;
+                const int kk = h ? (M - k) : k;
+                if (h && kk == k) break;
+                if (OUT_MODE == 1 && kk >= nb) continue;
+                double s, c;
+                sincos(x.y, &s, &c);
+                const double m = exp(x.x);
+                if (OUT_MODE == 0) {
+                    out_a[2 * (f * (int64_t)H + kk)] = (TO)(m * c);
+                    out_a[2 * (f * (int64_t)H + kk) + 1] = (TO)(m * s);
+                } else {
+                    out_a[f * (int64_t)nb + kk] = (TO)(m * c);
+                    out_b[f * (int64_t)nb + kk] = (TO)(m * s);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename TI, typename TO, int N, int OUT_MODE>
+static cudaError_t launch_mp_t(const void* mag, int64_t nfrm, const void* tw, void* out_a, void* out_b, int nb, int num_sms,
+                               cudaStream_t st) {
+    using G = FftGeom<double, N>;
+    const size_t smem = sizeof(double2) * (G::BUF_ELEMS + 2 * G::TW2_ELEMS);
+    auto kern = k_min_phase<TI, TO, N, OUT_MODE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G::TPB, smem);
+    if (e != cudaSuccess) return e;
+    int64_t grid = (int64_t)num_sms * (per_sm < 1 ? 1 : per_sm);
+    if (grid > nfrm) grid = nfrm;
+    if (grid < 1) return cudaSuccess;
+    kern<<<(unsigned)grid, G::TPB, smem, st>>>((const TI*)mag, nfrm, (const double2*)tw, (TO*)out_a, (TO*)out_b, nb);
+    return cudaGetLastError();
+}
+
+template <typename TI, typename TO, int OUT_MODE>
+static cudaError_t launch_mp_n(int fft_len, const void* mag, int64_t nfrm, const void* tw, void* out_a, void* out_b, int nb,
+                               int num_sms, cudaStream_t st) {
+    switch (fft_len) {
+        case 1024: return launch_mp_t<TI, TO, 1024, OUT_MODE>(mag, nfrm, tw, out_a, out_b, nb, num_sms, st);
+        case 2048: return launch_mp_t<TI, TO, 2048, OUT_MODE>(mag, nfrm, tw, out_a, out_b, nb, num_sms, st);
+        case 4096: return launch_mp_t<TI, TO, 4096, OUT_MODE>(mag, nfrm, tw, out_a, out_b, nb, num_sms, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// complex rows out (dtype of input and output: MPB_F32 -> complex64, MPB_F64 -> complex128)
+cudaError_t launch_min_phase(int fft_len, const void* mag, int dtype, int64_t nfrm, const void* tw64, void* out_cplx,
+                             int num_sms, cudaStream_t st) {
+    return dtype == MPB_F64 ? launch_mp_n<double, double, 0>(fft_len, mag, nfrm, tw64, out_cplx, nullptr, 0, num_sms, st)
+                            : launch_mp_n<float, float, 0>(fft_len, mag, nfrm, tw64, out_cplx, nullptr, 0, num_sms, st);
+}
+
+// float32 rows in, leading nb bins of Re / Im out (float32): feeds k_synthesis_compressed
+cudaError_t launch_min_phase_split(int fft_len, const float* mag, int64_t nfrm, const void* tw64, float* out_re, float* out_im,
+                                   int nb, int num_sms, cudaStream_t st) {
+    return launch_mp_n<float, float, 1>(fft_len, mag, nfrm, tw64, out_re, out_im, nb, num_sms, st);
+}
+
+}  // namespace mpb

@@ -687,8 +687,12 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
     l_noise: optional list of per-utterance noise vectors (else drawn from np.random, utterance by utterance)."""
     if b_fbank_mel:
         raise ValueError('b_fbank_mel=True (experimental filter-bank warping) is outside the CUDA hot path')
-    if per_phase_type not in ('magphase', 'linear'):
-        raise NotImplementedError("per_phase_type=%r: only 'magphase' and 'linear' run on the CUDA path" % (per_phase_type,))
+    if per_phase_type not in ('magphase', 'linear', 'min_phase'):
+        raise ValueError("per_phase_type must be 'magphase', 'min_phase' or 'linear'")
+    if per_phase_type == 'min_phase' and b_const_rate:
+        # the reference interpolates the un-warped magnitude first and builds the minimum phase of the interpolated
+        # frames (src/magphase.py:861-870 then :935-936); the device path builds it per feature row
+        raise NotImplementedError("per_phase_type='min_phase' with b_const_rate=True is not on the CUDA path yet")
     if fft_len is None:
         fft_len = define_fft_len(fs)
     mag_dim = np.shape(l_feats[0][0])[1]
@@ -706,6 +710,8 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
         if np.size(v) != n:
             raise ValueError('noise length %d != %d' % (np.size(v), n))
     need = arrs.pop('need_ph')
+    if per_phase_type == 'min_phase':
+        need = np.zeros_like(need)          # phase rows come from the minimum-phase kernel instead
     out_off = arrs['utt_out_off']
     fr = _lib.SynFrames(nfrm=int(arrs['utt_frm_off'][-1]), n_utt=n_utt, **{k: _lib.ptr(v) for k, v in arrs.items()})
     cat = lambda i: np.ascontiguousarray(np.concatenate([np.asarray(f[i], dtype=np.float64) for f in l_feats], axis=0))
@@ -714,7 +720,7 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
     out = np.empty(int(out_off[-1]), dtype=np.float64)
     _lib.check(_lib.lib().mpb_synthesis_compressed_host(
         plan.handle, _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), mag.shape[0], _lib.ptr(need), _lib.ptr(noise),
-        noise.size, C.byref(fr), 1 if per_phase_type == 'linear' else 0, _lib.ptr(out), out.size))
+        noise.size, C.byref(fr), {'magphase': 0, 'linear': 1, 'min_phase': 2}[per_phase_type], _lib.ptr(out), out.size))
     l_out = [out[out_off[u]:out_off[u + 1]] for u in range(n_utt)]
     if b_out_hpf:
         # 4th-order 40 Hz Butterworth high-pass (src/magphase.py:981-995); sequential IIR, host for now
@@ -723,3 +729,73 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
         v_b, v_a = signal.butter(4, 40 / (fs / 2.0), btype='highpass')
         l_out = [signal.lfilter(v_b, v_a, y) for y in l_out]
     return l_out
+
+
+# ----------------------------------------------------------------------------------------------
+# post-filter and minimum phase
+# ----------------------------------------------------------------------------------------------
+def post_filter(m_mag_mel_log, fs, av_len_at_zero=None, av_len_at_nyq=None, boost_at_zero=None, boost_at_nyq=None):
+    """MagPhase post-filter on the mel log-magnitude.  src/magphase.py:2300-2378"""
+    m = np.ascontiguousarray(m_mag_mel_log, dtype=np.float64)
+    nfrms, mag_dim = m.shape
+    if mag_dim != 60:
+        warnings.warn('Post-filter: It has been only tested with 60 dimensional mag data. If you use another dimension, '
+                      'the result may be suboptimal.')
+    opts = [av_len_at_zero, av_len_at_nyq, boost_at_zero, boost_at_nyq]
+    if fs == 48000:
+        defaults = [round_to_int(11.0 * (mag_dim / 60.0)), round_to_int(3.0 * (mag_dim / 60.0)), 1.8, 2.0]
+    elif fs == 16000:
+        if any(o is None for o in opts):
+            warnings.warn('Post-filter: The default parameters for 16kHz sample rate have not being tunned.')
+        defaults = [round_to_int(9.0 * (mag_dim / 60.0)), round_to_int(12.0 * (mag_dim / 60.0)), 2.0, 1.6]
+    else:
+        if any(o is None for o in opts):
+            raise ValueError('Post-filter: It has only been tested with 16kHz and 48kHz sample rates.'
+                             '\nProvide your own values for the options: av_len_at_zero, av_len_at_nyq, boost_at_zero,'
+                             '\nboost_at_nyq if you use another sample rate')
+        defaults = opts
+    l0, l1, b0, b1 = [d if o is None else o for d, o in zip(defaults, opts)]
+    # integer bookkeeping of the averaging windows (:2343-2346) and the boundary fill (:2357-2358)
+    v_nx = np.arange(np.floor(l0 / 2), mag_dim - np.floor(l1 / 2)).astype(int)
+    v_lens = (2 * np.ceil(np.linspace(l0, l1, v_nx.size) / 2) - 1).astype(int)
+    centre = np.empty(mag_dim, dtype=np.int32)
+    half = np.empty(mag_dim, dtype=np.int32)
+    centre[v_nx] = v_nx
+    half[v_nx] = v_lens // 2
+    centre[:v_nx[0]], half[:v_nx[0]] = v_nx[0], half[v_nx[0]]
+    centre[v_nx[-1]:], half[v_nx[-1]:] = v_nx[-1], half[v_nx[-1]]
+    tilt = np.ascontiguousarray(np.linspace(b0, b1, mag_dim), dtype=np.float64)
+    out = np.empty_like(m)
+    _lib.check(_lib.lib().mpb_post_filter_host(_lib.ctx(), _lib.ptr(m), nfrms, mag_dim, _lib.ptr(centre), _lib.ptr(half),
+                                               _lib.ptr(tilt), _lib.ptr(out)))
+    return out
+
+
+def build_min_phase_from_mag_spec(m_mag):
+    """Minimum-phase complex spectrum of a magnitude spectrum.  la.build_min_phase_from_mag_spec, src/libaudio.py:920-934"""
+    m = np.ascontiguousarray(m_mag, dtype=np.float64)
+    fft_len = 2 * (m.shape[1] - 1)
+    out = np.empty(m.shape, dtype=np.complex128)
+    _lib.check(_lib.lib().mpb_min_phase_host(_lib.ctx(), _lib.ptr(m), m.shape[0], fft_len, _lib.ptr(out)))
+    return out
+
+
+def synthesis_from_acoustic_modelling(in_feats_dir, filename_token, out_syn_dir, mag_dim, phase_dim, fs, fft_len=None,
+                                      pf_type='no', b_const_rate=False):
+    """Feature files -> wav.  src/magphase.py:3229-3275 (pf_type 'merlin' needs nine SPTK binaries: out of scope)."""
+    print("\nSynthesising file: " + filename_token + '.wav............................')
+    m_mag_mel_log = io.read_binfile(in_feats_dir + '/' + filename_token + '.mag', dim=mag_dim)
+    m_real_mel = io.read_binfile(in_feats_dir + '/' + filename_token + '.real', dim=phase_dim)
+    m_imag_mel = io.read_binfile(in_feats_dir + '/' + filename_token + '.imag', dim=phase_dim)
+    v_lf0 = io.read_binfile(in_feats_dir + '/' + filename_token + '.lf0', dim=1)
+    if pf_type == 'magphase':
+        print('Using MagPhase postfilter...')
+        m_mag_mel_log = post_filter(m_mag_mel_log, fs)
+    elif pf_type == 'merlin':
+        raise NotImplementedError("pf_type='merlin' shells out to nine SPTK binaries (src/magphase.py:3375-3465): out of scope")
+    elif pf_type == 'no':
+        print('No postfilter...')
+    v_syn_sig = synthesis_from_compressed(m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0, fs, fft_len=fft_len,
+                                          b_const_rate=b_const_rate)
+    io.write_audio_file(out_syn_dir + '/' + filename_token + '.wav', v_syn_sig, fs)
+    return

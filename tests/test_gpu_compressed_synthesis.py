@@ -112,10 +112,56 @@ def test_all_unvoiced_and_all_voiced(mp, gold):
         assert np.all(np.isfinite(y)) and y.shape == y_ref.shape and rms(y, y_ref) < TOL
 
 
+def test_min_phase_vs_reference_golden(mp, gold):
+    g, feats = gold
+    np.random.seed(int(g['seed']))
+    y = mp.synthesis_from_compressed(*feats, 48000, b_out_hpf=False, per_phase_type='min_phase')
+    assert y.shape == g['syn_minph_nohpf'].shape
+    assert rms(y, g['syn_minph_nohpf']) < TOL
+
+
+def test_post_filter_vs_reference_golden(mp, gold):
+    g, feats = gold
+    y = mp.post_filter(feats[0], 48000)
+    assert y.dtype == np.float64 and np.max(np.abs(y - g['post_filter_48k'])) < 1e-12
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        y16 = mp.post_filter(feats[0], 16000)
+        assert any('16kHz' in str(x.message) for x in w)
+    assert np.max(np.abs(y16 - g['post_filter_16k'])) < 1e-12
+    # explicit options and another dimension
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=(37, 80))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        a = mp.post_filter(x, 22050, av_len_at_zero=9, av_len_at_nyq=5, boost_at_zero=1.5, boost_at_nyq=2.5)
+        b = orc.post_filter(x, 22050, av_len_at_zero=9, av_len_at_nyq=5, boost_at_zero=1.5, boost_at_nyq=2.5)
+    assert np.max(np.abs(a - b)) < 1e-12
+    with pytest.raises(ValueError):
+        mp.post_filter(x, 22050)
+
+
+def test_build_min_phase_vs_reference_golden(mp):
+    g = np.load(os.path.join(GOLD, 'lossless_synth48k.npz'))
+    got = mp.build_min_phase_from_mag_spec(g['mag_rows'])
+    ref = g['minph_rows']
+    assert got.dtype == np.complex128 and got.shape == ref.shape
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-12)) < 1e-9
+    # |min-phase| reproduces the magnitude (property, any size); a zero bin hits the protected log
+    rng = np.random.default_rng(3)
+    mag = np.exp(rng.normal(size=(300, 1025)))
+    mag[5, 17] = 0.0
+    mpz = mp.build_min_phase_from_mag_spec(mag)
+    ok = np.ones(300, dtype=bool); ok[5] = False
+    assert np.max(np.abs(np.abs(mpz[ok]) / mag[ok] - 1)) < 1e-10
+    # (the -1e10 floor puts +-1e10/N terms into the cepstrum: float64 round-off alone is ~1e-6 relative here)
+    np.testing.assert_allclose(mpz[5], orc.build_min_phase_from_mag_spec(mag[5:6])[0], rtol=1e-4, atol=1e-300)
+
+
 def test_errors(mp, gold):
     g, feats = gold
-    with pytest.raises(NotImplementedError):
-        mp.synthesis_from_compressed(*feats, 48000, per_phase_type='min_phase')
+    with pytest.raises(ValueError):
+        mp.synthesis_from_compressed(*feats, 48000, per_phase_type='bogus')
     with pytest.raises(ValueError):
         mp.synthesis_from_compressed(*feats, 48000, b_fbank_mel=True)
     with pytest.raises(ValueError):        # f0 of 20 Hz: frames longer than fft_len/2
