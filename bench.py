@@ -182,18 +182,6 @@ class ClockSampler:
         return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
 
 
-def lpt_assign(sizes, n_bins):
-    """Longest-processing-time greedy assignment of utterances to GPUs."""
-    order = np.argsort(-np.asarray(sizes), kind='stable')
-    load = np.zeros(n_bins)
-    owner = np.zeros(len(sizes), dtype=np.int64)
-    for i in order:
-        b = int(np.argmin(load))
-        owner[i] = b
-        load[b] += sizes[i]
-    return owner
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -262,14 +250,9 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     # ---- work list: rank 0 enumerates utterances, LPT-assigns them, NCCL broadcasts the assignment ----
-    n_total = a.utts * world
-    owner = torch.zeros(n_total, dtype=torch.int64, device=dev)
-    if rank == 0:
-        sizes = np.full(n_total, int(round(a.dur * FS)))
-        owner = torch.from_numpy(lpt_assign(sizes, world)).to(dev)
-    if world > 1:
-        dist.broadcast(owner, src=0)
-    my_ids = torch.nonzero(owner == rank).flatten().cpu().numpy()
+    from magphase_b200.sharding import reduce_counters, scatter_work_list
+    sizes = np.full(a.utts * world, int(round(a.dur * FS))) if rank == 0 else None
+    my_ids, _ = scatter_work_list(sizes, device=dev)
 
     base = {}
     for u in my_ids[:DISTINCT]:
@@ -378,13 +361,9 @@ def main():
         d2h = feat_bytes + 8 * sum(y.size for y in ys)
 
     # ---- reduce over ranks: max time, summed frames ----
-    stats = torch.tensor([total_ms, e_secs, ana_ms, syn_ms], dtype=torch.float64, device=dev)
-    counts = torch.tensor([plan.nfrm, e_frames], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    total_ms, e_secs, ana_ms, syn_ms = [float(x) for x in stats.cpu()]
-    frames_all, e_frames_all = [float(x) for x in counts.cpu()]
+    stats, counts = reduce_counters([total_ms, e_secs, ana_ms, syn_ms], [plan.nfrm, e_frames], device=dev)
+    total_ms, e_secs, ana_ms, syn_ms = [float(x) for x in stats]
+    frames_all, e_frames_all = [float(x) for x in counts]
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
