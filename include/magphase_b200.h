@@ -227,6 +227,8 @@ int mpb_synthesis_compressed_dev(mpb_syn* plan, void* stream,
 int mpb_synthesis_compressed_host(mpb_syn* plan,
                                   const double* mag_mel, const double* real_mel, const double* imag_mel,
                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
+                                  uint32_t* mt_key, int32_t* mt_pos,   /* noise == NULL: draw it on the device from
+                                                                          NumPy's legacy state (in/out), see below */
                                   const mpb_syn_frames* frames, int per_linear, double* out, int64_t n_out);
 
 /* ---- post-filter and minimum phase ---------------------------------------------------------- */
@@ -246,6 +248,18 @@ int mpb_post_filter_host(mpb_ctx* ctx, const double* x, int64_t nfrm, int dim,
 int mpb_min_phase_dev(mpb_ctx* ctx, void* stream, const void* mag, int dtype, int64_t nfrm, int fft_len,
                       void* out_cplx);
 int mpb_min_phase_host(mpb_ctx* ctx, const double* mag, int64_t nfrm, int fft_len, double* out_cplx);
+
+/* ---- NumPy legacy random stream ------------------------------------------------------------- */
+/*
+ * n draws of np.random.uniform(low, high) from NumPy's global legacy MT19937 stream, generated on the device
+ * bit for bit (the reference draws its aperiodic noise there, src/magphase.py:883).  key[624] / *pos are the
+ * HOST copies of np.random.get_state()[1] / [2]; both are advanced exactly as NumPy would advance them, so
+ * np.random.set_state() afterwards leaves the stream where the reference would have left it.
+ */
+int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* pos, int64_t n,
+                            double low, double high, void* out_dev, int out_dtype);
+int mpb_mt19937_uniform_host(mpb_ctx* ctx, uint32_t* key, int32_t* pos, int64_t n,
+                             double low, double high, double* out);
 
 #ifdef __cplusplus
 }

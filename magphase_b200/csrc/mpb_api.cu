@@ -414,4 +414,43 @@ int mpb_min_phase_host(mpb_ctx* ctx, const double* mag, int64_t nfrm, int fft_le
     return MPB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// n draws of np.random.uniform(low, high) from NumPy's legacy MT19937 state (key[624], pos in [0, 624]) into a
+// DEVICE buffer; key/pos (HOST, in/out) are advanced exactly as NumPy would advance them.  Synchronises `stream`.
+int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* pos, int64_t n, double low, double high,
+                            void* out_dev, int out_dtype) {
+    if (!ctx || !key || !pos) return fail(MPB_ERR_BAD_ARG, "NULL argument");
+    if (!dtype_ok(out_dtype) || n < 0 || *pos < 0 || *pos > 624) return fail(MPB_ERR_BAD_ARG, "bad dtype, size or MT19937 position");
+    if (n == 0) return MPB_OK;
+    if (!out_dev) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf* b = ctx->scratch;
+    CU(b[9].need(sizeof(uint32_t) * 624 + sizeof(int32_t)));
+    CU(b[10].need(sizeof(uint32_t) * 2 * (size_t)n));
+    uint32_t* d_key = (uint32_t*)b[9].p;
+    int32_t* d_pos = (int32_t*)(d_key + 624);
+    CU(cudaMemcpyAsync(d_key, key, sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_pos, pos, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    LAUNCH(ctx, st, "k_mt19937_stream+k_mt_to_uniform",
+           launch_mt19937_uniform(d_key, d_pos, (uint32_t*)b[10].p, n, low, high, out_dev, out_dtype, st));
+    ctx->launches += 1;
+    CU(cudaMemcpyAsync(key, d_key, sizeof(uint32_t) * 624, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(pos, d_pos, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MPB_OK;
+}
+
+int mpb_mt19937_uniform_host(mpb_ctx* ctx, uint32_t* key, int32_t* pos, int64_t n, double low, double high, double* out) {
+    if (!ctx || !out) return fail(MPB_ERR_BAD_ARG, "NULL argument");
+    if (n == 0) return MPB_OK;
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx->scratch[11].need(sizeof(double) * (size_t)n));
+    int rc = mpb_mt19937_uniform_dev(ctx, ctx->stream, key, pos, n, low, high, ctx->scratch[11].p, MPB_F64);
+    if (rc != MPB_OK) return rc;
+    CU(cudaMemcpy(out, ctx->scratch[11].p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    return MPB_OK;
+}
+
 }  // extern "C"

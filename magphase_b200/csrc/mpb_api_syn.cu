@@ -3,6 +3,8 @@
 
 using namespace mpb;
 
+extern "C" int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* pos, int64_t n, double low,
+                                       double high, void* out_dev, int out_dtype);
 extern "C" int mpb_plan_ola_runs(const int32_t* pm, const int64_t* utt_frm_off, int32_t n_utt, int fft_len,
                                  int32_t target_frames, int32_t* out_runs, int64_t capacity, int64_t* n_runs);
 
@@ -125,13 +127,16 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
     return MPB_OK;
 }
 
-// HOST pointers everywhere.  noise: the uniform(-1, 1) samples of all utterances, concatenated.
+// HOST pointers everywhere.  noise: the uniform(-1, 1) samples of all utterances, concatenated -- or NULL with
+// mt_key / mt_pos (NumPy's legacy MT19937 state, in/out): then the same numbers are generated on the device.
 int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const double* real_mel, const double* imag_mel,
                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
-                                  const mpb_syn_frames* fr, int per_linear, double* out, int64_t n_out) {
+                                  uint32_t* mt_key, int32_t* mt_pos, const mpb_syn_frames* fr, int per_linear,
+                                  double* out, int64_t n_out) {
     if (!s || !fr) return fail(MPB_ERR_BAD_ARG, "NULL argument");
     if (n_out == 0) return MPB_OK;
-    if (!mag_mel || !real_mel || !imag_mel || !need_ph || !noise || !out) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    if (!mag_mel || !real_mel || !imag_mel || !need_ph || !out) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    if (!noise && !(mt_key && mt_pos)) return fail(MPB_ERR_BAD_ARG, "either noise or an MT19937 state is required");
     const int64_t F = fr->nfrm;
     const int32_t U = fr->n_utt;
     for (int64_t f = 0; f < F; ++f) {
@@ -153,8 +158,11 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
     std::vector<int32_t> runs(4 * (size_t)(n_runs > 0 ? n_runs : 1));
     rc = mpb_plan_ola_runs(fr->pm, fr->utt_frm_off, U, s->fft_len, target, runs.data(), n_runs, &n_runs);
     if (rc != MPB_OK) return rc;
-    std::vector<float> noise32((size_t)n_noise);
-    for (int64_t i = 0; i < n_noise; ++i) noise32[i] = (float)noise[i];
+    std::vector<float> noise32;
+    if (noise) {
+        noise32.resize((size_t)n_noise);
+        for (int64_t i = 0; i < n_noise; ++i) noise32[i] = (float)noise[i];
+    }
 
     mpb_ctx* ctx = s->ctx;
     CU(cudaSetDevice(ctx->device));
@@ -177,7 +185,15 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
     UP(real_mel, sizeof(double) * n_rows * s->n_ph, d_real);
     UP(imag_mel, sizeof(double) * n_rows * s->n_ph, d_imag);
     UP(need_ph, (size_t)n_rows, d_need);
-    UP(noise32.data(), sizeof(float) * n_noise, d_noise);
+    if (noise) {
+        UP(noise32.data(), sizeof(float) * n_noise, d_noise);
+    } else {
+        DevBuf& dn = b[bi++];
+        CU(dn.need(sizeof(float) * (size_t)(n_noise > 0 ? n_noise : 1)));
+        rc = mpb_mt19937_uniform_dev(ctx, st, mt_key, mt_pos, n_noise, -1.0, 1.0, dn.p, MPB_F32);
+        if (rc != MPB_OK) return rc;
+        d_noise = dn.p;
+    }
     UP(runs.data(), sizeof(int32_t) * 4 * n_runs, d_runs);
     UP(fr->pm, sizeof(int32_t) * F, d.pm);
     UP(fr->ncentre, sizeof(int64_t) * F, d.ncentre);

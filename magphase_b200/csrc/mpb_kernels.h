@@ -94,4 +94,8 @@ cudaError_t launch_min_phase(int fft_len, const void* mag, int dtype, int64_t nf
 cudaError_t launch_min_phase_split(int fft_len, const float* mag, int64_t nfrm, const void* tw64, float* out_re,
                                    float* out_im, int nb, int num_sms, cudaStream_t st);
 
+// ---- NumPy legacy MT19937 stream on the device (mpb_rng.cu) ----
+cudaError_t launch_mt19937_uniform(uint32_t* key_dev, int32_t* pos_dev, uint32_t* raw_dev, int64_t n, double low,
+                                   double high, void* out, int out_dtype, cudaStream_t st);
+
 }  // namespace mpb

@@ -704,11 +704,20 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
     n_utt = len(l_feats)
     arrs, l_ns_len = compressed_synthesis_geometry([f[3] for f in l_feats], [np.shape(f[0])[0] for f in l_feats], fs,
                                                    fft_len, b_voi_ap_win=b_voi_ap_win, b_const_rate=b_const_rate)
+    mt_key, mt_pos, np_state = None, None, None
     if l_noise is None:
-        l_noise = [np.random.uniform(-1, 1, n) for n in l_ns_len]          # :883, utterance by utterance
-    for v, n in zip(l_noise, l_ns_len):
-        if np.size(v) != n:
-            raise ValueError('noise length %d != %d' % (np.size(v), n))
+        # np.random.uniform(-1, 1, ns_len) per utterance (:883) == one run of sum(ns_len) draws on NumPy's global
+        # legacy stream.  The stream is advanced ON THE DEVICE, bit for bit, and handed back to NumPy afterwards.
+        np_state = np.random.get_state()
+        if np_state[0] == 'MT19937':
+            mt_key = np.ascontiguousarray(np_state[1], dtype=np.uint32).copy()
+            mt_pos = C.c_int32(int(np_state[2]))
+        else:
+            l_noise = [np.random.uniform(-1, 1, n) for n in l_ns_len]
+    if l_noise is not None:
+        for v, n in zip(l_noise, l_ns_len):
+            if np.size(v) != n:
+                raise ValueError('noise length %d != %d' % (np.size(v), n))
     need = arrs.pop('need_ph')
     if per_phase_type == 'min_phase':
         need = np.zeros_like(need)          # phase rows come from the minimum-phase kernel instead
@@ -716,11 +725,15 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
     fr = _lib.SynFrames(nfrm=int(arrs['utt_frm_off'][-1]), n_utt=n_utt, **{k: _lib.ptr(v) for k, v in arrs.items()})
     cat = lambda i: np.ascontiguousarray(np.concatenate([np.asarray(f[i], dtype=np.float64) for f in l_feats], axis=0))
     mag, real, imag = cat(0), cat(1), cat(2)
-    noise = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in l_noise]))
+    noise = None
+    if l_noise is not None:
+        noise = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in l_noise]))
     out = np.empty(int(out_off[-1]), dtype=np.float64)
     _lib.check(_lib.lib().mpb_synthesis_compressed_host(
         plan.handle, _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), mag.shape[0], _lib.ptr(need), _lib.ptr(noise),
-        noise.size, C.byref(fr), {'magphase': 0, 'linear': 1, 'min_phase': 2}[per_phase_type], _lib.ptr(out), out.size))
+        int(sum(l_ns_len)), _lib.ptr(mt_key), C.byref(mt_pos) if mt_pos is not None else None, C.byref(fr), {'magphase': 0, 'linear': 1, 'min_phase': 2}[per_phase_type], _lib.ptr(out), out.size))
+    if mt_key is not None:
+        np.random.set_state((np_state[0], mt_key, int(mt_pos.value), np_state[3], np_state[4]))
     l_out = [out[out_off[u]:out_off[u + 1]] for u in range(n_utt)]
     if b_out_hpf:
         # 4th-order 40 Hz Butterworth high-pass (src/magphase.py:981-995); sequential IIR, host for now
@@ -799,3 +812,18 @@ def synthesis_from_acoustic_modelling(in_feats_dir, filename_token, out_syn_dir,
                                           b_const_rate=b_const_rate)
     io.write_audio_file(out_syn_dir + '/' + filename_token + '.wav', v_syn_sig, fs)
     return
+
+
+def numpy_stream_uniform(low, high, n):
+    """np.random.uniform(low, high, n) on NumPy's global legacy stream, generated on the device (bit-identical,
+    the global state advances as if NumPy had drawn the numbers).  Exposed for tests."""
+    st = np.random.get_state()
+    if st[0] != 'MT19937':
+        raise RuntimeError('NumPy global stream is not MT19937')
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos = C.c_int32(int(st[2]))
+    out = np.empty(int(n), dtype=np.float64)
+    _lib.check(_lib.lib().mpb_mt19937_uniform_host(_lib.ctx(), _lib.ptr(key), C.byref(pos), int(n), float(low), float(high),
+                                                   _lib.ptr(out)))
+    np.random.set_state((st[0], key, int(pos.value), st[3], st[4]))
+    return out

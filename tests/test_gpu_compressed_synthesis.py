@@ -166,3 +166,20 @@ def test_errors(mp, gold):
         mp.synthesis_from_compressed(*feats, 48000, b_fbank_mel=True)
     with pytest.raises(ValueError):        # f0 of 20 Hz: frames longer than fft_len/2
         mp.synthesis_from_compressed(feats[0][:5], feats[1][:5], feats[2][:5], np.full(5, np.log(20.0)), 48000)
+
+
+def test_numpy_legacy_stream_on_device_is_bit_exact(mp):
+    """np.random.uniform on the global MT19937 stream, reproduced on the GPU: same numbers, same final state,
+    across block boundaries (624-word regenerations), odd positions and repeated calls."""
+    for seed, sizes in ((0, [1, 5, 311, 312, 313, 100000]), (12345, [7, 623, 1, 2_000_003])):
+        np.random.seed(seed)
+        np.random.uniform(size=3)                 # odd position inside the first block
+        ref = [np.random.uniform(-1, 1, n) for n in sizes]
+        ref_next = np.random.random_sample(5)
+        np.random.seed(seed)
+        np.random.uniform(size=3)
+        got = [mp.numpy_stream_uniform(-1, 1, n) for n in sizes]
+        got_next = np.random.random_sample(5)     # NumPy continues where the device left the stream
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b)
+        assert np.array_equal(got_next, ref_next)
