@@ -140,15 +140,39 @@ int mpb_mel_compress_host(mpb_mel* m, const double* mag, const double* real, con
     return MPB_OK;
 }
 
+int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const int64_t* sig_lens, int32_t n_sigs,
+                                  const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* voi,
+                                  int64_t nfrm, int compute_dtype, double* out_mag_mel, double* out_real_mel,
+                                  double* out_imag_mel);
+
 // analysis_lossless + format_for_modelling fused on the device: host signal in, low-dimensional features out.
 // The lossless features only ever exist as a float32 scratch in HBM (frame-chunked).
 int mpb_analysis_compressed_host(mpb_mel* m, const double* sig, int64_t n_sig, const int64_t* centre,
                                  const int32_t* left, const int32_t* right, const uint8_t* voi, int64_t nfrm,
                                  int compute_dtype, double* out_mag_mel, double* out_real_mel, double* out_imag_mel) {
+    const double* sigs[1] = {sig};
+    const int64_t lens[1] = {n_sig};
+    if (!sig && nfrm > 0) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    return mpb_analysis_compressed_hostv(m, sigs, lens, 1, centre, left, right, voi, nfrm, compute_dtype, out_mag_mel,
+                                         out_real_mel, out_imag_mel);
+}
+
+// Same, with the utterances given as separate HOST arrays (no concatenation on the caller's side): centre[] still
+// indexes the virtual concatenation sigs[0] | sigs[1] | ...
+int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const int64_t* sig_lens, int32_t n_sigs,
+                                  const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* voi,
+                                  int64_t nfrm, int compute_dtype, double* out_mag_mel, double* out_real_mel,
+                                  double* out_imag_mel) {
     if (!m) return fail(MPB_ERR_BAD_ARG, "plan is NULL");
     if (nfrm == 0) return MPB_OK;
-    if (!sig || !centre || !left || !right || !voi || !out_mag_mel || !out_real_mel || !out_imag_mel)
+    if (!sigs || !sig_lens || n_sigs < 1 || !centre || !left || !right || !voi || !out_mag_mel || !out_real_mel ||
+        !out_imag_mel)
         return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    int64_t n_sig = 0;
+    for (int32_t i = 0; i < n_sigs; ++i) {
+        if (!sigs[i] || sig_lens[i] < 0) return fail(MPB_ERR_BAD_ARG, "NULL signal");
+        n_sig += sig_lens[i];
+    }
     mpb_ctx* ctx = m->ctx;
     int rc = check_frames_host(centre, left, right, nfrm, n_sig, m->fft_len);
     if (rc != MPB_OK) return rc;
@@ -166,7 +190,13 @@ int mpb_analysis_compressed_host(mpb_mel* m, const double* sig, int64_t n_sig, c
     CU(m->small[5].need(sizeof(int64_t) * nfrm));
     CU(m->small[6].need(sizeof(int32_t) * nfrm));
     CU(m->small[7].need(sizeof(int32_t) * nfrm));
-    CU(cudaMemcpyAsync(m->small[4].p, sig, sizeof(double) * n_sig, cudaMemcpyHostToDevice, st));
+    {
+        int64_t off = 0;
+        for (int32_t i = 0; i < n_sigs; ++i) {
+            CU(cudaMemcpyAsync((double*)m->small[4].p + off, sigs[i], sizeof(double) * sig_lens[i], cudaMemcpyHostToDevice, st));
+            off += sig_lens[i];
+        }
+    }
     CU(cudaMemcpyAsync(m->small[5].p, centre, sizeof(int64_t) * nfrm, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(m->small[6].p, left, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(m->small[7].p, right, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));

@@ -481,11 +481,13 @@ def analysis_compressed_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None, mag_di
     left = np.ascontiguousarray(np.concatenate(lefts), dtype=np.int32)
     right = np.ascontiguousarray(np.concatenate(rights), dtype=np.int32)
     voi8 = np.ascontiguousarray(np.concatenate(vois), dtype=np.uint8)
-    sig_all = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.float64) for s in l_sig]))
+    sigs = [np.ascontiguousarray(s, dtype=np.float64) for s in l_sig]      # no copy for float64 arrays
+    sig_ptrs = (C.c_void_p * len(sigs))(*[s.ctypes.data for s in sigs])
+    sig_lens = np.ascontiguousarray([s.size for s in sigs], dtype=np.int64)
     n = centre.size
     o_mag = np.empty((n, mag_dim)); o_real = np.empty((n, phase_dim)); o_imag = np.empty((n, phase_dim))
-    _lib.check(_lib.lib().mpb_analysis_compressed_host(
-        plan.handle, _lib.ptr(sig_all), sig_all.size, _lib.ptr(centre), _lib.ptr(left), _lib.ptr(right),
+    _lib.check(_lib.lib().mpb_analysis_compressed_hostv(
+        plan.handle, sig_ptrs, _lib.ptr(sig_lens), len(sigs), _lib.ptr(centre), _lib.ptr(left), _lib.ptr(right),
         _lib.ptr(voi8), n, ANALYSIS_COMPUTE, _lib.ptr(o_mag), _lib.ptr(o_real), _lib.ptr(o_imag)))
     out, a = [], 0
     for u in range(len(l_sig)):
