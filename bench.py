@@ -377,6 +377,7 @@ def main():
     # algorithmic HBM bytes per launch of each kernel = what its own contract must move
     H, nf = FFT_LEN // 2 + 1, plan.nfrm
     kbytes = {
+        'k_analysis<logp>': plan.n_sig * 4 + nf * 16 + 3 * nf * H * 4,
         'k_analysis': plan.n_sig * 4 + nf * 16 + 3 * nf * H * (8 if (not comp and feat_dt == F64) else 4),
         'k_synthesis_lossless': 3 * nf * H * (8 if feat_dt == F64 else 4) + nf * 4 + getattr(plan, 'n_out', 0) * 4,
         'k_mel_gemm': 3 * nf * H * 4 + nf * 150 * 4,

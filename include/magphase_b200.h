@@ -178,6 +178,13 @@ int mpb_analysis_compressed_host(mpb_mel* plan,
                                  const uint8_t* voi, int64_t nfrm, int compute_dtype,
                                  double* out_mag_mel, double* out_real_mel, double* out_imag_mel);
 
+/* Device variant: sig / centre / left / right / voi and the outputs are DEVICE pointers; the intermediate float32
+ * log periodograms live in a plan-owned scratch (frame-chunked), float64 butterflies.                     */
+int mpb_analysis_compressed_dev(mpb_mel* plan, void* stream,
+                                const void* sig, int sig_dtype, int64_t n_sig,
+                                const int64_t* centre, const int32_t* left, const int32_t* right,
+                                const uint8_t* voi, int64_t nfrm,
+                                void* out_mag_mel, void* out_real_mel, void* out_imag_mel, int out_dtype);
 /* Same with the utterances as n_sigs separate HOST arrays; centre[] indexes their virtual concatenation.  */
 int mpb_analysis_compressed_hostv(mpb_mel* plan,
                                   const double* const* sigs, const int64_t* sig_lens, int32_t n_sigs,

@@ -68,7 +68,15 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
                 const T2 x = h ? x2 : x1;
                 const int kk = h ? (M - k) : k;
                 if (h && kk == k) break;    // k == M/2 pairs with itself
-                if (MODE == MODE_LOGSQ) {
+                if (MODE == MODE_LOGP) {
+                    // log periodograms exactly as the mel product consumes them (SPTK mcep -q 3 / -q 2 with -e 1e-8):
+                    // log(|X|^2 + 1e-8) and log(exp(2 Re/|X|) + 1e-8); SFU work that hides under the FP64 butterflies
+                    T mag, re, im;
+                    normalise(x.x, x.y, mag, re, im);
+                    __stcs(&oa[kk], (TO)__logf(fmaf((float)mag, (float)mag, 1.0e-8f)));
+                    __stcs(&ob[kk], (TO)__logf(__expf(2.0f * (float)re) + 1.0e-8f));
+                    __stcs(&oc[kk], (TO)__logf(__expf(2.0f * (float)im) + 1.0e-8f));
+                } else if (MODE == MODE_LOGSQ) {
                     if (kk != 0 && kk != M) {
                         const T p = x.x * x.x + x.y * x.y;
                         const double lg = p > (T)0 ? 0.5 * (double)log(p) : -1.0e10;   // la.log floor (src/libaudio.py:241-248)
@@ -125,6 +133,20 @@ template <typename T, typename TS, typename TO, int N>
 static cudaError_t launch_analysis_m(const AnalysisArgs& a, cudaStream_t st) {
     return a.mode == MODE_FFT ? launch_analysis_t<T, TS, TO, N, MODE_FFT>(a, st)
                               : launch_analysis_t<T, TS, TO, N, MODE_FEATS>(a, st);
+}
+
+// float32 log periodograms for the fused compressed analysis (float64 butterflies, float32 or float64 signal)
+template <typename TS>
+static cudaError_t launch_logp_n(const AnalysisArgs& a, cudaStream_t st) {
+    switch (a.fft_len) {
+        case 1024: return launch_analysis_t<double, TS, float, 1024, MODE_LOGP>(a, st);
+        case 2048: return launch_analysis_t<double, TS, float, 2048, MODE_LOGP>(a, st);
+        case 4096: return launch_analysis_t<double, TS, float, 4096, MODE_LOGP>(a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_analysis_logp(const AnalysisArgs& a, cudaStream_t st) {
+    return a.sig_dtype == MPB_F64 ? launch_logp_n<double>(a, st) : launch_logp_n<float>(a, st);
 }
 
 template <typename T, typename TS, typename TO>

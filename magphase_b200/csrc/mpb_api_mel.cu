@@ -73,9 +73,22 @@ int mpb_mel_get_warp_matrix(mpb_mel* m, int which, float* out_host) {
     return MPB_OK;
 }
 
+static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const void* real, const void* imag, int feat_dtype,
+                             int pre_logp, const uint8_t* voi, int64_t nfrm, void* out_mag_mel, void* out_real_mel,
+                             void* out_imag_mel, int out_dtype);
+
 int mpb_mel_compress_dev(mpb_mel* m, void* stream, const void* mag, const void* real, const void* imag, int feat_dtype,
                          const uint8_t* voi, int64_t nfrm, void* out_mag_mel, void* out_real_mel, void* out_imag_mel,
                          int out_dtype) {
+    return mel_compress_impl(m, stream, mag, real, imag, feat_dtype, 0, voi, nfrm, out_mag_mel, out_real_mel, out_imag_mel,
+                             out_dtype);
+}
+
+}  // extern "C"
+
+static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const void* real, const void* imag, int feat_dtype,
+                             int pre_logp, const uint8_t* voi, int64_t nfrm, void* out_mag_mel, void* out_real_mel,
+                             void* out_imag_mel, int out_dtype) {
     if (!m) return fail(MPB_ERR_BAD_ARG, "plan is NULL");
     if (!dtype_ok(feat_dtype) || !dtype_ok(out_dtype)) return fail(MPB_ERR_BAD_ARG, "unknown dtype");
     if (nfrm < 0) return fail(MPB_ERR_BAD_ARG, "negative size");
@@ -85,7 +98,7 @@ int mpb_mel_compress_dev(mpb_mel* m, void* stream, const void* mag, const void* 
     CU(cudaSetDevice(m->ctx->device));
     std::lock_guard<std::mutex> lk(m->mu);
     const int H = m->fft_len / 2 + 1;
-    const int n_slices = (H + MEL_KSLICE - 1) / MEL_KSLICE;
+    const int n_slices = (H - 1) / MEL_KSLICE;
     const int ncp = m->ld_mag > m->ld_ph ? m->ld_mag : m->ld_ph;
     const int64_t chunk = nfrm < MEL_CHUNK ? nfrm : MEL_CHUNK;
     CU(m->partial.need(sizeof(float) * 3 * (size_t)n_slices * (size_t)chunk * ncp));
@@ -94,7 +107,7 @@ int mpb_mel_compress_dev(mpb_mel* m, void* stream, const void* mag, const void* 
         const int64_t n = nfrm - f0 < chunk ? nfrm - f0 : chunk;
         MelArgs a;
         a.mag = (const char*)mag + fes * f0 * H; a.real = (const char*)real + fes * f0 * H;
-        a.imag = (const char*)imag + fes * f0 * H; a.feat_dtype = feat_dtype;
+        a.imag = (const char*)imag + fes * f0 * H; a.feat_dtype = feat_dtype; a.pre_logp = pre_logp;
         a.voi = voi + f0; a.nfrm = n; a.fft_len = m->fft_len;
         a.wt_mag = m->wt_mag; a.ld_mag = m->ld_mag; a.wt_ph = m->wt_ph; a.ld_ph = m->ld_ph;
         a.cos_mag = m->cos_mag; a.n_mag = m->n_mag; a.cos_ph = m->cos_ph; a.n_ph = m->n_ph; a.phase_dim = m->phase_dim;
@@ -105,6 +118,49 @@ int mpb_mel_compress_dev(mpb_mel* m, void* stream, const void* mag, const void* 
         a.out_dtype = out_dtype;
         LAUNCH(m->ctx, (cudaStream_t)stream, "k_mel_gemm", launch_mel_gemm(a, (cudaStream_t)stream));
         LAUNCH(m->ctx, (cudaStream_t)stream, "k_mel_finish", launch_mel_finish(a, (cudaStream_t)stream));
+    }
+    return MPB_OK;
+}
+
+extern "C" {
+
+// analysis_compressed on the device for a batch of frames: signal + frame geometry (device pointers) in,
+// low-dimensional features out.  Per chunk of frames: k_analysis (float64 butterflies) emits float32 log
+// periodograms into a plan-owned scratch, k_mel_gemm / k_mel_finish reduce them to mag_dim + 2*phase_dim values.
+int mpb_analysis_compressed_dev(mpb_mel* m, void* stream, const void* sig, int sig_dtype, int64_t n_sig,
+                                const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* voi,
+                                int64_t nfrm, void* out_mag_mel, void* out_real_mel, void* out_imag_mel, int out_dtype) {
+    if (!m) return fail(MPB_ERR_BAD_ARG, "plan is NULL");
+    if (!dtype_ok(sig_dtype) || !dtype_ok(out_dtype) || nfrm < 0 || n_sig < 0) return fail(MPB_ERR_BAD_ARG, "bad dtype or size");
+    if (nfrm == 0) return MPB_OK;
+    if (!sig || !centre || !left || !right || !voi || !out_mag_mel || !out_real_mel || !out_imag_mel)
+        return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    mpb_ctx* ctx = m->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const int H = m->fft_len / 2 + 1;
+    const int64_t chunk = nfrm < MEL_CHUNK ? nfrm : MEL_CHUNK;
+    {
+        std::lock_guard<std::mutex> lk(m->mu);
+        for (int i = 0; i < 3; ++i) CU(m->feats[i].need(sizeof(float) * (size_t)chunk * H));
+    }
+    const void* tw = nullptr;
+    int rc = get_twiddles(ctx, m->fft_len, MPB_F64, &tw);
+    if (rc != MPB_OK) return rc;
+    const size_t oes = out_dtype == MPB_F64 ? 8 : 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t f0 = 0; f0 < nfrm; f0 += chunk) {
+        const int64_t n = nfrm - f0 < chunk ? nfrm - f0 : chunk;
+        AnalysisArgs a;
+        a.sig = sig; a.sig_dtype = sig_dtype; a.n_sig = n_sig;
+        a.centre = centre + f0; a.left = left + f0; a.right = right + f0; a.win = nullptr;
+        a.nfrm = n; a.fft_len = m->fft_len; a.compute_dtype = MPB_F64; a.tw = tw;
+        a.out_a = m->feats[0].p; a.out_b = m->feats[1].p; a.out_c = m->feats[2].p; a.out_dtype = MPB_F32;
+        a.mode = MODE_LOGP; a.num_sms = ctx->num_sms;
+        LAUNCH(ctx, st, "k_analysis<logp>", launch_analysis_logp(a, st));
+        rc = mel_compress_impl(m, stream, m->feats[0].p, m->feats[1].p, m->feats[2].p, MPB_F32, 1, voi + f0, n,
+                               (char*)out_mag_mel + oes * f0 * m->n_mag, (char*)out_real_mel + oes * f0 * m->phase_dim,
+                               (char*)out_imag_mel + oes * f0 * m->phase_dim, out_dtype);
+        if (rc != MPB_OK) return rc;
     }
     return MPB_OK;
 }
@@ -181,7 +237,6 @@ int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const i
     const int H = m->fft_len / 2 + 1;
     cudaStream_t st = ctx->stream;
     const int64_t chunk = nfrm < MEL_CHUNK ? nfrm : MEL_CHUNK;
-    for (int i = 0; i < 3; ++i) CU(m->feats[i].need(sizeof(float) * (size_t)chunk * H));
     CU(m->small[0].need((size_t)nfrm));
     CU(m->small[1].need(sizeof(double) * nfrm * m->n_mag));
     CU(m->small[2].need(sizeof(double) * nfrm * m->phase_dim));
@@ -201,18 +256,11 @@ int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const i
     CU(cudaMemcpyAsync(m->small[6].p, left, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(m->small[7].p, right, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(m->small[0].p, voi, (size_t)nfrm, cudaMemcpyHostToDevice, st));
-    for (int64_t f0 = 0; f0 < nfrm; f0 += chunk) {
-        const int64_t n = nfrm - f0 < chunk ? nfrm - f0 : chunk;
-        rc = analysis_common(ctx, st, m->small[4].p, MPB_F64, n_sig, (const int64_t*)m->small[5].p + f0,
-                             (const int32_t*)m->small[6].p + f0, (const int32_t*)m->small[7].p + f0, nullptr, n,
-                             m->fft_len, compute_dtype, m->feats[0].p, m->feats[1].p, m->feats[2].p, MPB_F32, MODE_FEATS);
-        if (rc != MPB_OK) return rc;
-        rc = mpb_mel_compress_dev(m, st, m->feats[0].p, m->feats[1].p, m->feats[2].p, MPB_F32,
-                                  (const uint8_t*)m->small[0].p + f0, n, (double*)m->small[1].p + f0 * m->n_mag,
-                                  (double*)m->small[2].p + f0 * m->phase_dim, (double*)m->small[3].p + f0 * m->phase_dim,
-                                  MPB_F64);
-        if (rc != MPB_OK) return rc;
-    }
+    (void)compute_dtype;   // the fused path always runs float64 butterflies
+    rc = mpb_analysis_compressed_dev(m, st, m->small[4].p, MPB_F64, n_sig, (const int64_t*)m->small[5].p,
+                                     (const int32_t*)m->small[6].p, (const int32_t*)m->small[7].p,
+                                     (const uint8_t*)m->small[0].p, nfrm, m->small[1].p, m->small[2].p, m->small[3].p, MPB_F64);
+    if (rc != MPB_OK) return rc;
     CU(cudaMemcpyAsync(out_mag_mel, m->small[1].p, sizeof(double) * nfrm * m->n_mag, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(out_real_mel, m->small[2].p, sizeof(double) * nfrm * m->phase_dim, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(out_imag_mel, m->small[3].p, sizeof(double) * nfrm * m->phase_dim, cudaMemcpyDeviceToHost, st));

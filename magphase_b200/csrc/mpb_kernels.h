@@ -7,7 +7,7 @@
 
 namespace mpb {
 
-enum { MODE_FEATS = 0, MODE_FFT = 1, MODE_LOGSQ = 2 };
+enum { MODE_FEATS = 0, MODE_FFT = 1, MODE_LOGSQ = 2, MODE_LOGP = 3 };
 
 struct AnalysisArgs {
     const void* sig; int sig_dtype; int64_t n_sig;
@@ -15,11 +15,13 @@ struct AnalysisArgs {
     int64_t nfrm; int fft_len; int compute_dtype;
     const void* tw;                 // twiddle table in the compute precision
     void* out_a; void* out_b; void* out_c; int out_dtype;
-    int mode;                       // MODE_FEATS: a=mag b=real c=imag;  MODE_FFT: a=interleaved complex
+    int mode;                       // MODE_FEATS: a=mag b=real c=imag;  MODE_FFT: a=interleaved complex;
+                                    // MODE_LOGP: a,b,c = log periodograms of mag/real/imag as SPTK mcep sees them (float32)
     int num_sms;
 };
 cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st);
 cudaError_t launch_noise_stats(const AnalysisArgs& a, cudaStream_t st);   // out_a: double[nfrm]
+cudaError_t launch_analysis_logp(const AnalysisArgs& a, cudaStream_t st);  // float64 compute, float32 log periodograms
 
 // One OLA run = consecutive frames of one utterance handled by one CTA (see mpb_synthesis.cu).
 struct OlaRun {
@@ -47,10 +49,11 @@ constexpr int MEL_MAX_COEFFS = 128;    // largest supported mag_dim / nmel
 
 struct MelArgs {
     const void* mag; const void* real; const void* imag; int feat_dtype;   // nfrm x (fft_len/2+1)
+    int pre_logp;                                                           // rows already hold log periodograms
     const uint8_t* voi; int64_t nfrm; int fft_len;
     const float* wt_mag; int ld_mag; const float* wt_ph; int ld_ph;         // W^T, [kpad][ld] float32
     const double* cos_mag; int n_mag; const double* cos_ph; int n_ph; int phase_dim;
-    float* partial; int ncp_max;                                            // [3][slices][nfrm][ncp_max]
+    float* partial; int ncp_max;                                            // [3][nfrm][slices][ncp_max]
     void* out_mag; void* out_real; void* out_imag; int out_dtype;
 };
 cudaError_t build_warp_matrix(int fft_len, int n_out, double alpha, float* wt32, double* scratch64, int ld,

@@ -62,12 +62,11 @@ cudaError_t build_warp_matrix(int fft_len, int n_out, double alpha, float* wt32,
 // ---- tile product -----------------------------------------------------------------------------
 // log periodogram of one feature value as SPTK sees it (float32 input file):
 //   in_type 3 (|X|):   log(x^2 + 1e-8)            in_type 2 (ln|X|):  log(exp(2x) + 1e-8)
-template <int IN_TYPE>
-__device__ __forceinline__ float log_periodogram(float x) {
-    if (IN_TYPE == 3) return __logf(fmaf(x, x, 1.0e-8f));   // |rel err| <= 3 ulp: far below the float32 data noise
-    // 2x + log1p(1e-8 * exp(-2x)): exact to float precision for the |x| <= ~1 phase features, safe elsewhere
-    const float e = 1.0e-8f * __expf(-2.0f * x);
-    return (e < 1.0e-3f) ? fmaf(2.0f, x, e - 0.5f * e * e) : logf(expf(2.0f * x) + 1.0e-8f);
+// Fast intrinsics: their error (<= ~1e-6 absolute on the log) is far below the float32 noise of the data and is
+// attenuated by the warp matrix (row norms ~1e-2).
+__device__ __forceinline__ float log_periodogram(float x, bool is_mag) {
+    const float t = is_mag ? x * x : __expf(2.0f * x);
+    return __logf(t + 1.0e-8f);
 }
 
 constexpr int GEMM_FT = 128;          // frames per CTA tile
@@ -75,8 +74,9 @@ constexpr int GEMM_CT = 64;           // coefficients per CTA tile
 constexpr int GEMM_LDL = GEMM_FT + 4; // pitch of the transposed log-periodogram tile (floats)
 constexpr int GEMM_KS = 64;           // bins per shared-memory stage
 
-// grid: (frame tiles, K slices * coefficient tiles, 3 streams)
-template <typename TF>
+// grid: (frame tiles, K slices * coefficient tiles, 3 streams).  The K slices cover bins 0 .. H-2 (H-1 = N/2 is a
+// multiple of MEL_KSLICE); the Nyquist bin is added by k_mel_finish.  PRE: rows already hold log periodograms.
+template <typename TF, bool PRE>
 __global__ void __launch_bounds__(128, 4)
 k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __restrict__ imag, int64_t nfrm, int H,
            const float* __restrict__ wt_mag, int ld_mag, const float* __restrict__ wt_ph, int ld_ph,
@@ -93,6 +93,7 @@ k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __
     if (ctile * GEMM_CT >= ld) return;
     const int64_t f0 = (int64_t)blockIdx.x * GEMM_FT;
     const int k0 = slice * MEL_KSLICE;
+    const bool full = f0 + GEMM_FT <= nfrm;              // interior tile: no row predicate needed
 
     const int tf = tid >> 3, tc = tid & 7;
     float acc[8][8];
@@ -111,33 +112,31 @@ k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __
             reinterpret_cast<float4*>(Bs)[i] =
                 __ldg(reinterpret_cast<const float4*>(wt + (size_t)(k0 + ks + kk) * ld + ctile * GEMM_CT) + c4);
         }
-        // ---- stage the log-periodogram tile transposed: Ls[kk][f]; a warp takes 4 frames x 32 bins per step.
-        // 32 loads are issued before their first use (two DRAM latencies per stage, overlapped across 4 CTAs/SM). ----
+        // ---- stage the log-periodogram tile transposed: Ls[kk][f]; a warp takes 4 frames x 32 bins per step;
+        // 32 loads are issued before their first use (two DRAM latencies per stage, overlapped across 4 CTAs/SM) ----
 #pragma unroll 1
         for (int gh = 0; gh < 8; gh += 4) {
             float raw[4][2][4];                          // [frame group][bin chunk][frame in group]
+            const TF* __restrict__ p0 = src + (f0 + gh * 16 + warp * 4) * (int64_t)H + k0 + ks + lane;
 #pragma unroll
             for (int g = 0; g < 4; ++g)
 #pragma unroll
                 for (int c = 0; c < GEMM_KS / 32; ++c)
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const int64_t f = f0 + (gh + g) * 16 + warp * 4 + r;
-                        const int k = k0 + ks + c * 32 + lane;
-                        raw[g][c][r] = (f < nfrm && k < H) ? (float)__ldcs(src + f * (int64_t)H + k) : 0.0f;
+                        const bool ok = full || (f0 + (gh + g) * 16 + warp * 4 + r < nfrm);
+                        raw[g][c][r] = ok ? (float)__ldcs(p0 + (g * 16 + r) * (int64_t)H + c * 32) : 0.0f;
                     }
 #pragma unroll
             for (int g = 0; g < 4; ++g)
 #pragma unroll
                 for (int c = 0; c < GEMM_KS / 32; ++c) {
-                    const int k = k0 + ks + c * 32 + lane;
                     float4 v;
                     float* pv = &v.x;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const int64_t f = f0 + (gh + g) * 16 + warp * 4 + r;
-                        const float x = stream == 0 ? log_periodogram<3>(raw[g][c][r]) : log_periodogram<2>(raw[g][c][r]);
-                        pv[r] = (f < nfrm && k < H) ? x : 0.0f;
+                        const bool ok = full || (f0 + (gh + g) * 16 + warp * 4 + r < nfrm);
+                        pv[r] = PRE ? raw[g][c][r] : (ok ? log_periodogram(raw[g][c][r], stream == 0) : 0.0f);
                     }
                     *reinterpret_cast<float4*>(Ls + (c * 32 + lane) * GEMM_LDL + (gh + g) * 16 + warp * 4) = v;
                 }
@@ -161,23 +160,25 @@ k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __
                 for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
     }
-    // ---- partial[stream][slice][f][ncp_max] ----
-    float* out = partial + ((size_t)stream * n_slices + slice) * (size_t)nfrm * ncp_max;
+    // ---- partial[stream][f][slice][ncp_max] ----
+    float* out = partial + (size_t)stream * (size_t)nfrm * n_slices * ncp_max + (size_t)slice * ncp_max + ctile * GEMM_CT;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int64_t f = f0 + (i < 4 ? tf * 4 + i : 64 + tf * 4 + (i - 4));
         if (f >= nfrm) continue;
-        float* po = out + (size_t)f * ncp_max + ctile * GEMM_CT;
+        float* po = out + (size_t)f * n_slices * ncp_max;
         *reinterpret_cast<float4*>(po + tc * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         *reinterpret_cast<float4*>(po + 32 + tc * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
     }
 }
 
 // ---- finish -------------------------------------------------------------------------------------
-// one warp per (frame, stream): mc[j] = float32(sum over slices), out[o] = sum_j mc[j] cos_tab[j][o]
-template <typename TO>
+// one warp per (frame, stream): mc[j] = float32(sum over K slices + Nyquist-bin term), out[o] = sum_j mc[j] cos_tab[j][o]
+template <typename TF, typename TO, bool PRE>
 __global__ void __launch_bounds__(128)
 k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64_t nfrm,
+             const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __restrict__ imag, int H,
+             const float* __restrict__ wt_mag, int ld_mag, const float* __restrict__ wt_ph, int ld_ph,
              const double* __restrict__ cos_mag, int n_mag, const double* __restrict__ cos_ph, int n_ph, int phase_dim,
              const uint8_t* __restrict__ voi, TO* __restrict__ out_mag, TO* __restrict__ out_real, TO* __restrict__ out_imag) {
     __shared__ double mc[4][MEL_MAX_COEFFS];
@@ -188,10 +189,15 @@ k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64
     const int n_in = stream == 0 ? n_mag : n_ph;
     const int n_out = stream == 0 ? n_mag : phase_dim;
     const double* __restrict__ ct = stream == 0 ? cos_mag : cos_ph;      // [n_in][n_out]
+    const TF* __restrict__ src = stream == 0 ? mag : (stream == 1 ? real : imag);
+    const float* __restrict__ wt = stream == 0 ? wt_mag : wt_ph;
+    const int ld = stream == 0 ? ld_mag : ld_ph;
+    const float xl = (float)src[f * (int64_t)H + (H - 1)];
+    const float last = PRE ? xl : log_periodogram(xl, stream == 0);       // Nyquist bin, not covered by the K slices
+    const float* __restrict__ pp = partial + ((size_t)stream * (size_t)nfrm + (size_t)f) * n_slices * ncp_max;
     for (int j = lane; j < n_in; j += 32) {
-        double s = 0.0;
-        for (int sl = 0; sl < n_slices; ++sl)
-            s += (double)partial[(((size_t)stream * n_slices + sl) * (size_t)nfrm + f) * ncp_max + j];
+        double s = (double)last * (double)wt[(size_t)(H - 1) * ld + j];
+        for (int sl = 0; sl < n_slices; ++sl) s += (double)pp[sl * ncp_max + j];
         mc[warp][j] = (double)(float)s;                                    // SPTK writes float32 (src/libaudio.py:593)
     }
     __syncwarp();
@@ -210,42 +216,44 @@ k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64
     }
 }
 
-cudaError_t launch_mel_gemm(const MelArgs& a, cudaStream_t st) {
+template <typename TF, bool PRE>
+static cudaError_t launch_gemm_t(const MelArgs& a, cudaStream_t st) {
     const int H = a.fft_len / 2 + 1;
-    const int n_slices = (H + MEL_KSLICE - 1) / MEL_KSLICE;
+    const int n_slices = (H - 1) / MEL_KSLICE;
     const int ctiles = (a.ncp_max + GEMM_CT - 1) / GEMM_CT;
     const size_t smem = sizeof(float) * (GEMM_KS * GEMM_LDL + GEMM_KS * GEMM_CT);
     dim3 grid((unsigned)((a.nfrm + GEMM_FT - 1) / GEMM_FT), (unsigned)(n_slices * ctiles), 3);
-    cudaError_t e;
-    if (a.feat_dtype == MPB_F64) {
-        e = cudaFuncSetAttribute(k_mel_gemm<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_mel_gemm<double><<<grid, 128, smem, st>>>((const double*)a.mag, (const double*)a.real, (const double*)a.imag,
-                                                    a.nfrm, H, a.wt_mag, a.ld_mag, a.wt_ph, a.ld_ph, a.partial, n_slices,
-                                                    a.ncp_max);
-    } else {
-        e = cudaFuncSetAttribute(k_mel_gemm<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_mel_gemm<float><<<grid, 128, smem, st>>>((const float*)a.mag, (const float*)a.real, (const float*)a.imag,
-                                                   a.nfrm, H, a.wt_mag, a.ld_mag, a.wt_ph, a.ld_ph, a.partial, n_slices,
-                                                   a.ncp_max);
-    }
+    auto kern = k_mel_gemm<TF, PRE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 128, smem, st>>>((const TF*)a.mag, (const TF*)a.real, (const TF*)a.imag, a.nfrm, H, a.wt_mag, a.ld_mag,
+                                  a.wt_ph, a.ld_ph, a.partial, n_slices, a.ncp_max);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mel_gemm(const MelArgs& a, cudaStream_t st) {
+    if (a.feat_dtype == MPB_F64) return launch_gemm_t<double, false>(a, st);
+    return a.pre_logp ? launch_gemm_t<float, true>(a, st) : launch_gemm_t<float, false>(a, st);
+}
+
+template <typename TF, typename TO, bool PRE>
+static cudaError_t launch_finish_t(const MelArgs& a, cudaStream_t st) {
+    const int H = a.fft_len / 2 + 1;
+    const int n_slices = (H - 1) / MEL_KSLICE;
+    dim3 g2((unsigned)((a.nfrm + 3) / 4), 3);
+    k_mel_finish<TF, TO, PRE><<<g2, 128, 0, st>>>(a.partial, n_slices, a.ncp_max, a.nfrm, (const TF*)a.mag, (const TF*)a.real,
+                                                   (const TF*)a.imag, H, a.wt_mag, a.ld_mag, a.wt_ph, a.ld_ph, a.cos_mag,
+                                                   a.n_mag, a.cos_ph, a.n_ph, a.phase_dim, a.voi, (TO*)a.out_mag,
+                                                   (TO*)a.out_real, (TO*)a.out_imag);
     return cudaGetLastError();
 }
 
 cudaError_t launch_mel_finish(const MelArgs& a, cudaStream_t st) {
-    const int H = a.fft_len / 2 + 1;
-    const int n_slices = (H + MEL_KSLICE - 1) / MEL_KSLICE;
-    dim3 g2((unsigned)((a.nfrm + 3) / 4), 3);
-    if (a.out_dtype == MPB_F64)
-        k_mel_finish<double><<<g2, 128, 0, st>>>(a.partial, n_slices, a.ncp_max, a.nfrm, a.cos_mag, a.n_mag, a.cos_ph,
-                                                 a.n_ph, a.phase_dim, a.voi, (double*)a.out_mag, (double*)a.out_real,
-                                                 (double*)a.out_imag);
-    else
-        k_mel_finish<float><<<g2, 128, 0, st>>>(a.partial, n_slices, a.ncp_max, a.nfrm, a.cos_mag, a.n_mag, a.cos_ph,
-                                                a.n_ph, a.phase_dim, a.voi, (float*)a.out_mag, (float*)a.out_real,
-                                                (float*)a.out_imag);
-    return cudaGetLastError();
+    if (a.feat_dtype == MPB_F64)
+        return a.out_dtype == MPB_F64 ? launch_finish_t<double, double, false>(a, st) : launch_finish_t<double, float, false>(a, st);
+    if (a.pre_logp)
+        return a.out_dtype == MPB_F64 ? launch_finish_t<float, double, true>(a, st) : launch_finish_t<float, float, true>(a, st);
+    return a.out_dtype == MPB_F64 ? launch_finish_t<float, double, false>(a, st) : launch_finish_t<float, float, false>(a, st);
 }
 
 }  // namespace mpb

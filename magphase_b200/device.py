@@ -153,8 +153,7 @@ class CompressedPlan:
         rs = np.random.RandomState(noise_seed)
         self.h_noise = [rs.uniform(-1, 1, n) for n in self.l_ns_len]
         self.d_noise = up(np.concatenate(self.h_noise), np.float32)
-        # intermediates that live in HBM between the two halves
-        self.d_lossless = tuple(torch.empty((self.nfrm, self.H), dtype=torch.float32, device=self.device) for _ in range(3))
+        # the compressed features live in HBM between the two halves
         self.d_mel = (torch.empty((self.nfrm, mag_dim), dtype=torch.float32, device=self.device),
                       torch.empty((self.nfrm, phase_dim), dtype=torch.float32, device=self.device),
                       torch.empty((self.nfrm, phase_dim), dtype=torch.float32, device=self.device))
@@ -168,15 +167,12 @@ class CompressedPlan:
         return self.nfrm * (self.mag_dim + 2 * self.phase_dim) * 4 + self.nfrm * 45 + self.n_noise * 4 + self.n_out * 4
 
     def analysis(self, d_sig, compute=MPB_F64):
-        lib = _lib.lib()
+        """k_analysis<logp> -> k_mel_gemm -> k_mel_finish per chunk of frames (float64 butterflies)."""
         sig_dt = MPB_F64 if d_sig.dtype == torch.float64 else MPB_F32
-        f = self.d_lossless
-        _lib.check(lib.mpb_analysis_lossless_dev(
-            self.ctx, _stream(), _dp(d_sig), sig_dt, self.n_sig, _dp(self.d_centre), _dp(self.d_left), _dp(self.d_right),
-            None, self.nfrm, self.fft_len, compute, _dp(f[0]), _dp(f[1]), _dp(f[2]), MPB_F32))
-        _lib.check(lib.mpb_mel_compress_dev(self.mel.handle, _stream(), _dp(f[0]), _dp(f[1]), _dp(f[2]), MPB_F32,
-                                            _dp(self.d_voi_ana), self.nfrm, _dp(self.d_mel[0]), _dp(self.d_mel[1]),
-                                            _dp(self.d_mel[2]), MPB_F32))
+        _lib.check(_lib.lib().mpb_analysis_compressed_dev(
+            self.mel.handle, _stream(), _dp(d_sig), sig_dt, self.n_sig, _dp(self.d_centre), _dp(self.d_left),
+            _dp(self.d_right), _dp(self.d_voi_ana), self.nfrm, _dp(self.d_mel[0]), _dp(self.d_mel[1]), _dp(self.d_mel[2]),
+            MPB_F32))
         return self.d_mel
 
     def synthesis(self, d_mel=None):
