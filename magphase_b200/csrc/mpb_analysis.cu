@@ -12,7 +12,7 @@ namespace mpb {
 
 template <typename T, int N> struct KernelCfg {
     // register budget: 128 regs/thread for float64 butterflies, ~85 for float32
-    static constexpr int MINB = (sizeof(T) == 8 ? 512 : 768) / FftGeom<T, N>::TPB;
+    static constexpr int MINB = (sizeof(T) == 8 ? 640 : 768) / FftGeom<T, N>::TPB;
 };
 
 template <typename T, typename TS, typename TO, int N, int MODE>

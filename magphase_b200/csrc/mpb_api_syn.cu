@@ -80,9 +80,10 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
         !fr->utt_out_off || !fr->utt_t0)
         return fail(MPB_ERR_BAD_ARG, "NULL buffer");
     std::lock_guard<std::mutex> lk(s->mu);
-    CU(s->unw[0].need(sizeof(float) * (size_t)n_rows * s->H));
-    CU(s->unw[1].need(sizeof(float) * (size_t)n_rows * s->HB));
-    CU(s->unw[2].need(sizeof(float) * (size_t)n_rows * s->HB));
+    const int HP = (s->H + 3) & ~3, HBP = (s->HB + 3) & ~3;      // scratch row pitches: 16-byte aligned rows
+    CU(s->unw[0].need(sizeof(float) * (size_t)n_rows * HP));
+    CU(s->unw[1].need(sizeof(float) * (size_t)n_rows * HBP));
+    CU(s->unw[2].need(sizeof(float) * (size_t)n_rows * HBP));
     CU(s->logsq.need(sizeof(double) * (size_t)fr->nfrm));
     CU(s->gain.need(sizeof(double) * 2 * (size_t)fr->n_utt));
 
@@ -91,6 +92,7 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
     u.need_ph = need_ph; u.nfrm = n_rows; u.n_mag = s->n_mag; u.n_ph = s->n_ph;
     u.u_mag = s->u_mag; u.H = s->H; u.u_ph = s->u_ph; u.HB = s->HB;
     u.out_mag = (float*)s->unw[0].p; u.out_real = (float*)s->unw[1].p; u.out_imag = (float*)s->unw[2].p;
+    u.HP = HP; u.HBP = HBP;
     LAUNCH(ctx, st, "k_mel_unwarp", launch_mel_unwarp(u, st));
 
     const void* tw = nullptr;
@@ -105,7 +107,7 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
     LAUNCH(ctx, st, "k_analysis<noise_logsq>", launch_noise_stats(n, st));
 
     SynthCompArgs a;
-    a.m_mag = u.out_mag; a.m_real = u.out_real; a.m_imag = u.out_imag; a.H = s->H; a.HB = s->HB;
+    a.m_mag = u.out_mag; a.m_real = u.out_real; a.m_imag = u.out_imag; a.H = s->H; a.HB = s->HB; a.HP = HP; a.HBP = HBP;
     a.noise = noise; a.n_noise = n_noise;
     a.pm = fr->pm; a.ncentre = fr->ncentre; a.nleft = fr->nleft; a.nright = fr->nright;
     a.voi = fr->voi; a.nkind = fr->nkind; a.win_a = fr->win_a; a.win_b = fr->win_b;
@@ -118,8 +120,8 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
         const void* tw64 = nullptr;
         rc = get_twiddles(ctx, s->fft_len, MPB_F64, &tw64);
         if (rc != MPB_OK) return rc;
-        LAUNCH(ctx, st, "k_min_phase", launch_min_phase_split(s->fft_len, u.out_mag, n_rows, tw64, u.out_real, u.out_imag,
-                                                               s->HB, ctx->num_sms, st));
+        LAUNCH(ctx, st, "k_min_phase", launch_min_phase_split(s->fft_len, u.out_mag, HP, n_rows, tw64, u.out_real, u.out_imag,
+                                                               s->HB, HBP, ctx->num_sms, st));
     }
     a.out = out; a.out_dtype = out_dtype; a.n_out = n_out; a.num_sms = ctx->num_sms;
     LAUNCH(ctx, st, "k_noise_gain", launch_noise_gain(a, st));

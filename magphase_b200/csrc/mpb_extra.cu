@@ -50,8 +50,8 @@ cudaError_t launch_post_filter(const void* x, int dtype, int64_t nfrm, int dim, 
 // which the compressed synthesis kernel consumes for per_phase_type='min_phase'.
 template <typename TI, typename TO, int N, int OUT_MODE>
 __global__ void __launch_bounds__(FftGeom<double, N>::TPB, 384 / FftGeom<double, N>::TPB)
-k_min_phase(const TI* __restrict__ mag, int64_t nfrm, const double2* __restrict__ tw, TO* __restrict__ out_a,
-            TO* __restrict__ out_b, int nb) {
+k_min_phase(const TI* __restrict__ mag, int in_pitch, int64_t nfrm, const double2* __restrict__ tw, TO* __restrict__ out_a,
+            TO* __restrict__ out_b, int nb, int out_pitch) {
     using T = double;
     using G = FftGeom<T, N>;
     using T2 = double2;
@@ -71,7 +71,7 @@ k_min_phase(const TI* __restrict__ mag, int64_t nfrm, const double2* __restrict_
     T* bufT = reinterpret_cast<T*>(buf);
 
     for (int64_t f = blockIdx.x; f < nfrm; f += gridDim.x) {
-        const TI* __restrict__ row = mag + f * (int64_t)H;
+        const TI* __restrict__ row = mag + f * (int64_t)in_pitch;
         // ---- log magnitude (protected like la.log) packed for the Hermitian inverse transform ----
         auto lg = [&](int k) {
             const double m = (double)row[k];
@@ -134,8 +134,8 @@ k_min_phase(const TI* __restrict__ mag, int64_t nfrm, const double2* __restrict_
                     out_a[2 * (f * (int64_t)H + kk)] = (TO)(m * c);
                     out_a[2 * (f * (int64_t)H + kk) + 1] = (TO)(m * s);
                 } else {
-                    out_a[f * (int64_t)nb + kk] = (TO)(m * c);
-                    out_b[f * (int64_t)nb + kk] = (TO)(m * s);
+                    out_a[f * (int64_t)out_pitch + kk] = (TO)(m * c);
+                    out_b[f * (int64_t)out_pitch + kk] = (TO)(m * s);
                 }
             }
         }
@@ -144,8 +144,8 @@ k_min_phase(const TI* __restrict__ mag, int64_t nfrm, const double2* __restrict_
 }
 
 template <typename TI, typename TO, int N, int OUT_MODE>
-static cudaError_t launch_mp_t(const void* mag, int64_t nfrm, const void* tw, void* out_a, void* out_b, int nb, int num_sms,
-                               cudaStream_t st) {
+static cudaError_t launch_mp_t(const void* mag, int in_pitch, int64_t nfrm, const void* tw, void* out_a, void* out_b, int nb,
+                               int out_pitch, int num_sms, cudaStream_t st) {
     using G = FftGeom<double, N>;
     const size_t smem = sizeof(double2) * (G::BUF_ELEMS + 2 * G::TW2_ELEMS);
     auto kern = k_min_phase<TI, TO, N, OUT_MODE>;
@@ -157,17 +157,18 @@ static cudaError_t launch_mp_t(const void* mag, int64_t nfrm, const void* tw, vo
     int64_t grid = (int64_t)num_sms * (per_sm < 1 ? 1 : per_sm);
     if (grid > nfrm) grid = nfrm;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, G::TPB, smem, st>>>((const TI*)mag, nfrm, (const double2*)tw, (TO*)out_a, (TO*)out_b, nb);
+    kern<<<(unsigned)grid, G::TPB, smem, st>>>((const TI*)mag, in_pitch ? in_pitch : N / 2 + 1, nfrm, (const double2*)tw,
+                                               (TO*)out_a, (TO*)out_b, nb, out_pitch);
     return cudaGetLastError();
 }
 
 template <typename TI, typename TO, int OUT_MODE>
-static cudaError_t launch_mp_n(int fft_len, const void* mag, int64_t nfrm, const void* tw, void* out_a, void* out_b, int nb,
-                               int num_sms, cudaStream_t st) {
+static cudaError_t launch_mp_n(int fft_len, const void* mag, int in_pitch, int64_t nfrm, const void* tw, void* out_a,
+                               void* out_b, int nb, int out_pitch, int num_sms, cudaStream_t st) {
     switch (fft_len) {
-        case 1024: return launch_mp_t<TI, TO, 1024, OUT_MODE>(mag, nfrm, tw, out_a, out_b, nb, num_sms, st);
-        case 2048: return launch_mp_t<TI, TO, 2048, OUT_MODE>(mag, nfrm, tw, out_a, out_b, nb, num_sms, st);
-        case 4096: return launch_mp_t<TI, TO, 4096, OUT_MODE>(mag, nfrm, tw, out_a, out_b, nb, num_sms, st);
+        case 1024: return launch_mp_t<TI, TO, 1024, OUT_MODE>(mag, in_pitch, nfrm, tw, out_a, out_b, nb, out_pitch, num_sms, st);
+        case 2048: return launch_mp_t<TI, TO, 2048, OUT_MODE>(mag, in_pitch, nfrm, tw, out_a, out_b, nb, out_pitch, num_sms, st);
+        case 4096: return launch_mp_t<TI, TO, 4096, OUT_MODE>(mag, in_pitch, nfrm, tw, out_a, out_b, nb, out_pitch, num_sms, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -175,14 +176,14 @@ static cudaError_t launch_mp_n(int fft_len, const void* mag, int64_t nfrm, const
 // complex rows out (dtype of input and output: MPB_F32 -> complex64, MPB_F64 -> complex128)
 cudaError_t launch_min_phase(int fft_len, const void* mag, int dtype, int64_t nfrm, const void* tw64, void* out_cplx,
                              int num_sms, cudaStream_t st) {
-    return dtype == MPB_F64 ? launch_mp_n<double, double, 0>(fft_len, mag, nfrm, tw64, out_cplx, nullptr, 0, num_sms, st)
-                            : launch_mp_n<float, float, 0>(fft_len, mag, nfrm, tw64, out_cplx, nullptr, 0, num_sms, st);
+    return dtype == MPB_F64 ? launch_mp_n<double, double, 0>(fft_len, mag, 0, nfrm, tw64, out_cplx, nullptr, 0, 0, num_sms, st)
+                            : launch_mp_n<float, float, 0>(fft_len, mag, 0, nfrm, tw64, out_cplx, nullptr, 0, 0, num_sms, st);
 }
 
 // float32 rows in, leading nb bins of Re / Im out (float32): feeds k_synthesis_compressed
-cudaError_t launch_min_phase_split(int fft_len, const float* mag, int64_t nfrm, const void* tw64, float* out_re, float* out_im,
-                                   int nb, int num_sms, cudaStream_t st) {
-    return launch_mp_n<float, float, 1>(fft_len, mag, nfrm, tw64, out_re, out_im, nb, num_sms, st);
+cudaError_t launch_min_phase_split(int fft_len, const float* mag, int in_pitch, int64_t nfrm, const void* tw64, float* out_re,
+                                   float* out_im, int nb, int out_pitch, int num_sms, cudaStream_t st) {
+    return launch_mp_n<float, float, 1>(fft_len, mag, in_pitch, nfrm, tw64, out_re, out_im, nb, out_pitch, num_sms, st);
 }
 
 }  // namespace mpb

@@ -66,12 +66,13 @@ struct UnwarpArgs {
     const void* mag_mel; const void* real_mel; const void* imag_mel; int in_dtype;   // [nfrm][n_mag], [nfrm][n_ph]
     const uint8_t* need_ph; int64_t nfrm; int n_mag; int n_ph;
     const float* u_mag; int H; const float* u_ph; int HB;                           // [n_mag][H], [n_ph][HB]
-    float* out_mag; float* out_real; float* out_imag;                               // [nfrm][H], [nfrm][HB] x2
+    float* out_mag; float* out_real; float* out_imag;                               // [nfrm][HP], [nfrm][HBP] x2
+    int HP; int HBP;                                                                // row pitches (multiples of 4 floats)
 };
 cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st);
 
 struct SynthCompArgs {
-    const float* m_mag; const float* m_real; const float* m_imag; int H; int HB;
+    const float* m_mag; const float* m_real; const float* m_imag; int H; int HB; int HP; int HBP;
     const float* noise; int64_t n_noise;
     const int32_t* pm; const int64_t* ncentre; const int32_t* nleft; const int32_t* nright;
     const uint8_t* voi; const uint8_t* nkind; const int32_t* win_a; const int32_t* win_b;
@@ -94,8 +95,8 @@ cudaError_t launch_post_filter(const void* x, int dtype, int64_t nfrm, int dim, 
                                const double* tilt, void* out, cudaStream_t st);
 cudaError_t launch_min_phase(int fft_len, const void* mag, int dtype, int64_t nfrm, const void* tw64, void* out_cplx,
                              int num_sms, cudaStream_t st);
-cudaError_t launch_min_phase_split(int fft_len, const float* mag, int64_t nfrm, const void* tw64, float* out_re,
-                                   float* out_im, int nb, int num_sms, cudaStream_t st);
+cudaError_t launch_min_phase_split(int fft_len, const float* mag, int in_pitch, int64_t nfrm, const void* tw64, float* out_re,
+                                   float* out_im, int nb, int out_pitch, int num_sms, cudaStream_t st);
 
 // ---- NumPy legacy MT19937 stream on the device (mpb_rng.cu) ----
 cudaError_t launch_mt19937_uniform(uint32_t* key_dev, int32_t* pos_dev, uint32_t* raw_dev, int64_t n, double low,

@@ -52,10 +52,10 @@ __device__ __forceinline__ float lerp_row(const float* r0, const float* r1, floa
     return r1 ? fmaf(w, r1[k] - a, a) : a;
 }
 
-// asynchronous 4-byte global -> shared copies (rows of the un-warped features are only 4-byte aligned)
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+// asynchronous 16-byte global -> shared copies (the un-warped scratch rows are pitched to 16 bytes)
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(d), "l"(gmem_src));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(gmem_src));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
@@ -74,9 +74,9 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
     T2* tw2f = reinterpret_cast<T2*>(acc + N);
     T2* tw2i = tw2f + G::TW2_ELEMS;
     // feature rows of the current frame, prefetched with cp.async while the noise FFT runs
-    const int H = a.H, HB = a.HB;
-    const int rowlen = H + 2 * HB;
-    float* srow0 = reinterpret_cast<float*>(tw2i + G::TW2_ELEMS);      // [mag H | real HB | imag HB]
+    const int H = a.H, HB = a.HB, HP = a.HP, HBP = a.HBP;
+    const int rowlen = HP + 2 * HBP;
+    float* srow0 = reinterpret_cast<float*>(tw2i + G::TW2_ELEMS);      // [mag HP | real HBP | imag HBP]
     float* srow1 = a.row1 ? srow0 + rowlen : nullptr;
     const int t = threadIdx.x;
     const T scale = (T)1 / (T)N;
@@ -108,20 +108,21 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
 
             // ---- 0. kick off the asynchronous copy of this frame's un-warped feature rows ----
             {
-                const float* g0 = a.m_mag + (int64_t)a.row0[g] * H;
-                for (int k = t; k < H; k += TPB) cp_async4(srow0 + k, g0 + k);
-                if (voiced && !a.per_linear) {
-                    const float* gr = a.m_real + (int64_t)a.row0[g] * HB;
-                    const float* gi2 = a.m_imag + (int64_t)a.row0[g] * HB;
-                    for (int k = t; k < HB; k += TPB) { cp_async4(srow0 + H + k, gr + k); cp_async4(srow0 + H + HB + k, gi2 + k); }
+                const bool ph = voiced && !a.per_linear;
+                const float* g0 = a.m_mag + (int64_t)a.row0[g] * HP;
+                for (int k = 4 * t; k < HP; k += 4 * TPB) cp_async16(srow0 + k, g0 + k);
+                if (ph) {
+                    const float* gr = a.m_real + (int64_t)a.row0[g] * HBP;
+                    const float* gi2 = a.m_imag + (int64_t)a.row0[g] * HBP;
+                    for (int k = 4 * t; k < HBP; k += 4 * TPB) { cp_async16(srow0 + HP + k, gr + k); cp_async16(srow0 + HP + HBP + k, gi2 + k); }
                 }
                 if (srow1) {
-                    const float* g1 = a.m_mag + (int64_t)a.row1[g] * H;
-                    for (int k = t; k < H; k += TPB) cp_async4(srow1 + k, g1 + k);
-                    if (voiced && !a.per_linear) {
-                        const float* gr = a.m_real + (int64_t)a.row1[g] * HB;
-                        const float* gi2 = a.m_imag + (int64_t)a.row1[g] * HB;
-                        for (int k = t; k < HB; k += TPB) { cp_async4(srow1 + H + k, gr + k); cp_async4(srow1 + H + HB + k, gi2 + k); }
+                    const float* g1 = a.m_mag + (int64_t)a.row1[g] * HP;
+                    for (int k = 4 * t; k < HP; k += 4 * TPB) cp_async16(srow1 + k, g1 + k);
+                    if (ph) {
+                        const float* gr = a.m_real + (int64_t)a.row1[g] * HBP;
+                        const float* gi2 = a.m_imag + (int64_t)a.row1[g] * HBP;
+                        for (int k = 4 * t; k < HBP; k += 4 * TPB) { cp_async16(srow1 + HP + k, gr + k); cp_async16(srow1 + HP + HBP + k, gi2 + k); }
                     }
                 }
             }
@@ -136,10 +137,10 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
             __syncthreads();                                   // feature rows have landed for every thread
             const float* mag0 = srow0;
             const float* mag1 = srow1;
-            const float* re0 = srow0 + H;
-            const float* re1 = srow1 ? srow1 + H : nullptr;
-            const float* im0 = srow0 + H + HB;
-            const float* im1 = srow1 ? srow1 + H + HB : nullptr;
+            const float* re0 = srow0 + HP;
+            const float* re1 = srow1 ? srow1 + HP : nullptr;
+            const float* im0 = srow0 + HP + HBP;
+            const float* im1 = srow1 ? srow1 + HP + HBP : nullptr;
             const float rw = a.roww ? a.roww[g] : 0.0f;
             const float gi = voiced ? giv : giu;
             const float* __restrict__ tabA = voiced ? tabAv : tabAu;
@@ -228,7 +229,7 @@ template <typename TO, int N>
 static cudaError_t launch_sc_t(const SynthCompArgs& a, cudaStream_t st) {
     using G = FftGeom<float, N>;
     const size_t smem = sizeof(float2) * (G::BUF_ELEMS + 2 * G::TW2_ELEMS) + sizeof(float) * N +
-                        sizeof(float) * (size_t)(a.H + 2 * a.HB) * (a.row1 ? 2 : 1);
+                        sizeof(float) * (size_t)(a.HP + 2 * a.HBP) * (a.row1 ? 2 : 1);
     auto kern = k_synthesis_compressed<TO, N>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -23,14 +23,15 @@ k_mel_unwarp(const TI* __restrict__ mag_mel, const TI* __restrict__ real_mel, co
              const uint8_t* __restrict__ need_ph, int64_t nfrm, int n_mag, int n_ph,
              const float* __restrict__ u_mag, int H, const float* __restrict__ u_ph, int HB,
              float* __restrict__ out_mag, float* __restrict__ out_real, float* __restrict__ out_imag,
-             int tiles_mag, int tiles_ph, int kmax) {
+             int tiles_mag, int tiles_ph, int kmax, int HP, int HBP) {
     extern __shared__ __align__(16) float smem_f[];
     const int tid = threadIdx.x;
     int stream, btile;
     if ((int)blockIdx.y < tiles_mag) { stream = 0; btile = blockIdx.y; }
     else { stream = 1 + ((int)blockIdx.y - tiles_mag) / tiles_ph; btile = ((int)blockIdx.y - tiles_mag) % tiles_ph; }
     const int K = stream == 0 ? n_mag : n_ph;
-    const int nb = stream == 0 ? H : HB;                  // bins of this stream (= row pitch of U and of out)
+    const int nb = stream == 0 ? H : HB;                  // bins of this stream (= row pitch of U)
+    const int np = stream == 0 ? HP : HBP;                // row pitch of the output scratch (multiple of 4 floats)
     const TI* __restrict__ X = stream == 0 ? mag_mel : (stream == 1 ? real_mel : imag_mel);
     const float* __restrict__ U = stream == 0 ? u_mag : u_ph;
     float* __restrict__ Y = stream == 0 ? out_mag : (stream == 1 ? out_real : out_imag);
@@ -80,11 +81,15 @@ k_mel_unwarp(const TI* __restrict__ mag_mel, const TI* __restrict__ real_mel, co
         const int64_t f = f0 + (i < 4 ? tf * 4 + i : 32 + tf * 4 + (i - 4));
         if (f >= nfrm) continue;
         if (stream != 0 && need_ph[f] == 0) continue;
-        float* py = Y + f * (int64_t)nb + b0;
+        float* py = Y + f * (int64_t)np + b0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int b = j < 4 ? tb * 4 + j : 64 + tb * 4 + (j - 4);
-            if (b0 + b < nb) py[b] = stream == 0 ? expf(acc[i][j]) : acc[i][j];
+        for (int h = 0; h < 2; ++h) {                     // two groups of 4 consecutive bins -> one 16-byte store each
+            const int b = h * 64 + tb * 4;
+            if (b0 + b >= np) continue;                   // (the pad bins of the last group hold exp(0) / 0: never read)
+            float4 o;
+            if (stream == 0) o = make_float4(__expf(acc[i][4 * h]), __expf(acc[i][4 * h + 1]), __expf(acc[i][4 * h + 2]), __expf(acc[i][4 * h + 3]));
+            else o = make_float4(acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
+            *reinterpret_cast<float4*>(py + b) = o;
         }
     }
 }
@@ -101,14 +106,14 @@ cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st) {
         k_mel_unwarp<double><<<grid, 128, smem, st>>>((const double*)a.mag_mel, (const double*)a.real_mel,
                                                       (const double*)a.imag_mel, a.need_ph, a.nfrm, a.n_mag, a.n_ph,
                                                       a.u_mag, a.H, a.u_ph, a.HB, a.out_mag, a.out_real, a.out_imag,
-                                                      tiles_mag, tiles_ph, kmax);
+                                                      tiles_mag, tiles_ph, kmax, a.HP, a.HBP);
     } else {
         e = cudaFuncSetAttribute(k_mel_unwarp<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         k_mel_unwarp<float><<<grid, 128, smem, st>>>((const float*)a.mag_mel, (const float*)a.real_mel,
                                                      (const float*)a.imag_mel, a.need_ph, a.nfrm, a.n_mag, a.n_ph,
                                                      a.u_mag, a.H, a.u_ph, a.HB, a.out_mag, a.out_real, a.out_imag,
-                                                     tiles_mag, tiles_ph, kmax);
+                                                     tiles_mag, tiles_ph, kmax, a.HP, a.HBP);
     }
     return cudaGetLastError();
 }
