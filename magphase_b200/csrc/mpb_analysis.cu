@@ -71,11 +71,11 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
                 if (MODE == MODE_LOGP) {
                     // log periodograms exactly as the mel product consumes them (SPTK mcep -q 3 / -q 2 with -e 1e-8):
                     // log(|X|^2 + 1e-8) and log(exp(2 Re/|X|) + 1e-8); SFU work that hides under the FP64 butterflies
-                    T mag, re, im;
-                    normalise(x.x, x.y, mag, re, im);
-                    __stcs(&oa[kk], (TO)__logf(fmaf((float)mag, (float)mag, 1.0e-8f)));
-                    __stcs(&ob[kk], (TO)__logf(__expf(2.0f * (float)re) + 1.0e-8f));
-                    __stcs(&oc[kk], (TO)__logf(__expf(2.0f * (float)im) + 1.0e-8f));
+                    float mag, re, im, pw;
+                    normalise_to_f32(x.x, x.y, mag, re, im, pw);
+                    __stcs(&oa[kk], (TO)__logf(pw + 1.0e-8f));
+                    __stcs(&ob[kk], (TO)__logf(__expf(2.0f * re) + 1.0e-8f));
+                    __stcs(&oc[kk], (TO)__logf(__expf(2.0f * im) + 1.0e-8f));
                 } else if (MODE == MODE_LOGSQ) {
                     if (kk != 0 && kk != M) {
                         const T p = x.x * x.x + x.y * x.y;
@@ -85,6 +85,12 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
                 } else if (MODE == MODE_FFT) {
                     __stcs(&oa[2 * kk], (TO)x.x);
                     __stcs(&oa[2 * kk + 1], (TO)x.y);
+                } else if (sizeof(TO) == 4) {
+                    float mag, re, im, pw;
+                    normalise_to_f32(x.x, x.y, mag, re, im, pw);
+                    __stcs(&oa[kk], (TO)mag);
+                    __stcs(&ob[kk], (TO)re);
+                    __stcs(&oc[kk], (TO)im);
                 } else {
                     T mag, re, im;
                     normalise(x.x, x.y, mag, re, im);
