@@ -11,7 +11,7 @@ struct mpb_mel {
     float* wt_ph = nullptr;      // [kpad][ld_ph]
     double* cos_mag = nullptr;   // [n_mag][n_mag]
     double* cos_ph = nullptr;    // [n_ph][phase_dim]
-    DevBuf partial, feats[3], small[8];
+    DevBuf partial, feats[3], small[8], compact;
     std::mutex mu;
 };
 
@@ -55,7 +55,7 @@ int mpb_mel_destroy(mpb_mel* m) {
     if (!m) return MPB_OK;
     cudaSetDevice(m->ctx->device);
     cudaFree(m->wt_mag); cudaFree(m->wt_ph); cudaFree(m->cos_mag); cudaFree(m->cos_ph);
-    m->partial.release();
+    m->partial.release(); m->compact.release();
     for (auto& b : m->feats) b.release();
     for (auto& b : m->small) b.release();
     delete m;
@@ -102,6 +102,10 @@ static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const vo
     const int ncp = m->ld_mag > m->ld_ph ? m->ld_mag : m->ld_ph;
     const int64_t chunk = nfrm < MEL_CHUNK ? nfrm : MEL_CHUNK;
     CU(m->partial.need(sizeof(float) * 3 * (size_t)n_slices * (size_t)chunk * ncp));
+    CU(m->compact.need(sizeof(int32_t) * (2 * (size_t)chunk + 4)));
+    int32_t* d_vidx = (int32_t*)m->compact.p;
+    int32_t* d_cidx = d_vidx + chunk;
+    int32_t* d_cnt = d_cidx + chunk;
     const size_t fes = feat_dtype == MPB_F64 ? 8 : 4, oes = out_dtype == MPB_F64 ? 8 : 4;
     for (int64_t f0 = 0; f0 < nfrm; f0 += chunk) {
         const int64_t n = nfrm - f0 < chunk ? nfrm - f0 : chunk;
@@ -116,6 +120,9 @@ static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const vo
         a.out_real = (char*)out_real_mel + oes * f0 * m->phase_dim;
         a.out_imag = (char*)out_imag_mel + oes * f0 * m->phase_dim;
         a.out_dtype = out_dtype;
+        a.vidx = d_vidx; a.cidx = d_cidx; a.vcount = d_cnt;
+        LAUNCH(m->ctx, (cudaStream_t)stream, "k_voiced_compact",
+               launch_voiced_compact(a.voi, (int)n, d_vidx, d_cidx, d_cnt, (cudaStream_t)stream));
         LAUNCH(m->ctx, (cudaStream_t)stream, "k_mel_gemm", launch_mel_gemm(a, (cudaStream_t)stream));
         LAUNCH(m->ctx, (cudaStream_t)stream, "k_mel_finish", launch_mel_finish(a, (cudaStream_t)stream));
     }

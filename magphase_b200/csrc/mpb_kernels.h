@@ -55,7 +55,9 @@ struct MelArgs {
     const double* cos_mag; int n_mag; const double* cos_ph; int n_ph; int phase_dim;
     float* partial; int ncp_max;                                            // [3][nfrm][slices][ncp_max]
     void* out_mag; void* out_real; void* out_imag; int out_dtype;
+    const int32_t* vidx; const int32_t* cidx; const int32_t* vcount;        // voiced-frame compaction (NULL: off)
 };
+cudaError_t launch_voiced_compact(const uint8_t* voi, int n, int32_t* vidx, int32_t* cidx, int32_t* count, cudaStream_t st);
 cudaError_t build_warp_matrix(int fft_len, int n_out, double alpha, float* wt32, double* scratch64, int ld,
                               cudaStream_t st);
 cudaError_t launch_mel_gemm(const MelArgs& a, cudaStream_t st);

@@ -59,6 +59,50 @@ cudaError_t build_warp_matrix(int fft_len, int n_out, double alpha, float* wt32,
     return cudaGetLastError();
 }
 
+// ---- voiced-frame compaction ------------------------------------------------------------------
+// The phase streams of unvoiced frames are masked to zero (src/magphase.py:2527-2542), so only voiced frames go
+// through the real / imag tile products.  One CTA scans the voicing flags of a chunk: vidx[c] = frame of the c-th
+// voiced frame, cidx[f] = its rank (or -1), *count = number of voiced frames.  No host round trip.
+__global__ void __launch_bounds__(1024)
+k_voiced_compact(const uint8_t* __restrict__ voi, int n, int32_t* __restrict__ vidx, int32_t* __restrict__ cidx,
+                 int32_t* __restrict__ count) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int f = base + t;
+        const int v = (f < n && voi[f] != 0) ? 1 : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warp_sums[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int s = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        const int rank = carry + (w ? warp_sums[w - 1] : 0) + x - v;      // exclusive rank of this frame
+        if (f < n) {
+            cidx[f] = v ? rank : -1;
+            if (v) vidx[rank] = f;
+        }
+        __syncthreads();
+        if (t == 1023) carry = rank + v;
+        __syncthreads();
+    }
+    if (t == 0) *count = carry;
+}
+
+cudaError_t launch_voiced_compact(const uint8_t* voi, int n, int32_t* vidx, int32_t* cidx, int32_t* count, cudaStream_t st) {
+    k_voiced_compact<<<1, 1024, 0, st>>>(voi, n, vidx, cidx, count);
+    return cudaGetLastError();
+}
+
 // ---- tile product -----------------------------------------------------------------------------
 // log periodogram of one feature value as SPTK sees it (float32 input file):
 //   in_type 3 (|X|):   log(x^2 + 1e-8)            in_type 2 (ln|X|):  log(exp(2x) + 1e-8)
@@ -80,10 +124,12 @@ template <typename TF, bool PRE>
 __global__ void __launch_bounds__(128, 4)
 k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __restrict__ imag, int64_t nfrm, int H,
            const float* __restrict__ wt_mag, int ld_mag, const float* __restrict__ wt_ph, int ld_ph,
-           float* __restrict__ partial, int n_slices, int ncp_max) {
+           float* __restrict__ partial, int n_slices, int ncp_max, const int32_t* __restrict__ vidx,
+           const int32_t* __restrict__ vcount) {
     extern __shared__ __align__(16) float smem_f[];
     float* Ls = smem_f;                                  // [GEMM_KS][GEMM_LDL]
     float* Bs = smem_f + GEMM_KS * GEMM_LDL;             // [GEMM_KS][GEMM_CT]
+    __shared__ int rowmap[GEMM_FT];                      // tile row -> frame (-1: none)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int stream = blockIdx.z;
     const int slice = blockIdx.y % n_slices, ctile = blockIdx.y / n_slices;
@@ -93,7 +139,14 @@ k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __
     if (ctile * GEMM_CT >= ld) return;
     const int64_t f0 = (int64_t)blockIdx.x * GEMM_FT;
     const int k0 = slice * MEL_KSLICE;
-    const bool full = f0 + GEMM_FT <= nfrm;              // interior tile: no row predicate needed
+    // rows of this tile: consecutive frames for the magnitude stream, the f0-th.. voiced frames for the phase streams
+    const int64_t nrows = (stream == 0 || !vidx) ? nfrm : (int64_t)*vcount;
+    if (f0 >= nrows) return;
+    if (tid < GEMM_FT) {
+        const int64_t r = f0 + tid;
+        rowmap[tid] = r < nrows ? ((stream == 0 || !vidx) ? (int)r : vidx[r]) : -1;
+    }
+    __syncthreads();
 
     const int tf = tid >> 3, tc = tid & 7;
     float acc[8][8];
@@ -117,16 +170,16 @@ k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __
 #pragma unroll 1
         for (int gh = 0; gh < 8; gh += 4) {
             float raw[4][2][4];                          // [frame group][bin chunk][frame in group]
-            const TF* __restrict__ p0 = src + (f0 + gh * 16 + warp * 4) * (int64_t)H + k0 + ks + lane;
+            const TF* __restrict__ p0 = src + k0 + ks + lane;
 #pragma unroll
             for (int g = 0; g < 4; ++g)
 #pragma unroll
-                for (int c = 0; c < GEMM_KS / 32; ++c)
+                for (int r = 0; r < 4; ++r) {
+                    const int fr = rowmap[(gh + g) * 16 + warp * 4 + r];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const bool ok = full || (f0 + (gh + g) * 16 + warp * 4 + r < nfrm);
-                        raw[g][c][r] = ok ? (float)__ldcs(p0 + (g * 16 + r) * (int64_t)H + c * 32) : 0.0f;
-                    }
+                    for (int c = 0; c < GEMM_KS / 32; ++c)
+                        raw[g][c][r] = fr >= 0 ? (float)__ldcs(p0 + fr * (int64_t)H + c * 32) : 0.0f;
+                }
 #pragma unroll
             for (int g = 0; g < 4; ++g)
 #pragma unroll
@@ -135,7 +188,7 @@ k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __
                     float* pv = &v.x;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const bool ok = full || (f0 + (gh + g) * 16 + warp * 4 + r < nfrm);
+                        const bool ok = rowmap[(gh + g) * 16 + warp * 4 + r] >= 0;
                         pv[r] = PRE ? raw[g][c][r] : (ok ? log_periodogram(raw[g][c][r], stream == 0) : 0.0f);
                     }
                     *reinterpret_cast<float4*>(Ls + (c * 32 + lane) * GEMM_LDL + (gh + g) * 16 + warp * 4) = v;
@@ -160,12 +213,12 @@ k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __
                 for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
     }
-    // ---- partial[stream][f][slice][ncp_max] ----
+    // ---- partial[stream][row][slice][ncp_max]  (row = frame, or voiced rank for the phase streams) ----
     float* out = partial + (size_t)stream * (size_t)nfrm * n_slices * ncp_max + (size_t)slice * ncp_max + ctile * GEMM_CT;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int64_t f = f0 + (i < 4 ? tf * 4 + i : 64 + tf * 4 + (i - 4));
-        if (f >= nfrm) continue;
+        if (f >= nrows) continue;
         float* po = out + (size_t)f * n_slices * ncp_max;
         *reinterpret_cast<float4*>(po + tc * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         *reinterpret_cast<float4*>(po + 32 + tc * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
@@ -180,7 +233,8 @@ k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64
              const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __restrict__ imag, int H,
              const float* __restrict__ wt_mag, int ld_mag, const float* __restrict__ wt_ph, int ld_ph,
              const double* __restrict__ cos_mag, int n_mag, const double* __restrict__ cos_ph, int n_ph, int phase_dim,
-             const uint8_t* __restrict__ voi, TO* __restrict__ out_mag, TO* __restrict__ out_real, TO* __restrict__ out_imag) {
+             const uint8_t* __restrict__ voi, const int32_t* __restrict__ cidx, TO* __restrict__ out_mag,
+             TO* __restrict__ out_real, TO* __restrict__ out_imag) {
     __shared__ double mc[4][MEL_MAX_COEFFS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t f = (int64_t)blockIdx.x * 4 + warp;
@@ -192,17 +246,25 @@ k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64
     const TF* __restrict__ src = stream == 0 ? mag : (stream == 1 ? real : imag);
     const float* __restrict__ wt = stream == 0 ? wt_mag : wt_ph;
     const int ld = stream == 0 ? ld_mag : ld_ph;
+    TO* __restrict__ dst = (stream == 0 ? out_mag : (stream == 1 ? out_real : out_imag)) + f * (int64_t)n_out;
+    const bool voiced = voi[f] != 0;
+    int64_t row = f;                                                       // row of this frame in `partial`
+    if (stream != 0 && cidx) {
+        if (!voiced) {                                                     // masked anyway (src/magphase.py:2527-2528)
+            for (int o = lane; o < n_out; o += 32) dst[o] = (TO)0;
+            return;
+        }
+        row = cidx[f];
+    }
     const float xl = (float)src[f * (int64_t)H + (H - 1)];
     const float last = PRE ? xl : log_periodogram(xl, stream == 0);       // Nyquist bin, not covered by the K slices
-    const float* __restrict__ pp = partial + ((size_t)stream * (size_t)nfrm + (size_t)f) * n_slices * ncp_max;
+    const float* __restrict__ pp = partial + ((size_t)stream * (size_t)nfrm + (size_t)row) * n_slices * ncp_max;
     for (int j = lane; j < n_in; j += 32) {
         double s = (double)last * (double)wt[(size_t)(H - 1) * ld + j];
         for (int sl = 0; sl < n_slices; ++sl) s += (double)pp[sl * ncp_max + j];
         mc[warp][j] = (double)(float)s;                                    // SPTK writes float32 (src/libaudio.py:593)
     }
     __syncwarp();
-    const bool voiced = voi[f] != 0;
-    TO* __restrict__ dst = (stream == 0 ? out_mag : (stream == 1 ? out_real : out_imag)) + f * (int64_t)n_out;
     for (int o = lane; o < n_out; o += 32) {
         double s = 0.0;
         for (int j = 0; j < n_in; ++j) s = fma(mc[warp][j], ct[j * n_out + o], s);
@@ -227,7 +289,7 @@ static cudaError_t launch_gemm_t(const MelArgs& a, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, 128, smem, st>>>((const TF*)a.mag, (const TF*)a.real, (const TF*)a.imag, a.nfrm, H, a.wt_mag, a.ld_mag,
-                                  a.wt_ph, a.ld_ph, a.partial, n_slices, a.ncp_max);
+                                  a.wt_ph, a.ld_ph, a.partial, n_slices, a.ncp_max, a.vidx, a.vcount);
     return cudaGetLastError();
 }
 
@@ -243,7 +305,7 @@ static cudaError_t launch_finish_t(const MelArgs& a, cudaStream_t st) {
     dim3 g2((unsigned)((a.nfrm + 3) / 4), 3);
     k_mel_finish<TF, TO, PRE><<<g2, 128, 0, st>>>(a.partial, n_slices, a.ncp_max, a.nfrm, (const TF*)a.mag, (const TF*)a.real,
                                                    (const TF*)a.imag, H, a.wt_mag, a.ld_mag, a.wt_ph, a.ld_ph, a.cos_mag,
-                                                   a.n_mag, a.cos_ph, a.n_ph, a.phase_dim, a.voi, (TO*)a.out_mag,
+                                                   a.n_mag, a.cos_ph, a.n_ph, a.phase_dim, a.voi, a.cidx, (TO*)a.out_mag,
                                                    (TO*)a.out_real, (TO*)a.out_imag);
     return cudaGetLastError();
 }
