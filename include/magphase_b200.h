@@ -243,7 +243,9 @@ int mpb_synthesis_compressed_host(mpb_syn* plan,
                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
                                   uint32_t* mt_key, int32_t* mt_pos,   /* noise == NULL: draw it on the device from
                                                                           NumPy's legacy state (in/out), see below */
-                                  const mpb_syn_frames* frames, int per_linear, double* out, int64_t n_out);
+                                  const mpb_syn_frames* frames, int per_linear,
+                                  const double* hpf_sos,   /* output high-pass as 2 biquads (mpb_sos2_*), or NULL */
+                                  double* out, int64_t n_out);
 
 /* ---- post-filter and minimum phase ---------------------------------------------------------- */
 /*
@@ -262,6 +264,19 @@ int mpb_post_filter_host(mpb_ctx* ctx, const double* x, int64_t nfrm, int dim,
 int mpb_min_phase_dev(mpb_ctx* ctx, void* stream, const void* mag, int dtype, int64_t nfrm, int fft_len,
                       void* out_cplx);
 int mpb_min_phase_host(mpb_ctx* ctx, const double* mag, int64_t nfrm, int fft_len, double* out_cplx);
+
+/* ---- output high-pass ----------------------------------------------------------------------- */
+/*
+ * The reference's scipy.signal.lfilter(butter(4, 40 Hz, 'highpass')) on the synthesised waveform
+ * (src/magphase.py:981-995), in place, per utterance, as a blocked state-space scan: chunks run the filter in parallel
+ * from a zero state, a per-utterance carry pass links them, chunks rerun from their true start state.
+ * sos: HOST, two biquads in scipy's sos layout (2 x [b0 b1 b2 1 a1 a2]) factored by the host mirror from the
+ * reference's (b, a) -- the 4th-order direct form's state is too ill-conditioned for the carry pass.
+ * utt_off: HOST [n_utt+1] sample offsets of the concatenated utterances.  _dev: x is a DEVICE buffer (dtype).
+ */
+int mpb_sos2_dev(mpb_ctx* ctx, void* stream, void* x, int dtype, const int64_t* utt_off, int32_t n_utt,
+                 const double* sos);
+int mpb_sos2_host(mpb_ctx* ctx, double* x, const int64_t* utt_off, int32_t n_utt, const double* sos);
 
 /* ---- NumPy legacy random stream ------------------------------------------------------------- */
 /*

@@ -52,13 +52,15 @@ SIGNATURES = {
     'mpb_syn_destroy': [_vp],
     'mpb_synthesis_compressed_dev': [_vp, _vp, _vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _i64, _vp, _vp, _i32, C.c_int,
                                      _vp, C.c_int, _i64],
-    'mpb_synthesis_compressed_host': [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp, _i64],
+    'mpb_synthesis_compressed_host': [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp, _vp, _i64],
     'mpb_post_filter_dev': [_vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp],
     'mpb_post_filter_host': [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _vp],
     'mpb_min_phase_dev': [_vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp],
     'mpb_min_phase_host': [_vp, _vp, _i64, C.c_int, _vp],
     'mpb_mt19937_uniform_dev': [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, _vp, C.c_int],
     'mpb_mt19937_uniform_host': [_vp, _vp, _vp, _i64, C.c_double, C.c_double, _vp],
+    'mpb_sos2_dev': [_vp, _vp, _vp, C.c_int, _vp, _i32, _vp],
+    'mpb_sos2_host': [_vp, _vp, _vp, _i32, _vp],
 }
 _RESTYPES = {'mpb_last_error': C.c_char_p, 'mpb_version': C.c_char_p, 'mpb_launch_count': _i64}
 

@@ -453,4 +453,76 @@ int mpb_mt19937_uniform_host(mpb_ctx* ctx, uint32_t* key, int32_t* pos, int64_t 
     return MPB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two cascaded biquads (scipy sos layout: 2 x [b0 b1 b2 1 a1 a2], HOST) in place on a DEVICE buffer holding n_utt
+// concatenated utterances (utt_off: HOST array [n_utt+1]).
+int mpb_sos2_dev(mpb_ctx* ctx, void* stream, void* x, int dtype, const int64_t* utt_off, int32_t n_utt, const double* sos) {
+    if (!ctx || !utt_off || !sos) return fail(MPB_ERR_BAD_ARG, "NULL argument");
+    if (!dtype_ok(dtype) || n_utt < 0) return fail(MPB_ERR_BAD_ARG, "bad dtype or size");
+    if (sos[3] != 1.0 || sos[9] != 1.0) return fail(MPB_ERR_BAD_ARG, "sos sections must be normalised (a0 == 1)");
+    if (n_utt == 0 || utt_off[n_utt] == utt_off[0]) return MPB_OK;
+    if (!x) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int L = 512;
+    std::vector<int64_t> h(2 * ((size_t)n_utt + 1));
+    int64_t* uo = h.data();
+    int64_t* co = h.data() + n_utt + 1;
+    co[0] = 0;
+    for (int32_t u = 0; u <= n_utt; ++u) uo[u] = utt_off[u];
+    for (int32_t u = 0; u < n_utt; ++u) {
+        if (uo[u + 1] < uo[u]) return fail(MPB_ERR_BAD_ARG, "utt_off not non-decreasing");
+        co[u + 1] = co[u] + (uo[u + 1] - uo[u] + L - 1) / L;
+    }
+    const int64_t n_chunks = co[n_utt];
+    // zero-input state map of the cascade (one step on each unit state) and its L-th power by repeated squaring
+    double M[16], P[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, T[16];
+    for (int j = 0; j < 4; ++j) {
+        double z[4] = {0, 0, 0, 0};
+        z[j] = 1.0;
+        const double y1 = z[0];
+        double n0 = z[1] - sos[4] * y1, n1 = -sos[5] * y1;
+        const double y2 = sos[6] * y1 + z[2];
+        double n2 = sos[7] * y1 + z[3] - sos[10] * y2, n3 = sos[8] * y1 - sos[11] * y2;
+        M[0 * 4 + j] = n0; M[1 * 4 + j] = n1; M[2 * 4 + j] = n2; M[3 * 4 + j] = n3;
+    }
+    auto mul = [&](const double* A, const double* B, double* C) {
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                double acc = 0;
+                for (int k = 0; k < 4; ++k) acc += A[4 * i + k] * B[4 * k + j];
+                C[4 * i + j] = acc;
+            }
+    };
+    for (int e = L; e > 0; e >>= 1) {
+        if (e & 1) { mul(P, M, T); memcpy(P, T, sizeof(P)); }
+        mul(M, M, T); memcpy(M, T, sizeof(M));
+    }
+    DevBuf* sb = ctx->scratch;
+    CU(sb[12].need(sizeof(int64_t) * h.size()));
+    CU(sb[13].need(sizeof(double) * 4 * (size_t)n_chunks));
+    CU(cudaMemcpyAsync(sb[12].p, h.data(), sizeof(int64_t) * h.size(), cudaMemcpyHostToDevice, st));
+    LAUNCH(ctx, st, "k_iir_chunks x2 + k_iir_carry",
+           launch_sos2(x, dtype, (const int64_t*)sb[12].p, (const int64_t*)sb[12].p + n_utt + 1, n_utt, n_chunks, L, sos, P,
+                       (double*)sb[13].p, st));
+    ctx->launches += 2;
+    CU(cudaStreamSynchronize(st));      // h (pageable) was handed to an async copy
+    return MPB_OK;
+}
+
+int mpb_sos2_host(mpb_ctx* ctx, double* x, const int64_t* utt_off, int32_t n_utt, const double* sos) {
+    if (!ctx || !utt_off) return fail(MPB_ERR_BAD_ARG, "NULL argument");
+    if (n_utt == 0 || utt_off[n_utt] == utt_off[0]) return MPB_OK;
+    if (!x || utt_off[0] != 0) return fail(MPB_ERR_BAD_ARG, "NULL buffer or utt_off[0] != 0");
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t sz = sizeof(double) * (size_t)utt_off[n_utt];
+    CU(ctx->scratch[14].need(sz));
+    CU(cudaMemcpyAsync(ctx->scratch[14].p, x, sz, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = mpb_sos2_dev(ctx, ctx->stream, ctx->scratch[14].p, MPB_F64, utt_off, n_utt, sos);
+    if (rc != MPB_OK) return rc;
+    CU(cudaMemcpy(x, ctx->scratch[14].p, sz, cudaMemcpyDeviceToHost));
+    return MPB_OK;
+}
+
 }  // extern "C"

@@ -5,6 +5,8 @@ using namespace mpb;
 
 extern "C" int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* pos, int64_t n, double low,
                                        double high, void* out_dev, int out_dtype);
+extern "C" int mpb_sos2_dev(mpb_ctx* ctx, void* stream, void* x, int dtype, const int64_t* utt_off, int32_t n_utt,
+                            const double* sos);
 extern "C" int mpb_plan_ola_runs(const int32_t* pm, const int64_t* utt_frm_off, int32_t n_utt, int fft_len,
                                  int32_t target_frames, int32_t* out_runs, int64_t capacity, int64_t* n_runs);
 
@@ -134,7 +136,7 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
 int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const double* real_mel, const double* imag_mel,
                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
                                   uint32_t* mt_key, int32_t* mt_pos, const mpb_syn_frames* fr, int per_linear,
-                                  double* out, int64_t n_out) {
+                                  const double* hpf_sos, double* out, int64_t n_out) {
     if (!s || !fr) return fail(MPB_ERR_BAD_ARG, "NULL argument");
     if (n_out == 0) return MPB_OK;
     if (!mag_mel || !real_mel || !imag_mel || !need_ph || !out) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
@@ -217,6 +219,10 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
                                       (const float*)d_noise, n_noise, &d, (const int32_t*)d_runs, (int32_t)n_runs,
                                       per_linear, s->out.p, MPB_F64, n_out);
     if (rc != MPB_OK) return rc;
+    if (hpf_sos) {                   // output high-pass (src/magphase.py:981-995) on the device, per utterance
+        rc = mpb_sos2_dev(ctx, st, s->out.p, MPB_F64, fr->utt_out_off, U, hpf_sos);
+        if (rc != MPB_OK) return rc;
+    }
     CU(cudaMemcpyAsync(out, s->out.p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));   // also keeps noise32 / runs alive until the copies are done
     return MPB_OK;

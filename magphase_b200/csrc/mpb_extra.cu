@@ -186,4 +186,80 @@ cudaError_t launch_min_phase_split(int fft_len, const float* mag, int in_pitch, 
     return launch_mp_n<float, float, 1>(fft_len, mag, in_pitch, nfrm, tw64, out_re, out_im, nb, out_pitch, num_sms, st);
 }
 
+
+// ---- output high-pass (4th-order IIR) as a blocked state-space scan -----------------------------
+// Reference: scipy.signal.lfilter(b, a, x) with butter(4, 40 Hz, 'highpass'), src/magphase.py:981-995.
+// The recurrence is sequential in time but LINEAR in the state: an utterance is cut into chunks of L samples,
+//   pass 1  every chunk runs the filter from a ZERO state and keeps its 4-value end state            (parallel)
+//   pass 2  per utterance: s_{c+1} = M^L s_c + e_c  (M: the 4x4 state matrix, M^L from the host)       (tiny)
+//   pass 3  every chunk reruns the filter from its true start state s_c and writes y in place        (parallel)
+// The filter runs as two cascaded biquads (transposed direct form II each) factored from the reference's own
+// (b, a): the direct-form state of a 4th-order filter with four poles at |z| ~ 0.997 is so ill-conditioned that
+// M^L is not representable in float64 (its computed eigenvalues come out > 1), the biquad state is fine.
+struct SosCoef { double c[2][6]; double ML[16]; };
+
+__device__ __forceinline__ double sos_step(const SosCoef& cf, double* z, double xn) {
+    const double y1 = cf.c[0][0] * xn + z[0];
+    z[0] = cf.c[0][1] * xn + z[1] - cf.c[0][4] * y1;
+    z[1] = cf.c[0][2] * xn - cf.c[0][5] * y1;
+    const double y2 = cf.c[1][0] * y1 + z[2];
+    z[2] = cf.c[1][1] * y1 + z[3] - cf.c[1][4] * y2;
+    z[3] = cf.c[1][2] * y1 - cf.c[1][5] * y2;
+    return y2;
+}
+
+template <typename T, bool WRITE>
+__global__ void k_iir_chunks(T* __restrict__ x, const int64_t* __restrict__ utt_off, const int64_t* __restrict__ chunk_off,
+                             int n_utt, int L, SosCoef cf, double* __restrict__ state) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= chunk_off[n_utt]) return;
+    int u = 0;                                            // utterance of this chunk (binary search)
+    {
+        int lo = 0, hi = n_utt;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (chunk_off[mid] <= c) lo = mid; else hi = mid; }
+        u = lo;
+    }
+    const int64_t start = utt_off[u] + (c - chunk_off[u]) * (int64_t)L;
+    const int64_t end = start + L < utt_off[u + 1] ? start + L : utt_off[u + 1];
+    double z[4] = {0, 0, 0, 0};
+    if (WRITE) { z[0] = state[4 * c]; z[1] = state[4 * c + 1]; z[2] = state[4 * c + 2]; z[3] = state[4 * c + 3]; }
+    for (int64_t n = start; n < end; ++n) {
+        const double y = sos_step(cf, z, (double)x[n]);
+        if (WRITE) x[n] = (T)y;
+    }
+    if (!WRITE) { state[4 * c] = z[0]; state[4 * c + 1] = z[1]; state[4 * c + 2] = z[2]; state[4 * c + 3] = z[3]; }
+}
+
+// one thread per utterance: turn the zero-state end states into true start states (in place)
+__global__ void k_iir_carry(const int64_t* __restrict__ chunk_off, int n_utt, SosCoef cf, double* __restrict__ state) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_utt) return;
+    double s[4] = {0, 0, 0, 0};
+    for (int64_t c = chunk_off[u]; c < chunk_off[u + 1]; ++c) {
+        double e[4], nx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { e[i] = state[4 * c + i]; state[4 * c + i] = s[i]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            nx[i] = cf.ML[4 * i] * s[0] + cf.ML[4 * i + 1] * s[1] + cf.ML[4 * i + 2] * s[2] + cf.ML[4 * i + 3] * s[3] + e[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] = nx[i];
+    }
+}
+
+cudaError_t launch_sos2(void* x, int dtype, const int64_t* utt_off, const int64_t* chunk_off, int n_utt, int64_t n_chunks,
+                        int L, const double* sos, const double* ML, double* state, cudaStream_t st) {
+    if (n_chunks < 1) return cudaSuccess;
+    SosCoef cf;
+    for (int i = 0; i < 12; ++i) cf.c[i / 6][i % 6] = sos[i];
+    for (int i = 0; i < 16; ++i) cf.ML[i] = ML[i];
+    const unsigned grid = (unsigned)((n_chunks + 127) / 128);
+    if (dtype == MPB_F64) k_iir_chunks<double, false><<<grid, 128, 0, st>>>((double*)x, utt_off, chunk_off, n_utt, L, cf, state);
+    else k_iir_chunks<float, false><<<grid, 128, 0, st>>>((float*)x, utt_off, chunk_off, n_utt, L, cf, state);
+    k_iir_carry<<<(n_utt + 63) / 64, 64, 0, st>>>(chunk_off, n_utt, cf, state);
+    if (dtype == MPB_F64) k_iir_chunks<double, true><<<grid, 128, 0, st>>>((double*)x, utt_off, chunk_off, n_utt, L, cf, state);
+    else k_iir_chunks<float, true><<<grid, 128, 0, st>>>((float*)x, utt_off, chunk_off, n_utt, L, cf, state);
+    return cudaGetLastError();
+}
+
 }  // namespace mpb

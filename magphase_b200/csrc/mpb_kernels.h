@@ -100,6 +100,11 @@ cudaError_t launch_min_phase(int fft_len, const void* mag, int dtype, int64_t nf
 cudaError_t launch_min_phase_split(int fft_len, const float* mag, int in_pitch, int64_t nfrm, const void* tw64, float* out_re,
                                    float* out_im, int nb, int out_pitch, int num_sms, cudaStream_t st);
 
+// two cascaded biquads (scipy sos layout [2][6]) as a blocked state-space scan, in place on x (utterances
+// concatenated, utt_off[n_utt+1]; chunk_off[n_utt+1]: first chunk of every utterance; state: 4 doubles per chunk)
+cudaError_t launch_sos2(void* x, int dtype, const int64_t* utt_off, const int64_t* chunk_off, int n_utt, int64_t n_chunks,
+                        int L, const double* sos, const double* ML, double* state, cudaStream_t st);
+
 // ---- NumPy legacy MT19937 stream on the device (mpb_rng.cu) ----
 cudaError_t launch_mt19937_uniform(uint32_t* key_dev, int32_t* pos_dev, uint32_t* raw_dev, int64_t n, double low,
                                    double high, void* out, int out_dtype, cudaStream_t st);

@@ -608,6 +608,28 @@ def _const_rate_rows(v_locs, n_c, step):
     return j.astype(np.int32), (j + 1).astype(np.int32), w
 
 
+def output_hpf_coefficients(fs):
+    """(b, a) of the output high-pass: scipy.signal.butter(4, 40 Hz / (fs/2), 'highpass').  src/magphase.py:981-995.
+    Host constant table; the filter itself runs on the device (blocked state-space scan, mpb_iir4_*)."""
+    from scipy import signal
+    v_b, v_a = signal.butter(4, 40 / (fs / 2.0), btype='highpass')
+    return np.ascontiguousarray(v_b, dtype=np.float64), np.ascontiguousarray(v_a, dtype=np.float64)
+
+
+def output_hpf_sos(fs):
+    """The reference's (b, a) factored into two biquads (scipy sos layout) for the device scan: poles = np.roots(a)
+    paired by conjugates, zeros = the exact quadruple zero at z = 1 of a Butterworth high-pass, gain b[0] in the first
+    section.  The product of the sections reproduces (b, a) to ~1e-15."""
+    v_b, v_a = output_hpf_coefficients(fs)
+    poles = np.roots(v_a)
+    upper = sorted([p for p in poles if p.imag > 0], key=lambda p: p.imag)
+    if len(upper) != 2 or not np.allclose(v_b / v_b[0], [1, -4, 6, -4, 1], rtol=0, atol=1e-9):
+        raise ValueError('unexpected high-pass design')
+    sos = np.array([[v_b[0], -2 * v_b[0], v_b[0], 1.0, -2 * upper[0].real, abs(upper[0]) ** 2],
+                    [1.0, -2.0, 1.0, 1.0, -2 * upper[1].real, abs(upper[1]) ** 2]])
+    return np.ascontiguousarray(sos, dtype=np.float64)
+
+
 def synthesis_from_compressed(m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0, fs, fft_len=None, b_voi_ap_win=True,
                               b_fbank_mel=False, b_const_rate=False, per_phase_type='magphase', alpha_phase=None,
                               b_out_hpf=True):
@@ -730,19 +752,15 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
     noise = None
     if l_noise is not None:
         noise = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in l_noise]))
+    hpf_sos = output_hpf_sos(fs) if b_out_hpf else None
     out = np.empty(int(out_off[-1]), dtype=np.float64)
     _lib.check(_lib.lib().mpb_synthesis_compressed_host(
         plan.handle, _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), mag.shape[0], _lib.ptr(need), _lib.ptr(noise),
-        int(sum(l_ns_len)), _lib.ptr(mt_key), C.byref(mt_pos) if mt_pos is not None else None, C.byref(fr), {'magphase': 0, 'linear': 1, 'min_phase': 2}[per_phase_type], _lib.ptr(out), out.size))
+        int(sum(l_ns_len)), _lib.ptr(mt_key), C.byref(mt_pos) if mt_pos is not None else None, C.byref(fr), {'magphase': 0, 'linear': 1, 'min_phase': 2}[per_phase_type], _lib.ptr(hpf_sos),
+        _lib.ptr(out), out.size))
     if mt_key is not None:
         np.random.set_state((np_state[0], mt_key, int(mt_pos.value), np_state[3], np_state[4]))
     l_out = [out[out_off[u]:out_off[u + 1]] for u in range(n_utt)]
-    if b_out_hpf:
-        # 4th-order 40 Hz Butterworth high-pass (src/magphase.py:981-995); sequential IIR, host for now
-        # (SURVEY.md 8(f) rank 1 moves it onto the device as a blocked state-space scan)
-        from scipy import signal
-        v_b, v_a = signal.butter(4, 40 / (fs / 2.0), btype='highpass')
-        l_out = [signal.lfilter(v_b, v_a, y) for y in l_out]
     return l_out
 
 

@@ -183,3 +183,23 @@ def test_numpy_legacy_stream_on_device_is_bit_exact(mp):
         for a, b in zip(got, ref):
             assert np.array_equal(a, b)
         assert np.array_equal(got_next, ref_next)
+
+
+def test_device_hpf_matches_lfilter(mp):
+    """The blocked state-space scan against scipy.signal.lfilter (the reference's own call, src/magphase.py:995):
+    several utterances of odd lengths in one call.  lfilter's direct form carries ~1e-8 of rounding noise itself."""
+    import ctypes
+    from scipy import signal
+    from magphase_b200 import _lib
+    rng = np.random.default_rng(8)
+    lens = [1, 511, 512, 513, 40000, 123457]
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    x = rng.normal(size=int(off[-1])) * 0.3 + 0.05          # with a DC offset for the high-pass to remove
+    for fs in (48000, 16000):
+        b, a = mp.output_hpf_coefficients(fs)
+        sos = mp.output_hpf_sos(fs)
+        y = x.copy()
+        _lib.check(_lib.lib().mpb_sos2_host(_lib.ctx(), _lib.ptr(y), _lib.ptr(off), len(lens), _lib.ptr(sos)))
+        for u in range(len(lens)):
+            ref = signal.lfilter(b, a, x[off[u]:off[u + 1]])
+            assert np.max(np.abs(y[off[u]:off[u + 1]] - ref)) < 1e-6
