@@ -192,6 +192,17 @@ int mpb_analysis_compressed_hostv(mpb_mel* plan,
                                   const uint8_t* voi, int64_t nfrm, int compute_dtype,
                                   double* out_mag_mel, double* out_real_mel, double* out_imag_mel);
 
+/* analysis_compressed(b_const_rate=True) (src/magphase.py:2966-2983): nfrm variable-rate frames are analysed on the
+ * device; constant-rate output frame f is (1-w[f])*frame[r0[f]] + w[f]*frame[r1[f]] of the LOSSLESS features
+ * (interp_from_variable_to_const_frm_rate, :2219-2239, interpolated inside the tile-product loader before the log) and
+ * then compressed.  lerp_r0 / lerp_r1 / lerp_w / voi_out: HOST arrays with n_out entries.                     */
+int mpb_analysis_compressed_const_hostv(mpb_mel* plan,
+                                        const double* const* sigs, const int64_t* sig_lens, int32_t n_sigs,
+                                        const int64_t* centre, const int32_t* left, const int32_t* right, int64_t nfrm,
+                                        const int32_t* lerp_r0, const int32_t* lerp_r1, const float* lerp_w,
+                                        const uint8_t* voi_out, int64_t n_out,
+                                        double* out_mag_mel, double* out_real_mel, double* out_imag_mel);
+
 /* ---- compressed synthesis ------------------------------------------------------------------- */
 typedef struct mpb_syn mpb_syn;
 /*

@@ -73,9 +73,11 @@ int mpb_mel_get_warp_matrix(mpb_mel* m, int which, float* out_host) {
     return MPB_OK;
 }
 
+struct LerpRows { const int32_t* r0; const int32_t* r1; const float* w; };   // device arrays, one entry per OUTPUT frame
+
 static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const void* real, const void* imag, int feat_dtype,
                              int pre_logp, const uint8_t* voi, int64_t nfrm, void* out_mag_mel, void* out_real_mel,
-                             void* out_imag_mel, int out_dtype);
+                             void* out_imag_mel, int out_dtype, LerpRows lerp = LerpRows{nullptr, nullptr, nullptr});
 
 int mpb_mel_compress_dev(mpb_mel* m, void* stream, const void* mag, const void* real, const void* imag, int feat_dtype,
                          const uint8_t* voi, int64_t nfrm, void* out_mag_mel, void* out_real_mel, void* out_imag_mel,
@@ -88,7 +90,7 @@ int mpb_mel_compress_dev(mpb_mel* m, void* stream, const void* mag, const void* 
 
 static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const void* real, const void* imag, int feat_dtype,
                              int pre_logp, const uint8_t* voi, int64_t nfrm, void* out_mag_mel, void* out_real_mel,
-                             void* out_imag_mel, int out_dtype) {
+                             void* out_imag_mel, int out_dtype, LerpRows lerp) {
     if (!m) return fail(MPB_ERR_BAD_ARG, "plan is NULL");
     if (!dtype_ok(feat_dtype) || !dtype_ok(out_dtype)) return fail(MPB_ERR_BAD_ARG, "unknown dtype");
     if (nfrm < 0) return fail(MPB_ERR_BAD_ARG, "negative size");
@@ -110,8 +112,12 @@ static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const vo
     for (int64_t f0 = 0; f0 < nfrm; f0 += chunk) {
         const int64_t n = nfrm - f0 < chunk ? nfrm - f0 : chunk;
         MelArgs a;
-        a.mag = (const char*)mag + fes * f0 * H; a.real = (const char*)real + fes * f0 * H;
-        a.imag = (const char*)imag + fes * f0 * H; a.feat_dtype = feat_dtype; a.pre_logp = pre_logp;
+        // with row interpolation the source rows are addressed through lerp.r0 / r1 (global), else frame by frame
+        const int64_t src0 = lerp.r0 ? 0 : f0;
+        a.mag = (const char*)mag + fes * src0 * H; a.real = (const char*)real + fes * src0 * H;
+        a.imag = (const char*)imag + fes * src0 * H; a.feat_dtype = feat_dtype; a.pre_logp = pre_logp;
+        a.lerp_r0 = lerp.r0 ? lerp.r0 + f0 : nullptr; a.lerp_r1 = lerp.r1 ? lerp.r1 + f0 : nullptr;
+        a.lerp_w = lerp.w ? lerp.w + f0 : nullptr;
         a.voi = voi + f0; a.nfrm = n; a.fft_len = m->fft_len;
         a.wt_mag = m->wt_mag; a.ld_mag = m->ld_mag; a.wt_ph = m->wt_ph; a.ld_ph = m->ld_ph;
         a.cos_mag = m->cos_mag; a.n_mag = m->n_mag; a.cos_ph = m->cos_ph; a.n_ph = m->n_ph; a.phase_dim = m->phase_dim;
@@ -271,6 +277,74 @@ int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const i
     CU(cudaMemcpyAsync(out_mag_mel, m->small[1].p, sizeof(double) * nfrm * m->n_mag, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(out_real_mel, m->small[2].p, sizeof(double) * nfrm * m->phase_dim, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(out_imag_mel, m->small[3].p, sizeof(double) * nfrm * m->phase_dim, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MPB_OK;
+}
+
+// analysis_compressed(b_const_rate=True) (src/magphase.py:2966-2983): variable-rate lossless analysis on the device
+// (float32 rows, scratch), then every constant-rate output frame f is the linear interpolation
+// (1-w)*row[r0[f]] + w*row[r1[f]] of two analysed frames -- interpolated inside the tile-product loader, before the
+// log, exactly where interp1d sits in the reference -- and goes through the same mel compression.
+// lerp_r0 / lerp_r1 / lerp_w / voi_out: HOST arrays, one entry per output frame.
+int mpb_analysis_compressed_const_hostv(mpb_mel* m, const double* const* sigs, const int64_t* sig_lens, int32_t n_sigs,
+                                        const int64_t* centre, const int32_t* left, const int32_t* right, int64_t nfrm,
+                                        const int32_t* lerp_r0, const int32_t* lerp_r1, const float* lerp_w,
+                                        const uint8_t* voi_out, int64_t n_out, double* out_mag_mel, double* out_real_mel,
+                                        double* out_imag_mel) {
+    if (!m) return fail(MPB_ERR_BAD_ARG, "plan is NULL");
+    if (n_out == 0) return MPB_OK;
+    if (!sigs || !sig_lens || n_sigs < 1 || !centre || !left || !right || !lerp_r0 || !lerp_r1 || !lerp_w || !voi_out ||
+        !out_mag_mel || !out_real_mel || !out_imag_mel || nfrm < 1)
+        return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    int64_t n_sig = 0;
+    for (int32_t i = 0; i < n_sigs; ++i) {
+        if (!sigs[i] || sig_lens[i] < 0) return fail(MPB_ERR_BAD_ARG, "NULL signal");
+        n_sig += sig_lens[i];
+    }
+    for (int64_t f = 0; f < n_out; ++f)
+        if (lerp_r0[f] < 0 || lerp_r0[f] >= nfrm || lerp_r1[f] < 0 || lerp_r1[f] >= nfrm)
+            return fail(MPB_ERR_BAD_ARG, "interpolation row index out of range");
+    mpb_ctx* ctx = m->ctx;
+    int rc = check_frames_host(centre, left, right, nfrm, n_sig, m->fft_len);
+    if (rc != MPB_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int H = m->fft_len / 2 + 1;
+    cudaStream_t st = ctx->stream;
+    DevBuf* b = ctx->scratch;     // ctx scratch: lossless rows + descriptors; plan scratch: outputs
+    for (int i = 5; i < 8; ++i) CU(b[i].need(sizeof(float) * (size_t)nfrm * H));
+    CU(b[0].need(sizeof(double) * n_sig));
+    CU(b[1].need(sizeof(int64_t) * nfrm)); CU(b[2].need(sizeof(int32_t) * nfrm)); CU(b[3].need(sizeof(int32_t) * nfrm));
+    CU(m->small[0].need((size_t)n_out));
+    CU(m->small[1].need(sizeof(double) * n_out * m->n_mag));
+    CU(m->small[2].need(sizeof(double) * n_out * m->phase_dim));
+    CU(m->small[3].need(sizeof(double) * n_out * m->phase_dim));
+    CU(m->small[5].need(sizeof(int32_t) * n_out)); CU(m->small[6].need(sizeof(int32_t) * n_out));
+    CU(m->small[7].need(sizeof(float) * n_out));
+    {
+        int64_t off = 0;
+        for (int32_t i = 0; i < n_sigs; ++i) {
+            CU(cudaMemcpyAsync((double*)b[0].p + off, sigs[i], sizeof(double) * sig_lens[i], cudaMemcpyHostToDevice, st));
+            off += sig_lens[i];
+        }
+    }
+    CU(cudaMemcpyAsync(b[1].p, centre, sizeof(int64_t) * nfrm, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[2].p, left, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[3].p, right, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->small[0].p, voi_out, (size_t)n_out, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->small[5].p, lerp_r0, sizeof(int32_t) * n_out, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->small[6].p, lerp_r1, sizeof(int32_t) * n_out, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->small[7].p, lerp_w, sizeof(float) * n_out, cudaMemcpyHostToDevice, st));
+    rc = analysis_common(ctx, st, b[0].p, MPB_F64, n_sig, (const int64_t*)b[1].p, (const int32_t*)b[2].p, (const int32_t*)b[3].p,
+                         nullptr, nfrm, m->fft_len, MPB_F64, b[5].p, b[6].p, b[7].p, MPB_F32, MODE_FEATS);
+    if (rc != MPB_OK) return rc;
+    LerpRows lr{(const int32_t*)m->small[5].p, (const int32_t*)m->small[6].p, (const float*)m->small[7].p};
+    rc = mel_compress_impl(m, st, b[5].p, b[6].p, b[7].p, MPB_F32, 0, (const uint8_t*)m->small[0].p, n_out, m->small[1].p,
+                           m->small[2].p, m->small[3].p, MPB_F64, lr);
+    if (rc != MPB_OK) return rc;
+    CU(cudaMemcpyAsync(out_mag_mel, m->small[1].p, sizeof(double) * n_out * m->n_mag, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_real_mel, m->small[2].p, sizeof(double) * n_out * m->phase_dim, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_imag_mel, m->small[3].p, sizeof(double) * n_out * m->phase_dim, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return MPB_OK;
 }

@@ -56,6 +56,7 @@ struct MelArgs {
     float* partial; int ncp_max;                                            // [3][nfrm][slices][ncp_max]
     void* out_mag; void* out_real; void* out_imag; int out_dtype;
     const int32_t* vidx; const int32_t* cidx; const int32_t* vcount;        // voiced-frame compaction (NULL: off)
+    const int32_t* lerp_r0; const int32_t* lerp_r1; const float* lerp_w;    // output frame f = lerp of two source rows (NULL: off)
 };
 cudaError_t launch_voiced_compact(const uint8_t* voi, int n, int32_t* vidx, int32_t* cidx, int32_t* count, cudaStream_t st);
 cudaError_t build_warp_matrix(int fft_len, int n_out, double alpha, float* wt32, double* scratch64, int ld,

@@ -120,16 +120,19 @@ constexpr int GEMM_KS = 64;           // bins per shared-memory stage
 
 // grid: (frame tiles, K slices * coefficient tiles, 3 streams).  The K slices cover bins 0 .. H-2 (H-1 = N/2 is a
 // multiple of MEL_KSLICE); the Nyquist bin is added by k_mel_finish.  PRE: rows already hold log periodograms.
-template <typename TF, bool PRE>
+template <typename TF, bool PRE, bool LERP>
 __global__ void __launch_bounds__(128, 4)
 k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __restrict__ imag, int64_t nfrm, int H,
            const float* __restrict__ wt_mag, int ld_mag, const float* __restrict__ wt_ph, int ld_ph,
            float* __restrict__ partial, int n_slices, int ncp_max, const int32_t* __restrict__ vidx,
-           const int32_t* __restrict__ vcount) {
+           const int32_t* __restrict__ vcount, const int32_t* __restrict__ lr0, const int32_t* __restrict__ lr1,
+           const float* __restrict__ lw) {
     extern __shared__ __align__(16) float smem_f[];
     float* Ls = smem_f;                                  // [GEMM_KS][GEMM_LDL]
     float* Bs = smem_f + GEMM_KS * GEMM_LDL;             // [GEMM_KS][GEMM_CT]
     __shared__ int rowmap[GEMM_FT];                      // tile row -> frame (-1: none)
+    __shared__ int rowsrc[LERP ? 2 * GEMM_FT : 1];       // LERP: the two source rows of every tile row
+    __shared__ float roww[LERP ? GEMM_FT : 1];           //       and the interpolation weight
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int stream = blockIdx.z;
     const int slice = blockIdx.y % n_slices, ctile = blockIdx.y / n_slices;
@@ -144,7 +147,13 @@ k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __
     if (f0 >= nrows) return;
     if (tid < GEMM_FT) {
         const int64_t r = f0 + tid;
-        rowmap[tid] = r < nrows ? ((stream == 0 || !vidx) ? (int)r : vidx[r]) : -1;
+        const int fo = r < nrows ? ((stream == 0 || !vidx) ? (int)r : vidx[r]) : -1;
+        rowmap[tid] = fo;
+        if (LERP) {
+            rowsrc[2 * tid] = fo >= 0 ? lr0[fo] : 0;
+            rowsrc[2 * tid + 1] = fo >= 0 ? lr1[fo] : 0;
+            roww[tid] = fo >= 0 ? lw[fo] : 0.0f;
+        }
     }
     __syncthreads();
 
@@ -175,10 +184,22 @@ k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __
             for (int g = 0; g < 4; ++g)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const int fr = rowmap[(gh + g) * 16 + warp * 4 + r];
+                    const int tr = (gh + g) * 16 + warp * 4 + r;
+                    const int fr = rowmap[tr];
+                    if (LERP) {      // interp1d(kind='linear') between two source rows BEFORE the log (src/magphase.py:2967-2980)
+                        const int s0 = rowsrc[2 * tr], s1 = rowsrc[2 * tr + 1];
+                        const float w = roww[tr];
 #pragma unroll
-                    for (int c = 0; c < GEMM_KS / 32; ++c)
-                        raw[g][c][r] = fr >= 0 ? (float)__ldcs(p0 + fr * (int64_t)H + c * 32) : 0.0f;
+                        for (int c = 0; c < GEMM_KS / 32; ++c) {
+                            const float a0 = fr >= 0 ? (float)__ldcs(p0 + s0 * (int64_t)H + c * 32) : 0.0f;
+                            const float a1 = fr >= 0 ? (float)__ldcs(p0 + s1 * (int64_t)H + c * 32) : 0.0f;
+                            raw[g][c][r] = fmaf(w, a1 - a0, a0);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < GEMM_KS / 32; ++c)
+                            raw[g][c][r] = fr >= 0 ? (float)__ldcs(p0 + fr * (int64_t)H + c * 32) : 0.0f;
+                    }
                 }
 #pragma unroll
             for (int g = 0; g < 4; ++g)
@@ -227,13 +248,14 @@ k_mel_gemm(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __
 
 // ---- finish -------------------------------------------------------------------------------------
 // one warp per (frame, stream): mc[j] = float32(sum over K slices + Nyquist-bin term), out[o] = sum_j mc[j] cos_tab[j][o]
-template <typename TF, typename TO, bool PRE>
+template <typename TF, typename TO, bool PRE, bool LERP>
 __global__ void __launch_bounds__(128)
 k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64_t nfrm,
              const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __restrict__ imag, int H,
              const float* __restrict__ wt_mag, int ld_mag, const float* __restrict__ wt_ph, int ld_ph,
              const double* __restrict__ cos_mag, int n_mag, const double* __restrict__ cos_ph, int n_ph, int phase_dim,
-             const uint8_t* __restrict__ voi, const int32_t* __restrict__ cidx, TO* __restrict__ out_mag,
+             const uint8_t* __restrict__ voi, const int32_t* __restrict__ cidx, const int32_t* __restrict__ lr0,
+             const int32_t* __restrict__ lr1, const float* __restrict__ lw, TO* __restrict__ out_mag,
              TO* __restrict__ out_real, TO* __restrict__ out_imag) {
     __shared__ double mc[4][MEL_MAX_COEFFS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -256,7 +278,13 @@ k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64
         }
         row = cidx[f];
     }
-    const float xl = (float)src[f * (int64_t)H + (H - 1)];
+    float xl;
+    if (LERP) {
+        const float a0 = (float)src[lr0[f] * (int64_t)H + (H - 1)], a1 = (float)src[lr1[f] * (int64_t)H + (H - 1)];
+        xl = fmaf(lw[f], a1 - a0, a0);
+    } else {
+        xl = (float)src[f * (int64_t)H + (H - 1)];
+    }
     const float last = PRE ? xl : log_periodogram(xl, stream == 0);       // Nyquist bin, not covered by the K slices
     const float* __restrict__ pp = partial + ((size_t)stream * (size_t)nfrm + (size_t)row) * n_slices * ncp_max;
     for (int j = lane; j < n_in; j += 32) {
@@ -278,44 +306,52 @@ k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64
     }
 }
 
-template <typename TF, bool PRE>
+template <typename TF, bool PRE, bool LERP>
 static cudaError_t launch_gemm_t(const MelArgs& a, cudaStream_t st) {
     const int H = a.fft_len / 2 + 1;
     const int n_slices = (H - 1) / MEL_KSLICE;
     const int ctiles = (a.ncp_max + GEMM_CT - 1) / GEMM_CT;
     const size_t smem = sizeof(float) * (GEMM_KS * GEMM_LDL + GEMM_KS * GEMM_CT);
     dim3 grid((unsigned)((a.nfrm + GEMM_FT - 1) / GEMM_FT), (unsigned)(n_slices * ctiles), 3);
-    auto kern = k_mel_gemm<TF, PRE>;
+    auto kern = k_mel_gemm<TF, PRE, LERP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, 128, smem, st>>>((const TF*)a.mag, (const TF*)a.real, (const TF*)a.imag, a.nfrm, H, a.wt_mag, a.ld_mag,
-                                  a.wt_ph, a.ld_ph, a.partial, n_slices, a.ncp_max, a.vidx, a.vcount);
+                                  a.wt_ph, a.ld_ph, a.partial, n_slices, a.ncp_max, a.vidx, a.vcount, a.lerp_r0, a.lerp_r1,
+                                  a.lerp_w);
     return cudaGetLastError();
 }
 
 cudaError_t launch_mel_gemm(const MelArgs& a, cudaStream_t st) {
-    if (a.feat_dtype == MPB_F64) return launch_gemm_t<double, false>(a, st);
-    return a.pre_logp ? launch_gemm_t<float, true>(a, st) : launch_gemm_t<float, false>(a, st);
+    if (a.lerp_r0) return a.feat_dtype == MPB_F64 ? launch_gemm_t<double, false, true>(a, st) : launch_gemm_t<float, false, true>(a, st);
+    if (a.feat_dtype == MPB_F64) return launch_gemm_t<double, false, false>(a, st);
+    return a.pre_logp ? launch_gemm_t<float, true, false>(a, st) : launch_gemm_t<float, false, false>(a, st);
 }
 
-template <typename TF, typename TO, bool PRE>
+template <typename TF, typename TO, bool PRE, bool LERP>
 static cudaError_t launch_finish_t(const MelArgs& a, cudaStream_t st) {
     const int H = a.fft_len / 2 + 1;
     const int n_slices = (H - 1) / MEL_KSLICE;
     dim3 g2((unsigned)((a.nfrm + 3) / 4), 3);
-    k_mel_finish<TF, TO, PRE><<<g2, 128, 0, st>>>(a.partial, n_slices, a.ncp_max, a.nfrm, (const TF*)a.mag, (const TF*)a.real,
+    k_mel_finish<TF, TO, PRE, LERP><<<g2, 128, 0, st>>>(a.partial, n_slices, a.ncp_max, a.nfrm, (const TF*)a.mag, (const TF*)a.real,
                                                    (const TF*)a.imag, H, a.wt_mag, a.ld_mag, a.wt_ph, a.ld_ph, a.cos_mag,
-                                                   a.n_mag, a.cos_ph, a.n_ph, a.phase_dim, a.voi, a.cidx, (TO*)a.out_mag,
+                                                   a.n_mag, a.cos_ph, a.n_ph, a.phase_dim, a.voi, a.cidx, a.lerp_r0, a.lerp_r1, a.lerp_w, (TO*)a.out_mag,
                                                    (TO*)a.out_real, (TO*)a.out_imag);
     return cudaGetLastError();
 }
 
 cudaError_t launch_mel_finish(const MelArgs& a, cudaStream_t st) {
+    const bool o64 = a.out_dtype == MPB_F64;
+    if (a.lerp_r0) {
+        if (a.feat_dtype == MPB_F64)
+            return o64 ? launch_finish_t<double, double, false, true>(a, st) : launch_finish_t<double, float, false, true>(a, st);
+        return o64 ? launch_finish_t<float, double, false, true>(a, st) : launch_finish_t<float, float, false, true>(a, st);
+    }
     if (a.feat_dtype == MPB_F64)
-        return a.out_dtype == MPB_F64 ? launch_finish_t<double, double, false>(a, st) : launch_finish_t<double, float, false>(a, st);
+        return o64 ? launch_finish_t<double, double, false, false>(a, st) : launch_finish_t<double, float, false, false>(a, st);
     if (a.pre_logp)
-        return a.out_dtype == MPB_F64 ? launch_finish_t<float, double, true>(a, st) : launch_finish_t<float, float, true>(a, st);
-    return a.out_dtype == MPB_F64 ? launch_finish_t<float, double, false>(a, st) : launch_finish_t<float, float, false>(a, st);
+        return o64 ? launch_finish_t<float, double, true, false>(a, st) : launch_finish_t<float, float, true, false>(a, st);
+    return o64 ? launch_finish_t<float, double, false, false>(a, st) : launch_finish_t<float, float, false, false>(a, st);
 }
 
 }  // namespace mpb

@@ -410,8 +410,9 @@ def format_for_modelling(m_mag, m_real, m_imag, v_f0, fs, mag_dim=60, phase_dim=
 
 
 def interp_from_variable_to_const_frm_rate(m_data, v_pm_smpls, const_rate_ms, fs, interp_type='linear'):
-    """Linear resampling of per-frame data onto a constant frame-rate grid.  src/magphase.py:2219-2239
-    (host NumPy for now: SURVEY.md 8(f) rank 1 moves it onto the device)."""
+    """Linear resampling of per-frame data onto a constant frame-rate grid.  src/magphase.py:2219-2239.
+    Host version, used for the O(n) f0 / voicing tracks only; the feature matrices are interpolated on the device
+    (const_rate_rows + the tile-product loader)."""
     if interp_type != 'linear':
         raise ValueError('only linear interpolation is supported')
     m = np.asarray(m_data, dtype=np.float64)
@@ -424,10 +425,9 @@ def interp_from_variable_to_const_frm_rate(m_data, v_pm_smpls, const_rate_ms, fs
     if x[0] > 0:
         x = np.r_[0, x]
         m = np.vstack((m[0, :], m))
-    j = np.clip(np.searchsorted(x, centres, side='right') - 1, 0, x.size - 2)
-    # scipy.interpolate.interp1d(kind='linear'): slope * (x_new - x_lo) + y_lo
-    slope = (m[j + 1] - m[j]) / (x[j + 1] - x[j])[:, None]
-    out = slope * (centres - x[j])[:, None] + m[j]
+    # scipy's interp1d is what the reference calls: same arithmetic, bit-identical f0 / voicing tracks
+    from scipy import interpolate
+    out = interpolate.interp1d(x, m, axis=0, kind='linear')(centres)
     return out[:, 0] if one_d else out
 
 
@@ -449,22 +449,7 @@ def analysis_compressed_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None, mag_di
     if fft_len is None:
         fft_len = define_fft_len(fs)
     if b_const_rate:
-        out = []
-        for sig, pm, voi in zip(l_sig, l_pm_smpls, l_voi):
-            m_mag, m_real, m_imag, v_f0, _, v_shift = analysis_lossless_from_pm(sig, fs, pm, voi, fft_len=fft_len)
-            v_pm = np.cumsum(v_shift)                               # la.shift_to_pm (src/magphase.py:2970)
-            m_mag = interp_from_variable_to_const_frm_rate(m_mag, v_pm, 5.0, fs)
-            m_real = interp_from_variable_to_const_frm_rate(m_real, v_pm, 5.0, fs)
-            m_imag = interp_from_variable_to_const_frm_rate(m_imag, v_pm, 5.0, fs)
-            vv = v_f0 > 1.0
-            v_f0c = interp_from_variable_to_const_frm_rate(np.r_[v_f0[vv][0], v_f0[vv], v_f0[vv][-1]],
-                                                           np.r_[0, v_pm[vv], v_pm[-1]], 5.0, fs)
-            vvc = interp_from_variable_to_const_frm_rate(vv.astype(float), v_pm, 5.0, fs) > 0.5
-            v_f0c = v_f0c * vvc
-            feats = format_for_modelling(m_mag, m_real, m_imag, v_f0c, fs, mag_dim=mag_dim, phase_dim=phase_dim,
-                                         alpha_phase=alpha_phase)
-            out.append(feats + (v_shift, fs, fft_len))
-        return out
+        return _analysis_compressed_const_rate(l_sig, fs, l_pm_smpls, l_voi, fft_len, mag_dim, phase_dim, alpha_phase)
     plan = _MelPlan.get(fs, fft_len, mag_dim, phase_dim, alpha_phase)
     sig_off = np.zeros(len(l_sig) + 1, dtype=np.int64)
     centres, lefts, rights, vois, lf0s = [], [], [], [], []
@@ -493,6 +478,65 @@ def analysis_compressed_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None, mag_di
     for u in range(len(l_sig)):
         b = a + lefts[u].size
         out.append((o_mag[a:b], o_real[a:b], o_imag[a:b], lf0s[u], lefts[u].astype(int), fs, fft_len))
+        a = b
+    return out
+
+
+def const_rate_rows(v_pm_smpls, const_rate_ms, fs):
+    """Index form of interp_from_variable_to_const_frm_rate (src/magphase.py:2219-2239, linear): for every constant-rate
+    centre the two source frames and the weight of the second one.  Frame 0 is replicated at t = 0 when pm[0] > 0."""
+    step = fs * const_rate_ms / 1000
+    centres = np.arange(step, v_pm_smpls[-1], step)
+    x = np.asarray(v_pm_smpls, dtype=np.float64)
+    shift = 0
+    if x[0] > 0:
+        x = np.r_[0, x]
+        shift = 1
+    j = np.clip(np.searchsorted(x, centres, side='right') - 1, 0, x.size - 2)
+    w = (centres - x[j]) / (x[j + 1] - x[j])
+    r0 = np.maximum(j - shift, 0)
+    r1 = np.maximum(j + 1 - shift, 0)
+    return r0.astype(np.int32), r1.astype(np.int32), w
+
+
+def _analysis_compressed_const_rate(l_sig, fs, l_pm_smpls, l_voi, fft_len, mag_dim, phase_dim, alpha_phase):
+    """Constant-rate branch of analysis_compressed (src/magphase.py:2966-2983) on the device."""
+    plan = _MelPlan.get(fs, fft_len, mag_dim, phase_dim, alpha_phase)
+    sig_off, frm_off = 0, 0
+    centres, lefts, rights, r0s, r1s, ws, vois, lf0s, shifts, n_outs = [], [], [], [], [], [], [], [], [], []
+    for sig, pm, voi in zip(l_sig, l_pm_smpls, l_voi):
+        sig = np.asarray(sig)
+        P, v_shift, v_rights = frame_geometry(pm, sig.size)
+        _check_frames(v_shift, v_rights, fft_len)
+        v_f0 = shift_to_f0(v_shift.astype(int), np.asarray(voi, dtype=np.float64), fs, out='f0', b_smooth=False)
+        v_pm = np.cumsum(v_shift)                                   # la.shift_to_pm (:2970)
+        r0, r1, w = const_rate_rows(v_pm, 5.0, fs)
+        vv = v_f0 > 1.0
+        v_f0c = interp_from_variable_to_const_frm_rate(np.r_[v_f0[vv][0], v_f0[vv], v_f0[vv][-1]],
+                                                       np.r_[0, v_pm[vv], v_pm[-1]], 5.0, fs)
+        vvc = interp_from_variable_to_const_frm_rate(vv.astype(float), v_pm, 5.0, fs) > 0.5
+        v_voi_c, v_lf0 = _lf0_smoothed(v_f0c * vvc)
+        centres.append(P[1:-1] + sig_off); lefts.append(v_shift); rights.append(v_rights)
+        r0s.append(r0 + frm_off); r1s.append(r1 + frm_off); ws.append(w)
+        vois.append(v_voi_c > 0); lf0s.append(v_lf0); shifts.append(v_shift.astype(int)); n_outs.append(r0.size)
+        sig_off += sig.size
+        frm_off += v_shift.size
+    cat = lambda l, dt: np.ascontiguousarray(np.concatenate(l), dtype=dt)
+    centre, left, right = cat(centres, np.int64), cat(lefts, np.int32), cat(rights, np.int32)
+    lr0, lr1, lw, voi8 = cat(r0s, np.int32), cat(r1s, np.int32), cat(ws, np.float32), cat(vois, np.uint8)
+    sigs = [np.ascontiguousarray(s, dtype=np.float64) for s in l_sig]
+    sig_ptrs = (C.c_void_p * len(sigs))(*[s.ctypes.data for s in sigs])
+    sig_lens = np.ascontiguousarray([s.size for s in sigs], dtype=np.int64)
+    n = int(sum(n_outs))
+    o_mag = np.empty((n, mag_dim)); o_real = np.empty((n, phase_dim)); o_imag = np.empty((n, phase_dim))
+    _lib.check(_lib.lib().mpb_analysis_compressed_const_hostv(
+        plan.handle, sig_ptrs, _lib.ptr(sig_lens), len(sigs), _lib.ptr(centre), _lib.ptr(left), _lib.ptr(right),
+        centre.size, _lib.ptr(lr0), _lib.ptr(lr1), _lib.ptr(lw), _lib.ptr(voi8), n, _lib.ptr(o_mag), _lib.ptr(o_real),
+        _lib.ptr(o_imag)))
+    out, a = [], 0
+    for u in range(len(l_sig)):
+        b = a + n_outs[u]
+        out.append((o_mag[a:b], o_real[a:b], o_imag[a:b], lf0s[u], shifts[u], fs, fft_len))
         a = b
     return out
 

@@ -91,3 +91,18 @@ def test_host_bookkeeping_bit_exact():
         assert mp.define_fft_len(fs) == orc.define_fft_len(fs)
     with pytest.raises(ValueError):
         mp.define_alpha(8000)
+
+
+def test_const_rate_rows_reproduce_interp1d():
+    """Index form of interp_from_variable_to_const_frm_rate against the oracle's scipy interp1d, with and without
+    the replicated first row (pm[0] > 0 / pm[0] == 0)."""
+    import magphase_b200.magphase as mp
+    rng = np.random.default_rng(2)
+    for first in (0, 137):
+        pm = np.cumsum(np.r_[first, rng.integers(120, 900, 60)]).astype(np.int64)
+        data = rng.normal(size=(pm.size, 5))
+        r0, r1, w = mp.const_rate_rows(pm, 5.0, 48000)
+        got = data[r0] + (data[r1] - data[r0]) * w[:, None]
+        ref = orc.interp_from_variable_to_const_frm_rate(data, pm, 5.0, 48000)
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)

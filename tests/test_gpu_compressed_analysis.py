@@ -80,11 +80,19 @@ def test_analysis_compressed_batch_and_mag_dim_100(mp):
 
 
 def test_analysis_compressed_const_rate(mp):
-    sig, pm, voi = synth_utterance(9, fs=48000, dur_s=0.8)
-    ref = orc.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45, b_const_rate=True)
-    got = mp.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45, b_const_rate=True)
-    for a, b in zip(got[:4], ref[:4]):
-        assert a.shape == b.shape and rms(a, b) < TOL
+    """5 ms constant-rate output: the lossless rows are interpolated on the device inside the tile-product loader."""
+    utts = [synth_utterance(u, fs=48000, dur_s=0.8) for u in (9, 10)]
+    outs = mp.analysis_compressed_batch([u[0] for u in utts], 48000, [u[1] for u in utts], [u[2] for u in utts],
+                                        mag_dim=60, phase_dim=45, b_const_rate=True)
+    for (sig, pm, voi), got in zip(utts, outs):
+        ref = orc.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45, b_const_rate=True)
+        for a, b in zip(got[:3], ref[:3]):
+            assert a.shape == b.shape and rms(a, b) < TOL
+        assert np.array_equal(got[3], ref[3]) and np.array_equal(got[4], ref[4])
+    one = mp.analysis_compressed_from_pm(*utts[0][:1], 48000, utts[0][1], utts[0][2], mag_dim=60, phase_dim=45,
+                                         b_const_rate=True)
+    for a, b in zip(one[:4], outs[0][:4]):
+        assert np.array_equal(a, b)
 
 
 def test_dim_errors(mp):
