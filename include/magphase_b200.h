@@ -192,6 +192,13 @@ int mpb_analysis_compressed_hostv(mpb_mel* plan,
                                   const uint8_t* voi, int64_t nfrm, int compute_dtype,
                                   double* out_mag_mel, double* out_real_mel, double* out_imag_mel);
 
+/* la.sp_to_mcep (src/libaudio.py:575-601) itself, for three spectra at once: float32-rounded mel cepstra of a
+ * (in_type 3, |X|) and of b, c (in_type 2, ln|X|; pass x*ln(10)/20 for in_type 1 "dB" input).  HOST float64 rows of
+ * fft_len/2+1 bins; out_a: nfrm x n_mag, out_b / out_c: nfrm x n_ph.  Used by the legacy
+ * analysis_with_del_comp_and_ph_encoding (src/magphase.py:573-598).                                        */
+int mpb_sp_to_mcep_host(mpb_mel* plan, const double* a, const double* b, const double* c, int64_t nfrm,
+                        double* out_a, double* out_b, double* out_c);
+
 /* analysis_compressed(b_const_rate=True) (src/magphase.py:2966-2983): nfrm variable-rate frames are analysed on the
  * device; constant-rate output frame f is (1-w[f])*frame[r0[f]] + w[f]*frame[r1[f]] of the LOSSLESS features
  * (interp_from_variable_to_const_frm_rate, :2219-2239, interpolated inside the tile-product loader before the log) and

@@ -47,6 +47,7 @@ SIGNATURES = {
     'mpb_mel_compress_host': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     'mpb_analysis_compressed_host': [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp],
     'mpb_analysis_compressed_dev': [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int],
+    'mpb_sp_to_mcep_host': [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     'mpb_analysis_compressed_const_hostv': [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     'mpb_analysis_compressed_hostv': [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp],
     'mpb_syn_create': [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(_vp)],

@@ -73,11 +73,11 @@ int mpb_mel_get_warp_matrix(mpb_mel* m, int which, float* out_host) {
     return MPB_OK;
 }
 
-struct LerpRows { const int32_t* r0; const int32_t* r1; const float* w; };   // device arrays, one entry per OUTPUT frame
+struct LerpRows { const int32_t* r0; const int32_t* r1; const float* w; int raw_mc = 0; };   // device arrays, one entry per OUTPUT frame
 
 static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const void* real, const void* imag, int feat_dtype,
                              int pre_logp, const uint8_t* voi, int64_t nfrm, void* out_mag_mel, void* out_real_mel,
-                             void* out_imag_mel, int out_dtype, LerpRows lerp = LerpRows{nullptr, nullptr, nullptr});
+                             void* out_imag_mel, int out_dtype, LerpRows lerp = LerpRows{nullptr, nullptr, nullptr, 0});
 
 int mpb_mel_compress_dev(mpb_mel* m, void* stream, const void* mag, const void* real, const void* imag, int feat_dtype,
                          const uint8_t* voi, int64_t nfrm, void* out_mag_mel, void* out_real_mel, void* out_imag_mel,
@@ -109,6 +109,7 @@ static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const vo
     int32_t* d_cidx = d_vidx + chunk;
     int32_t* d_cnt = d_cidx + chunk;
     const size_t fes = feat_dtype == MPB_F64 ? 8 : 4, oes = out_dtype == MPB_F64 ? 8 : 4;
+    const int od_mag = m->n_mag, od_ph = lerp.raw_mc ? m->n_ph : m->phase_dim;   // output row widths
     for (int64_t f0 = 0; f0 < nfrm; f0 += chunk) {
         const int64_t n = nfrm - f0 < chunk ? nfrm - f0 : chunk;
         MelArgs a;
@@ -118,17 +119,19 @@ static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const vo
         a.imag = (const char*)imag + fes * src0 * H; a.feat_dtype = feat_dtype; a.pre_logp = pre_logp;
         a.lerp_r0 = lerp.r0 ? lerp.r0 + f0 : nullptr; a.lerp_r1 = lerp.r1 ? lerp.r1 + f0 : nullptr;
         a.lerp_w = lerp.w ? lerp.w + f0 : nullptr;
+        a.raw_mc = lerp.raw_mc;
         a.voi = voi + f0; a.nfrm = n; a.fft_len = m->fft_len;
         a.wt_mag = m->wt_mag; a.ld_mag = m->ld_mag; a.wt_ph = m->wt_ph; a.ld_ph = m->ld_ph;
         a.cos_mag = m->cos_mag; a.n_mag = m->n_mag; a.cos_ph = m->cos_ph; a.n_ph = m->n_ph; a.phase_dim = m->phase_dim;
         a.partial = (float*)m->partial.p; a.ncp_max = ncp;
-        a.out_mag = (char*)out_mag_mel + oes * f0 * m->n_mag;
-        a.out_real = (char*)out_real_mel + oes * f0 * m->phase_dim;
-        a.out_imag = (char*)out_imag_mel + oes * f0 * m->phase_dim;
+        a.out_mag = (char*)out_mag_mel + oes * f0 * od_mag;
+        a.out_real = (char*)out_real_mel + oes * f0 * od_ph;
+        a.out_imag = (char*)out_imag_mel + oes * f0 * od_ph;
         a.out_dtype = out_dtype;
         a.vidx = d_vidx; a.cidx = d_cidx; a.vcount = d_cnt;
-        LAUNCH(m->ctx, (cudaStream_t)stream, "k_voiced_compact",
-               launch_voiced_compact(a.voi, (int)n, d_vidx, d_cidx, d_cnt, (cudaStream_t)stream));
+        if (lerp.raw_mc) { a.vidx = nullptr; a.cidx = nullptr; a.vcount = nullptr; }   // every frame, every stream
+        else LAUNCH(m->ctx, (cudaStream_t)stream, "k_voiced_compact",
+                    launch_voiced_compact(a.voi, (int)n, d_vidx, d_cidx, d_cnt, (cudaStream_t)stream));
         LAUNCH(m->ctx, (cudaStream_t)stream, "k_mel_gemm", launch_mel_gemm(a, (cudaStream_t)stream));
         LAUNCH(m->ctx, (cudaStream_t)stream, "k_mel_finish", launch_mel_finish(a, (cudaStream_t)stream));
     }
@@ -345,6 +348,40 @@ int mpb_analysis_compressed_const_hostv(mpb_mel* m, const double* const* sigs, c
     CU(cudaMemcpyAsync(out_mag_mel, m->small[1].p, sizeof(double) * n_out * m->n_mag, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(out_real_mel, m->small[2].p, sizeof(double) * n_out * m->phase_dim, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(out_imag_mel, m->small[3].p, sizeof(double) * n_out * m->phase_dim, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MPB_OK;
+}
+
+// la.sp_to_mcep (src/libaudio.py:575-601) for three spectra at once: the float32-rounded mel cepstra of
+// a (in_type 3, |X|), b and c (in_type 2, ln|X|; feed x*ln(10)/20 for in_type 1 "dB" input), HOST float64 rows of
+// fft_len/2+1 bins.  out_a: nfrm x n_mag, out_b / out_c: nfrm x n_ph.  Any of b / c may alias a.
+int mpb_sp_to_mcep_host(mpb_mel* m, const double* a, const double* b, const double* c, int64_t nfrm, double* out_a,
+                        double* out_b, double* out_c) {
+    if (!m) return fail(MPB_ERR_BAD_ARG, "plan is NULL");
+    if (nfrm == 0) return MPB_OK;
+    if (!a || !b || !c || !out_a || !out_b || !out_c) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    mpb_ctx* ctx = m->ctx;
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int H = m->fft_len / 2 + 1;
+    const size_t fsz = sizeof(double) * (size_t)nfrm * H;
+    cudaStream_t st = ctx->stream;
+    for (int i = 0; i < 3; ++i) CU(m->feats[i].need(fsz));
+    CU(m->small[0].need((size_t)nfrm));
+    CU(m->small[1].need(sizeof(double) * nfrm * m->n_mag));
+    CU(m->small[2].need(sizeof(double) * nfrm * m->n_ph));
+    CU(m->small[3].need(sizeof(double) * nfrm * m->n_ph));
+    CU(cudaMemcpyAsync(m->feats[0].p, a, fsz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->feats[1].p, b, fsz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m->feats[2].p, c, fsz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(m->small[0].p, 1, (size_t)nfrm, st));
+    LerpRows lr{nullptr, nullptr, nullptr, 1};
+    int rc = mel_compress_impl(m, st, m->feats[0].p, m->feats[1].p, m->feats[2].p, MPB_F64, 0, (const uint8_t*)m->small[0].p,
+                               nfrm, m->small[1].p, m->small[2].p, m->small[3].p, MPB_F64, lr);
+    if (rc != MPB_OK) return rc;
+    CU(cudaMemcpyAsync(out_a, m->small[1].p, sizeof(double) * nfrm * m->n_mag, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_b, m->small[2].p, sizeof(double) * nfrm * m->n_ph, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_c, m->small[3].p, sizeof(double) * nfrm * m->n_ph, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return MPB_OK;
 }

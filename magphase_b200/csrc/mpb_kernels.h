@@ -50,6 +50,8 @@ constexpr int MEL_MAX_COEFFS = 128;    // largest supported mag_dim / nmel
 struct MelArgs {
     const void* mag; const void* real; const void* imag; int feat_dtype;   // nfrm x (fft_len/2+1)
     int pre_logp;                                                           // rows already hold log periodograms
+    int raw_mc;                                                             // output the float32-rounded mel cepstra themselves
+                                                                            // (la.sp_to_mcep): no cosine matrix, mask or clip
     const uint8_t* voi; int64_t nfrm; int fft_len;
     const float* wt_mag; int ld_mag; const float* wt_ph; int ld_ph;         // W^T, [kpad][ld] float32
     const double* cos_mag; int n_mag; const double* cos_ph; int n_ph; int phase_dim;

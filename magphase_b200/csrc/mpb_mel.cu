@@ -255,7 +255,7 @@ k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64
              const float* __restrict__ wt_mag, int ld_mag, const float* __restrict__ wt_ph, int ld_ph,
              const double* __restrict__ cos_mag, int n_mag, const double* __restrict__ cos_ph, int n_ph, int phase_dim,
              const uint8_t* __restrict__ voi, const int32_t* __restrict__ cidx, const int32_t* __restrict__ lr0,
-             const int32_t* __restrict__ lr1, const float* __restrict__ lw, TO* __restrict__ out_mag,
+             const int32_t* __restrict__ lr1, const float* __restrict__ lw, int raw_mc, TO* __restrict__ out_mag,
              TO* __restrict__ out_real, TO* __restrict__ out_imag) {
     __shared__ double mc[4][MEL_MAX_COEFFS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -263,7 +263,7 @@ k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64
     const int stream = blockIdx.y;
     if (f >= nfrm) return;
     const int n_in = stream == 0 ? n_mag : n_ph;
-    const int n_out = stream == 0 ? n_mag : phase_dim;
+    const int n_out = raw_mc ? n_in : (stream == 0 ? n_mag : phase_dim);
     const double* __restrict__ ct = stream == 0 ? cos_mag : cos_ph;      // [n_in][n_out]
     const TF* __restrict__ src = stream == 0 ? mag : (stream == 1 ? real : imag);
     const float* __restrict__ wt = stream == 0 ? wt_mag : wt_ph;
@@ -271,7 +271,7 @@ k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64
     TO* __restrict__ dst = (stream == 0 ? out_mag : (stream == 1 ? out_real : out_imag)) + f * (int64_t)n_out;
     const bool voiced = voi[f] != 0;
     int64_t row = f;                                                       // row of this frame in `partial`
-    if (stream != 0 && cidx) {
+    if (stream != 0 && cidx && !raw_mc) {
         if (!voiced) {                                                     // masked anyway (src/magphase.py:2527-2528)
             for (int o = lane; o < n_out; o += 32) dst[o] = (TO)0;
             return;
@@ -293,6 +293,10 @@ k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64
         mc[warp][j] = (double)(float)s;                                    // SPTK writes float32 (src/libaudio.py:593)
     }
     __syncwarp();
+    if (raw_mc) {                                                          // la.sp_to_mcep: the mel cepstrum itself
+        for (int o = lane; o < n_out; o += 32) dst[o] = (TO)mc[warp][o];
+        return;
+    }
     for (int o = lane; o < n_out; o += 32) {
         double s = 0.0;
         for (int j = 0; j < n_in; ++j) s = fma(mc[warp][j], ct[j * n_out + o], s);
@@ -335,7 +339,7 @@ static cudaError_t launch_finish_t(const MelArgs& a, cudaStream_t st) {
     dim3 g2((unsigned)((a.nfrm + 3) / 4), 3);
     k_mel_finish<TF, TO, PRE, LERP><<<g2, 128, 0, st>>>(a.partial, n_slices, a.ncp_max, a.nfrm, (const TF*)a.mag, (const TF*)a.real,
                                                    (const TF*)a.imag, H, a.wt_mag, a.ld_mag, a.wt_ph, a.ld_ph, a.cos_mag,
-                                                   a.n_mag, a.cos_ph, a.n_ph, a.phase_dim, a.voi, a.cidx, a.lerp_r0, a.lerp_r1, a.lerp_w, (TO*)a.out_mag,
+                                                   a.n_mag, a.cos_ph, a.n_ph, a.phase_dim, a.voi, a.cidx, a.lerp_r0, a.lerp_r1, a.lerp_w, a.raw_mc, (TO*)a.out_mag,
                                                    (TO*)a.out_real, (TO*)a.out_imag);
     return cudaGetLastError();
 }

@@ -891,3 +891,78 @@ def numpy_stream_uniform(low, high, n):
                                                    _lib.ptr(out)))
     np.random.set_state((st[0], key, int(pos.value), st[3], st[4]))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# legacy v1 analysis (kept for its signature: named in BASELINE.json north_star)
+# ----------------------------------------------------------------------------------------------
+def next_pow_of_two(x):
+    """src/libaudio.py next_pow_of_two"""
+    if x < 2:
+        x = 2
+    return int(2 ** np.ceil(np.log2(x)).astype(int))
+
+
+def _raw_mcep_plan(fft_len, n_coeffs, alpha):
+    """A mel plan whose three streams all produce plain la.sp_to_mcep output (n_coeffs each)."""
+    key = ('raw', _lib.default_device(), fft_len, n_coeffs, float("%1.2f" % alpha))
+    if key not in _MelPlan._cache:
+        eye = np.ascontiguousarray(np.eye(n_coeffs))
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mpb_mel_create(_lib.ctx(), fft_len, float("%1.2f" % alpha), n_coeffs, float("%1.2f" % alpha),
+                                             n_coeffs, n_coeffs, _lib.ptr(eye), _lib.ptr(eye), C.byref(h)))
+        _MelPlan._cache[key] = h
+    return _MelPlan._cache[key]
+
+
+def sp_to_mcep(m_sp, n_coeffs=60, alpha=0.77, in_type=3, fft_len=0):
+    """la.sp_to_mcep (src/libaudio.py:575-601): SPTK `mcep -a alpha -m n-1 -l fft_len -e 1.0E-8 -j 0 -f 0.0 -q in_type`
+    on the device (see mpb_mel.cu for the restatement).  in_type: 3 |f(w)|, 2 ln|f(w)|, 1 20*log10|f(w)|."""
+    m = np.ascontiguousarray(m_sp, dtype=np.float64)
+    if fft_len == 0:
+        fft_len = 2 * (m.shape[1] - 1)
+    if in_type == 1:
+        m = np.ascontiguousarray(m.astype(np.float32).astype(np.float64) * (np.log(10.0) / 20.0))   # dB -> ln
+    elif in_type not in (2, 3):
+        raise ValueError('in_type must be 1, 2 or 3')
+    h = _raw_mcep_plan(fft_len, n_coeffs, alpha)
+    outs = [np.empty((m.shape[0], n_coeffs)) for _ in range(3)]
+    _lib.check(_lib.lib().mpb_sp_to_mcep_host(h, _lib.ptr(m), _lib.ptr(m), _lib.ptr(m), m.shape[0], _lib.ptr(outs[0]),
+                                              _lib.ptr(outs[1]), _lib.ptr(outs[2])))
+    return outs[0] if in_type == 3 else outs[1]
+
+
+def analysis_with_del_comp_and_ph_encoding(v_in_sig, nFFT, fs, mvf, pm=None):
+    """Legacy v1 analysis (src/magphase.py:573-598 over analysis_with_del_comp :338-368): spectral envelope and the
+    sine / cosine of the phase up to `mvf` Hz, each as 60 mel-cepstral coefficients.
+    Returns (m_spmgc, m_phs_mgc, m_phc_mgc, v_shift).  `pm` (seconds) replaces the REAPER call when given."""
+    v_in_sig = np.asarray(v_in_sig, dtype=np.float64)
+    if pm is None:
+        tmp_wav, tmp_est = io.ins_pid('temp.wav'), io.ins_pid('temp.pm')
+        reaper = io.find_tool('reaper')
+        if reaper is None:
+            raise RuntimeError('REAPER binary not found: pass pm=<pitch marks in seconds>')
+        io.write_audio_file(tmp_wav, v_in_sig, fs, norm=None)
+        call(reaper + " -s -x 400 -m 50 -a -u 0.005 -i %s -p %s" % (tmp_wav, tmp_est), shell=True)
+        pm = np.loadtxt(tmp_est, skiprows=7)[:, 0]
+        os.remove(tmp_wav); os.remove(tmp_est)
+        pm = pm[np.hstack((True, np.diff(pm) > 0))]                       # src/libaudio.py:479-485
+        if (pm[-1] * fs) >= (np.size(v_in_sig) - 1):
+            pm = pm[:-1]
+    v_pm_smpls = np.asarray(pm, dtype=np.float64) * fs
+    P, v_shift, v_rights = frame_geometry(v_pm_smpls, v_in_sig.size)
+    len_max = int(np.max(v_shift + v_rights + 1))
+    if nFFT < len_max:
+        raise ValueError("nFFT (%d) is shorter than the maximum frame length (%d)" % (nFFT, len_max))
+    (m_sp, m_phc, m_phs), _, _ = _frames_call([v_in_sig], [v_pm_smpls], nFFT, [np.hanning], 'feats')
+    m_phc = np.where(m_sp == 0.0, 1.0, m_phc)                             # np.angle(0) = 0 -> cos = 1 (:423-426)
+    m_spmgc = sp_to_mcep(m_sp)                                            # 60 coefficients, alpha 0.77, in_type 3
+    mvf_bin = int(round_to_int(mvf * nFFT / float(fs)))
+    n_ph = next_pow_of_two(mvf_bin) + 1
+    from scipy import interpolate                                         # cubic resampling of a handful of bins: host
+    grid = np.linspace(0, mvf_bin - 1, n_ph)
+    m_phs_i = interpolate.interp1d(np.arange(mvf_bin), m_phs[:, :mvf_bin], kind='cubic')(grid)
+    m_phc_i = interpolate.interp1d(np.arange(mvf_bin), m_phc[:, :mvf_bin], kind='cubic')(grid)
+    m_phs_mgc = sp_to_mcep(m_phs_i, in_type=1)
+    m_phc_mgc = sp_to_mcep(m_phc_i, in_type=1)
+    return m_spmgc, m_phs_mgc, m_phc_mgc, v_shift.astype(int)

@@ -612,3 +612,34 @@ def analysis_compressed_from_pm(v_sig, fs, v_pm_smpls, v_voi, fft_len=None, mag_
     feats = format_for_modelling(m_mag, m_real, m_imag, v_f0, fs, mag_dim=mag_dim, phase_dim=phase_dim,
                                  alpha_phase=alpha_phase)
     return feats + (v_shift, fs, 2 * (m_mag.shape[1] - 1))
+
+
+# ----------------------------------------------------------------------------------------
+# legacy v1 analysis                                  src/magphase.py:573-598 over :338-368
+# ----------------------------------------------------------------------------------------
+def next_pow_of_two(x):
+    """src/libaudio.py next_pow_of_two"""
+    if x < 2:
+        x = 2
+    return int(2 ** np.ceil(np.log2(x)).astype(int))
+
+
+def analysis_with_del_comp_and_ph_encoding_from_pm(v_in_sig, nFFT, fs, mvf, v_pm_sec):
+    """analysis_with_del_comp_and_ph_encoding with REAPER's pitch marks (seconds) given as input.
+    The three la.sp_to_mcep calls go through mcep_j0 (SPTK restatement, parity unpinned)."""
+    v_pm_smpls = np.asarray(v_pm_sec, dtype=np.float64) * fs
+    P, v_shift, v_rights = frame_limits(v_pm_smpls, np.size(v_in_sig))
+    len_max = int(np.max(v_shift + v_rights + 1))
+    if nFFT < len_max:
+        raise ValueError("nFFT (%d) is shorter than the maximum frame length (%d)" % (nFFT, len_max))
+    m_frms, v_shift, _ = analysis_frames(v_in_sig, v_pm_smpls, nFFT)
+    m_fft = np.fft.fft(m_frms)[:, :nFFT // 2 + 1]
+    m_sp, m_ph = np.absolute(m_fft), np.angle(m_fft)
+    m_phs, m_phc = np.sin(m_ph), np.cos(m_ph)
+    m_spmgc = mcep_j0(m_sp)
+    mvf_bin = int(round_to_int(mvf * nFFT / float(fs)))
+    n_ph = next_pow_of_two(mvf_bin) + 1
+    grid = np.linspace(0, mvf_bin - 1, n_ph)
+    m_phs_i = interpolate.interp1d(np.arange(mvf_bin), m_phs[:, :mvf_bin], kind='cubic')(grid)
+    m_phc_i = interpolate.interp1d(np.arange(mvf_bin), m_phc[:, :mvf_bin], kind='cubic')(grid)
+    return m_spmgc, mcep_j0(m_phs_i, in_type=1), mcep_j0(m_phc_i, in_type=1), v_shift

@@ -101,3 +101,23 @@ def test_dim_errors(mp):
         mp.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=300, phase_dim=45)
     with pytest.raises(ValueError):
         mp.analysis_compressed_from_pm(sig, 8000, pm, voi)
+
+
+def test_legacy_analysis_with_del_comp_and_ph_encoding(mp):
+    """Named in BASELINE.json north_star: signature (v_in_sig, nFFT, fs, mvf) -> 4-tuple kept; runs on the analysis
+    and mel kernels (sp_to_mcep on the device) + host cubic resampling."""
+    sig, pm, voi = synth_utterance(14, fs=48000, dur_s=0.5)
+    pm_sec = pm / 48000.0
+    ref = orc.analysis_with_del_comp_and_ph_encoding_from_pm(sig, 4096, 48000, 4500, pm_sec)
+    got = mp.analysis_with_del_comp_and_ph_encoding(sig, 4096, 48000, 4500, pm=pm_sec)
+    assert len(got) == 4 and np.array_equal(got[3], ref[3])
+    assert rms(got[0], ref[0]) < TOL and got[0].shape == (pm.size, 60)
+    # the phase streams are cepstra of 10^(sin/10)-type spectra (in_type=1 applied to values in [-1, 1]):
+    # well conditioned, same 1e-5 bar
+    assert rms(got[1], ref[1]) < TOL and rms(got[2], ref[2]) < TOL
+    with pytest.raises(ValueError):
+        mp.analysis_with_del_comp_and_ph_encoding(sig, 512, 48000, 4500, pm=pm_sec)
+    # sp_to_mcep alone, all three input types
+    mag = orc.analysis_lossless_from_pm(sig, 48000, pm, voi)[0]
+    for it, x in ((3, mag), (2, np.log(mag + 1e-3)), (1, 20 * np.log10(mag + 1e-3))):
+        assert rms(mp.sp_to_mcep(x, in_type=it), orc.mcep_j0(x, in_type=it)) < TOL

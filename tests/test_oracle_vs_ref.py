@@ -156,3 +156,23 @@ def test_var_to_const_rate_matches_reference(ref_modules):
     m = rng.normal(size=(50, 7))
     np.testing.assert_allclose(orc.interp_from_variable_to_const_frm_rate(m, pm, 5.0, 48000),
                                mp.interp_from_variable_to_const_frm_rate(m.copy(), pm, 5.0, 48000), rtol=0, atol=1e-14)
+
+
+def test_legacy_ph_encoding_matches_reference_around_sptk(ref_modules, monkeypatch):
+    """analysis_with_del_comp_and_ph_encoding (src/magphase.py:573-598): the reference needs REAPER and SPTK; with
+    la.get_pitch_marks fed the same marks and la.sp_to_mcep replaced by the oracle's restatement of `mcep -j 0`,
+    everything else (windowing, FFT, phase encoding, cubic resampling, dimensions) is the reference's own code."""
+    mp, la, lu = ref_modules
+    sig, pm, voi = synth_utterance(14, dur_s=0.5)
+    pm_sec = pm / 48000.0
+    monkeypatch.setattr(la, 'get_pitch_marks', lambda v_sig, fs: pm_sec)
+    monkeypatch.setattr(la, 'sp_to_mcep', lambda m_sp, n_coeffs=60, alpha=0.77, in_type=3, fft_len=0:
+                        orc.mcep_j0(m_sp, n_coeffs=n_coeffs, alpha=alpha, in_type=in_type, fft_len=fft_len))
+    ref = mp.analysis_with_del_comp_and_ph_encoding(sig, 4096, 48000, 4500)
+    got = orc.analysis_with_del_comp_and_ph_encoding_from_pm(sig, 4096, 48000, 4500, pm_sec)
+    assert np.array_equal(got[3], ref[3])
+    for a, b in zip(got[:3], ref[:3]):
+        assert a.shape == b.shape == (pm.size, 60)
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-5)     # float32 outputs of an ill-conditioned dB -> cepstrum map
+    with pytest.raises(ValueError):
+        mp.analysis_with_del_comp_and_ph_encoding(sig, 512, 48000, 4500)
