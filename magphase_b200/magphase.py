@@ -685,6 +685,22 @@ def synthesis_from_compressed(m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0, fs, 
                                            alpha_phase=alpha_phase, b_out_hpf=b_out_hpf)[0]
 
 
+def _stack_rows(l_arr):
+    """np.concatenate(l_arr, axis=0) as float64 -- without the copy when the arrays already are consecutive row blocks
+    of one C-contiguous float64 buffer (what the *_batch analysis functions return)."""
+    a0 = l_arr[0]
+    if all(isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags['C_CONTIGUOUS'] and a.ndim == 2 for a in l_arr):
+        base = a0.base if a0.base is not None else a0
+        ptr, ok = a0.ctypes.data, isinstance(base, np.ndarray) and base.ndim == 2 and base.flags['C_CONTIGUOUS']
+        for a in l_arr:
+            ok = ok and (a.base is base or a is base) and a.ctypes.data == ptr and a.shape[1] == base.shape[1]
+            ptr += a.nbytes
+        if ok and a0.ctypes.data >= base.ctypes.data and ptr <= base.ctypes.data + base.nbytes:
+            r0 = (a0.ctypes.data - base.ctypes.data) // (base.shape[1] * 8)
+            return base[r0:r0 + sum(a.shape[0] for a in l_arr)]
+    return np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64) for a in l_arr], axis=0))
+
+
 def compressed_synthesis_geometry(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win=True, b_const_rate=False):
     """Host bookkeeping of synthesis_from_compressed for a batch (src/magphase.py:846-848, 861-870, 879-882,
     886-896, 968-971, 34-62): everything integer / float64 that the kernels consume as arrays.
@@ -791,8 +807,7 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
         need = np.zeros_like(need)          # phase rows come from the minimum-phase kernel instead
     out_off = arrs['utt_out_off']
     fr = _lib.SynFrames(nfrm=int(arrs['utt_frm_off'][-1]), n_utt=n_utt, **{k: _lib.ptr(v) for k, v in arrs.items()})
-    cat = lambda i: np.ascontiguousarray(np.concatenate([np.asarray(f[i], dtype=np.float64) for f in l_feats], axis=0))
-    mag, real, imag = cat(0), cat(1), cat(2)
+    mag, real, imag = (_stack_rows([f[i] for f in l_feats]) for i in range(3))
     noise = None
     if l_noise is not None:
         noise = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in l_noise]))
