@@ -26,7 +26,7 @@ int mpb_mel_create(mpb_ctx* ctx, int fft_len, double alpha_mag, int n_mag, doubl
     if (!ctx || !out || !cos_mag || !cos_ph) return fail(MPB_ERR_BAD_ARG, "NULL argument");
     if (!fft_len_ok(fft_len)) return fail(MPB_ERR_FFT_LEN, "fft_len must be 1024, 2048 or 4096");
     if (n_mag < 2 || n_ph < 2 || phase_dim < 1 || phase_dim > n_ph || n_mag > MEL_MAX_COEFFS || n_ph > MEL_MAX_COEFFS)
-        return fail(MPB_ERR_DIM, "mel dimensions must satisfy 2 <= mag_dim, nmel <= 128 and 1 <= phase_dim <= nmel");
+        return fail(MPB_ERR_DIM, "mel dimensions must satisfy 2 <= mag_dim, nmel <= 256 and 1 <= phase_dim <= nmel");
     CU(cudaSetDevice(ctx->device));
     mpb_mel* m = new mpb_mel();
     m->ctx = ctx; m->fft_len = fft_len; m->n_mag = n_mag; m->n_ph = n_ph; m->phase_dim = phase_dim;

@@ -36,7 +36,7 @@ int mpb_syn_create(mpb_ctx* ctx, int fft_len, int n_mag, int n_ph, int hb, const
     if (!fft_len_ok(fft_len)) return fail(MPB_ERR_FFT_LEN, "fft_len must be 1024, 2048 or 4096");
     const int H = fft_len / 2 + 1;
     if (n_mag < 1 || n_ph < 1 || n_mag > MEL_MAX_COEFFS || n_ph > MEL_MAX_COEFFS)
-        return fail(MPB_ERR_DIM, "mel dimensions must be in 1..128");
+        return fail(MPB_ERR_DIM, "mel dimensions must be in 1..256");
     if (hb < 1 || hb > fft_len / 4)
         return fail(MPB_ERR_DIM, "the periodic band (crossfade upper edge) must end at or below fft_len/4 bins");
     CU(cudaSetDevice(ctx->device));

@@ -45,7 +45,7 @@ cudaError_t launch_synthesis_lossless(const SynthArgs& a, cudaStream_t st);
 
 // ---- mel compression (mpb_mel.cu) ----
 constexpr int MEL_KSLICE = 128;        // spectral bins per K-slice of the tile product
-constexpr int MEL_MAX_COEFFS = 128;    // largest supported mag_dim / nmel
+constexpr int MEL_MAX_COEFFS = 256;    // largest supported mag_dim / nmel (nmel = 212 for phase_dim 45 at alpha_phase 0)
 
 struct MelArgs {
     const void* mag; const void* real; const void* imag; int feat_dtype;   // nfrm x (fft_len/2+1)
