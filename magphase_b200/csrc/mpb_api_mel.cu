@@ -15,7 +15,7 @@ struct mpb_mel {
     std::mutex mu;
 };
 
-static constexpr int64_t MEL_CHUNK = 16384;   // frames per pass: bounds the K-slice partial-sum scratch (~210 MB)
+static constexpr int64_t MEL_CHUNK = 32768;   // frames per pass: bounds the K-slice partial-sum scratch (~400 MB)
 
 static int pad64(int n) { return ((n + 63) / 64) * 64; }
 

@@ -13,18 +13,20 @@ extern "C" int mpb_plan_ola_runs(const int32_t* pm, const int64_t* utt_frm_off, 
 struct mpb_syn {
     mpb_ctx* ctx = nullptr;
     int fft_len = 0, n_mag = 0, n_ph = 0, H = 0, HB = 0;
-    float* u_mag = nullptr;   // [n_mag][H]
-    float* u_ph = nullptr;    // [n_ph][HB]
+    float* u_mag = nullptr;   // [n_mag][HP]   (rows pitched to 16 bytes, zero padded)
+    float* u_ph = nullptr;    // [n_ph][HBP]
     float* tab = nullptr;     // [3][H]
     DevBuf unw[3], logsq, gain, host_in[20], out;
     std::mutex mu;
 };
 
-static int upload_f32(const double* src, size_t n, float** dst) {
-    std::vector<float> h(n);
-    for (size_t i = 0; i < n; ++i) h[i] = (float)src[i];
-    CU(cudaMalloc((void**)dst, sizeof(float) * n));
-    CU(cudaMemcpy(*dst, h.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+// float64 host rows (pitch `cols`) -> float32 device rows pitched to `pitch` >= cols, zero padded
+static int upload_f32(const double* src, size_t rows, size_t cols, size_t pitch, float** dst) {
+    std::vector<float> h(rows * pitch, 0.0f);
+    for (size_t r = 0; r < rows; ++r)
+        for (size_t c = 0; c < cols; ++c) h[r * pitch + c] = (float)src[r * cols + c];
+    CU(cudaMalloc((void**)dst, sizeof(float) * h.size()));
+    CU(cudaMemcpy(*dst, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice));
     return MPB_OK;
 }
 
@@ -42,9 +44,9 @@ int mpb_syn_create(mpb_ctx* ctx, int fft_len, int n_mag, int n_ph, int hb, const
     CU(cudaSetDevice(ctx->device));
     mpb_syn* s = new mpb_syn();
     s->ctx = ctx; s->fft_len = fft_len; s->n_mag = n_mag; s->n_ph = n_ph; s->H = H; s->HB = hb;
-    int rc = upload_f32(u_mag, (size_t)n_mag * H, &s->u_mag);
-    if (rc == MPB_OK) rc = upload_f32(u_ph, (size_t)n_ph * hb, &s->u_ph);
-    if (rc == MPB_OK) rc = upload_f32(tab, (size_t)3 * H, &s->tab);
+    int rc = upload_f32(u_mag, n_mag, H, (H + 3) & ~3, &s->u_mag);
+    if (rc == MPB_OK) rc = upload_f32(u_ph, n_ph, hb, (hb + 3) & ~3, &s->u_ph);
+    if (rc == MPB_OK) rc = upload_f32(tab, 3, H, H, &s->tab);
     if (rc != MPB_OK) { delete s; return rc; }
     *out = s;
     return MPB_OK;

@@ -70,7 +70,7 @@ cudaError_t launch_mel_finish(const MelArgs& a, cudaStream_t st);
 struct UnwarpArgs {
     const void* mag_mel; const void* real_mel; const void* imag_mel; int in_dtype;   // [nfrm][n_mag], [nfrm][n_ph]
     const uint8_t* need_ph; int64_t nfrm; int n_mag; int n_ph;
-    const float* u_mag; int H; const float* u_ph; int HB;                           // [n_mag][H], [n_ph][HB]
+    const float* u_mag; int H; const float* u_ph; int HB;                           // [n_mag][HP], [n_ph][HBP] (zero padded)
     float* out_mag; float* out_real; float* out_imag;                               // [nfrm][HP], [nfrm][HBP] x2
     int HP; int HBP;                                                                // row pitches (multiples of 4 floats)
 };

@@ -30,8 +30,7 @@ k_mel_unwarp(const TI* __restrict__ mag_mel, const TI* __restrict__ real_mel, co
     if ((int)blockIdx.y < tiles_mag) { stream = 0; btile = blockIdx.y; }
     else { stream = 1 + ((int)blockIdx.y - tiles_mag) / tiles_ph; btile = ((int)blockIdx.y - tiles_mag) % tiles_ph; }
     const int K = stream == 0 ? n_mag : n_ph;
-    const int nb = stream == 0 ? H : HB;                  // bins of this stream (= row pitch of U)
-    const int np = stream == 0 ? HP : HBP;                // row pitch of the output scratch (multiple of 4 floats)
+    const int np = stream == 0 ? HP : HBP;                // row pitch of U and of the output scratch (multiple of 4 floats)
     const TI* __restrict__ X = stream == 0 ? mag_mel : (stream == 1 ? real_mel : imag_mel);
     const float* __restrict__ U = stream == 0 ? u_mag : u_ph;
     float* __restrict__ Y = stream == 0 ? out_mag : (stream == 1 ? out_real : out_imag);
@@ -45,13 +44,17 @@ k_mel_unwarp(const TI* __restrict__ mag_mel, const TI* __restrict__ real_mel, co
         for (int i = 0; i < UW_FT && f0 + i < nfrm; ++i) any |= need_ph[f0 + i] != 0;
         if (!any) return;
     }
-    for (int i = tid; i < UW_FT * K; i += 128) {          // features: row-major in HBM -> transposed tile
+    // features: the 64 x K tile is one contiguous run of the row-major matrix -> linear coalesced read, transposed store
+    for (int i = tid; i < UW_FT * K; i += 128) {
         const int f = i / K, c = i % K;
         Xs[c * UW_LDX + f] = (f0 + f < nfrm) ? (float)X[(f0 + f) * (int64_t)K + c] : 0.0f;
     }
-    for (int i = tid; i < K * UW_BT; i += 128) {
-        const int c = i / UW_BT, b = i % UW_BT;
-        Us[i] = (b0 + b < nb) ? __ldg(U + (size_t)c * nb + b0 + b) : 0.0f;
+    // un-warp matrix tile: rows are pitched to 16 bytes and zero padded on the host side -> float4 copies
+    for (int i = tid; i < K * (UW_BT / 4); i += 128) {
+        const int c = i / (UW_BT / 4), b4 = i % (UW_BT / 4);
+        const int b = b0 + 4 * b4;
+        reinterpret_cast<float4*>(Us)[i] = b < np ? __ldg(reinterpret_cast<const float4*>(U + (size_t)c * np + b))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
 
