@@ -402,13 +402,19 @@ def main():
         'k_synthesis_compressed': nf * H * 4 + 0.4 * nf * 2 * 513 * 4 + getattr(plan, 'n_noise', 0) * 4 + nf * 45
                                   + getattr(plan, 'n_out', 0) * 4,
     }
+    traffic_pf, traffic_src = {}, None
+    tpath = os.path.join(ROOT, 'profiles', 'r1', 'traffic_per_frame.json')
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic_pf, traffic_src = tj['dram_bytes_per_frame'], 'profiles/r1/traffic_per_frame.json (ncu --set full capture, scaled to this launch size)'
     kernels = []
     for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
         per_step_ms = ms / prof_steps
         kb = float(kbytes.get(name, 0))
         gbs = kb / (per_step_ms * 1e-3) / 1e9 if per_step_ms > 0 else 0.0
         kernels.append(dict(name=name, launches_per_step=cnt // prof_steps, ms_per_step=per_step_ms,
-                            algorithmic_bytes_per_step=int(kb), gbs=gbs, frac=gbs / peak))
+                            algorithmic_bytes_per_step=int(kb), gbs=gbs, frac=gbs / peak,
+                            dram_traffic_per_step=(int(traffic_pf[name] * nf) if name in traffic_pf else None)))
     dom = kernels[0]
     ms_per_step = total_ms / a.steps
     value = frames_all / (ms_per_step * 1e-3)
@@ -426,7 +432,10 @@ def main():
                 'd2h_bytes_per_step': int(d2h), 'utts_per_gpu_per_step': len(e_utts), 'api': api},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s',
-                     'frac': dom['frac'], 'traffic': None, 'peak_source': peak_src,
+                     'frac': dom['frac'],
+                     'traffic': (int(dom['dram_traffic_per_step'] / max(dom['launches_per_step'], 1))
+                                 if dom['dram_traffic_per_step'] else None),
+                     'traffic_source': traffic_src, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': int(dom['algorithmic_bytes_per_step'] / max(dom['launches_per_step'], 1)),
                      'ms_per_launch': dom['ms_per_step'] / max(dom['launches_per_step'], 1)},
         'halves': {'analysis_ms': ana_ms, 'synthesis_ms': syn_ms,
