@@ -58,6 +58,10 @@ int64_t mpb_launch_count(const mpb_ctx* ctx);
 int mpb_profile_begin(mpb_ctx* ctx);
 int mpb_profile_end(mpb_ctx* ctx, char* buf, int64_t buf_len);
 
+/* Page-locked host buffers for result arrays (device->host copies into them run at full PCIe rate).            */
+int mpb_host_alloc(mpb_ctx* ctx, int64_t bytes, void** out);
+int mpb_host_free(mpb_ctx* ctx, void* p);
+
 /* ---- lossless analysis --------------------------------------------------------------------- */
 /*
  * Replaces windowing() + the pad/rotate loop + np.fft.fft + remove_hermitian_half of

@@ -29,6 +29,8 @@ SIGNATURES = {
     'mpb_last_error': [],
     'mpb_version': [],
     'mpb_launch_count': [_vp],
+    'mpb_host_alloc': [_vp, _i64, C.POINTER(_vp)],
+    'mpb_host_free': [_vp, _vp],
     'mpb_profile_begin': [_vp],
     'mpb_profile_end': [_vp, C.c_char_p, _i64],
     'mpb_analysis_lossless_dev': [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int,
@@ -141,6 +143,64 @@ def profile_end(device=None):
         name, cnt, ms = line.rsplit(' ', 2)
         out[name] = (int(cnt), float(ms))
     return out
+
+
+class _PinnedPool:
+    """Recycled page-locked result buffers.  empty(shape) hands out a NumPy array backed by pinned memory; when the
+    array (and every view of it) is garbage collected the buffer goes back to the pool (bounded), so steady-state
+    batch loops neither page-fault fresh memory nor bounce D2H copies through the driver's staging buffer."""
+    MAX_POOLED = 2 << 30          # bytes kept for reuse
+    MAX_SINGLE = 1 << 30          # larger requests use ordinary pageable memory
+
+    def __init__(self):
+        self.free = {}            # bucket size -> [address]
+        self.pooled = 0
+        self.lock = threading.Lock()
+
+    @staticmethod
+    def _bucket(nbytes):
+        b = 1 << 16
+        while b < nbytes:
+            b <<= 1
+        return b if b - nbytes < (b >> 2) else ((nbytes + (1 << 20) - 1) >> 20) << 20
+
+    def empty(self, shape, dtype=np.float64):
+        import weakref
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        if nbytes == 0 or nbytes > self.MAX_SINGLE:
+            return np.empty(shape, dtype=dtype)
+        size = self._bucket(nbytes)
+        with self.lock:
+            lst = self.free.get(size)
+            addr = lst.pop() if lst else None
+            if addr is not None:
+                self.pooled -= size
+        if addr is None:
+            p = _vp()
+            try:
+                check(lib().mpb_host_alloc(ctx(), size, C.byref(p)))
+            except RuntimeError:
+                return np.empty(shape, dtype=dtype)
+            addr = p.value
+        buf = (C.c_char * size).from_address(addr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        weakref.finalize(buf, self._release, addr, size)
+        return arr
+
+    def _release(self, addr, size):
+        with self.lock:
+            if self.pooled + size <= self.MAX_POOLED:
+                self.free.setdefault(size, []).append(addr)
+                self.pooled += size
+                return
+        try:
+            lib().mpb_host_free(ctx(), _vp(addr))
+        except Exception:
+            pass
+
+
+pinned = _PinnedPool()
 
 
 def ptr(a):

@@ -525,4 +525,22 @@ int mpb_sos2_host(mpb_ctx* ctx, double* x, const int64_t* utt_off, int32_t n_utt
     return MPB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Page-locked host memory for result arrays: device -> host copies into it run at full PCIe rate instead of being
+// bounced through the driver's staging buffer into fresh pageable memory.  The Python mirror pools these buffers.
+int mpb_host_alloc(mpb_ctx* ctx, int64_t bytes, void** out) {
+    if (!ctx || !out || bytes < 0) return fail(MPB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+    return MPB_OK;
+}
+
+int mpb_host_free(mpb_ctx* ctx, void* p) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (!p) return MPB_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaFreeHost(p));
+    return MPB_OK;
+}
+
 }  // extern "C"

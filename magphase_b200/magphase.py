@@ -165,7 +165,7 @@ def _frames_call(l_sig, l_pm, fft_len, l_win, mode, compute=None):
                                          _lib.ptr(right), _lib.ptr(win), nfrm, fft_len, compute, _lib.ptr(out)))
         outs = (out,)
     else:
-        outs = tuple(np.empty((nfrm, H), dtype=np.float64) for _ in range(3))
+        outs = tuple(_lib.pinned.empty((nfrm, H)) for _ in range(3))
         _lib.check(l.mpb_analysis_lossless_host(_lib.ctx(), _lib.ptr(sig_all), sig_all.size, _lib.ptr(centre),
                                                 _lib.ptr(left), _lib.ptr(right), _lib.ptr(win), nfrm, fft_len, compute,
                                                 _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2])))
@@ -288,7 +288,7 @@ def _synthesis_lossless_call(l_feats, l_pm_int, l_t0, l_nout, fft_len, compute=N
         raise ValueError('feature matrices must be nfrms x %d' % H)
     pm = np.ascontiguousarray(np.concatenate(l_pm_int), dtype=np.int32)
     t0 = np.ascontiguousarray(l_t0, dtype=np.int32)
-    out = np.empty(int(out_off[-1]), dtype=np.float64)
+    out = _lib.pinned.empty(int(out_off[-1]))
     _lib.check(_lib.lib().mpb_synthesis_lossless_host(
         _lib.ctx(), _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), _lib.ptr(pm), pm.size, _lib.ptr(frm_off),
         _lib.ptr(out_off), _lib.ptr(t0), n_utt, fft_len, compute, _lib.ptr(out), out.size))
@@ -470,7 +470,7 @@ def analysis_compressed_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None, mag_di
     sig_ptrs = (C.c_void_p * len(sigs))(*[s.ctypes.data for s in sigs])
     sig_lens = np.ascontiguousarray([s.size for s in sigs], dtype=np.int64)
     n = centre.size
-    o_mag = np.empty((n, mag_dim)); o_real = np.empty((n, phase_dim)); o_imag = np.empty((n, phase_dim))
+    o_mag, o_real, o_imag = (_lib.pinned.empty((n, d)) for d in (mag_dim, phase_dim, phase_dim))
     _lib.check(_lib.lib().mpb_analysis_compressed_hostv(
         plan.handle, sig_ptrs, _lib.ptr(sig_lens), len(sigs), _lib.ptr(centre), _lib.ptr(left), _lib.ptr(right),
         _lib.ptr(voi8), n, ANALYSIS_COMPUTE, _lib.ptr(o_mag), _lib.ptr(o_real), _lib.ptr(o_imag)))
@@ -686,18 +686,20 @@ def synthesis_from_compressed(m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0, fs, 
 
 
 def _stack_rows(l_arr):
-    """np.concatenate(l_arr, axis=0) as float64 -- without the copy when the arrays already are consecutive row blocks
-    of one C-contiguous float64 buffer (what the *_batch analysis functions return)."""
+    """np.concatenate(l_arr, axis=0) as float64 -- without the copy when the arrays already sit back to back in memory
+    (the row blocks the *_batch analysis functions return).  The result is only used as a read-only argument of a C
+    call made while the inputs are still referenced, so viewing across the blocks is safe."""
     a0 = l_arr[0]
-    if all(isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags['C_CONTIGUOUS'] and a.ndim == 2 for a in l_arr):
-        base = a0.base if a0.base is not None else a0
-        ptr, ok = a0.ctypes.data, isinstance(base, np.ndarray) and base.ndim == 2 and base.flags['C_CONTIGUOUS']
+    if all(isinstance(a, np.ndarray) and a.dtype == np.float64 and a.ndim == 2 and a.flags['C_CONTIGUOUS'] and
+           a.shape[1] == a0.shape[1] for a in l_arr):
+        ptr = a0.ctypes.data
         for a in l_arr:
-            ok = ok and (a.base is base or a is base) and a.ctypes.data == ptr and a.shape[1] == base.shape[1]
+            if a.ctypes.data != ptr:
+                break
             ptr += a.nbytes
-        if ok and a0.ctypes.data >= base.ctypes.data and ptr <= base.ctypes.data + base.nbytes:
-            r0 = (a0.ctypes.data - base.ctypes.data) // (base.shape[1] * 8)
-            return base[r0:r0 + sum(a.shape[0] for a in l_arr)]
+        else:
+            rows = sum(a.shape[0] for a in l_arr)
+            return np.lib.stride_tricks.as_strided(a0, shape=(rows, a0.shape[1]), strides=a0.strides, writeable=False)
     return np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64) for a in l_arr], axis=0))
 
 
@@ -812,7 +814,7 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
     if l_noise is not None:
         noise = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in l_noise]))
     hpf_sos = output_hpf_sos(fs) if b_out_hpf else None
-    out = np.empty(int(out_off[-1]), dtype=np.float64)
+    out = _lib.pinned.empty(int(out_off[-1]))
     _lib.check(_lib.lib().mpb_synthesis_compressed_host(
         plan.handle, _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), mag.shape[0], _lib.ptr(need), _lib.ptr(noise),
         int(sum(l_ns_len)), _lib.ptr(mt_key), C.byref(mt_pos) if mt_pos is not None else None, C.byref(fr), {'magphase': 0, 'linear': 1, 'min_phase': 2}[per_phase_type], _lib.ptr(hpf_sos),
