@@ -34,6 +34,7 @@ extern "C" {
 #define MPB_ERR_CUDA (-4)         /* CUDA runtime failure (message has the cudaError string)        */
 #define MPB_ERR_NO_DEVICE (-5)    /* no usable CUDA device: there is NO CPU fallback                */
 #define MPB_ERR_DIM (-6)          /* mel dimensions exceed the compiled limits                      */
+#define MPB_ERR_INTERNAL (-7)     /* a self-check of the library failed (never expected)            */
 
 /* element types of caller buffers */
 #define MPB_F32 0
@@ -311,6 +312,13 @@ int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* 
                             double low, double high, void* out_dev, int out_dtype);
 int mpb_mt19937_uniform_host(mpb_ctx* ctx, uint32_t* key, int32_t* pos, int64_t n,
                              double low, double high, double* out);
+/*
+ * Long draws are cut into segments generated by different CTAs; a CTA reaches its segment by jump-ahead:
+ * x[m+J] = XOR over the set bits i of (x^J mod phi) of x[m+i], phi = characteristic polynomial of the twister
+ * (derived at run time by Berlekamp-Massey).  This HOST-only call returns x^n_words mod phi (n_words = 0: phi
+ * without its leading term x^19937) as 624 little-endian 32-bit words, so that the tests can check the algebra.
+ */
+int mpb_mt19937_jump_poly(int64_t n_words, uint32_t* out624);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,7 @@ SIGNATURES = {
     'mpb_min_phase_host': [_vp, _vp, _i64, C.c_int, _vp],
     'mpb_mt19937_uniform_dev': [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, _vp, C.c_int],
     'mpb_mt19937_uniform_host': [_vp, _vp, _vp, _i64, C.c_double, C.c_double, _vp],
+    'mpb_mt19937_jump_poly': [_i64, _vp],
     'mpb_sos2_dev': [_vp, _vp, _vp, C.c_int, _vp, _i32, _vp],
     'mpb_sos2_host': [_vp, _vp, _vp, _i32, _vp],
 }

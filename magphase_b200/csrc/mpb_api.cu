@@ -78,6 +78,7 @@ int mpb_destroy(mpb_ctx* ctx) {
     for (auto& kv : ctx->tw32) cudaFree(kv.second);
     for (auto& kv : ctx->tw64) cudaFree(kv.second);
     for (auto& b : ctx->scratch) b.release();
+    ctx->mt_jump.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MPB_OK;
@@ -426,18 +427,39 @@ int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* 
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     DevBuf* b = ctx->scratch;
-    CU(b[9].need(sizeof(uint32_t) * 624 + sizeof(int32_t)));
+    CU(b[9].need(sizeof(uint32_t) * 2 * 625));
     CU(b[10].need(sizeof(uint32_t) * 2 * (size_t)n));
-    uint32_t* d_key = (uint32_t*)b[9].p;
-    int32_t* d_pos = (int32_t*)(d_key + 624);
-    CU(cudaMemcpyAsync(d_key, key, sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_pos, pos, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    const uint16_t* d_jump = nullptr;
+    if (mt19937_needs_jump(*pos, n)) {            // more than one segment: jump polynomials (built once per process)
+        if (!ctx->mt_jump_ready) {
+            size_t n_idx = 0;
+            const uint16_t* h = mt19937_jump_table_host(&n_idx);
+            if (!h) return fail(MPB_ERR_INTERNAL, "MT19937 jump polynomials could not be derived");
+            CU(ctx->mt_jump.need(sizeof(uint16_t) * n_idx));
+            CU(cudaMemcpyAsync(ctx->mt_jump.p, h, sizeof(uint16_t) * n_idx, cudaMemcpyHostToDevice, st));
+            ctx->mt_jump_ready = true;
+        }
+        d_jump = (const uint16_t*)ctx->mt_jump.p;
+    }
+    uint32_t* d_state = (uint32_t*)b[9].p;
+    CU(cudaMemcpyAsync(d_state, key, sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
+    int slot = 0;
     LAUNCH(ctx, st, "k_mt19937_stream+k_mt_to_uniform",
-           launch_mt19937_uniform(d_key, d_pos, (uint32_t*)b[10].p, n, low, high, out_dev, out_dtype, st));
+           launch_mt19937_uniform(d_state, *pos, &slot, d_jump, (uint32_t*)b[10].p, n, low, high, out_dev, out_dtype, st));
     ctx->launches += 1;
-    CU(cudaMemcpyAsync(key, d_key, sizeof(uint32_t) * 624, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(pos, d_pos, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    uint32_t fin[625];
+    CU(cudaMemcpyAsync(fin, d_state + 625 * slot, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    memcpy(key, fin, sizeof(uint32_t) * 624);
+    *pos = (int32_t)fin[624];
+    return MPB_OK;
+}
+
+// x^(n_words) mod phi, phi = characteristic polynomial of the MT19937 transition (n_words = 0: phi minus its leading
+// term), as 624 little-endian 32-bit words.  Host only; exposes the jump-ahead arithmetic to the tests.
+int mpb_mt19937_jump_poly(int64_t n_words, uint32_t* out624) {
+    if (!out624 || n_words < 0) return fail(MPB_ERR_BAD_ARG, "bad argument");
+    if (mt19937_jump_poly(n_words, out624) != 0) return fail(MPB_ERR_INTERNAL, "Berlekamp-Massey did not return degree 19937");
     return MPB_OK;
 }
 

@@ -55,6 +55,8 @@ struct mpb_ctx {
     std::mutex tw_mu;
     int64_t launches = 0;
     DevBuf scratch[16];
+    DevBuf mt_jump;                                // MT19937 jump polynomials (set-bit lists), uploaded on first use
+    bool mt_jump_ready = false;
     KernelTimer timer;
 };
 

@@ -281,8 +281,8 @@ def _synthesis_lossless_call(l_feats, l_pm_int, l_t0, l_nout, fft_len, compute=N
     for u in range(n_utt):
         frm_off[u + 1] = frm_off[u] + l_pm_int[u].size
         out_off[u + 1] = out_off[u] + l_nout[u]
-    cat = lambda i: np.ascontiguousarray(np.concatenate([np.asarray(f[i], dtype=np.float64) for f in l_feats], axis=0))
-    mag, real, imag = cat(0), cat(1), cat(2)
+    # zero-copy when the rows already sit back to back (the blocks analysis_lossless_batch returns live in pinned memory)
+    mag, real, imag = (_stack_rows([f[i] for f in l_feats]) for i in range(3))
     H = fft_len // 2 + 1
     if mag.shape[1] != H or real.shape != mag.shape or imag.shape != mag.shape:
         raise ValueError('feature matrices must be nfrms x %d' % H)

@@ -185,6 +185,32 @@ def test_numpy_legacy_stream_on_device_is_bit_exact(mp):
         assert np.array_equal(got_next, ref_next)
 
 
+def test_numpy_legacy_stream_jump_ahead_segments(mp):
+    """Draws longer than one segment (256 twists = 159,744 words) are generated by several CTAs that JUMP to their
+    segment through x^J mod phi; draws longer than one launch (256 segments) chain launches.  Same numbers, same
+    final state as NumPy, from fresh seeds (arbitrary low bits in key[0]), mid-block positions and pos = 624."""
+    cases = ((7, 0, [79_872, 79_873, 1, 400_001]),           # exactly one segment, then one word more
+             (2024, 5, [3_000_001, 11, 2_500_000]),
+             (99, 0, [20_447_233 + 1000, 17]))                # crosses the 256-segment launch boundary
+    for seed, skip, sizes in cases:
+        np.random.seed(seed)
+        np.random.uniform(size=skip)
+        ref = [np.random.uniform(-1, 1, n) for n in sizes]
+        ref_state = np.random.get_state()
+        np.random.seed(seed)
+        np.random.uniform(size=skip)
+        got = [mp.numpy_stream_uniform(-1, 1, n) for n in sizes]
+        got_state = np.random.get_state()
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b)
+        assert got_state[2] == ref_state[2]
+        # NumPy's own key[0] keeps stale low bits that are not part of the state; compare what matters
+        assert np.array_equal(got_state[1][1:], ref_state[1][1:]) and (got_state[1][0] >> 31) == (ref_state[1][0] >> 31)
+        nxt = np.random.random_sample(700)                   # NumPy continues from the device's state, across a twist
+        np.random.set_state(ref_state)
+        assert np.array_equal(nxt, np.random.random_sample(700))
+
+
 def test_device_hpf_matches_lfilter(mp):
     """The blocked state-space scan against scipy.signal.lfilter (the reference's own call, src/magphase.py:995):
     several utterances of odd lengths in one call.  lfilter's direct form carries ~1e-8 of rounding noise itself."""
