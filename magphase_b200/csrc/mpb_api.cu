@@ -79,6 +79,7 @@ int mpb_destroy(mpb_ctx* ctx) {
     for (auto& kv : ctx->tw64) cudaFree(kv.second);
     for (auto& b : ctx->scratch) b.release();
     ctx->mt_jump.release();
+    ctx->stage.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MPB_OK;
@@ -199,12 +200,14 @@ static int frames_host(mpb_ctx* ctx, const double* sig, int64_t n_sig, const int
     CU(b[5].need(osz));
     if (mode == MODE_FEATS) { CU(b[6].need(osz)); CU(b[7].need(osz)); }
     cudaStream_t st = ctx->stream;
-    CU(cudaMemcpyAsync(b[0].p, sig, sizeof(double) * n_sig, cudaMemcpyHostToDevice, st));
+    int sig_dtype = MPB_F64;
+    rc = upload_signals(ctx, st, &sig, &n_sig, 1, b[0].p, &sig_dtype);
+    if (rc != MPB_OK) return rc;
     CU(cudaMemcpyAsync(b[1].p, centre, sizeof(int64_t) * nfrm, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b[2].p, left, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b[3].p, right, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
     if (win) CU(cudaMemcpyAsync(b[4].p, win, (size_t)nfrm, cudaMemcpyHostToDevice, st));
-    rc = analysis_common(ctx, st, b[0].p, MPB_F64, n_sig, (const int64_t*)b[1].p, (const int32_t*)b[2].p,
+    rc = analysis_common(ctx, st, b[0].p, sig_dtype, n_sig, (const int64_t*)b[1].p, (const int32_t*)b[2].p,
                          (const int32_t*)b[3].p, win ? (const uint8_t*)b[4].p : nullptr, nfrm, fft_len, compute_dtype,
                          b[5].p, b[6].p, b[7].p, MPB_F64, mode);
     if (rc != MPB_OK) return rc;

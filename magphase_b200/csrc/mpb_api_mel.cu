@@ -1,4 +1,6 @@
 // C-ABI: mel-compression plan (format_for_modelling) and the fused host entry point of analysis_compressed.
+#include <chrono>
+
 #include "mpb_ctx.h"
 
 using namespace mpb;
@@ -261,26 +263,33 @@ int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const i
     CU(m->small[5].need(sizeof(int64_t) * nfrm));
     CU(m->small[6].need(sizeof(int32_t) * nfrm));
     CU(m->small[7].need(sizeof(int32_t) * nfrm));
-    {
-        int64_t off = 0;
-        for (int32_t i = 0; i < n_sigs; ++i) {
-            CU(cudaMemcpyAsync((double*)m->small[4].p + off, sigs[i], sizeof(double) * sig_lens[i], cudaMemcpyHostToDevice, st));
-            off += sig_lens[i];
-        }
-    }
+    static const bool trace = getenv("MPB_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return 1e3 * std::chrono::duration<double>(b - a).count();
+    };
+    const auto t0 = now();
+    int sig_dtype = MPB_F64;
+    rc = upload_signals(ctx, st, sigs, sig_lens, n_sigs, m->small[4].p, &sig_dtype);
+    if (rc != MPB_OK) return rc;
+    const auto t1 = now();
     CU(cudaMemcpyAsync(m->small[5].p, centre, sizeof(int64_t) * nfrm, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(m->small[6].p, left, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(m->small[7].p, right, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(m->small[0].p, voi, (size_t)nfrm, cudaMemcpyHostToDevice, st));
     (void)compute_dtype;   // the fused path always runs float64 butterflies
-    rc = mpb_analysis_compressed_dev(m, st, m->small[4].p, MPB_F64, n_sig, (const int64_t*)m->small[5].p,
+    rc = mpb_analysis_compressed_dev(m, st, m->small[4].p, sig_dtype, n_sig, (const int64_t*)m->small[5].p,
                                      (const int32_t*)m->small[6].p, (const int32_t*)m->small[7].p,
                                      (const uint8_t*)m->small[0].p, nfrm, m->small[1].p, m->small[2].p, m->small[3].p, MPB_F64);
     if (rc != MPB_OK) return rc;
     CU(cudaMemcpyAsync(out_mag_mel, m->small[1].p, sizeof(double) * nfrm * m->n_mag, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(out_real_mel, m->small[2].p, sizeof(double) * nfrm * m->phase_dim, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(out_imag_mel, m->small[3].p, sizeof(double) * nfrm * m->phase_dim, cudaMemcpyDeviceToHost, st));
+    const auto t2 = now();
     CU(cudaStreamSynchronize(st));
+    if (trace)
+        fprintf(stderr, "[mpb] analysis_compressed_hostv: upload %.3f ms, enqueue %.3f ms, drain %.3f ms\n", ms(t0, t1),
+                ms(t1, t2), ms(t2, now()));
     return MPB_OK;
 }
 
@@ -324,13 +333,9 @@ int mpb_analysis_compressed_const_hostv(mpb_mel* m, const double* const* sigs, c
     CU(m->small[3].need(sizeof(double) * n_out * m->phase_dim));
     CU(m->small[5].need(sizeof(int32_t) * n_out)); CU(m->small[6].need(sizeof(int32_t) * n_out));
     CU(m->small[7].need(sizeof(float) * n_out));
-    {
-        int64_t off = 0;
-        for (int32_t i = 0; i < n_sigs; ++i) {
-            CU(cudaMemcpyAsync((double*)b[0].p + off, sigs[i], sizeof(double) * sig_lens[i], cudaMemcpyHostToDevice, st));
-            off += sig_lens[i];
-        }
-    }
+    int sig_dtype = MPB_F64;
+    rc = upload_signals(ctx, st, sigs, sig_lens, n_sigs, b[0].p, &sig_dtype);
+    if (rc != MPB_OK) return rc;
     CU(cudaMemcpyAsync(b[1].p, centre, sizeof(int64_t) * nfrm, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b[2].p, left, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b[3].p, right, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
@@ -338,7 +343,7 @@ int mpb_analysis_compressed_const_hostv(mpb_mel* m, const double* const* sigs, c
     CU(cudaMemcpyAsync(m->small[5].p, lerp_r0, sizeof(int32_t) * n_out, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(m->small[6].p, lerp_r1, sizeof(int32_t) * n_out, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(m->small[7].p, lerp_w, sizeof(float) * n_out, cudaMemcpyHostToDevice, st));
-    rc = analysis_common(ctx, st, b[0].p, MPB_F64, n_sig, (const int64_t*)b[1].p, (const int32_t*)b[2].p, (const int32_t*)b[3].p,
+    rc = analysis_common(ctx, st, b[0].p, sig_dtype, n_sig, (const int64_t*)b[1].p, (const int32_t*)b[2].p, (const int32_t*)b[3].p,
                          nullptr, nfrm, m->fft_len, MPB_F64, b[5].p, b[6].p, b[7].p, MPB_F32, MODE_FEATS);
     if (rc != MPB_OK) return rc;
     LerpRows lr{(const int32_t*)m->small[5].p, (const int32_t*)m->small[6].p, (const float*)m->small[7].p};

@@ -1,4 +1,6 @@
 // C-ABI: compressed synthesis plan (synthesis_from_compressed).
+#include <chrono>
+
 #include "mpb_ctx.h"
 
 using namespace mpb;
@@ -145,6 +147,12 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
     if (!noise && !(mt_key && mt_pos)) return fail(MPB_ERR_BAD_ARG, "either noise or an MT19937 state is required");
     const int64_t F = fr->nfrm;
     const int32_t U = fr->n_utt;
+    static const bool trace = getenv("MPB_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return 1e3 * std::chrono::duration<double>(b - a).count();
+    };
+    const auto t0 = now();
     for (int64_t f = 0; f < F; ++f) {
         if (fr->win_a[f] < 0 || fr->win_b[f] < 0 || fr->win_a[f] > s->fft_len / 2 || fr->win_b[f] >= s->fft_len / 2)
             return fail(MPB_ERR_FRAME_GEOM, "anti-ringing window longer than fft_len/2 (f0 too low for this fft_len)");
@@ -174,6 +182,7 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
     CU(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaStream_t st = ctx->stream;
+    const auto t1 = now();
     DevBuf* b = s->host_in;
     int bi = 0;
     auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
@@ -200,6 +209,7 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
         if (rc != MPB_OK) return rc;
         d_noise = dn.p;
     }
+    const auto t2 = now();
     UP(runs.data(), sizeof(int32_t) * 4 * n_runs, d_runs);
     UP(fr->pm, sizeof(int32_t) * F, d.pm);
     UP(fr->ncentre, sizeof(int64_t) * F, d.ncentre);
@@ -216,6 +226,7 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
     UP(fr->utt_out_off, sizeof(int64_t) * (U + 1), d.utt_out_off);
     UP(fr->utt_t0, sizeof(int32_t) * U, d.utt_t0);
 #undef UP
+    const auto t3 = now();
     CU(s->out.need(sizeof(double) * n_out));
     rc = mpb_synthesis_compressed_dev(s, st, d_mag, d_real, d_imag, MPB_F64, n_rows, (const uint8_t*)d_need,
                                       (const float*)d_noise, n_noise, &d, (const int32_t*)d_runs, (int32_t)n_runs,
@@ -226,7 +237,11 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
         if (rc != MPB_OK) return rc;
     }
     CU(cudaMemcpyAsync(out, s->out.p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
+    const auto t4 = now();
     CU(cudaStreamSynchronize(st));   // also keeps noise32 / runs alive until the copies are done
+    if (trace)
+        fprintf(stderr, "[mpb] synthesis_compressed_host: checks+runs %.3f ms, features+noise %.3f ms, descriptors %.3f ms, "
+                        "enqueue %.3f ms, drain %.3f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
     return MPB_OK;
 }
 

@@ -35,6 +35,20 @@ struct DevBuf {   // grow-only device scratch
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct PinnedBuf {   // grow-only page-locked host staging buffer
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t need(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, n, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct KernelTimer {   // optional per-kernel CUDA-event timing (mpb_profile_begin / mpb_profile_end)
     struct Rec { const char* name; cudaEvent_t a, b; };
     bool on = false;
@@ -57,6 +71,7 @@ struct mpb_ctx {
     DevBuf scratch[16];
     DevBuf mt_jump;                                // MT19937 jump polynomials (set-bit lists), uploaded on first use
     bool mt_jump_ready = false;
+    PinnedBuf stage;                               // float32 staging of host signals (upload_signals)
     KernelTimer timer;
 };
 
@@ -78,6 +93,11 @@ int analysis_common(mpb_ctx* ctx, void* stream, const void* sig, int sig_dtype, 
                     const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* win,
                     int64_t nfrm, int fft_len, int compute_dtype, void* out_a, void* out_b, void* out_c,
                     int out_dtype, int mode);
+// HOST float64 signals sigs[0] | sigs[1] | ... -> dev (>= 8 bytes per sample) on st; *out_dtype = MPB_F32 when the
+// samples could be narrowed exactly on the host (mpb_stage.cu), else MPB_F64.  Caller synchronises st before returning.
+int upload_signals(mpb_ctx* ctx, cudaStream_t st, const double* const* sigs, const int64_t* lens, int32_t n_sigs,
+                   void* dev, int* out_dtype);
+int host_threads();
 int check_frames_host(const int64_t* centre, const int32_t* left, const int32_t* right, int64_t nfrm,
                       int64_t n_sig, int fft_len);
 }

@@ -1,0 +1,78 @@
+"""The vectorised batch bookkeeping (one pass of NumPy calls per batch) against the per-utterance definitions that
+mirror the reference line by line.  Integer arrays must be identical, float arrays bit-identical.  No GPU needed."""
+import numpy as np
+import pytest
+
+import magphase_b200.magphase as mp
+from magphase_b200.synth import synth_utterance
+
+
+def _utts():
+    out = [synth_utterance(u, fs=48000, dur_s=d) for u, d in ((0, 0.7), (1, 1.3), (2, 0.4), (3, 2.0))]
+    sig, pm, voi = synth_utterance(4, fs=48000, dur_s=0.5)
+    out.append((sig, pm[:1], voi[:1]))                       # a single pitch mark
+    return out
+
+
+def test_batch_frame_geometry_equals_per_utterance():
+    utts = _utts()
+    pm, left, right, off = mp.batch_frame_geometry([u[1] for u in utts], [u[0].size for u in utts])
+    for k, (sig, p, _) in enumerate(utts):
+        P, v_shift, v_rights = mp.frame_geometry(p, sig.size)
+        a, b = off[k], off[k + 1]
+        assert np.array_equal(pm[a:b], P[1:-1])
+        assert np.array_equal(left[a:b], v_shift)
+        assert np.array_equal(right[a:b], v_rights)
+
+
+def test_medfilt3_segments_equals_scipy_per_utterance():
+    from scipy import signal
+    rng = np.random.default_rng(0)
+    segs = [rng.uniform(0, 300, n) * (rng.uniform(size=n) > 0.3) for n in (1, 2, 3, 50, 7)]
+    off = np.concatenate(([0], np.cumsum([s.size for s in segs])))
+    got = mp._medfilt3_segments(np.concatenate(segs), off)
+    ref = np.concatenate([signal.medfilt(s) for s in segs])
+    assert np.array_equal(got, ref)
+    assert np.array_equal(ref, np.concatenate([mp.medfilt3(s) for s in segs]))
+
+
+@pytest.mark.parametrize('b_voi_ap_win', [True, False])
+def test_flat_synthesis_geometry_equals_loop(b_voi_ap_win):
+    rng = np.random.default_rng(3)
+    l_lf0 = []
+    for n in (2, 3, 40, 333, 5):
+        f0 = rng.uniform(60, 380, n)
+        f0[rng.uniform(size=n) < 0.4] = 0.0
+        with np.errstate(divide='ignore'):
+            lf0 = np.log(f0)
+        lf0[np.isinf(lf0)] = -1e10
+        l_lf0.append(lf0)
+    l_lf0.append(np.full(6, -1e10))                           # all unvoiced
+    l_lf0.append(np.log(np.full(4, 48000.0 / 2047.4)))        # longest pitch period that still fits fft_len / 2
+    rows = [v.size for v in l_lf0]
+    for fs, fft_len in ((48000, 4096), (16000, 2048)):
+        if fs == 16000:
+            lf0s = [np.where(v > 0, v + np.log(1.2), v) for v in l_lf0[:-1]]
+        else:
+            lf0s = l_lf0
+        r = [v.size for v in lf0s]
+        a_flat, ns_flat = mp._compressed_synthesis_geometry_flat(lf0s, r, fs, fft_len, b_voi_ap_win)
+        a_loop, ns_loop = mp._compressed_synthesis_geometry_loop(lf0s, r, fs, fft_len, b_voi_ap_win, False)
+        assert ns_flat == ns_loop
+        assert set(a_flat) == set(a_loop)
+        for k in a_loop:
+            if a_loop[k] is None:
+                assert a_flat[k] is None
+            else:
+                assert a_flat[k].dtype == a_loop[k].dtype, k
+                assert np.array_equal(a_flat[k], a_loop[k]), k
+
+
+def test_flat_synthesis_geometry_errors():
+    ok = np.log(np.full(5, 100.0))
+    with pytest.raises(IndexError):
+        mp.compressed_synthesis_geometry([ok, ok[:1]], [5, 1], 48000, 4096)
+    with pytest.raises(ValueError):
+        mp.compressed_synthesis_geometry([ok], [4], 48000, 4096)
+    with pytest.raises(ValueError):                            # pitch period longer than fft_len / 2
+        mp.compressed_synthesis_geometry([np.log(np.full(5, 20.0))], [5], 48000, 4096)
