@@ -78,6 +78,9 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
                     __stcs(&ob[kk], (TO)__logf(__expf(2.0f * re) + 1.0e-8f));
                     __stcs(&oc[kk], (TO)__logf(__expf(2.0f * im) + 1.0e-8f));
                 } else if (MODE == MODE_LOGSQ) {
+                    // noise frames: the spectrum itself goes to HBM for k_synthesis_compressed (rows pitched to M + 2)
+                    if (sizeof(T) == 4 && out_b)
+                        reinterpret_cast<float2*>(out_b)[f * (int64_t)(M + 2) + kk] = make_float2((float)x.x, (float)x.y);
                     if (kk != 0 && kk != M) {
                         const T p = x.x * x.x + x.y * x.y;
                         if (sizeof(T) == 4 && p > (T)0) {      // float32 noise frames: fast log, ~17 terms per thread in float

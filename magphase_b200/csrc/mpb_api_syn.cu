@@ -18,7 +18,7 @@ struct mpb_syn {
     float* u_mag = nullptr;   // [n_mag][HP]   (rows pitched to 16 bytes, zero padded)
     float* u_ph = nullptr;    // [n_ph][HBP]
     float* tab = nullptr;     // [3][H]
-    DevBuf unw[3], logsq, gain, host_in[20], out;
+    DevBuf unw[3], logsq, nspec, gain, host_in[20], out;
     std::mutex mu;
 };
 
@@ -60,7 +60,7 @@ int mpb_syn_destroy(mpb_syn* s) {
     cudaFree(s->u_mag); cudaFree(s->u_ph); cudaFree(s->tab);
     for (auto& b : s->unw) b.release();
     for (auto& b : s->host_in) b.release();
-    s->logsq.release(); s->gain.release(); s->out.release();
+    s->logsq.release(); s->nspec.release(); s->gain.release(); s->out.release();
     delete s;
     return MPB_OK;
 }
@@ -91,6 +91,7 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
     CU(s->unw[1].need(sizeof(float) * (size_t)n_rows * HBP));
     CU(s->unw[2].need(sizeof(float) * (size_t)n_rows * HBP));
     CU(s->logsq.need(sizeof(double) * (size_t)fr->nfrm));
+    CU(s->nspec.need(sizeof(float2) * (size_t)fr->nfrm * (s->fft_len / 2 + 2)));
     CU(s->gain.need(sizeof(double) * 2 * (size_t)fr->n_utt));
 
     UnwarpArgs u;
@@ -108,13 +109,13 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
     n.sig = noise; n.sig_dtype = MPB_F32; n.n_sig = n_noise;
     n.centre = fr->ncentre; n.left = fr->nleft; n.right = fr->nright; n.win = fr->nkind;
     n.nfrm = fr->nfrm; n.fft_len = s->fft_len; n.compute_dtype = MPB_F32; n.tw = tw;
-    n.out_a = s->logsq.p; n.out_b = nullptr; n.out_c = nullptr; n.out_dtype = MPB_F64; n.mode = MODE_LOGSQ;
+    n.out_a = s->logsq.p; n.out_b = s->nspec.p; n.out_c = nullptr; n.out_dtype = MPB_F64; n.mode = MODE_LOGSQ;
     n.num_sms = ctx->num_sms;
     LAUNCH(ctx, st, "k_analysis<noise_logsq>", launch_noise_stats(n, st));
 
     SynthCompArgs a;
     a.m_mag = u.out_mag; a.m_real = u.out_real; a.m_imag = u.out_imag; a.H = s->H; a.HB = s->HB; a.HP = HP; a.HBP = HBP;
-    a.noise = noise; a.n_noise = n_noise;
+    a.noise = noise; a.n_noise = n_noise; a.nspec = (const float2*)s->nspec.p;
     a.pm = fr->pm; a.ncentre = fr->ncentre; a.nleft = fr->nleft; a.nright = fr->nright;
     a.voi = fr->voi; a.nkind = fr->nkind; a.win_a = fr->win_a; a.win_b = fr->win_b;
     a.row0 = fr->row0; a.row1 = fr->row1; a.roww = fr->roww;

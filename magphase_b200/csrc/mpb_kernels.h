@@ -20,7 +20,7 @@ struct AnalysisArgs {
     int num_sms;
 };
 cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st);
-cudaError_t launch_noise_stats(const AnalysisArgs& a, cudaStream_t st);   // out_a: double[nfrm]
+cudaError_t launch_noise_stats(const AnalysisArgs& a, cudaStream_t st);   // out_a: double[nfrm]; out_b: float2[nfrm][fft_len/2+2] spectra or NULL
 cudaError_t launch_analysis_logp(const AnalysisArgs& a, cudaStream_t st);  // float64 compute, float32 log periodograms
 
 // One OLA run = consecutive frames of one utterance handled by one CTA (see mpb_synthesis.cu).
@@ -79,6 +79,7 @@ cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st);
 struct SynthCompArgs {
     const float* m_mag; const float* m_real; const float* m_imag; int H; int HB; int HP; int HBP;
     const float* noise; int64_t n_noise;
+    const float2* nspec;                                                            // [nfrm][fft_len/2 + 2] noise spectra (k_analysis<noise_logsq>)
     const int32_t* pm; const int64_t* ncentre; const int32_t* nleft; const int32_t* nright;
     const uint8_t* voi; const uint8_t* nkind; const int32_t* win_a; const int32_t* win_b;
     const int32_t* row0; const int32_t* row1; const float* roww;                    // row1/roww NULL: no interpolation

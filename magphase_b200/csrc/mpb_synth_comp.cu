@@ -3,6 +3,7 @@
 // Reference: synthesis_from_compressed src/magphase.py:825-997.  Per frame (one CTA walks an OLA run):
 //   1. noise frame: windowing() with per-voicing window (:886-892), frm_list_to_matrix + fftshift (:895-896,
 //      src/libaudio.py:122-140) == the analysis buffer layout -> forward real FFT
+//      (done by k_analysis<noise_logsq> together with the gain statistics; the spectrum is read back here)
 //   2. aperiodic = noise_spec / gain(voicing class) * mag [* unvoiced tilt]                    (:905-918)
 //      periodic  = mag * (real + j imag)/|.| * voiced tilt                                      (:922-941)
 //      mix with sqrt(mask), sqrt(1 - mask); DC and Nyquist become |.|                           (:944-961)
@@ -10,8 +11,8 @@
 //   3. Hermitian inverse FFT, fftshift (index math), anti-ringing window (:968-973, la.gen_centr_win
 //      src/libaudio.py:90-103), ola() (:976, :34-62)
 // The noise gains need the mean of (log|N|)^2 over ALL voiced / unvoiced frames of the utterance (:902-903):
-// k_analysis<MODE_LOGSQ> produces per-frame sums, k_noise_gain reduces them per utterance, and this kernel
-// recomputes the noise FFT instead of storing the noise spectra (16 KB/frame of HBM traffic saved).
+// k_analysis<MODE_LOGSQ> produces per-frame sums AND stores the float32 noise spectra (16 KB/frame; HBM has the
+// headroom, the issue slots a second noise FFT would take here do not), k_noise_gain reduces the sums per utterance.
 #include "mpb_frame.cuh"
 
 namespace mpb {
@@ -52,15 +53,52 @@ __device__ __forceinline__ float lerp_row(const float* r0, const float* r1, floa
     return r1 ? fmaf(w, r1[k] - a, a) : a;
 }
 
-// asynchronous 16-byte global -> shared copies (the un-warped scratch rows are pitched to 16 bytes)
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(gmem_src));
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
+// Per-frame scalars, read one frame ahead so that their global-load latency hides under the previous frame's IFFT.
+struct FrameDesc {
+    int p, A, B, row0, row1;
+    float rw;
+    bool voiced;
+};
+__device__ __forceinline__ FrameDesc load_desc(const SynthCompArgs& a, int64_t g) {
+    FrameDesc d;
+    d.p = a.pm[g]; d.A = a.win_a[g]; d.B = a.win_b[g]; d.row0 = a.row0[g];
+    d.row1 = a.row1 ? a.row1[g] : 0;
+    d.rw = a.roww ? a.roww[g] : 0.0f;
+    d.voiced = a.voi[g] != 0;
+    return d;
+}
+
+// One CTA walks an OLA run.  Everything a frame reads from HBM -- its noise spectrum (k_analysis<noise_spec>), its
+// un-warped magnitude row and, for voiced frames, the two phase rows -- is staged into shared memory by TMA bulk copies
+// issued by one thread as soon as the previous frame's mix has consumed the staging area, i.e. the copies run under
+// the previous frame's inverse FFT and overlap-add.
 template <typename TO, int N>
-__global__ void __launch_bounds__(FftGeom<float, N>::TPB, 512 / FftGeom<float, N>::TPB)
+__global__ void __launch_bounds__(FftGeom<float, N>::TPB, 384 / FftGeom<float, N>::TPB)
 k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
     using T = float;
     using G = FftGeom<T, N>;
@@ -68,26 +106,49 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
     constexpr int M = G::M, TPB = G::TPB, HALF = N / 2;
     constexpr int NJ = (M / 2) / TPB;
     constexpr int STEP = TPB + TPB / 16;
+    constexpr int SP = M + 2;                                  // float2 pitch of a stored noise spectrum (16-byte rows)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T2* buf = reinterpret_cast<T2*>(smem_raw);
     T* acc = reinterpret_cast<T*>(buf + G::BUF_ELEMS);
-    T2* tw2f = reinterpret_cast<T2*>(acc + N);
-    T2* tw2i = tw2f + G::TW2_ELEMS;
-    // feature rows of the current frame, prefetched with cp.async while the noise FFT runs
+    T2* tw2i = reinterpret_cast<T2*>(acc + N);
     const int H = a.H, HB = a.HB, HP = a.HP, HBP = a.HBP;
     const int rowlen = HP + 2 * HBP;
-    float* srow0 = reinterpret_cast<float*>(tw2i + G::TW2_ELEMS);      // [mag HP | real HBP | imag HBP]
+    T2* sspec = tw2i + G::TW2_ELEMS;                                   // [SP] noise spectrum of the current frame
+    float* srow0 = reinterpret_cast<float*>(sspec + SP);               // [mag HP | real HBP | imag HBP]
     float* srow1 = a.row1 ? srow0 + rowlen : nullptr;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(srow0 + rowlen * (a.row1 ? 2 : 1));
     const int t = threadIdx.x;
     const T scale = (T)1 / (T)N;
-    FftCtx<T> ff, fi;
-    fft_setup<T, N, false>(ff, tw2f, (const T2*)a.tw, t);
-    fft_setup<T, N, true>(fi, tw2i, (const T2*)a.tw, t);
+    FftCtx<T> fi;
+    if (t == 0) { mbar_init(mbar, 1); fence_proxy_async(); }
+    fft_setup<T, N, true>(fi, tw2i, (const T2*)a.tw, t);               // (ends with a barrier: mbarrier is initialised)
     T2* pk = buf + G::nphys(t);
     T2* pmk = buf + G::nphys(M - t);
     const float* __restrict__ tabP = a.tab;
     const float* __restrict__ tabAv = a.tab + H;
     const float* __restrict__ tabAu = a.tab + 2 * H;
+    uint32_t phase = 0;
+
+    // stage frame g (descriptor d): one thread, all copies complete on mbar
+    auto stage = [&](int64_t g, const FrameDesc& d) {
+        const bool ph = d.voiced && !a.per_linear;
+        const uint32_t b_spec = (uint32_t)(SP * sizeof(T2)), b_mag = (uint32_t)(HP * 4), b_ph = (uint32_t)(HBP * 4);
+        const uint32_t per_row = b_mag + (ph ? 2 * b_ph : 0);
+        mbar_expect_tx(mbar, b_spec + per_row * (srow1 ? 2 : 1));
+        tma_load_1d(sspec, a.nspec + g * (int64_t)SP, b_spec, mbar);
+        tma_load_1d(srow0, a.m_mag + (int64_t)d.row0 * HP, b_mag, mbar);
+        if (ph) {
+            tma_load_1d(srow0 + HP, a.m_real + (int64_t)d.row0 * HBP, b_ph, mbar);
+            tma_load_1d(srow0 + HP + HBP, a.m_imag + (int64_t)d.row0 * HBP, b_ph, mbar);
+        }
+        if (srow1) {
+            tma_load_1d(srow1, a.m_mag + (int64_t)d.row1 * HP, b_mag, mbar);
+            if (ph) {
+                tma_load_1d(srow1 + HP, a.m_real + (int64_t)d.row1 * HBP, b_ph, mbar);
+                tma_load_1d(srow1 + HP + HBP, a.m_imag + (int64_t)d.row1 * HBP, b_ph, mbar);
+            }
+        }
+    };
 
     for (int r = blockIdx.x; r < a.n_runs; r += gridDim.x) {
         const OlaRun run = a.runs[r];
@@ -98,68 +159,41 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
         const int own_hi = (run.flags & 2) ? a.pm[run.first + run.count] - HALF : INT32_MAX;
         const float giv = (float)a.inv_gain[2 * run.utt + 0], giu = (float)a.inv_gain[2 * run.utt + 1];
 
+        FrameDesc dn = load_desc(a, run.first);
+        if (t == 0) { fence_proxy_async(); stage(run.first, dn); }     // (the previous run ended with a barrier)
         for (int n = t; n < N; n += TPB) acc[n] = (T)0;
         __syncthreads();
 
         for (int fr = 0; fr < run.count; ++fr) {
             const int64_t g = (int64_t)run.first + fr;
-            const int p = a.pm[g];
-            const bool voiced = a.voi[g] != 0;
+            const FrameDesc d = dn;
+            const bool more = fr + 1 < run.count;
+            if (more) dn = load_desc(a, g + 1);
+            const int p = d.p;
+            const bool voiced = d.voiced;
 
-            // ---- 0. kick off the asynchronous copy of this frame's un-warped feature rows ----
-            {
-                const bool ph = voiced && !a.per_linear;
-                const float* g0 = a.m_mag + (int64_t)a.row0[g] * HP;
-                for (int k = 4 * t; k < HP; k += 4 * TPB) cp_async16(srow0 + k, g0 + k);
-                if (ph) {
-                    const float* gr = a.m_real + (int64_t)a.row0[g] * HBP;
-                    const float* gi2 = a.m_imag + (int64_t)a.row0[g] * HBP;
-                    for (int k = 4 * t; k < HBP; k += 4 * TPB) { cp_async16(srow0 + HP + k, gr + k); cp_async16(srow0 + HP + HBP + k, gi2 + k); }
-                }
-                if (srow1) {
-                    const float* g1 = a.m_mag + (int64_t)a.row1[g] * HP;
-                    for (int k = 4 * t; k < HP; k += 4 * TPB) cp_async16(srow1 + k, g1 + k);
-                    if (ph) {
-                        const float* gr = a.m_real + (int64_t)a.row1[g] * HBP;
-                        const float* gi2 = a.m_imag + (int64_t)a.row1[g] * HBP;
-                        for (int k = 4 * t; k < HBP; k += 4 * TPB) { cp_async16(srow1 + HP + k, gr + k); cp_async16(srow1 + HP + HBP + k, gi2 + k); }
-                    }
-                }
-            }
-
-            // ---- 1. noise frame -> spectrum (natural padded layout in buf) ----
-            T2 v[16];
-            load_frame<T, float, N>(a.noise, a.n_noise, a.ncentre[g], a.nleft[g], a.nright[g], (int)a.nkind[g], buf, v, t);
-            fft_m<T, N, false>(v, buf, ff, t);
+            // ---- 1. wait for this frame's noise spectrum and feature rows ----
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
 
             // ---- 2. mix periodic + aperiodic per bin pair (k, M-k), pack for the inverse transform ----
-            cp_async_wait_all();
-            __syncthreads();                                   // feature rows have landed for every thread
             const float* mag0 = srow0;
             const float* mag1 = srow1;
             const float* re0 = srow0 + HP;
             const float* re1 = srow1 ? srow1 + HP : nullptr;
             const float* im0 = srow0 + HP + HBP;
             const float* im1 = srow1 ? srow1 + HP + HBP : nullptr;
-            const float rw = a.roww ? a.roww[g] : 0.0f;
+            const float rw = d.rw;
             const float gi = voiced ? giv : giu;
             const float* __restrict__ tabA = voiced ? tabAv : tabAu;
-            T2 znk[NJ + 1], znm[NJ + 1];
-            T2 wf = ff.wp, wi = fi.wp;
+            T2 wi = fi.wp;
 #pragma unroll
             for (int j = 0; j <= NJ; ++j) {
                 const int k = t + j * TPB;
                 if (j == NJ && t != 0) break;                  // k == M/2: thread 0 only
-                const T2 zk = pk[j * STEP];
-                const T2 zm = cconj(k == 0 ? buf[0] : pmk[-j * STEP]);
-                const T2 e = mk<T>(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
-                const T2 d = mk<T>(0.5f * (zk.x - zm.x), 0.5f * (zk.y - zm.y));
-                const T2 wo = cmul(mk<T>(d.y, -d.x), wf);
-                wf = cmul(wf, ff.wstep);
-                T2 n1 = cadd(e, wo);                           // noise spectrum N[k]
-                T2 n2 = cconj(csub(e, wo));                    // N[M-k]
-                if (k == 0) { n1.y = 0.0f; n2.y = 0.0f; }
                 const int km = M - k;
+                T2 n1 = sspec[k];                              // noise spectrum N[k], N[M-k]
+                T2 n2 = sspec[km];
                 const float magk = lerp_row(mag0, mag1, rw, k), magm = lerp_row(mag0, mag1, rw, km);
                 const float sk = gi * magk * __ldg(tabA + k), sm = gi * magm * __ldg(tabA + km);
                 T2 xk = mk<T>(n1.x * sk, n1.y * sk);
@@ -180,45 +214,38 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
                     xm = mk<T>(hypotf(xm.x, xm.y), 0.0f);
                 }
                 if (j == NJ) {                                 // k == M/2 pairs with itself: Z = 2 conj(X)
-                    znk[j] = mk<T>(2.0f * xk.x, -2.0f * xk.y);
-                    znm[j] = znk[j];
+                    pk[j * STEP] = mk<T>(2.0f * xk.x, -2.0f * xk.y);
                 } else {
                     xm.y = -xm.y;                              // conj(X[M-k])
                     const T2 e2 = cadd(xk, xm);
                     const T2 o2 = cmul(csub(xk, xm), wi);
                     wi = cmul(wi, fi.wstep);
-                    znk[j] = mk<T>(e2.x - o2.y, e2.y + o2.x);
-                    znm[j] = mk<T>(e2.x + o2.y, -e2.y + o2.x);
+                    pk[j * STEP] = mk<T>(e2.x - o2.y, e2.y + o2.x);
+                    if (k != 0) pmk[-j * STEP] = mk<T>(e2.x + o2.y, -e2.y + o2.x);
                 }
             }
-            __syncthreads();                                   // every thread is done reading the noise spectrum
-#pragma unroll
-            for (int j = 0; j <= NJ; ++j) {
-                const int k = t + j * TPB;
-                if (j == NJ && t != 0) break;
-                pk[j * STEP] = znk[j];
-                if (k != 0 && j != NJ) pmk[-j * STEP] = znm[j];
-            }
-            __syncthreads();
+            __syncthreads();                                   // Z complete; every thread is done with the staging area
+            if (t == 0 && more) { fence_proxy_async(); stage(g + 1, dn); }
+            T2 v[16];
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) v[n1] = pk[n1 * (G::S1 + G::S1 / 16)];
             __syncthreads();
             fft_m<T, N, true>(v, buf, fi, t);
 
             // ---- 3. anti-ringing window + overlap-add: sample d in [-A, B] around the pitch mark ----
-            const int A = a.win_a[g], B = a.win_b[g];
+            const int A = d.A, B = d.B;
             const T* bufT = reinterpret_cast<const T*>(buf);
             const float ia = A > 0 ? 1.0f / (float)A : 0.0f, ib = B > 0 ? 1.0f / (float)B : 0.0f;
-            for (int d = -A + t; d <= B; d += TPB) {
-                const int n = d & (N - 1);
-                const float w = d == 0 ? 1.0f : 0.5f + 0.5f * cospif(d < 0 ? (float)(-d) * ia : (float)d * ib);
-                acc[(p + d) & (N - 1)] += bufT[2 * G::nphys(n >> 1) + (n & 1)] * scale * w;
+            for (int dd = -A + t; dd <= B; dd += TPB) {
+                const int n = dd & (N - 1);
+                const float w = dd == 0 ? 1.0f : 0.5f + 0.5f * cospif(dd < 0 ? (float)(-dd) * ia : (float)dd * ib);
+                acc[(p + dd) & (N - 1)] += bufT[2 * G::nphys(n >> 1) + (n & 1)] * scale * w;
             }
             __syncthreads();
 
             const int lo = p - HALF;
             int hi = p + HALF;
-            if (fr + 1 < run.count) { const int nx = a.pm[g + 1] - HALF; hi = nx < hi ? nx : hi; }
+            if (more) { const int nx = dn.p - HALF; hi = nx < hi ? nx : hi; }
             ola_flush<T, TO, N, TPB>(acc, lo, hi, own_lo, own_hi, t0, out_len, out + out_off, t);
         }
         __syncthreads();
@@ -228,8 +255,8 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
 template <typename TO, int N>
 static cudaError_t launch_sc_t(const SynthCompArgs& a, cudaStream_t st) {
     using G = FftGeom<float, N>;
-    const size_t smem = sizeof(float2) * (G::BUF_ELEMS + 2 * G::TW2_ELEMS) + sizeof(float) * N +
-                        sizeof(float) * (size_t)(a.HP + 2 * a.HBP) * (a.row1 ? 2 : 1);
+    const size_t smem = sizeof(float2) * (G::BUF_ELEMS + G::TW2_ELEMS + G::M + 2) + sizeof(float) * N +
+                        sizeof(float) * (size_t)(a.HP + 2 * a.HBP) * (a.row1 ? 2 : 1) + 16;
     auto kern = k_synthesis_compressed<TO, N>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
