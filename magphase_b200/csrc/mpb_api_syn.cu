@@ -18,7 +18,7 @@ struct mpb_syn {
     float* u_mag = nullptr;   // [n_mag][HP]   (rows pitched to 16 bytes, zero padded)
     float* u_ph = nullptr;    // [n_ph][HBP]
     float* tab = nullptr;     // [3][H]
-    DevBuf unw[3], logsq, nspec, gain, host_in[20], out;
+    DevBuf unw[3], unw_flags, unw_cvt, logsq, nspec, gain, host_in[20], out;
     std::mutex mu;
 };
 
@@ -60,7 +60,7 @@ int mpb_syn_destroy(mpb_syn* s) {
     cudaFree(s->u_mag); cudaFree(s->u_ph); cudaFree(s->tab);
     for (auto& b : s->unw) b.release();
     for (auto& b : s->host_in) b.release();
-    s->logsq.release(); s->nspec.release(); s->gain.release(); s->out.release();
+    s->unw_flags.release(); s->unw_cvt.release(); s->logsq.release(); s->nspec.release(); s->gain.release(); s->out.release();
     delete s;
     return MPB_OK;
 }
@@ -85,6 +85,8 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
         !fr->nright || !fr->voi || !fr->nkind || !fr->win_a || !fr->win_b || !fr->row0 || !fr->utt_frm_off ||
         !fr->utt_out_off || !fr->utt_t0)
         return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    if (in_dtype == MPB_F32 && (((uintptr_t)mag_mel | (uintptr_t)real_mel | (uintptr_t)imag_mel) & 15))
+        return fail(MPB_ERR_BAD_ARG, "float32 feature matrices must be 16-byte aligned (they are fetched by TMA bulk copies)");
     std::lock_guard<std::mutex> lk(s->mu);
     const int HP = (s->H + 3) & ~3, HBP = (s->HB + 3) & ~3;      // scratch row pitches: 16-byte aligned rows
     CU(s->unw[0].need(sizeof(float) * (size_t)n_rows * HP));
@@ -99,7 +101,16 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
     u.need_ph = need_ph; u.nfrm = n_rows; u.n_mag = s->n_mag; u.n_ph = s->n_ph;
     u.u_mag = s->u_mag; u.H = s->H; u.u_ph = s->u_ph; u.HB = s->HB;
     u.out_mag = (float*)s->unw[0].p; u.out_real = (float*)s->unw[1].p; u.out_imag = (float*)s->unw[2].p;
-    u.HP = HP; u.HBP = HBP;
+    u.HP = HP; u.HBP = HBP; u.num_sms = ctx->num_sms;
+    CU(s->unw_flags.need((size_t)(n_rows + 63) / 64 + 1));
+    u.flags = (uint8_t*)s->unw_flags.p;
+    u.cvt = nullptr; u.cvt_pitch = 0;
+    if (in_dtype == MPB_F64) {
+        const size_t widest = (size_t)(s->n_mag > s->n_ph ? s->n_mag : s->n_ph);
+        u.cvt_pitch = ((size_t)n_rows * widest + 63) & ~(size_t)63;       // keeps every matrix 256-byte aligned
+        CU(s->unw_cvt.need(sizeof(float) * 3 * u.cvt_pitch));
+        u.cvt = (float*)s->unw_cvt.p;
+    }
     LAUNCH(ctx, st, "k_mel_unwarp", launch_mel_unwarp(u, st));
 
     const void* tw = nullptr;

@@ -73,6 +73,9 @@ struct UnwarpArgs {
     const float* u_mag; int H; const float* u_ph; int HB;                           // [n_mag][HP], [n_ph][HBP] (zero padded)
     float* out_mag; float* out_real; float* out_imag;                               // [nfrm][HP], [nfrm][HBP] x2
     int HP; int HBP;                                                                // row pitches (multiples of 4 floats)
+    uint8_t* flags;                                                                 // scratch: ceil(nfrm / 64) bytes
+    float* cvt; size_t cvt_pitch;                                                   // in_dtype F64: 3 x cvt_pitch floats of scratch
+    int num_sms;
 };
 cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st);
 

@@ -67,35 +67,33 @@ __global__ void __launch_bounds__(1024)
 k_voiced_compact(const uint8_t* __restrict__ voi, int n, int32_t* __restrict__ vidx, int32_t* __restrict__ cidx,
                  int32_t* __restrict__ count) {
     __shared__ int warp_sums[32];
-    __shared__ int carry;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (t == 0) carry = 0;
+    // warp w owns the contiguous frames [w*seg, (w+1)*seg), seg a multiple of 32: coalesced byte loads + ballots
+    const int seg = ((n + 1023) / 1024) * 32;
+    const int a = w * seg, b = min(n, a + seg);
+    int cnt = 0;
+#pragma unroll 4
+    for (int f = a + lane; f < a + seg; f += 32) cnt += __popc(__ballot_sync(0xffffffffu, f < b && voi[f] != 0));
+    if (lane == 0) warp_sums[w] = cnt;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int f = base + t;
-        const int v = (f < n && voi[f] != 0) ? 1 : 0;
-        int x = v;
+    if (w == 0) {
+        int s = warp_sums[lane];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) warp_sums[w] = x;
-        __syncthreads();
-        if (w == 0) {
-            int s = warp_sums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
-            warp_sums[lane] = s;
-        }
-        __syncthreads();
-        const int rank = carry + (w ? warp_sums[w - 1] : 0) + x - v;      // exclusive rank of this frame
-        if (f < n) {
-            cidx[f] = v ? rank : -1;
-            if (v) vidx[rank] = f;
-        }
-        __syncthreads();
-        if (t == 1023) carry = rank + v;
-        __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+        warp_sums[lane] = s;
     }
-    if (t == 0) *count = carry;
+    __syncthreads();
+    int rank = w ? warp_sums[w - 1] : 0;                                  // voiced frames before this warp's segment
+#pragma unroll 4
+    for (int f = a + lane; f < a + seg; f += 32) {
+        const bool v = f < b && voi[f] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, v);
+        const int r = rank + __popc(m & ((1u << lane) - 1u));
+        if (f < b) cidx[f] = v ? r : -1;
+        if (v) vidx[r] = f;
+        rank += __popc(m);
+    }
+    if (t == 1023) *count = warp_sums[31];
 }
 
 cudaError_t launch_voiced_compact(const uint8_t* voi, int n, int32_t* vidx, int32_t* cidx, int32_t* count, cudaStream_t st) {
@@ -287,9 +285,17 @@ k_mel_finish(const float* __restrict__ partial, int n_slices, int ncp_max, int64
     }
     const float last = PRE ? xl : log_periodogram(xl, stream == 0);       // Nyquist bin, not covered by the K slices
     const float* __restrict__ pp = partial + ((size_t)stream * (size_t)nfrm + (size_t)row) * n_slices * ncp_max;
+    // all K-slice partials of a coefficient are fetched before the first add (up to 16 independent loads in flight per
+    // lane: this kernel is pure DRAM latency); the sum itself runs in slice order, so it is reproducible
+    constexpr int MAX_SLICES = 4096 / 2 / MEL_KSLICE;
     for (int j = lane; j < n_in; j += 32) {
-        double s = (double)last * (double)wt[(size_t)(H - 1) * ld + j];
-        for (int sl = 0; sl < n_slices; ++sl) s += (double)pp[sl * ncp_max + j];
+        float v[MAX_SLICES];
+#pragma unroll
+        for (int sl = 0; sl < MAX_SLICES; ++sl) v[sl] = sl < n_slices ? __ldcs(pp + sl * ncp_max + j) : 0.0f;
+        double s = (double)last * (double)__ldg(wt + (size_t)(H - 1) * ld + j);
+#pragma unroll
+        for (int sl = 0; sl < MAX_SLICES; ++sl)
+            if (sl < n_slices) s += (double)v[sl];
         mc[warp][j] = (double)(float)s;                                    // SPTK writes float32 (src/libaudio.py:593)
     }
     __syncwarp();

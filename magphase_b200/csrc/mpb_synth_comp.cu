@@ -14,6 +14,7 @@
 // k_analysis<MODE_LOGSQ> produces per-frame sums AND stores the float32 noise spectra (16 KB/frame; HBM has the
 // headroom, the issue slots a second noise FFT would take here do not), k_noise_gain reduces the sums per utterance.
 #include "mpb_frame.cuh"
+#include "mpb_tma.cuh"
 
 namespace mpb {
 
@@ -51,31 +52,6 @@ cudaError_t launch_noise_gain(const SynthCompArgs& a, cudaStream_t st) {
 __device__ __forceinline__ float lerp_row(const float* r0, const float* r1, float w, int k) {
     const float a = r0[k];
     return r1 ? fmaf(w, r1[k] - a, a) : a;
-}
-
-// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // Per-frame scalars, read one frame ahead so that their global-load latency hides under the previous frame's IFFT.

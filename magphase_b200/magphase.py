@@ -627,7 +627,9 @@ class _SynPlan:
         H = fft_len // 2 + 1
         crsf_cf, crsf_bw = define_crossfade_params(fs)
         curve, bin_r = crossfade_curve(H, crsf_cf, crsf_bw, fs)
-        self.HB = bin_r + 1
+        # bins at and above the crossfade's upper edge carry no periodic part: the mask reaches exactly 0 at bin_r
+        # (hann(2B+1)[-1] == 0.0), so the phase rows are only needed for bins < bin_r
+        self.HB = bin_r if curve[bin_r] == 0.0 else bin_r + 1
         u_mag = mel_unwarp_matrix(mag_dim, H, alpha)
         nmel = get_num_full_mel_coeffs_from_num_phase_coeffs(crsf_cf, phase_dim, alpha_phase, fs)
         u_full = mel_unwarp_matrix(nmel, H, alpha_phase)[:, :self.HB]
