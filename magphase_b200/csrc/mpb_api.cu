@@ -68,6 +68,8 @@ int mpb_create(int device, mpb_ctx** out_ctx) {
     CU(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->stream_out, cudaStreamNonBlocking));
     *out_ctx = c;
     return MPB_OK;
 }
@@ -80,6 +82,11 @@ int mpb_destroy(mpb_ctx* ctx) {
     for (auto& b : ctx->scratch) b.release();
     ctx->mt_jump.release();
     ctx->stage.release();
+    ctx->desc_stage.release();
+    ctx->mt_fin.release();
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
+    if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MPB_OK;
@@ -419,21 +426,18 @@ int mpb_min_phase_host(mpb_ctx* ctx, const double* mag, int64_t nfrm, int fft_le
 }
 
 // ---------------------------------------------------------------------------------------------
-// n draws of np.random.uniform(low, high) from NumPy's legacy MT19937 state (key[624], pos in [0, 624]) into a
-// DEVICE buffer; key/pos (HOST, in/out) are advanced exactly as NumPy would advance them.  Synchronises `stream`.
-int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* pos, int64_t n, double low, double high,
-                            void* out_dev, int out_dtype) {
-    if (!ctx || !key || !pos) return fail(MPB_ERR_BAD_ARG, "NULL argument");
-    if (!dtype_ok(out_dtype) || n < 0 || *pos < 0 || *pos > 624) return fail(MPB_ERR_BAD_ARG, "bad dtype, size or MT19937 position");
-    if (n == 0) return MPB_OK;
-    if (!out_dev) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
+}  // extern "C"
+
+// Enqueues n draws of np.random.uniform(low, high) from the state (key[624], pos) on `stream` and an asynchronous
+// read-back of the final state (624 key words + position) into fin625, which must be PAGE-LOCKED host memory; nothing
+// is synchronised.  Internal building block of the pipelined synthesis entry point.
+int mpb::mt19937_enqueue(mpb_ctx* ctx, cudaStream_t st, const uint32_t* key, int32_t pos, int64_t n, double low, double high,
+                         void* out_dev, int out_dtype, uint32_t* fin625) {
     DevBuf* b = ctx->scratch;
     CU(b[9].need(sizeof(uint32_t) * 2 * 625));
     CU(b[10].need(sizeof(uint32_t) * 2 * (size_t)n));
     const uint16_t* d_jump = nullptr;
-    if (mt19937_needs_jump(*pos, n)) {            // more than one segment: jump polynomials (built once per process)
+    if (mt19937_needs_jump(pos, n)) {             // more than one segment: jump polynomials (built once per process)
         if (!ctx->mt_jump_ready) {
             size_t n_idx = 0;
             const uint16_t* h = mt19937_jump_table_host(&n_idx);
@@ -448,10 +452,28 @@ int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* 
     CU(cudaMemcpyAsync(d_state, key, sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
     int slot = 0;
     LAUNCH(ctx, st, "k_mt19937_stream+k_mt_to_uniform",
-           launch_mt19937_uniform(d_state, *pos, &slot, d_jump, (uint32_t*)b[10].p, n, low, high, out_dev, out_dtype, st));
+           launch_mt19937_uniform(d_state, pos, &slot, d_jump, (uint32_t*)b[10].p, n, low, high, out_dev, out_dtype, st));
     ctx->launches += 1;
-    uint32_t fin[625];
-    CU(cudaMemcpyAsync(fin, d_state + 625 * slot, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(fin625, d_state + 625 * slot, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, st));
+    return MPB_OK;
+}
+
+extern "C" {
+
+// n draws of np.random.uniform(low, high) from NumPy's legacy MT19937 state (key[624], pos in [0, 624]) into a
+// DEVICE buffer; key/pos (HOST, in/out) are advanced exactly as NumPy would advance them.  Synchronises `stream`.
+int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* pos, int64_t n, double low, double high,
+                            void* out_dev, int out_dtype) {
+    if (!ctx || !key || !pos) return fail(MPB_ERR_BAD_ARG, "NULL argument");
+    if (!dtype_ok(out_dtype) || n < 0 || *pos < 0 || *pos > 624) return fail(MPB_ERR_BAD_ARG, "bad dtype, size or MT19937 position");
+    if (n == 0) return MPB_OK;
+    if (!out_dev) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(ctx->mt_fin.need(sizeof(uint32_t) * 625));
+    uint32_t* fin = (uint32_t*)ctx->mt_fin.p;
+    int rc = mt19937_enqueue(ctx, st, key, *pos, n, low, high, out_dev, out_dtype, fin);
+    if (rc != MPB_OK) return rc;
     CU(cudaStreamSynchronize(st));
     memcpy(key, fin, sizeof(uint32_t) * 624);
     *pos = (int32_t)fin[624];

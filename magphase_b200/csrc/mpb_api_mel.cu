@@ -13,13 +13,27 @@ struct mpb_mel {
     float* wt_ph = nullptr;      // [kpad][ld_ph]
     double* cos_mag = nullptr;   // [n_mag][n_mag]
     double* cos_ph = nullptr;    // [n_ph][phase_dim]
-    DevBuf partial, feats[3], small[8], compact;
+    DevBuf partial, feats[3], small[8], compact, sig32;
     std::mutex mu;
 };
 
 static constexpr int64_t MEL_CHUNK = 32768;   // frames per pass: bounds the K-slice partial-sum scratch (~400 MB)
 
 static int pad64(int n) { return ((n + 63) / 64) * 64; }
+
+// grows the scratch of mpb_analysis_compressed_dev / mel_compress_impl for calls of up to nfrm frames
+static int mel_reserve(mpb_mel* m, int64_t nfrm) {
+    if (nfrm < 1) return MPB_OK;
+    std::lock_guard<std::mutex> lk(m->mu);
+    const int H = m->fft_len / 2 + 1;
+    const int n_slices = (H - 1) / MEL_KSLICE;
+    const int ncp = m->ld_mag > m->ld_ph ? m->ld_mag : m->ld_ph;
+    const int64_t chunk = nfrm < MEL_CHUNK ? nfrm : MEL_CHUNK;
+    for (int i = 0; i < 3; ++i) CU(m->feats[i].need(sizeof(float) * (size_t)chunk * H));
+    CU(m->partial.need(sizeof(float) * 3 * (size_t)n_slices * (size_t)chunk * ncp));
+    CU(m->compact.need(sizeof(int32_t) * (2 * (size_t)chunk + 4)));
+    return MPB_OK;
+}
 
 extern "C" {
 
@@ -57,7 +71,7 @@ int mpb_mel_destroy(mpb_mel* m) {
     if (!m) return MPB_OK;
     cudaSetDevice(m->ctx->device);
     cudaFree(m->wt_mag); cudaFree(m->wt_ph); cudaFree(m->cos_mag); cudaFree(m->cos_ph);
-    m->partial.release(); m->compact.release();
+    m->partial.release(); m->compact.release(); m->sig32.release();
     for (auto& b : m->feats) b.release();
     for (auto& b : m->small) b.release();
     delete m;
@@ -233,6 +247,11 @@ int mpb_analysis_compressed_host(mpb_mel* m, const double* sig, int64_t n_sig, c
 
 // Same, with the utterances given as separate HOST arrays (no concatenation on the caller's side): centre[] still
 // indexes the virtual concatenation sigs[0] | sigs[1] | ...
+//
+// The call is a three-stage pipeline over groups of utterances: while the host threads narrow group g+1 into the
+// page-locked staging buffer and its samples cross PCIe on stream_in, group g runs its kernels on the compute stream
+// and the features of group g-1 return on stream_out.  Events hand the groups from stage to stage; the scratch of the
+// kernels is shared, which is safe because the compute stream serialises them.
 int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const int64_t* sig_lens, int32_t n_sigs,
                                   const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* voi,
                                   int64_t nfrm, int compute_dtype, double* out_mag_mel, double* out_real_mel,
@@ -252,9 +271,36 @@ int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const i
     if (rc != MPB_OK) return rc;
     CU(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> lk(ctx->mu);
-    const int H = m->fft_len / 2 + 1;
-    cudaStream_t st = ctx->stream;
-    const int64_t chunk = nfrm < MEL_CHUNK ? nfrm : MEL_CHUNK;
+    static const bool trace = getenv("MPB_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return 1e3 * std::chrono::duration<double>(b - a).count();
+    };
+    const auto t0 = now();
+    cudaStream_t s_in = ctx->stream_in, s_cmp = ctx->stream, s_out = ctx->stream_out;
+
+    // ---- groups of whole utterances with about the same number of frames (frames never straddle utterances) ----
+    int n_groups = pipeline_groups();
+    if (n_groups > n_sigs) n_groups = n_sigs;
+    std::vector<int32_t> group_end((size_t)n_groups);          // one past the last signal of the group
+    std::vector<int64_t> group_frm((size_t)n_groups + 1, 0);   // frame range of the group
+    {
+        int64_t f = 0, off = 0;
+        int32_t g = 0;
+        for (int32_t i = 0; i < n_sigs; ++i) {
+            off += sig_lens[i];
+            while (f < nfrm && centre[f] < off) ++f;           // frames are ordered by utterance
+            const int32_t left_sigs = n_sigs - 1 - i, left_groups = n_groups - 1 - g;
+            if (i == n_sigs - 1 || (left_groups > 0 && (f * n_groups >= nfrm * (g + 1) || left_sigs == left_groups))) {
+                group_end[g] = i + 1;
+                group_frm[g + 1] = f;
+                if (++g == n_groups) break;
+            }
+        }
+        n_groups = g;
+        group_frm[n_groups] = nfrm;
+    }
+
     CU(m->small[0].need((size_t)nfrm));
     CU(m->small[1].need(sizeof(double) * nfrm * m->n_mag));
     CU(m->small[2].need(sizeof(double) * nfrm * m->phase_dim));
@@ -263,33 +309,67 @@ int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const i
     CU(m->small[5].need(sizeof(int64_t) * nfrm));
     CU(m->small[6].need(sizeof(int32_t) * nfrm));
     CU(m->small[7].need(sizeof(int32_t) * nfrm));
-    static const bool trace = getenv("MPB_TRACE") != nullptr;
-    auto now = [] { return std::chrono::steady_clock::now(); };
-    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-        return 1e3 * std::chrono::duration<double>(b - a).count();
-    };
-    const auto t0 = now();
-    int sig_dtype = MPB_F64;
-    rc = upload_signals(ctx, st, sigs, sig_lens, n_sigs, m->small[4].p, &sig_dtype);
-    if (rc != MPB_OK) return rc;
-    const auto t1 = now();
-    CU(cudaMemcpyAsync(m->small[5].p, centre, sizeof(int64_t) * nfrm, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(m->small[6].p, left, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(m->small[7].p, right, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(m->small[0].p, voi, (size_t)nfrm, cudaMemcpyHostToDevice, st));
+    CU(m->sig32.need(sizeof(float) * n_sig));
+    {   // size the kernels' scratch for the largest group up front: a grow in mid-pipeline would free live buffers
+        int64_t big = 0;
+        for (int g = 0; g < n_groups; ++g) big = std::max(big, group_frm[g + 1] - group_frm[g]);
+        rc = mel_reserve(m, big);
+        if (rc != MPB_OK) return rc;
+    }
+    // frame descriptors: one page-locked block, one copy (pageable copies would stall the enqueueing thread)
+    const size_t d_bytes = (sizeof(int64_t) + 2 * sizeof(int32_t) + 1) * (size_t)nfrm;
+    CU(ctx->desc_stage.need(d_bytes));
+    {
+        char* h = (char*)ctx->desc_stage.p;
+        memcpy(h, centre, sizeof(int64_t) * nfrm);
+        memcpy(h + 8 * nfrm, left, sizeof(int32_t) * nfrm);
+        memcpy(h + 12 * nfrm, right, sizeof(int32_t) * nfrm);
+        memcpy(h + 16 * nfrm, voi, (size_t)nfrm);
+        CU(cudaMemcpyAsync(m->small[5].p, h, sizeof(int64_t) * nfrm, cudaMemcpyHostToDevice, s_in));
+        CU(cudaMemcpyAsync(m->small[6].p, h + 8 * nfrm, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, s_in));
+        CU(cudaMemcpyAsync(m->small[7].p, h + 12 * nfrm, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, s_in));
+        CU(cudaMemcpyAsync(m->small[0].p, h + 16 * nfrm, (size_t)nfrm, cudaMemcpyHostToDevice, s_in));
+    }
     (void)compute_dtype;   // the fused path always runs float64 butterflies
-    rc = mpb_analysis_compressed_dev(m, st, m->small[4].p, sig_dtype, n_sig, (const int64_t*)m->small[5].p,
-                                     (const int32_t*)m->small[6].p, (const int32_t*)m->small[7].p,
-                                     (const uint8_t*)m->small[0].p, nfrm, m->small[1].p, m->small[2].p, m->small[3].p, MPB_F64);
-    if (rc != MPB_OK) return rc;
-    CU(cudaMemcpyAsync(out_mag_mel, m->small[1].p, sizeof(double) * nfrm * m->n_mag, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(out_real_mel, m->small[2].p, sizeof(double) * nfrm * m->phase_dim, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(out_imag_mel, m->small[3].p, sizeof(double) * nfrm * m->phase_dim, cudaMemcpyDeviceToHost, st));
+    const auto t1 = now();
+    std::vector<cudaEvent_t> evs;
+    auto on_group = [&](int32_t g, int dtype) -> int {
+        cudaEvent_t e_in = get_event(ctx), e_cmp = get_event(ctx);
+        evs.push_back(e_in); evs.push_back(e_cmp);
+        CU(cudaEventRecord(e_in, s_in));
+        CU(cudaStreamWaitEvent(s_cmp, e_in, 0));
+        const int64_t fa = group_frm[g], n = group_frm[g + 1] - fa;
+        if (n > 0) {
+            int r = mpb_analysis_compressed_dev(
+                m, s_cmp, dtype == MPB_F32 ? m->sig32.p : m->small[4].p, dtype, n_sig, (const int64_t*)m->small[5].p + fa,
+                (const int32_t*)m->small[6].p + fa, (const int32_t*)m->small[7].p + fa, (const uint8_t*)m->small[0].p + fa, n,
+                (double*)m->small[1].p + fa * m->n_mag, (double*)m->small[2].p + fa * m->phase_dim,
+                (double*)m->small[3].p + fa * m->phase_dim, MPB_F64);
+            if (r != MPB_OK) return r;
+        }
+        CU(cudaEventRecord(e_cmp, s_cmp));
+        CU(cudaStreamWaitEvent(s_out, e_cmp, 0));
+        if (n > 0) {
+            CU(cudaMemcpyAsync(out_mag_mel + fa * m->n_mag, (double*)m->small[1].p + fa * m->n_mag,
+                               sizeof(double) * n * m->n_mag, cudaMemcpyDeviceToHost, s_out));
+            CU(cudaMemcpyAsync(out_real_mel + fa * m->phase_dim, (double*)m->small[2].p + fa * m->phase_dim,
+                               sizeof(double) * n * m->phase_dim, cudaMemcpyDeviceToHost, s_out));
+            CU(cudaMemcpyAsync(out_imag_mel + fa * m->phase_dim, (double*)m->small[3].p + fa * m->phase_dim,
+                               sizeof(double) * n * m->phase_dim, cudaMemcpyDeviceToHost, s_out));
+        }
+        return MPB_OK;
+    };
+    rc = upload_signal_groups(ctx, s_in, sigs, sig_lens, n_sigs, group_end.data(), n_groups, m->sig32.p, m->small[4].p,
+                              on_group);
     const auto t2 = now();
-    CU(cudaStreamSynchronize(st));
+    // drain all three stages even after an error: host and staging buffers must not be reused under a live copy
+    cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
+    for (auto e : evs) put_event(ctx, e);
+    if (rc != MPB_OK) return rc;
+    CU(e1); CU(e2); CU(e3);
     if (trace)
-        fprintf(stderr, "[mpb] analysis_compressed_hostv: upload %.3f ms, enqueue %.3f ms, drain %.3f ms\n", ms(t0, t1),
-                ms(t1, t2), ms(t2, now()));
+        fprintf(stderr, "[mpb] analysis_compressed_hostv: %d groups, prepare %.3f ms, stage+enqueue %.3f ms, drain %.3f ms\n",
+                n_groups, ms(t0, t1), ms(t1, t2), ms(t2, now()));
     return MPB_OK;
 }
 

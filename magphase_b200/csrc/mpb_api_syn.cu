@@ -5,8 +5,6 @@
 
 using namespace mpb;
 
-extern "C" int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* pos, int64_t n, double low,
-                                       double high, void* out_dev, int out_dtype);
 extern "C" int mpb_sos2_dev(mpb_ctx* ctx, void* stream, void* x, int dtype, const int64_t* utt_off, int32_t n_utt,
                             const double* sos);
 extern "C" int mpb_plan_ola_runs(const int32_t* pm, const int64_t* utt_frm_off, int32_t n_utt, int fft_len,
@@ -65,6 +63,107 @@ int mpb_syn_destroy(mpb_syn* s) {
     return MPB_OK;
 }
 
+}  // extern "C"
+
+// A slice of a batch: whole utterances [utt_a, utt_b) with their feature rows, frames, OLA runs and output samples.
+// `ordinal` numbers the slices of one call (it spaces their private scratch regions).
+struct SynRange {
+    int64_t row_a, row_b, frm_a, frm_b, out_a, out_b;
+    int32_t utt_a, utt_b, run_a, run_b;
+    int ordinal;
+};
+
+// grows every scratch buffer of a call to its final size (the ranges of a pipelined call run while others are enqueued)
+static int syn_reserve(mpb_syn* s, int in_dtype, int64_t n_rows, int64_t nfrm, int32_t n_utt, int n_ranges, size_t* cvt_pitch) {
+    const int HP = (s->H + 3) & ~3, HBP = (s->HB + 3) & ~3;      // scratch row pitches: 16-byte aligned rows
+    CU(s->unw[0].need(sizeof(float) * (size_t)n_rows * HP));
+    CU(s->unw[1].need(sizeof(float) * (size_t)n_rows * HBP));
+    CU(s->unw[2].need(sizeof(float) * (size_t)n_rows * HBP));
+    CU(s->logsq.need(sizeof(double) * (size_t)nfrm));
+    CU(s->nspec.need(sizeof(float2) * (size_t)nfrm * (s->fft_len / 2 + 2)));
+    CU(s->gain.need(sizeof(double) * 2 * (size_t)n_utt));
+    CU(s->unw_flags.need((size_t)n_rows / 64 + n_ranges + 2));
+    *cvt_pitch = 0;
+    if (in_dtype == MPB_F64) {
+        const size_t widest = (size_t)(s->n_mag > s->n_ph ? s->n_mag : s->n_ph);
+        *cvt_pitch = ((size_t)n_rows * widest + 4 * ((size_t)n_ranges + 1) + 63) & ~(size_t)63;   // 256-byte aligned matrices
+        CU(s->unw_cvt.need(sizeof(float) * 3 * *cvt_pitch));
+    }
+    return MPB_OK;
+}
+
+// un-warp, [min-phase], noise statistics, gains and synthesis of one range, enqueued on st (scratch already reserved)
+static int syn_enqueue_range(mpb_syn* s, cudaStream_t st, const void* mag_mel, const void* real_mel, const void* imag_mel,
+                             int in_dtype, const uint8_t* need_ph, const float* noise, int64_t n_noise,
+                             const mpb_syn_frames* fr, const int32_t* runs, int per_linear, void* out, int out_dtype,
+                             size_t cvt_pitch, const SynRange& r) {
+    mpb_ctx* ctx = s->ctx;
+    const int HP = (s->H + 3) & ~3, HBP = (s->HB + 3) & ~3;
+    const size_t ies = in_dtype == MPB_F64 ? 8 : 4, oes = out_dtype == MPB_F64 ? 8 : 4;
+    const int64_t n_rows = r.row_b - r.row_a, nfrm = r.frm_b - r.frm_a;
+    CU(cudaMemsetAsync((char*)out + oes * r.out_a, 0, oes * (size_t)(r.out_b - r.out_a), st));
+    if (nfrm == 0 || n_rows == 0) return MPB_OK;
+
+    UnwarpArgs u;
+    u.mag_mel = (const char*)mag_mel + ies * r.row_a * s->n_mag;
+    u.real_mel = (const char*)real_mel + ies * r.row_a * s->n_ph;
+    u.imag_mel = (const char*)imag_mel + ies * r.row_a * s->n_ph;
+    u.in_dtype = in_dtype;
+    u.need_ph = need_ph + r.row_a; u.nfrm = n_rows; u.n_mag = s->n_mag; u.n_ph = s->n_ph;
+    u.u_mag = s->u_mag; u.H = s->H; u.u_ph = s->u_ph; u.HB = s->HB;
+    u.out_mag = (float*)s->unw[0].p + r.row_a * HP; u.out_real = (float*)s->unw[1].p + r.row_a * HBP;
+    u.out_imag = (float*)s->unw[2].p + r.row_a * HBP;
+    u.HP = HP; u.HBP = HBP; u.num_sms = ctx->num_sms;
+    u.flags = (uint8_t*)s->unw_flags.p + r.row_a / 64 + r.ordinal;
+    u.cvt = nullptr; u.cvt_pitch = cvt_pitch; u.cvt_off_mag = 0; u.cvt_off_ph = 0;
+    if (in_dtype == MPB_F64) {
+        // private, 16-byte aligned regions of the narrowing scratch (TMA sources) for this range
+        u.cvt = (float*)s->unw_cvt.p;
+        u.cvt_off_mag = (((size_t)r.row_a * s->n_mag + 3) & ~(size_t)3) + 4 * (size_t)r.ordinal;
+        u.cvt_off_ph = (((size_t)r.row_a * s->n_ph + 3) & ~(size_t)3) + 4 * (size_t)r.ordinal;
+    }
+    LAUNCH(ctx, st, "k_mel_unwarp", launch_mel_unwarp(u, st));
+
+    const void* tw = nullptr;
+    int rc = get_twiddles(ctx, s->fft_len, MPB_F32, &tw);
+    if (rc != MPB_OK) return rc;
+    const int SP = s->fft_len / 2 + 2;
+    AnalysisArgs n;
+    n.sig = noise; n.sig_dtype = MPB_F32; n.n_sig = n_noise;
+    n.centre = fr->ncentre + r.frm_a; n.left = fr->nleft + r.frm_a; n.right = fr->nright + r.frm_a; n.win = fr->nkind + r.frm_a;
+    n.nfrm = nfrm; n.fft_len = s->fft_len; n.compute_dtype = MPB_F32; n.tw = tw;
+    n.out_a = (double*)s->logsq.p + r.frm_a; n.out_b = (float2*)s->nspec.p + r.frm_a * SP; n.out_c = nullptr;
+    n.out_dtype = MPB_F64; n.mode = MODE_LOGSQ;
+    n.num_sms = ctx->num_sms;
+    LAUNCH(ctx, st, "k_analysis<noise_logsq>", launch_noise_stats(n, st));
+
+    SynthCompArgs a;
+    a.m_mag = (const float*)s->unw[0].p; a.m_real = (const float*)s->unw[1].p; a.m_imag = (const float*)s->unw[2].p;
+    a.H = s->H; a.HB = s->HB; a.HP = HP; a.HBP = HBP;
+    a.noise = noise; a.n_noise = n_noise; a.nspec = (const float2*)s->nspec.p;
+    a.pm = fr->pm; a.ncentre = fr->ncentre; a.nleft = fr->nleft; a.nright = fr->nright;
+    a.voi = fr->voi; a.nkind = fr->nkind; a.win_a = fr->win_a; a.win_b = fr->win_b;
+    a.row0 = fr->row0; a.row1 = fr->row1; a.roww = fr->roww;
+    a.logsq = (const double*)s->logsq.p; a.utt_frm_off = fr->utt_frm_off; a.inv_gain = (double*)s->gain.p;
+    a.tab = s->tab; a.utt_out_off = fr->utt_out_off; a.utt_t0 = fr->utt_t0; a.n_utt = fr->n_utt;
+    a.utt_a = r.utt_a; a.utt_b = r.utt_b;
+    a.runs = (const OlaRun*)runs + r.run_a; a.n_runs = r.run_b - r.run_a; a.nfrm = fr->nfrm;
+    a.fft_len = s->fft_len; a.per_linear = per_linear == 1; a.tw = tw;
+    if (per_linear == 2) {   // per_phase_type='min_phase': Re/Im of the minimum-phase spectrum replace the phase rows
+        const void* tw64 = nullptr;
+        rc = get_twiddles(ctx, s->fft_len, MPB_F64, &tw64);
+        if (rc != MPB_OK) return rc;
+        LAUNCH(ctx, st, "k_min_phase", launch_min_phase_split(s->fft_len, u.out_mag, HP, n_rows, tw64, u.out_real, u.out_imag,
+                                                               s->HB, HBP, ctx->num_sms, st));
+    }
+    a.out = out; a.out_dtype = out_dtype; a.n_out = 0; a.num_sms = ctx->num_sms;
+    LAUNCH(ctx, st, "k_noise_gain", launch_noise_gain(a, st));
+    LAUNCH(ctx, st, "k_synthesis_compressed", launch_synthesis_compressed(a, st));
+    return MPB_OK;
+}
+
+extern "C" {
+
 // per_linear: 0 = per_phase_type 'magphase', 1 = 'linear', 2 = 'min_phase' (pass need_ph all zero).
 // All pointers are DEVICE pointers (fr included: a host struct of device pointers).  Enqueues un-warp,
 // noise statistics, gains and the synthesis kernel on `stream`.
@@ -88,67 +187,21 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
     if (in_dtype == MPB_F32 && (((uintptr_t)mag_mel | (uintptr_t)real_mel | (uintptr_t)imag_mel) & 15))
         return fail(MPB_ERR_BAD_ARG, "float32 feature matrices must be 16-byte aligned (they are fetched by TMA bulk copies)");
     std::lock_guard<std::mutex> lk(s->mu);
-    const int HP = (s->H + 3) & ~3, HBP = (s->HB + 3) & ~3;      // scratch row pitches: 16-byte aligned rows
-    CU(s->unw[0].need(sizeof(float) * (size_t)n_rows * HP));
-    CU(s->unw[1].need(sizeof(float) * (size_t)n_rows * HBP));
-    CU(s->unw[2].need(sizeof(float) * (size_t)n_rows * HBP));
-    CU(s->logsq.need(sizeof(double) * (size_t)fr->nfrm));
-    CU(s->nspec.need(sizeof(float2) * (size_t)fr->nfrm * (s->fft_len / 2 + 2)));
-    CU(s->gain.need(sizeof(double) * 2 * (size_t)fr->n_utt));
-
-    UnwarpArgs u;
-    u.mag_mel = mag_mel; u.real_mel = real_mel; u.imag_mel = imag_mel; u.in_dtype = in_dtype;
-    u.need_ph = need_ph; u.nfrm = n_rows; u.n_mag = s->n_mag; u.n_ph = s->n_ph;
-    u.u_mag = s->u_mag; u.H = s->H; u.u_ph = s->u_ph; u.HB = s->HB;
-    u.out_mag = (float*)s->unw[0].p; u.out_real = (float*)s->unw[1].p; u.out_imag = (float*)s->unw[2].p;
-    u.HP = HP; u.HBP = HBP; u.num_sms = ctx->num_sms;
-    CU(s->unw_flags.need((size_t)(n_rows + 63) / 64 + 1));
-    u.flags = (uint8_t*)s->unw_flags.p;
-    u.cvt = nullptr; u.cvt_pitch = 0;
-    if (in_dtype == MPB_F64) {
-        const size_t widest = (size_t)(s->n_mag > s->n_ph ? s->n_mag : s->n_ph);
-        u.cvt_pitch = ((size_t)n_rows * widest + 63) & ~(size_t)63;       // keeps every matrix 256-byte aligned
-        CU(s->unw_cvt.need(sizeof(float) * 3 * u.cvt_pitch));
-        u.cvt = (float*)s->unw_cvt.p;
-    }
-    LAUNCH(ctx, st, "k_mel_unwarp", launch_mel_unwarp(u, st));
-
-    const void* tw = nullptr;
-    int rc = get_twiddles(ctx, s->fft_len, MPB_F32, &tw);
+    size_t cvt_pitch = 0;
+    int rc = syn_reserve(s, in_dtype, n_rows, fr->nfrm, fr->n_utt, 1, &cvt_pitch);
     if (rc != MPB_OK) return rc;
-    AnalysisArgs n;
-    n.sig = noise; n.sig_dtype = MPB_F32; n.n_sig = n_noise;
-    n.centre = fr->ncentre; n.left = fr->nleft; n.right = fr->nright; n.win = fr->nkind;
-    n.nfrm = fr->nfrm; n.fft_len = s->fft_len; n.compute_dtype = MPB_F32; n.tw = tw;
-    n.out_a = s->logsq.p; n.out_b = s->nspec.p; n.out_c = nullptr; n.out_dtype = MPB_F64; n.mode = MODE_LOGSQ;
-    n.num_sms = ctx->num_sms;
-    LAUNCH(ctx, st, "k_analysis<noise_logsq>", launch_noise_stats(n, st));
-
-    SynthCompArgs a;
-    a.m_mag = u.out_mag; a.m_real = u.out_real; a.m_imag = u.out_imag; a.H = s->H; a.HB = s->HB; a.HP = HP; a.HBP = HBP;
-    a.noise = noise; a.n_noise = n_noise; a.nspec = (const float2*)s->nspec.p;
-    a.pm = fr->pm; a.ncentre = fr->ncentre; a.nleft = fr->nleft; a.nright = fr->nright;
-    a.voi = fr->voi; a.nkind = fr->nkind; a.win_a = fr->win_a; a.win_b = fr->win_b;
-    a.row0 = fr->row0; a.row1 = fr->row1; a.roww = fr->roww;
-    a.logsq = (const double*)s->logsq.p; a.utt_frm_off = fr->utt_frm_off; a.inv_gain = (double*)s->gain.p;
-    a.tab = s->tab; a.utt_out_off = fr->utt_out_off; a.utt_t0 = fr->utt_t0; a.n_utt = fr->n_utt;
-    a.runs = (const OlaRun*)runs; a.n_runs = n_runs; a.nfrm = fr->nfrm;
-    a.fft_len = s->fft_len; a.per_linear = per_linear == 1; a.tw = tw;
-    if (per_linear == 2) {   // per_phase_type='min_phase': Re/Im of the minimum-phase spectrum replace the phase rows
-        const void* tw64 = nullptr;
-        rc = get_twiddles(ctx, s->fft_len, MPB_F64, &tw64);
-        if (rc != MPB_OK) return rc;
-        LAUNCH(ctx, st, "k_min_phase", launch_min_phase_split(s->fft_len, u.out_mag, HP, n_rows, tw64, u.out_real, u.out_imag,
-                                                               s->HB, HBP, ctx->num_sms, st));
-    }
-    a.out = out; a.out_dtype = out_dtype; a.n_out = n_out; a.num_sms = ctx->num_sms;
-    LAUNCH(ctx, st, "k_noise_gain", launch_noise_gain(a, st));
-    LAUNCH(ctx, st, "k_synthesis_compressed", launch_synthesis_compressed(a, st));
-    return MPB_OK;
+    SynRange r;
+    r.row_a = 0; r.row_b = n_rows; r.frm_a = 0; r.frm_b = fr->nfrm; r.out_a = 0; r.out_b = n_out;
+    r.utt_a = 0; r.utt_b = fr->n_utt; r.run_a = 0; r.run_b = n_runs; r.ordinal = 0;
+    return syn_enqueue_range(s, st, mag_mel, real_mel, imag_mel, in_dtype, need_ph, noise, n_noise, fr, runs, per_linear, out,
+                             out_dtype, cvt_pitch, r);
 }
 
-// HOST pointers everywhere.  noise: the uniform(-1, 1) samples of all utterances, concatenated -- or NULL with
-// mt_key / mt_pos (NumPy's legacy MT19937 state, in/out): then the same numbers are generated on the device.
+// Host buffers in, host buffer out.  Like the analysis entry point this is a three-stage pipeline over groups of
+// utterances: features of group g+1 cross PCIe on stream_in while group g runs un-warp / noise statistics / gains /
+// synthesis on the compute stream and the waveform of group g-1 returns on stream_out.  The noise of the whole batch
+// is drawn first on the compute stream (the MT19937 stream is one sequence); its final state comes back through
+// page-locked memory at the end.  Frame descriptors travel as one page-locked block.
 int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const double* real_mel, const double* imag_mel,
                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
                                   uint32_t* mt_key, int32_t* mt_pos, const mpb_syn_frames* fr, int per_linear,
@@ -157,19 +210,26 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
     if (n_out == 0) return MPB_OK;
     if (!mag_mel || !real_mel || !imag_mel || !need_ph || !out) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
     if (!noise && !(mt_key && mt_pos)) return fail(MPB_ERR_BAD_ARG, "either noise or an MT19937 state is required");
+    if (!noise && (*mt_pos < 0 || *mt_pos > 624)) return fail(MPB_ERR_BAD_ARG, "bad MT19937 position");
     const int64_t F = fr->nfrm;
     const int32_t U = fr->n_utt;
+    if (F < 0 || U < 0 || n_rows < 0 || n_noise < 0) return fail(MPB_ERR_BAD_ARG, "negative size");
+    if (F > 0 && (!fr->pm || !fr->ncentre || !fr->nleft || !fr->nright || !fr->voi || !fr->nkind || !fr->win_a || !fr->win_b ||
+                  !fr->row0 || !fr->utt_frm_off || !fr->utt_out_off || !fr->utt_t0))
+        return fail(MPB_ERR_BAD_ARG, "NULL buffer");
     static const bool trace = getenv("MPB_TRACE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return 1e3 * std::chrono::duration<double>(b - a).count();
     };
     const auto t0 = now();
+    bool identity_rows = fr->row1 == nullptr && n_rows == F;     // variable rate: frame f reads feature row f
     for (int64_t f = 0; f < F; ++f) {
         if (fr->win_a[f] < 0 || fr->win_b[f] < 0 || fr->win_a[f] > s->fft_len / 2 || fr->win_b[f] >= s->fft_len / 2)
             return fail(MPB_ERR_FRAME_GEOM, "anti-ringing window longer than fft_len/2 (f0 too low for this fft_len)");
         if (fr->row0[f] < 0 || fr->row0[f] >= n_rows || (fr->row1 && (fr->row1[f] < 0 || fr->row1[f] >= n_rows)))
             return fail(MPB_ERR_BAD_ARG, "feature row index out of range");
+        identity_rows = identity_rows && fr->row0[f] == f;
     }
     int rc = check_frames_host(fr->ncentre, fr->nleft, fr->nright, F, n_noise, s->fft_len);
     if (rc != MPB_OK) return rc;
@@ -184,76 +244,152 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
     std::vector<int32_t> runs(4 * (size_t)(n_runs > 0 ? n_runs : 1));
     rc = mpb_plan_ola_runs(fr->pm, fr->utt_frm_off, U, s->fft_len, target, runs.data(), n_runs, &n_runs);
     if (rc != MPB_OK) return rc;
-    std::vector<float> noise32;
-    if (noise) {
-        noise32.resize((size_t)n_noise);
-        for (int64_t i = 0; i < n_noise; ++i) noise32[i] = (float)noise[i];
+
+    // ---- groups of whole utterances with about the same number of frames; constant-rate input (frames address
+    // arbitrary feature rows) and the output high-pass (a per-utterance scan that synchronises) run as one group ----
+    int n_groups = (identity_rows && !hpf_sos) ? pipeline_groups() : 1;
+    if (n_groups > U) n_groups = U > 0 ? U : 1;
+    std::vector<SynRange> rg;
+    {
+        int32_t ua = 0, run_i = 0;
+        for (int g = 0; g < n_groups && ua < U; ++g) {
+            int32_t ub = ua + 1;
+            if (g == n_groups - 1) ub = U;
+            else while (ub < U - (n_groups - 1 - g) && fr->utt_frm_off[ub] * n_groups < F * (g + 1)) ++ub;
+            SynRange r;
+            r.utt_a = ua; r.utt_b = ub; r.ordinal = g;
+            r.frm_a = fr->utt_frm_off[ua]; r.frm_b = fr->utt_frm_off[ub];
+            r.row_a = n_groups == 1 ? 0 : r.frm_a; r.row_b = n_groups == 1 ? n_rows : r.frm_b;
+            r.out_a = fr->utt_out_off[ua]; r.out_b = fr->utt_out_off[ub];
+            r.run_a = run_i;
+            while (run_i < n_runs && runs[4 * (size_t)run_i + 2] < ub) ++run_i;
+            r.run_b = run_i;
+            rg.push_back(r);
+            ua = ub;
+        }
+        if (rg.empty()) { SynRange r{0, n_rows, 0, F, 0, n_out, 0, U, 0, (int32_t)n_runs, 0}; rg.push_back(r); }
+        rg.back().out_b = n_out;
     }
 
     mpb_ctx* ctx = s->ctx;
     CU(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> lk(ctx->mu);
-    cudaStream_t st = ctx->stream;
+    std::lock_guard<std::mutex> lk2(s->mu);
+    cudaStream_t s_in = ctx->stream_in, s_cmp = ctx->stream, s_out = ctx->stream_out;
     const auto t1 = now();
+
+    // ---- device buffers, all at their final size before anything is enqueued ----
     DevBuf* b = s->host_in;
-    int bi = 0;
-    auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
-        if (!src) { *dst = nullptr; ++bi; return MPB_OK; }
-        DevBuf& d = b[bi++];
-        CU(d.need(bytes > 0 ? bytes : 1));
-        CU(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, st));
-        *dst = d.p;
-        return MPB_OK;
-    };
+    enum { B_MAG = 0, B_REAL, B_IMAG, B_NOISE, B_DESC };
+    CU(b[B_MAG].need(sizeof(double) * (size_t)n_rows * s->n_mag + 16));
+    CU(b[B_REAL].need(sizeof(double) * (size_t)n_rows * s->n_ph + 16));
+    CU(b[B_IMAG].need(sizeof(double) * (size_t)n_rows * s->n_ph + 16));
+    CU(b[B_NOISE].need(sizeof(float) * (size_t)(n_noise > 0 ? n_noise : 1)));
+    CU(s->out.need(sizeof(double) * (size_t)n_out));
+    size_t cvt_pitch = 0;
+    rc = syn_reserve(s, MPB_F64, n_rows, F, U, (int)rg.size(), &cvt_pitch);
+    if (rc != MPB_OK) return rc;
+
+    // ---- descriptors: one page-locked block, one copy ----
+    struct Item { const void* src; size_t bytes; const void** dst; };
     mpb_syn_frames d = *fr;
-    const void *d_mag, *d_real, *d_imag, *d_need, *d_noise, *d_runs;
-#define UP(src, bytes, dst) do { rc = up(src, bytes, (const void**)&(dst)); if (rc != MPB_OK) return rc; } while (0)
-    UP(mag_mel, sizeof(double) * n_rows * s->n_mag, d_mag);
-    UP(real_mel, sizeof(double) * n_rows * s->n_ph, d_real);
-    UP(imag_mel, sizeof(double) * n_rows * s->n_ph, d_imag);
-    UP(need_ph, (size_t)n_rows, d_need);
+    const void *d_need = nullptr, *d_runs = nullptr;
+    const Item items[] = {
+        {need_ph, (size_t)n_rows, &d_need},
+        {runs.data(), sizeof(int32_t) * 4 * (size_t)n_runs, &d_runs},
+        {fr->pm, sizeof(int32_t) * F, (const void**)&d.pm},
+        {fr->ncentre, sizeof(int64_t) * F, (const void**)&d.ncentre},
+        {fr->nleft, sizeof(int32_t) * F, (const void**)&d.nleft},
+        {fr->nright, sizeof(int32_t) * F, (const void**)&d.nright},
+        {fr->voi, (size_t)F, (const void**)&d.voi},
+        {fr->nkind, (size_t)F, (const void**)&d.nkind},
+        {fr->win_a, sizeof(int32_t) * F, (const void**)&d.win_a},
+        {fr->win_b, sizeof(int32_t) * F, (const void**)&d.win_b},
+        {fr->row0, sizeof(int32_t) * F, (const void**)&d.row0},
+        {fr->row1, fr->row1 ? sizeof(int32_t) * F : 0, (const void**)&d.row1},
+        {fr->roww, fr->roww ? sizeof(float) * F : 0, (const void**)&d.roww},
+        {fr->utt_frm_off, sizeof(int64_t) * ((size_t)U + 1), (const void**)&d.utt_frm_off},
+        {fr->utt_out_off, sizeof(int64_t) * ((size_t)U + 1), (const void**)&d.utt_out_off},
+        {fr->utt_t0, sizeof(int32_t) * (size_t)U, (const void**)&d.utt_t0},
+    };
+    size_t d_bytes = 0;
+    for (const Item& it : items) d_bytes += (it.bytes + 15) & ~(size_t)15;
+    CU(ctx->desc_stage.need(d_bytes > 0 ? d_bytes : 16));
+    CU(b[B_DESC].need(d_bytes > 0 ? d_bytes : 16));
+    {
+        char* h = (char*)ctx->desc_stage.p;
+        size_t off = 0;
+        for (const Item& it : items) {
+            if (it.src && it.bytes) { memcpy(h + off, it.src, it.bytes); *it.dst = (const char*)b[B_DESC].p + off; }
+            else *it.dst = nullptr;
+            off += (it.bytes + 15) & ~(size_t)15;
+        }
+        if (d_bytes) CU(cudaMemcpyAsync(b[B_DESC].p, h, d_bytes, cudaMemcpyHostToDevice, s_in));
+    }
+
+    // ---- noise: explicit samples (narrowed on the host, uploaded) or the NumPy stream advanced on the device ----
+    std::vector<float> noise32;
+    uint32_t* mt_fin = nullptr;
     if (noise) {
-        UP(noise32.data(), sizeof(float) * n_noise, d_noise);
-    } else {
-        DevBuf& dn = b[bi++];
-        CU(dn.need(sizeof(float) * (size_t)(n_noise > 0 ? n_noise : 1)));
-        rc = mpb_mt19937_uniform_dev(ctx, st, mt_key, mt_pos, n_noise, -1.0, 1.0, dn.p, MPB_F32);
-        if (rc != MPB_OK) return rc;
-        d_noise = dn.p;
+        noise32.resize((size_t)n_noise);
+        for (int64_t i = 0; i < n_noise; ++i) noise32[i] = (float)noise[i];
+        if (n_noise) CU(cudaMemcpyAsync(b[B_NOISE].p, noise32.data(), sizeof(float) * n_noise, cudaMemcpyHostToDevice, s_in));
+    } else if (n_noise > 0) {
+        CU(ctx->mt_fin.need(sizeof(uint32_t) * 625));
+        mt_fin = (uint32_t*)ctx->mt_fin.p;
+        rc = mt19937_enqueue(ctx, s_cmp, mt_key, *mt_pos, n_noise, -1.0, 1.0, b[B_NOISE].p, MPB_F32, mt_fin);
+        if (rc != MPB_OK) { cudaStreamSynchronize(s_cmp); cudaStreamSynchronize(s_in); return rc; }
     }
     const auto t2 = now();
-    UP(runs.data(), sizeof(int32_t) * 4 * n_runs, d_runs);
-    UP(fr->pm, sizeof(int32_t) * F, d.pm);
-    UP(fr->ncentre, sizeof(int64_t) * F, d.ncentre);
-    UP(fr->nleft, sizeof(int32_t) * F, d.nleft);
-    UP(fr->nright, sizeof(int32_t) * F, d.nright);
-    UP(fr->voi, (size_t)F, d.voi);
-    UP(fr->nkind, (size_t)F, d.nkind);
-    UP(fr->win_a, sizeof(int32_t) * F, d.win_a);
-    UP(fr->win_b, sizeof(int32_t) * F, d.win_b);
-    UP(fr->row0, sizeof(int32_t) * F, d.row0);
-    UP(fr->row1, sizeof(int32_t) * F, d.row1);
-    UP(fr->roww, sizeof(float) * F, d.roww);
-    UP(fr->utt_frm_off, sizeof(int64_t) * (U + 1), d.utt_frm_off);
-    UP(fr->utt_out_off, sizeof(int64_t) * (U + 1), d.utt_out_off);
-    UP(fr->utt_t0, sizeof(int32_t) * U, d.utt_t0);
-#undef UP
-    const auto t3 = now();
-    CU(s->out.need(sizeof(double) * n_out));
-    rc = mpb_synthesis_compressed_dev(s, st, d_mag, d_real, d_imag, MPB_F64, n_rows, (const uint8_t*)d_need,
-                                      (const float*)d_noise, n_noise, &d, (const int32_t*)d_runs, (int32_t)n_runs,
-                                      per_linear, s->out.p, MPB_F64, n_out);
-    if (rc != MPB_OK) return rc;
-    if (hpf_sos) {                   // output high-pass (src/magphase.py:981-995) on the device, per utterance
-        rc = mpb_sos2_dev(ctx, st, s->out.p, MPB_F64, fr->utt_out_off, U, hpf_sos);
-        if (rc != MPB_OK) return rc;
+
+    // ---- the pipeline ----
+    std::vector<cudaEvent_t> evs;
+    for (const SynRange& r : rg) {
+        const int64_t nr = r.row_b - r.row_a;
+        if (nr > 0) {
+            CU(cudaMemcpyAsync((double*)b[B_MAG].p + r.row_a * s->n_mag, mag_mel + r.row_a * s->n_mag,
+                               sizeof(double) * nr * s->n_mag, cudaMemcpyHostToDevice, s_in));
+            CU(cudaMemcpyAsync((double*)b[B_REAL].p + r.row_a * s->n_ph, real_mel + r.row_a * s->n_ph,
+                               sizeof(double) * nr * s->n_ph, cudaMemcpyHostToDevice, s_in));
+            CU(cudaMemcpyAsync((double*)b[B_IMAG].p + r.row_a * s->n_ph, imag_mel + r.row_a * s->n_ph,
+                               sizeof(double) * nr * s->n_ph, cudaMemcpyHostToDevice, s_in));
+        }
+        cudaEvent_t e_in = get_event(ctx), e_cmp = get_event(ctx);
+        evs.push_back(e_in); evs.push_back(e_cmp);
+        CU(cudaEventRecord(e_in, s_in));
+        CU(cudaStreamWaitEvent(s_cmp, e_in, 0));
+        rc = syn_enqueue_range(s, s_cmp, b[B_MAG].p, b[B_REAL].p, b[B_IMAG].p, MPB_F64, (const uint8_t*)d_need,
+                               (const float*)b[B_NOISE].p, n_noise, &d, (const int32_t*)d_runs, per_linear, s->out.p,
+                               MPB_F64, cvt_pitch, r);
+        if (rc != MPB_OK) break;
+        if (!hpf_sos) {
+            CU(cudaEventRecord(e_cmp, s_cmp));
+            CU(cudaStreamWaitEvent(s_out, e_cmp, 0));
+            if (r.out_b > r.out_a)
+                CU(cudaMemcpyAsync(out + r.out_a, (double*)s->out.p + r.out_a, sizeof(double) * (r.out_b - r.out_a),
+                                   cudaMemcpyDeviceToHost, s_out));
+        }
     }
-    CU(cudaMemcpyAsync(out, s->out.p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
-    const auto t4 = now();
-    CU(cudaStreamSynchronize(st));   // also keeps noise32 / runs alive until the copies are done
+    if (rc == MPB_OK && hpf_sos) {   // output high-pass (src/magphase.py:981-995) on the device, per utterance
+        rc = mpb_sos2_dev(ctx, s_cmp, s->out.p, MPB_F64, fr->utt_out_off, U, hpf_sos);
+        if (rc == MPB_OK) {
+            cudaError_t e = cudaMemcpyAsync(out, s->out.p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, s_cmp);
+            if (e != cudaSuccess) rc = fail(MPB_ERR_CUDA, cudaGetErrorString(e));
+        }
+    }
+    const auto t3 = now();
+    // drain every stage, also after an error: noise32 / runs / the staging blocks must outlive the copies
+    cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
+    for (auto e : evs) put_event(ctx, e);
+    if (rc != MPB_OK) return rc;
+    CU(e1); CU(e2); CU(e3);
+    if (mt_fin) {
+        memcpy(mt_key, mt_fin, sizeof(uint32_t) * 624);
+        *mt_pos = (int32_t)mt_fin[624];
+    }
     if (trace)
-        fprintf(stderr, "[mpb] synthesis_compressed_host: checks+runs %.3f ms, features+noise %.3f ms, descriptors %.3f ms, "
-                        "enqueue %.3f ms, drain %.3f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
+        fprintf(stderr, "[mpb] synthesis_compressed_host: %d groups, checks+runs %.3f ms, descriptors+noise %.3f ms, "
+                        "enqueue %.3f ms, drain %.3f ms\n", (int)rg.size(), ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, now()));
     return MPB_OK;
 }
 

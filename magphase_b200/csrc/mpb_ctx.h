@@ -1,7 +1,10 @@
 // Shared internals of the C-ABI translation units: context, scratch buffers, error plumbing.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
+#include <algorithm>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -63,7 +66,11 @@ struct KernelTimer {   // optional per-kernel CUDA-event timing (mpb_profile_beg
 struct mpb_ctx {
     int device = 0;
     int num_sms = 0;
-    cudaStream_t stream = nullptr;                 // used by the *_host entry points
+    cudaStream_t stream = nullptr;                 // used by the *_host entry points (compute)
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;   // host->device / device->host copies of the pipelined entry points
+    std::vector<cudaEvent_t> ev_pool;              // timing-disabled events (pipeline hand-offs)
+    PinnedBuf desc_stage;                          // page-locked staging of descriptor arrays
+    PinnedBuf mt_fin;                              // page-locked landing zone of the MT19937 state read-back
     std::map<int, void*> tw32, tw64;               // fft_len -> twiddle table exp(-2 pi i j / N), j < N/2
     std::mutex mu;                                 // serialises the *_host entry points (shared scratch)
     std::mutex tw_mu;
@@ -74,6 +81,25 @@ struct mpb_ctx {
     PinnedBuf stage;                               // float32 staging of host signals (upload_signals)
     KernelTimer timer;
 };
+
+// timing-disabled events for the stage hand-offs of the pipelined *_host entry points (callers hold ctx->mu)
+inline cudaEvent_t get_event(mpb_ctx* ctx) {
+    if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return e;
+}
+inline void put_event(mpb_ctx* ctx, cudaEvent_t e) { if (e) ctx->ev_pool.push_back(e); }
+
+// number of utterance groups the pipelined *_host entry points cut a batch into (MPB_PIPELINE_GROUPS, default 4)
+inline int pipeline_groups() {
+    static const int n = [] {
+        const char* e = getenv("MPB_PIPELINE_GROUPS");
+        const int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : (v > 64 ? 64 : v);
+    }();
+    return n;
+}
 
 // Launch `expr` (returns cudaError_t) on stream `st`, bracketed by events when profiling is on.
 #define LAUNCH(ctx, st, kname, expr)                                                           \
@@ -97,7 +123,14 @@ int analysis_common(mpb_ctx* ctx, void* stream, const void* sig, int sig_dtype, 
 // samples could be narrowed exactly on the host (mpb_stage.cu), else MPB_F64.  Caller synchronises st before returning.
 int upload_signals(mpb_ctx* ctx, cudaStream_t st, const double* const* sigs, const int64_t* lens, int32_t n_sigs,
                    void* dev, int* out_dtype);
+// Same, group by group (see mpb_stage.cu): float32 groups land in dev_f32, others in dev_f64, both at absolute sample
+// offsets; on_group(g, dtype) runs on the calling thread right after the group's last copy has been enqueued.
+int upload_signal_groups(mpb_ctx* ctx, cudaStream_t st, const double* const* sigs, const int64_t* lens, int32_t n_sigs,
+                         const int32_t* group_end, int32_t n_groups, void* dev_f32, void* dev_f64,
+                         const std::function<int(int32_t, int)>& on_group);
 int host_threads();
+int mt19937_enqueue(mpb_ctx* ctx, cudaStream_t st, const uint32_t* key, int32_t pos, int64_t n, double low, double high,
+                    void* out_dev, int out_dtype, uint32_t* fin625);
 int check_frames_host(const int64_t* centre, const int32_t* left, const int32_t* right, int64_t nfrm,
                       int64_t n_sig, int fft_len);
 }

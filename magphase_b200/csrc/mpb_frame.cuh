@@ -130,8 +130,8 @@ __device__ __forceinline__ void load_frame(const TS* __restrict__ sig, int64_t n
         if ((ks & 1) && ks - 1 > q_eff) bufT[2 * G::nphys(ks >> 1)] = (T)0;
     }
     __syncthreads();
-#pragma unroll
     const cx<T>* pk = buf + G::nphys(t);
+#pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
         const int m = n1 * G::S1 + t;
         const bool nz = whole || (2 * m <= q_eff) || (2 * m + 1 >= N - l);

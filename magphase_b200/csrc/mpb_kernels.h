@@ -74,7 +74,8 @@ struct UnwarpArgs {
     float* out_mag; float* out_real; float* out_imag;                               // [nfrm][HP], [nfrm][HBP] x2
     int HP; int HBP;                                                                // row pitches (multiples of 4 floats)
     uint8_t* flags;                                                                 // scratch: ceil(nfrm / 64) bytes
-    float* cvt; size_t cvt_pitch;                                                   // in_dtype F64: 3 x cvt_pitch floats of scratch
+    float* cvt; size_t cvt_pitch;                                                   // in_dtype F64: 3 x cvt_pitch floats of scratch;
+    size_t cvt_off_mag, cvt_off_ph;                                                 //   float offsets (multiples of 4) inside each matrix
     int num_sms;
 };
 cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st);
@@ -90,6 +91,7 @@ struct SynthCompArgs {
     double* inv_gain;                                                               // [n_utt][2] scratch
     const float* tab;                                                               // [3][H]: P, Av, Au
     const int64_t* utt_out_off; const int32_t* utt_t0; int32_t n_utt;
+    int32_t utt_a, utt_b;                                                           // utterances whose gains this call computes
     const OlaRun* runs; int32_t n_runs; int64_t nfrm;
     int fft_len; int per_linear;
     const void* tw;                                                                 // float32 twiddles

@@ -112,64 +112,88 @@ inline bool narrow_exact(const double* __restrict__ src, float* __restrict__ dst
 
 int host_threads() { return HostPool::get().size(); }
 
-// Uploads the virtual concatenation sigs[0] | sigs[1] | ... (HOST float64) into dev (>= 8 * n_sig bytes) on stream st.
-// *out_dtype = MPB_F32 when every sample is exactly representable in float32 (narrowed on the host, half the PCIe
-// bytes), else MPB_F64.  The copies are asynchronous; the staging buffer is reused by the next call on this ctx, so the
-// caller synchronises st before returning to its own caller (all *_host entry points do).
-int upload_signals(mpb_ctx* ctx, cudaStream_t st, const double* const* sigs, const int64_t* lens, int32_t n_sigs,
-                   void* dev, int* out_dtype) {
+// Uploads the virtual concatenation sigs[0] | sigs[1] | ... (HOST float64) on stream st, GROUP by group (group_end[g] =
+// one past the last signal of group g; groups are contiguous and ordered).  A group whose samples are all exactly
+// representable in float32 is narrowed on the host into the page-locked staging buffer and lands in dev_f32 (absolute
+// sample offsets); any other group is uploaded as float64 into dev_f64.  As soon as the last copy of a group has been
+// enqueued, on_group(g, dtype) runs on the calling thread -- the caller records its event there and enqueues the
+// group's kernels while the pool is still narrowing the next group.  The copies are asynchronous and the staging
+// buffer is reused by the next call on this ctx: the caller synchronises before returning to its own caller.
+int upload_signal_groups(mpb_ctx* ctx, cudaStream_t st, const double* const* sigs, const int64_t* lens, int32_t n_sigs,
+                         const int32_t* group_end, int32_t n_groups, void* dev_f32, void* dev_f64,
+                         const std::function<int(int32_t, int)>& on_group) {
     int64_t n_sig = 0;
     for (int32_t i = 0; i < n_sigs; ++i) n_sig += lens[i];
-    *out_dtype = MPB_F64;
-    if (n_sig == 0) return MPB_OK;
-    PinnedBuf& pb = ctx->stage;
-    bool exact = false;
     static const bool trace = getenv("MPB_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
-    if (pb.need(sizeof(float) * (size_t)n_sig) == cudaSuccess) {
-        // chunks of <= CH samples that never straddle two utterances
-        constexpr int64_t CH = 1 << 18;
-        struct Chunk { const double* src; int64_t off, n; };
-        std::vector<Chunk> ch;
-        int64_t off = 0;
+    PinnedBuf& pb = ctx->stage;
+    const bool have_stage = n_sig > 0 && pb.need(sizeof(float) * (size_t)n_sig) == cudaSuccess;
+    if (!have_stage) cudaGetLastError();      // no page-locked memory to be had: plain float64 path for every group
+    // chunks of <= CH samples that never straddle two utterances
+    constexpr int64_t CH = 1 << 18;
+    struct Chunk { const double* src; int64_t off, n; int32_t group; bool last_of_group; };
+    std::vector<Chunk> ch;
+    std::vector<int64_t> sig_off((size_t)n_sigs + 1, 0);
+    {
+        int32_t g = 0;
         for (int32_t i = 0; i < n_sigs; ++i) {
-            for (int64_t a = 0; a < lens[i]; a += CH) {
+            while (g < n_groups - 1 && i >= group_end[g]) ++g;
+            sig_off[i + 1] = sig_off[i] + lens[i];
+            for (int64_t a = 0; a < lens[i] || (a == 0 && lens[i] == 0); a += CH) {
                 const int64_t n = lens[i] - a < CH ? lens[i] - a : CH;
-                ch.push_back({sigs[i] + a, off + a, n});
+                ch.push_back({sigs[i] + a, sig_off[i] + a, n, g, false});
+                if (lens[i] == 0) break;
             }
-            off += lens[i];
         }
-        float* h = (float*)pb.p;
-        std::atomic<int> inexact{0};
-        cudaError_t cerr = cudaSuccess;
-        HostPool::get().run(
-            (int)ch.size(),
-            [&](int c) {
-                if (inexact.load(std::memory_order_relaxed)) return;
-                if (!narrow_exact(ch[c].src, h + ch[c].off, ch[c].n)) inexact.store(1);
-            },
-            [&](int c) {
-                if (inexact.load() || cerr != cudaSuccess) return;
-                cerr = cudaMemcpyAsync((float*)dev + ch[c].off, h + ch[c].off, sizeof(float) * ch[c].n,
-                                       cudaMemcpyHostToDevice, st);
-            });
-        if (cerr != cudaSuccess) return fail(MPB_ERR_CUDA, std::string("signal upload: ") + cudaGetErrorString(cerr));
-        exact = !inexact.load();
-        if (trace)
-            fprintf(stderr, "[mpb] upload_signals: %lld samples, %d chunks, %d threads, narrow+issue %.3f ms, exact=%d\n",
-                    (long long)n_sig, (int)ch.size(), HostPool::get().size(),
-                    1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(), (int)exact);
-    } else {
-        cudaGetLastError();      // no page-locked memory to be had: fall through to the plain path
+        for (size_t c = 0; c < ch.size(); ++c)
+            ch[c].last_of_group = c + 1 == ch.size() || ch[c + 1].group != ch[c].group;
     }
-    if (exact) { *out_dtype = MPB_F32; return MPB_OK; }
-    // float64 upload; stream order puts it after any float32 chunk already issued into the same buffer
-    int64_t off = 0;
-    for (int32_t i = 0; i < n_sigs; ++i) {
-        CU(cudaMemcpyAsync((double*)dev + off, sigs[i], sizeof(double) * lens[i], cudaMemcpyHostToDevice, st));
-        off += lens[i];
-    }
-    return MPB_OK;
+    float* h = (float*)pb.p;
+    std::vector<std::atomic<int>> inexact((size_t)n_groups);
+    for (auto& x : inexact) x.store(have_stage ? 0 : 1);
+    int rc = MPB_OK;
+    size_t c_first = 0;                          // first chunk of the group currently being issued
+    HostPool::get().run(
+        (int)ch.size(),
+        [&](int c) {
+            const Chunk& k = ch[c];
+            if (inexact[k.group].load(std::memory_order_relaxed)) return;
+            if (!narrow_exact(k.src, h + k.off, k.n)) inexact[k.group].store(1);
+        },
+        [&](int c) {
+            if (rc != MPB_OK) return;
+            const Chunk& k = ch[c];
+            cudaError_t e = cudaSuccess;
+            // optimistic: a narrowed chunk goes out at once (its group may still turn out inexact; then the float64
+            // copies below supersede it -- in dev_f64, or later in stream order when both are the same buffer)
+            if (k.n > 0 && !inexact[k.group].load())
+                e = cudaMemcpyAsync((float*)dev_f32 + k.off, h + k.off, sizeof(float) * k.n, cudaMemcpyHostToDevice, st);
+            if (k.last_of_group && e == cudaSuccess) {
+                const bool f32 = !inexact[k.group].load();
+                if (!f32)
+                    for (size_t j = c_first; j <= (size_t)c && e == cudaSuccess; ++j)
+                        if (ch[j].n > 0)
+                            e = cudaMemcpyAsync((double*)dev_f64 + ch[j].off, ch[j].src, sizeof(double) * ch[j].n,
+                                                cudaMemcpyHostToDevice, st);
+                c_first = (size_t)c + 1;
+                if (e == cudaSuccess) { rc = on_group(k.group, f32 ? MPB_F32 : MPB_F64); return; }
+            }
+            if (e != cudaSuccess) rc = fail(MPB_ERR_CUDA, std::string("signal upload: ") + cudaGetErrorString(e));
+        });
+    if (trace)
+        fprintf(stderr, "[mpb] upload_signal_groups: %lld samples, %d chunks, %d groups, %d threads, %.3f ms\n",
+                (long long)n_sig, (int)ch.size(), (int)n_groups, HostPool::get().size(),
+                1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
+    return rc;
+}
+
+// One group: everything in dev (>= 8 bytes per sample); *out_dtype says how it was uploaded.
+int upload_signals(mpb_ctx* ctx, cudaStream_t st, const double* const* sigs, const int64_t* lens, int32_t n_sigs,
+                   void* dev, int* out_dtype) {
+    *out_dtype = MPB_F64;
+    const int32_t end = n_sigs;
+    return upload_signal_groups(ctx, st, sigs, lens, n_sigs, &end, 1, dev, dev,
+                                [&](int32_t, int dtype) { *out_dtype = dtype; return MPB_OK; });
 }
 
 }  // namespace mpb

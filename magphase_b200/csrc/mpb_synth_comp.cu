@@ -20,10 +20,11 @@ namespace mpb {
 
 // one warp per utterance, fixed summation order -> bit-reproducible gains
 __global__ void k_noise_gain(const double* __restrict__ logsq, const uint8_t* __restrict__ voi,
-                             const int64_t* __restrict__ utt_frm_off, int n_utt, int H, double* __restrict__ inv_gain) {
-    const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                             const int64_t* __restrict__ utt_frm_off, int utt_a, int utt_b, int H,
+                             double* __restrict__ inv_gain) {
+    const int u = utt_a + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (u >= n_utt) return;
+    if (u >= utt_b) return;
     double sv = 0.0, su = 0.0;
     long long nv = 0, nu = 0;
     for (int64_t f = utt_frm_off[u] + lane; f < utt_frm_off[u + 1]; f += 32) {
@@ -44,8 +45,9 @@ __global__ void k_noise_gain(const double* __restrict__ logsq, const uint8_t* __
 }
 
 cudaError_t launch_noise_gain(const SynthCompArgs& a, cudaStream_t st) {
-    if (a.n_utt < 1) return cudaSuccess;
-    k_noise_gain<<<(a.n_utt + 3) / 4, 128, 0, st>>>(a.logsq, a.voi, a.utt_frm_off, a.n_utt, a.fft_len / 2 + 1, a.inv_gain);
+    const int n = a.utt_b - a.utt_a;
+    if (n < 1) return cudaSuccess;
+    k_noise_gain<<<(n + 3) / 4, 128, 0, st>>>(a.logsq, a.voi, a.utt_frm_off, a.utt_a, a.utt_b, a.fft_len / 2 + 1, a.inv_gain);
     return cudaGetLastError();
 }
 
@@ -257,10 +259,8 @@ static cudaError_t launch_sc_n(const SynthCompArgs& a, cudaStream_t st) {
     return cudaErrorInvalidValue;
 }
 
+// (the caller has zeroed the output samples of the utterances behind a.runs: run boundaries are combined with atomicAdd)
 cudaError_t launch_synthesis_compressed(const SynthCompArgs& a, cudaStream_t st) {
-    const size_t esz = a.out_dtype == MPB_F64 ? 8 : 4;
-    cudaError_t e = cudaMemsetAsync(a.out, 0, esz * (size_t)a.n_out, st);
-    if (e != cudaSuccess) return e;
     return a.out_dtype == MPB_F64 ? launch_sc_n<double>(a, st) : launch_sc_n<float>(a, st);
 }
 

@@ -166,11 +166,13 @@ cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st) {
     const float *xm = (const float*)a.mag_mel, *xr = (const float*)a.real_mel, *xi = (const float*)a.imag_mel;
     if (a.in_dtype == MPB_F64) {
         const size_t nm = (size_t)a.nfrm * a.n_mag, np_ = (size_t)a.nfrm * a.n_ph;
-        float* c = a.cvt;
-        k_convert<double, float><<<(unsigned)((nm + 255) / 256), 256, 0, st>>>((const double*)a.mag_mel, c, nm);
-        k_convert<double, float><<<(unsigned)((np_ + 255) / 256), 256, 0, st>>>((const double*)a.real_mel, c + a.cvt_pitch, np_);
-        k_convert<double, float><<<(unsigned)((np_ + 255) / 256), 256, 0, st>>>((const double*)a.imag_mel, c + 2 * a.cvt_pitch, np_);
-        xm = c; xr = c + a.cvt_pitch; xi = c + 2 * a.cvt_pitch;
+        float* cm = a.cvt + a.cvt_off_mag;
+        float* cr = a.cvt + a.cvt_pitch + a.cvt_off_ph;
+        float* ci = a.cvt + 2 * a.cvt_pitch + a.cvt_off_ph;
+        k_convert<double, float><<<(unsigned)((nm + 255) / 256), 256, 0, st>>>((const double*)a.mag_mel, cm, nm);
+        k_convert<double, float><<<(unsigned)((np_ + 255) / 256), 256, 0, st>>>((const double*)a.real_mel, cr, np_);
+        k_convert<double, float><<<(unsigned)((np_ + 255) / 256), 256, 0, st>>>((const double*)a.imag_mel, ci, np_);
+        xm = cm; xr = cr; xi = ci;
     }
     const int64_t n_ft = (a.nfrm + UW_FT - 1) / UW_FT;
     k_unwarp_tile_flags<<<(unsigned)((n_ft + 3) / 4), 128, 0, st>>>(a.need_ph, a.nfrm, a.flags);
