@@ -222,7 +222,7 @@ def main():
     if a.cpu_dur == 0.0:
         a.cpu_dur = 2.0 if comp else a.dur     # the reference's compressed synthesis runs at ~70 frames/s/core
     if a.e2e_utts == 0:
-        a.e2e_utts = 32 if comp else 8
+        a.e2e_utts = 128 if comp else 8
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -367,11 +367,14 @@ def main():
     if comp:
         feat_bytes = 8 * sum(o[0].size + o[1].size + o[2].size for o in outs)
         n_noise = sum(y.size for y in ys)      # ~ one noise sample per output sample
-        h2d = 8 * n_smp + 17 * e_frames + feat_bytes + e_frames + 4 * n_noise + 45 * e_frames
-        d2h = feat_bytes + 8 * sum(y.size for y in ys)
+        # signals cross PCIe as float32 (PCM-exact samples are narrowed on the host, mpb_stage.cu); analysis descriptors
+        # 17 B/frame; features 8 B/value each way; synthesis descriptors 35 B/frame; the noise is drawn on the device
+        # (only the 2.5 KB MT19937 state travels)
+        h2d = 4 * n_smp + 17 * e_frames + feat_bytes + 35 * e_frames + 2500
+        d2h = feat_bytes + 8 * sum(y.size for y in ys) + 2500
     else:
         feat_bytes = 3 * 8 * sum(o[0].size for o in outs)
-        h2d = 8 * n_smp + 16 * e_frames + feat_bytes + 4 * e_frames
+        h2d = 4 * n_smp + 16 * e_frames + feat_bytes + 4 * e_frames
         d2h = feat_bytes + 8 * sum(y.size for y in ys)
 
     # ---- reduce over ranks: max time, summed frames ----
@@ -396,10 +399,10 @@ def main():
         'k_synthesis_lossless': 3 * nf * H * (8 if feat_dt == F64 else 4) + nf * 4 + getattr(plan, 'n_out', 0) * 4,
         'k_mel_gemm': 3 * nf * H * 4 + nf * 150 * 4,
         'k_mel_finish': nf * 150 * 4,
-        'k_mel_unwarp': nf * 150 * 4 + nf * H * 4 + 0.4 * nf * 2 * 513 * 4,
-        'k_analysis<noise_logsq>': getattr(plan, 'n_noise', 0) * 4 + nf * 25,
+        'k_mel_unwarp': nf * 150 * 4 + nf * H * 4 + 0.4 * nf * 2 * 512 * 4,
+        'k_analysis<noise_logsq>': getattr(plan, 'n_noise', 0) * 4 + nf * 25 + nf * (H + 1) * 8,      # + stored noise spectra
         'k_noise_gain': nf * 9,
-        'k_synthesis_compressed': nf * H * 4 + 0.4 * nf * 2 * 513 * 4 + getattr(plan, 'n_noise', 0) * 4 + nf * 45
+        'k_synthesis_compressed': nf * (H + 1) * 8 + nf * H * 4 + 0.4 * nf * 2 * 512 * 4 + nf * 45
                                   + getattr(plan, 'n_out', 0) * 4,
     }
     traffic_pf, traffic_src = {}, None

@@ -301,6 +301,22 @@ int mpb_sos2_dev(mpb_ctx* ctx, void* stream, void* x, int dtype, const int64_t* 
                  const double* sos);
 int mpb_sos2_host(mpb_ctx* ctx, double* x, const int64_t* utt_off, int32_t n_utt, const double* sos);
 
+/* ---- batch bookkeeping on the host (integer arithmetic, no CUDA) ---------------------------- */
+/*
+ * The reference's per-utterance NumPy bookkeeping for a whole batch in one pass; exp()/log() stay with the caller.
+ * mpb_analysis_geometry: windowing() frame geometry (src/magphase.py:74-84, 112-117) + the argument of the log in
+ * format_for_modelling (voi * medfilt3(voi_in * fs / shift), :2198-2207, :2499-2501).
+ * mpb_syn_geometry: the per-frame / per-utterance arrays of mpb_syn_frames for variable-rate synthesis_from_compressed
+ * (:879-896 noise frames, :968-971 anti-ringing windows, ola() :34-62); ns_len[u] = noise samples of utterance u.
+ */
+int mpb_analysis_geometry(const int64_t* pm_rounded, const int64_t* utt_frm_off, const int64_t* n_smpls, int32_t n_utt,
+                          const double* voi_in, double fs, int64_t* centre, int32_t* left, int32_t* right,
+                          double* f0_med, uint8_t* voi8);
+int mpb_syn_geometry(const int64_t* shift_trunc, const uint8_t* voi, const int64_t* utt_frm_off, int32_t n_utt,
+                     int fft_len, int b_voi_ap_win, int32_t* pm, int64_t* ncentre, int32_t* nleft, int32_t* nright,
+                     uint8_t* nkind, int32_t* win_a, int32_t* win_b, int32_t* row0, int64_t* utt_out_off,
+                     int32_t* utt_t0, int64_t* ns_len);
+
 /* ---- NumPy legacy random stream ------------------------------------------------------------- */
 /*
  * n draws of np.random.uniform(low, high) from NumPy's global legacy MT19937 stream, generated on the device

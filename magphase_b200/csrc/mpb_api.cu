@@ -70,6 +70,7 @@ int mpb_create(int device, mpb_ctx** out_ctx) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->stream_out, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->stream_aux, cudaStreamNonBlocking));
     *out_ctx = c;
     return MPB_OK;
 }
@@ -87,6 +88,7 @@ int mpb_destroy(mpb_ctx* ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
     if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
+    if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MPB_OK;
@@ -428,14 +430,18 @@ int mpb_min_phase_host(mpb_ctx* ctx, const double* mag, int64_t nfrm, int fft_le
 // ---------------------------------------------------------------------------------------------
 }  // extern "C"
 
-// Enqueues n draws of np.random.uniform(low, high) from the state (key[624], pos) on `stream` and an asynchronous
-// read-back of the final state (624 key words + position) into fin625, which must be PAGE-LOCKED host memory; nothing
-// is synchronised.  Internal building block of the pipelined synthesis entry point.
-int mpb::mt19937_enqueue(mpb_ctx* ctx, cudaStream_t st, const uint32_t* key, int32_t pos, int64_t n, double low, double high,
-                         void* out_dev, int out_dtype, uint32_t* fin625) {
+// Enqueues sum(part_n) draws of np.random.uniform(low, high) from the state (key[624], pos) on `st`, part by part
+// (part p fills out_dev[sum(part_n[0..p)) ...]; part_done[p], when given, is recorded after it), and an asynchronous
+// read-back of the final state (624 key words + position) into fin625, which must be PAGE-LOCKED host memory.  Nothing
+// is synchronised: the position after each part follows from the counts alone.  Building block of the pipelined
+// synthesis entry point.
+int mpb::mt19937_enqueue(mpb_ctx* ctx, cudaStream_t st, const uint32_t* key, int32_t pos, const int64_t* part_n, int n_parts,
+                         double low, double high, void* out_dev, int out_dtype, uint32_t* fin625, cudaEvent_t* part_done) {
+    int64_t n = 0;
+    for (int p = 0; p < n_parts; ++p) n += part_n[p];
     DevBuf* b = ctx->scratch;
     CU(b[9].need(sizeof(uint32_t) * 2 * 625));
-    CU(b[10].need(sizeof(uint32_t) * 2 * (size_t)n));
+    CU(b[10].need(sizeof(uint32_t) * 2 * (size_t)(n > 0 ? n : 1)));
     const uint16_t* d_jump = nullptr;
     if (mt19937_needs_jump(pos, n)) {             // more than one segment: jump polynomials (built once per process)
         if (!ctx->mt_jump_ready) {
@@ -451,10 +457,26 @@ int mpb::mt19937_enqueue(mpb_ctx* ctx, cudaStream_t st, const uint32_t* key, int
     uint32_t* d_state = (uint32_t*)b[9].p;
     CU(cudaMemcpyAsync(d_state, key, sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
     int slot = 0;
-    LAUNCH(ctx, st, "k_mt19937_stream+k_mt_to_uniform",
-           launch_mt19937_uniform(d_state, pos, &slot, d_jump, (uint32_t*)b[10].p, n, low, high, out_dev, out_dtype, st));
-    ctx->launches += 1;
-    CU(cudaMemcpyAsync(fin625, d_state + 625 * slot, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, st));
+    int64_t done = 0;
+    const size_t oes = out_dtype == MPB_F64 ? 8 : 4;
+    for (int p = 0; p < n_parts; ++p) {
+        if (part_n[p] > 0) {
+            LAUNCH(ctx, st, "k_mt19937_stream+k_mt_to_uniform",
+                   launch_mt19937_uniform(d_state, slot, pos, &slot, d_jump, (uint32_t*)b[10].p + 2 * done, part_n[p], low,
+                                          high, (char*)out_dev + oes * done, out_dtype, st));
+            ctx->launches += 1;
+            const int64_t last = (int64_t)pos + 2 * part_n[p] - 1;           // stream index of the last consumed word
+            pos = (int32_t)(last + 1 - (last / 624) * 624);
+            done += part_n[p];
+        }
+        if (part_done) CU(cudaEventRecord(part_done[p], st));
+    }
+    if (n > 0) {
+        CU(cudaMemcpyAsync(fin625, d_state + 625 * slot, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, st));
+    } else {
+        memcpy(fin625, key, sizeof(uint32_t) * 624);
+        fin625[624] = (uint32_t)pos;
+    }
     return MPB_OK;
 }
 
@@ -472,7 +494,7 @@ int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* 
     cudaStream_t st = (cudaStream_t)stream;
     CU(ctx->mt_fin.need(sizeof(uint32_t) * 625));
     uint32_t* fin = (uint32_t*)ctx->mt_fin.p;
-    int rc = mt19937_enqueue(ctx, st, key, *pos, n, low, high, out_dev, out_dtype, fin);
+    int rc = mt19937_enqueue(ctx, st, key, *pos, &n, 1, low, high, out_dev, out_dtype, fin, nullptr);
     if (rc != MPB_OK) return rc;
     CU(cudaStreamSynchronize(st));
     memcpy(key, fin, sizeof(uint32_t) * 624);

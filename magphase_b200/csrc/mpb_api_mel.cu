@@ -280,7 +280,7 @@ int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const i
     cudaStream_t s_in = ctx->stream_in, s_cmp = ctx->stream, s_out = ctx->stream_out;
 
     // ---- groups of whole utterances with about the same number of frames (frames never straddle utterances) ----
-    int n_groups = pipeline_groups();
+    int n_groups = pipeline_groups(nfrm, 5000, 8);
     if (n_groups > n_sigs) n_groups = n_sigs;
     std::vector<int32_t> group_end((size_t)n_groups);          // one past the last signal of the group
     std::vector<int64_t> group_frm((size_t)n_groups + 1, 0);   // frame range of the group

@@ -247,7 +247,7 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
 
     // ---- groups of whole utterances with about the same number of frames; constant-rate input (frames address
     // arbitrary feature rows) and the output high-pass (a per-utterance scan that synchronises) run as one group ----
-    int n_groups = (identity_rows && !hpf_sos) ? pipeline_groups() : 1;
+    int n_groups = (identity_rows && !hpf_sos) ? pipeline_groups(F, 10000, 6) : 1;
     if (n_groups > U) n_groups = U > 0 ? U : 1;
     std::vector<SynRange> rg;
     {
@@ -277,14 +277,30 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
     std::lock_guard<std::mutex> lk2(s->mu);
     cudaStream_t s_in = ctx->stream_in, s_cmp = ctx->stream, s_out = ctx->stream_out;
     const auto t1 = now();
-
-    // ---- device buffers, all at their final size before anything is enqueued ----
     DevBuf* b = s->host_in;
     enum { B_MAG = 0, B_REAL, B_IMAG, B_NOISE, B_DESC };
+    CU(b[B_NOISE].need(sizeof(float) * (size_t)(n_noise > 0 ? n_noise : 1)));
+    // ---- the NumPy noise stream goes first, on its own stream: the twister is latency bound (a few SMs), so it runs
+    // under the descriptor packing and the first feature upload; the first group's kernels wait for e_rng ----
+    uint32_t* mt_fin = nullptr;
+    std::vector<cudaEvent_t> e_rng;
+    if (!noise && n_noise > 0) {
+        CU(ctx->mt_fin.need(sizeof(uint32_t) * 625));
+        mt_fin = (uint32_t*)ctx->mt_fin.p;
+        e_rng.push_back(get_event(ctx));
+        rc = mt19937_enqueue(ctx, ctx->stream_aux, mt_key, *mt_pos, &n_noise, 1, -1.0, 1.0, b[B_NOISE].p, MPB_F32, mt_fin,
+                             e_rng.data());
+        if (rc != MPB_OK) {
+            cudaStreamSynchronize(ctx->stream_aux);
+            for (auto e : e_rng) put_event(ctx, e);
+            return rc;
+        }
+    }
+
+    // ---- device buffers, all at their final size before anything is enqueued ----
     CU(b[B_MAG].need(sizeof(double) * (size_t)n_rows * s->n_mag + 16));
     CU(b[B_REAL].need(sizeof(double) * (size_t)n_rows * s->n_ph + 16));
     CU(b[B_IMAG].need(sizeof(double) * (size_t)n_rows * s->n_ph + 16));
-    CU(b[B_NOISE].need(sizeof(float) * (size_t)(n_noise > 0 ? n_noise : 1)));
     CU(s->out.need(sizeof(double) * (size_t)n_out));
     size_t cvt_pitch = 0;
     rc = syn_reserve(s, MPB_F64, n_rows, F, U, (int)rg.size(), &cvt_pitch);
@@ -329,16 +345,10 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
 
     // ---- noise: explicit samples (narrowed on the host, uploaded) or the NumPy stream advanced on the device ----
     std::vector<float> noise32;
-    uint32_t* mt_fin = nullptr;
     if (noise) {
         noise32.resize((size_t)n_noise);
         for (int64_t i = 0; i < n_noise; ++i) noise32[i] = (float)noise[i];
         if (n_noise) CU(cudaMemcpyAsync(b[B_NOISE].p, noise32.data(), sizeof(float) * n_noise, cudaMemcpyHostToDevice, s_in));
-    } else if (n_noise > 0) {
-        CU(ctx->mt_fin.need(sizeof(uint32_t) * 625));
-        mt_fin = (uint32_t*)ctx->mt_fin.p;
-        rc = mt19937_enqueue(ctx, s_cmp, mt_key, *mt_pos, n_noise, -1.0, 1.0, b[B_NOISE].p, MPB_F32, mt_fin);
-        if (rc != MPB_OK) { cudaStreamSynchronize(s_cmp); cudaStreamSynchronize(s_in); return rc; }
     }
     const auto t2 = now();
 
@@ -358,11 +368,14 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
         evs.push_back(e_in); evs.push_back(e_cmp);
         CU(cudaEventRecord(e_in, s_in));
         CU(cudaStreamWaitEvent(s_cmp, e_in, 0));
+        if (!e_rng.empty() && r.ordinal == 0) CU(cudaStreamWaitEvent(s_cmp, e_rng[0], 0));
         rc = syn_enqueue_range(s, s_cmp, b[B_MAG].p, b[B_REAL].p, b[B_IMAG].p, MPB_F64, (const uint8_t*)d_need,
                                (const float*)b[B_NOISE].p, n_noise, &d, (const int32_t*)d_runs, per_linear, s->out.p,
                                MPB_F64, cvt_pitch, r);
         if (rc != MPB_OK) break;
         if (!hpf_sos) {
+            // (float64 on the wire: narrowing the waveform to float32 for PCIe and widening it again on the host was
+            // measured slower -- the widening pass costs more host memory bandwidth than the DMA engine saves)
             CU(cudaEventRecord(e_cmp, s_cmp));
             CU(cudaStreamWaitEvent(s_out, e_cmp, 0));
             if (r.out_b > r.out_a)
@@ -370,6 +383,7 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
                                    cudaMemcpyDeviceToHost, s_out));
         }
     }
+    const auto t3 = now();
     if (rc == MPB_OK && hpf_sos) {   // output high-pass (src/magphase.py:981-995) on the device, per utterance
         rc = mpb_sos2_dev(ctx, s_cmp, s->out.p, MPB_F64, fr->utt_out_off, U, hpf_sos);
         if (rc == MPB_OK) {
@@ -377,12 +391,13 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
             if (e != cudaSuccess) rc = fail(MPB_ERR_CUDA, cudaGetErrorString(e));
         }
     }
-    const auto t3 = now();
     // drain every stage, also after an error: noise32 / runs / the staging blocks must outlive the copies
     cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
+    cudaError_t e4 = cudaStreamSynchronize(ctx->stream_aux);
     for (auto e : evs) put_event(ctx, e);
+    for (auto e : e_rng) put_event(ctx, e);
     if (rc != MPB_OK) return rc;
-    CU(e1); CU(e2); CU(e3);
+    CU(e1); CU(e2); CU(e3); CU(e4);
     if (mt_fin) {
         memcpy(mt_key, mt_fin, sizeof(uint32_t) * 624);
         *mt_pos = (int32_t)mt_fin[624];

@@ -68,6 +68,7 @@ struct mpb_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;                 // used by the *_host entry points (compute)
     cudaStream_t stream_in = nullptr, stream_out = nullptr;   // host->device / device->host copies of the pipelined entry points
+    cudaStream_t stream_aux = nullptr;             // the MT19937 noise stream runs here, beside the compute stream
     std::vector<cudaEvent_t> ev_pool;              // timing-disabled events (pipeline hand-offs)
     PinnedBuf desc_stage;                          // page-locked staging of descriptor arrays
     PinnedBuf mt_fin;                              // page-locked landing zone of the MT19937 state read-back
@@ -91,14 +92,18 @@ inline cudaEvent_t get_event(mpb_ctx* ctx) {
 }
 inline void put_event(mpb_ctx* ctx, cudaEvent_t e) { if (e) ctx->ev_pool.push_back(e); }
 
-// number of utterance groups the pipelined *_host entry points cut a batch into (MPB_PIPELINE_GROUPS, default 4)
-inline int pipeline_groups() {
-    static const int n = [] {
+// number of utterance groups the pipelined *_host entry points cut a batch of nfrm frames into: about one group per
+// `frames_per_group` frames, at most `max_groups` (MPB_PIPELINE_GROUPS overrides).  Smaller groups shorten the fill and
+// drain of the pipeline, larger ones keep the persistent kernels' grids full.
+inline int pipeline_groups(int64_t nfrm, int64_t frames_per_group, int max_groups) {
+    static const int forced = [] {
         const char* e = getenv("MPB_PIPELINE_GROUPS");
-        const int v = e ? atoi(e) : 4;
-        return v < 1 ? 1 : (v > 64 ? 64 : v);
+        const int v = e ? atoi(e) : 0;
+        return v < 0 ? 0 : (v > 64 ? 64 : v);
     }();
-    return n;
+    if (forced) return forced;
+    const int64_t n = (nfrm + frames_per_group / 2) / frames_per_group;
+    return (int)(n < 1 ? 1 : (n > max_groups ? max_groups : n));
 }
 
 // Launch `expr` (returns cudaError_t) on stream `st`, bracketed by events when profiling is on.
@@ -129,8 +134,8 @@ int upload_signal_groups(mpb_ctx* ctx, cudaStream_t st, const double* const* sig
                          const int32_t* group_end, int32_t n_groups, void* dev_f32, void* dev_f64,
                          const std::function<int(int32_t, int)>& on_group);
 int host_threads();
-int mt19937_enqueue(mpb_ctx* ctx, cudaStream_t st, const uint32_t* key, int32_t pos, int64_t n, double low, double high,
-                    void* out_dev, int out_dtype, uint32_t* fin625);
+int mt19937_enqueue(mpb_ctx* ctx, cudaStream_t st, const uint32_t* key, int32_t pos, const int64_t* part_n, int n_parts,
+                    double low, double high, void* out_dev, int out_dtype, uint32_t* fin625, cudaEvent_t* part_done);
 int check_frames_host(const int64_t* centre, const int32_t* left, const int32_t* right, int64_t nfrm,
                       int64_t n_sig, int fft_len);
 }

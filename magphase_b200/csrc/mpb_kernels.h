@@ -116,11 +116,11 @@ cudaError_t launch_sos2(void* x, int dtype, const int64_t* utt_off, const int64_
 
 // ---- NumPy legacy MT19937 stream on the device (mpb_rng.cu) ----
 // n draws of uniform(low, high).  state_dev: 2 x 625 words of device scratch (624-word key + position word, ping-pong)
-// with the handed key in the first half; *final_slot tells which half holds the final state.  jump_idx_dev: device copy
+// with the handed key in half slot_in; *final_slot tells which half holds the final state.  jump_idx_dev: device copy
 // of mt19937_jump_table_host(), required when mt19937_needs_jump(pos, n) (the draw spans more than one segment).
-cudaError_t launch_mt19937_uniform(uint32_t* state_dev, int32_t pos_host, int* final_slot, const uint16_t* jump_idx_dev,
-                                   uint32_t* raw_dev, int64_t n, double low, double high, void* out, int out_dtype,
-                                   cudaStream_t st);
+cudaError_t launch_mt19937_uniform(uint32_t* state_dev, int slot_in, int32_t pos_host, int* final_slot,
+                                   const uint16_t* jump_idx_dev, uint32_t* raw_dev, int64_t n, double low, double high,
+                                   void* out, int out_dtype, cudaStream_t st);
 bool mt19937_needs_jump(int32_t pos, int64_t n);
 const uint16_t* mt19937_jump_table_host(size_t* n_entries);
 int mt19937_jump_poly(int64_t n_words, uint32_t* out624);

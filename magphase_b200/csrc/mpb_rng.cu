@@ -341,13 +341,13 @@ size_t mt19937_jump_table_bytes() {
     return jt.ok ? jt.idx.size() * sizeof(uint16_t) : 0;
 }
 
-// n draws; state_dev: 2 x 625 words of device scratch (key + position, ping-pong), with the handed state in the first
-// 625 words; on return *final_slot tells which half holds the final state.  jump_idx_dev: the device copy of the
+// n draws; state_dev: 2 x 625 words of device scratch (key + position, ping-pong), with the handed state in half
+// slot_in; on return *final_slot tells which half holds the final state.  jump_idx_dev: the device copy of the
 // set-bit lists (mt19937_jump_tables_host), only needed when the draw spans more than one segment.
-cudaError_t launch_mt19937_uniform(uint32_t* state_dev, int32_t pos_host, int* final_slot, const uint16_t* jump_idx_dev,
-                                   uint32_t* raw_dev, int64_t n, double low, double high, void* out, int out_dtype,
-                                   cudaStream_t st) {
-    *final_slot = 0;
+cudaError_t launch_mt19937_uniform(uint32_t* state_dev, int slot_in, int32_t pos_host, int* final_slot,
+                                   const uint16_t* jump_idx_dev, uint32_t* raw_dev, int64_t n, double low, double high,
+                                   void* out, int out_dtype, cudaStream_t st) {
+    *final_slot = slot_in;
     if (n < 1) return cudaSuccess;
     static bool attr_done = false;
     const size_t smem = sizeof(uint32_t) * (MT_WIN_ALLOC + 4 * 768);
@@ -365,7 +365,7 @@ cudaError_t launch_mt19937_uniform(uint32_t* state_dev, int32_t pos_host, int* f
     int64_t left = 2 * n;                      // 32-bit words still to draw
     int64_t pos = pos_host;
     uint32_t* o = raw_dev;
-    int slot = 0;
+    int slot = slot_in;
     const int64_t per_launch = (int64_t)MT_MAX_SEGS * MT_SEG_WORDS;
     while (left > 0) {
         // words this launch consumes: everything, or exactly up to the end of its last segment

@@ -163,6 +163,41 @@ def _medfilt3_segments(v, off):
     return np.maximum(np.minimum(a, v), np.minimum(np.maximum(a, v), c))
 
 
+_WORKSPACE = {}
+
+
+def _workspace(name, n, dtype):
+    """Reusable scratch array (descriptor arrays that only live for the duration of one C call): fresh NumPy
+    allocations of this size are mmap-ed and page-faulted on every call."""
+    a = _WORKSPACE.get(name)
+    if a is None or a.size < n or a.dtype != np.dtype(dtype):
+        a = np.empty(max(int(n), 1024) * 5 // 4, dtype=dtype)
+        _WORKSPACE[name] = a
+    return a[:n]
+
+
+def _analysis_geometry_c(l_pm_smpls, l_n_smpls, l_voi, fs):
+    """batch_frame_geometry + shift_to_f0(b_smooth=False) + the argument of the log of _lf0_smoothed for a batch, in one
+    C pass (mpb_analysis_geometry; integer arithmetic, IEEE multiply / divide and a median of three).  Returns
+    (centre, left, right, voi8, f0_med, frm_off); everything except frm_off lives in the module workspace."""
+    lens = np.array([np.size(p) for p in l_pm_smpls], dtype=np.int64)
+    if np.any(lens == 0):
+        raise ValueError('every utterance needs at least one pitch mark')
+    if any(np.size(v) != k for v, k in zip(l_voi, lens)):
+        raise ValueError('voicing and pitch-mark arrays must have the same length')
+    off = _seg_offsets(lens)
+    n = int(off[-1])
+    pm = np.round(np.concatenate([np.asarray(p, dtype=np.float64) for p in l_pm_smpls])).astype(np.int64)   # round_to_int
+    voi_in = np.concatenate([np.asarray(v, dtype=np.float64) for v in l_voi])
+    n_smpls = np.ascontiguousarray(l_n_smpls, dtype=np.int64)
+    centre, left, right = _workspace('a_centre', n, np.int64), _workspace('a_left', n, np.int32), _workspace('a_right', n, np.int32)
+    f0_med, voi8 = _workspace('a_f0med', n, np.float64), _workspace('a_voi8', n, np.uint8)
+    _lib.check(_lib.lib().mpb_analysis_geometry(_lib.ptr(pm), _lib.ptr(off), _lib.ptr(n_smpls), len(lens), _lib.ptr(voi_in),
+                                                float(fs), _lib.ptr(centre), _lib.ptr(left), _lib.ptr(right),
+                                                _lib.ptr(f0_med), _lib.ptr(voi8)))
+    return centre, left, right, voi8, f0_med, off
+
+
 # ----------------------------------------------------------------------------------------------
 # analysis
 # ----------------------------------------------------------------------------------------------
@@ -478,21 +513,10 @@ def analysis_compressed_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None, mag_di
         return _analysis_compressed_const_rate(l_sig, fs, l_pm_smpls, l_voi, fft_len, mag_dim, phase_dim, alpha_phase)
     plan = _MelPlan.get(fs, fft_len, mag_dim, phase_dim, alpha_phase)
     sizes = [np.size(x) for x in l_sig]
-    sig_off = _seg_offsets(sizes)
-    pm, left64, right64, frm_off = batch_frame_geometry(l_pm_smpls, sizes)
-    _check_frames(left64, right64, fft_len)
-    nfr = np.diff(frm_off)
-    centre = np.ascontiguousarray(pm + np.repeat(sig_off[:-1], nfr))
-    left = left64.astype(np.int32)
-    right = right64.astype(np.int32)
-    voi_in = np.concatenate([np.asarray(v, dtype=np.float64) for v in l_voi])
-    if voi_in.size != pm.size or any(np.size(v) != k for v, k in zip(l_voi, nfr)):
-        raise ValueError('voicing and pitch-mark arrays must have the same length')
-    v_f0 = voi_in * fs / left64.astype('float64')                             # shift_to_f0(b_smooth=False)
-    v_voi = (v_f0 > 0).astype('float')                                        # _lf0_smoothed, all utterances at once
-    lf0_all = f0_to_lf0(v_voi * _medfilt3_segments(v_f0, frm_off))
-    voi8 = np.ascontiguousarray(v_voi > 0, dtype=np.uint8)
-    lefts = [left64[frm_off[u]:frm_off[u + 1]] for u in range(len(l_sig))]
+    centre, left, right, voi8, f0_med, frm_off = _analysis_geometry_c(l_pm_smpls, sizes, l_voi, fs)
+    _check_frames(left, right, fft_len)
+    lf0_all = f0_to_lf0(f0_med)                                               # np.log: a fresh array
+    lefts = [left[frm_off[u]:frm_off[u + 1]] for u in range(len(l_sig))]
     lf0s = [lf0_all[frm_off[u]:frm_off[u + 1]] for u in range(len(l_sig))]
     sigs = [np.ascontiguousarray(s, dtype=np.float64) for s in l_sig]      # no copy for float64 arrays
     sig_ptrs = (C.c_void_p * len(sigs))(*[s.ctypes.data for s in sigs])
@@ -733,22 +757,22 @@ def _stack_rows(l_arr):
     return np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64) for a in l_arr], axis=0))
 
 
-def compressed_synthesis_geometry(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win=True, b_const_rate=False):
+def compressed_synthesis_geometry(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win=True, b_const_rate=False, _reuse=False):
     """Host bookkeeping of synthesis_from_compressed for a batch (src/magphase.py:846-848, 861-870, 879-882,
     886-896, 968-971, 34-62): everything integer / float64 that the kernels consume as arrays.
     Returns (dict of C-contiguous arrays for mpb_syn_frames + 'need_ph', list of per-utterance noise lengths).
     Variable-rate batches take the vectorised path; the per-utterance loop below is the definition (and the
     constant-rate path, whose reverse scan is sequential anyway)."""
     if not b_const_rate:
-        return _compressed_synthesis_geometry_flat(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win)
+        return _compressed_synthesis_geometry_flat(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win, reuse=_reuse)
     return _compressed_synthesis_geometry_loop(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win, b_const_rate)
 
 
-def _compressed_synthesis_geometry_flat(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win=True):
-    """compressed_synthesis_geometry(b_const_rate=False) for all utterances at once: ~40 NumPy calls per batch instead
-    of ~40 per utterance.  Integer results identical to the loop (tests/test_batch_geometry_cpu.py); the only float64
-    arithmetic, exp() and fs / f0, is elementwise and therefore the same numbers."""
-    half = fft_len // 2
+def _compressed_synthesis_geometry_flat(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win=True, reuse=False):
+    """compressed_synthesis_geometry(b_const_rate=False) for all utterances at once.  exp() and fs / f0 run in NumPy on
+    the concatenated lf0 (elementwise: the same numbers as per utterance); everything after the truncation to integer
+    shifts is one C pass (mpb_syn_geometry).  Integer results identical to the loop (tests/test_batch_geometry_cpu.py).
+    reuse=True hands out arrays of the module workspace (valid until the next call)."""
     n_utt = len(l_lf0)
     lens = np.array([np.size(v) for v in l_lf0], dtype=np.int64)
     if np.any(lens != np.asarray(l_nrows, dtype=np.int64)):
@@ -756,53 +780,22 @@ def _compressed_synthesis_geometry_flat(l_lf0, l_nrows, fs, fft_len, b_voi_ap_wi
     if np.any(lens < 2):
         raise IndexError('synthesis_from_compressed needs at least two frames (src/magphase.py:882)')
     off = _seg_offsets(lens)
-    first, last = off[:-1], off[1:] - 1
+    n = int(off[-1])
     v_f0 = np.exp(np.concatenate([np.asarray(v, dtype=np.float64) for v in l_lf0]))
-    v_voi = v_f0 > 1.0                                            # :847
-    shift = f0_to_shift(v_f0, fs).astype(int)                     # truncation BEFORE the cumsum (:879-880)
-    cs = np.cumsum(shift)
-    base = np.zeros(n_utt, dtype=cs.dtype)
-    base[1:] = cs[last[:-1]]
-    pm = cs - np.repeat(base, lens)                               # per-utterance integer cumsum
-    ns_len = 2 * pm[last] - pm[last - 1]                          # pm[-1] + (pm[-1] - pm[-2])
-    prev = np.empty_like(pm)
-    prev[1:] = pm[:-1]
-    prev[first] = 0
-    nxt = np.empty_like(pm)
-    nxt[:-1] = pm[1:]
-    nxt[last] = ns_len - 1
-    n_left, n_right = pm - prev, nxt - pm
-    if np.any(n_left > half) or np.any(n_right >= half):          # frame_shift() would get a negative pad (src/libaudio.py:137-140)
-        raise ValueError('negative dimensions are not allowed')
-    # anti-ringing half lengths: se = [s0, s..., s_last, s_last]; a = se[i] + se[i+1], b = se[i+2] + se[i+3]
-    s_prev = np.empty_like(shift)
-    s_prev[1:] = shift[:-1]
-    s_prev[first] = shift[first]
-    s_n1 = np.empty_like(shift)
-    s_n1[:-1] = shift[1:]
-    s_n1[last] = shift[last]
-    s_n2 = np.empty_like(shift)
-    s_n2[:-1] = s_n1[1:]
-    s_n2[last] = shift[last]
-    win_a, win_b = s_prev + shift, s_n1 + s_n2
-    # ola_geometry() per utterance, vectorised over utterances (Python slice semantics included)
-    pm_first, pm_last = pm[first], pm[last]
-    buf_len = pm_last + fft_len
-    s0 = half - pm_first
-    start = np.where(s0 < 0, np.maximum(buf_len + s0, 0), np.minimum(s0, buf_len))
-    n1 = np.maximum(buf_len - start, 0)
-    n_out = np.minimum(n1, np.maximum(pm_last + shift[last] + 1, 0))
-    t0 = start + pm_first - half
-    out_off = _seg_offsets(n_out)
-    noise_off = _seg_offsets(ns_len)
-    voi8 = v_voi.astype(np.uint8)
-    arrs = dict(pm=pm.astype(np.int32), ncentre=np.ascontiguousarray(pm + np.repeat(noise_off[:-1], lens), dtype=np.int64),
-                nleft=n_left.astype(np.int32), nright=n_right.astype(np.int32), voi=voi8,
-                nkind=np.where(v_voi & bool(b_voi_ap_win), WIN_BARTLETT25, WIN_HANN).astype(np.uint8),
-                win_a=win_a.astype(np.int32), win_b=win_b.astype(np.int32),
-                row0=np.arange(pm.size, dtype=np.int32), row1=None, roww=None,
-                utt_frm_off=off, utt_out_off=out_off, utt_t0=np.ascontiguousarray(t0, dtype=np.int32),
-                need_ph=voi8.copy())
+    voi8 = (v_f0 > 1.0).astype(np.uint8)                          # :847
+    v_f0[v_f0 == 0] = 200.0                                       # f0_to_shift (:2210-2215), in place on our own array
+    shift = (fs / v_f0).astype(np.int64)                          # truncation BEFORE the cumsum (:879-880)
+    new = (lambda name, k, dt: _workspace('s_' + name, k, dt)) if reuse else (lambda name, k, dt: np.empty(k, dtype=dt))
+    pm, ncentre = new('pm', n, np.int32), new('ncentre', n, np.int64)
+    nleft, nright, nkind = new('nleft', n, np.int32), new('nright', n, np.int32), new('nkind', n, np.uint8)
+    win_a, win_b, row0 = new('win_a', n, np.int32), new('win_b', n, np.int32), new('row0', n, np.int32)
+    out_off, t0, ns_len = np.empty(n_utt + 1, dtype=np.int64), np.empty(n_utt, dtype=np.int32), np.empty(n_utt, dtype=np.int64)
+    _lib.check(_lib.lib().mpb_syn_geometry(_lib.ptr(shift), _lib.ptr(voi8), _lib.ptr(off), n_utt, fft_len,
+                                           1 if b_voi_ap_win else 0, _lib.ptr(pm), _lib.ptr(ncentre), _lib.ptr(nleft),
+                                           _lib.ptr(nright), _lib.ptr(nkind), _lib.ptr(win_a), _lib.ptr(win_b), _lib.ptr(row0),
+                                           _lib.ptr(out_off), _lib.ptr(t0), _lib.ptr(ns_len)))
+    arrs = dict(pm=pm, ncentre=ncentre, nleft=nleft, nright=nright, voi=voi8, nkind=nkind, win_a=win_a, win_b=win_b,
+                row0=row0, row1=None, roww=None, utt_frm_off=off, utt_out_off=out_off, utt_t0=t0, need_ph=voi8)
     return arrs, [int(x) for x in ns_len]
 
 
@@ -889,7 +882,8 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
     plan = _SynPlan.get(fs, fft_len, mag_dim, phase_dim, alpha_phase)
     n_utt = len(l_feats)
     arrs, l_ns_len = compressed_synthesis_geometry([f[3] for f in l_feats], [np.shape(f[0])[0] for f in l_feats], fs,
-                                                   fft_len, b_voi_ap_win=b_voi_ap_win, b_const_rate=b_const_rate)
+                                                   fft_len, b_voi_ap_win=b_voi_ap_win, b_const_rate=b_const_rate,
+                                                   _reuse=True)
     mt_key, mt_pos, np_state = None, None, None
     if l_noise is None:
         # np.random.uniform(-1, 1, ns_len) per utterance (:883) == one run of sum(ns_len) draws on NumPy's global

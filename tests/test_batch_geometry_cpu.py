@@ -76,3 +76,22 @@ def test_flat_synthesis_geometry_errors():
         mp.compressed_synthesis_geometry([ok], [4], 48000, 4096)
     with pytest.raises(ValueError):                            # pitch period longer than fft_len / 2
         mp.compressed_synthesis_geometry([np.log(np.full(5, 20.0))], [5], 48000, 4096)
+
+
+def test_c_analysis_geometry_equals_numpy_definitions():
+    """mpb_analysis_geometry (one C pass) against frame_geometry / shift_to_f0 / _lf0_smoothed per utterance."""
+    utts = _utts()
+    fs = 48000
+    centre, left, right, voi8, f0_med, off = mp._analysis_geometry_c([u[1] for u in utts], [u[0].size for u in utts],
+                                                                     [u[2] for u in utts], fs)
+    sig_off = 0
+    for k, (sig, p, voi) in enumerate(utts):
+        P, v_shift, v_rights = mp.frame_geometry(p, sig.size)
+        a, b = off[k], off[k + 1]
+        assert np.array_equal(centre[a:b], P[1:-1] + sig_off)
+        assert np.array_equal(left[a:b], v_shift) and np.array_equal(right[a:b], v_rights)
+        v_f0 = mp.shift_to_f0(v_shift.astype(int), np.asarray(voi, dtype=np.float64), fs, out='f0', b_smooth=False)
+        v_voi, v_lf0 = mp._lf0_smoothed(v_f0)
+        assert np.array_equal(voi8[a:b], (v_voi > 0).astype(np.uint8))
+        assert np.array_equal(mp.f0_to_lf0(f0_med[a:b].copy()), v_lf0)            # bit-identical log argument
+        sig_off += sig.size
