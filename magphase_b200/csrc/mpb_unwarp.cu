@@ -11,7 +11,8 @@
 // ONE 128-bin tile of one stream -- its slice of U stays in shared memory for the CTA's lifetime -- and walks over the
 // frame tiles (64 frames) of its share of the batch: the 64 x K feature tile is one contiguous run of the row-major
 // matrix, fetched by a TMA bulk copy that runs under the previous tile's FMA loop, transposed in shared memory, and
-// multiplied with 8 x 8 outputs per thread; exp() is fused for the magnitude stream.
+// multiplied with 4 x 8 outputs per thread (256 threads: 24 warps per SM hide the FMA latencies); exp() is fused for the
+// magnitude stream.
 #include "mpb_kernels.h"
 #include "mpb_tma.cuh"
 
@@ -20,6 +21,7 @@ namespace mpb {
 constexpr int UW_FT = 64;             // frames per tile
 constexpr int UW_BT = 128;            // bins per CTA
 constexpr int UW_LDX = UW_FT + 4;     // pitch of the transposed feature tile
+constexpr int UW_TPB = 256;           // threads per CTA: 4 frames x 8 bins of the 64 x 128 tile each
 
 // flags[t] = 1 when any frame of frame tile t needs its phase rows (tiles without voiced frames are skipped)
 __global__ void k_unwarp_tile_flags(const uint8_t* __restrict__ need_ph, int64_t nfrm, uint8_t* __restrict__ flags) {
@@ -41,7 +43,7 @@ __global__ void k_convert(const TA* __restrict__ a, TB* __restrict__ b, size_t n
     if (i < n) b[i] = (TB)a[i];
 }
 
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(UW_TPB, 3)
 k_mel_unwarp(const float* __restrict__ mag_mel, const float* __restrict__ real_mel, const float* __restrict__ imag_mel,
              const uint8_t* __restrict__ need_ph, const uint8_t* __restrict__ tile_flags, int64_t nfrm, int n_mag, int n_ph,
              const float* __restrict__ u_mag, const float* __restrict__ u_ph,
@@ -73,7 +75,7 @@ k_mel_unwarp(const float* __restrict__ mag_mel, const float* __restrict__ real_m
 
     if (tid == 0) { mbar_init(mbar, 1); fence_proxy_async(); }
     // un-warp matrix tile: rows are pitched to 16 bytes and zero padded on the host side -> float4 copies
-    for (int i = tid; i < K * (UW_BT / 4); i += 128) {
+    for (int i = tid; i < K * (UW_BT / 4); i += UW_TPB) {
         const int c = i / (UW_BT / 4), b4 = i % (UW_BT / 4);
         const int b = b0 + 4 * b4;
         reinterpret_cast<float4*>(Us)[i] = b < np ? __ldg(reinterpret_cast<const float4*>(U + (size_t)c * np + b))
@@ -97,7 +99,7 @@ k_mel_unwarp(const float* __restrict__ mag_mel, const float* __restrict__ real_m
     if (ft < n_ft && by_tma(ft) && tid == 0) fetch(ft);
     uint32_t phase = 0;
 
-    const int tf = tid >> 4, tb = tid & 15;               // frames {tf*4.., 32+tf*4..}, bins {tb*4.., 64+tb*4..}
+    const int tf = tid >> 4, tb = tid & 15;               // frames tf*4 .. tf*4+3, bins {tb*4.., 64+tb*4..}
     const float* px = Xs + tf * 4;
     const float* pu = Us + tb * 4;
     while (ft < n_ft) {
@@ -107,11 +109,11 @@ k_mel_unwarp(const float* __restrict__ mag_mel, const float* __restrict__ real_m
             mbar_wait(mbar, phase);
             phase ^= 1u;
         } else {
-            for (int i = tid; i < rows * K; i += 128) raw[i] = X[f0 * K + i];
+            for (int i = tid; i < rows * K; i += UW_TPB) raw[i] = X[f0 * K + i];
             __syncthreads();
         }
         // transpose raw[f][c] -> Xs[c][f] (rows past the end of the batch read as zero)
-        for (int i = tid; i < UW_FT * K; i += 128) {
+        for (int i = tid; i < UW_FT * K; i += UW_TPB) {
             const int c = i / UW_FT, f = i % UW_FT;       // consecutive threads: consecutive f (conflict-free stores)
             Xs[c * UW_LDX + f] = f < rows ? raw[f * K + c] : 0.0f;
         }
@@ -119,27 +121,26 @@ k_mel_unwarp(const float* __restrict__ mag_mel, const float* __restrict__ real_m
         const int64_t ft_next = next_tile(ft + parts);
         if (ft_next < n_ft && by_tma(ft_next) && tid == 0) { fence_proxy_async(); fetch(ft_next); }
 
-        float acc[8][8];
+        float acc[4][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
 #pragma unroll 4
         for (int c = 0; c < K; ++c) {
             const float4 a0 = *reinterpret_cast<const float4*>(px + c * UW_LDX);
-            const float4 a1 = *reinterpret_cast<const float4*>(px + c * UW_LDX + 32);
             const float4 b0v = *reinterpret_cast<const float4*>(pu + c * UW_BT);
             const float4 b1v = *reinterpret_cast<const float4*>(pu + c * UW_BT + 64);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float a[4] = {a0.x, a0.y, a0.z, a0.w};
             const float b[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int64_t f = f0 + (i < 4 ? tf * 4 + i : 32 + tf * 4 + (i - 4));
+        for (int i = 0; i < 4; ++i) {
+            const int64_t f = f0 + tf * 4 + i;
             if (f >= nfrm) continue;
             if (stream != 0 && need_ph[f] == 0) continue;
             float* py = Y + f * (int64_t)np + b0;
@@ -180,7 +181,7 @@ cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(k_mel_unwarp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mel_unwarp, 128, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mel_unwarp, UW_TPB, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     // CTAs per bin tile, proportional to the work behind a tile: K = n_mag for every frame tile of the magnitude stream,
@@ -195,7 +196,7 @@ cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st) {
     if (g_mag > n_ft) g_mag = (int)n_ft;
     if (g_ph > n_ft) g_ph = (int)n_ft;
     const unsigned grid = (unsigned)(tiles_mag * g_mag + 2 * tiles_ph * g_ph);
-    k_mel_unwarp<<<grid, 128, smem, st>>>(xm, xr, xi, a.need_ph, a.flags, a.nfrm, a.n_mag, a.n_ph, a.u_mag, a.u_ph, a.out_mag,
+    k_mel_unwarp<<<grid, UW_TPB, smem, st>>>(xm, xr, xi, a.need_ph, a.flags, a.nfrm, a.n_mag, a.n_ph, a.u_mag, a.u_ph, a.out_mag,
                                           a.out_real, a.out_imag, tiles_mag, tiles_ph, g_mag, g_ph, kmax, a.HP, a.HBP);
     return cudaGetLastError();
 }

@@ -1,0 +1,79 @@
+"""The host entry points are pipelines over groups of utterances (mpb_stage.cu, mpb_api_mel.cu, mpb_api_syn.cu):
+PCM-exact signals are narrowed to float32 on the host, others travel as float64 -- decided per group -- and groups
+flow through H2D / compute / D2H streams.  None of that may change a number: a batch must equal its utterances
+processed one by one, whatever mix of exact and inexact signals it holds, and stay within tolerance of the oracle."""
+import numpy as np
+import pytest
+
+import magphase_oracle as orc
+from magphase_b200.synth import synth_utterance
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rms(a, b):
+    return float(np.sqrt(np.mean(np.abs(np.asarray(a) - np.asarray(b)) ** 2)))
+
+
+@pytest.fixture(scope='module')
+def mp():
+    import magphase_b200.magphase as m
+    return m
+
+
+def _batch(n=12, dur=0.35):
+    """Utterances of different lengths; every third one carries float64 samples that float32 cannot hold."""
+    rng = np.random.default_rng(5)
+    out = []
+    for u in range(n):
+        sig, pm, voi = synth_utterance(40 + u, fs=48000, dur_s=dur + 0.05 * (u % 4))
+        if u % 3 == 1:
+            sig = sig + rng.normal(scale=1e-9, size=sig.size)          # not representable in float32
+            assert np.any(sig.astype(np.float32).astype(np.float64) != sig)
+        out.append((sig, pm, voi))
+    return out
+
+
+def test_compressed_analysis_batch_equals_single_with_mixed_signal_precision(mp):
+    utts = _batch()
+    outs = mp.analysis_compressed_batch([u[0] for u in utts], 48000, [u[1] for u in utts], [u[2] for u in utts],
+                                        mag_dim=60, phase_dim=45)
+    for k, ((sig, pm, voi), got) in enumerate(zip(utts, outs)):
+        one = mp.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45)
+        for a, b in zip(got[:5], one[:5]):
+            assert np.array_equal(a, b), k                               # same kernels, same rows: bit-identical
+        if k in (0, 1, 5):
+            ref = orc.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45)
+            for a, b in zip(got[:3], ref[:3]):
+                assert rms(a, b) < TOL
+            assert np.array_equal(got[3], ref[3]) and np.array_equal(got[4], ref[4])
+
+
+def test_lossless_analysis_inexact_signal_takes_the_float64_path(mp):
+    sig, pm, voi = synth_utterance(3, fs=48000, dur_s=0.4)
+    sig = sig * (1.0 + 1e-12)                                            # every sample off the float32 grid
+    got = mp.analysis_lossless_from_pm(sig, 48000, pm, voi)
+    ref = orc.analysis_lossless_from_pm(sig, 48000, pm, voi)
+    for a, b in zip(got[:3], ref[:3]):
+        assert rms(a, b) < 1e-6
+
+
+def test_compressed_synthesis_batch_equals_single_across_pipeline_groups(mp):
+    """A batch long enough for several pipeline groups against the same utterances synthesised one at a time on the
+    same NumPy stream: the noise is one continuous MT19937 sequence either way."""
+    utts = _batch(n=48, dur=2.0)
+    feats = mp.analysis_compressed_batch([u[0] for u in utts], 48000, [u[1] for u in utts], [u[2] for u in utts],
+                                         mag_dim=60, phase_dim=45)
+    feats = [f[:4] for f in feats]
+    assert sum(f[0].shape[0] for f in feats) > 15000                     # > 1 group at 10,000 frames per group
+    np.random.seed(77)
+    ys = mp.synthesis_from_compressed_batch(feats, 48000, b_out_hpf=False)
+    state_batch = np.random.get_state()
+    np.random.seed(77)
+    singles = [mp.synthesis_from_compressed(*f, 48000, b_out_hpf=False) for f in feats]
+    state_single = np.random.get_state()
+    assert state_batch[2] == state_single[2] and np.array_equal(state_batch[1], state_single[1])
+    for k, (a, b) in enumerate(zip(ys, singles)):
+        assert a.shape == b.shape
+        assert rms(a, b) < 1e-7, (k, rms(a, b))                          # OLA run splits differ with the batch size
