@@ -27,6 +27,7 @@ public:
     int size() const { return (int)th_.size() + 1; }
     // runs fn(chunk) for chunk in [0, n) on the pool threads AND the caller; returns when all chunks are done
     void run(int n, const std::function<void(int)>& fn, const std::function<void(int)>& on_done_in_order) {
+        std::lock_guard<std::mutex> one_caller(run_mu_);       // contexts of different devices share the pool
         std::unique_lock<std::mutex> lk(mu_);
         fn_ = &fn;
         n_ = n;
@@ -51,9 +52,14 @@ public:
 
 private:
     HostPool() {
+        // default: 8 threads, or this process's share of the cores when a launcher runs one process per GPU
         int n = 8;
-        if (const char* e = getenv("MPB_HOST_THREADS")) n = atoi(e);
         const int hc = (int)std::thread::hardware_concurrency();
+        if (const char* w = getenv("LOCAL_WORLD_SIZE")) {
+            const int lw = atoi(w);
+            if (lw > 1 && hc > 0 && hc / lw < n) n = hc / lw;
+        }
+        if (const char* e = getenv("MPB_HOST_THREADS")) n = atoi(e);
         if (hc > 0 && n > hc) n = hc;
         if (n < 1) n = 1;
         for (int i = 0; i < n - 1; ++i) th_.emplace_back([this] { loop(); });
@@ -87,7 +93,7 @@ private:
         }
     }
     std::vector<std::thread> th_;
-    std::mutex mu_;
+    std::mutex mu_, run_mu_;
     std::condition_variable cv_, idle_cv_;
     const std::function<void(int)>* fn_ = nullptr;
     int n_ = 0, active_ = 0;

@@ -216,7 +216,7 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
             const float ia = A > 0 ? 1.0f / (float)A : 0.0f, ib = B > 0 ? 1.0f / (float)B : 0.0f;
             for (int dd = -A + t; dd <= B; dd += TPB) {
                 const int n = dd & (N - 1);
-                const float w = dd == 0 ? 1.0f : 0.5f + 0.5f * cospif(dd < 0 ? (float)(-dd) * ia : (float)dd * ib);
+                const float w = dd == 0 ? 1.0f : hann_side_f32(dd < 0 ? (float)(-dd) * ia : (float)dd * ib);
                 acc[(p + dd) & (N - 1)] += bufT[2 * G::nphys(n >> 1) + (n & 1)] * scale * w;
             }
             __syncthreads();
