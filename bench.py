@@ -157,7 +157,9 @@ def run_cpu_arm(n_utts, dur_s, steps, warmup, workload='compressed'):
 
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+    """nvidia-smi polled every 20 ms from before the warm-up; stop(t0, t1) keeps the samples whose timestamps fall
+    inside the timed region [t0, t1] (host wall clock), or the nearest ones when the region is shorter than a period."""
+    QUERY = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
 
@@ -165,12 +167,12 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
-                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                       '--format=csv,noheader,nounits', '-lms', '20'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.p is None:
             return None
         self.p.terminate()
@@ -181,19 +183,26 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        import datetime
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        samples = []
         for r in rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                ts = datetime.datetime.strptime(r[0].strip(), '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                samples.append((ts, float(r[1]), float(r[2]), [n for n, v in zip(names, r[5:9]) if v.strip().lower() == 'active']))
             except (ValueError, IndexError):
                 continue
-            for n, v in zip(names, r[5:9]):
-                if v.strip().lower() == 'active':
-                    reasons.add(n)
-        if not sm:
+        if not samples:
             return None
-        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        inside = [x for x in samples if t0 is not None and t0 <= x[0] <= t1]
+        note = 'samples inside the timed region'
+        if not inside:          # region shorter than the polling period: the two samples that bracket it
+            mid = 0.5 * (t0 + t1) if t0 is not None else samples[-1][0]
+            inside = sorted(samples, key=lambda x: abs(x[0] - mid))[:2]
+            note = 'timed region shorter than the polling period: nearest samples'
+        reasons = sorted({n for x in inside for n in x[3]})
+        return dict(sm_mhz=statistics.median([x[1] for x in inside]), sm_max_mhz=max(x[2] for x in inside),
+                    reasons=reasons, samples=len(inside), note=note)
 
 
 def main():
@@ -313,20 +322,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # polls from before the warm-up (nvidia-smi start-up)
     for _ in range(a.warmup):
         step()
     barrier()
     launches0 = _lib.launch_count(local_rank)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     t_start.record()
     for k in range(a.steps):
         step(ev[k])
     t_end.record()
     barrier()
-    clocks = sampler.stop() if sampler else None
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if sampler else None
     launches = _lib.launch_count(local_rank) - launches0
     total_ms = t_start.elapsed_time(t_end)
     ana_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / a.steps
@@ -406,10 +417,10 @@ def main():
                                   + getattr(plan, 'n_out', 0) * 4,
     }
     traffic_pf, traffic_src = {}, None
-    tpath = os.path.join(ROOT, 'profiles', 'r1', 'traffic_per_frame.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r1b', 'traffic_per_frame.json')
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        traffic_pf, traffic_src = tj['dram_bytes_per_frame'], 'profiles/r1/traffic_per_frame.json (ncu --set full capture, scaled to this launch size)'
+        traffic_pf, traffic_src = tj['dram_bytes_per_frame'], 'profiles/r1b/traffic_per_frame.json (ncu --set full capture, scaled to this launch size)'
     kernels = []
     for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
         per_step_ms = ms / prof_steps
