@@ -404,16 +404,18 @@ def main():
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     # algorithmic HBM bytes per launch of each kernel = what its own contract must move
     H, nf = FFT_LEN // 2 + 1, plan.nfrm
+    nv = getattr(plan, 'n_voiced', nf)       # the phase rows / phase-stream products only exist for voiced frames
+    vf = nv / max(nf, 1)
     kbytes = {
-        'k_analysis<logp>': plan.n_sig * 4 + nf * 16 + 3 * nf * H * 4,
+        'k_analysis<logp>': plan.n_sig * 4 + nf * 17 + (nf + 2 * nv) * H * 4,
         'k_analysis': plan.n_sig * 4 + nf * 16 + 3 * nf * H * (8 if (not comp and feat_dt == F64) else 4),
         'k_synthesis_lossless': 3 * nf * H * (8 if feat_dt == F64 else 4) + nf * 4 + getattr(plan, 'n_out', 0) * 4,
-        'k_mel_gemm': 3 * nf * H * 4 + nf * 150 * 4,
+        'k_mel_gemm': (nf + 2 * nv) * H * 4 + nf * 150 * 4,
         'k_mel_finish': nf * 150 * 4,
-        'k_mel_unwarp': nf * 150 * 4 + nf * H * 4 + 0.4 * nf * 2 * 512 * 4,
+        'k_mel_unwarp': nf * 150 * 4 + nf * H * 4 + vf * nf * 2 * 512 * 4,
         'k_analysis<noise_logsq>': getattr(plan, 'n_noise', 0) * 4 + nf * 25 + nf * (H + 1) * 8,      # + stored noise spectra
         'k_noise_gain': nf * 9,
-        'k_synthesis_compressed': nf * (H + 1) * 8 + nf * H * 4 + 0.4 * nf * 2 * 512 * 4 + nf * 45
+        'k_synthesis_compressed': nf * (H + 1) * 8 + nf * H * 4 + vf * nf * 2 * 512 * 4 + nf * 45
                                   + getattr(plan, 'n_out', 0) * 4,
     }
     traffic_pf, traffic_src = {}, None
@@ -439,6 +441,7 @@ def main():
         'dtype': 'f64 analysis butterflies, f32 elsewhere; f32 storage',
         'data': 'synthetic',
         'config': {'workload': workload, 'fs': FS, 'fft_len': FFT_LEN, 'frames_per_gpu_per_step': plan.nfrm,
+                   'voiced_fraction': round(vf, 3),
                    'mean_shift_samples': round(plan.mean_shift, 1),
                    'l2_note': 'per-step intermediates %.1f GB in HBM >> 126 MB L2' % (3 * nf * H * 4 / 1e9),
                    'parallelism': 'utterance-sharded x%d' % world},

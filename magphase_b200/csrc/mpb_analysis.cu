@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(FftGeom<T, N>::TPB, KernelCfg<T, N>::MINB)
 k_analysis(const TS* __restrict__ sig, int64_t n_sig,
            const int64_t* __restrict__ centre, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
            const uint8_t* __restrict__ win, int64_t nfrm, const cx<T>* __restrict__ tw,
-           TO* __restrict__ out_a, TO* __restrict__ out_b, TO* __restrict__ out_c) {
+           TO* __restrict__ out_a, TO* __restrict__ out_b, TO* __restrict__ out_c,
+           const uint8_t* __restrict__ ph_mask) {
     using G = FftGeom<T, N>;
     using T2 = cx<T>;
     constexpr int M = G::M, H = M + 1, TPB = G::TPB;
@@ -37,6 +38,9 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
         const int64_t c = centre[f];
         const int l = left[f], q = right[f];
         const int kind = win ? (int)win[f] : MPB_WIN_HANN;
+        // MODE_LOGP: the phase streams of unvoiced frames are masked downstream (src/magphase.py:2527-2542) and never
+        // read by the tile product: skip their two rows (a third of this kernel's epilogue and two thirds of its stores)
+        const bool need_ph = MODE != MODE_LOGP || !ph_mask || ph_mask[f] != 0;
 
         T2 v[16];
         load_frame<T, TS, N>(sig, n_sig, c, l, q, kind, buf, v, t);
@@ -72,11 +76,15 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
                 if (MODE == MODE_LOGP) {
                     // log periodograms exactly as the mel product consumes them (SPTK mcep -q 3 / -q 2 with -e 1e-8):
                     // log(|X|^2 + 1e-8) and log(exp(2 Re/|X|) + 1e-8); SFU work that hides under the FP64 butterflies
+                    // log(exp(2u) + 1e-8) = 2u + log1p(1e-8 exp(-2u)) = 2u + 1e-8 exp(-2u) to 1e-15 (|u| <= 1): one exp
+                    // instead of exp + log
                     float mag, re, im, pw;
                     normalise_to_f32(x.x, x.y, mag, re, im, pw);
                     __stcs(&oa[kk], (TO)__logf(pw + 1.0e-8f));
-                    __stcs(&ob[kk], (TO)__logf(__expf(2.0f * re) + 1.0e-8f));
-                    __stcs(&oc[kk], (TO)__logf(__expf(2.0f * im) + 1.0e-8f));
+                    if (need_ph) {
+                        __stcs(&ob[kk], (TO)fmaf(1.0e-8f, __expf(-2.0f * re), 2.0f * re));
+                        __stcs(&oc[kk], (TO)fmaf(1.0e-8f, __expf(-2.0f * im), 2.0f * im));
+                    }
                 } else if (MODE == MODE_LOGSQ) {
                     // noise frames: the spectrum itself goes to HBM for k_synthesis_compressed (rows pitched to M + 2)
                     if (sizeof(T) == 4 && out_b)
@@ -141,7 +149,7 @@ static cudaError_t launch_analysis_t(const AnalysisArgs& a, cudaStream_t st) {
     if (grid > a.nfrm) grid = a.nfrm;
     if (grid < 1) return cudaSuccess;
     kern<<<(unsigned)grid, G::TPB, smem, st>>>((const TS*)a.sig, a.n_sig, a.centre, a.left, a.right, a.win, a.nfrm,
-                                               (const cx<T>*)a.tw, (TO*)a.out_a, (TO*)a.out_b, (TO*)a.out_c);
+                                               (const cx<T>*)a.tw, (TO*)a.out_a, (TO*)a.out_b, (TO*)a.out_c, a.ph_mask);
     return cudaGetLastError();
 }
 

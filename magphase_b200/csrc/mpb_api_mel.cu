@@ -187,7 +187,7 @@ int mpb_analysis_compressed_dev(mpb_mel* m, void* stream, const void* sig, int s
         a.centre = centre + f0; a.left = left + f0; a.right = right + f0; a.win = nullptr;
         a.nfrm = n; a.fft_len = m->fft_len; a.compute_dtype = MPB_F64; a.tw = tw;
         a.out_a = m->feats[0].p; a.out_b = m->feats[1].p; a.out_c = m->feats[2].p; a.out_dtype = MPB_F32;
-        a.mode = MODE_LOGP; a.num_sms = ctx->num_sms;
+        a.mode = MODE_LOGP; a.num_sms = ctx->num_sms; a.ph_mask = voi + f0;
         LAUNCH(ctx, st, "k_analysis<logp>", launch_analysis_logp(a, st));
         rc = mel_compress_impl(m, stream, m->feats[0].p, m->feats[1].p, m->feats[2].p, MPB_F32, 1, voi + f0, n,
                                (char*)out_mag_mel + oes * f0 * m->n_mag, (char*)out_real_mel + oes * f0 * m->phase_dim,

@@ -18,6 +18,7 @@ struct AnalysisArgs {
     int mode;                       // MODE_FEATS: a=mag b=real c=imag;  MODE_FFT: a=interleaved complex;
                                     // MODE_LOGP: a,b,c = log periodograms of mag/real/imag as SPTK mcep sees them (float32)
     int num_sms;
+    const uint8_t* ph_mask = nullptr;   // MODE_LOGP: per-frame flag, 0 = the phase rows (b, c) of the frame are not needed
 };
 cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st);
 cudaError_t launch_noise_stats(const AnalysisArgs& a, cudaStream_t st);   // out_a: double[nfrm]; out_b: float2[nfrm][fft_len/2+2] spectra or NULL

@@ -68,6 +68,7 @@ class LosslessPlan:
         self.d_t0 = up(np.array(t0), np.int32)
         self.d_runs = up(runs, np.int32)
         self.mean_shift = float(np.mean(np.concatenate(left)))
+        self.n_voiced = int(sum(int(np.count_nonzero(v)) for v in voi8))
 
     # algorithmic HBM bytes per launch: samples in + descriptors, features out / the reverse
     def analysis_bytes(self, sig_dtype, feat_dtype):
