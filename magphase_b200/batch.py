@@ -1,0 +1,176 @@
+"""Batch drivers: the reference's two production scripts as library functions + a CLI.
+
+    scripts/batch_feature_extraction_for_tts.py   ->  run_feature_extraction()     wav (+ .est)  ->  .mag .real .imag .lf0 .shift
+    scripts/batch_waveform_generation.py          ->  run_waveform_generation()    feature files ->  wav
+
+The reference fans utterances out over forked processes (``lu.run_multithreaded``, src/libutils.py:32-63), each doing
+its own file IO and NumPy work.  Here the GPU does the arithmetic for a whole batch per call, so the host's job is to
+keep it fed: a pool of IO threads reads (and decodes) the files of batch k+1 and writes the results of batch k-1 while
+batch k is on the device -- disk, PCIe and kernels overlap.  File formats are the reference's own (SURVEY section 8(f)
+rank 2): PCM wav, raw little-endian float32 rows without header (src/libutils.py:112-127), REAPER ``.est`` text.
+
+Results are the same files the per-utterance wrappers write (``analysis_for_acoustic_modelling``,
+``synthesis_from_acoustic_modelling``): feature files byte for byte; waveforms from the same NumPy noise stream, consumed
+in list order exactly like the reference's sequential loop (``b_multiproc = False``, its default for synthesis).
+
+    python -m magphase_b200.batch extract  --scp file_id.scp --wav-dir wavs --out-dir feats [--est-dir est]
+    python -m magphase_b200.batch generate --scp file_id.scp --feats-dir feats --out-dir wavs_syn --fs 48000
+"""
+import argparse
+import concurrent.futures as cf
+import os
+import time
+
+import numpy as np
+
+from . import hostio as io
+from . import magphase as mp
+
+
+def read_tokens(files_scp):
+    """One file token per line, '#' comments (lu.read_text_file2, src/libutils.py:92-96)."""
+    with open(files_scp) as f:
+        return [ln.split('#')[0].strip() for ln in f if ln.split('#')[0].strip()]
+
+
+def _batches(items, n):
+    for a in range(0, len(items), n):
+        yield items[a:a + n]
+
+
+def _load_utterance(in_wav_dir, est_dir, token):
+    wav = os.path.join(in_wav_dir, token + '.wav')
+    v_sig, fs = io.read_audio_file(wav)
+    est = os.path.join(est_dir, token + '.est') if est_dir else None
+    v_pm_sec, v_voi = mp.get_pitch_marks_and_voicing(wav, len(v_sig), fs, est_file=est)
+    return v_sig, fs, v_pm_sec, v_voi
+
+
+def _write_features(out_dir, token, feats, b_const_rate):
+    m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0, v_shift = feats[:5]
+    io.write_binfile(m_mag_mel_log, os.path.join(out_dir, token + '.mag'))
+    io.write_binfile(m_real_mel, os.path.join(out_dir, token + '.real'))
+    io.write_binfile(m_imag_mel, os.path.join(out_dir, token + '.imag'))
+    io.write_binfile(v_lf0, os.path.join(out_dir, token + '.lf0'))
+    if not b_const_rate:
+        io.write_binfile(v_shift, os.path.join(out_dir, token + '.shift'))
+
+
+def run_feature_extraction(tokens, in_wav_dir, out_feats_dir, est_dir=None, fft_len=None, mag_dim=60, phase_dim=45,
+                           b_const_rate=False, batch_utts=64, io_threads=8, verbose=False):
+    """analysis_for_acoustic_modelling (src/magphase.py:2992-3022) for a list of file tokens (or an .scp path).
+    Pitch marks come from ``<est_dir>/<token>.est`` when est_dir is given, else from the REAPER binary (as the reference).
+    Returns {'utterances', 'frames', 'seconds'}."""
+    if isinstance(tokens, str):
+        tokens = read_tokens(tokens)
+    os.makedirs(out_feats_dir, exist_ok=True)
+    t0 = time.perf_counter()
+    n_frames = 0
+    with cf.ThreadPoolExecutor(max_workers=io_threads) as pool:
+        groups = list(_batches(list(tokens), batch_utts))
+        load = lambda g: [pool.submit(_load_utterance, in_wav_dir, est_dir, t) for t in g]
+        pending = load(groups[0]) if groups else []
+        writes = []
+        for k, g in enumerate(groups):
+            utts = [f.result() for f in pending]
+            pending = load(groups[k + 1]) if k + 1 < len(groups) else []      # disk reads overlap the GPU call below
+            fs = utts[0][1]
+            if any(u[1] != fs for u in utts):
+                raise ValueError('all utterances of a batch must share the sample rate')
+            # the reference passes alpha_phase=b_mag_fbank_mel (= False, i.e. 0.0) at src/magphase.py:3010 -- replicated
+            outs = mp.analysis_compressed_batch([u[0] for u in utts], fs, [u[2] * fs for u in utts], [u[3] for u in utts],
+                                                fft_len=fft_len, mag_dim=mag_dim, phase_dim=phase_dim,
+                                                b_const_rate=b_const_rate, alpha_phase=False)
+            for f in writes:
+                f.result()                                                    # surface write errors of batch k-1
+            writes = [pool.submit(_write_features, out_feats_dir, t, o, b_const_rate) for t, o in zip(g, outs)]
+            n_frames += sum(o[0].shape[0] for o in outs)
+            if verbose:
+                print('analysed %d / %d utterances' % (min((k + 1) * batch_utts, len(tokens)), len(tokens)))
+        for f in writes:
+            f.result()
+    return dict(utterances=len(tokens), frames=n_frames, seconds=time.perf_counter() - t0)
+
+
+def _load_features(in_feats_dir, token, mag_dim, phase_dim):
+    rd = lambda ext, dim: io.read_binfile(os.path.join(in_feats_dir, token + ext), dim=dim)
+    return rd('.mag', mag_dim), rd('.real', phase_dim), rd('.imag', phase_dim), rd('.lf0', 1)
+
+
+def run_waveform_generation(tokens, in_feats_dir, out_syn_dir, mag_dim, phase_dim, fs, fft_len=None, pf_type='magphase',
+                            b_const_rate=False, batch_utts=64, io_threads=8, verbose=False):
+    """synthesis_from_acoustic_modelling (src/magphase.py:3229-3275) for a list of file tokens (or an .scp path).
+    The aperiodic noise is drawn from NumPy's global stream in list order (seed it for reproducible output)."""
+    if isinstance(tokens, str):
+        tokens = read_tokens(tokens)
+    if pf_type == 'merlin':
+        raise NotImplementedError("pf_type='merlin' shells out to nine SPTK binaries (src/magphase.py:3375-3465): out of scope")
+    if pf_type not in ('magphase', 'no'):
+        raise ValueError("pf_type must be 'magphase', 'merlin' or 'no'")
+    os.makedirs(out_syn_dir, exist_ok=True)
+    t0 = time.perf_counter()
+    n_frames = 0
+    with cf.ThreadPoolExecutor(max_workers=io_threads) as pool:
+        groups = list(_batches(list(tokens), batch_utts))
+        load = lambda g: [pool.submit(_load_features, in_feats_dir, t, mag_dim, phase_dim) for t in g]
+        pending = load(groups[0]) if groups else []
+        writes = []
+        for k, g in enumerate(groups):
+            feats = [f.result() for f in pending]
+            pending = load(groups[k + 1]) if k + 1 < len(groups) else []
+            if pf_type == 'magphase':
+                # the post-filter works frame by frame (src/magphase.py:2300-2378): one call over the stacked rows
+                rows = np.concatenate([np.atleast_2d(f[0]) for f in feats], axis=0)
+                rows = mp.post_filter(rows, fs)
+                off = np.concatenate(([0], np.cumsum([np.atleast_2d(f[0]).shape[0] for f in feats])))
+                feats = [(rows[off[i]:off[i + 1]],) + f[1:] for i, f in enumerate(feats)]
+            ys = mp.synthesis_from_compressed_batch(feats, fs, fft_len=fft_len, b_const_rate=b_const_rate)
+            for f in writes:
+                f.result()
+            # (copies: the batch result is a view into a pooled page-locked block that the next batch reuses)
+            writes = [pool.submit(io.write_audio_file, os.path.join(out_syn_dir, t + '.wav'), np.array(y), fs)
+                      for t, y in zip(g, ys)]
+            n_frames += sum(np.atleast_2d(f[0]).shape[0] for f in feats)
+            if verbose:
+                print('synthesised %d / %d utterances' % (min((k + 1) * batch_utts, len(tokens)), len(tokens)))
+        for f in writes:
+            f.result()
+    return dict(utterances=len(tokens), frames=n_frames, seconds=time.perf_counter() - t0)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    sub = ap.add_subparsers(dest='cmd', required=True)
+    e = sub.add_parser('extract', help='wav (+ .est) -> .mag .real .imag .lf0 .shift')
+    e.add_argument('--scp', required=True)
+    e.add_argument('--wav-dir', required=True)
+    e.add_argument('--out-dir', required=True)
+    e.add_argument('--est-dir', default=None, help='REAPER .est files (<token>.est); default: run the REAPER binary')
+    g = sub.add_parser('generate', help='.mag .real .imag .lf0 -> wav')
+    g.add_argument('--scp', required=True)
+    g.add_argument('--feats-dir', required=True)
+    g.add_argument('--out-dir', required=True)
+    g.add_argument('--fs', type=int, default=48000)
+    g.add_argument('--pf-type', default='magphase', choices=['magphase', 'no'])
+    g.add_argument('--seed', type=int, default=None, help='np.random.seed for the aperiodic noise')
+    for p in (e, g):
+        p.add_argument('--mag-dim', type=int, default=60)
+        p.add_argument('--phase-dim', type=int, default=45)
+        p.add_argument('--const-rate', action='store_true')
+        p.add_argument('--batch-utts', type=int, default=64)
+        p.add_argument('--io-threads', type=int, default=8)
+    a = ap.parse_args(argv)
+    if a.cmd == 'extract':
+        r = run_feature_extraction(a.scp, a.wav_dir, a.out_dir, est_dir=a.est_dir, mag_dim=a.mag_dim, phase_dim=a.phase_dim,
+                                   b_const_rate=a.const_rate, batch_utts=a.batch_utts, io_threads=a.io_threads, verbose=True)
+    else:
+        if a.seed is not None:
+            np.random.seed(a.seed)
+        r = run_waveform_generation(a.scp, a.feats_dir, a.out_dir, a.mag_dim, a.phase_dim, a.fs, pf_type=a.pf_type,
+                                    b_const_rate=a.const_rate, batch_utts=a.batch_utts, io_threads=a.io_threads, verbose=True)
+    print('Done! %d utterances, %d frames in %.2f s (%.0f frames/s incl. file IO)'
+          % (r['utterances'], r['frames'], r['seconds'], r['frames'] / max(r['seconds'], 1e-9)))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,89 @@
+"""The batch drivers (magphase_b200/batch.py = the reference's scripts/batch_feature_extraction_for_tts.py and
+scripts/batch_waveform_generation.py on the GPU) against the per-utterance file wrappers: feature files byte for byte,
+waveforms from the same NumPy noise stream consumed in list order (the reference's sequential loop)."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from magphase_b200.synth import synth_utterance
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def corpus(tmp_path_factory):
+    from scipy.io import wavfile
+    from magphase_b200 import hostio
+    d = tmp_path_factory.mktemp('corpus')
+    wav_dir, est_dir = d / 'wavs', d / 'est'
+    os.makedirs(wav_dir); os.makedirs(est_dir)
+    tokens = []
+    for u, dur in enumerate((0.45, 0.8, 0.3, 0.65, 0.5)):
+        sig, pm, voi = synth_utterance(60 + u, fs=48000, dur_s=dur)
+        tok = 'utt_%02d' % u
+        wavfile.write(str(wav_dir / (tok + '.wav')), 48000, np.round(sig * 32768.0).astype(np.int16))
+        hostio.write_reaper_est_file(str(est_dir / (tok + '.est')), pm / 48000.0, voi)
+        tokens.append(tok)
+    scp = d / 'file_id.scp'
+    scp.write_text('# tokens\n' + '\n'.join(tokens) + '\n')
+    return d, str(scp), str(wav_dir), str(est_dir), tokens
+
+
+def test_batch_feature_extraction_writes_the_same_files(corpus):
+    import magphase_b200.magphase as mp
+    from magphase_b200 import batch
+    d, scp, wav_dir, est_dir, tokens = corpus
+    out_b, out_s = str(d / 'feats_batch'), str(d / 'feats_single')
+    os.makedirs(out_s)
+    r = batch.run_feature_extraction(scp, wav_dir, out_b, est_dir=est_dir, batch_utts=2, io_threads=3)   # 3 batches
+    assert r['utterances'] == len(tokens) and r['frames'] > 0
+    for tok in tokens:
+        mp.analysis_for_acoustic_modelling(os.path.join(wav_dir, tok + '.wav'), out_s, mag_dim=60, phase_dim=45,
+                                           est_file=os.path.join(est_dir, tok + '.est'))
+        for ext in ('.mag', '.real', '.imag', '.lf0', '.shift'):
+            a = open(os.path.join(out_b, tok + ext), 'rb').read()
+            b = open(os.path.join(out_s, tok + ext), 'rb').read()
+            assert a == b, (tok, ext)
+
+
+def test_batch_waveform_generation_matches_the_sequential_loop(corpus):
+    import magphase_b200.magphase as mp
+    from magphase_b200 import batch, hostio
+    d, scp, wav_dir, est_dir, tokens = corpus
+    feats = str(d / 'feats_batch')
+    if not os.path.isdir(feats):
+        batch.run_feature_extraction(scp, wav_dir, feats, est_dir=est_dir)
+    out_b, out_s = str(d / 'syn_batch'), str(d / 'syn_single')
+    os.makedirs(out_s)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        np.random.seed(5)
+        r = batch.run_waveform_generation(scp, feats, out_b, 60, 45, 48000, pf_type='magphase', batch_utts=2, io_threads=3)
+        state_b = np.random.get_state()
+        np.random.seed(5)
+        for tok in tokens:
+            mp.synthesis_from_acoustic_modelling(feats, tok, out_s, 60, 45, 48000, pf_type='magphase')
+        state_s = np.random.get_state()
+    assert r['utterances'] == len(tokens)
+    assert state_b[2] == state_s[2] and np.array_equal(state_b[1], state_s[1])       # same draws from the stream
+    for tok in tokens:
+        a, fa = hostio.read_audio_file(os.path.join(out_b, tok + '.wav'))
+        b, fb = hostio.read_audio_file(os.path.join(out_s, tok + '.wav'))
+        assert fa == fb == 48000 and a.shape == b.shape
+        assert np.max(np.abs(a - b)) <= 1.0 / 32768 + 1e-12                          # at most one PCM16 step
+        assert np.mean(a != b) < 0.01
+
+
+def test_batch_cli_and_errors(corpus, capsys):
+    from magphase_b200 import batch
+    d, scp, wav_dir, est_dir, tokens = corpus
+    out = str(d / 'feats_cli')
+    batch.main(['extract', '--scp', scp, '--wav-dir', wav_dir, '--out-dir', out, '--est-dir', est_dir, '--batch-utts', '8'])
+    assert 'Done!' in capsys.readouterr().out
+    assert sorted(os.listdir(out)) == sorted(t + e for t in tokens for e in ('.mag', '.real', '.imag', '.lf0', '.shift'))
+    with pytest.raises(NotImplementedError):
+        batch.run_waveform_generation(tokens, out, str(d / 'x'), 60, 45, 48000, pf_type='merlin')
+    with pytest.raises(FileNotFoundError):
+        batch.run_feature_extraction(['missing'], wav_dir, str(d / 'y'), est_dir=est_dir)
