@@ -68,7 +68,6 @@ class LosslessPlan:
         self.d_t0 = up(np.array(t0), np.int32)
         self.d_runs = up(runs, np.int32)
         self.mean_shift = float(np.mean(np.concatenate(left)))
-        self.n_voiced = int(sum(int(np.count_nonzero(v)) for v in voi8))
 
     # algorithmic HBM bytes per launch: samples in + descriptors, features out / the reverse
     def analysis_bytes(self, sig_dtype, feat_dtype):
@@ -130,6 +129,7 @@ class CompressedPlan:
         self.n_utt, self.n_sig = n_utt, int(sig_off[-1])
         self.nfrm = int(sum(a.size for a in left))
         self.mean_shift = float(np.mean(np.concatenate(left)))
+        self.n_voiced = int(sum(int(np.count_nonzero(v)) for v in voi8))
         arrs, self.l_ns_len = mp.compressed_synthesis_geometry(self.l_lf0, [a.size for a in left], fs, self.fft_len)
         self.n_noise = int(sum(self.l_ns_len))
         self.n_out = int(arrs['utt_out_off'][-1])

@@ -593,6 +593,59 @@ def build_min_phase_from_mag_spec(m_mag):
 
 
 # ----------------------------------------------------------------------------------------
+# pitch-synchronous Griffin-Lim                               src/magphase.py:3318-3373
+# ----------------------------------------------------------------------------------------
+def griffin_lim_initial_phase(m_mag, phase_init='random'):
+    """Full-length (nfrms x fft_len) initial phase matrix.  src/magphase.py:3330-3347.
+    'random' draws nfrms * fft_len numbers from NumPy's global stream (np.random.rand)."""
+    nfrms, H = m_mag.shape
+    N = 2 * (H - 1)
+    herm = lambda ph: np.hstack((np.zeros((nfrms, 1)), ph[:, 1:-1], np.zeros((nfrms, 1)), -ph[:, -2:0:-1]))   # la.add_hermitian_half 'phase'
+    if isinstance(phase_init, str):
+        if phase_init == 'random':
+            return 2 * np.pi * (np.random.rand(nfrms, N) - 0.5)
+        if phase_init == 'linear':
+            d = np.zeros((nfrms, N))
+            d[:, N // 2] = 1.0
+            return np.angle(np.fft.fft(d))
+        if phase_init == 'min_phase':
+            return herm(np.angle(build_min_phase_from_mag_spec(m_mag)))
+        raise ValueError('phase_init')
+    return herm(np.asarray(phase_init, dtype=np.float64))
+
+
+def griffin_lim(m_mag, v_shift, phase_init='random', niters=30):
+    """Pitch synchronous Griffin-Lim (win_func=np.hanning).  src/magphase.py:3318-3373.
+    Synthesis: ifft(mag * exp(j phase)).real rows overlap-added with the frame centre (column N/2) on the pitch marks,
+    NO fftshift (:3356-3358).  Analysis: windowing() around the marks, frame placed with its mark at column N/2
+    (la.frm_list_to_matrix, src/libaudio.py:122-140), fft, np.angle (:3364-3369).  Returns (v_sig, half phase)."""
+    m_mag = np.asarray(m_mag, dtype=np.float64)
+    v_shift = round_to_int(v_shift)
+    nfrms, H = m_mag.shape
+    N = 2 * (H - 1)
+    m_phase = griffin_lim_initial_phase(m_mag, phase_init)
+    m_mag_full = np.hstack((m_mag, m_mag[:, -2:0:-1]))                     # la.add_hermitian_half 'mag'
+    v_pm = np.cumsum(v_shift)
+    v_sig = None
+    for it in range(niters):
+        m_frms = np.fft.ifft(m_mag_full * np.exp(m_phase * 1j)).real
+        v_sig = ola(m_frms, v_pm)
+        if it == niters - 1:
+            break
+        P, v_l, v_r = frame_limits(v_pm, v_sig.size)
+        m_frms = np.zeros((nfrms, N))
+        for f in range(nfrms):
+            l, r = int(v_l[f]), int(v_r[f])
+            frm = v_sig[P[f]:P[f + 2] + 1] * asym_window(l, r, 'hann')
+            a = N // 2 - l                                                 # rel_shift of la.frame_shift
+            if a < 0 or a + frm.size > N:
+                raise ValueError('negative dimensions are not allowed')
+            m_frms[f, a:a + frm.size] = frm
+        m_phase = np.angle(np.fft.fft(m_frms, n=N))
+    return v_sig, m_phase[:, :H]
+
+
+# ----------------------------------------------------------------------------------------
 # compressed analysis                                         src/magphase.py:2947-2988
 # ----------------------------------------------------------------------------------------
 def analysis_compressed_from_pm(v_sig, fs, v_pm_smpls, v_voi, fft_len=None, mag_dim=60, phase_dim=45,
