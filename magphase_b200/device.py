@@ -183,3 +183,97 @@ class CompressedPlan:
             _dp(self.d_noise), self.n_noise, C.byref(self.frames), _dp(self.d_runs), self.n_runs, 0, _dp(self.d_out),
             MPB_F32, self.n_out))
         return self.d_out
+
+
+def griffin_lim(m_mag, v_shift, win_func=np.hanning, phase_init='random', niters=30, device=None):
+    """Pitch-synchronous Griffin-Lim (src/magphase.py:3318-3373) with every iteration on the device: the synthesis half is
+    k_synthesis_lossless, the analysis half k_analysis, both in float64, features and signal resident in HBM.
+
+    The reference keeps its frames centred on column N/2 without fftshift, the kernels keep the pitch mark at index 0
+    with fftshift on the way out; the two conventions differ by (-1)^k on the spectrum, i.e. phase_kernel = phase_ref -
+    pi k, and that factor cancels between the two halves of an iteration.  It is applied to the initial phase and
+    removed from the returned one.  Returns (v_sig, m_phase[nfrms, N/2+1]) like the reference."""
+    m_mag = np.ascontiguousarray(m_mag, dtype=np.float64)
+    if m_mag.ndim != 2:
+        raise ValueError('m_mag must be nfrms x (fft_len/2+1)')
+    nfrms, H = m_mag.shape
+    N = 2 * (H - 1)
+    if N not in (1024, 2048, 4096):
+        raise ValueError('fft_len must be 1024, 2048 or 4096')
+    if niters < 1:
+        raise ValueError('niters must be >= 1')
+    v_shift = mp.round_to_int(np.asarray(v_shift, dtype=np.float64))
+    if v_shift.size != nfrms:
+        raise ValueError('one shift per frame')
+    v_pm = np.cumsum(v_shift)
+    pm_int, t0, n_out = mp.ola_geometry(v_pm, N)
+    P, left, right = mp.frame_geometry(v_pm, n_out)
+    if np.any(left > N // 2) or np.any(right >= N // 2):          # la.frame_shift gets a negative pad (src/libaudio.py:137-140)
+        raise ValueError('negative dimensions are not allowed')
+    kinds = mp._win_codes(win_func, nfrms)
+
+    # ---- initial spectrum, as the first synthesis sees it (src/magphase.py:3330-3347, :3356-3357) ----
+    sgn = np.where(np.arange(H) % 2 == 0, 1.0, -1.0)
+    if isinstance(phase_init, str) and phase_init == 'random':
+        ph_full = 2 * np.pi * (np.random.rand(nfrms, N) - 0.5)     # NOT Hermitian: .real of the ifft symmetrises it
+        mag_full = np.hstack((m_mag, m_mag[:, -2:0:-1]))
+        x_full = mag_full * np.exp(1j * ph_full)
+        x_half = 0.5 * (x_full[:, :H] + np.conj(x_full[:, (N - np.arange(H)) % N]))
+        first_phase = ph_full[:, :H]
+    else:
+        if isinstance(phase_init, str):
+            if phase_init == 'linear':
+                ph = np.angle(np.tile(sgn + 0j, (nfrms, 1)))       # angle(fft(delta at N/2))
+            elif phase_init == 'min_phase':
+                ph = np.angle(mp.build_min_phase_from_mag_spec(m_mag))
+            else:
+                raise ValueError("phase_init must be 'random', 'linear', 'min_phase' or an array")
+        else:
+            ph = np.array(phase_init, dtype=np.float64)
+            if ph.shape != m_mag.shape:
+                raise ValueError('phase_init must have the shape of m_mag')
+        if not (isinstance(phase_init, str) and phase_init == 'linear'):
+            ph[:, 0] = 0.0                                          # la.add_hermitian_half(data_type='phase')
+            ph[:, -1] = 0.0
+        x_half = m_mag * np.exp(1j * ph)
+        first_phase = ph
+    x_half = x_half * sgn
+    mag0 = np.abs(x_half)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        u0 = np.where(mag0 > 0, x_half / mag0, 0.0)
+
+    dev = torch.device('cuda', _lib.default_device() if device is None else device)
+    ctx = _lib.ctx(dev.index)
+    lib = _lib.lib()
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+    frm_off = np.array([0, nfrms], dtype=np.int64)
+    n_runs = C.c_int64()
+    _lib.check(lib.mpb_plan_ola_runs(_lib.ptr(pm_int), _lib.ptr(frm_off), 1, N, 32, None, 0, C.byref(n_runs)))
+    runs = np.zeros((max(n_runs.value, 1), 4), dtype=np.int32)
+    _lib.check(lib.mpb_plan_ola_runs(_lib.ptr(pm_int), _lib.ptr(frm_off), 1, N, 32, _lib.ptr(runs), n_runs.value, C.byref(n_runs)))
+    d_pm, d_runs = up(pm_int, np.int32), up(runs, np.int32)
+    d_out_off, d_t0 = up(np.array([0, n_out]), np.int64), up(np.array([t0]), np.int32)
+    d_centre, d_left, d_right = up(P[1:-1], np.int64), up(left, np.int32), up(right, np.int32)
+    d_win = up(kinds, np.uint8) if kinds is not None else None
+    d_mag_t, d_mag0 = up(m_mag, np.float64), up(mag0, np.float64)
+    d_re, d_im = up(u0.real, np.float64), up(u0.imag, np.float64)
+    d_mag_w = torch.empty_like(d_mag_t)
+    d_sig = torch.empty(max(n_out, 1), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        st = _stream()
+        for it in range(niters):
+            d_mag = d_mag0 if it == 0 else d_mag_t
+            _lib.check(lib.mpb_synthesis_lossless_dev(ctx, st, _dp(d_mag), _dp(d_re), _dp(d_im), MPB_F64, _dp(d_pm), nfrms,
+                                                      _dp(d_out_off), _dp(d_t0), 1, _dp(d_runs), int(n_runs.value), N, MPB_F64,
+                                                      _dp(d_sig), MPB_F64, n_out))
+            if it == niters - 1:
+                break
+            _lib.check(lib.mpb_analysis_lossless_dev(ctx, st, _dp(d_sig), MPB_F64, n_out, _dp(d_centre), _dp(d_left),
+                                                     _dp(d_right), _dp(d_win), nfrms, N, MPB_F64, _dp(d_mag_w), _dp(d_re),
+                                                     _dp(d_im), MPB_F64))
+        v_sig = d_sig[:n_out].cpu().numpy()
+        if niters == 1:
+            m_phase = first_phase
+        else:
+            m_phase = np.angle(sgn * (d_re.cpu().numpy() + 1j * d_im.cpu().numpy()))
+    return v_sig, m_phase

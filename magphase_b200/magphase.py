@@ -989,6 +989,14 @@ def synthesis_from_acoustic_modelling(in_feats_dir, filename_token, out_syn_dir,
     return
 
 
+def griffin_lim(m_mag, v_shift, win_func=np.hanning, phase_init='random', niters=30):
+    """Pitch synchronous Griffin-Lim, src/magphase.py:3318-3373: phase_init 'random' (np.random.rand on the global
+    stream), 'linear', 'min_phase' or a phase matrix.  Every iteration runs on the device (device.griffin_lim)."""
+    from . import device
+    print('Starting Griffin-Lim. It could take a while...')
+    return device.griffin_lim(m_mag, v_shift, win_func=win_func, phase_init=phase_init, niters=niters)
+
+
 def numpy_stream_uniform(low, high, n):
     """np.random.uniform(low, high, n) on NumPy's global legacy stream, generated on the device (bit-identical,
     the global state advances as if NumPy had drawn the numbers).  Exposed for tests."""

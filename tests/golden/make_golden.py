@@ -77,9 +77,29 @@ def compressed():
     print('compressed:', {k: v.shape for k, v in out.items()})
 
 
+def griffin_lim():
+    """src/magphase.py:3318-3373 on the magnitudes of the lossless golden utterance: every phase_init, 4 iterations.
+    Inputs (marks, voicing, signal) are the ones stored in lossless_synth48k.npz; the magnitudes are re-derived from them
+    by the replaying test through the oracle (pinned against the reference to 1e-12)."""
+    fs = 48000
+    sig, pm, voi = synth_utterance(7, fs=fs, dur_s=0.4)
+    m_fft, v_shift = mp.analysis_with_del_comp_from_pm(sig, fs, pm)
+    m_mag, m_real, m_imag, v_f0 = mp.compute_lossless_feats(m_fft, v_shift, voi, fs)
+    out = {}
+    for init in ('linear', 'min_phase', 'random'):
+        np.random.seed(4321)
+        y, ph = mp.griffin_lim(m_mag.copy(), v_shift, phase_init=init, niters=4)
+        out['syn_' + init] = y
+        out['phase_rows_' + init] = ph[FULL_ROWS]
+    np.savez_compressed(os.path.join(HERE, 'griffin_lim_synth48k.npz'), seed=4321, niters=4, full_rows=np.array(FULL_ROWS),
+                        v_shift=v_shift.astype(np.int64), **out)
+    print('griffin_lim:', {k: v.shape for k, v in out.items()})
+
+
 if __name__ == '__main__':
     lossless()
     compressed()
+    griffin_lim()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -102,3 +102,19 @@ def test_mel_warp_unwarp_roundtrip_sane():
     assert mm.shape == (mag.shape[0], 60) and rr.shape == (mag.shape[0], 45) and ii.shape == rr.shape
     assert np.all(np.abs(rr) <= 1) and np.all(rr[~voiced] == 0)
     assert np.all(lf0[~voiced] == orc.MAGIC)
+
+
+def test_griffin_lim_golden():
+    """Reference griffin_lim outputs (src/magphase.py:3318-3373) replayed through the oracle on the golden utterance."""
+    g, gl = load('lossless_synth48k.npz'), load('griffin_lim_synth48k.npz')
+    sig = g['sig_i16'].astype(np.float64) / 32768.0
+    mag = orc.analysis_lossless_from_pm(sig, int(g['fs']), g['pm'], g['voi'])[0]
+    rows = gl['full_rows']
+    strong = mag[rows] > 1e-6 * mag.max()
+    for init in ('linear', 'min_phase', 'random'):
+        np.random.seed(int(gl['seed']))
+        y, ph = orc.griffin_lim(mag.copy(), gl['v_shift'], phase_init=init, niters=int(gl['niters']))
+        assert y.shape == gl['syn_' + init].shape
+        np.testing.assert_allclose(y, gl['syn_' + init], rtol=0, atol=1e-11)
+        d = np.abs(np.angle(np.exp(1j * (ph[rows] - gl['phase_rows_' + init]))))
+        assert np.max(d[strong]) < 1e-7

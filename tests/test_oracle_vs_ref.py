@@ -176,3 +176,20 @@ def test_legacy_ph_encoding_matches_reference_around_sptk(ref_modules, monkeypat
         np.testing.assert_allclose(a, b, rtol=0, atol=1e-5)     # float32 outputs of an ill-conditioned dB -> cepstrum map
     with pytest.raises(ValueError):
         mp.analysis_with_del_comp_and_ph_encoding(sig, 512, 48000, 4500)
+
+
+def test_griffin_lim_matches_reference(ref_modules):
+    """src/magphase.py:3318-3373, every phase_init; np.random.rand for 'random' is drawn from the same seeded stream."""
+    mp, la, lu = ref_modules
+    sig, pm, voi = synth_utterance(8, dur_s=0.6)
+    mag, real, imag, f0, fs, shift = orc.analysis_lossless_from_pm(sig, 48000, pm, voi)
+    for init in ('linear', 'min_phase', 'random', np.angle(real + 1j * imag)):
+        arg = lambda: init if isinstance(init, str) else init.copy()       # add_hermitian_half mutates its input
+        np.random.seed(3)
+        y_ref, ph_ref = mp.griffin_lim(mag.copy(), shift, phase_init=arg(), niters=5)
+        np.random.seed(3)
+        y, ph = orc.griffin_lim(mag.copy(), shift, phase_init=arg(), niters=5)
+        assert y.shape == y_ref.shape and ph.shape == ph_ref.shape
+        np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-12)
+        strong = mag > 1e-6 * mag.max()
+        assert np.max(np.abs(np.angle(np.exp(1j * (ph - ph_ref))))[strong]) < 1e-8
