@@ -45,7 +45,8 @@ __device__ __forceinline__ double2 feat_to_spec(double mag, double re, double im
 }
 
 template <typename T, int N> struct SynthCfg {
-    static constexpr int MINB = (sizeof(T) == 8 ? 384 : 768) / FftGeom<T, N>::TPB;
+    // float32: 5 CTAs/SM (102 registers) so that all loads of a frame can be in flight at once (measured best of 4/5/6)
+    static constexpr int MINB = (sizeof(T) == 8 ? 384 : 640) / FftGeom<T, N>::TPB;
 };
 
 template <typename T, typename TF, typename TO, int N>
@@ -58,7 +59,7 @@ k_synthesis_lossless(const TF* __restrict__ mag, const TF* __restrict__ real, co
     using T2 = cx<T>;
     constexpr int M = G::M, H = M + 1, TPB = G::TPB, HALF = N / 2;
     constexpr int NP = (M / 2) / TPB;            // spectrum pairs (k, M-k) per thread, k in [0, M/2)
-    constexpr int NPB = NP / 2;                  // pairs per load batch
+    constexpr int NPB = sizeof(T) == 8 ? NP / 2 : NP;   // pairs per load batch (float32: all 6*NP loads of a frame in flight)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T2* buf = reinterpret_cast<T2*>(smem_raw);
     T* acc = reinterpret_cast<T*>(buf + G::BUF_ELEMS);
