@@ -11,8 +11,8 @@
 namespace mpb {
 
 template <typename T, int N> struct KernelCfg {
-    // register budget: 128 regs/thread for float64 butterflies, ~85 for float32
-    static constexpr int MINB = (sizeof(T) == 8 ? 640 : 768) / FftGeom<T, N>::TPB;
+    // CTAs per SM, measured: float64 butterflies 5 (96 registers; 4 and 6 are both slower), float32 7 (72 registers)
+    static constexpr int MINB = (sizeof(T) == 8 ? 640 : 896) / FftGeom<T, N>::TPB;
 };
 
 template <typename T, typename TS, typename TO, int N, int MODE>
