@@ -82,6 +82,7 @@ int mpb_destroy(mpb_ctx* ctx) {
     for (auto& kv : ctx->tw64) cudaFree(kv.second);
     for (auto& b : ctx->scratch) b.release();
     ctx->mt_jump.release();
+    ctx->ticket.release();
     ctx->stage.release();
     ctx->desc_stage.release();
     ctx->mt_fin.release();
@@ -300,6 +301,8 @@ int mpb_synthesis_lossless_dev(mpb_ctx* ctx, void* stream, const void* mag, cons
     int rc = get_twiddles(ctx, fft_len, compute_dtype, &a.tw);
     if (rc != MPB_OK) return rc;
     a.out = out; a.out_dtype = out_dtype; a.n_out = n_out; a.num_sms = ctx->num_sms;
+    CU(ctx->ticket.need(sizeof(int)));
+    a.run_ticket = (int*)ctx->ticket.p;
     LAUNCH(ctx, (cudaStream_t)stream, "k_synthesis_lossless", launch_synthesis_lossless(a, (cudaStream_t)stream));
     return MPB_OK;
 }

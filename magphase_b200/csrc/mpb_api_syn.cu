@@ -16,7 +16,7 @@ struct mpb_syn {
     float* u_mag = nullptr;   // [n_mag][HP]   (rows pitched to 16 bytes, zero padded)
     float* u_ph = nullptr;    // [n_ph][HBP]
     float* tab = nullptr;     // [3][H]
-    DevBuf unw[3], unw_flags, unw_cvt, logsq, nspec, gain, host_in[20], out;
+    DevBuf unw[3], unw_flags, unw_cvt, logsq, nspec, gain, ticket, host_in[20], out;
     std::mutex mu;
 };
 
@@ -58,7 +58,7 @@ int mpb_syn_destroy(mpb_syn* s) {
     cudaFree(s->u_mag); cudaFree(s->u_ph); cudaFree(s->tab);
     for (auto& b : s->unw) b.release();
     for (auto& b : s->host_in) b.release();
-    s->unw_flags.release(); s->unw_cvt.release(); s->logsq.release(); s->nspec.release(); s->gain.release(); s->out.release();
+    s->ticket.release(); s->unw_flags.release(); s->unw_cvt.release(); s->logsq.release(); s->nspec.release(); s->gain.release(); s->out.release();
     delete s;
     return MPB_OK;
 }
@@ -82,6 +82,7 @@ static int syn_reserve(mpb_syn* s, int in_dtype, int64_t n_rows, int64_t nfrm, i
     CU(s->logsq.need(sizeof(double) * (size_t)nfrm));
     CU(s->nspec.need(sizeof(float2) * (size_t)nfrm * (s->fft_len / 2 + 2)));
     CU(s->gain.need(sizeof(double) * 2 * (size_t)n_utt));
+    CU(s->ticket.need(sizeof(int)));
     CU(s->unw_flags.need((size_t)n_rows / 64 + n_ranges + 2));
     *cvt_pitch = 0;
     if (in_dtype == MPB_F64) {
@@ -148,6 +149,7 @@ static int syn_enqueue_range(mpb_syn* s, cudaStream_t st, const void* mag_mel, c
     a.tab = s->tab; a.utt_out_off = fr->utt_out_off; a.utt_t0 = fr->utt_t0; a.n_utt = fr->n_utt;
     a.utt_a = r.utt_a; a.utt_b = r.utt_b;
     a.runs = (const OlaRun*)runs + r.run_a; a.n_runs = r.run_b - r.run_a; a.nfrm = fr->nfrm;
+    a.run_ticket = (int*)s->ticket.p;
     a.fft_len = s->fft_len; a.per_linear = per_linear == 1; a.tw = tw;
     if (per_linear == 2) {   // per_phase_type='min_phase': Re/Im of the minimum-phase spectrum replace the phase rows
         const void* tw64 = nullptr;

@@ -79,6 +79,7 @@ struct mpb_ctx {
     DevBuf scratch[16];
     DevBuf mt_jump;                                // MT19937 jump polynomials (set-bit lists), uploaded on first use
     bool mt_jump_ready = false;
+    DevBuf ticket;                                 // run hand-out counter of k_synthesis_lossless (one launch at a time per ctx stream)
     PinnedBuf stage;                               // float32 staging of host signals (upload_signals)
     KernelTimer timer;
 };

@@ -37,6 +37,7 @@ struct SynthArgs {
     const int32_t* pm; int64_t nfrm_total;
     const int64_t* utt_frm_off; const int64_t* utt_out_off; const int32_t* utt_t0; int32_t n_utt;
     const OlaRun* runs; int32_t n_runs;
+    int* run_ticket;                // device int, zeroed by the launcher: dynamic run hand-out
     int fft_len; int compute_dtype;
     const void* tw;
     void* out; int out_dtype; int64_t n_out;
@@ -94,6 +95,7 @@ struct SynthCompArgs {
     const int64_t* utt_out_off; const int32_t* utt_t0; int32_t n_utt;
     int32_t utt_a, utt_b;                                                           // utterances whose gains this call computes
     const OlaRun* runs; int32_t n_runs; int64_t nfrm;
+    int* run_ticket;                                                                // device int, zeroed by the launcher: dynamic run hand-out
     int fft_len; int per_linear;
     const void* tw;                                                                 // float32 twiddles
     void* out; int out_dtype; int64_t n_out;

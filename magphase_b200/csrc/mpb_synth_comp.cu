@@ -128,7 +128,11 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
         }
     };
 
-    for (int r = blockIdx.x; r < a.n_runs; r += gridDim.x) {
+    // runs are handed out dynamically (an atomic ticket per run after the CTA's first one): runs differ in length and
+    // a static stride left the slowest CTA ~1 run behind the average.  Run boundaries are combined with atomicAdd by
+    // exactly two contributors, so the result does not depend on which CTA takes which run.
+    __shared__ int s_ticket;
+    for (int r = blockIdx.x; r < a.n_runs;) {
         const OlaRun run = a.runs[r];
         const int64_t out_off = a.utt_out_off[run.utt];
         const int64_t out_len = a.utt_out_off[run.utt + 1] - out_off;
@@ -226,7 +230,10 @@ k_synthesis_compressed(const SynthCompArgs a, TO* __restrict__ out) {
             if (more) { const int nx = dn.p - HALF; hi = nx < hi ? nx : hi; }
             ola_flush<T, TO, N, TPB>(acc, lo, hi, own_lo, own_hi, t0, out_len, out + out_off, t);
         }
+        if (t == 0) s_ticket = (int)gridDim.x + atomicAdd(a.run_ticket, 1);
         __syncthreads();
+        r = s_ticket;
+        __syncthreads();                                   // (s_ticket is rewritten at the end of the next run)
     }
 }
 
@@ -245,6 +252,8 @@ static cudaError_t launch_sc_t(const SynthCompArgs& a, cudaStream_t st) {
     int64_t grid = (int64_t)a.num_sms * per_sm;
     if (grid > a.n_runs) grid = a.n_runs;
     if (grid < 1) return cudaSuccess;
+    e = cudaMemsetAsync(a.run_ticket, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
     kern<<<(unsigned)grid, G::TPB, smem, st>>>(a, (TO*)a.out);
     return cudaGetLastError();
 }

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(FftGeom<T, N>::TPB, SynthCfg<T, N>::MINB)
 k_synthesis_lossless(const TF* __restrict__ mag, const TF* __restrict__ real, const TF* __restrict__ imag,
                      const int32_t* __restrict__ pm, const int64_t* __restrict__ utt_out_off,
                      const int32_t* __restrict__ utt_t0, const OlaRun* __restrict__ runs, int32_t n_runs,
-                     const cx<T>* __restrict__ tw, TO* __restrict__ out) {
+                     const cx<T>* __restrict__ tw, TO* __restrict__ out, int* __restrict__ run_ticket) {
     using G = FftGeom<T, N>;
     using T2 = cx<T>;
     constexpr int M = G::M, H = M + 1, TPB = G::TPB, HALF = N / 2;
@@ -71,7 +71,10 @@ k_synthesis_lossless(const TF* __restrict__ mag, const TF* __restrict__ real, co
     T2* pk = buf + G::nphys(t);
     T2* pmk = buf + G::nphys(M - t);
 
-    for (int r = blockIdx.x; r < n_runs; r += gridDim.x) {
+    // runs are handed out dynamically after the CTA's first one (see k_synthesis_compressed): boundary samples are
+    // combined by exactly two atomicAdd contributors, so the result does not depend on the assignment
+    __shared__ int s_ticket;
+    for (int r = blockIdx.x; r < n_runs;) {
         const OlaRun run = runs[r];
         const int64_t out_off = utt_out_off[run.utt];
         const int64_t out_len = utt_out_off[run.utt + 1] - out_off;
@@ -144,6 +147,9 @@ k_synthesis_lossless(const TF* __restrict__ mag, const TF* __restrict__ real, co
             ola_flush<T, TO, N, TPB>(acc, lo, hi, own_lo, own_hi, t0, out_len, out + out_off, t);
             // the next frame's first write to acc happens after two more barriers: no barrier needed here
         }
+        if (t == 0) s_ticket = (int)gridDim.x + atomicAdd(run_ticket, 1);
+        __syncthreads();
+        r = s_ticket;
         __syncthreads();
     }
 }
@@ -162,9 +168,11 @@ static cudaError_t launch_synth_t(const SynthArgs& a, cudaStream_t st) {
     int64_t grid = (int64_t)a.num_sms * per_sm;
     if (grid > a.n_runs) grid = a.n_runs;
     if (grid < 1) return cudaSuccess;
+    e = cudaMemsetAsync(a.run_ticket, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
     kern<<<(unsigned)grid, G::TPB, smem, st>>>((const TF*)a.mag, (const TF*)a.real, (const TF*)a.imag, a.pm,
                                                a.utt_out_off, a.utt_t0, a.runs, a.n_runs, (const cx<T>*)a.tw,
-                                               (TO*)a.out);
+                                               (TO*)a.out, a.run_ticket);
     return cudaGetLastError();
 }
 
