@@ -222,6 +222,7 @@ def main():
     ap.add_argument('--feat-dtype', default='f32', choices=['f32', 'f64'], help='lossless feature storage in HBM')
     ap.add_argument('--analysis-compute', default='f64', choices=['f32', 'f64'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ola-target', type=int, default=32, help='frames per overlap-add run (device-timed arm)')
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
@@ -289,7 +290,7 @@ def main():
     d_sig = torch.from_numpy(np.concatenate([u[0] for u in utts]).astype(np.float32)).to(dev)   # PCM16/32768: exact in f32
     geom = ([u[0].size for u in utts], [u[1] for u in utts], [u[2] for u in utts])
     if comp:
-        plan = CompressedPlan(*geom, FS, FFT_LEN, mag_dim=60, phase_dim=45, device=local_rank)
+        plan = CompressedPlan(*geom, FS, FFT_LEN, mag_dim=60, phase_dim=45, device=local_rank, ola_target_frames=a.ola_target)
 
         def step(evs=None):
             if evs:
@@ -302,7 +303,7 @@ def main():
                 evs[2].record()
         bytes_ana, bytes_syn = plan.analysis_bytes(), plan.synthesis_bytes()
     else:
-        plan = LosslessPlan(*geom, FS, FFT_LEN, device=local_rank)
+        plan = LosslessPlan(*geom, FS, FFT_LEN, device=local_rank, ola_target_frames=a.ola_target)
         feats = plan.alloc_features(feat_dt)
         d_out = plan.alloc_output(F32)
 
