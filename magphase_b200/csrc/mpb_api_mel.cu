@@ -17,7 +17,8 @@ struct mpb_mel {
     std::mutex mu;
 };
 
-static constexpr int64_t MEL_CHUNK = 32768;   // frames per pass: bounds the K-slice partial-sum scratch (~400 MB)
+static constexpr int64_t MEL_CHUNK = 65536;   // frames per pass: bounds the scratch (log periodograms 1.6 GB + K-slice partial sums 0.4 GB);
+                                              // measured 32768 / 65536 / 131072: 3.62 / 3.50 / 3.48 ms per 116k frames
 
 static int pad64(int n) { return ((n + 63) / 64) * 64; }
 
