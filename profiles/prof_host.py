@@ -1,5 +1,5 @@
 """Host-path breakdown of the e2e arms (run on the GPU box): wall time per API call, device time per kernel,
-cProfile top entries.  Usage: python scratch/prof_host.py [compressed|lossless] [n_utts]"""
+cProfile top entries.  Usage: python profiles/prof_host.py [compressed|lossless] [n_utts]"""
 import cProfile
 import pstats
 import sys
