@@ -14,6 +14,7 @@ Differences from the reference, all additive:
 """
 import ctypes as C
 import os
+import threading
 import warnings
 from subprocess import call
 
@@ -163,16 +164,18 @@ def _medfilt3_segments(v, off):
     return np.maximum(np.minimum(a, v), np.minimum(np.maximum(a, v), c))
 
 
-_WORKSPACE = {}
+_WORKSPACE = threading.local()
 
 
 def _workspace(name, n, dtype):
     """Reusable scratch array (descriptor arrays that only live for the duration of one C call): fresh NumPy
-    allocations of this size are mmap-ed and page-faulted on every call."""
-    a = _WORKSPACE.get(name)
+    allocations of this size are mmap-ed and page-faulted on every call.  Per thread: ctypes releases the GIL inside
+    the C call that reads these arrays."""
+    ws = _WORKSPACE.__dict__
+    a = ws.get(name)
     if a is None or a.size < n or a.dtype != np.dtype(dtype):
         a = np.empty(max(int(n), 1024) * 5 // 4, dtype=dtype)
-        _WORKSPACE[name] = a
+        ws[name] = a
     return a[:n]
 
 
