@@ -44,7 +44,10 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
 
         T2 v[16];
         load_frame<T, TS, N>(sig, n_sig, c, l, q, kind, buf, v, t);
-        fft_m<T, N, false>(v, buf, fc, t);
+        // frames no longer than 2/16 of the FFT on either side of the mark only fill the first and the last sixteenth
+        // of the buffer: the first radix-16 butterfly sees two non-zero inputs
+        const bool ends_only = l <= 2 * G::S1 && min(q, N - l - 1) < 2 * G::S1;
+        fft_m<T, N, false>(v, buf, fc, t, ends_only);
 
         // real-FFT split:  X[k] = E + W_N^k O,  X[M-k] = conj(E - W_N^k O),
         //                  E = (Z[k] + conj Z[M-k]) / 2,  O = -i (Z[k] - conj Z[M-k]) / 2,   k = t + j*TPB
