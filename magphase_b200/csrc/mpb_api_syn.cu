@@ -16,7 +16,7 @@ struct mpb_syn {
     float* u_mag = nullptr;   // [n_mag][HP]   (rows pitched to 16 bytes, zero padded)
     float* u_ph = nullptr;    // [n_ph][HBP]
     float* tab = nullptr;     // [3][H]
-    DevBuf unw[3], unw_flags, unw_cvt, logsq, nspec, gain, ticket, host_in[20], out;
+    DevBuf unw[3], unw_flags, unw_cvt, logsq, nspec, gain, ticket, frm_rows[3], host_in[20], out;
     std::mutex mu;
 };
 
@@ -58,6 +58,7 @@ int mpb_syn_destroy(mpb_syn* s) {
     cudaFree(s->u_mag); cudaFree(s->u_ph); cudaFree(s->tab);
     for (auto& b : s->unw) b.release();
     for (auto& b : s->host_in) b.release();
+    for (auto& b : s->frm_rows) b.release();
     s->ticket.release(); s->unw_flags.release(); s->unw_cvt.release(); s->logsq.release(); s->nspec.release(); s->gain.release(); s->out.release();
     delete s;
     return MPB_OK;
@@ -155,8 +156,28 @@ static int syn_enqueue_range(mpb_syn* s, cudaStream_t st, const void* mag_mel, c
         const void* tw64 = nullptr;
         rc = get_twiddles(ctx, s->fft_len, MPB_F64, &tw64);
         if (rc != MPB_OK) return rc;
-        LAUNCH(ctx, st, "k_min_phase", launch_min_phase_split(s->fft_len, u.out_mag, HP, n_rows, tw64, u.out_real, u.out_imag,
-                                                               s->HB, HBP, ctx->num_sms, st));
+        if (fr->row1) {
+            // constant-rate input: the reference interpolates the un-warped magnitudes to the synthesis frames first and
+            // builds the minimum phase of the INTERPOLATED rows (src/magphase.py:861-870, then :935-936): materialise
+            // them per frame; the synthesis kernel then reads frame f's own row, no interpolation left
+            const int64_t F = fr->nfrm;
+            CU(s->frm_rows[0].need(sizeof(float) * (size_t)F * HP));
+            CU(s->frm_rows[1].need(sizeof(float) * (size_t)F * HBP));
+            CU(s->frm_rows[2].need(sizeof(float) * (size_t)F * HBP));
+            float* fm = (float*)s->frm_rows[0].p + r.frm_a * HP;
+            float* fre = (float*)s->frm_rows[1].p + r.frm_a * HBP;
+            float* fim = (float*)s->frm_rows[2].p + r.frm_a * HBP;
+            LAUNCH(ctx, st, "k_lerp_rows", launch_lerp_rows((const float*)s->unw[0].p, HP, fr->row0 + r.frm_a, fr->row1 + r.frm_a,
+                                                            fr->roww + r.frm_a, nfrm, fm, st));
+            LAUNCH(ctx, st, "k_min_phase", launch_min_phase_split(s->fft_len, fm, HP, nfrm, tw64, fre, fim, s->HB, HBP,
+                                                                   ctx->num_sms, st));
+            a.m_mag = (const float*)s->frm_rows[0].p; a.m_real = (const float*)s->frm_rows[1].p;
+            a.m_imag = (const float*)s->frm_rows[2].p;
+            a.row0 = nullptr; a.row1 = nullptr; a.roww = nullptr;
+        } else {
+            LAUNCH(ctx, st, "k_min_phase", launch_min_phase_split(s->fft_len, u.out_mag, HP, n_rows, tw64, u.out_real,
+                                                                   u.out_imag, s->HB, HBP, ctx->num_sms, st));
+        }
     }
     a.out = out; a.out_dtype = out_dtype; a.n_out = 0; a.num_sms = ctx->num_sms;
     LAUNCH(ctx, st, "k_noise_gain", launch_noise_gain(a, st));

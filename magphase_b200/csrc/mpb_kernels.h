@@ -81,6 +81,8 @@ struct UnwarpArgs {
     int num_sms;
 };
 cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st);
+cudaError_t launch_lerp_rows(const float* rows, int pitch, const int32_t* row0, const int32_t* row1, const float* roww,
+                             int64_t nfrm, float* out, cudaStream_t st);
 
 struct SynthCompArgs {
     const float* m_mag; const float* m_real; const float* m_imag; int H; int HB; int HP; int HBP;
@@ -88,7 +90,7 @@ struct SynthCompArgs {
     const float2* nspec;                                                            // [nfrm][fft_len/2 + 2] noise spectra (k_analysis<noise_logsq>)
     const int32_t* pm; const int64_t* ncentre; const int32_t* nleft; const int32_t* nright;
     const uint8_t* voi; const uint8_t* nkind; const int32_t* win_a; const int32_t* win_b;
-    const int32_t* row0; const int32_t* row1; const float* roww;                    // row1/roww NULL: no interpolation
+    const int32_t* row0; const int32_t* row1; const float* roww;                    // row0 NULL: frame f reads row f; row1/roww NULL: no interpolation
     const double* logsq; const int64_t* utt_frm_off;                                // noise statistics per frame
     double* inv_gain;                                                               // [n_utt][2] scratch
     const float* tab;                                                               // [3][H]: P, Av, Au

@@ -64,7 +64,7 @@ struct FrameDesc {
 };
 __device__ __forceinline__ FrameDesc load_desc(const SynthCompArgs& a, int64_t g) {
     FrameDesc d;
-    d.p = a.pm[g]; d.A = a.win_a[g]; d.B = a.win_b[g]; d.row0 = a.row0[g];
+    d.p = a.pm[g]; d.A = a.win_a[g]; d.B = a.win_b[g]; d.row0 = a.row0 ? a.row0[g] : (int)g;
     d.row1 = a.row1 ? a.row1[g] : 0;
     d.rw = a.roww ? a.roww[g] : 0.0f;
     d.voiced = a.voi[g] != 0;

@@ -159,6 +159,30 @@ k_mel_unwarp(const float* __restrict__ mag_mel, const float* __restrict__ real_m
     }
 }
 
+// Per-frame magnitude rows of constant-rate input: out[f] = (1 - w) row0 + w row1 of the UN-WARPED rows, the very
+// expression k_synthesis_compressed evaluates on the fly (src/magphase.py:861-870).  Only materialised when something
+// has to be computed FROM the interpolated row (the minimum phase, :935-936).
+__global__ void k_lerp_rows(const float* __restrict__ rows, int pitch, const int32_t* __restrict__ row0,
+                            const int32_t* __restrict__ row1, const float* __restrict__ roww, int64_t nfrm,
+                            float* __restrict__ out) {
+    const int64_t f = blockIdx.x;
+    if (f >= nfrm) return;
+    const float* a = rows + (int64_t)row0[f] * pitch;
+    const float* b = rows + (int64_t)row1[f] * pitch;
+    const float w = roww[f];
+    for (int k = threadIdx.x; k < pitch; k += blockDim.x) {
+        const float x = a[k];
+        out[f * pitch + k] = fmaf(w, b[k] - x, x);
+    }
+}
+
+cudaError_t launch_lerp_rows(const float* rows, int pitch, const int32_t* row0, const int32_t* row1, const float* roww,
+                             int64_t nfrm, float* out, cudaStream_t st) {
+    if (nfrm < 1) return cudaSuccess;
+    k_lerp_rows<<<(unsigned)nfrm, 256, 0, st>>>(rows, pitch, row0, row1, roww, nfrm, out);
+    return cudaGetLastError();
+}
+
 // in_f32: the three feature matrices as float32 (a float64 caller is narrowed into `cvt` first -- the same rounding
 // the tile loader used to apply element by element).  flags: ceil(nfrm / 64) bytes of scratch.
 cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st) {

@@ -871,10 +871,6 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
         raise ValueError('b_fbank_mel=True (experimental filter-bank warping) is outside the CUDA hot path')
     if per_phase_type not in ('magphase', 'linear', 'min_phase'):
         raise ValueError("per_phase_type must be 'magphase', 'min_phase' or 'linear'")
-    if per_phase_type == 'min_phase' and b_const_rate:
-        # the reference interpolates the un-warped magnitude first and builds the minimum phase of the interpolated
-        # frames (src/magphase.py:861-870 then :935-936); the device path builds it per feature row
-        raise NotImplementedError("per_phase_type='min_phase' with b_const_rate=True is not on the CUDA path yet")
     if fft_len is None:
         fft_len = define_fft_len(fs)
     mag_dim = np.shape(l_feats[0][0])[1]

@@ -120,6 +120,20 @@ def test_min_phase_vs_reference_golden(mp, gold):
     assert rms(y, g['syn_minph_nohpf']) < TOL
 
 
+def test_min_phase_with_const_rate_vs_oracle(mp, gold):
+    """min-phase of the INTERPOLATED magnitude rows (the oracle is pinned to the reference for this combination in
+    tests/test_oracle_vs_ref.py), 48 kHz and 16 kHz."""
+    g, feats = gold
+    for fs in (48000, 16000):
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            np.random.seed(21)
+            y_ref = orc.synthesis_from_compressed(*feats, fs, b_const_rate=True, per_phase_type='min_phase', b_out_hpf=False)
+            np.random.seed(21)
+            y = mp.synthesis_from_compressed(*feats, fs, b_const_rate=True, per_phase_type='min_phase', b_out_hpf=False)
+        assert y.shape == y_ref.shape and rms(y, y_ref) < TOL, (fs, rms(y, y_ref))
+
+
 def test_post_filter_vs_reference_golden(mp, gold):
     g, feats = gold
     y = mp.post_filter(feats[0], 48000)

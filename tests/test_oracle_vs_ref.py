@@ -148,6 +148,25 @@ def test_compressed_synthesis_const_rate_16k_matches_reference(ref_modules):
     np.testing.assert_allclose(y, y_r, rtol=0, atol=1e-6)   # HPF on (default): see note above
 
 
+def test_compressed_synthesis_min_phase_const_rate_matches_reference(ref_modules):
+    """per_phase_type='min_phase' with b_const_rate=True: the reference interpolates the un-warped magnitudes to the
+    synthesis frames first and builds the minimum phase of the interpolated rows (src/magphase.py:861-870, :935-936)."""
+    mp, la, lu = ref_modules
+    mag_mel, real_mel, imag_mel, lf0 = _pred('hvd_706')
+    np.random.seed(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        y_r = mp.synthesis_from_compressed(mag_mel.copy(), real_mel.copy(), imag_mel.copy(), lf0.copy(), 48000,
+                                           b_const_rate=True, per_phase_type='min_phase', b_out_hpf=False)
+    np.random.seed(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        y = orc.synthesis_from_compressed(mag_mel, real_mel, imag_mel, lf0, 48000, b_const_rate=True,
+                                          per_phase_type='min_phase', b_out_hpf=False)
+    assert y.shape == y_r.shape
+    np.testing.assert_allclose(y, y_r, rtol=0, atol=1e-12)
+
+
 def test_var_to_const_rate_matches_reference(ref_modules):
     mp, la, lu = ref_modules
     rng = np.random.default_rng(0)
