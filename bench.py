@@ -457,7 +457,10 @@ def main():
                                  if dom['dram_traffic_per_step'] else None),
                      'traffic_source': traffic_src, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': int(dom['algorithmic_bytes_per_step'] / max(dom['launches_per_step'], 1)),
-                     'ms_per_launch': dom['ms_per_step'] / max(dom['launches_per_step'], 1)},
+                     'ms_per_launch': dom['ms_per_step'] / max(dom['launches_per_step'], 1),
+                     'note': 'none of the kernels of this path is HBM-bound: the FFT kernels are issue / FP64-pipe limited '
+                             '(55-71 % of the issue slots, FP64 pipe 42 % in the analysis kernels), the tile products run at '
+                             '57-60 % of the FP32 FMA pipe; DRAM traffic equals the algorithmic bytes (profiles/README.md)'},
         'halves': {'analysis_ms': ana_ms, 'synthesis_ms': syn_ms,
                    'chain_algorithmic_bytes_per_step': int(chain_bytes),
                    'chain_gbs': chain_bytes / (ms_per_step * 1e-3) / 1e9},
