@@ -11,7 +11,7 @@
 // -- a tall-skinny product with K = H = N/2+1.  There is no cepstrum / IFFT left in the path.
 //   k_build_warp : builds W^T (H x n, float64 -> float32) on the GPU: one thread per spectral bin runs the
 //                  freqt recursion on that bin's cosine column.
-//   k_mel_gemm   : CUDA-core FMA tile kernel, split over K in slices of 128 bins; float32 products and
+//   k_mel_gemm   : CUDA-core FMA tile kernel, split over K in slices of MEL_KSLICE bins; float32 products and
 //                  accumulation inside a slice (the operands are float32 data anyway), partial sums to HBM.
 //   k_mel_finish : float64 sum over the K-slices -> float32 rounding (SPTK's float32 output file) ->
 //                  cosine matrix in float64 -> voicing mask / clip / log.
