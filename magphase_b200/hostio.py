@@ -64,7 +64,19 @@ def read_reaper_est_file(est_file, check_len_smpls=-1, fs=-1, skiprows=7, usecol
     beyond the last sample.  src/libaudio.py:421-447"""
     if (check_len_smpls > 0) and (fs == -1):
         raise ValueError('If check_len_smpls given, fs must be provided as well.')
-    m_data = np.atleast_2d(np.loadtxt(est_file, skiprows=skiprows, usecols=list(usecols)))
+    if skiprows == 7:
+        # the reference skips a fixed 7 lines (REAPER's usual header); follow the header's own end marker when the
+        # file carries one, so that extra header fields do not shift the data
+        with open(est_file) as f:
+            for i, line in enumerate(f):
+                if line.strip() == 'EST_Header_End':
+                    skiprows = i + 1
+                    break
+                if i > 64:
+                    break
+    m_data = np.loadtxt(est_file, skiprows=skiprows, usecols=list(usecols), ndmin=2)
+    if m_data.size == 0:
+        raise ValueError('%s holds no pitch marks' % est_file)
     v_pm_sec, v_voi = m_data[:, 0], m_data[:, 1]
     ok = np.hstack((True, np.diff(v_pm_sec) > 0))
     v_pm_sec, v_voi = v_pm_sec[ok], v_voi[ok]

@@ -1,0 +1,50 @@
+"""File formats either side of the path (host only): REAPER .est, raw float32 feature files, PCM wav."""
+import numpy as np
+import pytest
+
+from magphase_b200 import hostio
+
+
+def _est(path, header, rows):
+    path.write_text('\n'.join(header) + '\n' + '\n'.join('%.6f %d' % r for r in rows) + '\n')
+    return str(path)
+
+
+STD = ['EST_File Track', 'DataType ascii', 'NumFrames 4', 'NumChannels 1', 'FrameShift 0.00000', 'VoicingEnabled true',
+       'EST_Header_End']
+ROWS = [(0.005, 0), (0.010, 1), (0.010, 1), (0.0175, 1), (0.030, 0)]
+
+
+def test_est_reader_standard_header_and_filters(tmp_path):
+    t, v = hostio.read_reaper_est_file(_est(tmp_path / 'a.est', STD, ROWS))
+    assert np.allclose(t, [0.005, 0.010, 0.0175, 0.030]) and v.tolist() == [0, 1, 1, 0]      # repeated time dropped
+    # marks at or beyond the last sample are dropped when the signal length is given (src/libaudio.py:440-445)
+    t2, v2 = hostio.read_reaper_est_file(_est(tmp_path / 'b.est', STD, ROWS), check_len_smpls=1000, fs=48000)
+    assert np.allclose(t2, [0.005, 0.010, 0.0175])
+    with pytest.raises(ValueError):
+        hostio.read_reaper_est_file(str(tmp_path / 'b.est'), check_len_smpls=1000)
+
+
+def test_est_reader_follows_the_header_end_marker(tmp_path):
+    longer = STD[:-1] + ['BreaksPresent true', 'CommentChar ;', 'EST_Header_End']
+    t, v = hostio.read_reaper_est_file(_est(tmp_path / 'c.est', longer, ROWS))
+    assert t.size == 4 and v.tolist() == [0, 1, 1, 0]
+    with pytest.raises(ValueError):
+        hostio.read_reaper_est_file(_est(tmp_path / 'd.est', STD, []))
+
+
+def test_binfile_and_wav_round_trip(tmp_path):
+    m = np.random.default_rng(0).normal(size=(7, 60))
+    f = str(tmp_path / 'x.mag')
+    hostio.write_binfile(m, f)
+    back = hostio.read_binfile(f, dim=60)
+    assert back.dtype == np.float64 and np.array_equal(back, m.astype(np.float32).astype(np.float64))
+    with pytest.raises(ValueError):
+        hostio.read_binfile(f, dim=7 * 60 - 1)
+    sig = 0.5 * np.sin(np.arange(4800) * 0.05)
+    w = str(tmp_path / 'y.wav')
+    hostio.write_audio_file(w, sig, 48000)
+    y, fs = hostio.read_audio_file(w)
+    assert fs == 48000 and y.shape == sig.shape
+    assert abs(np.max(np.abs(y)) - 0.98) < 1e-3                                  # peak-normalised to 0.98
+    assert np.max(np.abs(y - 0.98 * sig / np.max(np.abs(sig)))) <= 1.0 / 32768 + 1e-12
