@@ -95,3 +95,53 @@ def test_c_analysis_geometry_equals_numpy_definitions():
         assert np.array_equal(voi8[a:b], (v_voi > 0).astype(np.uint8))
         assert np.array_equal(mp.f0_to_lf0(f0_med[a:b].copy()), v_lf0)            # bit-identical log argument
         sig_off += sig.size
+
+
+def test_c_geometry_randomised_against_the_definitions():
+    """Many random batches (seeded): the one-pass C bookkeeping must reproduce the per-utterance definitions exactly --
+    integer arrays identical, float arrays bit-identical -- for both sides of the path."""
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        n_utt = int(rng.integers(1, 7))
+        fs = int(rng.choice([48000, 16000]))
+        fft_len = 4096 if fs == 48000 else 2048
+        # ---- synthesis side: lf0 tracks with voiced / unvoiced stretches, periods up to the fft_len / 2 limit ----
+        l_lf0 = []
+        for _ in range(n_utt):
+            n = int(rng.integers(2, 120))
+            f0 = rng.uniform(fs / (fft_len / 2 - 2.0), 400.0, n)
+            f0[rng.uniform(size=n) < rng.uniform(0, 0.8)] = 0.0
+            with np.errstate(divide='ignore'):
+                lf0 = np.log(f0)
+            lf0[np.isinf(lf0)] = -1e10
+            l_lf0.append(lf0)
+        rows = [v.size for v in l_lf0]
+        for vw in (True, False):
+            a_flat, ns_flat = mp._compressed_synthesis_geometry_flat(l_lf0, rows, fs, fft_len, vw)
+            a_loop, ns_loop = mp._compressed_synthesis_geometry_loop(l_lf0, rows, fs, fft_len, vw, False)
+            assert ns_flat == ns_loop
+            for k in a_loop:
+                if a_loop[k] is None:
+                    assert a_flat[k] is None
+                else:
+                    assert a_flat[k].dtype == a_loop[k].dtype and np.array_equal(a_flat[k], a_loop[k]), (trial, k)
+        # ---- analysis side: jittered marks (including .5 positions: round half to even), random voicing ----
+        l_pm, l_n, l_voi = [], [], []
+        for _ in range(n_utt):
+            n = int(rng.integers(1, 90))
+            pm = np.cumsum(rng.integers(60, 900, n)).astype(np.float64) + rng.choice([0.0, 0.5, 0.25, -0.5], n)
+            l_pm.append(pm)
+            l_n.append(int(pm[-1]) + int(rng.integers(2, 500)))
+            l_voi.append((rng.uniform(size=n) < 0.6).astype(np.float64))
+        centre, left, right, voi8, f0_med, off = mp._analysis_geometry_c(l_pm, l_n, l_voi, fs)
+        sig_off = 0
+        for k in range(n_utt):
+            P, v_shift, v_rights = mp.frame_geometry(l_pm[k], l_n[k])
+            a, b = off[k], off[k + 1]
+            assert np.array_equal(centre[a:b], P[1:-1] + sig_off)
+            assert np.array_equal(left[a:b], v_shift) and np.array_equal(right[a:b], v_rights)
+            v_f0 = mp.shift_to_f0(v_shift.astype(int), l_voi[k], fs, out='f0', b_smooth=False)
+            v_voi, v_lf0 = mp._lf0_smoothed(v_f0)
+            assert np.array_equal(voi8[a:b], (v_voi > 0).astype(np.uint8))
+            assert np.array_equal(mp.f0_to_lf0(f0_med[a:b].copy()), v_lf0)
+            sig_off += l_n[k]
