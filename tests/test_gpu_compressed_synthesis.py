@@ -134,6 +134,21 @@ def test_min_phase_with_const_rate_vs_oracle(mp, gold):
         assert y.shape == y_ref.shape and rms(y, y_ref) < TOL, (fs, rms(y, y_ref))
 
 
+def test_explicit_fft_len_1024_and_2048_at_16k(mp, gold):
+    """fft_len is an argument of synthesis_from_compressed (src/magphase.py:825): the smallest engine size (1024 points,
+    32 threads per frame) and the default of 16 kHz, variable and constant rate."""
+    g, feats = gold
+    for fft_len in (1024, 2048):
+        for kw in (dict(), dict(b_const_rate=True)):
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                np.random.seed(9)
+                y_ref = orc.synthesis_from_compressed(*feats, 16000, fft_len=fft_len, b_out_hpf=False, **kw)
+                np.random.seed(9)
+                y = mp.synthesis_from_compressed(*feats, 16000, fft_len=fft_len, b_out_hpf=False, **kw)
+            assert y.shape == y_ref.shape and rms(y, y_ref) < TOL, (fft_len, kw, rms(y, y_ref))
+
+
 def test_post_filter_vs_reference_golden(mp, gold):
     g, feats = gold
     y = mp.post_filter(feats[0], 48000)
