@@ -11,6 +11,8 @@ struct mpb_mel {
     double alpha_mag = 0, alpha_ph = 0;
     float* wt_mag = nullptr;     // [kpad][ld_mag]
     float* wt_ph = nullptr;      // [kpad][ld_ph]
+    float* wt_tc_mag = nullptr;  // experimental (MPB_MEL_TC=1): W^T pre-split for the tcgen05 tile product, else NULL
+    float* wt_tc_ph = nullptr;
     double* cos_mag = nullptr;   // [n_mag][n_mag]
     double* cos_ph = nullptr;    // [n_ph][phase_dim]
     DevBuf partial, feats[3], small[8], compact, sig32;
@@ -61,6 +63,13 @@ int mpb_mel_create(mpb_ctx* ctx, int fft_len, double alpha_mag, int n_mag, doubl
     CU(cudaMemcpy(m->cos_ph, cos_ph, sizeof(double) * n_ph * phase_dim, cudaMemcpyHostToDevice));
     CU(build_warp_matrix(fft_len, n_mag, alpha_mag, m->wt_mag, scratch, m->ld_mag, ctx->stream));
     CU(build_warp_matrix(fft_len, n_ph, alpha_ph, m->wt_ph, scratch, m->ld_ph, ctx->stream));
+    static const bool mel_tc = [] { const char* e = getenv("MPB_MEL_TC"); return e && atoi(e) > 0; }();
+    if (mel_tc && m->ld_mag == 64 && m->ld_ph == 64) {       // experimental tensor-core tile product (mpb_mel_tc.cu)
+        CU(cudaMalloc(&m->wt_tc_mag, mel_tc_operand_bytes(fft_len)));
+        CU(cudaMalloc(&m->wt_tc_ph, mel_tc_operand_bytes(fft_len)));
+        CU(build_warp_matrix_tc(fft_len, m->wt_mag, m->ld_mag, m->wt_tc_mag, ctx->stream));
+        CU(build_warp_matrix_tc(fft_len, m->wt_ph, m->ld_ph, m->wt_tc_ph, ctx->stream));
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaFree(scratch));
     ctx->launches += 4;
@@ -72,6 +81,7 @@ int mpb_mel_destroy(mpb_mel* m) {
     if (!m) return MPB_OK;
     cudaSetDevice(m->ctx->device);
     cudaFree(m->wt_mag); cudaFree(m->wt_ph); cudaFree(m->cos_mag); cudaFree(m->cos_ph);
+    cudaFree(m->wt_tc_mag); cudaFree(m->wt_tc_ph);
     m->partial.release(); m->compact.release(); m->sig32.release();
     for (auto& b : m->feats) b.release();
     for (auto& b : m->small) b.release();
@@ -139,6 +149,7 @@ static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const vo
         a.raw_mc = lerp.raw_mc;
         a.voi = voi + f0; a.nfrm = n; a.fft_len = m->fft_len;
         a.wt_mag = m->wt_mag; a.ld_mag = m->ld_mag; a.wt_ph = m->wt_ph; a.ld_ph = m->ld_ph;
+        a.wt_tc_mag = m->wt_tc_mag; a.wt_tc_ph = m->wt_tc_ph;
         a.cos_mag = m->cos_mag; a.n_mag = m->n_mag; a.cos_ph = m->cos_ph; a.n_ph = m->n_ph; a.phase_dim = m->phase_dim;
         a.partial = (float*)m->partial.p; a.ncp_max = ncp;
         a.out_mag = (char*)out_mag_mel + oes * f0 * od_mag;

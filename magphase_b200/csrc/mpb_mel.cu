@@ -333,6 +333,7 @@ static cudaError_t launch_gemm_t(const MelArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_mel_gemm(const MelArgs& a, cudaStream_t st) {
+    if (mel_tc_usable(a)) return launch_mel_gemm_tc(a, st);       // experimental, only when the plan carries tensor-core operands
     if (a.lerp_r0) return a.feat_dtype == MPB_F64 ? launch_gemm_t<double, false, true>(a, st) : launch_gemm_t<float, false, true>(a, st);
     if (a.feat_dtype == MPB_F64) return launch_gemm_t<double, false, false>(a, st);
     return a.pre_logp ? launch_gemm_t<float, true, false>(a, st) : launch_gemm_t<float, false, false>(a, st);
