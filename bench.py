@@ -29,6 +29,25 @@ FS = 48000
 FFT_LEN = 4096
 DISTINCT = 16          # distinct synthetic utterances generated per rank (tiled up to --utts)
 
+def fp32_fma_view(kernels, nf, nv, H, sm_mhz, num_sms, mag_dim=60, nmel=58, phase_dim=45, hb=512):
+    """the two tile products are FP32-FMA bound, not HBM bound, so next to their HBM fraction report the
+    algorithmic FLOP/s against the non-tensor FP32 peak.  Peak = SMs x 128 FMA lanes x 2 x the SM clock sampled during the
+    timed region (derived from the clock, not a measured GEMM).  FMAs per step: warp product (nf x mag_dim + 2 nv x nmel)
+    x (H - 1) bins (src/libaudio.py:575-601 as a matrix); un-warp product nf x mag_dim x H +
+    2 nv x phase_dim x hb (src/libaudio.py:667-684).  Adds an 'fp32_fma' entry to those kernels in place."""
+    peak = num_sms * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fmas = {'k_mel_gemm': (nf * mag_dim + 2 * nv * nmel) * (H - 1),
+            'k_mel_unwarp': nf * mag_dim * H + 2 * nv * phase_dim * hb}
+    for k in kernels:
+        n = fmas.get(k['name'])
+        if n and k['ms_per_step'] > 0 and peak > 0:
+            tf = 2.0 * n / (k['ms_per_step'] * 1e-3) / 1e12
+            k['fp32_fma'] = {'flops_per_step': int(2 * n), 'achieved_tflops': tf, 'peak_tflops': peak, 'frac': tf / peak,
+                             'peak_source': '%d SMs x 128 FMA/clk x 2 x %.0f MHz (sampled SM clock; derived, not measured)'
+                                            % (num_sms, sm_mhz)}
+    return kernels
+
+
 # --------------------------------------------------------------------------------------------
 # CPU arm: the reference's own implementation (oracle/_ref, py3 translation) or the numpy oracle port
 # --------------------------------------------------------------------------------------------
@@ -435,6 +454,12 @@ def main():
                             algorithmic_bytes_per_step=int(kb), gbs=gbs, frac=gbs / peak,
                             dram_traffic_per_step=(int(traffic_pf[name] * nf) if name in traffic_pf else None)))
     dom = kernels[0]
+    try:          # explanatory only: never let it cost the line
+        if comp:
+            fp32_fma_view(kernels, nf, nv, H, float(clocks.get('sm_mhz') or clocks.get('sm_max_mhz') or 0.0),
+                          torch.cuda.get_device_properties(dev).multi_processor_count)
+    except Exception:
+        pass
     ms_per_step = total_ms / a.steps
     value = frames_all / (ms_per_step * 1e-3)
     chain_bytes = bytes_ana + bytes_syn

@@ -29,3 +29,20 @@ def test_reference_arm_prints_the_contract_line():
 
 def test_reference_arm_only_rank_zero_speaks():
     assert _run({'RANK': '1', 'WORLD_SIZE': '2', 'LOCAL_RANK': '1'}) == []
+
+
+def test_fp32_fma_view_of_the_tile_products():
+    """bench.fp32_fma_view: algorithmic FLOP/s of the two tile products against the derived non-tensor FP32 peak."""
+    sys.path.insert(0, ROOT)
+    import bench
+    nf, nv, H = 116432, 54257, 2049
+    ks = [dict(name='k_mel_gemm', ms_per_step=1.44), dict(name='k_mel_unwarp', ms_per_step=1.057),
+          dict(name='k_analysis<logp>', ms_per_step=1.6)]
+    bench.fp32_fma_view(ks, nf, nv, H, 1965.0, 148)
+    g, u = ks[0]['fp32_fma'], ks[1]['fp32_fma']
+    assert 'fp32_fma' not in ks[2]
+    assert abs(g['peak_tflops'] - 148 * 128 * 2 * 1.965e9 / 1e12) < 1e-9
+    assert g['flops_per_step'] == 2 * (nf * 60 + 2 * nv * 58) * 2048
+    assert u['flops_per_step'] == 2 * (nf * 60 * 2049 + 2 * nv * 45 * 512)
+    assert 0.0 < u['frac'] < g['frac'] < 1.0
+    assert abs(g['achieved_tflops'] - g['flops_per_step'] / 1.44e-3 / 1e12) < 1e-9
