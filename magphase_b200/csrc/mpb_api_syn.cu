@@ -15,6 +15,7 @@ struct mpb_syn {
     int fft_len = 0, n_mag = 0, n_ph = 0, H = 0, HB = 0;
     float* u_mag = nullptr;   // [n_mag][HP]   (rows pitched to 16 bytes, zero padded)
     float* u_ph = nullptr;    // [n_ph][HBP]
+    float* u_tc_mag = nullptr, *u_tc_ph = nullptr;   // experimental (MPB_MEL_TC=1): U pre-split for the tcgen05 un-warp product, else NULL
     float* tab = nullptr;     // [3][H]
     DevBuf unw[3], unw_flags, unw_cvt, logsq, nspec, gain, ticket, frm_rows[3], host_in[20], out;
     std::mutex mu;
@@ -48,6 +49,15 @@ int mpb_syn_create(mpb_ctx* ctx, int fft_len, int n_mag, int n_ph, int hb, const
     if (rc == MPB_OK) rc = upload_f32(u_ph, n_ph, hb, (hb + 3) & ~3, &s->u_ph);
     if (rc == MPB_OK) rc = upload_f32(tab, 3, H, H, &s->tab);
     if (rc != MPB_OK) { delete s; return rc; }
+    static const bool mel_tc = [] { const char* e = getenv("MPB_MEL_TC"); return e && atoi(e) > 0; }();
+    if (mel_tc && n_mag <= 64 && n_ph <= 64) {               // experimental tensor-core un-warp product (mpb_mel_tc.cu)
+        const int HP = (H + 3) & ~3, HBP = (hb + 3) & ~3;
+        CU(cudaMalloc((void**)&s->u_tc_mag, unwarp_tc_operand_bytes(HP, n_mag)));
+        CU(cudaMalloc((void**)&s->u_tc_ph, unwarp_tc_operand_bytes(HBP, n_ph)));
+        CU(build_unwarp_matrix_tc(s->u_mag, n_mag, HP, s->u_tc_mag, ctx->stream));
+        CU(build_unwarp_matrix_tc(s->u_ph, n_ph, HBP, s->u_tc_ph, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     *out = s;
     return MPB_OK;
 }
@@ -56,6 +66,7 @@ int mpb_syn_destroy(mpb_syn* s) {
     if (!s) return MPB_OK;
     cudaSetDevice(s->ctx->device);
     cudaFree(s->u_mag); cudaFree(s->u_ph); cudaFree(s->tab);
+    cudaFree(s->u_tc_mag); cudaFree(s->u_tc_ph);
     for (auto& b : s->unw) b.release();
     for (auto& b : s->host_in) b.release();
     for (auto& b : s->frm_rows) b.release();
@@ -113,6 +124,7 @@ static int syn_enqueue_range(mpb_syn* s, cudaStream_t st, const void* mag_mel, c
     u.in_dtype = in_dtype;
     u.need_ph = need_ph + r.row_a; u.nfrm = n_rows; u.n_mag = s->n_mag; u.n_ph = s->n_ph;
     u.u_mag = s->u_mag; u.H = s->H; u.u_ph = s->u_ph; u.HB = s->HB;
+    u.u_tc_mag = s->u_tc_mag; u.u_tc_ph = s->u_tc_ph;
     u.out_mag = (float*)s->unw[0].p + r.row_a * HP; u.out_real = (float*)s->unw[1].p + r.row_a * HBP;
     u.out_imag = (float*)s->unw[2].p + r.row_a * HBP;
     u.HP = HP; u.HBP = HBP; u.num_sms = ctx->num_sms;

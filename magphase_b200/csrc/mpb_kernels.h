@@ -85,8 +85,14 @@ struct UnwarpArgs {
     float* cvt; size_t cvt_pitch;                                                   // in_dtype F64: 3 x cvt_pitch floats of scratch;
     size_t cvt_off_mag, cvt_off_ph;                                                 //   float offsets (multiples of 4) inside each matrix
     int num_sms;
+    const float* u_tc_mag = nullptr; const float* u_tc_ph = nullptr;               // pre-split tensor-core operands (experimental, mpb_mel_tc.cu; NULL: off)
 };
 cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st);
+// experimental tcgen05 variant (mpb_mel_tc.cu); selected by MPB_MEL_TC=1 when the plan was created
+size_t unwarp_tc_operand_bytes(int np, int K);
+cudaError_t build_unwarp_matrix_tc(const float* U, int K, int np, float* out, cudaStream_t st);
+bool unwarp_tc_usable(const UnwarpArgs& a);
+cudaError_t launch_mel_unwarp_tc(const UnwarpArgs& a, const float* xm, const float* xr, const float* xi, cudaStream_t st);
 cudaError_t launch_lerp_rows(const float* rows, int pitch, const int32_t* row0, const int32_t* row1, const float* roww,
                              int64_t nfrm, float* out, cudaStream_t st);
 

@@ -1,5 +1,7 @@
-// EXPERIMENTAL, OFF BY DEFAULT (MPB_MEL_TC=1 selects it; never run on a GPU yet -- written at the end of round 1 after
-// the GPU budget was spent, to be brought up in round 2).
+// EXPERIMENTAL, OFF BY DEFAULT (MPB_MEL_TC=1 selects it when a plan is created).  Written at the end of round 1 after the
+// GPU budget was spent, to be brought up in round 2: k_mel_gemm_tc has run exactly once on a B200
+// (the fused compressed-analysis parity test passed with it, profiles/r1b/mel_tc_first_run.txt) and has never been timed;
+// k_mel_unwarp_tc (second half of this file) has only been compiled.
 //
 // The mel-warp tile product of format_for_modelling (src/magphase.py:2490-2544 -> la.sp_mel_warp src/libaudio.py:643-661)
 //     MC[F x 64] = log-periodogram[F x 2048] . W^T[2048 x 64]          (per stream; the Nyquist bin stays in k_mel_finish)
@@ -248,6 +250,188 @@ k_mel_gemm_tc(const float* __restrict__ mag, const float* __restrict__ real, con
     }
 }
 
+
+// ================================================================================================================
+// Un-warp product (synthesis side), same scheme.  la.sp_mel_unwarp src/libaudio.py:667-684 as one matrix per stream:
+//     Y[f][b] = sum_c X[f][c] . U[c][b],   K = mag_dim (60) or phase_dim (45), b < np (2052 / 512 pitched bins)
+// computed TRANSPOSED so that the epilogue writes coalesced rows:  D[bin][frame] = U^T[128 bins x K] . X^T[K x 64 frames]
+// (UMMA M = 128 bins = TMEM lanes, N = 64 frames = TMEM columns): a warp's 32 lanes hold 32 consecutive bins of one frame.
+// A CTA owns one 128-bin tile of one stream for its lifetime (U^T tile, pre-split hi | lo, one bulk copy) and walks over
+// its share of the 64-frame tiles exactly like k_mel_unwarp (same tile flags, same grid split): raw feature tile by TMA
+// bulk copy -> hi / lo split into the canonical K-major layout -> 3 x K/8 tcgen05.mma -> tcgen05.ld -> exp -> stores.
+// The steps of a tile are serialised inside the CTA; two (magnitude) or three (phase) CTAs per SM overlap each other.
+constexpr int UT_FT = 64;                       // frames per tile (UMMA N)
+constexpr int UT_BT = 128;                      // bins per CTA (UMMA M)
+constexpr int UT_THREADS = 128;
+constexpr int UT_LBO = 128;                     // both operands: K chunks of a core-matrix row group are contiguous
+
+__host__ __device__ inline int ut_kpad(int K) { return (K + 7) & ~7; }
+
+// U [K][np] float32 (zero padded rows) -> per 128-bin tile: [hi | lo][m/8][k/4][m%8][k%4], K padded to a multiple of 8
+__global__ void k_split_unwarp_tc(const float* __restrict__ U, int K, int np, int kpad, int n_tiles, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tiles * UT_BT * kpad) return;
+    const int k = i % kpad, m = (i / kpad) % UT_BT, t = i / (kpad * UT_BT);
+    const int b = t * UT_BT + m;
+    const float u = (k < K && b < np) ? U[(size_t)k * np + b] : 0.0f;
+    const float hi = __uint_as_float(__float_as_uint(u) & TF32_MASK);
+    const float lo = __uint_as_float(__float_as_uint(u - hi) & TF32_MASK);
+    const int part = UT_BT * kpad;              // floats per part
+    const size_t off = (size_t)t * 2 * part + (m >> 3) * (kpad / 4) * 32 + (k >> 2) * 32 + (m & 7) * 4 + (k & 3);
+    out[off] = hi;
+    out[off + part] = lo;
+}
+
+__global__ void __launch_bounds__(UT_THREADS, 2)
+k_mel_unwarp_tc(const float* __restrict__ mag_mel, const float* __restrict__ real_mel, const float* __restrict__ imag_mel,
+                const uint8_t* __restrict__ need_ph, const uint8_t* __restrict__ tile_flags, int64_t nfrm, int n_mag, int n_ph,
+                const float* __restrict__ utc_mag, const float* __restrict__ utc_ph,
+                float* __restrict__ out_mag, float* __restrict__ out_real, float* __restrict__ out_imag,
+                int tiles_mag, int tiles_ph, int g_mag, int g_ph, int HP, int HBP) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int stream, btile, part, parts;
+    {
+        const int b = blockIdx.x, nm = tiles_mag * g_mag;
+        if (b < nm) { stream = 0; btile = b / g_mag; part = b % g_mag; parts = g_mag; }
+        else {
+            const int c = b - nm;
+            stream = 1 + c / (tiles_ph * g_ph);
+            btile = (c % (tiles_ph * g_ph)) / g_ph; part = c % g_ph; parts = g_ph;
+        }
+    }
+    const int K = stream == 0 ? n_mag : n_ph;
+    const int kpad = ut_kpad(K);
+    const int np = stream == 0 ? HP : HBP;
+    const float* __restrict__ X = stream == 0 ? mag_mel : (stream == 1 ? real_mel : imag_mel);
+    const float* __restrict__ UT = (stream == 0 ? utc_mag : utc_ph) + (size_t)btile * 2 * UT_BT * kpad;
+    float* __restrict__ Y = stream == 0 ? out_mag : (stream == 1 ? out_real : out_imag);
+    const int b0 = btile * UT_BT;
+    const int a_part = UT_BT * kpad * 4, b_part = UT_FT * kpad * 4;          // bytes of one hi / lo part
+    const int sbo = (kpad / 4) * UT_LBO;                                     // bytes between 8-row groups (both operands)
+    uint8_t* As = smem;                                                      // [hi | lo] U^T tile
+    uint8_t* Bs = As + 2 * a_part;                                           // [hi | lo] feature tile, canonical layout
+    float* raw = reinterpret_cast<float*>(Bs + 2 * b_part);                  // [UT_FT][K] as it sits in HBM (TMA destination)
+    uint8_t* tail = reinterpret_cast<uint8_t*>(raw) + ((UT_FT * K * 4 + 15) & ~15);
+    uint64_t* bar_a = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* bar_raw = bar_a + 1;
+    uint64_t* bar_mma = bar_a + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_a + 3);
+    uint8_t* need_s = reinterpret_cast<uint8_t*>(tmem_slot + 2);             // [UT_FT] frame of the tile is written
+    const int64_t n_ft = (nfrm + UT_FT - 1) / UT_FT;
+
+    if (tid == 0) {
+        mbar_init(bar_a, 1); mbar_init(bar_raw, 1); mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)UT_FT) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 2 * b_part / 16; i += UT_THREADS)                  // the K padding of the feature tile stays zero
+        reinterpret_cast<float4*>(Bs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto next_tile = [&](int64_t ft) {
+        while (ft < n_ft && stream != 0 && tile_flags[ft] == 0) ft += parts;
+        return ft;
+    };
+    auto tile_rows = [&](int64_t ft) { return (int)(nfrm - ft * UT_FT < UT_FT ? nfrm - ft * UT_FT : UT_FT); };
+    auto by_tma = [&](int64_t ft) { return ((tile_rows(ft) * K) & 3) == 0; };
+    auto fetch = [&](int64_t ft) {                                           // thread 0 only
+        const uint32_t bytes = (uint32_t)(tile_rows(ft) * K * 4);
+        mbar_expect_tx(bar_raw, bytes);
+        tma_load_1d(raw, X + ft * (int64_t)(UT_FT * K), bytes, bar_raw);
+    };
+    int64_t ft = next_tile(part);
+    if (tid == 0) {
+        if (ft < n_ft) {                                                     // the U^T tile: hi | lo are contiguous
+            mbar_expect_tx(bar_a, 2 * (uint32_t)a_part);
+            tma_load_1d(As, UT, (uint32_t)a_part, bar_a);
+            tma_load_1d(As + a_part, UT + a_part / 4, (uint32_t)a_part, bar_a);
+        }
+        if (ft < n_ft && by_tma(ft)) fetch(ft);
+    }
+    if (ft < n_ft) mbar_wait(bar_a, 0u);
+    uint32_t ph_raw = 0, ph_mma = 0;
+    const int bin = b0 + warp * 32 + lane;                                   // this thread's TMEM lane
+    const bool bin_ok = bin < np;
+
+    while (ft < n_ft) {
+        const int64_t f0 = ft * UT_FT;
+        const int rows = tile_rows(ft);
+        if (by_tma(ft)) {
+            mbar_wait(bar_raw, ph_raw);
+            ph_raw ^= 1u;
+        } else {
+            for (int i = tid; i < rows * K; i += UT_THREADS) raw[i] = X[f0 * K + i];
+            __syncthreads();
+        }
+        if (tid < UT_FT) need_s[tid] = (tid < rows && (stream == 0 || need_ph[f0 + tid] != 0)) ? 1 : 0;
+        // hi / lo split: one item = 4 consecutive coefficients of one frame = one 16-byte row of a core matrix
+        for (int i = tid; i < UT_FT * (kpad / 4); i += UT_THREADS) {
+            const int f = i % UT_FT, k4 = i / UT_FT;                         // 8 consecutive threads: the 8 rows of one core matrix
+            float x[4], hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 4 * k4 + j;
+                x[j] = (f < rows && c < K) ? raw[f * K + c] : 0.0f;
+                hi[j] = __uint_as_float(__float_as_uint(x[j]) & TF32_MASK);
+                lo[j] = __uint_as_float(__float_as_uint(x[j] - hi[j]) & TF32_MASK);
+            }
+            const int off = (f >> 3) * sbo + k4 * UT_LBO + (f & 7) * 16;
+            *reinterpret_cast<float4*>(Bs + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(Bs + b_part + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async();
+        __syncthreads();                                                     // feature tile complete, raw free
+        const int64_t ft_next = next_tile(ft + parts);
+        if (tid == 0) {
+            if (ft_next < n_ft && by_tma(ft_next)) fetch(ft_next);           // lands under the MMAs and the epilogue
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(As), a_lo = a_hi + (uint32_t)a_part;
+            const uint32_t b_hi = smem_u32(Bs), b_lo = b_hi + (uint32_t)b_part;
+            for (int j = 0; j < kpad / 8; ++j) {
+                const uint64_t da_hi = smem_desc(a_hi + j * 2 * UT_LBO, UT_LBO, (uint32_t)sbo);
+                const uint64_t da_lo = smem_desc(a_lo + j * 2 * UT_LBO, UT_LBO, (uint32_t)sbo);
+                const uint64_t db_hi = smem_desc(b_hi + j * 2 * UT_LBO, UT_LBO, (uint32_t)sbo);
+                const uint64_t db_lo = smem_desc(b_lo + j * 2 * UT_LBO, UT_LBO, (uint32_t)sbo);
+                umma_tf32(tmem_base, da_hi, db_hi, j == 0 ? 0u : 1u);
+                umma_tf32(tmem_base, da_lo, db_hi, 1u);
+                umma_tf32(tmem_base, da_hi, db_lo, 1u);
+            }
+            umma_commit(bar_mma);
+        }
+        __syncwarp();
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1u;
+        tc_fence_after();
+        // epilogue: lane = bin, column = frame; every store instruction of a warp writes 128 contiguous bytes of one row
+#pragma unroll 1
+        for (int c = 0; c < UT_FT / 16; ++c) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 16), v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (need_s[c * 16 + j] && bin_ok)
+                    Y[(f0 + c * 16 + j) * (int64_t)np + bin] = stream == 0 ? __expf(v[j]) : v[j];
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                                     // accumulator and feature tile are free again
+        ft = ft_next;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)UT_FT) : "memory");
+    }
+}
+
 }  // namespace
 
 size_t mel_tc_operand_bytes(int fft_len) { return (size_t)((fft_len / 2) / TC_KS) * 2 * TC_B_PART; }
@@ -272,6 +456,45 @@ cudaError_t launch_mel_gemm_tc(const MelArgs& a, cudaStream_t st) {
     dim3 grid((unsigned)((a.nfrm + TC_M - 1) / TC_M), 3);
     k_mel_gemm_tc<<<grid, TC_THREADS, TC_SMEM, st>>>((const float*)a.mag, (const float*)a.real, (const float*)a.imag, a.nfrm, H,
                                                       a.wt_tc_mag, a.wt_tc_ph, a.partial, n_slices, a.ncp_max, a.vidx, a.vcount);
+    return cudaGetLastError();
+}
+
+// ---- un-warp product ----
+size_t unwarp_tc_operand_bytes(int np, int K) { return (size_t)((np + UT_BT - 1) / UT_BT) * 2 * UT_BT * ut_kpad(K) * sizeof(float); }
+
+cudaError_t build_unwarp_matrix_tc(const float* U, int K, int np, float* out, cudaStream_t st) {
+    const int n_tiles = (np + UT_BT - 1) / UT_BT, kpad = ut_kpad(K);
+    const int n = n_tiles * UT_BT * kpad;
+    k_split_unwarp_tc<<<(n + 255) / 256, 256, 0, st>>>(U, K, np, kpad, n_tiles, out);
+    return cudaGetLastError();
+}
+
+bool unwarp_tc_usable(const UnwarpArgs& a) { return a.u_tc_mag && a.u_tc_ph && a.n_mag <= 64 && a.n_ph <= 64; }
+
+// xm / xr / xi: the float32 feature matrices (already narrowed by launch_mel_unwarp), a.flags already filled
+cudaError_t launch_mel_unwarp_tc(const UnwarpArgs& a, const float* xm, const float* xr, const float* xi, cudaStream_t st) {
+    const int tiles_mag = (a.HP + UT_BT - 1) / UT_BT, tiles_ph = (a.HBP + UT_BT - 1) / UT_BT;
+    const int kmax = a.n_mag > a.n_ph ? a.n_mag : a.n_ph, kp = ut_kpad(kmax);
+    const size_t smem = (size_t)2 * UT_BT * kp * 4 + (size_t)2 * UT_FT * kp * 4 + (((size_t)UT_FT * kmax * 4 + 15) & ~(size_t)15) + 128;
+    cudaError_t e = cudaFuncSetAttribute(k_mel_unwarp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mel_unwarp_tc, UT_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 512 / UT_FT) per_sm = 512 / UT_FT;                          // TMEM columns
+    const int64_t n_ft = (a.nfrm + UT_FT - 1) / UT_FT;
+    const int slots = a.num_sms * per_sm;
+    const double w_mag = (double)tiles_mag * a.n_mag, w_ph = 2.0 * tiles_ph * a.n_ph * 0.95;
+    int g_ph = (int)((double)slots * w_ph / (w_mag + w_ph) / (2 * tiles_ph));
+    if (g_ph < 1) g_ph = 1;
+    int g_mag = (slots - 2 * tiles_ph * g_ph) / tiles_mag;
+    if (g_mag < 1) g_mag = 1;
+    if (g_mag > n_ft) g_mag = (int)n_ft;
+    if (g_ph > n_ft) g_ph = (int)n_ft;
+    const unsigned grid = (unsigned)(tiles_mag * g_mag + 2 * tiles_ph * g_ph);
+    k_mel_unwarp_tc<<<grid, UT_THREADS, smem, st>>>(xm, xr, xi, a.need_ph, a.flags, a.nfrm, a.n_mag, a.n_ph, a.u_tc_mag, a.u_tc_ph,
+                                                    a.out_mag, a.out_real, a.out_imag, tiles_mag, tiles_ph, g_mag, g_ph, a.HP, a.HBP);
     return cudaGetLastError();
 }
 
