@@ -63,7 +63,7 @@ int mpb_mel_create(mpb_ctx* ctx, int fft_len, double alpha_mag, int n_mag, doubl
     CU(cudaMemcpy(m->cos_ph, cos_ph, sizeof(double) * n_ph * phase_dim, cudaMemcpyHostToDevice));
     CU(build_warp_matrix(fft_len, n_mag, alpha_mag, m->wt_mag, scratch, m->ld_mag, ctx->stream));
     CU(build_warp_matrix(fft_len, n_ph, alpha_ph, m->wt_ph, scratch, m->ld_ph, ctx->stream));
-    static const bool mel_tc = [] { const char* e = getenv("MPB_MEL_TC"); return e && atoi(e) > 0; }();
+    static const bool mel_tc = [] { const char* e = getenv("MPB_MEL_TC"); return e && (atoi(e) & 1); }();   // bit 0: warp product, bit 1: un-warp product
     if (mel_tc && m->ld_mag == 64 && m->ld_ph == 64) {       // experimental tensor-core tile product (mpb_mel_tc.cu)
         CU(cudaMalloc(&m->wt_tc_mag, mel_tc_operand_bytes(fft_len)));
         CU(cudaMalloc(&m->wt_tc_ph, mel_tc_operand_bytes(fft_len)));

@@ -49,7 +49,7 @@ int mpb_syn_create(mpb_ctx* ctx, int fft_len, int n_mag, int n_ph, int hb, const
     if (rc == MPB_OK) rc = upload_f32(u_ph, n_ph, hb, (hb + 3) & ~3, &s->u_ph);
     if (rc == MPB_OK) rc = upload_f32(tab, 3, H, H, &s->tab);
     if (rc != MPB_OK) { delete s; return rc; }
-    static const bool mel_tc = [] { const char* e = getenv("MPB_MEL_TC"); return e && atoi(e) > 0; }();
+    static const bool mel_tc = [] { const char* e = getenv("MPB_MEL_TC"); return e && (atoi(e) & 2); }();   // bit 0: warp product, bit 1: un-warp product
     if (mel_tc && n_mag <= 64 && n_ph <= 64) {               // experimental tensor-core un-warp product (mpb_mel_tc.cu)
         const int HP = (H + 3) & ~3, HBP = (hb + 3) & ~3;
         CU(cudaMalloc((void**)&s->u_tc_mag, unwarp_tc_operand_bytes(HP, n_mag)));

@@ -1,4 +1,4 @@
-// EXPERIMENTAL, OFF BY DEFAULT (MPB_MEL_TC=1 selects it when a plan is created).  Written at the end of round 1 after the
+// EXPERIMENTAL, OFF BY DEFAULT (environment MPB_MEL_TC, read when a plan is created: bit 0 = warp product, bit 1 = un-warp product).  Written at the end of round 1 after the
 // GPU budget was spent, to be brought up in round 2: k_mel_gemm_tc has run exactly once on a B200
 // (the fused compressed-analysis parity test passed with it, profiles/r1b/mel_tc_first_run.txt) and has never been timed;
 // k_mel_unwarp_tc (second half of this file) has only been compiled.
