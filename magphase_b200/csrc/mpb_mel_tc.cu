@@ -1,4 +1,5 @@
-// EXPERIMENTAL, OFF BY DEFAULT (environment MPB_MEL_TC, read when a plan is created: bit 0 = warp product, bit 1 = un-warp product).  Written at the end of round 1 after the
+// EXPERIMENTAL, OFF BY DEFAULT (environment MPB_MEL_TC, read when a plan is created: bit 0 = warp product, bit 1 = un-warp product,
+// bit 2 = deeper load pipeline in the warp product).  Written at the end of round 1 after the
 // GPU budget was spent, to be brought up in round 2: k_mel_gemm_tc has run exactly once on a B200
 // (the fused compressed-analysis parity test passed with it, profiles/r1b/mel_tc_first_run.txt) and has never been timed;
 // k_mel_unwarp_tc (second half of this file) has only been compiled.
@@ -26,6 +27,8 @@
 //   warp  8    one lane issues the tcgen05.mma instructions, tcgen05.commit releases the stage / signals the epilogue;
 //   warps 0-3  epilogue: tcgen05.ld of the n_slices x 64 accumulator columns -> partial sums in HBM.
 // A 4-stage ring of full / empty mbarriers connects them.
+#include <stdlib.h>
+
 #include "mpb_kernels.h"
 #include "mpb_tma.cuh"
 
@@ -104,6 +107,8 @@ __global__ void k_split_warp_tc(const float* __restrict__ wt, int ld, int n_stag
     out[off + TC_B_PART / 4] = lo;
 }
 
+// DEEP: the producers keep three stages of row loads in flight instead of one (untested variant, MPB_MEL_TC bit 2)
+template <bool DEEP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_mel_gemm_tc(const float* __restrict__ mag, const float* __restrict__ real, const float* __restrict__ imag, int64_t nfrm,
               int H, const float* __restrict__ btc_mag, const float* __restrict__ btc_ph, float* __restrict__ partial,
@@ -146,8 +151,45 @@ k_mel_gemm_tc(const float* __restrict__ mag, const float* __restrict__ real, con
 
     if (warp < 8) {
         // ---- producers: warp w owns tile rows 16w .. 16w+15, lane = bin inside the stage ----
-        float cur[16], nxt[16];
         const int m0 = warp * 16;
+        if constexpr (DEEP) {
+            float buf[4][16];                                                // ring of register buffers: stage s lives in buf[s % 4]
+            auto load_stage = [&](int st, float* dst) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int fr = rowmap[m0 + i];
+                    dst[i] = fr >= 0 ? __ldcs(src + (int64_t)fr * H + st * TC_KS + lane) : 0.0f;
+                }
+            };
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                if (p < n_stages) load_stage(p, buf[p]);
+#pragma unroll 1
+            for (int s0 = 0; s0 < n_stages; s0 += 4) {                       // n_stages is a multiple of 8
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int s = s0 + u;
+                    if (s + 3 < n_stages) load_stage(s + 3, buf[(u + 3) & 3]);
+                    const int slot = s % TC_ST, it = s / TC_ST;
+                    if (it > 0) mbar_wait(&empty[slot], (uint32_t)((it - 1) & 1));
+                    uint8_t* a_hi = smem + slot * TC_STAGE;
+                    uint8_t* a_lo = a_hi + TC_A_PART;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int m = m0 + i;
+                        const int off = (m >> 3) * TC_SBO_A + (lane >> 2) * TC_LBO_A + (m & 7) * 16 + (lane & 3) * 4;
+                        const float x = buf[u][i];
+                        const float hi = __uint_as_float(__float_as_uint(x) & TF32_MASK);
+                        const float lo = __uint_as_float(__float_as_uint(x - hi) & TF32_MASK);
+                        *reinterpret_cast<float*>(a_hi + off) = hi;
+                        *reinterpret_cast<float*>(a_lo + off) = lo;
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(&full[slot]);
+                }
+            }
+        } else {
+        float cur[16], nxt[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int fr = rowmap[m0 + i];
@@ -180,6 +222,7 @@ k_mel_gemm_tc(const float* __restrict__ mag, const float* __restrict__ real, con
             mbar_arrive(&full[slot]);
 #pragma unroll
             for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+        }
         }
         // ---- epilogue: warps 0-3 read the TMEM lanes 32w .. 32w+31 (= tile rows) ----
         if (warp < 4) {
@@ -451,10 +494,12 @@ cudaError_t build_warp_matrix_tc(int fft_len, const float* wt32, int ld, float* 
 cudaError_t launch_mel_gemm_tc(const MelArgs& a, cudaStream_t st) {
     const int H = a.fft_len / 2 + 1;
     const int n_slices = (H - 1) / MEL_KSLICE;
-    cudaError_t e = cudaFuncSetAttribute(k_mel_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    static const bool deep = [] { const char* e = getenv("MPB_MEL_TC"); return e && (atoi(e) & 4); }();
+    auto kern = deep ? k_mel_gemm_tc<true> : k_mel_gemm_tc<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((a.nfrm + TC_M - 1) / TC_M), 3);
-    k_mel_gemm_tc<<<grid, TC_THREADS, TC_SMEM, st>>>((const float*)a.mag, (const float*)a.real, (const float*)a.imag, a.nfrm, H,
+    kern<<<grid, TC_THREADS, TC_SMEM, st>>>((const float*)a.mag, (const float*)a.real, (const float*)a.imag, a.nfrm, H,
                                                       a.wt_tc_mag, a.wt_tc_ph, a.partial, n_slices, a.ncp_max, a.vidx, a.vcount);
     return cudaGetLastError();
 }
