@@ -212,3 +212,59 @@ def test_griffin_lim_matches_reference(ref_modules):
         np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-12)
         strong = mag > 1e-6 * mag.max()
         assert np.max(np.abs(np.angle(np.exp(1j * (ph - ph_ref))))[strong]) < 1e-8
+
+
+def test_const_rate_reverse_scan_is_bit_exact_against_reference(ref_modules):
+    """get_shifts_and_frm_locs_from_const_shifts (src/magphase.py:1426-1449): the reference walks back with scipy's
+    interp1d until it raises; the oracle and the host mirror use np.interp with explicit range checks.  The shifts are
+    truncated to integers downstream (:879), so the three must agree to the last bit -- randomised tracks, both rates."""
+    import magphase_b200.magphase as host
+    mp, la, lu = ref_modules
+    rng = np.random.default_rng(11)
+    for trial in range(24):
+        fs = (48000, 16000)[trial % 2]
+        n = int(rng.integers(3, 400))
+        f0 = rng.uniform(60, 380, n)
+        f0[rng.uniform(size=n) < 0.35] = 0.0                      # unvoiced stretches
+        v_shift_c = orc.f0_to_shift(f0, fs)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            s_ref, l_ref = mp.get_shifts_and_frm_locs_from_const_shifts(v_shift_c.copy(), 5.0, fs, interp_type='linear')
+        s_orc, l_orc = orc.get_shifts_and_frm_locs_from_const_shifts(v_shift_c, 5.0, fs)
+        s_host, l_host = host.get_shifts_and_frm_locs_from_const_shifts(v_shift_c, 5.0, fs)
+        for s, l in ((s_orc, l_orc), (s_host, l_host)):
+            assert s.shape == np.shape(s_ref) and np.array_equal(s, s_ref), (trial, fs, n)
+            assert np.array_equal(l, l_ref), (trial, fs, n)
+
+
+def test_const_to_variable_rate_rows_match_reference(ref_modules):
+    """interp_from_const_to_variable_rate (src/magphase.py:2242-2252) against the row pairs + weights the kernels use."""
+    import magphase_b200.magphase as host
+    mp, la, lu = ref_modules
+    rng = np.random.default_rng(12)
+    for fs in (48000, 16000):
+        n_c = 120
+        step = fs * 5.0 / 1000
+        data = rng.normal(size=(n_c, 6))
+        locs = np.sort(rng.uniform(step, step * n_c, 300))
+        locs[0], locs[-1] = step, step * n_c                      # both ends of the interpolation range
+        ref = mp.interp_from_const_to_variable_rate(data.copy(), locs, 5.0, fs, interp_type='linear')
+        r0, r1, w = host._const_rate_rows(locs, n_c, step)
+        got = data[r0] + (data[r1] - data[r0]) * w[:, None]
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-13)
+        np.testing.assert_allclose(orc.interp_from_const_to_variable_rate(data, locs, 5.0, fs), ref, rtol=0, atol=1e-14)
+
+
+def test_intermediate_epochs_match_reference(ref_modules):
+    """nwin_per_pitch_period >= 1 (src/magphase.py:280-288): the host mirror's epoch expansion followed by its frame
+    geometry gives the reference's v_shift, integer for integer."""
+    import magphase_b200.magphase as host
+    mp, la, lu = ref_modules
+    sig, pm, voi = synth_utterance(5, fs=48000, dur_s=0.6)
+    for nwin in (1.0, 2.0):
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            _, v_shift_ref = mp.analysis_with_del_comp_from_pm(sig.copy(), 48000, pm.copy(), nwin_per_pitch_period=nwin)
+        v_pm = host._expand_epochs(np.asarray(pm, dtype=np.float64), nwin)
+        _, v_shift, _ = host.frame_geometry(v_pm, sig.size)
+        assert np.array_equal(v_shift, v_shift_ref), nwin
