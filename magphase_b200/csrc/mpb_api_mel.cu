@@ -150,6 +150,7 @@ static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const vo
         a.voi = voi + f0; a.nfrm = n; a.fft_len = m->fft_len;
         a.wt_mag = m->wt_mag; a.ld_mag = m->ld_mag; a.wt_ph = m->wt_ph; a.ld_ph = m->ld_ph;
         a.wt_tc_mag = m->wt_tc_mag; a.wt_tc_ph = m->wt_tc_ph;
+        a.partial_slices = 0;
         a.cos_mag = m->cos_mag; a.n_mag = m->n_mag; a.cos_ph = m->cos_ph; a.n_ph = m->n_ph; a.phase_dim = m->phase_dim;
         a.partial = (float*)m->partial.p; a.ncp_max = ncp;
         a.out_mag = (char*)out_mag_mel + oes * f0 * od_mag;
@@ -160,6 +161,7 @@ static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const vo
         if (lerp.raw_mc) { a.vidx = nullptr; a.cidx = nullptr; a.vcount = nullptr; }   // every frame, every stream
         else LAUNCH(m->ctx, (cudaStream_t)stream, "k_voiced_compact",
                     launch_voiced_compact(a.voi, (int)n, d_vidx, d_cidx, d_cnt, (cudaStream_t)stream));
+        if (mel_tc_usable(a) && mel_tc_sums_slices()) a.partial_slices = 1;   // experimental: slice sums inside the tensor-core kernel
         LAUNCH(m->ctx, (cudaStream_t)stream, "k_mel_gemm", launch_mel_gemm(a, (cudaStream_t)stream));
         LAUNCH(m->ctx, (cudaStream_t)stream, "k_mel_finish", launch_mel_finish(a, (cudaStream_t)stream));
     }

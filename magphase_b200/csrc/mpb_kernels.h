@@ -62,6 +62,7 @@ struct MelArgs {
     const int32_t* vidx; const int32_t* cidx; const int32_t* vcount;        // voiced-frame compaction (NULL: off)
     const int32_t* lerp_r0; const int32_t* lerp_r1; const float* lerp_w;    // output frame f = lerp of two source rows (NULL: off)
     const float* wt_tc_mag = nullptr; const float* wt_tc_ph = nullptr;      // pre-split tensor-core operands (experimental, mpb_mel_tc.cu; NULL: off)
+    int partial_slices = 0;                                                 // 0: one partial per K slice (default); 1: `partial` already holds the slice sums
 };
 cudaError_t launch_voiced_compact(const uint8_t* voi, int n, int32_t* vidx, int32_t* cidx, int32_t* count, cudaStream_t st);
 cudaError_t build_warp_matrix(int fft_len, int n_out, double alpha, float* wt32, double* scratch64, int ld,
@@ -71,6 +72,7 @@ cudaError_t launch_mel_finish(const MelArgs& a, cudaStream_t st);
 // experimental tcgen05 variant of the tile product (mpb_mel_tc.cu); selected by MPB_MEL_TC=1 when the plan was created
 size_t mel_tc_operand_bytes(int fft_len);
 bool mel_tc_usable(const MelArgs& a);
+bool mel_tc_sums_slices();
 cudaError_t build_warp_matrix_tc(int fft_len, const float* wt32, int ld, float* out, cudaStream_t st);
 cudaError_t launch_mel_gemm_tc(const MelArgs& a, cudaStream_t st);
 

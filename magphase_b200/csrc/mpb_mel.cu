@@ -342,7 +342,7 @@ cudaError_t launch_mel_gemm(const MelArgs& a, cudaStream_t st) {
 template <typename TF, typename TO, bool PRE, bool LERP>
 static cudaError_t launch_finish_t(const MelArgs& a, cudaStream_t st) {
     const int H = a.fft_len / 2 + 1;
-    const int n_slices = (H - 1) / MEL_KSLICE;
+    const int n_slices = a.partial_slices > 0 ? a.partial_slices : (H - 1) / MEL_KSLICE;
     dim3 g2((unsigned)((a.nfrm + 3) / 4), 3);
     k_mel_finish<TF, TO, PRE, LERP><<<g2, 128, 0, st>>>(a.partial, n_slices, a.ncp_max, a.nfrm, (const TF*)a.mag, (const TF*)a.real,
                                                    (const TF*)a.imag, H, a.wt_mag, a.ld_mag, a.wt_ph, a.ld_ph, a.cos_mag,

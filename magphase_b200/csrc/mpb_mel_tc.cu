@@ -1,5 +1,5 @@
 // EXPERIMENTAL, OFF BY DEFAULT (environment MPB_MEL_TC, read when a plan is created: bit 0 = warp product, bit 1 = un-warp product,
-// bit 2 = deeper load pipeline in the warp product).  Written at the end of round 1 after the
+// bit 2 = deeper load pipeline in the warp product, bit 3 = K-slice sums inside the warp-product kernel).  Written at the end of round 1 after the
 // GPU budget was spent, to be brought up in round 2: k_mel_gemm_tc has run exactly once on a B200
 // (the fused compressed-analysis parity test passed with it, profiles/r1b/mel_tc_first_run.txt) and has never been timed;
 // k_mel_unwarp_tc (second half of this file) has only been compiled.
@@ -108,7 +108,9 @@ __global__ void k_split_warp_tc(const float* __restrict__ wt, int ld, int n_stag
 }
 
 // DEEP: the producers keep three stages of row loads in flight instead of one (untested variant, MPB_MEL_TC bit 2)
-template <bool DEEP>
+// SUM: the epilogue adds the K-slice accumulators in float64 itself and writes ONE float32 partial per coefficient
+// (partial[stream][row][1][64]); k_mel_finish then runs with n_slices = 1 (untested variant, MPB_MEL_TC bit 3)
+template <bool DEEP, bool SUM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_mel_gemm_tc(const float* __restrict__ mag, const float* __restrict__ real, const float* __restrict__ imag, int64_t nfrm,
               int H, const float* __restrict__ btc_mag, const float* __restrict__ btc_ph, float* __restrict__ partial,
@@ -230,6 +232,28 @@ k_mel_gemm_tc(const float* __restrict__ mag, const float* __restrict__ real, con
             tc_fence_after();
             const int r = warp * 32 + lane;
             const bool valid = rowmap[r] >= 0;
+            if constexpr (SUM) {
+                float* po = partial + ((size_t)stream * (size_t)nfrm + (size_t)(f0 + r)) * ncp_max;
+#pragma unroll 1
+                for (int c = 0; c < TC_N / 16; ++c) {
+                    double acc[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+#pragma unroll 1
+                    for (int sl = 0; sl < n_slices; ++sl) {                  // slice order, like k_mel_finish
+                        float v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sl * TC_N + c * 16), v);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] += (double)v[j];
+                    }
+                    if (valid) {
+                        float4* q = reinterpret_cast<float4*>(po + c * 16);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            q[j] = make_float4((float)acc[4 * j], (float)acc[4 * j + 1], (float)acc[4 * j + 2], (float)acc[4 * j + 3]);
+                    }
+                }
+            } else {
             float* po = partial + (size_t)stream * (size_t)nfrm * n_slices * ncp_max + (size_t)(f0 + r) * n_slices * ncp_max;
 #pragma unroll 1
             for (int sl = 0; sl < n_slices; ++sl) {
@@ -243,6 +267,7 @@ k_mel_gemm_tc(const float* __restrict__ mag, const float* __restrict__ real, con
                         for (int j = 0; j < 4; ++j) q[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
                 }
+            }
             }
             tc_fence_before();
         }
@@ -479,6 +504,12 @@ k_mel_unwarp_tc(const float* __restrict__ mag_mel, const float* __restrict__ rea
 
 size_t mel_tc_operand_bytes(int fft_len) { return (size_t)((fft_len / 2) / TC_KS) * 2 * TC_B_PART; }
 
+// MPB_MEL_TC bit 3: the tensor-core kernel sums the K slices itself (see SUM above)
+bool mel_tc_sums_slices() {
+    static const bool on = [] { const char* e = getenv("MPB_MEL_TC"); return e && (atoi(e) & 8); }();
+    return on;
+}
+
 bool mel_tc_usable(const MelArgs& a) {
     return a.wt_tc_mag && a.wt_tc_ph && a.pre_logp && a.feat_dtype == MPB_F32 && !a.lerp_r0 && a.ncp_max == TC_N &&
            a.ld_mag == TC_N && a.ld_ph == TC_N;
@@ -495,7 +526,9 @@ cudaError_t launch_mel_gemm_tc(const MelArgs& a, cudaStream_t st) {
     const int H = a.fft_len / 2 + 1;
     const int n_slices = (H - 1) / MEL_KSLICE;
     static const bool deep = [] { const char* e = getenv("MPB_MEL_TC"); return e && (atoi(e) & 4); }();
-    auto kern = deep ? k_mel_gemm_tc<true> : k_mel_gemm_tc<false>;
+    const bool sum = a.partial_slices == 1;
+    auto kern = deep ? (sum ? k_mel_gemm_tc<true, true> : k_mel_gemm_tc<true, false>)
+                     : (sum ? k_mel_gemm_tc<false, true> : k_mel_gemm_tc<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((a.nfrm + TC_M - 1) / TC_M), 3);

@@ -1,18 +1,18 @@
 #!/bin/bash
 # Runs ON THE GPU BOX (gpurun --timeout 900 -- 'bash profiles/tc_bringup.sh'): first measurements of the experimental
 # tensor-core tile products (magphase_b200/csrc/mpb_mel_tc.cu; MPB_MEL_TC bit 0 = warp product, bit 1 = un-warp product,
-# bit 2 = warp product with three stages of row loads in flight).
+# bit 2 = warp product with three stages of row loads in flight, bit 3 = K-slice sums inside the warp-product kernel).
 # Every step runs under its own timeout so that a hanging kernel (mbarrier deadlock) cannot hold the box.
 # Order: cheapest evidence first.  Logs land in gpurun_out/tc_*.log.
 mkdir -p gpurun_out
 T="timeout 120"
-for m in 1 5 2 3; do
+for m in 1 5 9 2 3; do
   MPB_MEL_TC=$m $T python -m pytest tests/test_gpu_compressed_analysis.py tests/test_gpu_compressed_synthesis.py tests/test_gpu_full_size.py \
       tests/test_gpu_host_pipeline.py -x -q > gpurun_out/tc_tests_$m.log 2>&1
   echo "MPB_MEL_TC=$m tests rc=$?" | tee -a gpurun_out/tc_summary.log
   tail -3 gpurun_out/tc_tests_$m.log | tee -a gpurun_out/tc_summary.log
 done
-for m in 0 1 5 2 7; do
+for m in 0 1 5 9 13 2 15; do
   MPB_MEL_TC=$m $T python bench.py --no-cpu-baseline --steps 10 --warmup 3 > gpurun_out/tc_bench_$m.log 2>&1
   echo "MPB_MEL_TC=$m bench rc=$?" | tee -a gpurun_out/tc_summary.log
   python profiles/show_bench.py gpurun_out/tc_bench_$m.log 2>/dev/null | head -20 | tee -a gpurun_out/tc_summary.log
