@@ -162,18 +162,22 @@ static cudaError_t launch_analysis_m(const AnalysisArgs& a, cudaStream_t st) {
                               : launch_analysis_t<T, TS, TO, N, MODE_FEATS>(a, st);
 }
 
-// float32 log periodograms for the fused compressed analysis (float64 butterflies, float32 or float64 signal)
-template <typename TS>
+// float32 log periodograms for the fused compressed analysis (float64 butterflies, float32 or float64 signal).
+// T = float is an experiment (MPB_LOGP_F32=1, off by default, never run): the mel products average the per-bin round-off
+// of float32 butterflies, a CPU emulation stays 40x under the 1e-5 bar (profiles/f32_fft_compressed_emulation.py).
+template <typename T, typename TS>
 static cudaError_t launch_logp_n(const AnalysisArgs& a, cudaStream_t st) {
     switch (a.fft_len) {
-        case 1024: return launch_analysis_t<double, TS, float, 1024, MODE_LOGP>(a, st);
-        case 2048: return launch_analysis_t<double, TS, float, 2048, MODE_LOGP>(a, st);
-        case 4096: return launch_analysis_t<double, TS, float, 4096, MODE_LOGP>(a, st);
+        case 1024: return launch_analysis_t<T, TS, float, 1024, MODE_LOGP>(a, st);
+        case 2048: return launch_analysis_t<T, TS, float, 2048, MODE_LOGP>(a, st);
+        case 4096: return launch_analysis_t<T, TS, float, 4096, MODE_LOGP>(a, st);
     }
     return cudaErrorInvalidValue;
 }
 cudaError_t launch_analysis_logp(const AnalysisArgs& a, cudaStream_t st) {
-    return a.sig_dtype == MPB_F64 ? launch_logp_n<double>(a, st) : launch_logp_n<float>(a, st);
+    if (a.compute_dtype == MPB_F32)
+        return a.sig_dtype == MPB_F64 ? launch_logp_n<float, double>(a, st) : launch_logp_n<float, float>(a, st);
+    return a.sig_dtype == MPB_F64 ? launch_logp_n<double, double>(a, st) : launch_logp_n<double, float>(a, st);
 }
 
 template <typename T, typename TS, typename TO>

@@ -189,8 +189,11 @@ int mpb_analysis_compressed_dev(mpb_mel* m, void* stream, const void* sig, int s
         std::lock_guard<std::mutex> lk(m->mu);
         for (int i = 0; i < 3; ++i) CU(m->feats[i].need(sizeof(float) * (size_t)chunk * H));
     }
+    // float64 butterflies (default); MPB_LOGP_F32=1 selects the float32 engine for this fused path only (experiment, see
+    // launch_analysis_logp)
+    static const int logp_compute = [] { const char* e = getenv("MPB_LOGP_F32"); return (e && atoi(e) > 0) ? MPB_F32 : MPB_F64; }();
     const void* tw = nullptr;
-    int rc = get_twiddles(ctx, m->fft_len, MPB_F64, &tw);
+    int rc = get_twiddles(ctx, m->fft_len, logp_compute, &tw);
     if (rc != MPB_OK) return rc;
     const size_t oes = out_dtype == MPB_F64 ? 8 : 4;
     cudaStream_t st = (cudaStream_t)stream;
@@ -199,7 +202,7 @@ int mpb_analysis_compressed_dev(mpb_mel* m, void* stream, const void* sig, int s
         AnalysisArgs a;
         a.sig = sig; a.sig_dtype = sig_dtype; a.n_sig = n_sig;
         a.centre = centre + f0; a.left = left + f0; a.right = right + f0; a.win = nullptr;
-        a.nfrm = n; a.fft_len = m->fft_len; a.compute_dtype = MPB_F64; a.tw = tw;
+        a.nfrm = n; a.fft_len = m->fft_len; a.compute_dtype = logp_compute; a.tw = tw;
         a.out_a = m->feats[0].p; a.out_b = m->feats[1].p; a.out_c = m->feats[2].p; a.out_dtype = MPB_F32;
         a.mode = MODE_LOGP; a.num_sms = ctx->num_sms; a.ph_mask = voi + f0;
         LAUNCH(ctx, st, "k_analysis<logp>", launch_analysis_logp(a, st));

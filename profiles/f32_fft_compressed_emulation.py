@@ -1,0 +1,34 @@
+"""CPU experiment: does the COMPRESSED analysis need float64 butterflies?
+
+The lossless features need them (normalised real / imag of near-silent bins miss 1e-5 RMS with float32 butterflies,
+DESIGN.md "Precision").  The compressed features are mel-warped projections of those rows (60 + 45 + 45 smooth
+combinations of 2049 bins), which average the per-bin round-off.  This script runs the oracle's analysis with a float32
+FFT (scipy.fft on float32 frames, pocketfft single precision: the same error class as a float32 radix-16 engine) and a
+float64 FFT and compares the outputs of format_for_modelling.   python profiles/f32_fft_compressed_emulation.py
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.fft
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import magphase_oracle as orc
+from magphase_b200.synth import synth_utterance
+
+rms = lambda a, b: float(np.sqrt(np.mean((a - b) ** 2)))
+for fs, N, uid in ((48000, 4096, 3), (48000, 4096, 7), (16000, 2048, 5)):
+    sig, pm, voi = synth_utterance(uid, fs, 2.0)
+    frms, v_shift, _ = orc.analysis_frames(sig, pm, N)
+    H = N // 2 + 1
+    X64 = np.fft.fft(frms)[:, :H]
+    X32 = scipy.fft.fft(frms.astype(np.float32), axis=1)[:, :H].astype(np.complex128)
+    assert scipy.fft.fft(frms.astype(np.float32), axis=1).dtype == np.complex64
+    f64 = orc.compute_lossless_feats(X64, v_shift, voi, fs)
+    f32 = orc.compute_lossless_feats(X32, v_shift, voi, fs)
+    print('fs %d N %d frames %d: lossless rms  mag %.2e  real %.2e  imag %.2e' % (fs, N, len(v_shift), rms(f32[0], f64[0]), rms(f32[1], f64[1]), rms(f32[2], f64[2])))
+    c64 = orc.format_for_modelling(*f64, fs, mag_dim=60, phase_dim=45)
+    c32 = orc.format_for_modelling(*f32, fs, mag_dim=60, phase_dim=45)
+    print('    compressed rms  mag_mel_log %.2e  real_mel %.2e  imag_mel %.2e   (bar 1e-5)' % (rms(c32[0], c64[0]), rms(c32[1], c64[1]), rms(c32[2], c64[2])))
+    print('    compressed max  mag_mel_log %.2e  real_mel %.2e  imag_mel %.2e' % (np.abs(c32[0] - c64[0]).max(), np.abs(c32[1] - c64[1]).max(), np.abs(c32[2] - c64[2]).max()))

@@ -17,6 +17,13 @@ for m in 0 1 5 9 13 2 15; do
   echo "MPB_MEL_TC=$m bench rc=$?" | tee -a gpurun_out/tc_summary.log
   python profiles/show_bench.py gpurun_out/tc_bench_$m.log 2>/dev/null | head -20 | tee -a gpurun_out/tc_summary.log
 done
+# float32 butterflies in the fused compressed analysis (MPB_LOGP_F32=1), alone and with the best tensor-core setting
+MPB_LOGP_F32=1 $T python -m pytest tests/test_gpu_compressed_analysis.py tests/test_gpu_full_size.py tests/test_gpu_host_pipeline.py -x -q > gpurun_out/tc_tests_f32.log 2>&1
+echo "MPB_LOGP_F32=1 tests rc=$?" | tee -a gpurun_out/tc_summary.log; tail -3 gpurun_out/tc_tests_f32.log | tee -a gpurun_out/tc_summary.log
+MPB_LOGP_F32=1 $T python bench.py --no-cpu-baseline --steps 10 --warmup 3 > gpurun_out/tc_bench_f32.log 2>&1
+python profiles/show_bench.py gpurun_out/tc_bench_f32.log 2>/dev/null | head -20 | tee -a gpurun_out/tc_summary.log
+MPB_LOGP_F32=1 MPB_MEL_TC=15 $T python bench.py --no-cpu-baseline --steps 10 --warmup 3 > gpurun_out/tc_bench_f32_tc15.log 2>&1
+python profiles/show_bench.py gpurun_out/tc_bench_f32_tc15.log 2>/dev/null | head -20 | tee -a gpurun_out/tc_summary.log
 # one full capture of the two tensor-core kernels (launch counts: see the launch list first if -s / -c need adjusting)
 B="python bench.py --no-cpu-baseline --utts 32 --e2e-utts 2 --steps 1 --warmup 3"
 MPB_MEL_TC=3 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/tc_launches.csv $B > gpurun_out/tc_ncu_l.log 2>&1
