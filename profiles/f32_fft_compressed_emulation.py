@@ -32,3 +32,23 @@ for fs, N, uid in ((48000, 4096, 3), (48000, 4096, 7), (16000, 2048, 5)):
     c32 = orc.format_for_modelling(*f32, fs, mag_dim=60, phase_dim=45)
     print('    compressed rms  mag_mel_log %.2e  real_mel %.2e  imag_mel %.2e   (bar 1e-5)' % (rms(c32[0], c64[0]), rms(c32[1], c64[1]), rms(c32[2], c64[2])))
     print('    compressed max  mag_mel_log %.2e  real_mel %.2e  imag_mel %.2e' % (np.abs(c32[0] - c64[0]).max(), np.abs(c32[1] - c64[1]).max(), np.abs(c32[2] - c64[2]).max()))
+
+# the bundled natural recordings (only where /root/reference exists): quiet high-frequency bins make this the harder case
+d = '/root/reference/demos/data_48k/wavs_nat'
+if os.path.isdir(d):
+    from scipy.io import wavfile
+    from magphase_b200.synth import synth_marks_for_wav
+    for name in sorted(os.listdir(d))[:4]:
+        fs, x = wavfile.read(os.path.join(d, name))
+        sig = x.astype(np.float64) / 32768.0
+        pm, voi = synth_marks_for_wav(sig.size, fs)
+        N = 4096; H = N // 2 + 1
+        frms, v_shift, _ = orc.analysis_frames(sig, pm, N)
+        X64 = np.fft.fft(frms)[:, :H]
+        X32 = scipy.fft.fft(frms.astype(np.float32), axis=1)[:, :H].astype(np.complex128)
+        f64 = orc.compute_lossless_feats(X64, v_shift, voi, fs)
+        f32 = orc.compute_lossless_feats(X32, v_shift, voi, fs)
+        c64 = orc.format_for_modelling(*f64, fs, mag_dim=60, phase_dim=45)
+        c32 = orc.format_for_modelling(*f32, fs, mag_dim=60, phase_dim=45)
+        print('%s frames %d: lossless rms real %.2e imag %.2e | compressed rms mag_mel_log %.2e real_mel %.2e imag_mel %.2e' % (
+            name, len(v_shift), rms(f32[1], f64[1]), rms(f32[2], f64[2]), rms(c32[0], c64[0]), rms(c32[1], c64[1]), rms(c32[2], c64[2])))
