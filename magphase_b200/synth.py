@@ -56,6 +56,21 @@ def synth_utterance(u, fs=48000, dur_s=5.0):
     return v_sig, pm, vv
 
 
+def synth_utterance_band_limited(u, fs=48000, dur_s=5.0, cutoff_hz=7000.0, floor_db=-72.0):
+    """synth_utterance(u) through a steep low-pass plus a faint white floor, re-quantised to int16 steps: quiet
+    high-frequency bins like those of a studio recording -- the hard case for anything computed in float32 (normalised
+    real / imag of near-silent bins).  floor_db=None leaves only the quantisation noise (about -100 dB) above the cut-off,
+    which is harder than any real recording.  Sensitivity to float32 butterflies, measured on the CPU with the oracle
+    (profiles/f32_fft_compressed_emulation.py): see that script's output."""
+    v_sig, pm, vv = synth_utterance(u, fs=fs, dur_s=dur_s)
+    sos = signal.butter(10, cutoff_hz / (fs / 2.0), btype='lowpass', output='sos')
+    y = signal.sosfilt(sos, v_sig)
+    if floor_db is not None:
+        rng = np.random.Generator(np.random.PCG64(9000 + int(u)))
+        y = y + rng.uniform(-1, 1, y.size) * (10.0 ** (floor_db / 20.0))
+    return np.clip(np.round(y * 32768.0), -32768, 32767) / 32768.0, pm, vv
+
+
 def synth_marks_for_wav(n_smpls, fs=48000, seed=0):
     """Deterministic pitch marks + voicing for an arbitrary (e.g. bundled natural) waveform."""
     rng = np.random.Generator(np.random.PCG64(7000 + int(seed)))

@@ -48,3 +48,17 @@ def test_binfile_and_wav_round_trip(tmp_path):
     assert fs == 48000 and y.shape == sig.shape
     assert abs(np.max(np.abs(y)) - 0.98) < 1e-3                                  # peak-normalised to 0.98
     assert np.max(np.abs(y - 0.98 * sig / np.max(np.abs(sig)))) <= 1.0 / 32768 + 1e-12
+
+
+def test_band_limited_synthetic_utterance():
+    """synth_utterance_band_limited: same marks as synth_utterance, int16-exact samples, high band at the faint floor."""
+    from magphase_b200.synth import synth_utterance, synth_utterance_band_limited
+    a = synth_utterance(3, 48000, 0.5)
+    b = synth_utterance_band_limited(3, 48000, 0.5)
+    b2 = synth_utterance_band_limited(3, 48000, 0.5)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(b[0], b2[0])
+    assert np.array_equal(np.round(b[0] * 32768.0), b[0] * 32768.0)
+    spec = np.abs(np.fft.rfft(b[0] * np.hanning(b[0].size)))
+    f = np.fft.rfftfreq(b[0].size, 1.0 / 48000)
+    lo, hi = spec[(f > 300) & (f < 3000)].max(), spec[f > 10000].max()
+    assert 20 * np.log10(hi / lo) < -50.0
