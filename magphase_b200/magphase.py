@@ -519,7 +519,8 @@ def analysis_compressed_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None, mag_di
     centre, left, right, voi8, f0_med, frm_off = _analysis_geometry_c(l_pm_smpls, sizes, l_voi, fs)
     _check_frames(left, right, fft_len)
     lf0_all = f0_to_lf0(f0_med)                                               # np.log: a fresh array
-    lefts = [left[frm_off[u]:frm_off[u + 1]] for u in range(len(l_sig))]
+    shift_all = left.astype(int)                                              # one copy out of the reusable workspace
+    lefts = [shift_all[frm_off[u]:frm_off[u + 1]] for u in range(len(l_sig))]
     lf0s = [lf0_all[frm_off[u]:frm_off[u + 1]] for u in range(len(l_sig))]
     sigs = [np.ascontiguousarray(s, dtype=np.float64) for s in l_sig]      # no copy for float64 arrays
     sig_ptrs = (C.c_void_p * len(sigs))(*[s.ctypes.data for s in sigs])
@@ -532,7 +533,7 @@ def analysis_compressed_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None, mag_di
     out, a = [], 0
     for u in range(len(l_sig)):
         b = a + lefts[u].size
-        out.append((o_mag[a:b], o_real[a:b], o_imag[a:b], lf0s[u], lefts[u].astype(int), fs, fft_len))
+        out.append((o_mag[a:b], o_real[a:b], o_imag[a:b], lf0s[u], lefts[u], fs, fft_len))
         a = b
     return out
 
