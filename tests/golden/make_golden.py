@@ -25,7 +25,7 @@ warnings.simplefilter('ignore')
 import magphase as mp  # noqa: E402  (the reference)
 import libaudio as la  # noqa: E402
 
-from magphase_b200.synth import synth_utterance  # noqa: E402
+from magphase_b200.synth import synth_marks_for_wav, synth_utterance  # noqa: E402
 
 REF_DATA = '/root/reference/demos/data_48k'
 BIN_STEP = 32
@@ -96,10 +96,48 @@ def griffin_lim():
     print('griffin_lim:', {k: v.shape for k, v in out.items()})
 
 
+def natural():
+    """BASELINE config 1 names a bundled natural recording (demos/demo_copy_synthesis_lossless.py:57-91 on
+    demos/data_48k/wavs_nat/hvd_593.wav).  REAPER is not available, so the marks come from synth_marks_for_wav (seeded);
+    everything downstream of the marks is the real reference: analysis_with_del_comp_from_pm (src/magphase.py:266-334),
+    compute_lossless_feats (:457-476), synthesis_from_lossless (:1759-1776), synthesis_from_compressed (:825-997).  The
+    compressed features are the oracle's format_for_modelling of the reference's lossless features (SPTK mcep restated,
+    unpinned).  Half-second slices (24,000 int16 samples each) of two recordings: silence -> onset -> vowel, and a
+    stretch with quiet high-frequency bins -- the hard case for float32 butterflies."""
+    import magphase_oracle as orc
+    from scipy.io import wavfile
+    fs = 48000
+    out = {}
+    for tag, name, a, seed in (('a', 'hvd_593', 12000, 593), ('b', 'hvd_577', 48000, 577)):
+        fs_w, x = wavfile.read(os.path.join(REF_DATA, 'wavs_nat', name + '.wav'))
+        assert fs_w == fs and x.dtype == np.int16
+        x = x[a:a + 24000]
+        sig = x.astype(np.float64) / 32768.0                       # sf.read of PCM16
+        pm, voi = synth_marks_for_wav(sig.size, fs=fs, seed=seed)
+        m_fft, v_shift = mp.analysis_with_del_comp_from_pm(sig, fs, pm)
+        m_mag, m_real, m_imag, v_f0 = mp.compute_lossless_feats(m_fft, v_shift, voi, fs)
+        y = mp.synthesis_from_lossless(m_mag.copy(), m_real.copy(), m_imag.copy(), v_f0.copy(), fs)
+        mm, rr, ii, lf0 = orc.format_for_modelling(m_mag, m_real, m_imag, v_f0, fs, mag_dim=60, phase_dim=45)
+        mm3, rr3, ii3, _ = orc.format_for_modelling(m_mag, m_real, m_imag, v_f0, fs, mag_dim=60, phase_dim=10, alpha_phase=0.0)
+        np.random.seed(2000 + seed)
+        yc = mp.synthesis_from_compressed(mm.copy(), rr.copy(), ii.copy(), lf0.copy(), fs, b_out_hpf=False)
+        rows = [0, 5, 23, v_shift.size // 2, -1]
+        out.update({tag + '_' + k: v for k, v in dict(
+            sig_i16=x, pm=pm, voi=voi, v_shift=v_shift.astype(np.int64), v_f0=v_f0, full_rows=np.array(rows),
+            mag_rows=m_mag[rows], real_rows=m_real[rows], imag_rows=m_imag[rows],
+            mag_cols=m_mag[:, ::BIN_STEP], real_cols=m_real[:, ::BIN_STEP], imag_cols=m_imag[:, ::BIN_STEP],
+            syn=y, mag_mel_log=mm, real_mel=rr, imag_mel=ii, lf0=lf0,
+            real_mel_tts=rr3, imag_mel_tts=ii3, seed=2000 + seed, syn_compressed=yc).items()})
+        print('natural %s: %d frames (%d voiced), syn %d, compressed syn %d samples' % (
+            name, v_shift.size, int(voi.sum()), y.size, yc.size))
+    np.savez_compressed(os.path.join(HERE, 'natural_48k.npz'), fs=fs, bin_step=BIN_STEP, **out)
+
+
 if __name__ == '__main__':
-    lossless()
-    compressed()
-    griffin_lim()
+    only = sys.argv[1:]
+    for fn in (lossless, compressed, griffin_lim, natural):
+        if not only or fn.__name__ in only:
+            fn()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

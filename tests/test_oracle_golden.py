@@ -33,6 +33,28 @@ def test_lossless_analysis_golden():
     np.testing.assert_allclose(orc.build_min_phase_from_mag_spec(mag[rows]), g['minph_rows'], rtol=1e-11, atol=1e-12)
 
 
+def test_natural_speech_golden():
+    """The oracle on the bundled natural recordings (hvd_593 / hvd_577 slices) against the real reference."""
+    g = load('natural_48k.npz')
+    for tag in ('a', 'b'):
+        sig = g[tag + '_sig_i16'].astype(np.float64) / 32768.0
+        mag, real, imag, f0, fs, v_shift = orc.analysis_lossless_from_pm(sig, int(g['fs']), g[tag + '_pm'], g[tag + '_voi'])
+        assert np.array_equal(v_shift, g[tag + '_v_shift']) and np.array_equal(f0, g[tag + '_v_f0'])
+        rows, st = g[tag + '_full_rows'], int(g['bin_step'])
+        np.testing.assert_allclose(mag[rows], g[tag + '_mag_rows'], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(real[:, ::st], g[tag + '_real_cols'], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(imag[:, ::st], g[tag + '_imag_cols'], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(orc.synthesis_from_lossless(mag, real, imag, f0, fs), g[tag + '_syn'], rtol=0, atol=1e-13)
+        mm, rr, ii, lf0 = orc.format_for_modelling(mag, real, imag, f0, fs, mag_dim=60, phase_dim=45)
+        np.testing.assert_allclose(mm, g[tag + '_mag_mel_log'], rtol=0, atol=1e-6)      # float32 SPTK file rounding inside
+        np.testing.assert_allclose(rr, g[tag + '_real_mel'], rtol=0, atol=1e-6)
+        assert np.array_equal(lf0, g[tag + '_lf0'])
+        np.random.seed(int(g[tag + '_seed']))
+        y = orc.synthesis_from_compressed(g[tag + '_mag_mel_log'], g[tag + '_real_mel'], g[tag + '_imag_mel'], g[tag + '_lf0'],
+                                          48000, b_out_hpf=False)
+        np.testing.assert_allclose(y, g[tag + '_syn_compressed'], rtol=0, atol=1e-12)
+
+
 def test_compressed_synthesis_golden():
     g = load('compressed_hvd704.npz')
     f64 = lambda k: g[k].astype(np.float64)
