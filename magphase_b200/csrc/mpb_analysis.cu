@@ -21,7 +21,7 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
            const int64_t* __restrict__ centre, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
            const uint8_t* __restrict__ win, int64_t nfrm, const cx<T>* __restrict__ tw,
            TO* __restrict__ out_a, TO* __restrict__ out_b, TO* __restrict__ out_c,
-           const uint8_t* __restrict__ ph_mask) {
+           const uint8_t* __restrict__ ph_mask, int row_pitch, const int32_t* __restrict__ ph_row) {
     using G = FftGeom<T, N>;
     using T2 = cx<T>;
     constexpr int M = G::M, H = M + 1, TPB = G::TPB;
@@ -40,7 +40,11 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
         const int kind = win ? (int)win[f] : MPB_WIN_HANN;
         // MODE_LOGP: the phase streams of unvoiced frames are masked downstream (src/magphase.py:2527-2542) and never
         // read by the tile product: skip their two rows (a third of this kernel's epilogue and two thirds of its stores)
-        const bool need_ph = MODE != MODE_LOGP || !ph_mask || ph_mask[f] != 0;
+        bool need_ph = MODE != MODE_LOGP || !ph_mask || ph_mask[f] != 0;
+        // MODE_LOGP with a row map: the phase rows are compacted to the voiced frames (the tensor-core product reads them
+        // through a tensor map, which cannot gather); rows are pitched to a multiple of 16 bytes
+        int64_t prow = f;
+        if (MODE == MODE_LOGP && ph_row) { prow = ph_row[f]; need_ph = prow >= 0; }
 
         T2 v[16];
         load_frame<T, TS, N>(sig, n_sig, c, l, q, kind, buf, v, t);
@@ -51,9 +55,10 @@ k_analysis(const TS* __restrict__ sig, int64_t n_sig,
 
         // real-FFT split:  X[k] = E + W_N^k O,  X[M-k] = conj(E - W_N^k O),
         //                  E = (Z[k] + conj Z[M-k]) / 2,  O = -i (Z[k] - conj Z[M-k]) / 2,   k = t + j*TPB
-        TO* oa = out_a + (MODE == MODE_LOGSQ ? 0 : f * (int64_t)H * (MODE == MODE_FFT ? 2 : 1));
-        TO* ob = out_b + (MODE == MODE_LOGSQ ? 0 : f * (int64_t)H);
-        TO* oc = out_c + (MODE == MODE_LOGSQ ? 0 : f * (int64_t)H);
+        const int64_t pitch = MODE == MODE_LOGP ? (int64_t)row_pitch : (int64_t)H;
+        TO* oa = out_a + (MODE == MODE_LOGSQ ? 0 : f * pitch * (MODE == MODE_FFT ? 2 : 1));
+        TO* ob = out_b + (MODE == MODE_LOGSQ ? 0 : (need_ph ? prow : 0) * pitch);
+        TO* oc = out_c + (MODE == MODE_LOGSQ ? 0 : (need_ph ? prow : 0) * pitch);
         T2 w = fc.wp;
         constexpr int NJ = (M / 2) / TPB;
         double lsum = 0.0;                         // MODE_LOGSQ: sum over bins 1..H-2 of (log|X|)^2
@@ -152,7 +157,8 @@ static cudaError_t launch_analysis_t(const AnalysisArgs& a, cudaStream_t st) {
     if (grid > a.nfrm) grid = a.nfrm;
     if (grid < 1) return cudaSuccess;
     kern<<<(unsigned)grid, G::TPB, smem, st>>>((const TS*)a.sig, a.n_sig, a.centre, a.left, a.right, a.win, a.nfrm,
-                                               (const cx<T>*)a.tw, (TO*)a.out_a, (TO*)a.out_b, (TO*)a.out_c, a.ph_mask);
+                                               (const cx<T>*)a.tw, (TO*)a.out_a, (TO*)a.out_b, (TO*)a.out_c, a.ph_mask,
+                                               a.row_pitch > 0 ? a.row_pitch : a.fft_len / 2 + 1, a.ph_row);
     return cudaGetLastError();
 }
 

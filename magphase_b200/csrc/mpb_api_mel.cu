@@ -11,8 +11,8 @@ struct mpb_mel {
     double alpha_mag = 0, alpha_ph = 0;
     float* wt_mag = nullptr;     // [kpad][ld_mag]
     float* wt_ph = nullptr;      // [kpad][ld_ph]
-    float* wt_tc_mag = nullptr;  // experimental (MPB_MEL_TC=1): W^T pre-split for the tcgen05 tile product, else NULL
-    float* wt_tc_ph = nullptr;
+    float* wt_tc_mag = nullptr;  // W^T pre-split per 32-bin stage for the tcgen05 tile product (mpb_mel_warp_tc.cu); NULL when a stream
+    float* wt_tc_ph = nullptr;   // has more than 64 coefficients or MPB_MEL_TC=0 was set at plan creation: FMA kernels then
     double* cos_mag = nullptr;   // [n_mag][n_mag]
     double* cos_ph = nullptr;    // [n_ph][phase_dim]
     DevBuf partial, feats[3], small[8], compact, sig32;
@@ -23,6 +23,7 @@ static constexpr int64_t MEL_CHUNK = 65536;   // frames per pass: bounds the scr
                                               // measured 32768 / 65536 / 131072: 3.62 / 3.50 / 3.48 ms per 116k frames
 
 static int pad64(int n) { return ((n + 63) / 64) * 64; }
+static int lp_pitch_of(int H) { return (H + 3) & ~3; }   // row pitch of the log-periodogram scratch: 16-byte rows (TMA)
 
 // grows the scratch of mpb_analysis_compressed_dev / mel_compress_impl for calls of up to nfrm frames
 static int mel_reserve(mpb_mel* m, int64_t nfrm) {
@@ -32,8 +33,8 @@ static int mel_reserve(mpb_mel* m, int64_t nfrm) {
     const int n_slices = (H - 1) / MEL_KSLICE;
     const int ncp = m->ld_mag > m->ld_ph ? m->ld_mag : m->ld_ph;
     const int64_t chunk = nfrm < MEL_CHUNK ? nfrm : MEL_CHUNK;
-    for (int i = 0; i < 3; ++i) CU(m->feats[i].need(sizeof(float) * (size_t)chunk * H));
-    CU(m->partial.need(sizeof(float) * 3 * (size_t)n_slices * (size_t)chunk * ncp));
+    for (int i = 0; i < 3; ++i) CU(m->feats[i].need(sizeof(float) * (size_t)chunk * lp_pitch_of(H)));
+    CU(m->partial.need(sizeof(float) * 3 * (size_t)(m->wt_tc_mag ? 1 : n_slices) * (size_t)chunk * ncp));
     CU(m->compact.need(sizeof(int32_t) * (2 * (size_t)chunk + 4)));
     return MPB_OK;
 }
@@ -63,8 +64,8 @@ int mpb_mel_create(mpb_ctx* ctx, int fft_len, double alpha_mag, int n_mag, doubl
     CU(cudaMemcpy(m->cos_ph, cos_ph, sizeof(double) * n_ph * phase_dim, cudaMemcpyHostToDevice));
     CU(build_warp_matrix(fft_len, n_mag, alpha_mag, m->wt_mag, scratch, m->ld_mag, ctx->stream));
     CU(build_warp_matrix(fft_len, n_ph, alpha_ph, m->wt_ph, scratch, m->ld_ph, ctx->stream));
-    static const bool mel_tc = [] { const char* e = getenv("MPB_MEL_TC"); return e && (atoi(e) & 1); }();   // bit 0: warp product, bit 1: un-warp product
-    if (mel_tc && m->ld_mag == 64 && m->ld_ph == 64) {       // experimental tensor-core tile product (mpb_mel_tc.cu)
+    static const bool mel_tc = [] { const char* e = getenv("MPB_MEL_TC"); return !e || (atoi(e) & 1); }();   // default on; MPB_MEL_TC=0: FMA kernels
+    if (mel_tc && m->ld_mag == 64 && m->ld_ph == 64) {       // tensor-core tile product with fused finish (mpb_mel_warp_tc.cu)
         CU(cudaMalloc(&m->wt_tc_mag, mel_tc_operand_bytes(fft_len)));
         CU(cudaMalloc(&m->wt_tc_ph, mel_tc_operand_bytes(fft_len)));
         CU(build_warp_matrix_tc(fft_len, m->wt_mag, m->ld_mag, m->wt_tc_mag, ctx->stream));
@@ -149,8 +150,6 @@ static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const vo
         a.raw_mc = lerp.raw_mc;
         a.voi = voi + f0; a.nfrm = n; a.fft_len = m->fft_len;
         a.wt_mag = m->wt_mag; a.ld_mag = m->ld_mag; a.wt_ph = m->wt_ph; a.ld_ph = m->ld_ph;
-        a.wt_tc_mag = m->wt_tc_mag; a.wt_tc_ph = m->wt_tc_ph;
-        a.partial_slices = 0;
         a.cos_mag = m->cos_mag; a.n_mag = m->n_mag; a.cos_ph = m->cos_ph; a.n_ph = m->n_ph; a.phase_dim = m->phase_dim;
         a.partial = (float*)m->partial.p; a.ncp_max = ncp;
         a.out_mag = (char*)out_mag_mel + oes * f0 * od_mag;
@@ -161,7 +160,6 @@ static int mel_compress_impl(mpb_mel* m, void* stream, const void* mag, const vo
         if (lerp.raw_mc) { a.vidx = nullptr; a.cidx = nullptr; a.vcount = nullptr; }   // every frame, every stream
         else LAUNCH(m->ctx, (cudaStream_t)stream, "k_voiced_compact",
                     launch_voiced_compact(a.voi, (int)n, d_vidx, d_cidx, d_cnt, (cudaStream_t)stream));
-        if (mel_tc_usable(a) && mel_tc_sums_slices()) a.partial_slices = 1;   // experimental: slice sums inside the tensor-core kernel
         LAUNCH(m->ctx, (cudaStream_t)stream, "k_mel_gemm", launch_mel_gemm(a, (cudaStream_t)stream));
         LAUNCH(m->ctx, (cudaStream_t)stream, "k_mel_finish", launch_mel_finish(a, (cudaStream_t)stream));
     }
@@ -185,9 +183,15 @@ int mpb_analysis_compressed_dev(mpb_mel* m, void* stream, const void* sig, int s
     CU(cudaSetDevice(ctx->device));
     const int H = m->fft_len / 2 + 1;
     const int64_t chunk = nfrm < MEL_CHUNK ? nfrm : MEL_CHUNK;
+    const int LP = lp_pitch_of(H);
+    const bool use_tc = m->wt_tc_mag != nullptr;
     {
         std::lock_guard<std::mutex> lk(m->mu);
-        for (int i = 0; i < 3; ++i) CU(m->feats[i].need(sizeof(float) * (size_t)chunk * H));
+        for (int i = 0; i < 3; ++i) CU(m->feats[i].need(sizeof(float) * (size_t)chunk * LP));
+        if (use_tc) {
+            CU(m->compact.need(sizeof(int32_t) * (2 * (size_t)chunk + 4)));
+            CU(m->partial.need(sizeof(float) * 3 * (size_t)chunk * 64));      // float32 mel cepstra between the two kernels
+        }
     }
     // float64 butterflies (default); MPB_LOGP_F32=1 selects the float32 engine for this fused path only (experiment, see
     // launch_analysis_logp)
@@ -205,6 +209,32 @@ int mpb_analysis_compressed_dev(mpb_mel* m, void* stream, const void* sig, int s
         a.nfrm = n; a.fft_len = m->fft_len; a.compute_dtype = logp_compute; a.tw = tw;
         a.out_a = m->feats[0].p; a.out_b = m->feats[1].p; a.out_c = m->feats[2].p; a.out_dtype = MPB_F32;
         a.mode = MODE_LOGP; a.num_sms = ctx->num_sms; a.ph_mask = voi + f0;
+        if (use_tc) {
+            // tensor-core product with the finish step in its epilogue: 16-byte pitched rows, the phase rows compacted to the
+            // voiced frames (rank from the one-CTA scan), nothing but the low-dimensional features leaves the second kernel
+            std::lock_guard<std::mutex> lk(m->mu);
+            int32_t* d_vidx = (int32_t*)m->compact.p;
+            int32_t* d_cidx = d_vidx + chunk;
+            int32_t* d_cnt = d_cidx + chunk;
+            LAUNCH(ctx, st, "k_voiced_compact", launch_voiced_compact(voi + f0, (int)n, d_vidx, d_cidx, d_cnt, st));
+            a.row_pitch = LP; a.ph_row = d_cidx;
+            LAUNCH(ctx, st, "k_analysis<logp>", launch_analysis_logp(a, st));
+            MelArgs g;
+            g.mag = m->feats[0].p; g.real = m->feats[1].p; g.imag = m->feats[2].p; g.feat_dtype = MPB_F32; g.pre_logp = 1; g.raw_mc = 0;
+            g.voi = voi + f0; g.nfrm = n; g.fft_len = m->fft_len;
+            g.wt_mag = m->wt_mag; g.ld_mag = m->ld_mag; g.wt_ph = m->wt_ph; g.ld_ph = m->ld_ph;
+            g.cos_mag = m->cos_mag; g.n_mag = m->n_mag; g.cos_ph = m->cos_ph; g.n_ph = m->n_ph; g.phase_dim = m->phase_dim;
+            g.partial = (float*)m->partial.p; g.ncp_max = 64;
+            g.out_mag = (char*)out_mag_mel + oes * f0 * m->n_mag; g.out_real = (char*)out_real_mel + oes * f0 * m->phase_dim;
+            g.out_imag = (char*)out_imag_mel + oes * f0 * m->phase_dim; g.out_dtype = out_dtype;
+            g.vidx = d_vidx; g.cidx = d_cidx; g.vcount = d_cnt;
+            g.lerp_r0 = nullptr; g.lerp_r1 = nullptr; g.lerp_w = nullptr;
+            g.wt_tc_mag = m->wt_tc_mag; g.wt_tc_ph = m->wt_tc_ph; g.lp_pitch = LP; g.num_sms = ctx->num_sms;
+            if (!mel_tc_usable(g)) return fail(MPB_ERR_INTERNAL, "tensor-core mel product not usable for this plan");
+            LAUNCH(ctx, st, "k_mel_warp_tc", launch_mel_warp_tc(g, st));
+            LAUNCH(ctx, st, "k_mel_cos", launch_mel_cos(g, st));
+            continue;
+        }
         LAUNCH(ctx, st, "k_analysis<logp>", launch_analysis_logp(a, st));
         rc = mel_compress_impl(m, stream, m->feats[0].p, m->feats[1].p, m->feats[2].p, MPB_F32, 1, voi + f0, n,
                                (char*)out_mag_mel + oes * f0 * m->n_mag, (char*)out_real_mel + oes * f0 * m->phase_dim,

@@ -15,8 +15,10 @@ struct mpb_syn {
     int fft_len = 0, n_mag = 0, n_ph = 0, H = 0, HB = 0;
     float* u_mag = nullptr;   // [n_mag][HP]   (rows pitched to 16 bytes, zero padded)
     float* u_ph = nullptr;    // [n_ph][HBP]
-    float* u_tc_mag = nullptr, *u_tc_ph = nullptr;   // experimental (MPB_MEL_TC=1): U pre-split for the tcgen05 un-warp product, else NULL
     float* tab = nullptr;     // [3][H]
+    float* ut_mag = nullptr;  // U^T split for the tensor-core un-warp product (mpb_mel_unwarp_tc.cu); NULL when a stream has more
+    float* ut_ph = nullptr;   // than 64 coefficients or MPB_MEL_TC=0 was set at plan creation: FMA kernel then
+    DevBuf unw_x[3], unw_idx;
     DevBuf unw[3], unw_flags, unw_cvt, logsq, nspec, gain, ticket, frm_rows[3], host_in[20], out;
     std::mutex mu;
 };
@@ -49,14 +51,15 @@ int mpb_syn_create(mpb_ctx* ctx, int fft_len, int n_mag, int n_ph, int hb, const
     if (rc == MPB_OK) rc = upload_f32(u_ph, n_ph, hb, (hb + 3) & ~3, &s->u_ph);
     if (rc == MPB_OK) rc = upload_f32(tab, 3, H, H, &s->tab);
     if (rc != MPB_OK) { delete s; return rc; }
-    static const bool mel_tc = [] { const char* e = getenv("MPB_MEL_TC"); return e && (atoi(e) & 2); }();   // bit 0: warp product, bit 1: un-warp product
-    if (mel_tc && n_mag <= 64 && n_ph <= 64) {               // experimental tensor-core un-warp product (mpb_mel_tc.cu)
+    static const bool mel_tc = [] { const char* e = getenv("MPB_MEL_TC"); return !e || (atoi(e) & 2); }();   // default on; bit 1 clear: FMA kernel
+    if (mel_tc && n_mag <= 64 && n_ph <= 64 && (H - 1) % 128 == 0) {
         const int HP = (H + 3) & ~3, HBP = (hb + 3) & ~3;
-        CU(cudaMalloc((void**)&s->u_tc_mag, unwarp_tc_operand_bytes(HP, n_mag)));
-        CU(cudaMalloc((void**)&s->u_tc_ph, unwarp_tc_operand_bytes(HBP, n_ph)));
-        CU(build_unwarp_matrix_tc(s->u_mag, n_mag, HP, s->u_tc_mag, ctx->stream));
-        CU(build_unwarp_matrix_tc(s->u_ph, n_ph, HBP, s->u_tc_ph, ctx->stream));
+        CU(cudaMalloc((void**)&s->ut_mag, unwarp_tc_operand_bytes(H - 1)));
+        CU(cudaMalloc((void**)&s->ut_ph, unwarp_tc_operand_bytes(hb)));
+        CU(build_unwarp_matrix_tc(s->u_mag, n_mag, HP, H - 1, s->ut_mag, ctx->stream));
+        CU(build_unwarp_matrix_tc(s->u_ph, n_ph, HBP, hb, s->ut_ph, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        ctx->launches += 2;
     }
     *out = s;
     return MPB_OK;
@@ -65,8 +68,9 @@ int mpb_syn_create(mpb_ctx* ctx, int fft_len, int n_mag, int n_ph, int hb, const
 int mpb_syn_destroy(mpb_syn* s) {
     if (!s) return MPB_OK;
     cudaSetDevice(s->ctx->device);
-    cudaFree(s->u_mag); cudaFree(s->u_ph); cudaFree(s->tab);
-    cudaFree(s->u_tc_mag); cudaFree(s->u_tc_ph);
+    cudaFree(s->u_mag); cudaFree(s->u_ph); cudaFree(s->tab); cudaFree(s->ut_mag); cudaFree(s->ut_ph);
+    for (auto& b : s->unw_x) b.release();
+    s->unw_idx.release();
     for (auto& b : s->unw) b.release();
     for (auto& b : s->host_in) b.release();
     for (auto& b : s->frm_rows) b.release();
@@ -96,6 +100,10 @@ static int syn_reserve(mpb_syn* s, int in_dtype, int64_t n_rows, int64_t nfrm, i
     CU(s->gain.need(sizeof(double) * 2 * (size_t)n_utt));
     CU(s->ticket.need(sizeof(int)));
     CU(s->unw_flags.need((size_t)n_rows / 64 + n_ranges + 2));
+    if (s->ut_mag) {
+        for (int i = 0; i < 3; ++i) CU(s->unw_x[i].need(unwarp_tc_feature_bytes(n_rows)));
+        CU(s->unw_idx.need(sizeof(int32_t) * (2 * (size_t)n_rows + 4 * ((size_t)n_ranges + 1))));
+    }
     *cvt_pitch = 0;
     if (in_dtype == MPB_F64) {
         const size_t widest = (size_t)(s->n_mag > s->n_ph ? s->n_mag : s->n_ph);
@@ -124,7 +132,6 @@ static int syn_enqueue_range(mpb_syn* s, cudaStream_t st, const void* mag_mel, c
     u.in_dtype = in_dtype;
     u.need_ph = need_ph + r.row_a; u.nfrm = n_rows; u.n_mag = s->n_mag; u.n_ph = s->n_ph;
     u.u_mag = s->u_mag; u.H = s->H; u.u_ph = s->u_ph; u.HB = s->HB;
-    u.u_tc_mag = s->u_tc_mag; u.u_tc_ph = s->u_tc_ph;
     u.out_mag = (float*)s->unw[0].p + r.row_a * HP; u.out_real = (float*)s->unw[1].p + r.row_a * HBP;
     u.out_imag = (float*)s->unw[2].p + r.row_a * HBP;
     u.HP = HP; u.HBP = HBP; u.num_sms = ctx->num_sms;
@@ -136,7 +143,22 @@ static int syn_enqueue_range(mpb_syn* s, cudaStream_t st, const void* mag_mel, c
         u.cvt_off_mag = (((size_t)r.row_a * s->n_mag + 3) & ~(size_t)3) + 4 * (size_t)r.ordinal;
         u.cvt_off_ph = (((size_t)r.row_a * s->n_ph + 3) & ~(size_t)3) + 4 * (size_t)r.ordinal;
     }
-    LAUNCH(ctx, st, "k_mel_unwarp", launch_mel_unwarp(u, st));
+    if (s->ut_mag) {
+        // tensor-core product: compaction of the frames that need their phase rows, split operands, tiles (mpb_mel_unwarp_tc.cu)
+        int32_t* vidx = (int32_t*)s->unw_idx.p + r.row_a;
+        int32_t* cidx = (int32_t*)s->unw_idx.p + (size_t)(s->unw_idx.cap / sizeof(int32_t) / 2) + r.row_a;
+        int32_t* cnt = (int32_t*)s->unw_idx.p + s->unw_idx.cap / sizeof(int32_t) - 4 - r.ordinal;
+        u.ut_mag = s->ut_mag; u.ut_ph = s->ut_ph;
+        for (int i = 0; i < 3; ++i) u.xs[i] = (float*)s->unw_x[i].p + (size_t)r.row_a * 128;
+        u.vidx = vidx; u.cidx = cidx; u.vcount = cnt;
+    }
+    if (unwarp_tc_usable(u)) {
+        LAUNCH(ctx, st, "k_voiced_compact", launch_voiced_compact(u.need_ph, (int)n_rows, (int32_t*)u.vidx, (int32_t*)u.cidx,
+                                                                  (int32_t*)u.vcount, st));
+        LAUNCH(ctx, st, "k_mel_unwarp_tc", launch_mel_unwarp_tc(u, st));
+    } else {
+        LAUNCH(ctx, st, "k_mel_unwarp", launch_mel_unwarp(u, st));
+    }
 
     const void* tw = nullptr;
     int rc = get_twiddles(ctx, s->fft_len, MPB_F32, &tw);

@@ -19,6 +19,8 @@ struct AnalysisArgs {
                                     // MODE_LOGP: a,b,c = log periodograms of mag/real/imag as SPTK mcep sees them (float32)
     int num_sms;
     const uint8_t* ph_mask = nullptr;   // MODE_LOGP: per-frame flag, 0 = the phase rows (b, c) of the frame are not needed
+    int row_pitch = 0;                  // MODE_LOGP: output row pitch in elements (0: fft_len/2+1, unpadded)
+    const int32_t* ph_row = nullptr;    // MODE_LOGP: row of frame f in the COMPACTED phase matrices b, c (< 0: none); NULL: row f
 };
 cudaError_t launch_analysis(const AnalysisArgs& a, cudaStream_t st);
 cudaError_t launch_noise_stats(const AnalysisArgs& a, cudaStream_t st);   // out_a: double[nfrm]; out_b: float2[nfrm][fft_len/2+2] spectra or NULL
@@ -61,20 +63,23 @@ struct MelArgs {
     void* out_mag; void* out_real; void* out_imag; int out_dtype;
     const int32_t* vidx; const int32_t* cidx; const int32_t* vcount;        // voiced-frame compaction (NULL: off)
     const int32_t* lerp_r0; const int32_t* lerp_r1; const float* lerp_w;    // output frame f = lerp of two source rows (NULL: off)
-    const float* wt_tc_mag = nullptr; const float* wt_tc_ph = nullptr;      // pre-split tensor-core operands (experimental, mpb_mel_tc.cu; NULL: off)
-    int partial_slices = 0;                                                 // 0: one partial per K slice (default); 1: `partial` already holds the slice sums
+    const float* wt_tc_mag = nullptr; const float* wt_tc_ph = nullptr;      // W^T pre-split per 32-bin stage for the tensor-core product (mpb_mel_warp_tc.cu; NULL: off)
+    int lp_pitch = 0;                                                       // > 0: mag / real / imag are float32 log periodograms with this row pitch (multiple
+                                                                            // of 4 floats), the real / imag rows compacted to the voiced frames (row = cidx[f])
+    int num_sms = 0;
 };
 cudaError_t launch_voiced_compact(const uint8_t* voi, int n, int32_t* vidx, int32_t* cidx, int32_t* count, cudaStream_t st);
 cudaError_t build_warp_matrix(int fft_len, int n_out, double alpha, float* wt32, double* scratch64, int ld,
                               cudaStream_t st);
 cudaError_t launch_mel_gemm(const MelArgs& a, cudaStream_t st);
 cudaError_t launch_mel_finish(const MelArgs& a, cudaStream_t st);
-// experimental tcgen05 variant of the tile product (mpb_mel_tc.cu); selected by MPB_MEL_TC=1 when the plan was created
+// tcgen05 tile product with the finish step fused into its epilogue (mpb_mel_warp_tc.cu): the default of the fused compressed
+// analysis whenever both streams have at most 64 coefficients (MPB_MEL_TC=0 at plan creation selects the FMA kernels)
 size_t mel_tc_operand_bytes(int fft_len);
 bool mel_tc_usable(const MelArgs& a);
-bool mel_tc_sums_slices();
 cudaError_t build_warp_matrix_tc(int fft_len, const float* wt32, int ld, float* out, cudaStream_t st);
-cudaError_t launch_mel_gemm_tc(const MelArgs& a, cudaStream_t st);
+cudaError_t launch_mel_warp_tc(const MelArgs& a, cudaStream_t st);   // log periodograms -> float32 mel cepstra (a.partial)
+cudaError_t launch_mel_cos(const MelArgs& a, cudaStream_t st);       // mel cepstra -> features (cosine matrix, floor / clip)
 
 // ---- mel un-warping + compressed synthesis (mpb_unwarp.cu, mpb_synth_comp.cu) ----
 struct UnwarpArgs {
@@ -87,14 +92,18 @@ struct UnwarpArgs {
     float* cvt; size_t cvt_pitch;                                                   // in_dtype F64: 3 x cvt_pitch floats of scratch;
     size_t cvt_off_mag, cvt_off_ph;                                                 //   float offsets (multiples of 4) inside each matrix
     int num_sms;
-    const float* u_tc_mag = nullptr; const float* u_tc_ph = nullptr;               // pre-split tensor-core operands (experimental, mpb_mel_tc.cu; NULL: off)
+    // tensor-core path (mpb_mel_unwarp_tc.cu; all NULL: FMA kernel)
+    const float* ut_mag = nullptr; const float* ut_ph = nullptr;                    // U^T split [bin][hi(64) | lo(64)]
+    float* xs[3] = {nullptr, nullptr, nullptr};                                     // scratch: split feature rows [row][128] per stream
+    const int32_t* vidx = nullptr; const int32_t* cidx = nullptr; const int32_t* vcount = nullptr;   // compaction of need_ph
 };
 cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st);
-// experimental tcgen05 variant (mpb_mel_tc.cu); selected by MPB_MEL_TC=1 when the plan was created
-size_t unwarp_tc_operand_bytes(int np, int K);
-cudaError_t build_unwarp_matrix_tc(const float* U, int K, int np, float* out, cudaStream_t st);
+// tcgen05 variant: the default when both streams have at most 64 coefficients (MPB_MEL_TC=0 at plan creation: FMA kernel)
+size_t unwarp_tc_operand_bytes(int nbins);
+size_t unwarp_tc_feature_bytes(int64_t n_rows);
+cudaError_t build_unwarp_matrix_tc(const float* U, int K, int np, int nbins, float* out, cudaStream_t st);
 bool unwarp_tc_usable(const UnwarpArgs& a);
-cudaError_t launch_mel_unwarp_tc(const UnwarpArgs& a, const float* xm, const float* xr, const float* xi, cudaStream_t st);
+cudaError_t launch_mel_unwarp_tc(const UnwarpArgs& a, cudaStream_t st);
 cudaError_t launch_lerp_rows(const float* rows, int pitch, const int32_t* row0, const int32_t* row1, const float* roww,
                              int64_t nfrm, float* out, cudaStream_t st);
 

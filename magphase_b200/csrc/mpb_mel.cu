@@ -333,7 +333,6 @@ static cudaError_t launch_gemm_t(const MelArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_mel_gemm(const MelArgs& a, cudaStream_t st) {
-    if (mel_tc_usable(a)) return launch_mel_gemm_tc(a, st);       // experimental, only when the plan carries tensor-core operands
     if (a.lerp_r0) return a.feat_dtype == MPB_F64 ? launch_gemm_t<double, false, true>(a, st) : launch_gemm_t<float, false, true>(a, st);
     if (a.feat_dtype == MPB_F64) return launch_gemm_t<double, false, false>(a, st);
     return a.pre_logp ? launch_gemm_t<float, true, false>(a, st) : launch_gemm_t<float, false, false>(a, st);
@@ -342,7 +341,7 @@ cudaError_t launch_mel_gemm(const MelArgs& a, cudaStream_t st) {
 template <typename TF, typename TO, bool PRE, bool LERP>
 static cudaError_t launch_finish_t(const MelArgs& a, cudaStream_t st) {
     const int H = a.fft_len / 2 + 1;
-    const int n_slices = a.partial_slices > 0 ? a.partial_slices : (H - 1) / MEL_KSLICE;
+    const int n_slices = (H - 1) / MEL_KSLICE;
     dim3 g2((unsigned)((a.nfrm + 3) / 4), 3);
     k_mel_finish<TF, TO, PRE, LERP><<<g2, 128, 0, st>>>(a.partial, n_slices, a.ncp_max, a.nfrm, (const TF*)a.mag, (const TF*)a.real,
                                                    (const TF*)a.imag, H, a.wt_mag, a.ld_mag, a.wt_ph, a.ld_ph, a.cos_mag,

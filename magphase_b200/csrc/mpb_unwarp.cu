@@ -201,7 +201,6 @@ cudaError_t launch_mel_unwarp(const UnwarpArgs& a, cudaStream_t st) {
     }
     const int64_t n_ft = (a.nfrm + UW_FT - 1) / UW_FT;
     k_unwarp_tile_flags<<<(unsigned)((n_ft + 3) / 4), 128, 0, st>>>(a.need_ph, a.nfrm, a.flags);
-    if (unwarp_tc_usable(a)) return launch_mel_unwarp_tc(a, xm, xr, xi, st);   // experimental, only when the plan carries tensor-core operands
     const size_t smem = sizeof(float) * ((size_t)UW_FT * kmax + (size_t)kmax * UW_LDX + (size_t)kmax * UW_BT) + 16;
     cudaError_t e = cudaFuncSetAttribute(k_mel_unwarp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -46,3 +46,36 @@ for fs in (48000, 16000):
         np.random.seed(3)
         y_ref, ph_ref = orc.griffin_lim(ref[0].copy(), ref[5], phase_init='min_phase', niters=8)
         print('%-44s %s' % (tag + 'griffin_lim (8 iterations) signal', err(y, y_ref)))
+
+# ---- natural speech (golden slices of the bundled recordings, generated from the real reference) and the band-limited
+# synthetic stress case: the rows that guard every float32 / tensor-core decision ----
+import os
+from magphase_b200.synth import synth_utterance_band_limited
+g = np.load(os.path.join('tests', 'golden', 'natural_48k.npz'))
+for tag, name in (('a', 'hvd_593'), ('b', 'hvd_577')):
+    sig = g[tag + '_sig_i16'].astype(np.float64) / 32768.0
+    pm, voi = g[tag + '_pm'], g[tag + '_voi']
+    got = mp.analysis_lossless_from_pm(sig, 48000, pm, voi)
+    st = int(g['bin_step'])
+    for n, a in zip(('mag', 'real', 'imag'), got[:3]):
+        print('%-44s %s' % ('natural %s analysis_lossless %s (cols)' % (name, n), err(a[:, ::st], g['%s_%s_cols' % (tag, n)])))
+    print('%-44s %s' % ('natural %s synthesis_from_lossless' % name, err(mp.synthesis_from_lossless(*got[:4], 48000), g[tag + '_syn'])))
+    cg = mp.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45)
+    for n, a in zip(('mag_mel_log', 'real_mel', 'imag_mel'), cg[:3]):
+        print('%-44s %s' % ('natural %s analysis_compressed %s' % (name, n), err(a, g['%s_%s' % (tag, n)])))
+    c3 = mp.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=10, alpha_phase=0.0)
+    print('%-44s %s' % ('natural %s analysis (tts dims) real_mel' % name, err(c3[1], g[tag + '_real_mel_tts'])))
+    np.random.seed(int(g[tag + '_seed']))
+    y = mp.synthesis_from_compressed(g[tag + '_mag_mel_log'], g[tag + '_real_mel'], g[tag + '_imag_mel'], g[tag + '_lf0'], 48000, b_out_hpf=False)
+    print('%-44s %s' % ('natural %s synthesis_from_compressed' % name, err(y, g[tag + '_syn_compressed'])))
+for floor in (-72.0, None):
+    sig, pm, voi = synth_utterance_band_limited(31, fs=48000, dur_s=0.6, floor_db=floor)
+    ref = orc.analysis_lossless_from_pm(sig, 48000, pm, voi)
+    got = mp.analysis_lossless_from_pm(sig, 48000, pm, voi)
+    t = 'band-limited (floor %s) ' % floor
+    for n, a, b in zip(('mag', 'real', 'imag'), got[:3], ref[:3]):
+        print('%-44s %s' % (t + 'lossless ' + n, err(a, b)))
+    cr = orc.format_for_modelling(*ref[:4], 48000, mag_dim=60, phase_dim=45)
+    cg = mp.analysis_compressed_from_pm(sig, 48000, pm, voi, mag_dim=60, phase_dim=45)
+    for n, a, b in zip(('mag_mel_log', 'real_mel', 'imag_mel'), cg[:3], cr[:3]):
+        print('%-44s %s' % (t + 'compressed ' + n, err(a, b)))
