@@ -15,7 +15,8 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
 # The kernel files are compiled with --use_fast_math: flush-to-zero, approximate float32 division / square root and fused
 # multiply-add for FLOAT32 arithmetic only (3-6 % on the float32 kernels; float64 code -- analysis butterflies,
 # Griffin-Lim, K-slice sums, cosine matrices -- is not affected).  The parity tests (1e-5 RMS) are the guard.
-EXTRA_FLAGS = {f: ['--use_fast_math'] for f in ('mpb_synth_comp.cu', 'mpb_synthesis.cu', 'mpb_unwarp.cu', 'mpb_mel.cu', 'mpb_analysis.cu')}
+EXTRA_FLAGS = {f: ['--use_fast_math'] for f in ('mpb_synth_comp.cu', 'mpb_synthesis.cu', 'mpb_unwarp.cu', 'mpb_mel.cu', 'mpb_analysis.cu',
+                                                          'mpb_mel_unwarp_tc.cu')}
 
 
 def _nvcc():

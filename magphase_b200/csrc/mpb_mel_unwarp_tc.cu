@@ -98,6 +98,41 @@ __global__ void k_split_unwarp(const float* __restrict__ U, int K, int np, int n
     out[(size_t)b * XP + UK + c] = u - __uint_as_float(__float_as_uint(u) & TF32_MASK);
 }
 
+// predicated streaming store without a branch (a branch per element costs more than the store)
+__device__ __forceinline__ void st_cs_if(float* ptr, float v, int off) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ge.s32 p, %2, 0;\n"
+        "@p st.global.cs.f32 [%0], %1;\n"
+        "}\n" ::"l"(ptr), "f"(v), "r"(off) : "memory");
+}
+
+// 64 accumulator columns (frames) of this thread's bin -> rows of the output; off[j]: element offset of column j's row, < 0: none
+template <bool EXP>
+__device__ __forceinline__ void epilogue_store(uint32_t ta, const int32_t* __restrict__ off, float* __restrict__ Y, bool bin_ok) {
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {
+        uint32_t v[32];
+        tmem_ld16_nowait(ta + c, v);
+        tmem_ld16_nowait(ta + c + 16, v + 16);
+        tmem_ld_wait();
+        if (bin_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const int4 o = *reinterpret_cast<const int4*>(off + c + j);
+                const int oo[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float y = __uint_as_float(v[j + u]);
+                    if (EXP) y = exp2f(y * 1.4426950408889634f);      // --use_fast_math: ex2.approx
+                    st_cs_if(Y + oo[u], y, oo[u]);
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(U_THREADS, 1)
 k_mel_unwarp_tc(const __grid_constant__ CUtensorMap map_u_mag, const __grid_constant__ CUtensorMap map_u_ph,
                 const __grid_constant__ CUtensorMap map_x_mag, const __grid_constant__ CUtensorMap map_x_re,
@@ -246,19 +281,8 @@ k_mel_unwarp_tc(const __grid_constant__ CUtensorMap map_u_mag, const __grid_cons
                 mbar_wait_warp(&d_full[d], nd & 1u, lane);
                 fence_after();
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + d * UF + half * 64;
-#pragma unroll
-                for (int c = 0; c < 64; c += 32) {
-                    uint32_t v[32];
-                    tmem_ld16_nowait(ta + c, v);
-                    tmem_ld16_nowait(ta + c + 16, v + 16);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int off = off_s[half * 64 + c + j];
-                        const float y = __uint_as_float(v[j]);
-                        if (off >= 0 && bin_ok) __stcs(Y + off, stream == 0 ? __expf(y) : y);
-                    }
-                }
+                if (stream == 0) epilogue_store<true>(ta, off_s + half * 64, Y, bin_ok);
+                else epilogue_store<false>(ta, off_s + half * 64, Y, bin_ok);
                 fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d_empty[d]);

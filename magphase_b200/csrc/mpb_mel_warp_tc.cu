@@ -327,28 +327,24 @@ struct CosParams {
     void* out[3]; int out_f64;
 };
 
-// NO = outputs per thread (8 threads across the outputs): 8 covers 64 outputs, 6 covers 48 (phase_dim 45)
+// One 128-row tile: NO = outputs per thread (8 threads across the outputs): 8 covers 64 outputs, 6 covers 48 (phase_dim 45).
 template <int NO>
-__global__ void __launch_bounds__(CO_THREADS, 2)
-k_mel_cos(const CosParams p, int stream0) {
-    extern __shared__ __align__(16) uint8_t cos_smem[];
-    double* ct_s = reinterpret_cast<double*>(cos_smem);                 // [64][64], zero padded
-    double* mc_s = ct_s + 64 * 64;                                      // [CO_ROWS][CO_PITCH], widened once while staging
-    const int stream = stream0 + blockIdx.y, kind = stream == 0 ? 0 : 1, tid = threadIdx.x;
-    const int64_t nrows = (stream == 0 || !p.vcount) ? p.nfrm : (int64_t)*p.vcount;
-    const int64_t row0 = (int64_t)blockIdx.x * CO_ROWS;
-    if (row0 >= nrows) return;
-    const int n_in = p.n_in[kind], n_out = p.n_out[kind];
-    for (int i = tid; i < 64 * 64; i += CO_THREADS) {
-        const int j = i >> 6, o = i & 63;
-        ct_s[i] = (j < n_in && o < n_out) ? p.ct[kind][j * n_out + o] : 0.0;
-    }
+__device__ __forceinline__ void cos_tile(const CosParams& p, int stream, int n_in, int n_out, int64_t row0, int64_t nrows,
+                                         const double* __restrict__ ct_s, double* __restrict__ mc_s, int tid) {
+    // stage the tile's mel cepstra, widened once: all 16 loads of a thread are issued before the first use
     const float4* src = reinterpret_cast<const float4*>(p.mc[stream] + row0 * 64);
-    for (int i = tid; i < CO_ROWS * 16; i += CO_THREADS) {
-        const int r = i >> 4, c = (i & 15) * 4;
-        const float4 v = row0 + r < nrows ? __ldcs(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        double* d = mc_s + r * CO_PITCH + c;
-        d[0] = (double)v.x; d[1] = (double)v.y; d[2] = (double)v.z; d[3] = (double)v.w;
+    float4 v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int i = tid + k * CO_THREADS;
+        v[k] = row0 + (i >> 4) < nrows ? __ldcs(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();                                                     // the previous tile's product has read mc_s
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int i = tid + k * CO_THREADS;
+        double* d = mc_s + (i >> 4) * CO_PITCH + (i & 15) * 4;
+        d[0] = (double)v[k].x; d[1] = (double)v[k].y; d[2] = (double)v[k].z; d[3] = (double)v[k].w;
     }
     __syncthreads();
     // rows tr + 16 i; outputs 16 u + 2 tc + {0, 1}, u < NO / 2: the 8 threads of a row group read 128 contiguous bytes of the
@@ -387,6 +383,26 @@ k_mel_cos(const CosParams p, int stream0) {
             if (p.out_f64) reinterpret_cast<double*>(p.out[stream])[frame * n_out + o] = s;
             else reinterpret_cast<float*>(p.out[stream])[frame * n_out + o] = (float)s;
         }
+    }
+}
+
+// persistent: grid (x, 3 streams); a CTA stages its stream's cosine table once and walks over the row tiles x, x + gridDim.x, ...
+__global__ void __launch_bounds__(CO_THREADS, 2)
+k_mel_cos(const CosParams p) {
+    extern __shared__ __align__(16) uint8_t cos_smem[];
+    double* ct_s = reinterpret_cast<double*>(cos_smem);                 // [64][64], zero padded
+    double* mc_s = ct_s + 64 * 64;                                      // [CO_ROWS][CO_PITCH]
+    const int stream = blockIdx.y, kind = stream == 0 ? 0 : 1, tid = threadIdx.x;
+    const int64_t nrows = (stream == 0 || !p.vcount) ? p.nfrm : (int64_t)*p.vcount;
+    if ((int64_t)blockIdx.x * CO_ROWS >= nrows) return;
+    const int n_in = p.n_in[kind], n_out = p.n_out[kind];
+    for (int i = tid; i < 64 * 64; i += CO_THREADS) {
+        const int j = i >> 6, o = i & 63;
+        ct_s[i] = (j < n_in && o < n_out) ? __ldg(p.ct[kind] + j * n_out + o) : 0.0;
+    }
+    for (int64_t row0 = (int64_t)blockIdx.x * CO_ROWS; row0 < nrows; row0 += (int64_t)gridDim.x * CO_ROWS) {
+        if (n_out <= 48) cos_tile<6>(p, stream, n_in, n_out, row0, nrows, ct_s, mc_s, tid);
+        else cos_tile<8>(p, stream, n_in, n_out, row0, nrows, ct_s, mc_s, tid);
     }
 }
 
@@ -475,17 +491,14 @@ cudaError_t launch_mel_cos(const MelArgs& a, cudaStream_t st) {
     c.vidx = a.vidx; c.vcount = a.vcount; c.nfrm = a.nfrm;
     c.out[0] = a.out_mag; c.out[1] = a.out_real; c.out[2] = a.out_imag; c.out_f64 = a.out_dtype == MPB_F64 ? 1 : 0;
     const int cos_smem_bytes = 64 * 64 * 8 + CO_ROWS * CO_PITCH * 8;
-    const unsigned tiles = (unsigned)((a.nfrm + CO_ROWS - 1) / CO_ROWS);
-    // magnitude stream, then the two phase streams (48 outputs cover phase_dim <= 48)
-    auto run = [&](auto kern, int stream0, int n_streams) -> cudaError_t {
-        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cos_smem_bytes);
-        if (e2 != cudaSuccess) return e2;
-        kern<<<dim3(tiles, n_streams), CO_THREADS, cos_smem_bytes, st>>>(c, stream0);
-        return cudaGetLastError();
-    };
-    e = a.n_mag <= 48 ? run(k_mel_cos<6>, 0, 1) : run(k_mel_cos<8>, 0, 1);
+    const int64_t tiles = (a.nfrm + CO_ROWS - 1) / CO_ROWS;
+    int gx = (2 * a.num_sms + 2) / 3;                                   // 3 streams x gx CTAs ~ two CTAs per SM
+    if (gx > tiles) gx = (int)tiles;
+    if (gx < 1) return cudaSuccess;
+    e = cudaFuncSetAttribute(k_mel_cos, cudaFuncAttributeMaxDynamicSharedMemorySize, cos_smem_bytes);
     if (e != cudaSuccess) return e;
-    return a.phase_dim <= 48 ? run(k_mel_cos<6>, 1, 2) : run(k_mel_cos<8>, 1, 2);
+    k_mel_cos<<<dim3((unsigned)gx, 3), CO_THREADS, cos_smem_bytes, st>>>(c);
+    return cudaGetLastError();
 }
 
 }  // namespace mpb
