@@ -9,10 +9,17 @@ magphase_b200/synth.py).  `value` is device-timed with signals, descriptors and 
 Under torchrun every rank runs its own shard of utterances (weak scaling, no data-path collective: the only
 NCCL traffic is the scattered work list and the final counters).
 """
+import os
+
+# The CPU arm forks one worker per core (the reference's own fan-out, src/libutils.py:32-63): every worker must run its BLAS
+# single-threaded or 32 workers x 32 BLAS threads oversubscribe the host.  OpenBLAS / MKL / OpenMP size their pools when numpy
+# is IMPORTED, so the variables are set before that import (round 1 set them afterwards: the N=1 reference value was 6x low).
+for _k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
+    os.environ[_k] = '1'
+
 import argparse
 import json
 import multiprocessing
-import os
 import statistics
 import subprocess
 import sys
@@ -28,25 +35,6 @@ METRIC = 'analysis+synthesis frames/sec at 48 kHz FFT=4096'
 FS = 48000
 FFT_LEN = 4096
 DISTINCT = 16          # distinct synthetic utterances generated per rank (tiled up to --utts)
-
-def fp32_fma_view(kernels, nf, nv, H, sm_mhz, num_sms, mag_dim=60, nmel=58, phase_dim=45, hb=512):
-    """the two tile products are FP32-FMA bound, not HBM bound, so next to their HBM fraction report the
-    algorithmic FLOP/s against the non-tensor FP32 peak.  Peak = SMs x 128 FMA lanes x 2 x the SM clock sampled during the
-    timed region (derived from the clock, not a measured GEMM).  FMAs per step: warp product (nf x mag_dim + 2 nv x nmel)
-    x (H - 1) bins (src/libaudio.py:575-601 as a matrix); un-warp product nf x mag_dim x H +
-    2 nv x phase_dim x hb (src/libaudio.py:667-684).  Adds an 'fp32_fma' entry to those kernels in place."""
-    peak = num_sms * 128 * 2 * sm_mhz * 1e6 / 1e12
-    fmas = {'k_mel_gemm': (nf * mag_dim + 2 * nv * nmel) * (H - 1),
-            'k_mel_unwarp': nf * mag_dim * H + 2 * nv * phase_dim * hb}
-    for k in kernels:
-        n = fmas.get(k['name'])
-        if n and k['ms_per_step'] > 0 and peak > 0:
-            tf = 2.0 * n / (k['ms_per_step'] * 1e-3) / 1e12
-            k['fp32_fma'] = {'flops_per_step': int(2 * n), 'achieved_tflops': tf, 'peak_tflops': peak, 'frac': tf / peak,
-                             'peak_source': '%d SMs x 128 FMA/clk x 2 x %.0f MHz (sampled SM clock; derived, not measured)'
-                                            % (num_sms, sm_mhz)}
-    return kernels
-
 
 # --------------------------------------------------------------------------------------------
 # CPU arm: the reference's own implementation (oracle/_ref, py3 translation) or the numpy oracle port
@@ -123,6 +111,11 @@ def _cpu_init(workload):
     so that no timed pass pays for them."""
     global _CPU_WORKLOAD
     _CPU_WORKLOAD = workload
+    try:                                   # belt and braces: also cap pools a library may have sized before the fork
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
     from magphase_b200.synth import synth_utterance
     sig, pm, voi = synth_utterance(99, fs=FS, dur_s=0.3)
     if workload == 'compressed':
@@ -149,8 +142,6 @@ def make_cpu_inputs(n_utts, dur_s):
 def run_cpu_arm(n_utts, dur_s, steps, warmup, workload='compressed'):
     """K timed steps (after W warm-ups), each a Pool.map over n_utts utterances on all host cores --
     the reference's own fan-out (src/libutils.py:32-63)."""
-    for k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
-        os.environ[k] = '1'
     global _CPU_WORKLOAD
     _CPU_WORKLOAD = workload
     kind = _cpu_impl()[0]
@@ -165,7 +156,7 @@ def run_cpu_arm(n_utts, dur_s, steps, warmup, workload='compressed'):
             f, dt = cpu_pass(pool, n_utts)
             frames += f
             secs += dt
-    return dict(kind=kind, cores=cores, frames_per_step=frames // max(steps, 1), value=frames / secs,
+    return dict(kind=kind, cores=cores, n_utts=n_utts, dur_s=dur_s, frames_per_step=frames // max(steps, 1), value=frames / secs,
                 ms_per_step=1e3 * secs / max(steps, 1),
                 sample=('%d x %.1f s synth48k-v1 utterances per step, Pool(%d): ' % (n_utts, dur_s, cores)) + (
                     'analysis_with_del_comp_from_pm + compute_lossless_feats + format_for_modelling(60/45/45; SPTK mcep '
@@ -224,6 +215,51 @@ class ClockSampler:
                     reasons=reasons, samples=len(inside), note=note)
 
 
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        if os.path.exists(peaks_path):
+            return float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except (KeyError, ValueError, TypeError, OSError):
+        pass
+    return 6650.0, 'fallback (B200_PROFILING.md: 6.65 TB/s)'
+
+
+def kernel_table(prof, prof_steps, kbytes, kflops, peak_gbs, fma_peaks, traffic_pf, nf):
+    """Per-kernel records from the library's CUDA-event brackets: algorithmic HBM bytes -> GB/s and fraction of the measured
+    copy bandwidth; for the compute-bound kernels also algorithmic flops against the MEASURED non-tensor FMA peak."""
+    out = []
+    for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        per = ms / prof_steps
+        kb = float(kbytes.get(name, 0))
+        gbs = kb / (per * 1e-3) / 1e9 if per > 0 else 0.0
+        rec = dict(name=name, launches_per_step=cnt // prof_steps, ms_per_step=per, algorithmic_bytes_per_step=int(kb), gbs=gbs,
+                   frac=gbs / peak_gbs,
+                   dram_traffic_per_step=(int(traffic_pf[name] * nf) if name in traffic_pf else None))
+        if name in kflops and per > 0:
+            fl, which = kflops[name]
+            tf = fl / (per * 1e-3) / 1e12
+            rec['compute'] = {'flops_per_step': int(fl), 'achieved_tflops': tf, 'pipe': which, 'peak_tflops': fma_peaks[which],
+                              'frac': tf / fma_peaks[which] if fma_peaks[which] > 0 else None,
+                              'peak_source': 'measured on this device by mpb_measure_fma_peak (register-resident FMA chains)'}
+        out.append(rec)
+    return out
+
+
+def time_steps(step, steps, warmup, barrier, torch):
+    """W untimed + K timed calls of step(); device time of the timed region in ms (CUDA events on the current stream)."""
+    for _ in range(warmup):
+        step()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step()
+    t1.record()
+    barrier()
+    return t0.elapsed_time(t1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -236,20 +272,23 @@ def main():
     ap.add_argument('--utts', type=int, default=128, help='utterances per GPU per step (device-timed arm)')
     ap.add_argument('--dur', type=float, default=5.0, help='utterance length in seconds')
     ap.add_argument('--e2e-utts', type=int, default=0, help='utterances per GPU per step (host-API arm); 0 = auto')
-    ap.add_argument('--cpu-utts', type=int, default=0, help='utterances per step of the CPU arm; 0 = auto')
-    ap.add_argument('--cpu-dur', type=float, default=0.0, help='utterance length of the CPU arm sample; 0 = auto')
+    ap.add_argument('--cpu-utts', type=int, default=0, help='utterances per step of the CPU arm; 0 = 2 per host core')
+    ap.add_argument('--cpu-dur', type=float, default=0.0, help='utterance length of the CPU arm sample; 0 = --dur')
     ap.add_argument('--feat-dtype', default='f32', choices=['f32', 'f64'], help='lossless feature storage in HBM')
     ap.add_argument('--analysis-compute', default='f64', choices=['f32', 'f64'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the sub-records (lossless chain, configs 3 / 4 / 5)')
+    ap.add_argument('--stream-utts', type=int, default=2048, help='utterances per GPU of the streamed many-batch record (config 5)')
     ap.add_argument('--ola-target', type=int, default=32, help='frames per overlap-add run (device-timed arm)')
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
     comp = a.workload == 'compressed'
+    cores = os.cpu_count() or 1
     if a.cpu_utts == 0:
-        a.cpu_utts = 16 if comp else 32
+        a.cpu_utts = 2 * cores            # two tasks per worker: no core idles while the slowest utterance finishes
     if a.cpu_dur == 0.0:
-        a.cpu_dur = 2.0 if comp else a.dur     # the reference's compressed synthesis runs at ~70 frames/s/core
+        a.cpu_dur = a.dur                 # the same utterances as the GPU arm
     if a.e2e_utts == 0:
         a.e2e_utts = 128 if comp else 8
     rank = int(os.environ.get('RANK', 0))
@@ -267,7 +306,8 @@ def main():
             'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': 'frames/s', 'n_gpus': a.gpus,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload, 'fs': FS, 'fft_len': FFT_LEN},
+            'config': {'workload': workload, 'fs': FS, 'fft_len': FFT_LEN,
+                       'sample': 'each step = %d of those utterances (%.0f s each) on %d host cores' % (r['n_utts'], r['dur_s'], r['cores'])},
             'cpu_baseline': {'value': r['value'], 'unit': 'frames/s', 'cores': r['cores'], 'kind': r['kind'],
                              'sample': r['sample']},
             'e2e': {'value': r['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -308,6 +348,25 @@ def main():
     ana_compute = F64 if a.analysis_compute == 'f64' else F32
     d_sig = torch.from_numpy(np.concatenate([u[0] for u in utts]).astype(np.float32)).to(dev)   # PCM16/32768: exact in f32
     geom = ([u[0].size for u in utts], [u[1] for u in utts], [u[2] for u in utts])
+
+    def make_lossless(g, n_utts=None):
+        gg = g if n_utts is None else tuple(x[:n_utts] for x in g)
+        lp = LosslessPlan(*gg, FS, FFT_LEN, device=local_rank, ola_target_frames=a.ola_target)
+        feats = lp.alloc_features(feat_dt)
+        d_out = lp.alloc_output(F32)
+        sig = d_sig if n_utts is None else d_sig[:int(sum(gg[0]))]
+
+        def step(evs=None):
+            if evs:
+                evs[0].record()
+            lp.analysis(sig, feats, compute=ana_compute)
+            if evs:
+                evs[1].record()
+            lp.synthesis(feats, d_out, compute=F32)
+            if evs:
+                evs[2].record()
+        return lp, step
+
     if comp:
         plan = CompressedPlan(*geom, FS, FFT_LEN, mag_dim=60, phase_dim=45, device=local_rank, ola_target_frames=a.ola_target)
 
@@ -317,24 +376,12 @@ def main():
             plan.analysis(d_sig, compute=ana_compute)
             if evs:
                 evs[1].record()
-            plan.synthesis()
+            plan.synthesis()           # includes the MT19937 draw of the aperiodic noise (src/magphase.py:883) on the device
             if evs:
                 evs[2].record()
         bytes_ana, bytes_syn = plan.analysis_bytes(), plan.synthesis_bytes()
     else:
-        plan = LosslessPlan(*geom, FS, FFT_LEN, device=local_rank, ola_target_frames=a.ola_target)
-        feats = plan.alloc_features(feat_dt)
-        d_out = plan.alloc_output(F32)
-
-        def step(evs=None):
-            if evs:
-                evs[0].record()
-            plan.analysis(d_sig, feats, compute=ana_compute)
-            if evs:
-                evs[1].record()
-            plan.synthesis(feats, d_out, compute=F32)
-            if evs:
-                evs[2].record()
+        plan, step = make_lossless(geom)
         bytes_ana, bytes_syn = plan.analysis_bytes(F32, feat_dt), plan.synthesis_bytes(feat_dt, F32)
 
     def barrier():
@@ -397,7 +444,6 @@ def main():
     n_smp = sum(s.size for s in e_sig)
     if comp:
         feat_bytes = 8 * sum(o[0].size + o[1].size + o[2].size for o in outs)
-        n_noise = sum(y.size for y in ys)      # ~ one noise sample per output sample
         # signals cross PCIe as float32 (PCM-exact samples are narrowed on the host, mpb_stage.cu); analysis descriptors
         # 17 B/frame; features 8 B/value each way; synthesis descriptors 35 B/frame; the noise is drawn on the device
         # (only the 2.5 KB MT19937 state travels)
@@ -407,6 +453,20 @@ def main():
         feat_bytes = 3 * 8 * sum(o[0].size for o in outs)
         h2d = 4 * n_smp + 16 * e_frames + feat_bytes + 4 * e_frames
         d2h = feat_bytes + 8 * sum(y.size for y in ys)
+    del outs, ys
+
+    # ---- sub-records: the other chain and the other BASELINE configs, each its own short timed region ----
+    extras = {}
+    H, nf = FFT_LEN // 2 + 1, plan.nfrm
+    if not a.no_extras and comp:
+        try:
+            extras = run_extras(a, torch, _lib, mp, CompressedPlan, make_lossless, geom, d_sig, utts, barrier, local_rank, world, rank)
+        except Exception as e:                      # explanatory records must never cost the headline line
+            extras = {'error': '%s: %s' % (type(e).__name__, e)}
+
+    # ---- measured roofline denominators ----
+    peak, peak_src = hbm_peak()
+    fma_peaks = {'fp32': _lib.measure_fma_peak(F32, local_rank), 'fp64': _lib.measure_fma_peak(F64, local_rank)}
 
     # ---- reduce over ranks: max time, summed frames ----
     stats, counts = reduce_counters([total_ms, e_secs, ana_ms, syn_ms], [plan.nfrm, e_frames], device=dev)
@@ -417,64 +477,63 @@ def main():
     if rank != 0:
         return
 
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md: 6.65 TB/s)'
-    try:
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
-    except (KeyError, ValueError, TypeError, OSError):
-        pass
-    # algorithmic HBM bytes per launch of each kernel = what its own contract must move
-    H, nf = FFT_LEN // 2 + 1, plan.nfrm
+    # algorithmic HBM bytes per step of each kernel = what its own contract must move, and the
+    # algorithmic flops of the compute-bound ones (a real N-point FFT = 2.5 N log2 N flops)
     nv = getattr(plan, 'n_voiced', nf)       # the phase rows / phase-stream products only exist for voiced frames
     vf = nv / max(nf, 1)
+    LP = (H + 3) & ~3
+    fft_flops = 2.5 * FFT_LEN * np.log2(FFT_LEN)
+    n_noise, n_out = getattr(plan, 'n_noise', 0), getattr(plan, 'n_out', 0)
     kbytes = {
-        'k_analysis<logp>': plan.n_sig * 4 + nf * 17 + (nf + 2 * nv) * H * 4,
+        'k_analysis<logp>': plan.n_sig * 4 + nf * 17 + (nf + 2 * nv) * LP * 4,
         'k_analysis': plan.n_sig * 4 + nf * 16 + 3 * nf * H * (8 if (not comp and feat_dt == F64) else 4),
-        'k_synthesis_lossless': 3 * nf * H * (8 if feat_dt == F64 else 4) + nf * 4 + getattr(plan, 'n_out', 0) * 4,
-        'k_mel_gemm': (nf + 2 * nv) * H * 4 + nf * 150 * 4,
-        'k_mel_finish': nf * 150 * 4,
-        'k_mel_unwarp': nf * 150 * 4 + nf * H * 4 + vf * nf * 2 * 512 * 4,
-        'k_analysis<noise_logsq>': getattr(plan, 'n_noise', 0) * 4 + nf * 25 + nf * (H + 1) * 8,      # + stored noise spectra
+        'k_synthesis_lossless': 3 * nf * H * (8 if feat_dt == F64 else 4) + nf * 4 + n_out * 4,
+        'k_mel_warp_tc': (nf + 2 * nv) * LP * 4 + (nf + 2 * nv) * 64 * 4,
+        'k_mel_cos': (nf + 2 * nv) * 64 * 4 + nf * 150 * 4,
+        'k_mel_unwarp_tc': nf * 150 * 4 + nf * H * 4 + 2 * nv * 512 * 4,
+        'k_mel_gemm': (nf + 2 * nv) * H * 4 + nf * 150 * 4, 'k_mel_finish': nf * 150 * 4,
+        'k_mel_unwarp': nf * 150 * 4 + nf * H * 4 + 2 * nv * 512 * 4,
+        'k_analysis<noise_logsq>': n_noise * 4 + nf * 25 + nf * (H + 1) * 8,      # + stored noise spectra
+        'k_mt19937_stream+k_mt_to_uniform': n_noise * 4,
         'k_noise_gain': nf * 9,
-        'k_synthesis_compressed': nf * (H + 1) * 8 + nf * H * 4 + vf * nf * 2 * 512 * 4 + nf * 45
-                                  + getattr(plan, 'n_out', 0) * 4,
+        'k_synthesis_compressed': nf * (H + 1) * 8 + nf * H * 4 + 2 * nv * 512 * 4 + nf * 45 + n_out * 4,
+    }
+    kflops = {
+        'k_analysis<logp>': (nf * fft_flops, 'fp64'), 'k_analysis': (nf * fft_flops, 'fp64' if ana_compute == F64 else 'fp32'),
+        'k_analysis<noise_logsq>': (nf * fft_flops, 'fp32'), 'k_synthesis_compressed': (nf * fft_flops, 'fp32'),
+        'k_synthesis_lossless': (nf * fft_flops, 'fp32'),
+        'k_mel_cos': (2.0 * (nf * 60 * 60 + 2 * nv * 58 * 45), 'fp64'),
     }
     traffic_pf, traffic_src = {}, None
-    tpath = os.path.join(ROOT, 'profiles', 'r1b', 'traffic_per_frame.json')
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        traffic_pf, traffic_src = tj['dram_bytes_per_frame'], 'profiles/r1b/traffic_per_frame.json (ncu --set full capture, scaled to this launch size)'
-    kernels = []
-    for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-        per_step_ms = ms / prof_steps
-        kb = float(kbytes.get(name, 0))
-        gbs = kb / (per_step_ms * 1e-3) / 1e9 if per_step_ms > 0 else 0.0
-        kernels.append(dict(name=name, launches_per_step=cnt // prof_steps, ms_per_step=per_step_ms,
-                            algorithmic_bytes_per_step=int(kb), gbs=gbs, frac=gbs / peak,
-                            dram_traffic_per_step=(int(traffic_pf[name] * nf) if name in traffic_pf else None)))
+    for rdir in ('r2', 'r1b'):
+        tpath = os.path.join(ROOT, 'profiles', rdir, 'traffic_per_frame.json')
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic_pf = tj['dram_bytes_per_frame']
+            traffic_src = 'profiles/%s/traffic_per_frame.json (ncu --set full capture, scaled to this launch size)' % rdir
+            break
+    kernels = kernel_table(prof, prof_steps, kbytes, kflops, peak, fma_peaks, traffic_pf, nf)
     dom = kernels[0]
-    try:          # explanatory only: never let it cost the line
-        if comp:
-            fp32_fma_view(kernels, nf, nv, H, float(clocks.get('sm_mhz') or clocks.get('sm_max_mhz') or 0.0),
-                          torch.cuda.get_device_properties(dev).multi_processor_count)
-    except Exception:
-        pass
     ms_per_step = total_ms / a.steps
     value = frames_all / (ms_per_step * 1e-3)
     chain_bytes = bytes_ana + bytes_syn
+    known = [k['dram_traffic_per_step'] for k in kernels if k['dram_traffic_per_step']]
+    chain_traffic = int(sum(known)) if known else None
+    e2e_value = e_frames_all / (e_secs / e_steps)
     line = {
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64 analysis butterflies, f32 elsewhere; f32 storage',
+        'dtype': 'f64 analysis butterflies; f32 elsewhere; 3xTF32 tensor-core tile products; f32 storage',
         'data': 'synthetic',
         'config': {'workload': workload, 'fs': FS, 'fft_len': FFT_LEN, 'frames_per_gpu_per_step': plan.nfrm,
                    'voiced_fraction': round(vf, 3),
                    'mean_shift_samples': round(plan.mean_shift, 1),
+                   'rng': 'the np.random.uniform draw of the aperiodic noise runs on the device inside every timed step',
                    'l2_note': 'per-step intermediates %.1f GB in HBM >> 126 MB L2' % (3 * nf * H * 4 / 1e9),
                    'parallelism': 'utterance-sharded x%d' % world},
-        'e2e': {'value': e_frames_all / (e_secs / e_steps), 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d),
-                'd2h_bytes_per_step': int(d2h), 'utts_per_gpu_per_step': len(e_utts), 'api': api},
+        'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d),
+                'd2h_bytes_per_step': int(d2h), 'utts_per_gpu_per_step': len(e_utts), 'api': api,
+                'frac_of_value': e2e_value / value if value > 0 else None},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s',
                      'frac': dom['frac'],
@@ -483,19 +542,132 @@ def main():
                      'traffic_source': traffic_src, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': int(dom['algorithmic_bytes_per_step'] / max(dom['launches_per_step'], 1)),
                      'ms_per_launch': dom['ms_per_step'] / max(dom['launches_per_step'], 1),
-                     'note': 'none of the kernels of this path is HBM-bound: the FFT kernels are issue / FP64-pipe limited '
-                             '(55-71 % of the issue slots, FP64 pipe 42 % in the analysis kernels), the tile products run at '
-                             '57-60 % of the FP32 FMA pipe; DRAM traffic equals the algorithmic bytes (profiles/README.md)'},
-        'halves': {'analysis_ms': ana_ms, 'synthesis_ms': syn_ms,
-                   'chain_algorithmic_bytes_per_step': int(chain_bytes),
-                   'chain_gbs': chain_bytes / (ms_per_step * 1e-3) / 1e9},
+                     'compute': dom.get('compute'),
+                     'note': 'the dominant kernels are the three FFT kernels: their contract is HBM bytes (this fraction), their '
+                             'practical limit is instruction issue / the FP64 pipe (see compute.frac against the measured FMA '
+                             'peak and profiles/); the tensor-core tile products are HBM-bound (their own frac in kernels[])'},
+        'chain': {'algorithmic_bytes_per_step': int(chain_bytes), 'gbs': chain_bytes / (ms_per_step * 1e-3) / 1e9,
+                  'frac_of_hbm': chain_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                  'dram_traffic_per_step': chain_traffic,
+                  'traffic_over_algorithmic': (chain_traffic / chain_bytes if chain_traffic else None),
+                  'note': 'SURVEY 8(d) bytes of the reference API contract (samples + descriptors + low-dimensional features); '
+                          'the intermediates between the kernels (log periodograms, noise spectra, un-warped rows) are extra traffic'},
+        'fma_peaks_tflops': fma_peaks,
+        'halves': {'analysis_ms': ana_ms, 'synthesis_ms': syn_ms},
         'kernels': kernels,
         'clocks': clocks,
     }
+    line.update(extras)
     if cpu is not None:
         line['cpu_baseline'] = {'value': cpu['value'], 'unit': 'frames/s', 'cores': cpu['cores'], 'kind': cpu['kind'],
                                 'sample': cpu['sample']}
     print(json.dumps(line))
+
+
+def run_extras(a, torch, _lib, mp, CompressedPlan, make_lossless, geom, d_sig, utts, barrier, local_rank, world, rank):
+    """Sub-records of the default line (each a short timed region of its own, per GPU; under torchrun every rank runs them and
+    rank 0 reports its own numbers):
+      lossless      BASELINE config 1 chain, device-resident (the chain SURVEY 8(d)'s 125 M frames/s HBM roofline is written for)
+      extract_tts   config 3: analysis_for_acoustic_modelling's feature extraction (mag 60, phase_dim 10, alpha_phase=False quirk)
+      generate_16k  config 4: 16 kHz constant-rate features -> post_filter -> synthesis_from_compressed with the output high-pass
+      stream        config 5 per GPU: many batches of UNEQUAL utterances streamed through the host API (LPT order)"""
+    ex = {}
+    steps = max(3, min(a.steps, 5))
+    peak, _ = hbm_peak()
+    F32 = _lib.MPB_F32
+    # ---- lossless chain ----
+    n_l = min(len(utts), 64)
+    lp, lstep = make_lossless(geom, n_l)
+    ms = time_steps(lstep, steps, 3, barrier, torch) / steps
+    _lib.profile_begin(local_rank)
+    for _ in range(2):
+        lstep()
+    prof = _lib.profile_end(local_rank)
+    lb = lp.analysis_bytes(F32, F32) + lp.synthesis_bytes(F32, F32)
+    ex['lossless'] = {'workload': 'analysis_lossless -> synthesis_from_lossless, %d x %.0f s utterances, float32 features in HBM' % (n_l, a.dur),
+                      'value': lp.nfrm / (ms * 1e-3), 'unit': 'frames/s', 'ms_per_step': ms,
+                      'chain_algorithmic_bytes_per_step': int(lb), 'chain_gbs': lb / (ms * 1e-3) / 1e9,
+                      'frac_of_hbm': lb / (ms * 1e-3) / 1e9 / peak,
+                      'kernels': [dict(name=k, ms_per_step=v[1] / 2) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])]}
+    del lp, lstep
+    torch.cuda.empty_cache()
+    # ---- config 3: feature extraction for TTS (analysis only) ----
+    p3 = CompressedPlan(*geom, FS, FFT_LEN, mag_dim=60, phase_dim=10, device=local_rank, alpha_phase=0.0)
+    ms = time_steps(lambda: p3.analysis(d_sig), steps, 3, barrier, torch) / steps
+    e_n = min(len(utts), 128)
+    e_sig, e_pm, e_voi = [u[0] for u in utts[:e_n]], [u[1] for u in utts[:e_n]], [u[2] for u in utts[:e_n]]
+    f3 = lambda: mp.analysis_compressed_batch(e_sig, FS, e_pm, e_voi, fft_len=FFT_LEN, mag_dim=60, phase_dim=10, alpha_phase=0.0)
+    f3(); outs = f3()
+    barrier()
+    t = time.perf_counter()
+    for _ in range(3):
+        f3()
+    torch.cuda.synchronize()
+    e_s = (time.perf_counter() - t) / 3
+    ex['extract_tts'] = {'workload': 'config 3: analysis_compressed(mag_dim=60, phase_dim=10, alpha_phase=0.0 as analysis_for_acoustic_modelling '
+                                     'passes it), %d x %.0f s utterances' % (len(utts), a.dur),
+                         'value': p3.nfrm / (ms * 1e-3), 'unit': 'frames/s', 'ms_per_step': ms,
+                         'e2e': {'value': sum(o[4].size for o in outs) / e_s, 'unit': 'frames/s', 'utts': e_n,
+                                 'api': 'analysis_compressed_batch (NumPy in / out)'}}
+    del p3, outs
+    torch.cuda.empty_cache()
+    # ---- config 4: 16 kHz constant-rate generation with post-filter and output high-pass (host API: NumPy in / out) ----
+    from magphase_b200.synth import synth_utterance
+    fs16 = 16000
+    base16 = [synth_utterance(3000 + u, fs=fs16, dur_s=a.dur) for u in range(8)]
+    n16 = 128
+    u16 = [base16[i % len(base16)] for i in range(n16)]
+    feats16 = mp.analysis_compressed_batch([u[0] for u in u16], fs16, [u[1] for u in u16], [u[2] for u in u16], mag_dim=60,
+                                           phase_dim=45, b_const_rate=True)
+    feats16 = [f[:4] for f in feats16]
+    n_rows = sum(f[0].shape[0] for f in feats16)
+
+    def g16():
+        pf = [(mp.post_filter(f[0], fs16), f[1], f[2], f[3]) for f in feats16]
+        return mp.synthesis_from_compressed_batch(pf, fs16, b_const_rate=True, b_out_hpf=True)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        g16(); ys = g16()
+        barrier()
+        t = time.perf_counter()
+        for _ in range(3):
+            g16()
+        torch.cuda.synchronize()
+        g_s = (time.perf_counter() - t) / 3
+    n_smp = sum(y.size for y in ys)
+    ex['generate_16k'] = {'workload': 'config 4: %d utterances of %.0f s at 16 kHz, constant-rate (5 ms) features -> post_filter -> '
+                                      'synthesis_from_compressed(b_const_rate=True, b_out_hpf=True), host API end to end' % (n16, a.dur),
+                          'value': n_rows / g_s, 'unit': 'constant-rate frames/s', 'seconds_per_step': g_s,
+                          'audio_seconds_per_second': n_smp / fs16 / g_s}
+    del feats16, ys
+    # ---- config 5 (per GPU): a stream of many batches of unequal utterances through the host API ----
+    durs = [2.0, 3.0, 4.0, 5.0, 6.0, 8.0]
+    pool = [synth_utterance(5000 + i, fs=FS, dur_s=d) for i, d in enumerate(durs)]
+    n_total = max(128, int(a.stream_utts))
+    order = np.random.Generator(np.random.PCG64(7)).integers(0, len(pool), n_total)
+    # longest first (LPT) inside this GPU's shard, then batches of 128 utterances
+    order = sorted(order.tolist(), key=lambda i: -pool[i][0].size)
+    batches = [order[i:i + 128] for i in range(0, n_total, 128)]
+    def run_stream(bl):
+        frames = 0
+        for b in bl:
+            sig, pm, voi = [pool[i][0] for i in b], [pool[i][1] for i in b], [pool[i][2] for i in b]
+            outs = mp.analysis_compressed_batch(sig, FS, pm, voi, fft_len=FFT_LEN, mag_dim=60, phase_dim=45)
+            mp.synthesis_from_compressed_batch([o[:4] for o in outs], FS, b_out_hpf=False)
+            frames += sum(o[4].size for o in outs)
+        return frames
+    run_stream(batches[:1])        # warm-up: largest batch first (scratch buffers grow once)
+    barrier()
+    t = time.perf_counter()
+    frames = run_stream(batches)
+    torch.cuda.synchronize()
+    s_s = time.perf_counter() - t
+    ex['stream'] = {'workload': 'config 5 per GPU: %d utterances of 2-8 s (LPT order), %d batches of 128 through '
+                                'analysis_compressed_batch -> synthesis_from_compressed_batch' % (n_total, len(batches)),
+                    'value': frames / s_s, 'unit': 'frames/s', 'frames': int(frames), 'seconds': s_s,
+                    'note': 'BASELINE config 5 = 12,500 such utterances per GPU on 8 GPUs: run with --stream-utts 12500'}
+    return ex
 
 
 if __name__ == '__main__':

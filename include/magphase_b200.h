@@ -59,6 +59,11 @@ int64_t mpb_launch_count(const mpb_ctx* ctx);
 int mpb_profile_begin(mpb_ctx* ctx);
 int mpb_profile_end(mpb_ctx* ctx, char* buf, int64_t buf_len);
 
+/* Measured non-tensor FMA peak of the device in TFLOP/s (2 flops per FMA) for MPB_F32 / MPB_F64: register-resident FMA
+ * chains on every SM, best of three timed repetitions.  The roofline denominator of the compute-bound kernels
+ * (the reference publishes no throughput; SURVEY.md 8(d) asks for a measured figure).                             */
+int mpb_measure_fma_peak(mpb_ctx* ctx, int dtype, double* tflops);
+
 /* Page-locked host buffers for result arrays (device->host copies into them run at full PCIe rate).            */
 int mpb_host_alloc(mpb_ctx* ctx, int64_t bytes, void** out);
 int mpb_host_free(mpb_ctx* ctx, void* p);
@@ -328,6 +333,10 @@ int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* 
                             double low, double high, void* out_dev, int out_dtype);
 int mpb_mt19937_uniform_host(mpb_ctx* ctx, uint32_t* key, int32_t* pos, int64_t n,
                              double low, double high, double* out);
+/* Enqueue-only variant of mpb_mt19937_uniform_dev: fills out_dev on `stream` without synchronising and without advancing the
+ * caller's state (device-resident pipelines that re-draw the same stretch of the stream every step).                         */
+int mpb_mt19937_fill_dev(mpb_ctx* ctx, void* stream, const uint32_t* key, int32_t pos, int64_t n,
+                         double low, double high, void* out_dev, int out_dtype);
 /*
  * Long draws are cut into segments generated by different CTAs; a CTA reaches its segment by jump-ahead:
  * x[m+J] = XOR over the set bits i of (x^J mod phi) of x[m+i], phi = characteristic polynomial of the twister

@@ -31,6 +31,7 @@ SIGNATURES = {
     'mpb_launch_count': [_vp],
     'mpb_host_alloc': [_vp, _i64, C.POINTER(_vp)],
     'mpb_host_free': [_vp, _vp],
+    'mpb_measure_fma_peak': [_vp, C.c_int, C.POINTER(C.c_double)],
     'mpb_profile_begin': [_vp],
     'mpb_profile_end': [_vp, C.c_char_p, _i64],
     'mpb_analysis_lossless_dev': [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int,
@@ -62,6 +63,7 @@ SIGNATURES = {
     'mpb_min_phase_dev': [_vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp],
     'mpb_min_phase_host': [_vp, _vp, _i64, C.c_int, _vp],
     'mpb_mt19937_uniform_dev': [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, _vp, C.c_int],
+    'mpb_mt19937_fill_dev': [_vp, _vp, _vp, C.c_int32, _i64, C.c_double, C.c_double, _vp, C.c_int],
     'mpb_mt19937_uniform_host': [_vp, _vp, _vp, _i64, C.c_double, C.c_double, _vp],
     'mpb_mt19937_jump_poly': [_i64, _vp],
     'mpb_analysis_geometry': [_vp, _vp, _vp, C.c_int32, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp],
@@ -131,6 +133,13 @@ def ctx(device=None):
 
 def launch_count(device=None):
     return int(lib().mpb_launch_count(ctx(device)))
+
+
+def measure_fma_peak(dtype, device=None):
+    """Measured non-tensor FMA peak (TFLOP/s) of the device for MPB_F32 / MPB_F64."""
+    v = C.c_double()
+    check(lib().mpb_measure_fma_peak(ctx(device), dtype, C.byref(v)))
+    return float(v.value)
 
 
 def profile_begin(device=None):

@@ -505,6 +505,20 @@ int mpb_mt19937_uniform_dev(mpb_ctx* ctx, void* stream, uint32_t* key, int32_t* 
     return MPB_OK;
 }
 
+// Same draw, enqueue only: nothing is synchronised and the caller's state (key, pos: HOST, read before returning) is NOT
+// advanced -- for device-resident pipelines that re-draw the same stretch of the stream every step (bench.py times the
+// draw inside its step this way).
+int mpb_mt19937_fill_dev(mpb_ctx* ctx, void* stream, const uint32_t* key, int32_t pos, int64_t n, double low, double high,
+                         void* out_dev, int out_dtype) {
+    if (!ctx || !key) return fail(MPB_ERR_BAD_ARG, "NULL argument");
+    if (!dtype_ok(out_dtype) || n < 0 || pos < 0 || pos > 624) return fail(MPB_ERR_BAD_ARG, "bad dtype, size or MT19937 position");
+    if (n == 0) return MPB_OK;
+    if (!out_dev) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->mt_fin.need(sizeof(uint32_t) * 625));
+    return mt19937_enqueue(ctx, (cudaStream_t)stream, key, pos, &n, 1, low, high, out_dev, out_dtype, (uint32_t*)ctx->mt_fin.p, nullptr);
+}
+
 // x^(n_words) mod phi, phi = characteristic polynomial of the MT19937 transition (n_words = 0: phi minus its leading
 // term), as 624 little-endian 32-bit words.  Host only; exposes the jump-ahead arithmetic to the tests.
 int mpb_mt19937_jump_poly(int64_t n_words, uint32_t* out624) {

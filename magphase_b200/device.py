@@ -107,14 +107,16 @@ class CompressedPlan:
     (frame geometry, lf0, synthesis shifts, noise frame geometry, OLA runs) is computed once and uploaded."""
 
     def __init__(self, l_nsmpls, l_pm_smpls, l_voi, fs, fft_len=None, mag_dim=60, phase_dim=45, device=None,
-                 ola_target_frames=32, noise_seed=1234):
+                 ola_target_frames=32, noise_seed=1234, alpha_phase=None):
         self.fs = fs
         self.fft_len = mp.define_fft_len(fs) if fft_len is None else fft_len
         self.H = self.fft_len // 2 + 1
         self.mag_dim, self.phase_dim = mag_dim, phase_dim
         self.device = torch.device('cuda', _lib.default_device() if device is None else device)
         self.ctx = _lib.ctx(self.device.index)
-        self.mel = mp._MelPlan.get(fs, self.fft_len, mag_dim, phase_dim, None)
+        # alpha_phase: analysis-side warping of the phase streams (0.0 reproduces analysis_for_acoustic_modelling's
+        # alpha_phase=False quirk, src/magphase.py:3010); the synthesis side always un-warps with the default (:3271)
+        self.mel = mp._MelPlan.get(fs, self.fft_len, mag_dim, phase_dim, alpha_phase)
         self.syn = mp._SynPlan.get(fs, self.fft_len, mag_dim, phase_dim, None)
         n_utt = len(l_nsmpls)
         sig_off = np.zeros(n_utt + 1, dtype=np.int64)
@@ -151,9 +153,14 @@ class CompressedPlan:
         self._keep = {k: (up(v, v.dtype) if v is not None else None) for k, v in arrs.items()}
         self.frames = _lib.SynFrames(nfrm=self.nfrm, n_utt=n_utt,
                                      **{k: (_dp(v) if v is not None else None) for k, v in self._keep.items()})
-        rs = np.random.RandomState(noise_seed)
-        self.h_noise = [rs.uniform(-1, 1, n) for n in self.l_ns_len]
-        self.d_noise = up(np.concatenate(self.h_noise), np.float32)
+        # the aperiodic noise (np.random.uniform(-1, 1, ns_len) per utterance, src/magphase.py:883) is drawn ON THE DEVICE
+        # inside synthesis(), from NumPy's legacy MT19937 state for `noise_seed` (bit-identical stream); every call re-draws
+        # the same stretch, so repeated steps do the same work on the same numbers
+        st = np.random.RandomState(noise_seed).get_state()
+        self.mt_key = np.ascontiguousarray(st[1], dtype=np.uint32)
+        self.mt_pos = int(st[2])
+        self.d_noise = torch.empty(max(self.n_noise, 1), dtype=torch.float32, device=self.device)
+        self.draw_noise = True
         # the compressed features live in HBM between the two halves
         self.d_mel = (torch.empty((self.nfrm, mag_dim), dtype=torch.float32, device=self.device),
                       torch.empty((self.nfrm, phase_dim), dtype=torch.float32, device=self.device),
@@ -176,8 +183,17 @@ class CompressedPlan:
             MPB_F32))
         return self.d_mel
 
+    def host_noise(self):
+        """The same draws as a list of float64 arrays (one per utterance), for parity checks against the oracle."""
+        rs = np.random.RandomState()
+        rs.set_state(('MT19937', self.mt_key.copy(), self.mt_pos, 0, 0.0))
+        return [rs.uniform(-1, 1, n) for n in self.l_ns_len]
+
     def synthesis(self, d_mel=None):
         m = self.d_mel if d_mel is None else d_mel
+        if self.draw_noise:
+            _lib.check(_lib.lib().mpb_mt19937_fill_dev(self.ctx, _stream(), _lib.ptr(self.mt_key), self.mt_pos, self.n_noise, -1.0,
+                                                       1.0, _dp(self.d_noise), MPB_F32))
         _lib.check(_lib.lib().mpb_synthesis_compressed_dev(
             self.syn.handle, _stream(), _dp(m[0]), _dp(m[1]), _dp(m[2]), MPB_F32, self.nfrm, _dp(self.d_need),
             _dp(self.d_noise), self.n_noise, C.byref(self.frames), _dp(self.d_runs), self.n_runs, 0, _dp(self.d_out),
