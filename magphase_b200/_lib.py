@@ -171,10 +171,17 @@ class _PinnedPool:
 
     @staticmethod
     def _bucket(nbytes):
+        """Sizes are quantised to {1, 1.25, 1.5, 1.75} x 2^k (at most 25 % slack): batches of similar size share buffers."""
         b = 1 << 16
         while b < nbytes:
             b <<= 1
-        return b if b - nbytes < (b >> 2) else ((nbytes + (1 << 20) - 1) >> 20) << 20
+        if b <= (1 << 16):
+            return b
+        q = b >> 3                       # eighths of the power of two: the candidates above b / 2 are 5/8 .. 8/8 of b
+        for m in (5, 6, 7, 8):
+            if m * q >= nbytes:
+                return m * q
+        return b
 
     def empty(self, shape, dtype=np.float64):
         import weakref
@@ -183,10 +190,14 @@ class _PinnedPool:
         if nbytes == 0 or nbytes > self.MAX_SINGLE:
             return np.empty(shape, dtype=dtype)
         size = self._bucket(nbytes)
+        addr = None
         with self.lock:
-            lst = self.free.get(size)
-            addr = lst.pop() if lst else None
-            if addr is not None:
+            # exact bucket first, else the smallest pooled buffer that is large enough and at most twice the request
+            # (page-locking a fresh buffer costs ~0.3 ms per MB: far more than carrying some slack)
+            cands = [sz for sz, lst in self.free.items() if lst and size <= sz <= 2 * size]
+            if cands:
+                size = min(cands)
+                addr = self.free[size].pop()
                 self.pooled -= size
         if addr is None:
             p = _vp()

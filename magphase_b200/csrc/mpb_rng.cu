@@ -14,10 +14,17 @@
 //    state transition is GF(2)-linear with characteristic polynomial phi (degree 19937), so with
 //    g_J(x) = x^J mod phi every word of the stream obeys  x[m+J] = XOR_{i : g_J[i] = 1} x[m+i]  (Cayley-Hamilton):
 //    a CTA generates the 19937+623 words that follow its current block and folds them with the set bits of g_J.
-//    Segment s is reached from the handed state through its base-4 digits with the polynomials g_{d J 4^e}
-//    (d = 1..3, e = 0..3): at most 4 folds.  phi comes from Berlekamp-Massey on the twister's own output and the
-//    polynomials from square-and-multiply, once per process on the host (mt_jump_tables) -- no magic tables.
+//    A fold is 19937 x 624 / 2 word XORs out of shared memory (25 MB of shared-memory traffic) -- as much as generating
+//    0.8 M words -- so the number of folds is what a draw costs: segment s = d0 + 256 d1 is reached with ONE fold by
+//    g_{d0 J} (255 polynomials) plus one by g_{256 d1 J} (d1 = 1..3) for the rare launch beyond 256 segments.  (Base-4
+//    digits, round 1: up to four folds per segment, 1.95 ms for the 30.7 M draws of a bench step.)  phi comes from
+//    Berlekamp-Massey on the twister's own output and the polynomials from square-and-multiply / repeated
+//    multiplication, once per process on host threads (jump_tables) -- no magic tables.
+#include <string.h>
+
+#include <algorithm>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "mpb_kernels.h"
@@ -39,20 +46,20 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 
 constexpr int MT_THREADS = 1024;
 constexpr int MT_DEG = 19937;
-constexpr int MT_SEG_TWISTS = 256;
+constexpr int MT_SEG_TWISTS = 1024;                           // a fold costs as much as ~1300 twists of generation: few, long segments
 constexpr int MT_SEG_WORDS = MT_SEG_TWISTS * 624;              // words per segment (a multiple of the block size)
-constexpr int MT_DIGITS = 4;                                   // base-4 digits of the segment index
-constexpr int MT_MAX_SEGS = 256;                               // segments per launch
+constexpr int MT_NPOLY = 255 + 3;                              // g_{d0 J}, d0 = 1..255, then g_{256 d1 J}, d1 = 1..3
+constexpr int MT_MAX_SEGS = 1024;                              // segments per launch
+constexpr int MT_HDR = 2 * MT_NPOLY * 2;                       // uint16 slots of the table header: int32 off[], cnt[]
 constexpr int MT_WIN = MT_DEG + 623;                           // words a fold reads: x[i + t], i < 19937, t < 624
 constexpr int MT_PAD = 768;                                    // zero words behind the window (padding index target)
 constexpr int MT_WIN_ALLOC = MT_WIN + MT_PAD;
 constexpr int MT_RING = 2048;
+constexpr int MT_IDX_STAGE = 5632;                             // uint16 indices staged per pass of a fold (11 KB: 2 CTAs per SM)
 
 struct MtJumpArgs {
-    const uint16_t* idx;                    // concatenated set-bit lists of the 12 polynomials, each padded to x16
-    int32_t off[3 * MT_DIGITS];
-    int32_t cnt[3 * MT_DIGITS];
-};
+    const uint16_t* idx;                    // header (int32 off[MT_NPOLY], cnt[MT_NPOLY], in uint16 units behind the header),
+};                                          // then the concatenated set-bit lists, each padded to a multiple of 16
 
 // x[] is the twister's word stream: x[n] = x[n-227] ^ f(x[n-624], x[n-623]),  f(m) := mt_mix(x[m], x[m+1]).
 // f is GF(2)-linear, so the recurrence can be substituted into itself:
@@ -78,21 +85,33 @@ __device__ __forceinline__ void mt_extend_flat(uint32_t* __restrict__ w, int hav
 }
 
 // One fold: w[0..623] = x[m .. m+623]  ->  w[0..623] = x[m+J .. m+J+623] for the polynomial given as a set-bit list.
-// part: 4 x 640 words of scratch.
-__device__ __forceinline__ void mt_fold(uint32_t* __restrict__ w, uint32_t* __restrict__ part,
+// part: 4 x 768 words of scratch; idx_s: MT_IDX_STAGE uint16 of shared memory.  The set-bit list (about 10,000 indices) is
+// staged through shared memory in two halves with coalesced 16-byte loads: read straight from global memory, the inner
+// loop waited one L2 latency per four indices (measured: 2.1 ms for the 30.7 M draws of a bench step, 80 % of it here).
+__device__ __forceinline__ void mt_fold(uint32_t* __restrict__ w, uint32_t* __restrict__ part, uint16_t* __restrict__ idx_s,
                                         const uint16_t* __restrict__ idx, int cnt, int t) {
     mt_extend_flat(w, 624, MT_WIN, t);
     const int q = t >> 8, u = t & 255;
-    const int per = cnt >> 2;                                  // cnt is a multiple of 16
-    const uint2* p = reinterpret_cast<const uint2*>(idx + q * per);
+    const int per = cnt >> 2;                                  // cnt is a multiple of 16: per is a multiple of 4
     const uint32_t* wu = w + u;
     uint32_t a0 = 0, a1 = 0, a2 = 0;
-#pragma unroll 2
-    for (int i = 0; i < per / 4; ++i) {
-        const uint2 v = __ldg(p + i);
-        const int i0 = v.x & 0xffff, i1 = v.x >> 16, i2 = v.y & 0xffff, i3 = v.y >> 16;
-        a0 ^= wu[i0] ^ wu[i1];          a1 ^= wu[i0 + 256] ^ wu[i1 + 256];   a2 ^= wu[i0 + 512] ^ wu[i1 + 512];
-        a0 ^= wu[i2] ^ wu[i3];          a1 ^= wu[i2 + 256] ^ wu[i3 + 256];   a2 ^= wu[i2 + 512] ^ wu[i3 + 512];
+    // quarter q of the CTA owns indices [q * per, (q + 1) * per); each pass stages `chunk` indices of every quarter
+    for (int done = 0; done < per; done += MT_IDX_STAGE / 4) {
+        const int chunk = min(per - done, MT_IDX_STAGE / 4);   // multiple of 4
+        __syncthreads();                                       // the previous pass has read idx_s
+        for (int i = t; i < chunk; i += MT_THREADS) {  // 2-byte loads, consecutive threads consecutive indices
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) idx_s[qq * (MT_IDX_STAGE / 4) + i] = __ldg(idx + qq * per + done + i);
+        }
+        __syncthreads();
+        const uint2* p = reinterpret_cast<const uint2*>(idx_s + q * (MT_IDX_STAGE / 4));
+#pragma unroll 4
+        for (int i = 0; i < chunk / 4; ++i) {
+            const uint2 v = p[i];
+            const int i0 = v.x & 0xffff, i1 = v.x >> 16, i2 = v.y & 0xffff, i3 = v.y >> 16;
+            a0 ^= wu[i0] ^ wu[i1];          a1 ^= wu[i0 + 256] ^ wu[i1 + 256];   a2 ^= wu[i0 + 512] ^ wu[i1 + 512];
+            a0 ^= wu[i2] ^ wu[i3];          a1 ^= wu[i2 + 256] ^ wu[i3 + 256];   a2 ^= wu[i2 + 512] ^ wu[i3 + 512];
+        }
     }
     part[q * 768 + u] = a0;
     part[q * 768 + u + 256] = a1;
@@ -111,6 +130,7 @@ k_mt19937_stream(const uint32_t* __restrict__ key_in, int32_t pos_in, uint32_t* 
     extern __shared__ uint32_t sm[];
     uint32_t* w = sm;                              // MT_WIN_ALLOC words: fold window, later the generation ring
     uint32_t* part = sm + MT_WIN_ALLOC;            // 4 x 768
+    uint16_t* idx_s = reinterpret_cast<uint16_t*>(part + 4 * 768);   // MT_IDX_STAGE staged set-bit indices
     const int t = threadIdx.x;
     const int s = blockIdx.x;
     const int64_t pos0 = pos_in;
@@ -133,11 +153,11 @@ k_mt19937_stream(const uint32_t* __restrict__ key_in, int32_t pos_in, uint32_t* 
             w[0] = (w[0] & 0x80000000u) | (y & 0x7fffffffu);
         }
         __syncthreads();
-#pragma unroll 1
-        for (int e = 0; e < MT_DIGITS; ++e) {
-            const int d = (s >> (2 * e)) & 3;
-            if (d) mt_fold(w, part, jt.idx + jt.off[3 * e + d - 1], jt.cnt[3 * e + d - 1], t);
-        }
+        const int32_t* hdr = reinterpret_cast<const int32_t*>(jt.idx);
+        const uint16_t* lists = jt.idx + MT_HDR;
+        const int d0 = s & 255, d1 = s >> 8;
+        if (d1) mt_fold(w, part, idx_s, lists + hdr[255 + d1 - 1], hdr[MT_NPOLY + 255 + d1 - 1], t);
+        if (d0) mt_fold(w, part, idx_s, lists + hdr[d0 - 1], hdr[MT_NPOLY + d0 - 1], t);
     }
     // ---- generation: ring of MT_RING words, ring index = (stream index - base) mod MT_RING ----
     const int64_t end = (base + MT_SEG_WORDS < need) ? base + MT_SEG_WORDS : need;
@@ -184,7 +204,7 @@ __global__ void k_mt_to_uniform(const uint32_t* __restrict__ raw, int64_t n, dou
     if (i >= n) return;
     const uint2 ab = reinterpret_cast<const uint2*>(raw)[i];
     const double r = ((double)(ab.x >> 5) * 67108864.0 + (double)(ab.y >> 6)) / 9007199254740992.0;
-    out[i] = (TO)(low + scale * r);
+    out[i] = (TO)__dadd_rn(low, __dmul_rn(scale, r));     // NumPy rounds the product, then the sum (no fused multiply-add)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -291,9 +311,7 @@ Limbs powx(uint64_t e, const Limbs& phi) {
 
 struct JumpTables {
     bool ok = false;
-    Limbs poly[3 * MT_DIGITS];
-    std::vector<uint16_t> idx;
-    int32_t off[3 * MT_DIGITS], cnt[3 * MT_DIGITS];
+    std::vector<uint16_t> idx;              // header + lists, exactly as the kernel reads it
 };
 
 const JumpTables& jump_tables() {
@@ -302,20 +320,38 @@ const JumpTables& jump_tables() {
     std::call_once(once, [] {
         const Limbs phi = mt_char_poly();
         if (!bit_of(phi, MT_DEG)) return;
-        Limbs b = powx((uint64_t)MT_SEG_WORDS, phi);
-        for (int e = 0; e < MT_DIGITS; ++e) {
-            jt.poly[3 * e + 0] = b;
-            jt.poly[3 * e + 1] = sqrmod(b, phi);
-            jt.poly[3 * e + 2] = mulmod(jt.poly[3 * e + 1], b, phi);
-            if (e + 1 < MT_DIGITS) b = sqrmod(jt.poly[3 * e + 1], phi);
-        }
-        for (int k = 0; k < 3 * MT_DIGITS; ++k) {
-            jt.off[k] = (int32_t)jt.idx.size();
+        std::vector<Limbs> poly((size_t)MT_NPOLY);
+        const Limbs g1 = powx((uint64_t)MT_SEG_WORDS, phi);
+        // g_{k J} = g_{(k-1) J} . g_J : eight host threads, each starting its range of k from a square-and-multiply power
+        const int n_thr = 8, span = (255 + n_thr - 1) / n_thr;
+        std::vector<std::thread> th;
+        for (int i = 0; i < n_thr; ++i)
+            th.emplace_back([&, i] {
+                const int k0 = i * span + 1, k1 = std::min(255, (i + 1) * span);
+                if (k0 > k1) return;
+                Limbs cur = k0 == 1 ? g1 : powx((uint64_t)MT_SEG_WORDS * (uint64_t)k0, phi);
+                for (int k = k0; k <= k1; ++k) {
+                    poly[(size_t)k - 1] = cur;
+                    if (k < k1) cur = mulmod(cur, g1, phi);
+                }
+            });
+        for (auto& t : th) t.join();
+        poly[255] = mulmod(poly[254], g1, phi);                  // g_{256 J}
+        poly[256] = sqrmod(poly[255], phi);                      // g_{512 J}
+        poly[257] = mulmod(poly[256], poly[255], phi);           // g_{768 J}
+        std::vector<int32_t> off((size_t)MT_NPOLY), cnt((size_t)MT_NPOLY);
+        std::vector<uint16_t> lists;
+        for (int k = 0; k < MT_NPOLY; ++k) {
+            off[k] = (int32_t)lists.size();
             for (int i = 0; i < MT_DEG; ++i)
-                if (bit_of(jt.poly[k], i)) jt.idx.push_back((uint16_t)i);
-            while ((jt.idx.size() - jt.off[k]) % 16) jt.idx.push_back((uint16_t)MT_WIN);   // points at the zero padding
-            jt.cnt[k] = (int32_t)jt.idx.size() - jt.off[k];
+                if (bit_of(poly[k], i)) lists.push_back((uint16_t)i);
+            while ((lists.size() - off[k]) % 16) lists.push_back((uint16_t)MT_WIN);   // points at the zero padding
+            cnt[k] = (int32_t)lists.size() - off[k];
         }
+        jt.idx.resize((size_t)MT_HDR + lists.size());
+        memcpy(jt.idx.data(), off.data(), sizeof(int32_t) * MT_NPOLY);
+        memcpy(jt.idx.data() + 2 * MT_NPOLY, cnt.data(), sizeof(int32_t) * MT_NPOLY);
+        memcpy(jt.idx.data() + MT_HDR, lists.data(), sizeof(uint16_t) * lists.size());
         jt.ok = true;
     });
     return jt;
@@ -350,7 +386,7 @@ cudaError_t launch_mt19937_uniform(uint32_t* state_dev, int slot_in, int32_t pos
     *final_slot = slot_in;
     if (n < 1) return cudaSuccess;
     static bool attr_done = false;
-    const size_t smem = sizeof(uint32_t) * (MT_WIN_ALLOC + 4 * 768);
+    const size_t smem = sizeof(uint32_t) * (MT_WIN_ALLOC + 4 * 768) + sizeof(uint16_t) * MT_IDX_STAGE;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_mt19937_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -358,10 +394,6 @@ cudaError_t launch_mt19937_uniform(uint32_t* state_dev, int slot_in, int32_t pos
     }
     MtJumpArgs ja{};
     ja.idx = jump_idx_dev;
-    if (jump_idx_dev) {
-        const JumpTables& jt = jump_tables();
-        for (int k = 0; k < 3 * MT_DIGITS; ++k) { ja.off[k] = jt.off[k]; ja.cnt[k] = jt.cnt[k]; }
-    }
     int64_t left = 2 * n;                      // 32-bit words still to draw
     int64_t pos = pos_host;
     uint32_t* o = raw_dev;

@@ -214,13 +214,23 @@ def test_numpy_legacy_stream_on_device_is_bit_exact(mp):
         assert np.array_equal(got_next, ref_next)
 
 
+def test_numpy_legacy_stream_arbitrary_range(mp):
+    """low + (high - low) * r with NumPy's two roundings (product, then sum): a fused multiply-add differs in the last bit
+    unless the scale is a power of two."""
+    np.random.seed(31)
+    ref = np.random.uniform(0.1, 0.7, 200_001)
+    np.random.seed(31)
+    got = mp.numpy_stream_uniform(0.1, 0.7, 200_001)
+    assert np.array_equal(got, ref)
+
+
 def test_numpy_legacy_stream_jump_ahead_segments(mp):
-    """Draws longer than one segment (256 twists = 159,744 words) are generated by several CTAs that JUMP to their
-    segment through x^J mod phi; draws longer than one launch (256 segments) chain launches.  Same numbers, same
-    final state as NumPy, from fresh seeds (arbitrary low bits in key[0]), mid-block positions and pos = 624."""
-    cases = ((7, 0, [79_872, 79_873, 1, 400_001]),           # exactly one segment, then one word more
+    """Draws longer than one segment (1024 twists = 638,976 words = 319,488 draws) are generated by several CTAs that JUMP
+    to their segment through x^(s J) mod phi (one fold; a second one beyond 256 segments).  Same numbers, same final state
+    as NumPy, from fresh seeds (arbitrary low bits in key[0]), mid-block positions and pos = 624."""
+    cases = ((7, 0, [319_488, 319_489, 1, 400_001]),         # exactly one segment, then one word more
              (2024, 5, [3_000_001, 11, 2_500_000]),
-             (99, 0, [20_447_233 + 1000, 17]))                # crosses the 256-segment launch boundary
+             (99, 0, [81_788_929 + 1000, 17]))                # beyond segment 256: the second-digit polynomials
     for seed, skip, sizes in cases:
         np.random.seed(seed)
         np.random.uniform(size=skip)
