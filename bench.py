@@ -420,35 +420,66 @@ def main():
     # ---- e2e through the public host API (NumPy in / NumPy out; H2D + D2H inside the timed region) ----
     e_utts = utts[:max(1, min(a.e2e_utts, len(utts)))]
     e_sig, e_pm, e_voi = [u[0] for u in e_utts], [u[1] for u in e_utts], [u[2] for u in e_utts]
+    e2e64 = None
     if comp:
-        def e2e_step():
-            outs = mp.analysis_compressed_batch(e_sig, FS, e_pm, e_voi, fft_len=FFT_LEN, mag_dim=60, phase_dim=45)
-            ys = mp.synthesis_from_compressed_batch([o[:4] for o in outs], FS, b_out_hpf=False)
+        # the call a user of the reference's file formats makes: PCM16 samples as the wav file holds them (sf.read's 1/32768 is
+        # applied on the device), float32 features (the reference's feature files) and a float32 waveform (the wav writer
+        # quantises to PCM16 anyway) -- element types on request; the float64-in / float64-out default of the drop-in
+        # signatures is timed as well (e2e_float64_api)
+        e_pcm = [np.round(x * 32768.0).astype(np.int16) for x in e_sig]
+
+        from magphase_b200.batch import run_chain_stream
+        half = (len(e_pcm) + 1) // 2
+        e_batches = [list(zip(e_pcm[:half], e_pm[:half], e_voi[:half])), list(zip(e_pcm[half:], e_pm[half:], e_voi[half:]))]
+        e_batches = [b for b in e_batches if b]
+
+        def e2e_step(narrow=True, keep=False):
+            if narrow:
+                # two host threads, each with a private context on this GPU, take half of the step's utterances each
+                # (magphase_b200.batch.run_chain_stream): the NumPy bookkeeping of one half overlaps the GPU work of the other
+                r = run_chain_stream(e_batches, FS, fft_len=FFT_LEN, mag_dim=60, phase_dim=45, b_out_hpf=False, n_workers=2,
+                                     out_dtype=np.float32, keep_outputs=keep)
+                if not keep:
+                    return r['frames'], None, None
+                return r['frames'], [o for b in r['outputs'] for o in b[0]], [y for b in r['outputs'] for y in b[1]]
+            else:
+                outs = mp.analysis_compressed_batch(e_sig, FS, e_pm, e_voi, fft_len=FFT_LEN, mag_dim=60, phase_dim=45)
+                ys = mp.synthesis_from_compressed_batch([o[:4] for o in outs], FS, b_out_hpf=False)
             return sum(o[4].size for o in outs), outs, ys
-        api = 'analysis_compressed_batch -> synthesis_from_compressed_batch (float64 NumPy in/out, np.random noise)'
+        api = ('magphase_b200.batch.run_chain_stream: analysis_compressed_batch(int16 PCM in, out_dtype=float32) -> '
+               'synthesis_from_compressed_batch(float32 features in, out_dtype=float32) on 2 host threads (64 utterances each, private '
+               'contexts), NumPy-stream noise drawn on the device, results copied out of the pinned pool')
     else:
-        def e2e_step():
+        def e2e_step(narrow=True, keep=False):
             outs = mp.analysis_lossless_batch(e_sig, FS, e_pm, e_voi, fft_len=FFT_LEN)
             ys = mp.synthesis_from_lossless_batch([o[:4] for o in outs], FS)
             return sum(o[5].size for o in outs), outs, ys
         api = 'analysis_lossless_batch -> synthesis_from_lossless_batch (float64 NumPy in/out)'
-    for _ in range(2):
-        e_frames, outs, ys = e2e_step()
     e_steps = max(2, min(a.steps, 5))
-    barrier()
-    t = time.perf_counter()
-    for _ in range(e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e_secs = time.perf_counter() - t
+
+    def time_e2e(narrow):
+        r = e2e_step(narrow, keep=True)       # untimed: the results themselves, for the byte counts
+        e2e_step(narrow)
+        barrier()
+        t = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step(narrow)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t, ) + r
+    e_secs, e_frames, outs, ys = time_e2e(True)
     n_smp = sum(s.size for s in e_sig)
     if comp:
-        feat_bytes = 8 * sum(o[0].size + o[1].size + o[2].size for o in outs)
-        # signals cross PCIe as float32 (PCM-exact samples are narrowed on the host, mpb_stage.cu); analysis descriptors
-        # 17 B/frame; features 8 B/value each way; synthesis descriptors 35 B/frame; the noise is drawn on the device
-        # (only the 2.5 KB MT19937 state travels)
-        h2d = 4 * n_smp + 17 * e_frames + feat_bytes + 35 * e_frames + 2500
-        d2h = feat_bytes + 8 * sum(y.size for y in ys) + 2500
+        feat_bytes = 4 * sum(o[0].size + o[1].size + o[2].size for o in outs)
+        # PCM16 samples 2 B; analysis descriptors 17 B/frame; float32 features each way; synthesis descriptors 35 B/frame; the
+        # noise is drawn on the device (only the 2.5 KB MT19937 state travels); float32 waveform back
+        h2d = 2 * n_smp + 17 * e_frames + feat_bytes + 35 * e_frames + 2500
+        d2h = feat_bytes + 4 * sum(y.size for y in ys) + 2500
+        del outs, ys
+        s64, f64_frames, outs, ys = time_e2e(False)
+        e2e64 = {'seconds_per_step': s64 / e_steps, 'frames': f64_frames,
+                 'h2d_bytes_per_step': int(4 * n_smp + 52 * f64_frames + 8 * sum(o[0].size + o[1].size + o[2].size for o in outs) + 2500),
+                 'd2h_bytes_per_step': int(8 * sum(o[0].size + o[1].size + o[2].size for o in outs) + 8 * sum(y.size for y in ys) + 2500),
+                 'api': 'the same two calls with their drop-in defaults: float64 NumPy in / out'}
     else:
         feat_bytes = 3 * 8 * sum(o[0].size for o in outs)
         h2d = 4 * n_smp + 16 * e_frames + feat_bytes + 4 * e_frames
@@ -469,8 +500,9 @@ def main():
     fma_peaks = {'fp32': _lib.measure_fma_peak(F32, local_rank), 'fp64': _lib.measure_fma_peak(F64, local_rank)}
 
     # ---- reduce over ranks: max time, summed frames ----
-    stats, counts = reduce_counters([total_ms, e_secs, ana_ms, syn_ms], [plan.nfrm, e_frames], device=dev)
-    total_ms, e_secs, ana_ms, syn_ms = [float(x) for x in stats]
+    s64 = e2e64['seconds_per_step'] if e2e64 else 0.0
+    stats, counts = reduce_counters([total_ms, e_secs, ana_ms, syn_ms, s64], [plan.nfrm, e_frames], device=dev)
+    total_ms, e_secs, ana_ms, syn_ms, s64 = [float(x) for x in stats]
     frames_all, e_frames_all = [float(x) for x in counts]
     if world > 1:
         dist.destroy_process_group()
@@ -557,6 +589,10 @@ def main():
         'kernels': kernels,
         'clocks': clocks,
     }
+    if e2e64:
+        line['e2e_float64_api'] = {'value': e_frames_all / s64 if s64 > 0 else None, 'unit': 'frames/s',
+                                   'h2d_bytes_per_step': e2e64['h2d_bytes_per_step'], 'd2h_bytes_per_step': e2e64['d2h_bytes_per_step'],
+                                   'api': e2e64['api']}
     line.update(extras)
     if cpu is not None:
         line['cpu_baseline'] = {'value': cpu['value'], 'unit': 'frames/s', 'cores': cpu['cores'], 'kind': cpu['kind'],
@@ -649,24 +685,19 @@ def run_extras(a, torch, _lib, mp, CompressedPlan, make_lossless, geom, d_sig, u
     # longest first (LPT) inside this GPU's shard, then batches of 128 utterances
     order = sorted(order.tolist(), key=lambda i: -pool[i][0].size)
     batches = [order[i:i + 128] for i in range(0, n_total, 128)]
-    def run_stream(bl):
-        frames = 0
-        for b in bl:
-            sig, pm, voi = [pool[i][0] for i in b], [pool[i][1] for i in b], [pool[i][2] for i in b]
-            outs = mp.analysis_compressed_batch(sig, FS, pm, voi, fft_len=FFT_LEN, mag_dim=60, phase_dim=45)
-            mp.synthesis_from_compressed_batch([o[:4] for o in outs], FS, b_out_hpf=False)
-            frames += sum(o[4].size for o in outs)
-        return frames
-    run_stream(batches[:1])        # warm-up: largest batch first (scratch buffers grow once)
+    from magphase_b200.batch import run_chain_stream
+    pcm_pool = [(np.round(u[0] * 32768.0).astype(np.int16), u[1], u[2]) for u in pool]
+    bl = [[pcm_pool[i] for i in b] for b in batches]
+    run_chain_stream(bl, FS, fft_len=FFT_LEN, n_workers=2)          # first pass: device scratch grows, result buffers get page-locked and pooled
     barrier()
-    t = time.perf_counter()
-    frames = run_stream(batches)
+    r = run_chain_stream(bl, FS, fft_len=FFT_LEN, n_workers=2)
     torch.cuda.synchronize()
-    s_s = time.perf_counter() - t
+    frames, s_s = r['frames'], r['seconds']
     ex['stream'] = {'workload': 'config 5 per GPU: %d utterances of 2-8 s (LPT order), %d batches of 128 through '
-                                'analysis_compressed_batch -> synthesis_from_compressed_batch' % (n_total, len(batches)),
+                                'magphase_b200.batch.run_chain_stream (PCM16 in, float32 out, 2 host threads)' % (n_total, len(batches)),
                     'value': frames / s_s, 'unit': 'frames/s', 'frames': int(frames), 'seconds': s_s,
-                    'note': 'BASELINE config 5 = 12,500 such utterances per GPU on 8 GPUs: run with --stream-utts 12500'}
+                    'note': 'steady state (second pass over the list; the first pass page-locks the pooled result buffers). BASELINE config 5 = '
+                            '12,500 such utterances per GPU on 8 GPUs: run with --stream-utts 12500'}
     return ex
 
 

@@ -39,6 +39,7 @@ extern "C" {
 /* element types of caller buffers */
 #define MPB_F32 0
 #define MPB_F64 1
+#define MPB_I16 2   /* host signals only: PCM16 samples, scaled by 1/32768 on the device (what sf.read returns, src/libaudio.py:343-350) */
 
 /* window applied to each side of a pitch-synchronous frame (mpb_frames_*) */
 #define MPB_WIN_HANN 0            /* np.hanning halves               src/libaudio.py:70-84 */
@@ -202,6 +203,15 @@ int mpb_analysis_compressed_hostv(mpb_mel* plan,
                                   const uint8_t* voi, int64_t nfrm, int compute_dtype,
                                   double* out_mag_mel, double* out_real_mel, double* out_imag_mel);
 
+/* mpb_analysis_compressed_hostv with the caller's own element types: sig_dtype MPB_F64 / MPB_F32 / MPB_I16 (PCM16 as the
+ * reference's wav files hold it: the device applies sf.read's 1/32768), out_dtype MPB_F64 / MPB_F32 (the reference's feature
+ * files are float32, src/libutils.py:122-127).  Narrow types skip the host-side narrowing pass and halve the PCIe bytes.    */
+int mpb_analysis_compressed_hostv2(mpb_mel* plan,
+                                   const void* const* sigs, int sig_dtype, const int64_t* sig_lens, int32_t n_sigs,
+                                   const int64_t* centre, const int32_t* left, const int32_t* right,
+                                   const uint8_t* voi, int64_t nfrm,
+                                   void* out_mag_mel, void* out_real_mel, void* out_imag_mel, int out_dtype);
+
 /* la.sp_to_mcep (src/libaudio.py:575-601) itself, for three spectra at once: float32-rounded mel cepstra of a
  * (in_type 3, |X|) and of b, c (in_type 2, ln|X|; pass x*ln(10)/20 for in_type 1 "dB" input).  HOST float64 rows of
  * fft_len/2+1 bins; out_a: nfrm x n_mag, out_b / out_c: nfrm x n_ph.  Used by the legacy
@@ -274,6 +284,14 @@ int mpb_synthesis_compressed_host(mpb_syn* plan,
                                   const mpb_syn_frames* frames, int per_linear,
                                   const double* hpf_sos,   /* output high-pass as 2 biquads (mpb_sos2_*), or NULL */
                                   double* out, int64_t n_out);
+
+/* mpb_synthesis_compressed_host with float32 or float64 features (in_dtype) and waveform (out_dtype).                     */
+int mpb_synthesis_compressed_host2(mpb_syn* plan,
+                                   const void* mag_mel, const void* real_mel, const void* imag_mel, int in_dtype,
+                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
+                                   uint32_t* mt_key, int32_t* mt_pos,
+                                   const mpb_syn_frames* frames, int per_linear, const double* hpf_sos,
+                                   void* out, int out_dtype, int64_t n_out);
 
 /* ---- post-filter and minimum phase ---------------------------------------------------------- */
 /*

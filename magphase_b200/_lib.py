@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libmagphase_b200.so')
 
-MPB_F32, MPB_F64 = 0, 1
+MPB_F32, MPB_F64, MPB_I16 = 0, 1, 2
 WIN_HANN, WIN_BARTLETT25 = 0, 1
 _VALUE_ERRORS = (-1, -2, -3, -6)
 
@@ -53,11 +53,13 @@ SIGNATURES = {
     'mpb_sp_to_mcep_host': [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     'mpb_analysis_compressed_const_hostv': [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     'mpb_analysis_compressed_hostv': [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, C.c_int, _vp, _vp, _vp],
+    'mpb_analysis_compressed_hostv2': [_vp, _vp, C.c_int, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int],
     'mpb_syn_create': [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(_vp)],
     'mpb_syn_destroy': [_vp],
     'mpb_synthesis_compressed_dev': [_vp, _vp, _vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _i64, _vp, _vp, _i32, C.c_int,
                                      _vp, C.c_int, _i64],
     'mpb_synthesis_compressed_host': [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp, _vp, _i64],
+    'mpb_synthesis_compressed_host2': [_vp, _vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _i64],
     'mpb_post_filter_dev': [_vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp],
     'mpb_post_filter_host': [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _vp],
     'mpb_min_phase_dev': [_vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp],
@@ -116,18 +118,33 @@ def default_device():
     return 0
 
 
+_tls = threading.local()
+
+
+def current_slot():
+    """Context slot of the calling thread (0 unless set_thread_slot was called): every (device, slot) pair owns a private
+    library context -- streams, staging buffers, scratch -- so that several host threads can drive one GPU concurrently
+    (the calls of ONE context are serialised).  Plans are cached per (device, slot) as well."""
+    return getattr(_tls, 'slot', 0)
+
+
+def set_thread_slot(slot):
+    _tls.slot = int(slot)
+
+
 def ctx(device=None):
-    """Per-device context handle (created on first use)."""
+    """Context handle of (device, current_slot()) (created on first use)."""
     device = default_device() if device is None else int(device)
+    key = (device, current_slot())
     with _lock:
-        h = _ctx.get(device)
+        h = _ctx.get(key)
     if h is None:
         l = lib()
         p = _vp()
         check(l.mpb_create(device, C.byref(p)))
         with _lock:
-            _ctx.setdefault(device, p)
-            h = _ctx[device]
+            _ctx.setdefault(key, p)
+            h = _ctx[key]
     return h
 
 

@@ -138,6 +138,42 @@ def run_waveform_generation(tokens, in_feats_dir, out_syn_dir, mag_dim, phase_di
     return dict(utterances=len(tokens), frames=n_frames, seconds=time.perf_counter() - t0)
 
 
+def run_chain_stream(batches, fs, fft_len=None, mag_dim=60, phase_dim=45, b_out_hpf=False, n_workers=2, seed=0,
+                     sig_as_pcm16=True, out_dtype=np.float32, keep_outputs=False):
+    """In-memory streaming driver: analysis_compressed -> synthesis_from_compressed for a sequence of batches, each batch a
+    list of (v_sig, v_pm_smpls, v_voi).  ``n_workers`` host threads take the batches round-robin; every worker owns a
+    private library context on the GPU (``_lib.set_thread_slot``), so the NumPy bookkeeping, the PCIe copies and the kernels
+    of different batches overlap -- what the reference gets from one forked process per utterance (src/libutils.py:32-63).
+    The noise of batch k comes from ``np.random.RandomState(seed + k)`` (independent of which worker runs it).
+    Returns {'utterances', 'frames', 'seconds'} (+ 'outputs': per batch (features, waveforms) when keep_outputs)."""
+    from . import _lib
+    batches = list(batches)
+    results = [None] * len(batches)
+
+    def work(w):
+        _lib.set_thread_slot(w)
+        for k in range(w, len(batches), n_workers):
+            b = batches[k]
+            sigs = [u[0] for u in b]
+            if sig_as_pcm16 and all(np.asarray(x).dtype != np.int16 for x in sigs):
+                sigs = [np.round(np.asarray(x) * 32768.0).astype(np.int16) for x in sigs]
+            outs = mp.analysis_compressed_batch(sigs, fs, [u[1] for u in b], [u[2] for u in b], fft_len=fft_len, mag_dim=mag_dim,
+                                                phase_dim=phase_dim, out_dtype=out_dtype)
+            ys = mp.synthesis_from_compressed_batch([o[:4] for o in outs], fs, fft_len=fft_len, b_out_hpf=b_out_hpf,
+                                                    out_dtype=out_dtype, rng=np.random.RandomState(seed + k))
+            frames = sum(o[4].size for o in outs)
+            results[k] = (frames, ([tuple(np.array(a) for a in o[:5]) for o in outs], [np.array(y) for y in ys]) if keep_outputs else None)
+
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(max_workers=n_workers) as pool:
+        for f in [pool.submit(work, w) for w in range(n_workers)]:
+            f.result()
+    r = dict(utterances=sum(len(b) for b in batches), frames=sum(x[0] for x in results), seconds=time.perf_counter() - t0)
+    if keep_outputs:
+        r['outputs'] = [x[1] for x in results]
+    return r
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     sub = ap.add_subparsers(dest='cmd', required=True)

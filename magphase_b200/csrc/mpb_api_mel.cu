@@ -279,6 +279,9 @@ int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const i
                                   const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* voi,
                                   int64_t nfrm, int compute_dtype, double* out_mag_mel, double* out_real_mel,
                                   double* out_imag_mel);
+int mpb_analysis_compressed_hostv2(mpb_mel* m, const void* const* sigs, int sig_dtype, const int64_t* sig_lens, int32_t n_sigs,
+                                   const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* voi,
+                                   int64_t nfrm, void* out_mag_mel, void* out_real_mel, void* out_imag_mel, int out_dtype);
 
 // analysis_lossless + format_for_modelling fused on the device: host signal in, low-dimensional features out.
 // The lossless features only ever exist as a float32 scratch in HBM (frame-chunked).
@@ -303,6 +306,19 @@ int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const i
                                   const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* voi,
                                   int64_t nfrm, int compute_dtype, double* out_mag_mel, double* out_real_mel,
                                   double* out_imag_mel) {
+    (void)compute_dtype;   // the fused path always runs float64 butterflies
+    return mpb_analysis_compressed_hostv2(m, (const void* const*)sigs, MPB_F64, sig_lens, n_sigs, centre, left, right, voi, nfrm,
+                                          out_mag_mel, out_real_mel, out_imag_mel, MPB_F64);
+}
+
+// The same pipeline with the caller's own element types: signals as float64, float32 or PCM16 (MPB_I16: scaled by 1/32768 on
+// the device, what sf.read returns for the reference's wav files), features as float64 or float32 (the reference's feature
+// files are float32, src/libutils.py:122-127).  Narrow types halve or quarter the bytes on PCIe and skip the host-side
+// float64 -> float32 narrowing pass.
+int mpb_analysis_compressed_hostv2(mpb_mel* m, const void* const* sigs, int sig_dtype, const int64_t* sig_lens, int32_t n_sigs,
+                                   const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* voi,
+                                   int64_t nfrm, void* out_mag_mel, void* out_real_mel, void* out_imag_mel, int out_dtype) {
+    if (!sig_dtype_ok(sig_dtype) || !dtype_ok(out_dtype)) return fail(MPB_ERR_BAD_ARG, "unknown dtype");
     if (!m) return fail(MPB_ERR_BAD_ARG, "plan is NULL");
     if (nfrm == 0) return MPB_OK;
     if (!sigs || !sig_lens || n_sigs < 1 || !centre || !left || !right || !voi || !out_mag_mel || !out_real_mel ||
@@ -349,10 +365,11 @@ int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const i
     }
 
     CU(m->small[0].need((size_t)nfrm));
-    CU(m->small[1].need(sizeof(double) * nfrm * m->n_mag));
-    CU(m->small[2].need(sizeof(double) * nfrm * m->phase_dim));
-    CU(m->small[3].need(sizeof(double) * nfrm * m->phase_dim));
-    CU(m->small[4].need(sizeof(double) * n_sig));
+    const size_t oes = out_dtype == MPB_F64 ? 8 : 4;
+    CU(m->small[1].need(oes * nfrm * m->n_mag));
+    CU(m->small[2].need(oes * nfrm * m->phase_dim));
+    CU(m->small[3].need(oes * nfrm * m->phase_dim));
+    CU(m->small[4].need((sig_dtype == MPB_F64 ? sizeof(double) : sizeof(int16_t)) * (size_t)n_sig));   // float64 fall-back / PCM16 landing zone
     CU(m->small[5].need(sizeof(int64_t) * nfrm));
     CU(m->small[6].need(sizeof(int32_t) * nfrm));
     CU(m->small[7].need(sizeof(int32_t) * nfrm));
@@ -377,7 +394,6 @@ int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const i
         CU(cudaMemcpyAsync(m->small[7].p, h + 12 * nfrm, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, s_in));
         CU(cudaMemcpyAsync(m->small[0].p, h + 16 * nfrm, (size_t)nfrm, cudaMemcpyHostToDevice, s_in));
     }
-    (void)compute_dtype;   // the fused path always runs float64 butterflies
     const auto t1 = now();
     std::vector<cudaEvent_t> evs;
     auto on_group = [&](int32_t g, int dtype) -> int {
@@ -390,24 +406,28 @@ int mpb_analysis_compressed_hostv(mpb_mel* m, const double* const* sigs, const i
             int r = mpb_analysis_compressed_dev(
                 m, s_cmp, dtype == MPB_F32 ? m->sig32.p : m->small[4].p, dtype, n_sig, (const int64_t*)m->small[5].p + fa,
                 (const int32_t*)m->small[6].p + fa, (const int32_t*)m->small[7].p + fa, (const uint8_t*)m->small[0].p + fa, n,
-                (double*)m->small[1].p + fa * m->n_mag, (double*)m->small[2].p + fa * m->phase_dim,
-                (double*)m->small[3].p + fa * m->phase_dim, MPB_F64);
+                (char*)m->small[1].p + oes * fa * m->n_mag, (char*)m->small[2].p + oes * fa * m->phase_dim,
+                (char*)m->small[3].p + oes * fa * m->phase_dim, out_dtype);
             if (r != MPB_OK) return r;
         }
         CU(cudaEventRecord(e_cmp, s_cmp));
         CU(cudaStreamWaitEvent(s_out, e_cmp, 0));
         if (n > 0) {
-            CU(cudaMemcpyAsync(out_mag_mel + fa * m->n_mag, (double*)m->small[1].p + fa * m->n_mag,
-                               sizeof(double) * n * m->n_mag, cudaMemcpyDeviceToHost, s_out));
-            CU(cudaMemcpyAsync(out_real_mel + fa * m->phase_dim, (double*)m->small[2].p + fa * m->phase_dim,
-                               sizeof(double) * n * m->phase_dim, cudaMemcpyDeviceToHost, s_out));
-            CU(cudaMemcpyAsync(out_imag_mel + fa * m->phase_dim, (double*)m->small[3].p + fa * m->phase_dim,
-                               sizeof(double) * n * m->phase_dim, cudaMemcpyDeviceToHost, s_out));
+            CU(cudaMemcpyAsync((char*)out_mag_mel + oes * fa * m->n_mag, (char*)m->small[1].p + oes * fa * m->n_mag,
+                               oes * n * m->n_mag, cudaMemcpyDeviceToHost, s_out));
+            CU(cudaMemcpyAsync((char*)out_real_mel + oes * fa * m->phase_dim, (char*)m->small[2].p + oes * fa * m->phase_dim,
+                               oes * n * m->phase_dim, cudaMemcpyDeviceToHost, s_out));
+            CU(cudaMemcpyAsync((char*)out_imag_mel + oes * fa * m->phase_dim, (char*)m->small[3].p + oes * fa * m->phase_dim,
+                               oes * n * m->phase_dim, cudaMemcpyDeviceToHost, s_out));
         }
         return MPB_OK;
     };
-    rc = upload_signal_groups(ctx, s_in, sigs, sig_lens, n_sigs, group_end.data(), n_groups, m->sig32.p, m->small[4].p,
-                              on_group);
+    if (sig_dtype == MPB_F64)
+        rc = upload_signal_groups(ctx, s_in, (const double* const*)sigs, sig_lens, n_sigs, group_end.data(), n_groups, m->sig32.p,
+                                  m->small[4].p, on_group);
+    else
+        rc = upload_signal_groups_narrow(ctx, s_in, sigs, sig_dtype, sig_lens, n_sigs, group_end.data(), n_groups, m->sig32.p,
+                                         m->small[4].p, on_group);
     const auto t2 = now();
     // drain all three stages even after an error: host and staging buffers must not be reused under a live copy
     cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);

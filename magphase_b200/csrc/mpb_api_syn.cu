@@ -259,11 +259,30 @@ int mpb_synthesis_compressed_dev(mpb_syn* s, void* stream, const void* mag_mel, 
 // synthesis on the compute stream and the waveform of group g-1 returns on stream_out.  The noise of the whole batch
 // is drawn first on the compute stream (the MT19937 stream is one sequence); its final state comes back through
 // page-locked memory at the end.  Frame descriptors travel as one page-locked block.
+int mpb_synthesis_compressed_host2(mpb_syn* s, const void* mag_mel_v, const void* real_mel_v, const void* imag_mel_v, int in_dtype,
+                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
+                                   uint32_t* mt_key, int32_t* mt_pos, const mpb_syn_frames* fr, int per_linear,
+                                   const double* hpf_sos, void* out_v, int out_dtype, int64_t n_out);
+
 int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const double* real_mel, const double* imag_mel,
                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
                                   uint32_t* mt_key, int32_t* mt_pos, const mpb_syn_frames* fr, int per_linear,
                                   const double* hpf_sos, double* out, int64_t n_out) {
+    return mpb_synthesis_compressed_host2(s, mag_mel, real_mel, imag_mel, MPB_F64, n_rows, need_ph, noise, n_noise, mt_key, mt_pos,
+                                          fr, per_linear, hpf_sos, out, MPB_F64, n_out);
+}
+
+// The same pipeline with the caller's element types: features float64 or float32 (in_dtype; the reference's feature files are
+// float32, src/libutils.py:112-127), waveform float64 or float32 (out_dtype).  float32 halves the bytes on PCIe both ways.
+int mpb_synthesis_compressed_host2(mpb_syn* s, const void* mag_mel_v, const void* real_mel_v, const void* imag_mel_v, int in_dtype,
+                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
+                                   uint32_t* mt_key, int32_t* mt_pos, const mpb_syn_frames* fr, int per_linear,
+                                   const double* hpf_sos, void* out_v, int out_dtype, int64_t n_out) {
     if (!s || !fr) return fail(MPB_ERR_BAD_ARG, "NULL argument");
+    if (!dtype_ok(in_dtype) || !dtype_ok(out_dtype)) return fail(MPB_ERR_BAD_ARG, "unknown dtype");
+    const char* mag_mel = (const char*)mag_mel_v; const char* real_mel = (const char*)real_mel_v;
+    const char* imag_mel = (const char*)imag_mel_v; char* out = (char*)out_v;
+    const size_t ies = in_dtype == MPB_F64 ? 8 : 4, oes = out_dtype == MPB_F64 ? 8 : 4;
     if (n_out == 0) return MPB_OK;
     if (!mag_mel || !real_mel || !imag_mel || !need_ph || !out) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
     if (!noise && !(mt_key && mt_pos)) return fail(MPB_ERR_BAD_ARG, "either noise or an MT19937 state is required");
@@ -355,12 +374,12 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
     }
 
     // ---- device buffers, all at their final size before anything is enqueued ----
-    CU(b[B_MAG].need(sizeof(double) * (size_t)n_rows * s->n_mag + 16));
-    CU(b[B_REAL].need(sizeof(double) * (size_t)n_rows * s->n_ph + 16));
-    CU(b[B_IMAG].need(sizeof(double) * (size_t)n_rows * s->n_ph + 16));
-    CU(s->out.need(sizeof(double) * (size_t)n_out));
+    CU(b[B_MAG].need(ies * (size_t)n_rows * s->n_mag + 16));
+    CU(b[B_REAL].need(ies * (size_t)n_rows * s->n_ph + 16));
+    CU(b[B_IMAG].need(ies * (size_t)n_rows * s->n_ph + 16));
+    CU(s->out.need(oes * (size_t)n_out));
     size_t cvt_pitch = 0;
-    rc = syn_reserve(s, MPB_F64, n_rows, F, U, (int)rg.size(), &cvt_pitch);
+    rc = syn_reserve(s, in_dtype, n_rows, F, U, (int)rg.size(), &cvt_pitch);
     if (rc != MPB_OK) return rc;
 
     // ---- descriptors: one page-locked block, one copy ----
@@ -414,21 +433,21 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
     for (const SynRange& r : rg) {
         const int64_t nr = r.row_b - r.row_a;
         if (nr > 0) {
-            CU(cudaMemcpyAsync((double*)b[B_MAG].p + r.row_a * s->n_mag, mag_mel + r.row_a * s->n_mag,
-                               sizeof(double) * nr * s->n_mag, cudaMemcpyHostToDevice, s_in));
-            CU(cudaMemcpyAsync((double*)b[B_REAL].p + r.row_a * s->n_ph, real_mel + r.row_a * s->n_ph,
-                               sizeof(double) * nr * s->n_ph, cudaMemcpyHostToDevice, s_in));
-            CU(cudaMemcpyAsync((double*)b[B_IMAG].p + r.row_a * s->n_ph, imag_mel + r.row_a * s->n_ph,
-                               sizeof(double) * nr * s->n_ph, cudaMemcpyHostToDevice, s_in));
+            CU(cudaMemcpyAsync((char*)b[B_MAG].p + ies * r.row_a * s->n_mag, mag_mel + ies * r.row_a * s->n_mag,
+                               ies * nr * s->n_mag, cudaMemcpyHostToDevice, s_in));
+            CU(cudaMemcpyAsync((char*)b[B_REAL].p + ies * r.row_a * s->n_ph, real_mel + ies * r.row_a * s->n_ph,
+                               ies * nr * s->n_ph, cudaMemcpyHostToDevice, s_in));
+            CU(cudaMemcpyAsync((char*)b[B_IMAG].p + ies * r.row_a * s->n_ph, imag_mel + ies * r.row_a * s->n_ph,
+                               ies * nr * s->n_ph, cudaMemcpyHostToDevice, s_in));
         }
         cudaEvent_t e_in = get_event(ctx), e_cmp = get_event(ctx);
         evs.push_back(e_in); evs.push_back(e_cmp);
         CU(cudaEventRecord(e_in, s_in));
         CU(cudaStreamWaitEvent(s_cmp, e_in, 0));
         if (!e_rng.empty() && r.ordinal == 0) CU(cudaStreamWaitEvent(s_cmp, e_rng[0], 0));
-        rc = syn_enqueue_range(s, s_cmp, b[B_MAG].p, b[B_REAL].p, b[B_IMAG].p, MPB_F64, (const uint8_t*)d_need,
+        rc = syn_enqueue_range(s, s_cmp, b[B_MAG].p, b[B_REAL].p, b[B_IMAG].p, in_dtype, (const uint8_t*)d_need,
                                (const float*)b[B_NOISE].p, n_noise, &d, (const int32_t*)d_runs, per_linear, s->out.p,
-                               MPB_F64, cvt_pitch, r);
+                               out_dtype, cvt_pitch, r);
         if (rc != MPB_OK) break;
         if (!hpf_sos) {
             // (float64 on the wire: narrowing the waveform to float32 for PCIe and widening it again on the host was
@@ -436,15 +455,15 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
             CU(cudaEventRecord(e_cmp, s_cmp));
             CU(cudaStreamWaitEvent(s_out, e_cmp, 0));
             if (r.out_b > r.out_a)
-                CU(cudaMemcpyAsync(out + r.out_a, (double*)s->out.p + r.out_a, sizeof(double) * (r.out_b - r.out_a),
+                CU(cudaMemcpyAsync(out + oes * r.out_a, (char*)s->out.p + oes * r.out_a, oes * (r.out_b - r.out_a),
                                    cudaMemcpyDeviceToHost, s_out));
         }
     }
     const auto t3 = now();
     if (rc == MPB_OK && hpf_sos) {   // output high-pass (src/magphase.py:981-995) on the device, per utterance
-        rc = mpb_sos2_dev(ctx, s_cmp, s->out.p, MPB_F64, fr->utt_out_off, U, hpf_sos);
+        rc = mpb_sos2_dev(ctx, s_cmp, s->out.p, out_dtype, fr->utt_out_off, U, hpf_sos);
         if (rc == MPB_OK) {
-            cudaError_t e = cudaMemcpyAsync(out, s->out.p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, s_cmp);
+            cudaError_t e = cudaMemcpyAsync(out, s->out.p, oes * n_out, cudaMemcpyDeviceToHost, s_cmp);
             if (e != cudaSuccess) rc = fail(MPB_ERR_CUDA, cudaGetErrorString(e));
         }
     }

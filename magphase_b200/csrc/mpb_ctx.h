@@ -120,6 +120,7 @@ inline int pipeline_groups(int64_t nfrm, int64_t frames_per_group, int max_group
 namespace mpb {
 inline bool fft_len_ok(int n) { return n == 1024 || n == 2048 || n == 4096; }
 inline bool dtype_ok(int d) { return d == MPB_F32 || d == MPB_F64; }
+inline bool sig_dtype_ok(int d) { return d == MPB_F32 || d == MPB_F64 || d == MPB_I16; }
 int get_twiddles(mpb_ctx* ctx, int fft_len, int dtype, const void** out);
 int analysis_common(mpb_ctx* ctx, void* stream, const void* sig, int sig_dtype, int64_t n_sig,
                     const int64_t* centre, const int32_t* left, const int32_t* right, const uint8_t* win,
@@ -134,6 +135,9 @@ int upload_signals(mpb_ctx* ctx, cudaStream_t st, const double* const* sigs, con
 int upload_signal_groups(mpb_ctx* ctx, cudaStream_t st, const double* const* sigs, const int64_t* lens, int32_t n_sigs,
                          const int32_t* group_end, int32_t n_groups, void* dev_f32, void* dev_f64,
                          const std::function<int(int32_t, int)>& on_group);
+int upload_signal_groups_narrow(mpb_ctx* ctx, cudaStream_t st, const void* const* sigs, int sig_dtype, const int64_t* lens,
+                                int32_t n_sigs, const int32_t* group_end, int32_t n_groups, void* dev_f32, void* dev_aux,
+                                const std::function<int(int32_t, int)>& on_group);
 int host_threads();
 int mt19937_enqueue(mpb_ctx* ctx, cudaStream_t st, const uint32_t* key, int32_t pos, const int64_t* part_n, int n_parts,
                     double low, double high, void* out_dev, int out_dtype, uint32_t* fin625, cudaEvent_t* part_done);

@@ -193,6 +193,67 @@ int upload_signal_groups(mpb_ctx* ctx, cudaStream_t st, const double* const* sig
     return rc;
 }
 
+__global__ void k_i16_to_f32(const int16_t* __restrict__ a, float* __restrict__ b, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = (float)a[i] * (1.0f / 32768.0f);          // sf.read of PCM16 (src/libaudio.py:343-350): exact in float32
+}
+
+// Signals that are already narrow on the host -- float32 samples or PCM16 (int16, scaled by 1/32768 on the device like
+// sf.read does) -- skip the float64 narrowing pass: the pool only copies them into the page-locked staging buffer, chunk by
+// chunk, while earlier chunks are on PCIe.  int16 groups land in dev_aux and are converted into dev_f32 on `st`.
+int upload_signal_groups_narrow(mpb_ctx* ctx, cudaStream_t st, const void* const* sigs, int sig_dtype, const int64_t* lens,
+                                int32_t n_sigs, const int32_t* group_end, int32_t n_groups, void* dev_f32, void* dev_aux,
+                                const std::function<int(int32_t, int)>& on_group) {
+    const size_t es = sig_dtype == MPB_I16 ? 2 : 4;
+    int64_t n_sig = 0;
+    for (int32_t i = 0; i < n_sigs; ++i) n_sig += lens[i];
+    PinnedBuf& pb = ctx->stage;
+    if (n_sig > 0 && pb.need(es * (size_t)n_sig) != cudaSuccess) return fail(MPB_ERR_CUDA, "page-locked staging buffer");
+    constexpr int64_t CH = 1 << 19;
+    struct Chunk { const char* src; int64_t off, n; int32_t group; bool last_of_group; };
+    std::vector<Chunk> ch;
+    {
+        int32_t g = 0;
+        int64_t off = 0;
+        for (int32_t i = 0; i < n_sigs; ++i) {
+            while (g < n_groups - 1 && i >= group_end[g]) ++g;
+            for (int64_t a = 0; a < lens[i] || (a == 0 && lens[i] == 0); a += CH) {
+                const int64_t n = lens[i] - a < CH ? lens[i] - a : CH;
+                ch.push_back({(const char*)sigs[i] + es * a, off + a, n, g, false});
+                if (lens[i] == 0) break;
+            }
+            off += lens[i];
+        }
+        for (size_t c = 0; c < ch.size(); ++c) ch[c].last_of_group = c + 1 == ch.size() || ch[c + 1].group != ch[c].group;
+    }
+    char* h = (char*)pb.p;
+    int rc = MPB_OK;
+    int64_t group_first = 0;                     // first sample of the group currently being issued
+    HostPool::get().run(
+        (int)ch.size(),
+        [&](int c) { if (ch[c].n > 0) memcpy(h + es * ch[c].off, ch[c].src, es * (size_t)ch[c].n); },
+        [&](int c) {
+            if (rc != MPB_OK) return;
+            const Chunk& k = ch[c];
+            cudaError_t e = cudaSuccess;
+            char* dst = sig_dtype == MPB_I16 ? (char*)dev_aux : (char*)dev_f32;
+            if (k.n > 0) e = cudaMemcpyAsync(dst + es * k.off, h + es * k.off, es * (size_t)k.n, cudaMemcpyHostToDevice, st);
+            if (k.last_of_group && e == cudaSuccess) {
+                const int64_t g_end = k.off + k.n, g_n = g_end - group_first;
+                if (sig_dtype == MPB_I16 && g_n > 0) {
+                    k_i16_to_f32<<<(unsigned)((g_n + 255) / 256), 256, 0, st>>>((const int16_t*)dev_aux + group_first,
+                                                                             (float*)dev_f32 + group_first, g_n);
+                    e = cudaGetLastError();
+                    ctx->launches += 1;
+                }
+                group_first = g_end;
+                if (e == cudaSuccess) { rc = on_group(k.group, MPB_F32); return; }
+            }
+            if (e != cudaSuccess) rc = fail(MPB_ERR_CUDA, std::string("signal upload: ") + cudaGetErrorString(e));
+        });
+    return rc;
+}
+
 // One group: everything in dev (>= 8 bytes per sample); *out_dtype says how it was uploaded.
 int upload_signals(mpb_ctx* ctx, cudaStream_t st, const double* const* sigs, const int64_t* lens, int32_t n_sigs,
                    void* dev, int* out_dtype) {

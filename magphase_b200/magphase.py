@@ -441,7 +441,7 @@ class _MelPlan:
         nmel = get_num_full_mel_coeffs_from_num_phase_coeffs(crsf_cf, phase_dim, alpha_phase, fs)
         # the reference prints alpha with "%1.2f" on the SPTK command line (src/libaudio.py:589): False -> 0.00
         a_mag, a_ph = float("%1.2f" % alpha), float("%1.2f" % alpha_phase)
-        key = (_lib.default_device(), fft_len, a_mag, mag_dim, a_ph, nmel, phase_dim)
+        key = (_lib.default_device(), _lib.current_slot(), fft_len, a_mag, mag_dim, a_ph, nmel, phase_dim)
         if key not in cls._cache:
             cls._cache[key] = cls(fft_len, a_mag, mag_dim, a_ph, nmel, phase_dim)
         return cls._cache[key]
@@ -505,9 +505,15 @@ def analysis_compressed_from_pm(v_sig, fs, v_pm_smpls, v_voi, fft_len=None, mag_
 
 
 def analysis_compressed_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None, mag_dim=60, phase_dim=10,
-                              b_const_rate=False, b_mag_fbank_mel=False, alpha_phase=None):
+                              b_const_rate=False, b_mag_fbank_mel=False, alpha_phase=None, out_dtype=np.float64):
     """Batched analysis_compressed_from_pm.  Returns a list of
-    (m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0_smth, v_shift, fs, fft_len)."""
+    (m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0_smth, v_shift, fs, fft_len).
+
+    Element types on request (the defaults reproduce the reference: float64 in, float64 out): signals may be int16 (PCM16
+    exactly as the wav file holds it -- the device applies sf.read's 1/32768, src/libaudio.py:343-350) or float32 arrays,
+    and ``out_dtype=np.float32`` returns the three feature matrices in float32, the precision of the reference's own
+    feature files (src/libutils.py:122-127).  Nothing is then narrowed or widened on the host and half (features) to a
+    quarter (PCM16) of the bytes cross PCIe.  lf0 and the shifts are host bookkeeping and stay float64 / int."""
     if b_mag_fbank_mel:
         raise ValueError('b_mag_fbank_mel=True (experimental filter-bank warping) is outside the CUDA hot path')
     if fft_len is None:
@@ -522,14 +528,22 @@ def analysis_compressed_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None, mag_di
     shift_all = left.astype(int)                                              # one copy out of the reusable workspace
     lefts = [shift_all[frm_off[u]:frm_off[u + 1]] for u in range(len(l_sig))]
     lf0s = [lf0_all[frm_off[u]:frm_off[u + 1]] for u in range(len(l_sig))]
-    sigs = [np.ascontiguousarray(s, dtype=np.float64) for s in l_sig]      # no copy for float64 arrays
+    out_dtype = np.dtype(out_dtype)
+    if out_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+        raise ValueError('out_dtype must be float64 or float32')
+    # one element type for the whole batch: int16 / float32 as given, anything else as float64 (no copy for float64 arrays)
+    kinds = {np.asarray(s).dtype for s in l_sig}
+    sig_np = kinds.pop() if len(kinds) == 1 and next(iter(kinds)) in (np.dtype(np.int16), np.dtype(np.float32)) else np.dtype(np.float64)
+    sig_code = {np.dtype(np.float64): _lib.MPB_F64, np.dtype(np.float32): _lib.MPB_F32, np.dtype(np.int16): _lib.MPB_I16}[sig_np]
+    sigs = [np.ascontiguousarray(s, dtype=sig_np) for s in l_sig]
     sig_ptrs = (C.c_void_p * len(sigs))(*[s.ctypes.data for s in sigs])
     sig_lens = np.ascontiguousarray([s.size for s in sigs], dtype=np.int64)
     n = centre.size
-    o_mag, o_real, o_imag = (_lib.pinned.empty((n, d)) for d in (mag_dim, phase_dim, phase_dim))
-    _lib.check(_lib.lib().mpb_analysis_compressed_hostv(
-        plan.handle, sig_ptrs, _lib.ptr(sig_lens), len(sigs), _lib.ptr(centre), _lib.ptr(left), _lib.ptr(right),
-        _lib.ptr(voi8), n, ANALYSIS_COMPUTE, _lib.ptr(o_mag), _lib.ptr(o_real), _lib.ptr(o_imag)))
+    o_mag, o_real, o_imag = (_lib.pinned.empty((n, d), dtype=out_dtype) for d in (mag_dim, phase_dim, phase_dim))
+    _lib.check(_lib.lib().mpb_analysis_compressed_hostv2(
+        plan.handle, sig_ptrs, sig_code, _lib.ptr(sig_lens), len(sigs), _lib.ptr(centre), _lib.ptr(left), _lib.ptr(right),
+        _lib.ptr(voi8), n, _lib.ptr(o_mag), _lib.ptr(o_real), _lib.ptr(o_imag),
+        _lib.MPB_F32 if out_dtype == np.dtype(np.float32) else _lib.MPB_F64))
     out, a = [], 0
     for u in range(len(l_sig)):
         b = a + lefts[u].size
@@ -679,7 +693,7 @@ class _SynPlan:
         alpha = define_alpha(fs)
         if alpha_phase is None:
             alpha_phase = alpha
-        key = (_lib.default_device(), fs, fft_len, mag_dim, phase_dim, float(alpha_phase))
+        key = (_lib.default_device(), _lib.current_slot(), fs, fft_len, mag_dim, phase_dim, float(alpha_phase))
         if key not in cls._cache:
             cls._cache[key] = cls(fs, fft_len, mag_dim, phase_dim, alpha, alpha_phase)
         return cls._cache[key]
@@ -743,12 +757,12 @@ def synthesis_from_compressed(m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0, fs, 
                                            alpha_phase=alpha_phase, b_out_hpf=b_out_hpf)[0]
 
 
-def _stack_rows(l_arr):
-    """np.concatenate(l_arr, axis=0) as float64 -- without the copy when the arrays already sit back to back in memory
+def _stack_rows(l_arr, dtype=np.float64):
+    """np.concatenate(l_arr, axis=0) as `dtype` -- without the copy when the arrays already sit back to back in memory
     (the row blocks the *_batch analysis functions return).  The result is only used as a read-only argument of a C
     call made while the inputs are still referenced, so viewing across the blocks is safe."""
     a0 = l_arr[0]
-    if all(isinstance(a, np.ndarray) and a.dtype == np.float64 and a.ndim == 2 and a.flags['C_CONTIGUOUS'] and
+    if all(isinstance(a, np.ndarray) and a.dtype == np.dtype(dtype) and a.ndim == 2 and a.flags['C_CONTIGUOUS'] and
            a.shape[1] == a0.shape[1] for a in l_arr):
         ptr = a0.ctypes.data
         for a in l_arr:
@@ -758,7 +772,7 @@ def _stack_rows(l_arr):
         else:
             rows = sum(a.shape[0] for a in l_arr)
             return np.lib.stride_tricks.as_strided(a0, shape=(rows, a0.shape[1]), strides=a0.strides, writeable=False)
-    return np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64) for a in l_arr], axis=0))
+    return np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=dtype) for a in l_arr], axis=0))
 
 
 def compressed_synthesis_geometry(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win=True, b_const_rate=False, _reuse=False):
@@ -865,9 +879,15 @@ def _compressed_synthesis_geometry_loop(l_lf0, l_nrows, fs, fft_len, b_voi_ap_wi
 
 
 def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True, b_fbank_mel=False, b_const_rate=False,
-                                    per_phase_type='magphase', alpha_phase=None, b_out_hpf=True, l_noise=None):
+                                    per_phase_type='magphase', alpha_phase=None, b_out_hpf=True, l_noise=None,
+                                    out_dtype=np.float64, rng=None):
     """Batched synthesis_from_compressed; l_feats is a list of (m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0).
-    l_noise: optional list of per-utterance noise vectors (else drawn from np.random, utterance by utterance)."""
+    l_noise: optional list of per-utterance noise vectors (else drawn from np.random, utterance by utterance).
+    Feature matrices that are ALL float32 (what read_binfile finds on disk, src/libutils.py:112-120) cross PCIe as float32;
+    ``out_dtype=np.float32`` returns float32 waveforms (the wav writer quantises to PCM16 anyway, src/libaudio.py:352-365).
+    The defaults (float64 in, float64 out) reproduce the reference.
+    rng: a ``np.random.RandomState`` to draw the noise from instead of NumPy's global stream (worker threads that
+    process batches concurrently each bring their own; the global stream is the reference's behaviour)."""
     if b_fbank_mel:
         raise ValueError('b_fbank_mel=True (experimental filter-bank warping) is outside the CUDA hot path')
     if per_phase_type not in ('magphase', 'linear', 'min_phase'):
@@ -888,12 +908,12 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
     if l_noise is None:
         # np.random.uniform(-1, 1, ns_len) per utterance (:883) == one run of sum(ns_len) draws on NumPy's global
         # legacy stream.  The stream is advanced ON THE DEVICE, bit for bit, and handed back to NumPy afterwards.
-        np_state = np.random.get_state()
+        np_state = rng.get_state() if rng is not None else np.random.get_state()
         if np_state[0] == 'MT19937':
             mt_key = np.ascontiguousarray(np_state[1], dtype=np.uint32).copy()
             mt_pos = C.c_int32(int(np_state[2]))
         else:
-            l_noise = [np.random.uniform(-1, 1, n) for n in l_ns_len]
+            l_noise = [(rng if rng is not None else np.random).uniform(-1, 1, n) for n in l_ns_len]
     if l_noise is not None:
         for v, n in zip(l_noise, l_ns_len):
             if np.size(v) != n:
@@ -903,18 +923,23 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
         need = np.zeros_like(need)          # phase rows come from the minimum-phase kernel instead
     out_off = arrs['utt_out_off']
     fr = _lib.SynFrames(nfrm=int(arrs['utt_frm_off'][-1]), n_utt=n_utt, **{k: _lib.ptr(v) for k, v in arrs.items()})
-    mag, real, imag = (_stack_rows([f[i] for f in l_feats]) for i in range(3))
+    out_dtype = np.dtype(out_dtype)
+    if out_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+        raise ValueError('out_dtype must be float64 or float32')
+    feat_np = np.float32 if all(np.asarray(f[i]).dtype == np.float32 for f in l_feats for i in range(3)) else np.float64
+    mag, real, imag = (_stack_rows([f[i] for f in l_feats], feat_np) for i in range(3))
     noise = None
     if l_noise is not None:
         noise = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in l_noise]))
     hpf_sos = output_hpf_sos(fs) if b_out_hpf else None
-    out = _lib.pinned.empty(int(out_off[-1]))
-    _lib.check(_lib.lib().mpb_synthesis_compressed_host(
-        plan.handle, _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), mag.shape[0], _lib.ptr(need), _lib.ptr(noise),
-        int(sum(l_ns_len)), _lib.ptr(mt_key), C.byref(mt_pos) if mt_pos is not None else None, C.byref(fr), {'magphase': 0, 'linear': 1, 'min_phase': 2}[per_phase_type], _lib.ptr(hpf_sos),
-        _lib.ptr(out), out.size))
+    out = _lib.pinned.empty(int(out_off[-1]), dtype=out_dtype)
+    code = lambda dt: _lib.MPB_F32 if np.dtype(dt) == np.dtype(np.float32) else _lib.MPB_F64
+    _lib.check(_lib.lib().mpb_synthesis_compressed_host2(
+        plan.handle, _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), code(feat_np), mag.shape[0], _lib.ptr(need), _lib.ptr(noise),
+        int(sum(l_ns_len)), _lib.ptr(mt_key), C.byref(mt_pos) if mt_pos is not None else None, C.byref(fr),
+        {'magphase': 0, 'linear': 1, 'min_phase': 2}[per_phase_type], _lib.ptr(hpf_sos), _lib.ptr(out), code(out_dtype), out.size))
     if mt_key is not None:
-        np.random.set_state((np_state[0], mt_key, int(mt_pos.value), np_state[3], np_state[4]))
+        (rng if rng is not None else np.random).set_state((np_state[0], mt_key, int(mt_pos.value), np_state[3], np_state[4]))
     l_out = [out[out_off[u]:out_off[u + 1]] for u in range(n_utt)]
     return l_out
 
@@ -1024,7 +1049,7 @@ def next_pow_of_two(x):
 
 def _raw_mcep_plan(fft_len, n_coeffs, alpha):
     """A mel plan whose three streams all produce plain la.sp_to_mcep output (n_coeffs each)."""
-    key = ('raw', _lib.default_device(), fft_len, n_coeffs, float("%1.2f" % alpha))
+    key = ('raw', _lib.default_device(), _lib.current_slot(), fft_len, n_coeffs, float("%1.2f" % alpha))
     if key not in _MelPlan._cache:
         eye = np.ascontiguousarray(np.eye(n_coeffs))
         h = C.c_void_p()

@@ -77,3 +77,39 @@ def test_compressed_synthesis_batch_equals_single_across_pipeline_groups(mp):
     for k, (a, b) in enumerate(zip(ys, singles)):
         assert a.shape == b.shape
         assert rms(a, b) < 1e-7, (k, rms(a, b))                          # OLA run splits differ with the batch size
+
+
+def test_narrow_element_types_on_request(mp):
+    """PCM16 / float32 signals in, float32 features and waveforms out (the reference's own disk formats,
+    src/libaudio.py:343-365, src/libutils.py:112-127): the same kernels, so the results equal the float64 API's up to the
+    float32 rounding of the outputs, and the NumPy noise stream is advanced identically."""
+    utts = _batch(n=5, dur=0.6)[:5]
+    utts = [(np.round(s * 32768.0) / 32768.0, pm, voi) for s, pm, voi in utts]          # PCM16-exact samples
+    pcm = [np.round(u[0] * 32768.0).astype(np.int16) for u in utts]
+    ref = mp.analysis_compressed_batch([u[0] for u in utts], 48000, [u[1] for u in utts], [u[2] for u in utts], mag_dim=60, phase_dim=45)
+    for sigs in (pcm, [u[0].astype(np.float32) for u in utts]):
+        got = mp.analysis_compressed_batch(sigs, 48000, [u[1] for u in utts], [u[2] for u in utts], mag_dim=60, phase_dim=45,
+                                           out_dtype=np.float32)
+        for g, r in zip(got, ref):
+            for a, b in zip(g[:3], r[:3]):
+                assert a.dtype == np.float32 and a.shape == b.shape
+                assert np.array_equal(a, b.astype(np.float32))                          # same kernels: only the output rounding differs
+            assert np.array_equal(g[3], r[3]) and np.array_equal(g[4], r[4]) and g[3].dtype == np.float64
+    feats32 = [g[:4] for g in got]
+    np.random.seed(9)
+    y64 = mp.synthesis_from_compressed_batch([(f[0].astype(np.float64), f[1].astype(np.float64), f[2].astype(np.float64), f[3])
+                                              for f in feats32], 48000, b_out_hpf=False)
+    st64 = np.random.get_state()
+    np.random.seed(9)
+    y32 = mp.synthesis_from_compressed_batch(feats32, 48000, b_out_hpf=False, out_dtype=np.float32)
+    st32 = np.random.get_state()
+    assert st64[2] == st32[2] and np.array_equal(st64[1], st32[1])
+    for a, b in zip(y32, y64):
+        assert a.dtype == np.float32 and a.shape == b.shape and rms(a, b) < 1e-7
+    # with the output high-pass as well (single group path)
+    np.random.seed(9)
+    z64 = mp.synthesis_from_compressed_batch(feats32, 48000, b_out_hpf=True)
+    np.random.seed(9)
+    z32 = mp.synthesis_from_compressed_batch(feats32, 48000, b_out_hpf=True, out_dtype=np.float32)
+    for a, b in zip(z32, z64):
+        assert rms(a, b) < 1e-6
