@@ -116,15 +116,44 @@ __device__ __forceinline__ void normalise_to_f32(float x, float y, float& mag, f
 //   b[k]   = sig[c+k] * w(k, q)   k = 0..q_eff       truncation branch src/magphase.py:313-315)
 // Only the l + q_eff + 1 non-zero samples are touched (~18 % of N for speech); everything else is known
 // to be zero from the frame geometry and never goes through shared memory.
+// 1 / s for an integer side length s >= 1 in float64: float32 reciprocal refined by two Newton steps (four DFMA instead of
+// the ~40 instructions of an IEEE division; within one ulp of it, far inside every tolerance of the path)
+__device__ __forceinline__ double recip_len(int s) {
+    const double d = (double)s;
+    double r = (double)__frcp_rn((float)s);
+    r = fma(r, fma(-d, r, 1.0), r);
+    r = fma(r, fma(-d, r, 1.0), r);
+    return r;
+}
+
 template <typename T, typename TS, int N>
 __device__ __forceinline__ void load_frame(const TS* __restrict__ sig, int64_t n_sig, int64_t c, int l, int q, int kind,
-                                           cx<T>* __restrict__ buf, cx<T>* v, int t) {
+                                           cx<T>* __restrict__ buf, cx<T>* v, int t, bool ends_only = false) {
     using G = FftGeom<T, N>;
+    const double inv_l = l > 0 ? recip_len(l) : 0.0, inv_q = q > 0 ? recip_len(q) : 0.0;
+    if (ends_only) {
+        // l <= 2 S1 and q < 2 S1 (uniform over the CTA; most speech frames): only z[t] (b[2t], b[2t+1], right part) and
+        // z[M - S1 + t] (b[N - 2 S1 + 2t], +1, left part) can be non-zero -- this thread's own first and last butterfly
+        // input.  Straight from global memory into registers: no staging, no barrier, no index search.
+        auto right_part = [&](int k) -> T {                       // b[k] = sig[c + k] w(k, q), k <= q
+            const int64_t i = c + k;
+            return (k <= q && i >= 0 && i < n_sig) ? (T)sig[i] * side_window<T>(k, inv_q, kind) : (T)0;
+        };
+        auto left_part = [&](int j) -> T {                        // b[N - j] = sig[c - j] w(j, l), 1 <= j <= l
+            const int64_t i = c - j;
+            return (j >= 1 && j <= l && i >= 0 && i < n_sig) ? (T)sig[i] * side_window<T>(j, inv_l, kind) : (T)0;
+        };
+        const int j0 = 2 * G::S1 - 2 * t;                         // b[N - 2 S1 + 2t] is j = 2 S1 - 2t; the next sample j - 1
+#pragma unroll
+        for (int n1 = 1; n1 < 15; ++n1) v[n1] = mk<T>((T)0, (T)0);
+        v[0] = mk<T>(right_part(2 * t), right_part(2 * t + 1));
+        v[15] = mk<T>(left_part(j0), left_part(j0 - 1));
+        return;
+    }
     T* bufT = reinterpret_cast<T*>(buf);
     // l >= N (pitch period longer than the FFT): the reference keeps the first N samples of the frame and its
     // hstack((v[l:], v[:l])) rotation degenerates to the identity -> b[k] = sig[c-l+k] * w(l-k, l)
     const bool whole = l >= N;
-    const double inv_l = l > 0 ? 1.0 / (double)l : 0.0, inv_q = q > 0 ? 1.0 / (double)q : 0.0;
     const int q_eff = whole ? -1 : min(q, N - l - 1);
     const int total = whole ? N : l + q_eff + 1;
     for (int idx = t; idx < total; idx += G::TPB) {
