@@ -304,6 +304,13 @@ int mpb_post_filter_dev(mpb_ctx* ctx, void* stream, const void* x, int dtype, in
 int mpb_post_filter_host(mpb_ctx* ctx, const double* x, int64_t nfrm, int dim,
                          const int32_t* centre, const int32_t* half, const double* tilt, double* out);
 /*
+ * Heavy step of post_filter_merlin (src/magphase.py:3375-3465): r[0] of SPTK `freqt -m n-1 -a alpha -M L/2-1 -A 0 | c2acr -M 0
+ * -l L` (:3419-3427) for nfrm cepstra c[nfrm][n].  G is a HOST float64 table [n][L/2+1], the all-pass transform folded into
+ * the cosine table of the length-L transform by the host mirror; r0[f] = (1/L) sum_k w_k exp(2 (c[f] . G)[k]).  The SPTK
+ * binaries are not available: the pipeline is restated from their published algorithms (parity unpinned, like mcep).
+ */
+int mpb_cep_energy_host(mpb_ctx* ctx, const double* c, int64_t nfrm, int n, const double* G, int K, int L, double* r0);
+/*
  * la.build_min_phase_from_mag_spec (src/libaudio.py:920-934): log|X| -> real cepstrum -> causal lifter -> FFT ->
  * exp, one fused float64 kernel.  mag: nfrm x (fft_len/2+1); out_cplx: nfrm x (fft_len/2+1) x 2 (re, im).
  */

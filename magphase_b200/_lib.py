@@ -62,6 +62,7 @@ SIGNATURES = {
     'mpb_synthesis_compressed_host2': [_vp, _vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _i64],
     'mpb_post_filter_dev': [_vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp],
     'mpb_post_filter_host': [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _vp],
+    'mpb_cep_energy_host': [_vp, _vp, _i64, C.c_int, _vp, C.c_int, C.c_int, _vp],
     'mpb_min_phase_dev': [_vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp],
     'mpb_min_phase_host': [_vp, _vp, _i64, C.c_int, _vp],
     'mpb_mt19937_uniform_dev': [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, _vp, C.c_int],

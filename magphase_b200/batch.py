@@ -103,9 +103,7 @@ def run_waveform_generation(tokens, in_feats_dir, out_syn_dir, mag_dim, phase_di
     The aperiodic noise is drawn from NumPy's global stream in list order (seed it for reproducible output)."""
     if isinstance(tokens, str):
         tokens = read_tokens(tokens)
-    if pf_type == 'merlin':
-        raise NotImplementedError("pf_type='merlin' shells out to nine SPTK binaries (src/magphase.py:3375-3465): out of scope")
-    if pf_type not in ('magphase', 'no'):
+    if pf_type not in ('magphase', 'merlin', 'no'):
         raise ValueError("pf_type must be 'magphase', 'merlin' or 'no'")
     os.makedirs(out_syn_dir, exist_ok=True)
     t0 = time.perf_counter()
@@ -118,10 +116,10 @@ def run_waveform_generation(tokens, in_feats_dir, out_syn_dir, mag_dim, phase_di
         for k, g in enumerate(groups):
             feats = [f.result() for f in pending]
             pending = load(groups[k + 1]) if k + 1 < len(groups) else []
-            if pf_type == 'magphase':
-                # the post-filter works frame by frame (src/magphase.py:2300-2378): one call over the stacked rows
+            if pf_type in ('magphase', 'merlin'):
+                # both post-filters work frame by frame (src/magphase.py:2300-2378, 3375-3465): one call over the stacked rows
                 rows = np.concatenate([np.atleast_2d(f[0]) for f in feats], axis=0)
-                rows = mp.post_filter(rows, fs)
+                rows = mp.post_filter(rows, fs) if pf_type == 'magphase' else mp.post_filter_merlin(rows, fs)
                 off = np.concatenate(([0], np.cumsum([np.atleast_2d(f[0]).shape[0] for f in feats])))
                 feats = [(rows[off[i]:off[i + 1]],) + f[1:] for i, f in enumerate(feats)]
             ys = mp.synthesis_from_compressed_batch(feats, fs, fft_len=fft_len, b_const_rate=b_const_rate)
@@ -187,7 +185,7 @@ def main(argv=None):
     g.add_argument('--feats-dir', required=True)
     g.add_argument('--out-dir', required=True)
     g.add_argument('--fs', type=int, default=48000)
-    g.add_argument('--pf-type', default='magphase', choices=['magphase', 'no'])
+    g.add_argument('--pf-type', default='magphase', choices=['magphase', 'merlin', 'no'])
     g.add_argument('--seed', type=int, default=None, help='np.random.seed for the aperiodic noise')
     for p in (e, g):
         p.add_argument('--mag-dim', type=int, default=60)

@@ -369,6 +369,26 @@ int mpb_post_filter_dev(mpb_ctx* ctx, void* stream, const void* x, int dtype, in
     return MPB_OK;
 }
 
+// r0 of SPTK `freqt -A 0 | c2acr -M 0` for nfrm cepstra of n coefficients (post_filter_merlin, src/magphase.py:3419-3427).
+// G: HOST float64 [n][K], K = L/2 + 1: the all-pass transform folded into the cosine table by the host mirror.
+int mpb_cep_energy_host(mpb_ctx* ctx, const double* c, int64_t nfrm, int n, const double* G, int K, int L, double* r0) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (nfrm == 0) return MPB_OK;
+    if (!c || !G || !r0 || n < 1 || n > 1024 || K < 2 || L != 2 * (K - 1)) return fail(MPB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevBuf* b = ctx->scratch;
+    cudaStream_t st = ctx->stream;
+    CU(b[0].need(sizeof(double) * (size_t)nfrm * n)); CU(b[1].need(sizeof(double) * (size_t)n * K)); CU(b[5].need(sizeof(double) * (size_t)nfrm));
+    CU(cudaMemcpyAsync(b[0].p, c, sizeof(double) * (size_t)nfrm * n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b[1].p, G, sizeof(double) * (size_t)n * K, cudaMemcpyHostToDevice, st));
+    LAUNCH(ctx, st, "k_cep_energy", launch_cep_energy((const double*)b[0].p, nfrm, n, (const double*)b[1].p, K, L, (double*)b[5].p,
+                                                      ctx->num_sms, st));
+    CU(cudaMemcpyAsync(r0, b[5].p, sizeof(double) * (size_t)nfrm, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MPB_OK;
+}
+
 int mpb_post_filter_host(mpb_ctx* ctx, const double* x, int64_t nfrm, int dim, const int32_t* centre,
                          const int32_t* half, const double* tilt, double* out) {
     if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");

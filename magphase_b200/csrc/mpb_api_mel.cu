@@ -396,6 +396,7 @@ int mpb_analysis_compressed_hostv2(mpb_mel* m, const void* const* sigs, int sig_
     }
     const auto t1 = now();
     std::vector<cudaEvent_t> evs;
+    PipelineDrain drain(ctx, &evs);                // every exit path below drains the streams first
     auto on_group = [&](int32_t g, int dtype) -> int {
         cudaEvent_t e_in = get_event(ctx), e_cmp = get_event(ctx);
         evs.push_back(e_in); evs.push_back(e_cmp);
@@ -431,7 +432,6 @@ int mpb_analysis_compressed_hostv2(mpb_mel* m, const void* const* sigs, int sig_
     const auto t2 = now();
     // drain all three stages even after an error: host and staging buffers must not be reused under a live copy
     cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
-    for (auto e : evs) put_event(ctx, e);
     if (rc != MPB_OK) return rc;
     CU(e1); CU(e2); CU(e3);
     if (trace)

@@ -359,18 +359,16 @@ int mpb_synthesis_compressed_host2(mpb_syn* s, const void* mag_mel_v, const void
     // ---- the NumPy noise stream goes first, on its own stream: the twister is latency bound (a few SMs), so it runs
     // under the descriptor packing and the first feature upload; the first group's kernels wait for e_rng ----
     uint32_t* mt_fin = nullptr;
-    std::vector<cudaEvent_t> e_rng;
+    std::vector<cudaEvent_t> e_rng, evs;
+    std::vector<float> noise32;
+    PipelineDrain drain(ctx, &evs, &e_rng);        // from here on every exit path drains the streams first
     if (!noise && n_noise > 0) {
         CU(ctx->mt_fin.need(sizeof(uint32_t) * 625));
         mt_fin = (uint32_t*)ctx->mt_fin.p;
         e_rng.push_back(get_event(ctx));
         rc = mt19937_enqueue(ctx, ctx->stream_aux, mt_key, *mt_pos, &n_noise, 1, -1.0, 1.0, b[B_NOISE].p, MPB_F32, mt_fin,
                              e_rng.data());
-        if (rc != MPB_OK) {
-            cudaStreamSynchronize(ctx->stream_aux);
-            for (auto e : e_rng) put_event(ctx, e);
-            return rc;
-        }
+        if (rc != MPB_OK) return rc;
     }
 
     // ---- device buffers, all at their final size before anything is enqueued ----
@@ -420,7 +418,6 @@ int mpb_synthesis_compressed_host2(mpb_syn* s, const void* mag_mel_v, const void
     }
 
     // ---- noise: explicit samples (narrowed on the host, uploaded) or the NumPy stream advanced on the device ----
-    std::vector<float> noise32;
     if (noise) {
         noise32.resize((size_t)n_noise);
         for (int64_t i = 0; i < n_noise; ++i) noise32[i] = (float)noise[i];
@@ -429,7 +426,6 @@ int mpb_synthesis_compressed_host2(mpb_syn* s, const void* mag_mel_v, const void
     const auto t2 = now();
 
     // ---- the pipeline ----
-    std::vector<cudaEvent_t> evs;
     for (const SynRange& r : rg) {
         const int64_t nr = r.row_b - r.row_a;
         if (nr > 0) {
@@ -470,8 +466,6 @@ int mpb_synthesis_compressed_host2(mpb_syn* s, const void* mag_mel_v, const void
     // drain every stage, also after an error: noise32 / runs / the staging blocks must outlive the copies
     cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
     cudaError_t e4 = cudaStreamSynchronize(ctx->stream_aux);
-    for (auto e : evs) put_event(ctx, e);
-    for (auto e : e_rng) put_event(ctx, e);
     if (rc != MPB_OK) return rc;
     CU(e1); CU(e2); CU(e3); CU(e4);
     if (mt_fin) {

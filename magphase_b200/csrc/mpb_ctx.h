@@ -93,6 +93,21 @@ inline cudaEvent_t get_event(mpb_ctx* ctx) {
 }
 inline void put_event(mpb_ctx* ctx, cudaEvent_t e) { if (e) ctx->ev_pool.push_back(e); }
 
+// Scope guard of the pipelined *_host entry points: whatever path leaves the function (CU() returns on any CUDA error), the
+// four streams are drained before host / staging memory that live copies still read goes out of scope, and the hand-off
+// events go back to the pool.
+struct PipelineDrain {
+    mpb_ctx* ctx;
+    std::vector<cudaEvent_t>* evs[2] = {nullptr, nullptr};
+    explicit PipelineDrain(mpb_ctx* c, std::vector<cudaEvent_t>* a = nullptr, std::vector<cudaEvent_t>* b = nullptr) : ctx(c) { evs[0] = a; evs[1] = b; }
+    ~PipelineDrain() {
+        cudaStreamSynchronize(ctx->stream_in); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream_out);
+        cudaStreamSynchronize(ctx->stream_aux);
+        for (auto* v : evs)
+            if (v) { for (auto e : *v) put_event(ctx, e); v->clear(); }
+    }
+};
+
 // number of utterance groups the pipelined *_host entry points cut a batch of nfrm frames into: about one group per
 // `frames_per_group` frames, at most `max_groups` (MPB_PIPELINE_GROUPS overrides).  Smaller groups shorten the fill and
 // drain of the pipeline, larger ones keep the persistent kernels' grids full.

@@ -42,6 +42,47 @@ cudaError_t launch_post_filter(const void* x, int dtype, int64_t nfrm, int dim, 
     return cudaGetLastError();
 }
 
+// ---- cepstrum -> r[0] (energy of the spectrum a cepstrum describes) ---------------------------------
+// SPTK `c2acr -M 0` behind `freqt -A 0` (src/magphase.py:3419-3427, post_filter_merlin): with the all-pass transform folded
+// into the cosine table on the host, r0[f] = (1 / L) sum_k w_k exp(2 sum_j c[f][j] G[j][k]) over the K = L/2 + 1 half-circle
+// bins (w_k = 2 except at DC and Nyquist).  One CTA per frame; float64; partial sums reduced in a fixed order.
+__global__ void __launch_bounds__(256)
+k_cep_energy(const double* __restrict__ c, int64_t nfrm, int n, const double* __restrict__ G, int K, int L,
+             double* __restrict__ r0) {
+    extern __shared__ double ce_s[];                 // [n] cepstrum of the frame, then [8] warp sums
+    double* red = ce_s + n;
+    const int t = threadIdx.x;
+    for (int64_t f = blockIdx.x; f < nfrm; f += gridDim.x) {
+        __syncthreads();
+        for (int j = t; j < n; j += 256) ce_s[j] = c[f * n + j];
+        __syncthreads();
+        double acc = 0.0;
+        for (int k = t; k < K; k += 256) {
+            double s = 0.0;
+            for (int j = 0; j < n; ++j) s = fma(ce_s[j], __ldg(G + (size_t)j * K + k), s);
+            acc += ((k == 0 || k == K - 1) ? 1.0 : 2.0) * exp(2.0 * s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((t & 31) == 0) red[t >> 5] = acc;
+        __syncthreads();
+        if (t == 0) {
+            double s = 0.0;
+            for (int i = 0; i < 8; ++i) s += red[i];
+            r0[f] = s / (double)L;
+        }
+    }
+}
+
+cudaError_t launch_cep_energy(const double* c, int64_t nfrm, int n, const double* G, int K, int L, double* r0, int num_sms,
+                              cudaStream_t st) {
+    if (nfrm < 1) return cudaSuccess;
+    int64_t grid = (int64_t)num_sms * 8;
+    if (grid > nfrm) grid = nfrm;
+    k_cep_energy<<<(unsigned)grid, 256, sizeof(double) * (n + 8), st>>>(c, nfrm, n, G, K, L, r0);
+    return cudaGetLastError();
+}
+
 // ---- minimum phase ------------------------------------------------------------------------------
 // Reference: la.build_min_phase_from_mag_spec src/libaudio.py:920-934 (with la.log :241-248):
 //   log|X| -> Hermitian extend -> ifft.real (real cepstrum) -> zero n >= H, double n = 1..H-2 -> fft -> half -> exp

@@ -32,6 +32,28 @@ template <typename T> using cx = typename Vec2<T>::type;
 template <typename T> __device__ __forceinline__ cx<T> mk(T x, T y) { cx<T> r; r.x = x; r.y = y; return r; }
 template <typename T2> __device__ __forceinline__ T2 cadd(T2 a, T2 b) { a.x += b.x; a.y += b.y; return a; }
 template <typename T2> __device__ __forceinline__ T2 csub(T2 a, T2 b) { a.x -= b.x; a.y -= b.y; return a; }
+// float32 complex add / subtract as ONE packed instruction (Blackwell add.f32x2 / sub.f32x2, SASS FADD2): the float32 FFT
+// kernels are issue-bound and complex adds are a fifth of their instructions
+__device__ __forceinline__ unsigned long long f2_bits(float2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 bits_f2(unsigned long long r) {
+    float2 a;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+    return a;
+}
+template <> __device__ __forceinline__ float2 cadd<float2>(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+template <> __device__ __forceinline__ float2 csub<float2>(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
 template <typename T2> __device__ __forceinline__ T2 cmul(T2 a, T2 b) {
     T2 r;
     r.x = a.x * b.x - a.y * b.y;

@@ -286,8 +286,9 @@ def analysis_lossless_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None):
 
 
 def get_pitch_marks_and_voicing(wav_file, n_smpls, fs, est_file=None, pm=None):
-    """Pitch marks (seconds) + voicing for analysis_lossless: explicit arrays, a REAPER .est file, or the
-    REAPER binary itself when installed (src/magphase.py:2875-2878, src/libaudio.py:421-455)."""
+    """Pitch marks (seconds) + voicing for analysis_lossless: explicit arrays, a REAPER .est file, the REAPER binary
+    itself when installed (src/magphase.py:2875-2878, src/libaudio.py:421-455) -- or, without it, this package's own
+    provider (magphase_b200/pitchmarks.py: autocorrelation voicing + peak picking; same output layout, no parity claim)."""
     if pm is not None:
         v_pm_sec, v_voi = pm
         return np.asarray(v_pm_sec, dtype=np.float64), np.asarray(v_voi, dtype=np.float64)
@@ -295,8 +296,13 @@ def get_pitch_marks_and_voicing(wav_file, n_smpls, fs, est_file=None, pm=None):
         return io.read_reaper_est_file(est_file, check_len_smpls=n_smpls, fs=fs)
     reaper = io.find_tool('reaper')
     if reaper is None:
-        raise RuntimeError('analysis_lossless: REAPER binary not found (config.ini [TOOLS] bin_dir / tools/bin). '
-                           'Pass est_file=<REAPER .est file> or pm=(v_pm_sec, v_voi).')
+        from .pitchmarks import estimate_pitch_marks
+        warnings.warn('REAPER binary not found (config.ini [TOOLS] bin_dir / tools/bin): pitch marks come from '
+                      'magphase_b200.pitchmarks.estimate_pitch_marks (pass est_file= / pm= to supply your own)')
+        v_sig, fs_w = io.read_audio_file(wav_file)
+        v_pm_sec, v_voi = estimate_pitch_marks(v_sig, fs_w)
+        ok = np.round(v_pm_sec * fs_w).astype(int) < (n_smpls - 1)
+        return v_pm_sec[ok], v_voi[ok]
     tmp_est = io.ins_pid('temp.est')
     print("Extracting epochs with REAPER...")
     call(reaper + " -s -x 400 -m 50 -a -u 0.005 -i %s -p %s" % (wav_file, tmp_est), shell=True)
@@ -984,6 +990,70 @@ def post_filter(m_mag_mel_log, fs, av_len_at_zero=None, av_len_at_nyq=None, boos
     return out
 
 
+_MERLIN_TABLES = {}
+
+
+def _freqt_matrix(n_out, n_in, alpha):
+    """SPTK freqt (Oppenheim all-pass recursion, inputs consumed from the last coefficient down) as an (n_out x n_in) matrix:
+    the recursion run on all unit vectors at once."""
+    g = np.zeros((n_out, n_in))
+    b = 1.0 - alpha * alpha
+    eye = np.eye(n_in)
+    for i in range(n_in - 1, -1, -1):
+        d = g.copy()
+        g[0] = eye[i] + alpha * d[0]
+        if n_out > 1:
+            g[1] = b * d[0] + alpha * d[1]
+        for j in range(2, n_out):
+            g[j] = d[j - 1] + alpha * (d[j] - g[j - 1])
+    return g
+
+
+def post_filter_merlin(m_mag_mel_log, fs, pf_coef=1.4):
+    """Merlin-style post-filter (src/magphase.py:3375-3465): lifter the mel cepstrum by pf_coef above the second
+    coefficient and restore the frame energy.  The reference pipes the cepstra through nine SPTK-3.9 binaries (x2x, freqt,
+    c2acr, vopr, mc2b, bcp, sopr, merge, b2mc; command lines :3418-3444) that are not available here: every stage is
+    restated from the published algorithm of its binary, with SPTK's float32 files at every boundary -- PARITY UNPINNED,
+    like `mcep`.  The heavy stage (two energy integrals over a 4096-point spectrum per frame, `freqt | c2acr`) runs on the
+    device (k_cep_energy); the O(60)-per-frame recursions around it are vectorised NumPy."""
+    m = np.ascontiguousarray(m_mag_mel_log, dtype=np.float64)
+    n = m.shape[1]
+    fft_len, alpha = 4096, define_alpha(fs)
+    f32 = lambda x: np.asarray(x, dtype=np.float32).astype(np.float64)
+    key = (n, alpha)
+    if key not in _MERLIN_TABLES:
+        # freqt -m n-1 -a alpha -M fft_len/2-1 -A 0 (all-pass back to the linear axis: a = -alpha) folded into the cosine
+        # table of c2acr's length-4096 real transform: G[j][k] = sum_i F[i][j] cos(2 pi k i / L)
+        F = _freqt_matrix(fft_len // 2, n, -alpha)
+        k = np.arange(fft_len // 2 + 1)
+        G = np.cos(2 * np.pi * np.outer(np.arange(fft_len // 2), k) / fft_len).T @ F
+        _MERLIN_TABLES[key] = np.ascontiguousarray(G.T)                      # [n][K]
+    G = _MERLIN_TABLES[key]
+    ext = np.hstack((m, m[:, -2:0:-1]))                                      # la.rceps(in_type='log', out_type='compact')
+    ceps = np.fft.ifft(ext, axis=1).real
+    ceps[:, 1:(n - 2)] *= 2
+    mcep = f32(ceps[:, :n])
+    w = f32(np.r_[1.0, 1.0, np.full(n - 2, float('%1.2f' % pf_coef))])
+    lifted = f32(mcep * w)
+    both = np.ascontiguousarray(np.vstack((mcep, lifted)))
+    r = np.empty(both.shape[0])
+    _lib.check(_lib.lib().mpb_cep_energy_host(_lib.ctx(), _lib.ptr(both), both.shape[0], n, _lib.ptr(G), G.shape[1], fft_len,
+                                              _lib.ptr(r)))
+    r0, p_r0 = f32(r[:m.shape[0]]), f32(r[m.shape[0]:])
+    b = lifted.copy()                                                        # mc2b
+    for i in range(n - 2, -1, -1):
+        b[:, i] = b[:, i] - alpha * b[:, i + 1]
+    b = f32(b)
+    p_b0 = f32(f32(f32(np.log(f32(r0 / p_r0))) / 2.0) + b[:, 0])
+    merged = np.hstack((p_b0[:, None], b[:, 1:]))
+    mcep_pf = merged.copy()                                                  # b2mc
+    mcep_pf[:, :-1] = merged[:, :-1] + alpha * merged[:, 1:]
+    mcep_pf = f32(mcep_pf)
+    out = mcep_pf @ np.cos(np.arange(n)[:, None] * warped_axis(0.0, n)[None, :])   # la.mcep_to_sp_cosmat(alpha=0, 'log')
+    out[np.isnan(out)] = MAGIC
+    return out
+
+
 def build_min_phase_from_mag_spec(m_mag):
     """Minimum-phase complex spectrum of a magnitude spectrum.  la.build_min_phase_from_mag_spec, src/libaudio.py:920-934"""
     m = np.ascontiguousarray(m_mag, dtype=np.float64)
@@ -995,7 +1065,7 @@ def build_min_phase_from_mag_spec(m_mag):
 
 def synthesis_from_acoustic_modelling(in_feats_dir, filename_token, out_syn_dir, mag_dim, phase_dim, fs, fft_len=None,
                                       pf_type='no', b_const_rate=False):
-    """Feature files -> wav.  src/magphase.py:3229-3275 (pf_type 'merlin' needs nine SPTK binaries: out of scope)."""
+    """Feature files -> wav.  src/magphase.py:3229-3275."""
     print("\nSynthesising file: " + filename_token + '.wav............................')
     m_mag_mel_log = io.read_binfile(in_feats_dir + '/' + filename_token + '.mag', dim=mag_dim)
     m_real_mel = io.read_binfile(in_feats_dir + '/' + filename_token + '.real', dim=phase_dim)
@@ -1005,7 +1075,8 @@ def synthesis_from_acoustic_modelling(in_feats_dir, filename_token, out_syn_dir,
         print('Using MagPhase postfilter...')
         m_mag_mel_log = post_filter(m_mag_mel_log, fs)
     elif pf_type == 'merlin':
-        raise NotImplementedError("pf_type='merlin' shells out to nine SPTK binaries (src/magphase.py:3375-3465): out of scope")
+        print('Using Merlin postfilter...')
+        m_mag_mel_log = post_filter_merlin(m_mag_mel_log, fs)
     elif pf_type == 'no':
         print('No postfilter...')
     v_syn_sig = synthesis_from_compressed(m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0, fs, fft_len=fft_len,

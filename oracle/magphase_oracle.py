@@ -696,3 +696,61 @@ def analysis_with_del_comp_and_ph_encoding_from_pm(v_in_sig, nFFT, fs, mvf, v_pm
     m_phs_i = interpolate.interp1d(np.arange(mvf_bin), m_phs[:, :mvf_bin], kind='cubic')(grid)
     m_phc_i = interpolate.interp1d(np.arange(mvf_bin), m_phc[:, :mvf_bin], kind='cubic')(grid)
     return m_spmgc, mcep_j0(m_phs_i, in_type=1), mcep_j0(m_phc_i, in_type=1), v_shift
+
+
+# ------------------------------------------------------------------------------------------------
+# Merlin-style post-filter (src/magphase.py:3375-3465).  PARITY UNPINNED: the reference pipes the cepstra through nine
+# SPTK-3.9 binaries (x2x freqt c2acr vopr mc2b bcp sopr merge b2mc, fetched by tools/download_and_compile_tools.sh:5,
+# absent here, no fixture shipped); each stage below restates the published algorithm of the binary named beside it,
+# with SPTK's float32 file format at every pipe / file boundary.
+# ------------------------------------------------------------------------------------------------
+def _f32(x):
+    return np.asarray(x, dtype=np.float32).astype(np.float64)
+
+
+def sptk_mc2b(m_mc, alpha):
+    """SPTK mc2b: b[m] = c[m]; b[i] = c[i] - alpha b[i+1]."""
+    b = np.array(m_mc, dtype=np.float64)
+    for i in range(b.shape[1] - 2, -1, -1):
+        b[:, i] = b[:, i] - alpha * b[:, i + 1]
+    return b
+
+
+def sptk_b2mc(m_b, alpha):
+    """SPTK b2mc: c[m] = b[m]; c[i] = b[i] + alpha b[i+1] (b as given, not the updated values)."""
+    c = np.array(m_b, dtype=np.float64)
+    c[:, :-1] = m_b[:, :-1] + alpha * m_b[:, 1:]
+    return c
+
+
+def sptk_c2acr_r0(m_c, fft_len):
+    """SPTK c2acr -M 0: x = Re FFT_l(c zero padded); r[0] = mean_k exp(2 x[k])."""
+    x = np.fft.fft(m_c, n=fft_len, axis=1).real
+    return np.mean(np.exp(2.0 * x), axis=1)
+
+
+def post_filter_merlin(m_mag_mel_log, fs, pf_coef=1.4):
+    """src/magphase.py:3375-3465 (command lines :3418-3444)."""
+    fft_len = 4096
+    minph_ord = fft_len // 2 - 1
+    alpha = define_alpha(fs)
+    n = m_mag_mel_log.shape[1]
+    # la.rceps(in_type='log', out_type='compact'), written as float32 (:3397-3398)
+    ext = np.hstack((m_mag_mel_log, m_mag_mel_log[:, -2:0:-1]))
+    ceps = np.fft.ifft(ext, axis=1).real
+    ceps[:, 1:(n - 2)] *= 2
+    mcep = _f32(ceps[:, :n])
+    w = _f32(np.r_[1.0, 1.0, np.full(n - 2, float('%1.2f' % pf_coef))])        # echo 1 1 pf pf ... | x2x +af
+    # freqt -m n-1 -a alpha -M 2047 -A 0: all-pass from warping alpha to 0, i.e. freqt with a = (0 - alpha) / (1 - 0 alpha)
+    F = freqt_matrix(minph_ord + 1, n, -alpha)
+    lifted = _f32(mcep * w)                                                   # vopr -m
+    r0 = _f32(sptk_c2acr_r0(_f32(mcep @ F.T), fft_len))
+    p_r0 = _f32(sptk_c2acr_r0(_f32(lifted @ F.T), fft_len))
+    b = _f32(sptk_mc2b(lifted, alpha))                                        # mc2b
+    b0 = b[:, 0]                                                              # bcp -s 0 -e 0
+    p_b0 = _f32(_f32(_f32(np.log(_f32(r0 / p_r0))) / 2.0) + b0)               # vopr -d | sopr -LN -d 2 | vopr -a
+    merged = np.hstack((p_b0[:, None], b[:, 1:]))                             # bcp -s 1 -e n-1 | merge -s 0
+    mcep_pf = _f32(sptk_b2mc(merged, alpha))                                  # b2mc
+    out = mcep_to_sp_cosmat(mcep_pf, n, alpha=0.0, out_type='log')
+    out[np.isnan(out)] = MAGIC
+    return out

@@ -13,8 +13,6 @@ def test_read_tokens_and_batches(tmp_path):
 
 
 def test_argument_errors_come_before_device_work(tmp_path):
-    with pytest.raises(NotImplementedError):
-        batch.run_waveform_generation(['a'], str(tmp_path), str(tmp_path / 'o'), 60, 45, 48000, pf_type='merlin')
     with pytest.raises(ValueError):
         batch.run_waveform_generation(['a'], str(tmp_path), str(tmp_path / 'o'), 60, 45, 48000, pf_type='bogus')
     # an empty token list is a no-op on both sides

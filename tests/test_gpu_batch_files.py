@@ -83,7 +83,8 @@ def test_batch_cli_and_errors(corpus, capsys):
     batch.main(['extract', '--scp', scp, '--wav-dir', wav_dir, '--out-dir', out, '--est-dir', est_dir, '--batch-utts', '8'])
     assert 'Done!' in capsys.readouterr().out
     assert sorted(os.listdir(out)) == sorted(t + e for t in tokens for e in ('.mag', '.real', '.imag', '.lf0', '.shift'))
-    with pytest.raises(NotImplementedError):
-        batch.run_waveform_generation(tokens, out, str(d / 'x'), 60, 45, 48000, pf_type='merlin')
+    np.random.seed(3)
+    r = batch.run_waveform_generation(tokens, out, str(d / 'x'), 60, 45, 48000, pf_type='merlin')       # Merlin-style post-filter
+    assert r['utterances'] == len(tokens) and sorted(os.listdir(str(d / 'x'))) == sorted(t + '.wav' for t in tokens)
     with pytest.raises(FileNotFoundError):
         batch.run_feature_extraction(['missing'], wav_dir, str(d / 'y'), est_dir=est_dir)
