@@ -294,6 +294,16 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    # one process per GPU on a shared host: every rank keeps to its own slice of the cores (its NumPy bookkeeping, staging
+    # copies and the two worker threads of the end-to-end arm would otherwise migrate across all of them)
+    lws = int(os.environ.get('LOCAL_WORLD_SIZE', world))
+    if a.impl == 'ours' and lws > 1 and hasattr(os, 'sched_setaffinity'):
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cpus) // lws)
+            os.sched_setaffinity(0, cpus[local_rank * per:(local_rank + 1) * per] or cpus)
+        except OSError:
+            pass
     chain = ('analysis_compressed(mag=60, real=45, imag=45) -> synthesis_from_compressed(b_out_hpf=False)' if comp
              else 'analysis_lossless -> synthesis_from_lossless')
     workload = '%s chain: %s, %d x %.0f s synth48k-v1 utterances per GPU per step' % (a.workload, chain, a.utts, a.dur)
