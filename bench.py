@@ -277,6 +277,8 @@ def main():
     ap.add_argument('--feat-dtype', default='f32', choices=['f32', 'f64'], help='lossless feature storage in HBM')
     ap.add_argument('--analysis-compute', default='f64', choices=['f32', 'f64'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-rng-overlap', action='store_true', help='draw the noise on the main stream, before the synthesis half')
+    ap.add_argument('--e2e-workers', type=int, default=4, help='host threads (private contexts) of the end-to-end arm')
     ap.add_argument('--no-extras', action='store_true', help='skip the sub-records (lossless chain, configs 3 / 4 / 5)')
     ap.add_argument('--stream-utts', type=int, default=2048, help='utterances per GPU of the streamed many-batch record (config 5)')
     ap.add_argument('--ola-target', type=int, default=32, help='frames per overlap-add run (device-timed arm)')
@@ -366,7 +368,7 @@ def main():
         d_out = lp.alloc_output(F32)
         sig = d_sig if n_utts is None else d_sig[:int(sum(gg[0]))]
 
-        def step(evs=None):
+        def step(evs=None, sequential=False):
             if evs:
                 evs[0].record()
             lp.analysis(sig, feats, compute=ana_compute)
@@ -380,13 +382,18 @@ def main():
     if comp:
         plan = CompressedPlan(*geom, FS, FFT_LEN, mag_dim=60, phase_dim=45, device=local_rank, ola_target_frames=a.ola_target)
 
-        def step(evs=None):
+        def step(evs=None, sequential=False):
             if evs:
                 evs[0].record()
-            plan.analysis(d_sig, compute=ana_compute)
-            if evs:
-                evs[1].record()
-            plan.synthesis()           # includes the MT19937 draw of the aperiodic noise (src/magphase.py:883) on the device
+            if sequential or a.no_rng_overlap:
+                plan.analysis(d_sig, compute=ana_compute)
+                if evs:
+                    evs[1].record()
+                plan.synthesis()       # draws the aperiodic noise (src/magphase.py:883) on the main stream first
+            else:
+                # the MT19937 draw runs on a side stream next to the analysis half; both join before the synthesis half,
+                # inside the timed region
+                plan.chain(d_sig, compute=ana_compute, mid_event=evs[1] if evs else None)
             if evs:
                 evs[2].record()
         bytes_ana, bytes_syn = plan.analysis_bytes(), plan.synthesis_bytes()
@@ -424,7 +431,7 @@ def main():
     prof_steps = 3
     _lib.profile_begin(local_rank)
     for _ in range(prof_steps):
-        step()
+        step(sequential=True)          # the noise draw on the main stream: clean per-kernel times
     prof = _lib.profile_end(local_rank)
 
     # ---- e2e through the public host API (NumPy in / NumPy out; H2D + D2H inside the timed region) ----
@@ -439,36 +446,48 @@ def main():
         e_pcm = [np.round(x * 32768.0).astype(np.int16) for x in e_sig]
 
         from magphase_b200.batch import run_chain_stream
-        half = (len(e_pcm) + 1) // 2
-        e_batches = [list(zip(e_pcm[:half], e_pm[:half], e_voi[:half])), list(zip(e_pcm[half:], e_pm[half:], e_voi[half:]))]
-        e_batches = [b for b in e_batches if b]
+        e_batch = list(zip(e_pcm, e_pm, e_voi))
 
-        def e2e_step(narrow=True, keep=False):
+        def e2e_step(narrow=True, keep=False, n=1):
             if narrow:
-                # two host threads, each with a private context on this GPU, take half of the step's utterances each
-                # (magphase_b200.batch.run_chain_stream): the NumPy bookkeeping of one half overlaps the GPU work of the other
-                r = run_chain_stream(e_batches, FS, fft_len=FFT_LEN, mag_dim=60, phase_dim=45, b_out_hpf=False, n_workers=2,
-                                     out_dtype=np.float32, keep_outputs=keep)
+                # n steps = n batches streamed through `--e2e-workers` host threads, each with a private context on this GPU
+                # (magphase_b200.batch.run_chain_stream): the NumPy bookkeeping and PCIe copies of one step overlap the kernels
+                # of its neighbours -- what the reference gets from one forked process per utterance.  Every step's inputs are
+                # copied to the device and its results back to the host inside the timed region.
+                r = run_chain_stream([e_batch] * n, FS, fft_len=FFT_LEN, mag_dim=60, phase_dim=45, b_out_hpf=False,
+                                     n_workers=a.e2e_workers, out_dtype=np.float32, keep_outputs=keep)
                 if not keep:
-                    return r['frames'], None, None
-                return r['frames'], [o for b in r['outputs'] for o in b[0]], [y for b in r['outputs'] for y in b[1]]
+                    return r['frames'] // n, None, None
+                return r['frames'] // n, r['outputs'][0][0], r['outputs'][0][1]
             else:
                 outs = mp.analysis_compressed_batch(e_sig, FS, e_pm, e_voi, fft_len=FFT_LEN, mag_dim=60, phase_dim=45)
                 ys = mp.synthesis_from_compressed_batch([o[:4] for o in outs], FS, b_out_hpf=False)
             return sum(o[4].size for o in outs), outs, ys
-        api = ('magphase_b200.batch.run_chain_stream: analysis_compressed_batch(int16 PCM in, out_dtype=float32) -> '
-               'synthesis_from_compressed_batch(float32 features in, out_dtype=float32) on 2 host threads (64 utterances each, private '
-               'contexts), NumPy-stream noise drawn on the device, results copied out of the pinned pool')
+        api = ('magphase_b200.batch.run_chain_stream: per step analysis_compressed_batch(int16 PCM in, out_dtype=float32) -> '
+               'synthesis_from_compressed_batch(float32 features in, out_dtype=float32) over %d utterances; the steps are taken '
+               'round-robin by %d host threads with private contexts; NumPy-stream noise drawn on the device' % (len(e_batch), a.e2e_workers))
     else:
         def e2e_step(narrow=True, keep=False):
             outs = mp.analysis_lossless_batch(e_sig, FS, e_pm, e_voi, fft_len=FFT_LEN)
             ys = mp.synthesis_from_lossless_batch([o[:4] for o in outs], FS)
             return sum(o[5].size for o in outs), outs, ys
         api = 'analysis_lossless_batch -> synthesis_from_lossless_batch (float64 NumPy in/out)'
-    e_steps = max(2, min(a.steps, 5))
+    e_steps = max(6, a.steps) if comp else max(2, min(a.steps, 5))
+
+    pool_stats = {}
 
     def time_e2e(narrow):
         r = e2e_step(narrow, keep=True)       # untimed: the results themselves, for the byte counts
+        if narrow and comp:
+            e2e_step(True, n=e_steps)         # untimed pass of the same stream: every worker's context and pinned blocks exist
+            barrier()
+            pool0 = dict(_lib.pinned.stats)
+            t = time.perf_counter()
+            e2e_step(True, n=e_steps)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t
+            pool_stats.update({k: round(v - pool0[k], 4) for k, v in _lib.pinned.stats.items()})
+            return (dt, ) + r
         e2e_step(narrow)
         barrier()
         t = time.perf_counter()
@@ -575,7 +594,8 @@ def main():
                    'parallelism': 'utterance-sharded x%d' % world},
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d),
                 'd2h_bytes_per_step': int(d2h), 'utts_per_gpu_per_step': len(e_utts), 'api': api,
-                'frac_of_value': e2e_value / value if value > 0 else None},
+                'frac_of_value': e2e_value / value if value > 0 else None, 'steps': e_steps,
+                'pinned_pool_during_timed_steps': pool_stats or None},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s',
                      'frac': dom['frac'],
@@ -698,13 +718,13 @@ def run_extras(a, torch, _lib, mp, CompressedPlan, make_lossless, geom, d_sig, u
     from magphase_b200.batch import run_chain_stream
     pcm_pool = [(np.round(u[0] * 32768.0).astype(np.int16), u[1], u[2]) for u in pool]
     bl = [[pcm_pool[i] for i in b] for b in batches]
-    run_chain_stream(bl, FS, fft_len=FFT_LEN, n_workers=2)          # first pass: device scratch grows, result buffers get page-locked and pooled
+    run_chain_stream(bl, FS, fft_len=FFT_LEN, n_workers=a.e2e_workers)   # first pass: device scratch grows, result buffers get page-locked and pooled
     barrier()
-    r = run_chain_stream(bl, FS, fft_len=FFT_LEN, n_workers=2)
+    r = run_chain_stream(bl, FS, fft_len=FFT_LEN, n_workers=a.e2e_workers)
     torch.cuda.synchronize()
     frames, s_s = r['frames'], r['seconds']
     ex['stream'] = {'workload': 'config 5 per GPU: %d utterances of 2-8 s (LPT order), %d batches of 128 through '
-                                'magphase_b200.batch.run_chain_stream (PCM16 in, float32 out, 2 host threads)' % (n_total, len(batches)),
+                                'magphase_b200.batch.run_chain_stream (PCM16 in, float32 out, %d host threads)' % (n_total, len(batches), a.e2e_workers),
                     'value': frames / s_s, 'unit': 'frames/s', 'frames': int(frames), 'seconds': s_s,
                     'note': 'steady state (second pass over the list; the first pass page-locks the pooled result buffers). BASELINE config 5 = '
                             '12,500 such utterances per GPU on 8 GPUs: run with --stream-utts 12500'}

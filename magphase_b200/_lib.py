@@ -6,6 +6,7 @@ entry point raises.
 import ctypes as C
 import os
 import threading
+import time
 
 import numpy as np
 
@@ -133,6 +134,32 @@ def set_thread_slot(slot):
     _tls.slot = int(slot)
 
 
+class _NoGate:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_gate = _NoGate()
+
+
+def set_device_gate(n_inflight):
+    """Optional admission gate around the pipelined host entry points (None: no gate): with W worker threads and a gate of
+    G < W, at most G of them are inside a C call (staging, kernels, draining) at any time; the others run their NumPy
+    bookkeeping and queue at the gate.  A knob for hosts with few cores per GPU; on the development box it never beat the
+    ungated run (magphase_b200.batch.run_chain_stream has the numbers).  Returns the previous gate."""
+    global _gate
+    prev = _gate
+    _gate = _NoGate() if n_inflight is None else (n_inflight if hasattr(n_inflight, '__enter__') else threading.BoundedSemaphore(int(n_inflight)))
+    return prev
+
+
+def device_gate():
+    return _gate
+
+
 def ctx(device=None):
     """Context handle of (device, current_slot()) (created on first use)."""
     device = default_device() if device is None else int(device)
@@ -176,69 +203,111 @@ def profile_end(device=None):
 
 
 class _PinnedPool:
-    """Recycled page-locked result buffers.  empty(shape) hands out a NumPy array backed by pinned memory; when the
-    array (and every view of it) is garbage collected the buffer goes back to the pool (bounded), so steady-state
-    batch loops neither page-fault fresh memory nor bounce D2H copies through the driver's staging buffer."""
-    MAX_POOLED = 2 << 30          # bytes kept for reuse
-    MAX_SINGLE = 1 << 30          # larger requests use ordinary pageable memory
+    """Page-locked result buffers, sub-allocated from a few large arenas.  empty(shape) hands out a NumPy array backed by
+    pinned memory; when the array (and every view of it) is garbage collected its block goes back to the arena's free list
+    (coalescing with its neighbours).  Page-locking costs ~0.3 ms per MB -- 30-50 ms for one batch's waveform -- so it must
+    never happen in a steady-state batch loop, whatever the order in which worker threads take and return blocks of
+    different sizes: arenas are locked once (``ARENA`` bytes each, ~0.3 s, up to ``MAX_TOTAL``) and never returned to the driver.
+    Requests that do not fit (a single array larger than an arena gets an arena of its own while the budget lasts) fall
+    back to ordinary pageable memory."""
+    ARENA = int(os.environ.get('MPB_PINNED_ARENA_MB', '1024')) << 20
+    MAX_TOTAL = int(os.environ.get('MPB_PINNED_MAX_MB', '8192')) << 20
+    GRAIN = 1 << 16               # block sizes and offsets are multiples of 64 KB
+    BIG = 32 << 20                # blocks from this size on are cut from the END of a free range, smaller ones from its start:
+                                  # waveforms and feature matrices do not interleave, so returned ranges merge again
 
-    def __init__(self):
-        self.free = {}            # bucket size -> [address]
-        self.pooled = 0
+    def __init__(self, alloc=None):
+        self.arenas = []          # [base address, size, free list [[offset, size], ...] sorted by offset]
+        self.total = 0
         self.lock = threading.Lock()
+        self.stats = {'allocs': 0, 'alloc_s': 0.0, 'reuses': 0, 'pageable': 0}
+        self._alloc = alloc or self._cuda_alloc
 
     @staticmethod
-    def _bucket(nbytes):
-        """Sizes are quantised to {1, 1.25, 1.5, 1.75} x 2^k (at most 25 % slack): batches of similar size share buffers."""
-        b = 1 << 16
-        while b < nbytes:
-            b <<= 1
-        if b <= (1 << 16):
-            return b
-        q = b >> 3                       # eighths of the power of two: the candidates above b / 2 are 5/8 .. 8/8 of b
-        for m in (5, 6, 7, 8):
-            if m * q >= nbytes:
-                return m * q
-        return b
+    def _cuda_alloc(size):
+        p = _vp()
+        check(lib().mpb_host_alloc(ctx(), size, C.byref(p)))
+        return p.value
+
+    def _take(self, n):
+        """Best fit over all arenas: (arena index, offset) or None.  Caller holds the lock."""
+        best = None
+        for ai, (_, _, free) in enumerate(self.arenas):
+            for bi, (off, sz) in enumerate(free):
+                if sz >= n and (best is None or sz < best[2]):
+                    best = (ai, bi, sz)
+        if best is None:
+            return None
+        ai, bi, sz = best
+        free = self.arenas[ai][2]
+        off = free[bi][0]
+        if sz == n:
+            free.pop(bi)
+        elif n >= self.BIG:
+            free[bi][1] = sz - n
+            off += sz - n
+        else:
+            free[bi] = [off + n, sz - n]
+        return ai, off
+
+    def _give(self, ai, off, n):
+        with self.lock:
+            free = self.arenas[ai][2]
+            lo, hi = 0, len(free)
+            while lo < hi:
+                mid = (lo + hi) // 2
+                if free[mid][0] < off:
+                    lo = mid + 1
+                else:
+                    hi = mid
+            free.insert(lo, [off, n])
+            if lo + 1 < len(free) and free[lo][0] + free[lo][1] == free[lo + 1][0]:
+                free[lo][1] += free.pop(lo + 1)[1]
+            if lo > 0 and free[lo - 1][0] + free[lo - 1][1] == free[lo][0]:
+                free[lo - 1][1] += free.pop(lo)[1]
+
+    def reserve(self, nbytes):
+        """(address, release callback) of a pinned block of at least nbytes, or (None, None) when the budget is spent."""
+        n = -(-int(nbytes) // self.GRAIN) * self.GRAIN
+        with self.lock:
+            hit = self._take(n)
+            if hit is not None:
+                self.stats['reuses'] += 1
+            else:
+                size = max(min(self.ARENA, max(64 << 20, 8 * n)), n)      # small callers lock small arenas
+                if self.total + size > self.MAX_TOTAL:
+                    size = n
+                if self.total + size > self.MAX_TOTAL:
+                    self.stats['pageable'] += 1
+                    return None, None
+                t0 = time.perf_counter()
+                try:
+                    base = self._alloc(size)
+                except RuntimeError:
+                    self.stats['pageable'] += 1
+                    return None, None
+                self.stats['allocs'] += 1
+                self.stats['alloc_s'] += time.perf_counter() - t0
+                self.total += size
+                self.arenas.append([base, size, [[0, size]]])
+                hit = self._take(n)
+        ai, off = hit
+        return self.arenas[ai][0] + off, (ai, off, n)
 
     def empty(self, shape, dtype=np.float64):
         import weakref
         dtype = np.dtype(dtype)
-        nbytes = int(np.prod(shape)) * dtype.itemsize
-        if nbytes == 0 or nbytes > self.MAX_SINGLE:
+        count = int(np.prod(shape))
+        nbytes = count * dtype.itemsize
+        if nbytes == 0:
             return np.empty(shape, dtype=dtype)
-        size = self._bucket(nbytes)
-        addr = None
-        with self.lock:
-            # exact bucket first, else the smallest pooled buffer that is large enough and at most twice the request
-            # (page-locking a fresh buffer costs ~0.3 ms per MB: far more than carrying some slack)
-            cands = [sz for sz, lst in self.free.items() if lst and size <= sz <= 2 * size]
-            if cands:
-                size = min(cands)
-                addr = self.free[size].pop()
-                self.pooled -= size
+        addr, blk = self.reserve(nbytes)
         if addr is None:
-            p = _vp()
-            try:
-                check(lib().mpb_host_alloc(ctx(), size, C.byref(p)))
-            except RuntimeError:
-                return np.empty(shape, dtype=dtype)
-            addr = p.value
-        buf = (C.c_char * size).from_address(addr)
-        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        weakref.finalize(buf, self._release, addr, size)
+            return np.empty(shape, dtype=dtype)
+        buf = (C.c_char * nbytes).from_address(addr)
+        arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+        weakref.finalize(buf, self._give, *blk)
         return arr
-
-    def _release(self, addr, size):
-        with self.lock:
-            if self.pooled + size <= self.MAX_POOLED:
-                self.free.setdefault(size, []).append(addr)
-                self.pooled += size
-                return
-        try:
-            lib().mpb_host_free(ctx(), _vp(addr))
-        except Exception:
-            pass
 
 
 pinned = _PinnedPool()

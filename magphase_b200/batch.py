@@ -137,12 +137,16 @@ def run_waveform_generation(tokens, in_feats_dir, out_syn_dir, mag_dim, phase_di
 
 
 def run_chain_stream(batches, fs, fft_len=None, mag_dim=60, phase_dim=45, b_out_hpf=False, n_workers=2, seed=0,
-                     sig_as_pcm16=True, out_dtype=np.float32, keep_outputs=False):
+                     sig_as_pcm16=True, out_dtype=np.float32, keep_outputs=False, n_inflight=None):
     """In-memory streaming driver: analysis_compressed -> synthesis_from_compressed for a sequence of batches, each batch a
     list of (v_sig, v_pm_smpls, v_voi).  ``n_workers`` host threads take the batches round-robin; every worker owns a
     private library context on the GPU (``_lib.set_thread_slot``), so the NumPy bookkeeping, the PCIe copies and the kernels
     of different batches overlap -- what the reference gets from one forked process per utterance (src/libutils.py:32-63).
     The noise of batch k comes from ``np.random.RandomState(seed + k)`` (independent of which worker runs it).
+    ``n_inflight`` (default: no limit) is an optional admission gate of the device calls (``_lib.set_device_gate``).
+    Measured on a B200 (128 x 5 s utterances per batch, PCM16 in / float32 out): 1 / 2 / 3 / 4 / 6 workers give 8.5 / 14.5 /
+    15.7 / 17.3 / 17.6 M frames/s; a gate below the worker count never helped (one call in flight keeps the GPU busy only
+    about half of the time: the first group's upload and the last group's download are not covered).
     Returns {'utterances', 'frames', 'seconds'} (+ 'outputs': per batch (features, waveforms) when keep_outputs)."""
     from . import _lib
     batches = list(batches)
@@ -150,8 +154,10 @@ def run_chain_stream(batches, fs, fft_len=None, mag_dim=60, phase_dim=45, b_out_
 
     def work(w):
         _lib.set_thread_slot(w)
+        outs = ys = None
         for k in range(w, len(batches), n_workers):
             b = batches[k]
+            del outs, ys                 # the previous batch's page-locked result blocks go back to the pool first
             sigs = [u[0] for u in b]
             if sig_as_pcm16 and all(np.asarray(x).dtype != np.int16 for x in sigs):
                 sigs = [np.round(np.asarray(x) * 32768.0).astype(np.int16) for x in sigs]
@@ -162,10 +168,14 @@ def run_chain_stream(batches, fs, fft_len=None, mag_dim=60, phase_dim=45, b_out_
             frames = sum(o[4].size for o in outs)
             results[k] = (frames, ([tuple(np.array(a) for a in o[:5]) for o in outs], [np.array(y) for y in ys]) if keep_outputs else None)
 
+    prev_gate = _lib.set_device_gate(n_inflight if n_inflight and n_inflight < n_workers else None)
     t0 = time.perf_counter()
-    with cf.ThreadPoolExecutor(max_workers=n_workers) as pool:
-        for f in [pool.submit(work, w) for w in range(n_workers)]:
-            f.result()
+    try:
+        with cf.ThreadPoolExecutor(max_workers=n_workers) as pool:
+            for f in [pool.submit(work, w) for w in range(n_workers)]:
+                f.result()
+    finally:
+        _lib.set_device_gate(prev_gate)
     r = dict(utterances=sum(len(b) for b in batches), frames=sum(x[0] for x in results), seconds=time.perf_counter() - t0)
     if keep_outputs:
         r['outputs'] = [x[1] for x in results]

@@ -102,7 +102,7 @@ static int syn_reserve(mpb_syn* s, int in_dtype, int64_t n_rows, int64_t nfrm, i
     CU(s->unw_flags.need((size_t)n_rows / 64 + n_ranges + 2));
     if (s->ut_mag) {
         for (int i = 0; i < 3; ++i) CU(s->unw_x[i].need(unwarp_tc_feature_bytes(n_rows)));
-        CU(s->unw_idx.need(sizeof(int32_t) * (2 * (size_t)n_rows + 4 * ((size_t)n_ranges + 1))));
+        CU(s->unw_idx.need(sizeof(int32_t) * (2 * (size_t)n_rows + 4 * ((size_t)n_ranges + 1) + 8)));
     }
     *cvt_pitch = 0;
     if (in_dtype == MPB_F64) {
@@ -146,7 +146,7 @@ static int syn_enqueue_range(mpb_syn* s, cudaStream_t st, const void* mag_mel, c
     if (s->ut_mag) {
         // tensor-core product: compaction of the frames that need their phase rows, split operands, tiles (mpb_mel_unwarp_tc.cu)
         int32_t* vidx = (int32_t*)s->unw_idx.p + r.row_a;
-        int32_t* cidx = (int32_t*)s->unw_idx.p + (size_t)(s->unw_idx.cap / sizeof(int32_t) / 2) + r.row_a;
+        int32_t* cidx = (int32_t*)s->unw_idx.p + (((size_t)(s->unw_idx.cap / sizeof(int32_t) / 2) + 3) & ~(size_t)3) + r.row_a;
         int32_t* cnt = (int32_t*)s->unw_idx.p + s->unw_idx.cap / sizeof(int32_t) - 4 - r.ordinal;
         u.ut_mag = s->ut_mag; u.ut_ph = s->ut_ph;
         for (int i = 0; i < 3; ++i) u.xs[i] = (float*)s->unw_x[i].p + (size_t)r.row_a * 128;

@@ -161,6 +161,7 @@ class CompressedPlan:
         self.mt_pos = int(st[2])
         self.d_noise = torch.empty(max(self.n_noise, 1), dtype=torch.float32, device=self.device)
         self.draw_noise = True
+        self._side = None
         # the compressed features live in HBM between the two halves
         self.d_mel = (torch.empty((self.nfrm, mag_dim), dtype=torch.float32, device=self.device),
                       torch.empty((self.nfrm, phase_dim), dtype=torch.float32, device=self.device),
@@ -189,11 +190,39 @@ class CompressedPlan:
         rs.set_state(('MT19937', self.mt_key.copy(), self.mt_pos, 0, 0.0))
         return [rs.uniform(-1, 1, n) for n in self.l_ns_len]
 
+    def draw(self):
+        """Enqueues the MT19937 draw of the whole batch's aperiodic noise on the current stream."""
+        _lib.check(_lib.lib().mpb_mt19937_fill_dev(self.ctx, _stream(), _lib.ptr(self.mt_key), self.mt_pos, self.n_noise, -1.0,
+                                                   1.0, _dp(self.d_noise), MPB_F32))
+
+    def chain(self, d_sig, compute=MPB_F64, mid_event=None):
+        """analysis -> synthesis with the noise draw on a side stream NEXT TO the analysis half: the draw is one wave of
+        latency-bound CTAs (the twister's recurrence), the analysis kernels fill the rest of every SM meanwhile.  The draw
+        does not depend on the signal, only on NumPy's generator state, so the result is the same as analysis() followed by
+        synthesis()."""
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._ev_free, self._ev_noise = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_free.record(main)                 # everything enqueued so far (the previous synthesis reads d_noise)
+        self._side.wait_event(self._ev_free)
+        with torch.cuda.stream(self._side):
+            self.draw()
+            self._ev_noise.record(self._side)
+        self.analysis(d_sig, compute=compute)
+        if mid_event is not None:
+            mid_event.record(main)
+        main.wait_event(self._ev_noise)
+        keep, self.draw_noise = self.draw_noise, False
+        try:
+            return self.synthesis()
+        finally:
+            self.draw_noise = keep
+
     def synthesis(self, d_mel=None):
         m = self.d_mel if d_mel is None else d_mel
         if self.draw_noise:
-            _lib.check(_lib.lib().mpb_mt19937_fill_dev(self.ctx, _stream(), _lib.ptr(self.mt_key), self.mt_pos, self.n_noise, -1.0,
-                                                       1.0, _dp(self.d_noise), MPB_F32))
+            self.draw()
         _lib.check(_lib.lib().mpb_synthesis_compressed_dev(
             self.syn.handle, _stream(), _dp(m[0]), _dp(m[1]), _dp(m[2]), MPB_F32, self.nfrm, _dp(self.d_need),
             _dp(self.d_noise), self.n_noise, C.byref(self.frames), _dp(self.d_runs), self.n_runs, 0, _dp(self.d_out),

@@ -546,10 +546,11 @@ def analysis_compressed_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None, mag_di
     sig_lens = np.ascontiguousarray([s.size for s in sigs], dtype=np.int64)
     n = centre.size
     o_mag, o_real, o_imag = (_lib.pinned.empty((n, d), dtype=out_dtype) for d in (mag_dim, phase_dim, phase_dim))
-    _lib.check(_lib.lib().mpb_analysis_compressed_hostv2(
-        plan.handle, sig_ptrs, sig_code, _lib.ptr(sig_lens), len(sigs), _lib.ptr(centre), _lib.ptr(left), _lib.ptr(right),
-        _lib.ptr(voi8), n, _lib.ptr(o_mag), _lib.ptr(o_real), _lib.ptr(o_imag),
-        _lib.MPB_F32 if out_dtype == np.dtype(np.float32) else _lib.MPB_F64))
+    with _lib.device_gate():
+        _lib.check(_lib.lib().mpb_analysis_compressed_hostv2(
+            plan.handle, sig_ptrs, sig_code, _lib.ptr(sig_lens), len(sigs), _lib.ptr(centre), _lib.ptr(left), _lib.ptr(right),
+            _lib.ptr(voi8), n, _lib.ptr(o_mag), _lib.ptr(o_real), _lib.ptr(o_imag),
+            _lib.MPB_F32 if out_dtype == np.dtype(np.float32) else _lib.MPB_F64))
     out, a = [], 0
     for u in range(len(l_sig)):
         b = a + lefts[u].size
@@ -940,10 +941,12 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
     hpf_sos = output_hpf_sos(fs) if b_out_hpf else None
     out = _lib.pinned.empty(int(out_off[-1]), dtype=out_dtype)
     code = lambda dt: _lib.MPB_F32 if np.dtype(dt) == np.dtype(np.float32) else _lib.MPB_F64
-    _lib.check(_lib.lib().mpb_synthesis_compressed_host2(
-        plan.handle, _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), code(feat_np), mag.shape[0], _lib.ptr(need), _lib.ptr(noise),
-        int(sum(l_ns_len)), _lib.ptr(mt_key), C.byref(mt_pos) if mt_pos is not None else None, C.byref(fr),
-        {'magphase': 0, 'linear': 1, 'min_phase': 2}[per_phase_type], _lib.ptr(hpf_sos), _lib.ptr(out), code(out_dtype), out.size))
+    with _lib.device_gate():
+        _lib.check(_lib.lib().mpb_synthesis_compressed_host2(
+            plan.handle, _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), code(feat_np), mag.shape[0], _lib.ptr(need),
+            _lib.ptr(noise), int(sum(l_ns_len)), _lib.ptr(mt_key), C.byref(mt_pos) if mt_pos is not None else None, C.byref(fr),
+            {'magphase': 0, 'linear': 1, 'min_phase': 2}[per_phase_type], _lib.ptr(hpf_sos), _lib.ptr(out), code(out_dtype),
+            out.size))
     if mt_key is not None:
         (rng if rng is not None else np.random).set_state((np_state[0], mt_key, int(mt_pos.value), np_state[3], np_state[4]))
     l_out = [out[out_off[u]:out_off[u + 1]] for u in range(n_utt)]

@@ -21,6 +21,12 @@ SHORT = [  # (regex on the demangled name, bench.py kernel key, file stem)
     (r'k_analysis<double, float, float, \d+, 3>', 'k_analysis<logp>', 'k_analysis_logp'),
     (r'k_analysis<float, float, double, \d+, 2>', 'k_analysis<noise_logsq>', 'k_analysis_noise_logsq'),
     (r'k_analysis<double, float, float, \d+, 0>', 'k_analysis', 'k_analysis'),
+    (r'k_mel_warp_tc', 'k_mel_warp_tc', 'k_mel_warp_tc'),
+    (r'k_mel_cos', 'k_mel_cos', 'k_mel_cos'),
+    (r'k_mel_unwarp_tc', 'k_mel_unwarp_tc', 'k_mel_unwarp_tc'),
+    (r'k_unwarp_prep', 'k_mel_unwarp_tc', 'k_unwarp_prep'),                     # bench.py brackets it with the product
+    (r'k_mt19937_stream', 'k_mt19937_stream+k_mt_to_uniform', 'k_mt19937_stream'),
+    (r'k_mt_to_uniform', 'k_mt19937_stream+k_mt_to_uniform', 'k_mt_to_uniform'),
     (r'k_mel_gemm', 'k_mel_gemm', 'k_mel_gemm'),
     (r'k_mel_finish', 'k_mel_finish', 'k_mel_finish'),
     (r'k_mel_unwarp', 'k_mel_unwarp', 'k_mel_unwarp'),
@@ -78,19 +84,24 @@ def opcode_mix(block, top=16):
 
 
 def main(src_dir, dst_dir, frames):
+    """One bench step per report: the rows up to and including the first launch of the chain's last kernel.  DRAM bytes and
+    time are SUMMED per bench.py kernel key over that step (a key can cover several launches: the two pipeline groups of
+    the analysis half, the preparation kernels in front of the un-warp product); the per-kernel text file is written for
+    the longest launch of each kernel."""
     os.makedirs(dst_dir, exist_ok=True)
-    traffic, times = {}, {}
-    for rep, prefix in (('prof_compressed.ncu-rep', 'c_'), ('prof_lossless.ncu-rep', 'l_')):
+    traffic, times, launches = defaultdict(float), defaultdict(float), defaultdict(int)
+    for rep, prefix, last in (('prof_compressed.ncu-rep', 'c_', 'k_synthesis_compressed'),
+                              ('prof_lossless.ncu-rep', 'l_', 'k_synthesis_lossless')):
         path = os.path.join(src_dir, rep)
         if not os.path.exists(path):
             continue
         hdr, units, rows = raw_page(path)
         blocks = sass_blocks(path)
         per_kernel = len(blocks) // max(len(rows), 1) or 1          # the source page repeats every kernel per view
+        best = {}
         for k, vals in enumerate(rows):
             name = vals[hdr.index('Kernel Name')]
             key, stem = classify(name)
-            lines = ['== ' + name[:150]]
             get = {}
             for i, h in enumerate(hdr):
                 try:
@@ -98,24 +109,39 @@ def main(src_dir, dst_dir, frames):
                 except ValueError:
                     fv = 0.0
                 get[h] = (fv, units[i])
+
+            def to_bytes(m):
+                v, u = get[m]
+                return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
+            v, u = get['gpu__time_duration.sum']
+            us = v * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3}.get(u, 1.0)
+            if key:
+                traffic[key] += to_bytes('dram__bytes_read.sum') + to_bytes('dram__bytes_write.sum')
+                times[key] += us
+                launches[key] += 1
+            if stem not in best or us > best[stem][0]:
+                best[stem] = (us, k, name, vals)
+            if last in name:
+                break
+        for stem, (us, k, name, vals) in best.items():
+            lines = ['== ' + name[:150]]
+            for i, h in enumerate(hdr):
+                try:
+                    fv = float(vals[i].replace(',', ''))
+                except ValueError:
+                    fv = 0.0
                 if h in WANT or (h.startswith('smsp__average_warps_issue_stalled') and
                                  h.endswith('per_issue_active.ratio') and fv > 0.3):
                     lines.append('  %-78s %-14s %s' % (h, units[i], vals[i]))
             lines += ['', '-- SASS opcode mix --'] + opcode_mix(blocks[k * per_kernel])
             open(os.path.join(dst_dir, prefix + stem + '.txt'), 'w').write('\n'.join(lines) + '\n')
-
-            def to_bytes(m):
-                v, u = get[m]
-                return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
-            if key:
-                traffic[key] = (to_bytes('dram__bytes_read.sum') + to_bytes('dram__bytes_write.sum')) / frames
-                v, u = get['gpu__time_duration.sum']
-                times[key] = v * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3}.get(u, 1.0)
-            print(prefix + stem, times.get(key))
-    json.dump({'source': 'ncu --set full --clock-control none, one launch over %d frames (bench.py --utts 32), '
-                         'dram__bytes_read.sum + dram__bytes_write.sum; see the per-kernel .txt files' % frames,
-               'frames_per_captured_launch': frames, 'dram_bytes_per_frame': traffic,
-               'ncu_us_per_captured_launch': times}, open(os.path.join(dst_dir, 'traffic_per_frame.json'), 'w'), indent=1)
+            print(prefix + stem, '%.1f us' % us)
+    json.dump({'source': 'ncu --set full --clock-control none, ONE bench step over %d frames (bench.py --utts 32), '
+                         'dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of each kernel key in that '
+                         'step; see the per-kernel .txt files' % frames,
+               'frames_per_captured_step': frames, 'launches_per_step': dict(launches),
+               'dram_bytes_per_frame': {k: v / frames for k, v in traffic.items()},
+               'ncu_us_per_captured_step': dict(times)}, open(os.path.join(dst_dir, 'traffic_per_frame.json'), 'w'), indent=1)
     for f in ('launches_compressed.csv', 'launches_lossless.csv'):
         p = os.path.join(src_dir, f)
         if os.path.exists(p):
