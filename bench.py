@@ -650,11 +650,26 @@ def run_extras(a, torch, _lib, mp, CompressedPlan, make_lossless, geom, d_sig, u
         lstep()
     prof = _lib.profile_end(local_rank)
     lb = lp.analysis_bytes(F32, F32) + lp.synthesis_bytes(F32, F32)
+    # per kernel: its half of the chain's algorithmic bytes against the measured copy bandwidth, and one N-point real FFT per
+    # frame (2.5 N log2 N flops) against the measured FMA peak of the pipe it runs on (float64 analysis, float32 synthesis)
+    fpk = {'fp32': _lib.measure_fma_peak(_lib.MPB_F32, local_rank), 'fp64': _lib.measure_fma_peak(_lib.MPB_F64, local_rank)}
+    fl = lp.nfrm * 2.5 * FFT_LEN * np.log2(FFT_LEN)
+    kb = {'k_analysis': (lp.analysis_bytes(F32, F32), 'fp64'), 'k_synthesis_lossless': (lp.synthesis_bytes(F32, F32), 'fp32')}
+    lk = []
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        per = v[1] / 2
+        rec = dict(name=k, ms_per_step=per)
+        if k in kb and per > 0:
+            rec.update(algorithmic_bytes_per_step=int(kb[k][0]), gbs=kb[k][0] / (per * 1e-3) / 1e9,
+                       frac=kb[k][0] / (per * 1e-3) / 1e9 / peak,
+                       compute={'pipe': kb[k][1], 'achieved_tflops': fl / (per * 1e-3) / 1e12,
+                                'frac': fl / (per * 1e-3) / 1e12 / fpk[kb[k][1]]})
+        lk.append(rec)
     ex['lossless'] = {'workload': 'analysis_lossless -> synthesis_from_lossless, %d x %.0f s utterances, float32 features in HBM' % (n_l, a.dur),
                       'value': lp.nfrm / (ms * 1e-3), 'unit': 'frames/s', 'ms_per_step': ms,
                       'chain_algorithmic_bytes_per_step': int(lb), 'chain_gbs': lb / (ms * 1e-3) / 1e9,
                       'frac_of_hbm': lb / (ms * 1e-3) / 1e9 / peak,
-                      'kernels': [dict(name=k, ms_per_step=v[1] / 2) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])]}
+                      'kernels': lk}
     del lp, lstep
     torch.cuda.empty_cache()
     # ---- config 3: feature extraction for TTS (analysis only) ----

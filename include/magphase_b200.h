@@ -276,6 +276,12 @@ int mpb_synthesis_compressed_dev(mpb_syn* plan, void* stream,
                                  int64_t n_rows, const uint8_t* need_ph, const float* noise, int64_t n_noise,
                                  const mpb_syn_frames* frames, const int32_t* runs, int32_t n_runs, int per_linear,
                                  void* out, int out_dtype, int64_t n_out);
+/* Optional pre-stage: the noise half of the synthesis (windowed noise frames -> FFT -> gain statistics + stored spectra,
+ * src/magphase.py:886-903) enqueued on its own stream; it needs the noise and the frame geometry, not the features.  The
+ * next mpb_synthesis_compressed_dev call of this plan with the same noise pointer and frame count skips that stage; the
+ * caller orders the two streams (event).                                                                     */
+int mpb_synthesis_noise_stage_dev(mpb_syn* plan, void* stream, const float* noise, int64_t n_noise,
+                                  const mpb_syn_frames* frames);
 int mpb_synthesis_compressed_host(mpb_syn* plan,
                                   const double* mag_mel, const double* real_mel, const double* imag_mel,
                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,

@@ -5,6 +5,7 @@ host in the reference) uploaded once; signals and features then stay in HBM betw
 synthesis.  Used by ``bench.py`` (device-timed ``value``) and by the sharded multi-GPU driver.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -162,6 +163,8 @@ class CompressedPlan:
         self.d_noise = torch.empty(max(self.n_noise, 1), dtype=torch.float32, device=self.device)
         self.draw_noise = True
         self._side = None
+        self.noise_stage_early = os.environ.get('MPB_NOISE_EARLY', '1') != '0'
+        self.side_high_priority = os.environ.get('MPB_SIDE_PRIO', '1') != '0'
         # the compressed features live in HBM between the two halves
         self.d_mel = (torch.empty((self.nfrm, mag_dim), dtype=torch.float32, device=self.device),
                       torch.empty((self.nfrm, phase_dim), dtype=torch.float32, device=self.device),
@@ -202,12 +205,16 @@ class CompressedPlan:
         synthesis()."""
         main = torch.cuda.current_stream()
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            self._side = torch.cuda.Stream(device=self.device, priority=-1 if self.side_high_priority else 0)
             self._ev_free, self._ev_noise = torch.cuda.Event(), torch.cuda.Event()
         self._ev_free.record(main)                 # everything enqueued so far (the previous synthesis reads d_noise)
         self._side.wait_event(self._ev_free)
         with torch.cuda.stream(self._side):
             self.draw()
+            if self.noise_stage_early:
+                # the noise frames' FFTs (float32 pipes) beside the signal frames' FFTs (float64 pipe): neither needs the other
+                _lib.check(_lib.lib().mpb_synthesis_noise_stage_dev(self.syn.handle, _stream(), _dp(self.d_noise), self.n_noise,
+                                                                    C.byref(self.frames)))
             self._ev_noise.record(self._side)
         self.analysis(d_sig, compute=compute)
         if mid_event is not None:
