@@ -278,7 +278,8 @@ def main():
     ap.add_argument('--analysis-compute', default='f64', choices=['f32', 'f64'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-rng-overlap', action='store_true', help='draw the noise on the main stream, before the synthesis half')
-    ap.add_argument('--e2e-workers', type=int, default=4, help='host threads (private contexts) of the end-to-end arm')
+    ap.add_argument('--e2e-workers', type=int, default=0,
+                    help='host threads (private contexts) of the end-to-end arm; 0 = 4')
     ap.add_argument('--no-extras', action='store_true', help='skip the sub-records (lossless chain, configs 3 / 4 / 5)')
     ap.add_argument('--stream-utts', type=int, default=2048, help='utterances per GPU of the streamed many-batch record (config 5)')
     ap.add_argument('--ola-target', type=int, default=32, help='frames per overlap-add run (device-timed arm)')
@@ -306,6 +307,10 @@ def main():
             os.sched_setaffinity(0, cpus[local_rank * per:(local_rank + 1) * per] or cpus)
         except OSError:
             pass
+    if a.e2e_workers <= 0:
+        # measured on 8 ranks x 4 cores: 4 workers with yielding waits (MPB_SYNC=block, the library's default under a
+        # one-process-per-GPU launcher) 32 M frames/s, 2 workers 12 M -- the workers mostly sleep on the device
+        a.e2e_workers = 4
     chain = ('analysis_compressed(mag=60, real=45, imag=45) -> synthesis_from_compressed(b_out_hpf=False)' if comp
              else 'analysis_lossless -> synthesis_from_lossless')
     workload = '%s chain: %s, %d x %.0f s synth48k-v1 utterances per GPU per step' % (a.workload, chain, a.utts, a.dur)
@@ -482,11 +487,13 @@ def main():
             e2e_step(True, n=e_steps)         # untimed pass of the same stream: every worker's context and pinned blocks exist
             barrier()
             pool0 = dict(_lib.pinned.stats)
+            c0 = time.process_time()
             t = time.perf_counter()
             e2e_step(True, n=e_steps)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t
             pool_stats.update({k: round(v - pool0[k], 4) for k, v in _lib.pinned.stats.items()})
+            pool_stats['host_cpu_ms_per_step'] = round(1e3 * (time.process_time() - c0) / e_steps, 2)   # all threads of this rank
             return (dt, ) + r
         e2e_step(narrow)
         barrier()
@@ -530,9 +537,11 @@ def main():
 
     # ---- reduce over ranks: max time, summed frames ----
     s64 = e2e64['seconds_per_step'] if e2e64 else 0.0
-    stats, counts = reduce_counters([total_ms, e_secs, ana_ms, syn_ms, s64], [plan.nfrm, e_frames], device=dev)
+    stats, counts = reduce_counters([total_ms, e_secs, ana_ms, syn_ms, s64], [plan.nfrm, e_frames, pool_stats.get('allocs', 0)],
+                                    device=dev)
     total_ms, e_secs, ana_ms, syn_ms, s64 = [float(x) for x in stats]
-    frames_all, e_frames_all = [float(x) for x in counts]
+    frames_all, e_frames_all, pool_allocs_all = [float(x) for x in counts]
+    pool_allocs_all = int(pool_allocs_all)
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -594,7 +603,9 @@ def main():
                    'parallelism': 'utterance-sharded x%d' % world},
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d),
                 'd2h_bytes_per_step': int(d2h), 'utts_per_gpu_per_step': len(e_utts), 'api': api,
-                'frac_of_value': e2e_value / value if value > 0 else None, 'steps': e_steps,
+                'frac_of_value': e2e_value / value if value > 0 else None, 'steps': e_steps, 'workers': a.e2e_workers,
+                'host_cpu_ms_per_step': pool_stats.pop('host_cpu_ms_per_step', None),
+                'page_lock_calls_during_timed_steps_all_ranks': pool_allocs_all,
                 'pinned_pool_during_timed_steps': pool_stats or None},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s',

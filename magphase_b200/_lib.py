@@ -295,6 +295,24 @@ class _PinnedPool:
         ai, off = hit
         return self.arenas[ai][0] + off, (ai, off, n)
 
+    def ensure(self, nbytes):
+        """Locks arenas now until the pool holds at least nbytes (capped by MAX_TOTAL): a streaming driver that knows its
+        peak demand pays for page-locking before its loop instead of at a timing-dependent moment inside it."""
+        while True:
+            with self.lock:
+                if self.total >= min(int(nbytes), self.MAX_TOTAL) or self.total + self.ARENA > self.MAX_TOTAL:
+                    return
+            t0 = time.perf_counter()
+            try:
+                base = self._alloc(self.ARENA)
+            except RuntimeError:
+                return
+            with self.lock:
+                self.stats['allocs'] += 1
+                self.stats['alloc_s'] += time.perf_counter() - t0
+                self.total += self.ARENA
+                self.arenas.append([base, self.ARENA, [[0, self.ARENA]]])
+
     def empty(self, shape, dtype=np.float64):
         import weakref
         dtype = np.dtype(dtype)

@@ -168,6 +168,10 @@ def run_chain_stream(batches, fs, fft_len=None, mag_dim=60, phase_dim=45, b_out_
             frames = sum(o[4].size for o in outs)
             results[k] = (frames, ([tuple(np.array(a) for a in o[:5]) for o in outs], [np.array(y) for y in ys]) if keep_outputs else None)
 
+    # page-lock the result arenas up front: every worker holds the features and the waveform of one batch (float32: 150
+    # values per frame + one per sample), twice that for the order in which blocks of different sizes come and go
+    peak = max((sum(4 * (np.size(u[0]) + 150 * np.size(u[1])) for u in b) for b in batches), default=0)
+    _lib.pinned.ensure(2 * n_workers * peak * (np.dtype(out_dtype).itemsize // 4 or 1))
     prev_gate = _lib.set_device_gate(n_inflight if n_inflight and n_inflight < n_workers else None)
     t0 = time.perf_counter()
     try:

@@ -431,7 +431,7 @@ int mpb_analysis_compressed_hostv2(mpb_mel* m, const void* const* sigs, int sig_
                                          m->small[4].p, on_group);
     const auto t2 = now();
     // drain all three stages even after an error: host and staging buffers must not be reused under a live copy
-    cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
+    cudaError_t e1 = host_wait(ctx, s_in), e2 = host_wait(ctx, s_cmp), e3 = host_wait(ctx, s_out);
     if (rc != MPB_OK) return rc;
     CU(e1); CU(e2); CU(e3);
     if (trace)

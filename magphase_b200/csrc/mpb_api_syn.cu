@@ -503,8 +503,8 @@ int mpb_synthesis_compressed_host2(mpb_syn* s, const void* mag_mel_v, const void
         }
     }
     // drain every stage, also after an error: noise32 / runs / the staging blocks must outlive the copies
-    cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_cmp), e3 = cudaStreamSynchronize(s_out);
-    cudaError_t e4 = cudaStreamSynchronize(ctx->stream_aux);
+    cudaError_t e1 = host_wait(ctx, s_in), e2 = host_wait(ctx, s_cmp), e3 = host_wait(ctx, s_out);
+    cudaError_t e4 = host_wait(ctx, ctx->stream_aux);
     if (rc != MPB_OK) return rc;
     CU(e1); CU(e2); CU(e3); CU(e4);
     if (mt_fin) {

@@ -70,6 +70,8 @@ struct mpb_ctx {
     cudaStream_t stream_in = nullptr, stream_out = nullptr;   // host->device / device->host copies of the pipelined entry points
     cudaStream_t stream_aux = nullptr;             // the MT19937 noise stream runs here, beside the compute stream
     std::vector<cudaEvent_t> ev_pool;              // timing-disabled events (pipeline hand-offs)
+    std::vector<cudaEvent_t> ev_block;             // blocking-sync events of host_wait()
+    std::mutex ev_mu;
     PinnedBuf desc_stage;                          // page-locked staging of descriptor arrays
     PinnedBuf mt_fin;                              // page-locked landing zone of the MT19937 state read-back
     std::map<int, void*> tw32, tw64;               // fft_len -> twiddle table exp(-2 pi i j / N), j < N/2
@@ -93,6 +95,37 @@ inline cudaEvent_t get_event(mpb_ctx* ctx) {
 }
 inline void put_event(mpb_ctx* ctx, cudaEvent_t e) { if (e) ctx->ev_pool.push_back(e); }
 
+// Host-side wait for a stream.  cudaStreamSynchronize spins (the runtime's default when there are more cores than contexts):
+// a worker thread that drains a 5 ms pipeline burns a core the whole time, and with one process per GPU and a few cores per
+// process the staging threads then starve (measured at 8 ranks x 4 cores: end-to-end throughput per rank fell to a quarter).
+// MPB_SYNC=block (default when a launcher runs several processes per host, LOCAL_WORLD_SIZE > 1): record an event created
+// with cudaEventBlockingSync and sleep on it.  MPB_SYNC=spin forces the runtime's behaviour.
+inline bool sync_blocks() {
+    static const int mode = [] {
+        if (const char* e = getenv("MPB_SYNC")) return (e[0] == 'b' || e[0] == 'B') ? 1 : 0;
+        if (const char* w = getenv("LOCAL_WORLD_SIZE")) return atoi(w) > 1 ? 1 : 0;
+        return 0;
+    }();
+    return mode == 1;
+}
+inline cudaError_t host_wait(mpb_ctx* ctx, cudaStream_t st) {
+    if (!sync_blocks()) return cudaStreamSynchronize(st);
+    cudaEvent_t e = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->ev_mu);
+        if (!ctx->ev_block.empty()) { e = ctx->ev_block.back(); ctx->ev_block.pop_back(); }
+    }
+    if (!e) {
+        cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync);
+        if (r != cudaSuccess) return r;
+    }
+    cudaError_t r = cudaEventRecord(e, st);
+    if (r == cudaSuccess) r = cudaEventSynchronize(e);
+    std::lock_guard<std::mutex> lk(ctx->ev_mu);
+    ctx->ev_block.push_back(e);
+    return r;
+}
+
 // Scope guard of the pipelined *_host entry points: whatever path leaves the function (CU() returns on any CUDA error), the
 // four streams are drained before host / staging memory that live copies still read goes out of scope, and the hand-off
 // events go back to the pool.
@@ -101,8 +134,8 @@ struct PipelineDrain {
     std::vector<cudaEvent_t>* evs[2] = {nullptr, nullptr};
     explicit PipelineDrain(mpb_ctx* c, std::vector<cudaEvent_t>* a = nullptr, std::vector<cudaEvent_t>* b = nullptr) : ctx(c) { evs[0] = a; evs[1] = b; }
     ~PipelineDrain() {
-        cudaStreamSynchronize(ctx->stream_in); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream_out);
-        cudaStreamSynchronize(ctx->stream_aux);
+        host_wait(ctx, ctx->stream_in); host_wait(ctx, ctx->stream); host_wait(ctx, ctx->stream_out);
+        host_wait(ctx, ctx->stream_aux);
         for (auto* v : evs)
             if (v) { for (auto e : *v) put_event(ctx, e); v->clear(); }
     }

@@ -66,3 +66,16 @@ def test_budget_spent_falls_back_to_pageable_memory():
     big = p.empty(3 << 20, np.uint8)                              # larger than the whole budget
     assert p.stats['pageable'] == 2 and big.size == 3 << 20
     assert a.size == b.size
+
+
+def test_ensure_reserves_whole_arenas_up_front():
+    p = make_pool(arena_mb=1, max_mb=8)
+    p.ensure(int(2.5 * (1 << 20)))
+    assert p.stats['allocs'] == 3 and p.total == 3 << 20
+    p.ensure(1 << 20)                                             # already there
+    assert p.stats['allocs'] == 3
+    a = [p.empty(900000, np.uint8) for _ in range(3)]
+    assert p.stats['allocs'] == 3 and p.stats['reuses'] == 3
+    p.ensure(100 << 20)                                           # capped by the budget
+    assert p.total == 8 << 20
+    del a
