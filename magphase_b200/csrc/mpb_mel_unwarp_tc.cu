@@ -16,11 +16,14 @@
 //   k_unwarp_prep    one warp per frame: feature rows -> [row][hi(64) | lo(64)] float32 (zero padded K), the rows of the two
 //                    phase streams compacted to the frames that need them; the Nyquist bin of the magnitude stream (bin
 //                    H-1 = 16 x 128 + 1 would cost a whole 128-bin tile) is a 60-term dot product done here.
-//   k_mel_unwarp_tc  persistent CTAs, 320 threads.  Work item = (stream, 128-bin tile, chunk of 128-frame tiles): the U^T
-//                    tile is loaded once per item, the feature tiles stream through a 2-stage ring (2-D tiled TMA, 128-byte
-//                    swizzle = the UMMA K-major layout), the accumulators are double buffered in TMEM.
+//   k_mel_unwarp_tc  persistent CTAs, 320 threads.  Work item = (stream, 128-frame tile, group of 4 bin tiles): the feature
+//                    tile is loaded once per item, the U^T tiles (1 MB in all: L2 resident) stream through a 2-stage ring
+//                    (2-D tiled TMA, 128-byte swizzle = the UMMA K-major layout), the accumulators are double buffered in
+//                    TMEM.  Items that run at the same time complete whole output rows together (DRAM page locality).
 //                    warp 8: TMA producer, warp 9: MMA issuer (both warp-uniform, one elected lane issues),
 //                    warps 0-7: epilogue -- tcgen05.ld, exp (magnitude stream), coalesced streaming stores.
+#include <stdlib.h>
+
 #include "mpb_kernels.h"
 #include "mpb_tc.cuh"
 
@@ -41,7 +44,7 @@ constexpr int EPI_WARPS = 8;                  // two per TMEM lane quadrant: col
 constexpr int U_TMA_WARP = 8, U_MMA_WARP = 9;
 constexpr int U_THREADS = 10 * 32;
 constexpr int U_SMEM = 1024 + OPND + U_ST * OPND + 128 * 4 + 256;
-constexpr int CHUNK = 24;                     // frame tiles per work item
+constexpr int IT_BT_DEFAULT = 4;              // bin tiles per work item (MPB_UNWARP_ITBT overrides: experiments)
 constexpr uint32_t U_TMEM = 256;              // 2 accumulators of 128 columns
 constexpr uint32_t U_IDESC = idesc_tf32(UB, UF);
 
@@ -49,6 +52,7 @@ struct UParams {
     int64_t nfrm; int n_bins[2]; int ksteps[2];          // bins / K steps of 8: magnitude, phase
     const int32_t* vidx; const int32_t* vcount;          // phase rows: rank -> frame, number of rows
     float* out[3]; int pitch[2];
+    int it_bt;                                           // bin tiles per work item
 };
 
 // features -> split operands (+ Nyquist bin of the magnitude stream)
@@ -154,10 +158,15 @@ k_mel_unwarp_tc(const __grid_constant__ CUtensorMap map_u_mag, const __grid_cons
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // (warp reductions: tell the compiler these loaded values are warp-uniform, see mpb_mel_warp_tc.cu)
     const int64_t nv = p.vcount ? (int64_t)__reduce_max_sync(0xffffffffu, (unsigned)*p.vcount) : 0;
+    // Work item = (stream, 128-frame tile, group of IT_BT bin tiles): the frame tile's features stay in shared memory, the U^T
+    // tiles of the group stream through the ring.  Neighbouring items (= CTAs running at the same time) are the bin groups of
+    // ONE frame tile, so whole 8 KB output rows are written within a short window: the stores of a 128-bin tile are 512-byte
+    // pieces of 128 different rows, and DRAM wants its pages written while they are open.
     const int ft_mag = (int)((p.nfrm + UF - 1) / UF), ft_ph = (int)((nv + UF - 1) / UF);
-    const int ch_mag = (ft_mag + CHUNK - 1) / CHUNK, ch_ph = (ft_ph + CHUNK - 1) / CHUNK;
     const int bt_mag = (p.n_bins[0] + UB - 1) / UB, bt_ph = (p.n_bins[1] + UB - 1) / UB;
-    const int items_mag = bt_mag * ch_mag, items_ph = bt_ph * ch_ph;
+    const int IT_BT = p.it_bt;
+    const int bg_mag = (bt_mag + IT_BT - 1) / IT_BT, bg_ph = (bt_ph + IT_BT - 1) / IT_BT;
+    const int items_mag = ft_mag * bg_mag, items_ph = ft_ph * bg_ph;
     const int n_items = items_mag + 2 * items_ph;
 
     if (tid == 0) {
@@ -177,79 +186,79 @@ k_mel_unwarp_tc(const __grid_constant__ CUtensorMap map_u_mag, const __grid_cons
     fence_after();
     const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
 
-    // item -> stream, bin tile, frame tiles [ft0, ft1).  Chunks of one bin tile are adjacent: neighbouring CTAs share the U^T tile in L2.
-    auto decode = [&](int item, int& stream, int& bt, int& ft0, int& ft1) {
-        if (item < items_mag) { stream = 0; bt = item / ch_mag; ft0 = (item % ch_mag) * CHUNK; ft1 = min(ft0 + CHUNK, ft_mag); }
+    // item -> stream, frame tile, bin tiles [bt0, bt1)
+    auto decode = [&](int item, int& stream, int& ft, int& bt0, int& bt1) {
+        if (item < items_mag) { stream = 0; ft = item / bg_mag; bt0 = (item % bg_mag) * IT_BT; bt1 = min(bt0 + IT_BT, bt_mag); }
         else {
             const int j = item - items_mag;
             stream = 1 + j / items_ph;
             const int k = j % items_ph;
-            bt = k / ch_ph; ft0 = (k % ch_ph) * CHUNK; ft1 = min(ft0 + CHUNK, ft_ph);
+            ft = k / bg_ph; bt0 = (k % bg_ph) * IT_BT; bt1 = min(bt0 + IT_BT, bt_ph);
         }
     };
 
     if (warp == U_TMA_WARP) {
-        // ---- TMA producer ----
+        // ---- TMA producer: a_s = the item's feature tile, b_s ring = U^T tiles ----
         uint32_t it = 0, item_n = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
-            int stream, bt, ft0, ft1;
-            decode(item, stream, bt, ft0, ft1);
+            int stream, ft, bt0, bt1;
+            decode(item, stream, ft, bt0, bt1);
             const CUtensorMap* mu = stream == 0 ? &map_u_mag : &map_u_ph;
             const CUtensorMap* mx = stream == 0 ? &map_x_mag : (stream == 1 ? &map_x_re : &map_x_im);
             mbar_wait(a_empty, (item_n & 1u) ^ 1u);
             if (elect_one()) {
                 mbar_expect_tx(a_full, OPND);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) tma_load_2d(a_s + q * ATOM, mu, q * 32, bt * UB, a_full);
+                for (int q = 0; q < 4; ++q) tma_load_2d(a_s + q * ATOM, mx, q * 32, ft * UF, a_full);
             }
             __syncwarp();
-            for (int ft = ft0; ft < ft1; ++ft, ++it) {
+            for (int bt = bt0; bt < bt1; ++bt, ++it) {
                 const uint32_t s = it % U_ST, n = it / U_ST;
                 mbar_wait(&b_empty[s], (n & 1u) ^ 1u);
                 if (elect_one()) {
                     mbar_expect_tx(&b_full[s], OPND);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) tma_load_2d(b_s + s * OPND + q * ATOM, mx, q * 32, ft * UF, &b_full[s]);
+                    for (int q = 0; q < 4; ++q) tma_load_2d(b_s + s * OPND + q * ATOM, mu, q * 32, bt * UB, &b_full[s]);
                 }
                 __syncwarp();
             }
         }
     } else if (warp == U_MMA_WARP) {
-        // ---- MMA issuer ----
+        // ---- MMA issuer: D[bins x frames] = U^T tile (ring, A operand) . X^T (resident, B operand) ----
         uint32_t it = 0, item_n = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
-            int stream, bt, ft0, ft1;
-            decode(item, stream, bt, ft0, ft1);
+            int stream, ft, bt0, bt1;
+            decode(item, stream, ft, bt0, bt1);
             const int ksteps = p.ksteps[stream == 0 ? 0 : 1];
             mbar_wait(a_full, item_n & 1u);
-            for (int ft = ft0; ft < ft1; ++ft, ++it) {
+            for (int bt = bt0; bt < bt1; ++bt, ++it) {
                 const uint32_t s = it % U_ST, n = it / U_ST, d = it & 1u, nd = it >> 1;
                 mbar_wait(&d_empty[d], (nd & 1u) ^ 1u);
                 mbar_wait(&b_full[s], n & 1u);
                 fence_after();
                 if (elect_one()) {
-                    const uint32_t a_lo32 = ((smem_u32(a_s) >> 4) & 0x3FFFu) | ((16u >> 4) << 16);
-                    const uint32_t b_lo32 = ((smem_u32(b_s + s * OPND) >> 4) & 0x3FFFu) | ((16u >> 4) << 16);
+                    const uint32_t x_lo32 = ((smem_u32(a_s) >> 4) & 0x3FFFu) | ((16u >> 4) << 16);
+                    const uint32_t u_lo32 = ((smem_u32(b_s + s * OPND) >> 4) & 0x3FFFu) | ((16u >> 4) << 16);
                     constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (LAYOUT_SW128 << 29);
                     const uint32_t dcol = tmem_base + d * UF;
                     // cross products first (see the header), then the main product; part: 0 = hi, 1 = lo
                     uint32_t acc = 0u;
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const int pa = pass == 0 ? 1 : 0, pb = pass == 1 ? 1 : 0;     // lo.hi, hi.lo, hi.hi
+                        const int pu = pass == 0 ? 1 : 0, px = pass == 1 ? 1 : 0;     // lo.hi, hi.lo, hi.hi
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             if (j < ksteps) {
                                 const uint32_t off = (uint32_t)(((j >> 2) * ATOM + (j & 3) * 32) >> 4);
-                                umma_ss(dcol, make_desc(a_lo32 + (uint32_t)((pa * 2 * ATOM) >> 4) + off, HI),
-                                        make_desc(b_lo32 + (uint32_t)((pb * 2 * ATOM) >> 4) + off, HI), U_IDESC, acc);
+                                umma_ss(dcol, make_desc(u_lo32 + (uint32_t)((pu * 2 * ATOM) >> 4) + off, HI),
+                                        make_desc(x_lo32 + (uint32_t)((px * 2 * ATOM) >> 4) + off, HI), U_IDESC, acc);
                                 acc = 1u;
                             }
                         }
                     }
                     umma_commit(&b_empty[s]);
                     umma_commit(&d_full[d]);
-                    if (ft == ft1 - 1) umma_commit(a_empty);
+                    if (bt == bt1 - 1) umma_commit(a_empty);
                 }
                 __syncwarp();
             }
@@ -259,25 +268,25 @@ k_mel_unwarp_tc(const __grid_constant__ CUtensorMap map_u_mag, const __grid_cons
         const int q = warp & 3, half = warp >> 2;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            int stream, bt, ft0, ft1;
-            decode(item, stream, bt, ft0, ft1);
+            int stream, ft, bt0, bt1;
+            decode(item, stream, ft, bt0, bt1);
             const int kind = stream == 0 ? 0 : 1;
-            const int bin = bt * UB + q * 32 + lane;
-            const bool bin_ok = bin < p.n_bins[kind];
             const int64_t nrows = stream == 0 ? p.nfrm : nv;
-            float* __restrict__ Y = p.out[stream] + bin;
             const int pitch = p.pitch[kind];
-            for (int ft = ft0; ft < ft1; ++ft, ++it) {
+            // element offset of every column's output row (-1: no such frame), once per item: identity rows for the magnitude
+            // stream, the compacted rank's frame for the phase streams
+            named_bar_sync(1, EPI_WARPS * 32);              // the previous item's stores are issued: off_s may be rewritten
+            if (tid < UF) {
+                const int64_t r = (int64_t)ft * UF + tid;
+                const int fr = r < nrows ? (stream == 0 ? (int)r : p.vidx[r]) : -1;
+                off_s[tid] = fr >= 0 ? fr * pitch : -1;
+            }
+            named_bar_sync(1, EPI_WARPS * 32);
+            for (int bt = bt0; bt < bt1; ++bt, ++it) {
                 const uint32_t d = it & 1u, nd = it >> 1;
-                // element offset of every column's output row (-1: no such frame): identity rows for the magnitude stream, the
-                // compacted rank's frame for the phase streams
-                named_bar_sync(1, EPI_WARPS * 32);          // the previous tile's stores are issued: off_s may be rewritten
-                if (tid < UF) {
-                    const int64_t r = (int64_t)ft * UF + tid;
-                    const int fr = r < nrows ? (stream == 0 ? (int)r : p.vidx[r]) : -1;
-                    off_s[tid] = fr >= 0 ? fr * pitch : -1;
-                }
-                named_bar_sync(1, EPI_WARPS * 32);
+                const int bin = bt * UB + q * 32 + lane;
+                const bool bin_ok = bin < p.n_bins[kind];
+                float* __restrict__ Y = p.out[stream] + bin;
                 mbar_wait_warp(&d_full[d], nd & 1u, lane);
                 fence_after();
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + d * UF + half * 64;
@@ -331,15 +340,18 @@ cudaError_t launch_mel_unwarp_tc(const UnwarpArgs& a, cudaStream_t st) {
     if (e == cudaSuccess) e = make_tensor_map_f32_2d(&m[1], a.ut_ph, XP, (uint64_t)rows_ph, XP, 32, 128);
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = make_tensor_map_f32_2d(&m[2 + i], a.xs[i], XP, (uint64_t)a.nfrm, XP, 32, 128);
     if (e != cudaSuccess) return e;
+    static const int it_bt = [] { const char* e = getenv("MPB_UNWARP_ITBT"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 64 ? v : IT_BT_DEFAULT; }();
     UParams p;
     p.nfrm = a.nfrm; p.n_bins[0] = nb_mag; p.n_bins[1] = a.HB;
     p.ksteps[0] = (a.n_mag + 7) / 8; p.ksteps[1] = (a.n_ph + 7) / 8;
     p.vidx = a.vidx; p.vcount = a.vcount;
+    p.it_bt = it_bt;
     p.out[0] = a.out_mag; p.out[1] = a.out_real; p.out[2] = a.out_imag; p.pitch[0] = a.HP; p.pitch[1] = a.HBP;
     e = cudaFuncSetAttribute(k_mel_unwarp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM);
     if (e != cudaSuccess) return e;
-    const int64_t ft = (a.nfrm + UF - 1) / UF, ch = (ft + CHUNK - 1) / CHUNK;
-    const int64_t items_max = ch * ((nb_mag + UB - 1) / UB + 2 * ((a.HB + UB - 1) / UB));
+    const int64_t ft = (a.nfrm + UF - 1) / UF;
+    const int64_t bt_m = (nb_mag + UB - 1) / UB, bt_p = (a.HB + UB - 1) / UB;
+    const int64_t items_max = ft * ((bt_m + it_bt - 1) / it_bt + 2 * ((bt_p + it_bt - 1) / it_bt));
     const int grid = (int)(items_max < a.num_sms ? items_max : a.num_sms);
     if (grid < 1) return cudaSuccess;
     k_mel_unwarp_tc<<<grid, U_THREADS, U_SMEM, st>>>(m[0], m[1], m[2], m[3], m[4], p);
