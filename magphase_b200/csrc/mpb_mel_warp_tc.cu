@@ -325,6 +325,7 @@ struct CosParams {
     const float* mc[3]; const double* ct[2]; int n_in[2]; int n_out[2];
     const int32_t* vidx; const int32_t* vcount; int64_t nfrm;
     void* out[3]; int out_f64;
+    int g_mag, g_ph;                       // CTAs of the magnitude stream / of each phase stream (grid = g_mag + 2 g_ph)
 };
 
 // One 128-row tile: NO = outputs per thread (8 threads across the outputs): 8 covers 64 outputs, 6 covers 48 (phase_dim 45).
@@ -386,21 +387,27 @@ __device__ __forceinline__ void cos_tile(const CosParams& p, int stream, int n_i
     }
 }
 
-// persistent: grid (x, 3 streams); a CTA stages its stream's cosine table once and walks over the row tiles x, x + gridDim.x, ...
+// persistent, 1-D grid: the first g_mag CTAs serve the magnitude stream, then g_ph CTAs per phase stream -- in proportion to
+// the streams' work (the magnitude stream has every frame and 60 x 60 terms per row, a phase stream the voiced frames and
+// 58 x 45: with the same number of CTAs per stream the magnitude CTAs did 59 % of the work on a third of the grid).  A CTA
+// stages its stream's cosine table once and walks over the row tiles i, i + g, ...
 __global__ void __launch_bounds__(CO_THREADS, 2)
 k_mel_cos(const CosParams p) {
     extern __shared__ __align__(16) uint8_t cos_smem[];
     double* ct_s = reinterpret_cast<double*>(cos_smem);                 // [64][64], zero padded
     double* mc_s = ct_s + 64 * 64;                                      // [CO_ROWS][CO_PITCH]
-    const int stream = blockIdx.y, kind = stream == 0 ? 0 : 1, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int stream = b < p.g_mag ? 0 : 1 + (b - p.g_mag) / p.g_ph;
+    const int idx = b < p.g_mag ? b : (b - p.g_mag) % p.g_ph, g = stream == 0 ? p.g_mag : p.g_ph;
+    const int kind = stream == 0 ? 0 : 1;
     const int64_t nrows = (stream == 0 || !p.vcount) ? p.nfrm : (int64_t)*p.vcount;
-    if ((int64_t)blockIdx.x * CO_ROWS >= nrows) return;
+    if ((int64_t)idx * CO_ROWS >= nrows) return;
     const int n_in = p.n_in[kind], n_out = p.n_out[kind];
     for (int i = tid; i < 64 * 64; i += CO_THREADS) {
         const int j = i >> 6, o = i & 63;
         ct_s[i] = (j < n_in && o < n_out) ? __ldg(p.ct[kind] + j * n_out + o) : 0.0;
     }
-    for (int64_t row0 = (int64_t)blockIdx.x * CO_ROWS; row0 < nrows; row0 += (int64_t)gridDim.x * CO_ROWS) {
+    for (int64_t row0 = (int64_t)idx * CO_ROWS; row0 < nrows; row0 += (int64_t)g * CO_ROWS) {
         if (n_out <= 48) cos_tile<6>(p, stream, n_in, n_out, row0, nrows, ct_s, mc_s, tid);
         else cos_tile<8>(p, stream, n_in, n_out, row0, nrows, ct_s, mc_s, tid);
     }
@@ -492,12 +499,20 @@ cudaError_t launch_mel_cos(const MelArgs& a, cudaStream_t st) {
     c.out[0] = a.out_mag; c.out[1] = a.out_real; c.out[2] = a.out_imag; c.out_f64 = a.out_dtype == MPB_F64 ? 1 : 0;
     const int cos_smem_bytes = 64 * 64 * 8 + CO_ROWS * CO_PITCH * 8;
     const int64_t tiles = (a.nfrm + CO_ROWS - 1) / CO_ROWS;
-    int gx = (2 * a.num_sms + 2) / 3;                                   // 3 streams x gx CTAs ~ two CTAs per SM
-    if (gx > tiles) gx = (int)tiles;
-    if (gx < 1) return cudaSuccess;
+    // two CTAs per SM, split by the streams' work; the voiced fraction is only known on the device: assume one half
+    const double w_mag = (double)a.n_mag * (a.n_mag <= 48 ? 48 : 64), w_ph = 0.5 * (double)a.n_ph * (a.phase_dim <= 48 ? 48 : 64);
+    const int total = 2 * a.num_sms;
+    int g_ph = (int)(total * w_ph / (w_mag + 2.0 * w_ph) + 0.5);
+    if (g_ph < 1) g_ph = 1;
+    int g_mag = total - 2 * g_ph;
+    if (g_mag < 1) g_mag = 1;
+    if (g_mag > tiles) g_mag = (int)tiles;
+    if (g_ph > tiles) g_ph = (int)tiles;
+    if (tiles < 1) return cudaSuccess;
+    c.g_mag = g_mag; c.g_ph = g_ph;
     e = cudaFuncSetAttribute(k_mel_cos, cudaFuncAttributeMaxDynamicSharedMemorySize, cos_smem_bytes);
     if (e != cudaSuccess) return e;
-    k_mel_cos<<<dim3((unsigned)gx, 3), CO_THREADS, cos_smem_bytes, st>>>(c);
+    k_mel_cos<<<(unsigned)(g_mag + 2 * g_ph), CO_THREADS, cos_smem_bytes, st>>>(c);
     return cudaGetLastError();
 }
 
