@@ -26,9 +26,15 @@ from ._lib import MPB_F32, MPB_F64, WIN_BARTLETT25, WIN_HANN
 
 MAGIC = -1.0e10   # src/libaudio.py:17
 
-# compute precision of the analysis butterflies.  float64 is needed to keep the normalised real/imag
-# features of near-silent bins within 1e-5 of the reference; synthesis is float32-safe
-# but defaults to float64 for the drop-in API (the batch/bench path selects float32).
+# Compute precision of the LOSSLESS entry points (analysis_lossless*, synthesis_from_lossless*, griffin_lim).  float64
+# butterflies are needed to keep the normalised real/imag features of near-silent bins within 1e-5 of the reference
+# (SURVEY.md 7.3-1); lossless synthesis is float32-safe but defaults to float64 for the drop-in API (the device-resident
+# batch / bench path selects float32).
+# These constants do NOT apply to the compressed chain, whose precision is fixed: analysis_compressed* runs float64
+# butterflies and keeps everything after X[k] in float32 (log periodograms, 3xTF32 tile products, float32 mel cepstra like
+# SPTK's files); synthesis_from_compressed* is float32 throughout, including the noise samples (NumPy's uniform draws are
+# reproduced bit for bit as float64 and narrowed to float32 before the noise FFT); results are widened to float64 on return.
+# All of it is held to 1e-5 RMS against the float64 oracle.
 ANALYSIS_COMPUTE = MPB_F64
 SYNTHESIS_COMPUTE = MPB_F64
 
