@@ -348,6 +348,12 @@ int mpb_sos2_host(mpb_ctx* ctx, double* x, const int64_t* utt_off, int32_t n_utt
 int mpb_analysis_geometry(const int64_t* pm_rounded, const int64_t* utt_frm_off, const int64_t* n_smpls, int32_t n_utt,
                           const double* voi_in, double fs, int64_t* centre, int32_t* left, int32_t* right,
                           double* f0_med, uint8_t* voi8);
+/* mpb_const_rate_scan: the reverse scan of get_shifts_and_frm_locs_from_const_shifts (src/magphase.py:1426-1449) for a batch,
+ * np.interp semantics bit for bit.  shift_c: constant-rate shifts of all utterances, row_off[n_utt+1], step = fs * 5 / 1000.
+ * Utterance u writes its (shift, location) pairs in SCAN order (last frame first) from index 2 * row_off[u]; count[u]
+ * entries (at most 2 n_u - 1).                                                                               */
+int mpb_const_rate_scan(const double* shift_c, const int64_t* row_off, int32_t n_utt, double step,
+                        double* out_shift, double* out_loc, int64_t* count);
 int mpb_syn_geometry(const int64_t* shift_trunc, const uint8_t* voi, const int64_t* utt_frm_off, int32_t n_utt,
                      int fft_len, int b_voi_ap_win, int32_t* pm, int64_t* ncentre, int32_t* nleft, int32_t* nright,
                      uint8_t* nkind, int32_t* win_a, int32_t* win_b, int32_t* row0, int64_t* utt_out_off,

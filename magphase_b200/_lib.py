@@ -72,6 +72,7 @@ SIGNATURES = {
     'mpb_mt19937_uniform_host': [_vp, _vp, _vp, _i64, C.c_double, C.c_double, _vp],
     'mpb_mt19937_jump_poly': [_i64, _vp],
     'mpb_analysis_geometry': [_vp, _vp, _vp, C.c_int32, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp],
+    'mpb_const_rate_scan': [_vp, _vp, C.c_int32, C.c_double, _vp, _vp, _vp],
     'mpb_syn_geometry': [_vp, _vp, _vp, C.c_int32, C.c_int, C.c_int] + [_vp] * 11,
     'mpb_sos2_dev': [_vp, _vp, _vp, C.c_int, _vp, _i32, _vp],
     'mpb_sos2_host': [_vp, _vp, _vp, _i32, _vp],

@@ -114,4 +114,55 @@ int mpb_syn_geometry(const int64_t* shift, const uint8_t* voi, const int64_t* ut
     return MPB_OK;
 }
 
+// Constant-rate -> variable-rate reverse scan (get_shifts_and_frm_locs_from_const_shifts, src/magphase.py:1426-1449) for a
+// batch: per utterance, walk back from the last constant-rate centre, subtracting the linearly interpolated shift, until
+// the position leaves [centres[0], centres[-1]].  Sequential and data dependent, hence host work -- but 750 NumPy calls per
+// utterance in the mirror (90 % of the host time of constant-rate synthesis).  The interpolation reproduces np.interp bit
+// for bit: interval j with xp[j] <= x < xp[j+1]; exact hits and the last knot return fp[j]; otherwise
+// slope * (x - xp[j]) + fp[j] with slope = (fp[j+1] - fp[j]) / (xp[j+1] - xp[j]) (no FMA contraction in host code).
+//   shift_c[R]  constant-rate shifts of all utterances (float64), row_off[U+1], step = fs * frm_rate_ms / 1000
+//   out_shift / out_loc [2 R]: utterance u writes at most 2 n_u - 1 entries from out_off = 2 row_off[u], IN SCAN ORDER (last
+//   frame first); count[u] = entries written.  centres[k] = step * (k + 1) as NumPy computes them (one rounding).
+int mpb_const_rate_scan(const double* shift_c, const int64_t* row_off, int32_t n_utt, double step, double* out_shift,
+                        double* out_loc, int64_t* count) {
+    if (!shift_c || !row_off || !out_shift || !out_loc || !count || n_utt < 0) return fail(MPB_ERR_BAD_ARG, "NULL argument");
+    if (!(step > 0.0)) return fail(MPB_ERR_BAD_ARG, "step must be positive");
+    for (int32_t u = 0; u < n_utt; ++u) {
+        const int64_t a = row_off[u], n = row_off[u + 1] - a;
+        if (n < 0) return fail(MPB_ERR_BAD_ARG, "row_off not non-decreasing");
+        count[u] = 0;
+        if (n == 0) continue;
+        const double* fp = shift_c + a;
+        double* os = out_shift + 2 * a;
+        double* ol = out_loc + 2 * a;
+        auto xp = [step](int64_t k) { return step * (double)(k + 1); };
+        const double lo = xp(0), hi = xp(n - 1);
+        double pos = hi;
+        int64_t j = n - 1, c = 0;
+        for (int64_t it = 0; it < 2 * n - 1; ++it) {
+            if (pos < lo || pos > hi || pos != pos) break;
+            // interval search from the previous one (the scan only moves left; a negative shift is followed as well)
+            if (j > n - 1) j = n - 1;
+            while (j + 1 <= n - 1 && xp(j + 1) <= pos) ++j;
+            while (j > 0 && xp(j) > pos) --j;
+            double sft;
+            if (j == n - 1 || xp(j) == pos) sft = fp[j];
+            else {
+                const double slope = (fp[j + 1] - fp[j]) / (xp(j + 1) - xp(j));
+                sft = slope * (pos - xp(j)) + fp[j];
+                if (sft != sft) {                                  // np.interp: "if we get nan in one direction, try the other"
+                    sft = slope * (pos - xp(j + 1)) + fp[j + 1];
+                    if (sft != sft && fp[j] == fp[j + 1]) sft = fp[j];
+                }
+            }
+            ol[c] = pos;
+            os[c] = sft;
+            ++c;
+            pos = pos - sft;
+        }
+        count[u] = c;
+    }
+    return MPB_OK;
+}
+
 }  // extern "C"

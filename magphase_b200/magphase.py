@@ -729,6 +729,23 @@ def get_shifts_and_frm_locs_from_const_shifts(v_shift_c_rate, frm_rate_ms, fs, i
     return np.array(shifts[::-1]), np.array(locs[::-1])
 
 
+def const_rate_scan_batch(l_shift_c, frm_rate_ms, fs):
+    """get_shifts_and_frm_locs_from_const_shifts for a list of utterances in one C pass (mpb_const_rate_scan: np.interp's
+    arithmetic bit for bit, tests/test_batch_geometry_cpu.py).  Returns a list of (v_shift, v_locs)."""
+    lens = np.array([np.size(v) for v in l_shift_c], dtype=np.int64)
+    off = _seg_offsets(lens)
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in l_shift_c])) if len(l_shift_c) else np.zeros(0)
+    o_s, o_l = np.empty(2 * flat.size + 2), np.empty(2 * flat.size + 2)
+    cnt = np.zeros(len(l_shift_c) + 1, dtype=np.int64)
+    _lib.check(_lib.lib().mpb_const_rate_scan(_lib.ptr(flat), _lib.ptr(off), len(l_shift_c), float(fs * frm_rate_ms / 1000),
+                                              _lib.ptr(o_s), _lib.ptr(o_l), _lib.ptr(cnt)))
+    out = []
+    for u in range(len(l_shift_c)):
+        a, c = 2 * int(off[u]), int(cnt[u])
+        out.append((o_s[a:a + c][::-1].copy(), o_l[a:a + c][::-1].copy()))
+    return out
+
+
 def _const_rate_rows(v_locs, n_c, step):
     """Row pairs + weights of interp_from_const_to_variable_rate (src/magphase.py:2242-2252), linear."""
     centres = step * np.arange(1, n_c + 1)
@@ -839,15 +856,19 @@ def _compressed_synthesis_geometry_loop(l_lf0, l_nrows, fs, fft_len, b_voi_ap_wi
     acc = {k: [] for k in ('pm', 'ncentre', 'nleft', 'nright', 'voi', 'nkind', 'win_a', 'win_b', 'row0', 'row1', 'roww',
                            'need', 't0')}
     l_ns_len = []
+    l_f0 = [np.exp(np.asarray(l_lf0[u], dtype=np.float64)) for u in range(n_utt)]
+    for u in range(n_utt):
+        if l_f0[u].size != int(l_nrows[u]):
+            raise ValueError('lf0 length must equal the number of feature rows')
+    # the sequential reverse scan of every utterance in one C pass
+    l_scan = const_rate_scan_batch([f0_to_shift(f, fs) for f in l_f0], 5.0, fs) if b_const_rate else None
     for u in range(n_utt):
         n_c = int(l_nrows[u])
-        v_f0 = np.exp(np.asarray(l_lf0[u], dtype=np.float64))
-        if v_f0.size != n_c:
-            raise ValueError('lf0 length must equal the number of feature rows')
+        v_f0 = l_f0[u]
         v_voi = v_f0 > 1.0                                        # :847
-        v_shift = f0_to_shift(v_f0, fs)
+        v_shift = f0_to_shift(v_f0, fs) if not b_const_rate else None
         if b_const_rate:
-            v_shift, v_locs = get_shifts_and_frm_locs_from_const_shifts(v_shift, 5.0, fs)
+            v_shift, v_locs = l_scan[u]
             r0, r1, w = _const_rate_rows(v_locs, n_c, fs * 5.0 / 1000)
             vf = v_voi.astype(np.float64)
             v_voi = (vf[r0] + (vf[r1] - vf[r0]) * w) > 0.5        # :868

@@ -145,3 +145,26 @@ def test_c_geometry_randomised_against_the_definitions():
             assert np.array_equal(voi8[a:b], (v_voi > 0).astype(np.uint8))
             assert np.array_equal(mp.f0_to_lf0(f0_med[a:b].copy()), v_lf0)
             sig_off += l_n[k]
+
+
+def test_const_rate_reverse_scan_c_pass_is_bit_identical_to_the_numpy_loop():
+    """mpb_const_rate_scan == get_shifts_and_frm_locs_from_const_shifts (np.interp per step, src/magphase.py:1426-1449):
+    the shifts are truncated to integers afterwards and become pitch marks, so the floats must agree to the last bit --
+    including exact knot hits, single-row utterances, all-unvoiced and all-voiced tracks, integer and fractional steps."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    for fs in (16000, 22050, 44100, 48000):
+        tracks = []
+        for u in range(24):
+            n_c = int(rng.integers(1, 700))
+            kind = u % 4
+            voiced = np.ones(n_c, bool) if kind == 0 else (np.zeros(n_c, bool) if kind == 1 else rng.random(n_c) < 0.5)
+            f0 = np.where(voiced, rng.uniform(50.0, 420.0, n_c), 0.0)
+            if kind == 3:
+                f0 = np.where(voiced, fs / (0.005 * fs * rng.integers(1, 3, n_c)), 0.0)     # shifts that land exactly on knots
+            tracks.append(mp.f0_to_shift(f0, fs))
+        got = mp.const_rate_scan_batch(tracks, 5.0, fs)
+        assert len(got) == len(tracks)
+        for v, (s, loc) in zip(tracks, got):
+            rs, rl = mp.get_shifts_and_frm_locs_from_const_shifts(v, 5.0, fs)
+            assert s.dtype == rs.dtype == np.float64 and np.array_equal(rs, s) and np.array_equal(rl, loc)
+    assert mp.const_rate_scan_batch([], 5.0, 16000) == []
