@@ -140,13 +140,14 @@ int mpb_const_rate_scan(const double* shift_c, const int64_t* row_off, int32_t n
         double pos = hi;
         int64_t j = n - 1, c = 0;
         for (int64_t it = 0; it < 2 * n - 1; ++it) {
-            if (pos < lo || pos > hi || pos != pos) break;
+            if (pos < lo || pos > hi) break;                       // (false for NaN, like the mirror's comparison)
             // interval search from the previous one (the scan only moves left; a negative shift is followed as well)
             if (j > n - 1) j = n - 1;
             while (j + 1 <= n - 1 && xp(j + 1) <= pos) ++j;
             while (j > 0 && xp(j) > pos) --j;
             double sft;
-            if (j == n - 1 || xp(j) == pos) sft = fp[j];
+            if (pos != pos) sft = pos;                             // np.interp hands NaN through
+            else if (j == n - 1 || xp(j) == pos) sft = fp[j];
             else {
                 const double slope = (fp[j + 1] - fp[j]) / (xp(j + 1) - xp(j));
                 sft = slope * (pos - xp(j)) + fp[j];

@@ -106,3 +106,34 @@ def test_const_rate_rows_reproduce_interp1d():
         ref = orc.interp_from_variable_to_const_frm_rate(data, pm, 5.0, 48000)
         assert got.shape == ref.shape
         np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
+
+
+def test_const_rate_scan_argument_checks_and_edge_cases():
+    """mpb_const_rate_scan (host only): bad arguments are refused with MPB_ERR_BAD_ARG -> ValueError; an empty utterance
+    writes nothing; a track with non-finite shifts (f0 = 0 gives fs / 0 upstream only if the caller skipped f0_to_shift's
+    floor) behaves like the NumPy loop: NaN is handed through until the iteration cap."""
+    from magphase_b200 import _lib
+    lib = _lib.lib()
+    sh = np.array([80.0, 90.0, 100.0, 0.0, 70.0], dtype=np.float64)
+    off = np.array([0, 3, 3, 5], dtype=np.int64)                      # utterance 1 is empty
+    o_s, o_l = np.full(12, -1.0), np.full(12, -1.0)
+    cnt = np.zeros(4, dtype=np.int64)
+    _lib.check(lib.mpb_const_rate_scan(_lib.ptr(sh), _lib.ptr(off), 3, 80.0, _lib.ptr(o_s), _lib.ptr(o_l), _lib.ptr(cnt)))
+    assert cnt[1] == 0 and cnt[0] >= 1 and cnt[0] <= 5
+    assert o_l[0] == 240.0 and o_s[0] == 100.0                         # the walk starts on the last centre with its own shift
+    # utterance 2: a zero shift at its first row would stall the walk on one position; the iteration cap (2 n - 1) ends it
+    assert 1 <= cnt[2] <= 3 and o_l[6] == 160.0 and o_s[6] == 70.0
+    with pytest.raises(ValueError):
+        _lib.check(lib.mpb_const_rate_scan(_lib.ptr(sh), _lib.ptr(off), 3, 0.0, _lib.ptr(o_s), _lib.ptr(o_l), _lib.ptr(cnt)))
+    with pytest.raises(ValueError):
+        _lib.check(lib.mpb_const_rate_scan(None, _lib.ptr(off), 3, 80.0, _lib.ptr(o_s), _lib.ptr(o_l), _lib.ptr(cnt)))
+    bad = np.array([0, 3, 2, 5], dtype=np.int64)
+    with pytest.raises(ValueError):
+        _lib.check(lib.mpb_const_rate_scan(_lib.ptr(sh), _lib.ptr(bad), 3, 80.0, _lib.ptr(o_s), _lib.ptr(o_l), _lib.ptr(cnt)))
+    nan = np.array([80.0, np.nan, 100.0], dtype=np.float64)
+    _lib.check(lib.mpb_const_rate_scan(_lib.ptr(nan), _lib.ptr(np.array([0, 3], dtype=np.int64)), 1, 80.0, _lib.ptr(o_s),
+                                       _lib.ptr(o_l), _lib.ptr(cnt)))
+    import magphase_b200.magphase as mp
+    rs, rl = mp.get_shifts_and_frm_locs_from_const_shifts(nan, 5.0, 16000)      # the NumPy loop: NaN is handed through to the cap
+    assert cnt[0] == rs.size == 5
+    assert np.array_equal(o_s[:5][::-1], rs, equal_nan=True) and np.array_equal(o_l[:5][::-1], rl, equal_nan=True)
