@@ -299,6 +299,17 @@ int mpb_synthesis_compressed_host2(mpb_syn* plan,
                                    const mpb_syn_frames* frames, int per_linear, const double* hpf_sos,
                                    void* out, int out_dtype, int64_t n_out);
 
+/* mpb_synthesis_compressed_host2 with the feature rows of every utterance in a host block of its own (one feature file per
+ * utterance, src/magphase.py:3229-3275): block b holds block_rows[b] rows; with variable-rate features block b is utterance b
+ * of `frames`.  The blocks are copied straight into page-locked staging by the host thread pool.                     */
+int mpb_synthesis_compressed_hostv2(mpb_syn* plan,
+                                    const void* const* mag_blocks, const void* const* real_blocks, const void* const* imag_blocks,
+                                    const int64_t* block_rows, int32_t n_blocks, int in_dtype,
+                                    const uint8_t* need_ph, const double* noise, int64_t n_noise,
+                                    uint32_t* mt_key, int32_t* mt_pos,
+                                    const mpb_syn_frames* frames, int per_linear, const double* hpf_sos,
+                                    void* out, int out_dtype, int64_t n_out);
+
 /* ---- post-filter and minimum phase ---------------------------------------------------------- */
 /*
  * post_filter (src/magphase.py:2300-2378): ave[b] = mean(x[centre[b]-half[b] .. centre[b]+half[b]]),

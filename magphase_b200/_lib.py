@@ -62,6 +62,8 @@ SIGNATURES = {
     'mpb_synthesis_noise_stage_dev': [_vp, _vp, _vp, _i64, _vp],
     'mpb_synthesis_compressed_host': [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp, _vp, _i64],
     'mpb_synthesis_compressed_host2': [_vp, _vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _i64],
+    'mpb_synthesis_compressed_hostv2': [_vp, _vp, _vp, _vp, _vp, _i32, C.c_int, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp, _vp,
+                                        C.c_int, _i64],
     'mpb_post_filter_dev': [_vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp],
     'mpb_post_filter_host': [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _vp],
     'mpb_cep_energy_host': [_vp, _vp, _i64, C.c_int, _vp, C.c_int, C.c_int, _vp],

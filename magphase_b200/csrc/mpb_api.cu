@@ -84,6 +84,7 @@ int mpb_destroy(mpb_ctx* ctx) {
     ctx->mt_jump.release();
     ctx->ticket.release();
     ctx->stage.release();
+    ctx->stage_feat.release();
     ctx->desc_stage.release();
     ctx->mt_fin.release();
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);

@@ -1,4 +1,5 @@
 // C-ABI: compressed synthesis plan (synthesis_from_compressed).
+#include <algorithm>
 #include <chrono>
 
 #include "mpb_ctx.h"
@@ -303,6 +304,47 @@ int mpb_synthesis_compressed_host2(mpb_syn* s, const void* mag_mel_v, const void
                                    uint32_t* mt_key, int32_t* mt_pos, const mpb_syn_frames* fr, int per_linear,
                                    const double* hpf_sos, void* out_v, int out_dtype, int64_t n_out);
 
+// feature rows handed over as one host block per utterance (mpb_synthesis_compressed_hostv2) instead of stacked matrices
+struct RowBlocks {
+    const void* const* blk[3];        // mag, real, imag: n pointers each
+    const int64_t* rows;              // rows per block
+    int32_t n;
+    std::vector<int64_t> off;         // [n + 1] first row of every block
+};
+static int syn_host_pipeline(const RowBlocks* rb, mpb_syn* s, const void* mag_mel_v, const void* real_mel_v, const void* imag_mel_v,
+                             int in_dtype, int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
+                             uint32_t* mt_key, int32_t* mt_pos, const mpb_syn_frames* fr, int per_linear, const double* hpf_sos,
+                             void* out_v, int out_dtype, int64_t n_out);
+
+int mpb_synthesis_compressed_host2(mpb_syn* s, const void* mag_mel_v, const void* real_mel_v, const void* imag_mel_v, int in_dtype,
+                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
+                                   uint32_t* mt_key, int32_t* mt_pos, const mpb_syn_frames* fr, int per_linear,
+                                   const double* hpf_sos, void* out_v, int out_dtype, int64_t n_out) {
+    return syn_host_pipeline(nullptr, s, mag_mel_v, real_mel_v, imag_mel_v, in_dtype, n_rows, need_ph, noise, n_noise, mt_key, mt_pos,
+                             fr, per_linear, hpf_sos, out_v, out_dtype, n_out);
+}
+
+// mpb_synthesis_compressed_host2 with the feature rows of every utterance in a host block of its own (what a caller that read
+// one feature file per utterance holds): block u has block_rows[u] rows; with variable-rate features block u must be
+// utterance u of `fr`.  The host pool copies the blocks straight into page-locked staging -- no stacked copy on the caller's side.
+int mpb_synthesis_compressed_hostv2(mpb_syn* s, const void* const* mag_blocks, const void* const* real_blocks,
+                                    const void* const* imag_blocks, const int64_t* block_rows, int32_t n_blocks, int in_dtype,
+                                    const uint8_t* need_ph, const double* noise, int64_t n_noise, uint32_t* mt_key, int32_t* mt_pos,
+                                    const mpb_syn_frames* fr, int per_linear, const double* hpf_sos, void* out_v, int out_dtype,
+                                    int64_t n_out) {
+    if (!s || !fr || !mag_blocks || !real_blocks || !imag_blocks || !block_rows || n_blocks < 0)
+        return fail(MPB_ERR_BAD_ARG, "NULL argument");
+    RowBlocks rb;
+    rb.blk[0] = mag_blocks; rb.blk[1] = real_blocks; rb.blk[2] = imag_blocks; rb.rows = block_rows; rb.n = n_blocks;
+    rb.off.assign((size_t)n_blocks + 1, 0);
+    for (int32_t b = 0; b < n_blocks; ++b) {
+        if (block_rows[b] < 0) return fail(MPB_ERR_BAD_ARG, "negative block size");
+        rb.off[b + 1] = rb.off[b] + block_rows[b];
+    }
+    return syn_host_pipeline(&rb, s, nullptr, nullptr, nullptr, in_dtype, rb.off[n_blocks], need_ph, noise, n_noise, mt_key, mt_pos, fr,
+                             per_linear, hpf_sos, out_v, out_dtype, n_out);
+}
+
 int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const double* real_mel, const double* imag_mel,
                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
                                   uint32_t* mt_key, int32_t* mt_pos, const mpb_syn_frames* fr, int per_linear,
@@ -311,19 +353,20 @@ int mpb_synthesis_compressed_host(mpb_syn* s, const double* mag_mel, const doubl
                                           fr, per_linear, hpf_sos, out, MPB_F64, n_out);
 }
 
-// The same pipeline with the caller's element types: features float64 or float32 (in_dtype; the reference's feature files are
+// The pipeline with the caller's element types: features float64 or float32 (in_dtype; the reference's feature files are
 // float32, src/libutils.py:112-127), waveform float64 or float32 (out_dtype).  float32 halves the bytes on PCIe both ways.
-int mpb_synthesis_compressed_host2(mpb_syn* s, const void* mag_mel_v, const void* real_mel_v, const void* imag_mel_v, int in_dtype,
-                                   int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
-                                   uint32_t* mt_key, int32_t* mt_pos, const mpb_syn_frames* fr, int per_linear,
-                                   const double* hpf_sos, void* out_v, int out_dtype, int64_t n_out) {
+// rb == NULL: stacked feature matrices (mag_mel_v, ...); else one host block per utterance.
+static int syn_host_pipeline(const RowBlocks* rb, mpb_syn* s, const void* mag_mel_v, const void* real_mel_v, const void* imag_mel_v,
+                             int in_dtype, int64_t n_rows, const uint8_t* need_ph, const double* noise, int64_t n_noise,
+                             uint32_t* mt_key, int32_t* mt_pos, const mpb_syn_frames* fr, int per_linear, const double* hpf_sos,
+                             void* out_v, int out_dtype, int64_t n_out) {
     if (!s || !fr) return fail(MPB_ERR_BAD_ARG, "NULL argument");
     if (!dtype_ok(in_dtype) || !dtype_ok(out_dtype)) return fail(MPB_ERR_BAD_ARG, "unknown dtype");
     const char* mag_mel = (const char*)mag_mel_v; const char* real_mel = (const char*)real_mel_v;
     const char* imag_mel = (const char*)imag_mel_v; char* out = (char*)out_v;
     const size_t ies = in_dtype == MPB_F64 ? 8 : 4, oes = out_dtype == MPB_F64 ? 8 : 4;
     if (n_out == 0) return MPB_OK;
-    if (!mag_mel || !real_mel || !imag_mel || !need_ph || !out) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    if ((!rb && (!mag_mel || !real_mel || !imag_mel)) || !need_ph || !out) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
     if (!noise && !(mt_key && mt_pos)) return fail(MPB_ERR_BAD_ARG, "either noise or an MT19937 state is required");
     if (!noise && (*mt_pos < 0 || *mt_pos > 624)) return fail(MPB_ERR_BAD_ARG, "bad MT19937 position");
     const int64_t F = fr->nfrm;
@@ -465,15 +508,41 @@ int mpb_synthesis_compressed_host2(mpb_syn* s, const void* mag_mel_v, const void
     const auto t2 = now();
 
     // ---- the pipeline ----
+    const size_t stage_real = (ies * (size_t)n_rows * s->n_mag + 255) & ~(size_t)255;
+    const size_t stage_imag = stage_real + ((ies * (size_t)n_rows * s->n_ph + 255) & ~(size_t)255);
+    if (n_rows > 0 && (rb || !(host_is_page_locked(mag_mel) && host_is_page_locked(real_mel) && host_is_page_locked(imag_mel))))
+        CU(ctx->stage_feat.need(stage_imag + ies * (size_t)n_rows * s->n_ph));
     for (const SynRange& r : rg) {
         const int64_t nr = r.row_b - r.row_a;
         if (nr > 0) {
-            CU(cudaMemcpyAsync((char*)b[B_MAG].p + ies * r.row_a * s->n_mag, mag_mel + ies * r.row_a * s->n_mag,
-                               ies * nr * s->n_mag, cudaMemcpyHostToDevice, s_in));
-            CU(cudaMemcpyAsync((char*)b[B_REAL].p + ies * r.row_a * s->n_ph, real_mel + ies * r.row_a * s->n_ph,
-                               ies * nr * s->n_ph, cudaMemcpyHostToDevice, s_in));
-            CU(cudaMemcpyAsync((char*)b[B_IMAG].p + ies * r.row_a * s->n_ph, imag_mel + ies * r.row_a * s->n_ph,
-                               ies * nr * s->n_ph, cudaMemcpyHostToDevice, s_in));
+            // (pageable sources -- features read from files -- are staged by the host pool; page-locked ones go straight to DMA)
+            const size_t o_mag = ies * r.row_a * s->n_mag, o_ph = ies * r.row_a * s->n_ph;
+            if (rb) {
+                // the blocks that make up rows [row_a, row_b): ranges are whole utterances, so they start and end on block edges
+                const int32_t b0 = (int32_t)(std::lower_bound(rb->off.begin(), rb->off.end(), r.row_a) - rb->off.begin());
+                const int32_t b1 = (int32_t)(std::lower_bound(rb->off.begin(), rb->off.end(), r.row_b) - rb->off.begin());
+                if (b0 > rb->n || b1 > rb->n || rb->off[b0] != r.row_a || rb->off[b1] != r.row_b) {
+                    rc = fail(MPB_ERR_BAD_ARG, "feature blocks do not line up with the utterances");
+                    break;
+                }
+                rc = h2d_gather_staged(ctx, s_in, (char*)b[B_MAG].p + o_mag, rb->blk[0], rb->rows, b0, b1, ies * s->n_mag,
+                                       ctx->stage_feat, o_mag);
+                if (rc == MPB_OK)
+                    rc = h2d_gather_staged(ctx, s_in, (char*)b[B_REAL].p + o_ph, rb->blk[1], rb->rows, b0, b1, ies * s->n_ph,
+                                           ctx->stage_feat, stage_real + o_ph);
+                if (rc == MPB_OK)
+                    rc = h2d_gather_staged(ctx, s_in, (char*)b[B_IMAG].p + o_ph, rb->blk[2], rb->rows, b0, b1, ies * s->n_ph,
+                                           ctx->stage_feat, stage_imag + o_ph);
+            } else {
+                rc = h2d_staged(ctx, s_in, (char*)b[B_MAG].p + o_mag, mag_mel + o_mag, ies * nr * s->n_mag, ctx->stage_feat, o_mag);
+                if (rc == MPB_OK)
+                    rc = h2d_staged(ctx, s_in, (char*)b[B_REAL].p + o_ph, real_mel + o_ph, ies * nr * s->n_ph, ctx->stage_feat,
+                                    stage_real + o_ph);
+                if (rc == MPB_OK)
+                    rc = h2d_staged(ctx, s_in, (char*)b[B_IMAG].p + o_ph, imag_mel + o_ph, ies * nr * s->n_ph, ctx->stage_feat,
+                                    stage_imag + o_ph);
+            }
+            if (rc != MPB_OK) break;
         }
         cudaEvent_t e_in = get_event(ctx), e_cmp = get_event(ctx);
         evs.push_back(e_in); evs.push_back(e_cmp);

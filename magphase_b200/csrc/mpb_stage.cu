@@ -254,6 +254,64 @@ int upload_signal_groups_narrow(mpb_ctx* ctx, cudaStream_t st, const void* const
     return rc;
 }
 
+bool host_is_page_locked(const void* p) {
+    cudaPointerAttributes a;
+    const cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int h2d_staged(mpb_ctx* ctx, cudaStream_t st, void* dev, const void* host, size_t bytes, PinnedBuf& stage, size_t stage_off) {
+    (void)ctx;
+    if (bytes == 0) return MPB_OK;
+    if (host_is_page_locked(host) || stage_off + bytes > stage.cap) {
+        const cudaError_t e = cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st);
+        return e == cudaSuccess ? MPB_OK : fail(MPB_ERR_CUDA, std::string("feature upload: ") + cudaGetErrorString(e));
+    }
+    constexpr size_t CH = (size_t)2 << 20;
+    const int n = (int)((bytes + CH - 1) / CH);
+    char* h = (char*)stage.p + stage_off;
+    int rc = MPB_OK;
+    HostPool::get().run(
+        n,
+        [&](int c) { const size_t a = (size_t)c * CH; memcpy(h + a, (const char*)host + a, bytes - a < CH ? bytes - a : CH); },
+        [&](int c) {
+            if (rc != MPB_OK) return;
+            const size_t a = (size_t)c * CH;
+            const cudaError_t e = cudaMemcpyAsync((char*)dev + a, h + a, bytes - a < CH ? bytes - a : CH, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) rc = fail(MPB_ERR_CUDA, std::string("feature upload: ") + cudaGetErrorString(e));
+        });
+    return rc;
+}
+
+int h2d_gather_staged(mpb_ctx* ctx, cudaStream_t st, void* dev, const void* const* blocks, const int64_t* blk_rows, int32_t b0,
+                      int32_t b1, size_t row_bytes, PinnedBuf& stage, size_t stage_off) {
+    (void)ctx;
+    constexpr size_t CH = (size_t)2 << 20;
+    struct Chunk { const char* src; size_t off, n; };
+    std::vector<Chunk> ch;
+    size_t total = 0;
+    for (int32_t b = b0; b < b1; ++b) {
+        const size_t bytes = (size_t)blk_rows[b] * row_bytes;
+        if (bytes && !blocks[b]) return fail(MPB_ERR_BAD_ARG, "NULL feature block");
+        for (size_t a = 0; a < bytes; a += CH) ch.push_back({(const char*)blocks[b] + a, total + a, bytes - a < CH ? bytes - a : CH});
+        total += bytes;
+    }
+    if (total == 0) return MPB_OK;
+    if (stage_off + total > stage.cap) return fail(MPB_ERR_INTERNAL, "feature staging buffer too small");
+    char* h = (char*)stage.p + stage_off;
+    int rc = MPB_OK;
+    HostPool::get().run(
+        (int)ch.size(),
+        [&](int c) { memcpy(h + ch[c].off, ch[c].src, ch[c].n); },
+        [&](int c) {
+            if (rc != MPB_OK) return;
+            const cudaError_t e = cudaMemcpyAsync((char*)dev + ch[c].off, h + ch[c].off, ch[c].n, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) rc = fail(MPB_ERR_CUDA, std::string("feature upload: ") + cudaGetErrorString(e));
+        });
+    return rc;
+}
+
 // One group: everything in dev (>= 8 bytes per sample); *out_dtype says how it was uploaded.
 int upload_signals(mpb_ctx* ctx, cudaStream_t st, const double* const* sigs, const int64_t* lens, int32_t n_sigs,
                    void* dev, int* out_dtype) {

@@ -787,10 +787,11 @@ def synthesis_from_compressed(m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0, fs, 
                                            alpha_phase=alpha_phase, b_out_hpf=b_out_hpf)[0]
 
 
-def _stack_rows(l_arr, dtype=np.float64):
+def _stack_rows(l_arr, dtype=np.float64, copy=True):
     """np.concatenate(l_arr, axis=0) as `dtype` -- without the copy when the arrays already sit back to back in memory
     (the row blocks the *_batch analysis functions return).  The result is only used as a read-only argument of a C
-    call made while the inputs are still referenced, so viewing across the blocks is safe."""
+    call made while the inputs are still referenced, so viewing across the blocks is safe.  copy=False: None instead of
+    a stacked copy when the blocks are not adjacent."""
     a0 = l_arr[0]
     if all(isinstance(a, np.ndarray) and a.dtype == np.dtype(dtype) and a.ndim == 2 and a.flags['C_CONTIGUOUS'] and
            a.shape[1] == a0.shape[1] for a in l_arr):
@@ -802,6 +803,8 @@ def _stack_rows(l_arr, dtype=np.float64):
         else:
             rows = sum(a.shape[0] for a in l_arr)
             return np.lib.stride_tricks.as_strided(a0, shape=(rows, a0.shape[1]), strides=a0.strides, writeable=False)
+    if not copy:
+        return None
     return np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=dtype) for a in l_arr], axis=0))
 
 
@@ -961,19 +964,40 @@ def synthesis_from_compressed_batch(l_feats, fs, fft_len=None, b_voi_ap_win=True
     if out_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
         raise ValueError('out_dtype must be float64 or float32')
     feat_np = np.float32 if all(np.asarray(f[i]).dtype == np.float32 for f in l_feats for i in range(3)) else np.float64
-    mag, real, imag = (_stack_rows([f[i] for f in l_feats], feat_np) for i in range(3))
+    # three ways in: row blocks that already sit back to back (what the batch analysis returns: viewed, no copy), one
+    # C-contiguous block per utterance (what a caller that read one feature file per utterance holds: pointers handed to the
+    # library, whose host threads copy them straight into page-locked staging), anything else: stacked here
+    mags, reals, imags = ([f[i] for f in l_feats] for i in range(3))
+    mag = _stack_rows(mags, feat_np, copy=False)
+    real = _stack_rows(reals, feat_np, copy=False) if mag is not None else None
+    imag = _stack_rows(imags, feat_np, copy=False) if real is not None else None
+    blocks = None
+    if imag is None:
+        ok = lambda a: isinstance(a, np.ndarray) and a.dtype == np.dtype(feat_np) and a.ndim == 2 and a.flags['C_CONTIGUOUS']
+        if (all(ok(a) for a in mags) and all(ok(a) for a in reals) and all(ok(a) for a in imags) and
+                all(m.shape[0] == r.shape[0] == i.shape[0] for m, r, i in zip(mags, reals, imags))):
+            blocks = tuple((C.c_void_p * n_utt)(*[a.ctypes.data for a in l]) for l in (mags, reals, imags))
+            block_rows = np.ascontiguousarray([a.shape[0] for a in mags], dtype=np.int64)
+        else:
+            mag, real, imag = (_stack_rows(l, feat_np) for l in (mags, reals, imags))
     noise = None
     if l_noise is not None:
         noise = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64) for v in l_noise]))
     hpf_sos = output_hpf_sos(fs) if b_out_hpf else None
     out = _lib.pinned.empty(int(out_off[-1]), dtype=out_dtype)
     code = lambda dt: _lib.MPB_F32 if np.dtype(dt) == np.dtype(np.float32) else _lib.MPB_F64
+    ppt = {'magphase': 0, 'linear': 1, 'min_phase': 2}[per_phase_type]
     with _lib.device_gate():
-        _lib.check(_lib.lib().mpb_synthesis_compressed_host2(
-            plan.handle, _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), code(feat_np), mag.shape[0], _lib.ptr(need),
-            _lib.ptr(noise), int(sum(l_ns_len)), _lib.ptr(mt_key), C.byref(mt_pos) if mt_pos is not None else None, C.byref(fr),
-            {'magphase': 0, 'linear': 1, 'min_phase': 2}[per_phase_type], _lib.ptr(hpf_sos), _lib.ptr(out), code(out_dtype),
-            out.size))
+        if blocks is not None:
+            _lib.check(_lib.lib().mpb_synthesis_compressed_hostv2(
+                plan.handle, blocks[0], blocks[1], blocks[2], _lib.ptr(block_rows), n_utt, code(feat_np), _lib.ptr(need),
+                _lib.ptr(noise), int(sum(l_ns_len)), _lib.ptr(mt_key), C.byref(mt_pos) if mt_pos is not None else None,
+                C.byref(fr), ppt, _lib.ptr(hpf_sos), _lib.ptr(out), code(out_dtype), out.size))
+        else:
+            _lib.check(_lib.lib().mpb_synthesis_compressed_host2(
+                plan.handle, _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), code(feat_np), mag.shape[0], _lib.ptr(need),
+                _lib.ptr(noise), int(sum(l_ns_len)), _lib.ptr(mt_key), C.byref(mt_pos) if mt_pos is not None else None,
+                C.byref(fr), ppt, _lib.ptr(hpf_sos), _lib.ptr(out), code(out_dtype), out.size))
     if mt_key is not None:
         (rng if rng is not None else np.random).set_state((np_state[0], mt_key, int(mt_pos.value), np_state[3], np_state[4]))
     l_out = [out[out_off[u]:out_off[u + 1]] for u in range(n_utt)]
