@@ -816,7 +816,7 @@ def compressed_synthesis_geometry(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win=True
     constant-rate path, whose reverse scan is sequential anyway)."""
     if not b_const_rate:
         return _compressed_synthesis_geometry_flat(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win, reuse=_reuse)
-    return _compressed_synthesis_geometry_loop(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win, b_const_rate)
+    return _compressed_synthesis_geometry_const_flat(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win)
 
 
 def _compressed_synthesis_geometry_flat(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win=True, reuse=False):
@@ -847,6 +847,60 @@ def _compressed_synthesis_geometry_flat(l_lf0, l_nrows, fs, fft_len, b_voi_ap_wi
                                            _lib.ptr(out_off), _lib.ptr(t0), _lib.ptr(ns_len)))
     arrs = dict(pm=pm, ncentre=ncentre, nleft=nleft, nright=nright, voi=voi8, nkind=nkind, win_a=win_a, win_b=win_b,
                 row0=row0, row1=None, roww=None, utt_frm_off=off, utt_out_off=out_off, utt_t0=t0, need_ph=voi8)
+    return arrs, [int(x) for x in ns_len]
+
+
+def _compressed_synthesis_geometry_const_flat(l_lf0, l_nrows, fs, fft_len, b_voi_ap_win=True):
+    """compressed_synthesis_geometry(b_const_rate=True) for all utterances at once: the reverse scan in C
+    (mpb_const_rate_scan), the row pairs / weights and the interpolated voicing (src/magphase.py:861-870) vectorised over the
+    concatenated frames, everything after the truncation to integer shifts in mpb_syn_geometry.  Bit-identical to the loop
+    below (tests/test_batch_geometry_cpu.py), which stays the definition."""
+    n_utt = len(l_lf0)
+    n_c = np.array([np.size(v) for v in l_lf0], dtype=np.int64)
+    if np.any(n_c != np.asarray(l_nrows, dtype=np.int64)):
+        raise ValueError('lf0 length must equal the number of feature rows')
+    row_off = _seg_offsets(n_c)
+    n_rows = int(row_off[-1])
+    v_f0 = np.exp(np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in l_lf0])) if n_utt else np.zeros(0)
+    vf = (v_f0 > 1.0).astype(np.float64)                          # :847
+    shift_c = f0_to_shift(v_f0, fs)
+    step = float(fs * 5.0 / 1000)
+    o_s, o_l = np.empty(2 * n_rows + 2), np.empty(2 * n_rows + 2)
+    cnt = np.zeros(n_utt + 1, dtype=np.int64)
+    _lib.check(_lib.lib().mpb_const_rate_scan(_lib.ptr(np.ascontiguousarray(shift_c)), _lib.ptr(row_off), n_utt, step,
+                                              _lib.ptr(o_s), _lib.ptr(o_l), _lib.ptr(cnt)))
+    cnt = cnt[:n_utt]
+    if np.any(cnt < 2):
+        raise IndexError('synthesis_from_compressed needs at least two frames (src/magphase.py:882)')
+    frm_off = _seg_offsets(cnt)
+    n = int(frm_off[-1])
+    # frame k of utterance u (forward order) is entry cnt[u] - 1 - k of its scan, which starts at 2 * row_off[u]
+    k_in = np.arange(n, dtype=np.int64) - np.repeat(frm_off[:-1], cnt)
+    idx = np.repeat(2 * row_off[:-1] + cnt - 1, cnt) - k_in
+    v_shift, v_locs = o_s[idx], o_l[idx]
+    # rows (src/magphase.py:2242-2252): j = clip(#{centres <= loc} - 1, 0, n_c - 2) with centres[k] = step * (k + 1)
+    j = (v_locs / step).astype(np.int64) - 1
+    for _ in range(2):                                            # the quotient can be one off in either direction
+        j = np.where(step * (j + 2).astype(np.float64) <= v_locs, j + 1, j)
+        j = np.where(step * (j + 1).astype(np.float64) > v_locs, j - 1, j)
+    j = np.clip(j, 0, np.repeat(n_c - 2, cnt))
+    c0, c1 = step * (j + 1).astype(np.float64), step * (j + 2).astype(np.float64)
+    w = (v_locs - c0) / (c1 - c0)
+    r0 = j + np.repeat(row_off[:-1], cnt)
+    r1 = r0 + 1
+    voi8 = ((vf[r0] + (vf[r1] - vf[r0]) * w) > 0.5).astype(np.uint8)                        # :868
+    shift = v_shift.astype(np.int64)                              # truncation BEFORE the cumsum (:879-880)
+    pm, ncentre = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64)
+    nleft, nright, nkind = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.uint8)
+    win_a, win_b, row_id = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+    out_off, t0, ns_len = np.empty(n_utt + 1, dtype=np.int64), np.empty(n_utt, dtype=np.int32), np.empty(n_utt, dtype=np.int64)
+    _lib.check(_lib.lib().mpb_syn_geometry(_lib.ptr(shift), _lib.ptr(voi8), _lib.ptr(frm_off), n_utt, fft_len,
+                                           1 if b_voi_ap_win else 0, _lib.ptr(pm), _lib.ptr(ncentre), _lib.ptr(nleft),
+                                           _lib.ptr(nright), _lib.ptr(nkind), _lib.ptr(win_a), _lib.ptr(win_b), _lib.ptr(row_id),
+                                           _lib.ptr(out_off), _lib.ptr(t0), _lib.ptr(ns_len)))
+    arrs = dict(pm=pm, ncentre=ncentre, nleft=nleft, nright=nright, voi=voi8, nkind=nkind, win_a=win_a, win_b=win_b,
+                row0=r0.astype(np.int32), row1=r1.astype(np.int32), roww=w.astype(np.float32), utt_frm_off=frm_off,
+                utt_out_off=out_off, utt_t0=t0, need_ph=np.ones(n_rows, dtype=np.uint8))
     return arrs, [int(x) for x in ns_len]
 
 

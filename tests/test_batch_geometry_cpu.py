@@ -168,3 +168,27 @@ def test_const_rate_reverse_scan_c_pass_is_bit_identical_to_the_numpy_loop():
             rs, rl = mp.get_shifts_and_frm_locs_from_const_shifts(v, 5.0, fs)
             assert s.dtype == rs.dtype == np.float64 and np.array_equal(rs, s) and np.array_equal(rl, loc)
     assert mp.const_rate_scan_batch([], 5.0, 16000) == []
+
+
+def test_const_rate_synthesis_geometry_vectorised_equals_the_loop():
+    """compressed_synthesis_geometry(b_const_rate=True): the batch version (C reverse scan + vectorised row pairs / voicing +
+    mpb_syn_geometry) against the per-utterance loop that follows src/magphase.py:846-896 line by line -- every array
+    identical in dtype and value, for integer and fractional constant-rate steps."""
+    rng = np.random.Generator(np.random.PCG64(23))
+    for fs, fft_len in ((16000, 2048), (48000, 4096), (44100, 4096), (22050, 2048)):
+        for trial in range(4):
+            l_lf0 = []
+            for u in range(int(rng.integers(1, 8))):
+                n_c = int(rng.integers(3, 400))
+                voiced = rng.random(n_c) < (0.0 if trial == 0 and u == 0 else 0.6)
+                f0 = np.where(voiced, rng.uniform(70.0, 380.0, n_c), 0.0)
+                l_lf0.append(np.where(f0 > 0, np.log(np.maximum(f0, 1e-3)), -1.0e10))
+            rows = [v.size for v in l_lf0]
+            for vw in (True, False):
+                a, ns_a = mp._compressed_synthesis_geometry_const_flat(l_lf0, rows, fs, fft_len, vw)
+                b, ns_b = mp._compressed_synthesis_geometry_loop(l_lf0, rows, fs, fft_len, vw, True)
+                assert ns_a == ns_b and set(a) == set(b)
+                for k in b:
+                    assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), (fs, trial, k)
+    with pytest.raises(ValueError):
+        mp._compressed_synthesis_geometry_const_flat([np.zeros(5)], [4], 16000, 2048)
