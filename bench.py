@@ -711,11 +711,15 @@ def run_extras(a, torch, _lib, mp, CompressedPlan, make_lossless, geom, d_sig, u
     u16 = [base16[i % len(base16)] for i in range(n16)]
     feats16 = mp.analysis_compressed_batch([u[0] for u in u16], fs16, [u[1] for u in u16], [u[2] for u in u16], mag_dim=60,
                                            phase_dim=45, b_const_rate=True)
-    feats16 = [f[:4] for f in feats16]
+    feats16 = [tuple(np.array(a) for a in f[:4]) for f in feats16]     # one pageable array per utterance and stream, as read from files
     n_rows = sum(f[0].shape[0] for f in feats16)
 
     def g16():
-        pf = [(mp.post_filter(f[0], fs16), f[1], f[2], f[3]) for f in feats16]
+        # as magphase_b200.batch.run_waveform_generation does it: the post-filter works frame by frame, one call over the
+        # stacked rows of the batch; the feature rows stay one block per utterance (as read from one file per utterance)
+        rows = mp.post_filter(np.concatenate([f[0] for f in feats16], axis=0), fs16)
+        off = np.concatenate(([0], np.cumsum([f[0].shape[0] for f in feats16])))
+        pf = [(np.ascontiguousarray(rows[off[i]:off[i + 1]]), f[1], f[2], f[3]) for i, f in enumerate(feats16)]
         return mp.synthesis_from_compressed_batch(pf, fs16, b_const_rate=True, b_out_hpf=True)
     import warnings
     with warnings.catch_warnings():
