@@ -683,6 +683,26 @@ def run_extras(a, torch, _lib, mp, CompressedPlan, make_lossless, geom, d_sig, u
                       'kernels': lk}
     del lp, lstep
     torch.cuda.empty_cache()
+    # the same chain through the host API (float64 NumPy in / out like the reference: 3 x 2049 float64 features per frame
+    # cross PCIe in each direction, 98 KB per frame -- this path is a PCIe measurement)
+    n_le = min(len(utts), 8)
+    le = ([u[0] for u in utts[:n_le]], [u[1] for u in utts[:n_le]], [u[2] for u in utts[:n_le]])
+
+    def l_e2e():
+        o = mp.analysis_lossless_batch(le[0], FS, le[1], le[2], fft_len=FFT_LEN)
+        mp.synthesis_from_lossless_batch([x[:4] for x in o], FS)
+        return sum(x[5].size for x in o)
+    l_e2e(); l_frames = l_e2e()
+    barrier()
+    t = time.perf_counter()
+    for _ in range(3):
+        l_e2e()
+    torch.cuda.synchronize()
+    l_s = (time.perf_counter() - t) / 3
+    ex['lossless']['e2e'] = {'value': l_frames / l_s, 'unit': 'frames/s', 'utts': n_le,
+                             'h2d_bytes_per_step': int(sum(x.size for x in le[0]) * 4 + l_frames * (3 * (FFT_LEN // 2 + 1) * 8 + 16)),
+                             'd2h_bytes_per_step': int(l_frames * 3 * (FFT_LEN // 2 + 1) * 8 + sum(x.size for x in le[0]) * 8),
+                             'api': 'analysis_lossless_batch -> synthesis_from_lossless_batch (float64 NumPy in / out)'}
     # ---- config 3: feature extraction for TTS (analysis only) ----
     p3 = CompressedPlan(*geom, FS, FFT_LEN, mag_dim=60, phase_dim=10, device=local_rank, alpha_phase=0.0)
     ms = time_steps(lambda: p3.analysis(d_sig), steps, 3, barrier, torch) / steps
