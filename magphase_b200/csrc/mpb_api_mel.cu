@@ -19,8 +19,15 @@ struct mpb_mel {
     std::mutex mu;
 };
 
-static constexpr int64_t MEL_CHUNK = 131072;   // frames per pass: bounds the scratch (log periodograms 3.2 GB + mel cepstra 0.1 GB);
+static constexpr int64_t MEL_CHUNK_DEFAULT = 131072;   // frames per pass: bounds the scratch (log periodograms 3.2 GB + mel cepstra 0.1 GB);
                                               // measured 32768 / 65536 / 131072: 3.62 / 3.50 / 3.48 ms per 116k frames
+
+// (MPB_MEL_CHUNK overrides it: tests run the chunk loop with a few thousand frames per pass)
+static int64_t mel_chunk() {
+    static const int64_t v = [] { const char* e = getenv("MPB_MEL_CHUNK"); const long long x = e ? atoll(e) : 0; return x >= 256 ? (int64_t)x : MEL_CHUNK_DEFAULT; }();
+    return v;
+}
+#define MEL_CHUNK mel_chunk()
 
 static int pad64(int n) { return ((n + 63) / 64) * 64; }
 static int lp_pitch_of(int H) { return (H + 3) & ~3; }   // row pitch of the log-periodogram scratch: 16-byte rows (TMA)
