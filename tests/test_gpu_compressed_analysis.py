@@ -67,6 +67,25 @@ def test_analysis_compressed_fused_vs_oracle(mp):
         assert rms(a, b) < TOL, (name, rms(a, b))
 
 
+def test_analysis_compressed_all_unvoiced_all_voiced_and_mixed_batch(mp):
+    """The phase streams run over the voiced frames only (compacted rows, tensor-core tiles sized by the device-side count):
+    an utterance without a single voiced frame, one without an unvoiced frame, and a batch that mixes them with an ordinary
+    utterance must all match the oracle; unvoiced frames keep exact zeros in real_mel / imag_mel (src/magphase.py:2527-2528)."""
+    sig, pm, voi = synth_utterance(31, fs=48000, dur_s=0.6)
+    cases = [(sig, pm, np.zeros_like(voi)), (sig, pm, np.ones_like(voi)), (sig, pm, voi)]
+    refs = [orc.analysis_compressed_from_pm(s, 48000, p, v, mag_dim=60, phase_dim=45) for s, p, v in cases]
+    singles = [mp.analysis_compressed_from_pm(s, 48000, p, v, mag_dim=60, phase_dim=45) for s, p, v in cases]
+    batch = mp.analysis_compressed_batch([c[0] for c in cases], 48000, [c[1] for c in cases], [c[2] for c in cases], mag_dim=60,
+                                         phase_dim=45)
+    for ref, one, bat, (_, _, v) in zip(refs, singles, batch, cases):
+        for a, b, c in zip(one[:3], bat[:3], ref[:3]):
+            assert a.shape == c.shape and rms(a, c) < TOL and np.array_equal(a, b)       # batch == single, byte for byte
+        assert np.array_equal(one[3], ref[3]) and np.array_equal(bat[3], ref[3])
+        unv = np.asarray(ref[3]) < -1.0e9                                                # lf0 of unvoiced frames is the -1e10 floor
+        assert np.all(one[1][unv] == 0.0) and np.all(one[2][unv] == 0.0)
+    assert np.all(np.asarray(refs[0][3]) < -1.0e9) and np.all(singles[0][1] == 0.0)
+
+
 def test_analysis_compressed_batch_and_mag_dim_100(mp):
     """mag_dim=100 is what the shipped low-dim demo uses (demos/demo_copy_synthesis_low_dim.py:63)."""
     utts = [synth_utterance(u, fs=48000, dur_s=0.4) for u in (20, 21)]
