@@ -179,7 +179,7 @@ class CompressedPlan:
         return self.nfrm * (self.mag_dim + 2 * self.phase_dim) * 4 + self.nfrm * 45 + self.n_noise * 4 + self.n_out * 4
 
     def analysis(self, d_sig, compute=MPB_F64):
-        """k_analysis<logp> -> k_mel_gemm -> k_mel_finish per chunk of frames (float64 butterflies)."""
+        """k_voiced_compact -> k_analysis<logp> (float64 butterflies) -> k_mel_warp_tc -> k_mel_cos per chunk of frames."""
         sig_dt = MPB_F64 if d_sig.dtype == torch.float64 else MPB_F32
         _lib.check(_lib.lib().mpb_analysis_compressed_dev(
             self.mel.handle, _stream(), _dp(d_sig), sig_dt, self.n_sig, _dp(self.d_centre), _dp(self.d_left),
