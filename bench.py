@@ -688,21 +688,34 @@ def run_extras(a, torch, _lib, mp, CompressedPlan, make_lossless, geom, d_sig, u
     n_le = min(len(utts), 8)
     le = ([u[0] for u in utts[:n_le]], [u[1] for u in utts[:n_le]], [u[2] for u in utts[:n_le]])
 
-    def l_e2e():
-        o = mp.analysis_lossless_batch(le[0], FS, le[1], le[2], fft_len=FFT_LEN)
-        mp.synthesis_from_lossless_batch([x[:4] for x in o], FS)
+    le_pcm = [np.round(x * 32768.0).astype(np.int16) for x in le[0]]
+
+    def l_e2e(narrow=False):
+        if narrow:      # the reference's file formats: PCM16 in, float32 feature matrices, float32 waveform
+            o = mp.analysis_lossless_batch(le_pcm, FS, le[1], le[2], fft_len=FFT_LEN, out_dtype=np.float32)
+            mp.synthesis_from_lossless_batch([x[:4] for x in o], FS, out_dtype=np.float32)
+        else:
+            o = mp.analysis_lossless_batch(le[0], FS, le[1], le[2], fft_len=FFT_LEN)
+            mp.synthesis_from_lossless_batch([x[:4] for x in o], FS)
         return sum(x[5].size for x in o)
-    l_e2e(); l_frames = l_e2e()
-    barrier()
-    t = time.perf_counter()
-    for _ in range(3):
-        l_e2e()
-    torch.cuda.synchronize()
-    l_s = (time.perf_counter() - t) / 3
+
+    def l_time(narrow):
+        l_e2e(narrow); n = l_e2e(narrow)
+        barrier()
+        t = time.perf_counter()
+        for _ in range(3):
+            l_e2e(narrow)
+        torch.cuda.synchronize()
+        return n, (time.perf_counter() - t) / 3
+    l_frames, l_s = l_time(False)
+    _, l_sn = l_time(True)
     ex['lossless']['e2e'] = {'value': l_frames / l_s, 'unit': 'frames/s', 'utts': n_le,
                              'h2d_bytes_per_step': int(sum(x.size for x in le[0]) * 4 + l_frames * (3 * (FFT_LEN // 2 + 1) * 8 + 16)),
                              'd2h_bytes_per_step': int(l_frames * 3 * (FFT_LEN // 2 + 1) * 8 + sum(x.size for x in le[0]) * 8),
-                             'api': 'analysis_lossless_batch -> synthesis_from_lossless_batch (float64 NumPy in / out)'}
+                             'api': 'analysis_lossless_batch -> synthesis_from_lossless_batch (float64 NumPy in / out)',
+                             'narrow': {'value': l_frames / l_sn, 'unit': 'frames/s',
+                                        'api': 'the same two calls with PCM16 signals in, float32 feature matrices and float32 waveform '
+                                               '(out_dtype=np.float32): 49 KB per frame and direction'}}
     # ---- config 3: feature extraction for TTS (analysis only) ----
     p3 = CompressedPlan(*geom, FS, FFT_LEN, mag_dim=60, phase_dim=10, device=local_rank, alpha_phase=0.0)
     ms = time_steps(lambda: p3.analysis(d_sig), steps, 3, barrier, torch) / steps

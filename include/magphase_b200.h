@@ -96,6 +96,15 @@ int mpb_analysis_lossless_host(mpb_ctx* ctx,
                                const uint8_t* win, int64_t nfrm, int fft_len, int compute_dtype,
                                double* out_mag, double* out_real, double* out_imag);
 
+/* mpb_analysis_lossless_host with the caller's element types: signal MPB_F64 / MPB_F32 / MPB_I16 (PCM16 as the wav file holds
+ * it; the device applies sf.read's 1/32768, src/libaudio.py:343-350), feature matrices MPB_F64 / MPB_F32 (the reference's
+ * .mag/.real/.imag files are float32, src/libutils.py:122-127).                                                   */
+int mpb_analysis_lossless_host2(mpb_ctx* ctx,
+                                const void* sig, int sig_dtype, int64_t n_sig,
+                                const int64_t* centre, const int32_t* left, const int32_t* right,
+                                const uint8_t* win, int64_t nfrm, int fft_len, int compute_dtype,
+                                void* out_mag, void* out_real, void* out_imag, int out_dtype);
+
 /* Complex half spectra only (m_fft of analysis_with_del_comp_from_pm, src/magphase.py:325-332):
  * out_fft is nfrm x (fft_len/2+1) x 2 (re, im interleaved == complex64/complex128).              */
 int mpb_frames_fft_dev(mpb_ctx* ctx, void* stream,
@@ -151,6 +160,14 @@ int mpb_synthesis_lossless_host(mpb_ctx* ctx,
                                 const int64_t* utt_frm_off, const int64_t* utt_out_off, const int32_t* utt_t0,
                                 int32_t n_utt, int fft_len, int compute_dtype,
                                 double* out, int64_t n_out);
+
+/* mpb_synthesis_lossless_host with float64 or float32 feature matrices (feat_dtype) and waveform (out_dtype).     */
+int mpb_synthesis_lossless_host2(mpb_ctx* ctx,
+                                 const void* mag, const void* real, const void* imag, int feat_dtype,
+                                 const int32_t* pm, int64_t nfrm_total,
+                                 const int64_t* utt_frm_off, const int64_t* utt_out_off, const int32_t* utt_t0,
+                                 int32_t n_utt, int fft_len, int compute_dtype,
+                                 void* out, int out_dtype, int64_t n_out);
 
 /* ---- low-dimensional compression (analysis side) --------------------------------------------- */
 typedef struct mpb_mel mpb_mel;

@@ -38,12 +38,15 @@ SIGNATURES = {
     'mpb_analysis_lossless_dev': [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int,
                                   _vp, _vp, _vp, C.c_int],
     'mpb_analysis_lossless_host': [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp],
+    'mpb_analysis_lossless_host2': [_vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int],
     'mpb_frames_fft_dev': [_vp, _vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_int],
     'mpb_frames_fft_host': [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp],
     'mpb_plan_ola_runs': [_vp, _vp, _i32, C.c_int, _i32, _vp, _i64, C.POINTER(_i64)],
     'mpb_synthesis_lossless_dev': [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _vp, _i32, _vp, _i32,
                                    C.c_int, C.c_int, _vp, C.c_int, _i64],
     'mpb_synthesis_lossless_host': [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, C.c_int, C.c_int, _vp, _i64],
+    'mpb_synthesis_lossless_host2': [_vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _vp, _vp, _i32, C.c_int, C.c_int, _vp, C.c_int,
+                                     _i64],
     'mpb_mel_create': [_vp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, C.POINTER(_vp)],
     'mpb_mel_destroy': [_vp],
     'mpb_mel_get_warp_matrix': [_vp, C.c_int, _vp],

@@ -189,9 +189,11 @@ int mpb::check_frames_host(const int64_t* centre, const int32_t* left, const int
 
 extern "C" {
 
-static int frames_host(mpb_ctx* ctx, const double* sig, int64_t n_sig, const int64_t* centre, const int32_t* left,
+// sig_dtype: MPB_F64 (narrowed on the host when that is exact), MPB_F32 or MPB_I16 (PCM16, scaled by 1/32768 on the device);
+// out_dtype: element type of the host output matrices
+static int frames_host(mpb_ctx* ctx, const void* sig, int sig_in_dtype, int64_t n_sig, const int64_t* centre, const int32_t* left,
                        const int32_t* right, const uint8_t* win, int64_t nfrm, int fft_len, int compute_dtype,
-                       double* o0, double* o1, double* o2, int mode) {
+                       void* o0, void* o1, void* o2, int out_dtype, int mode) {
     if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
     if (nfrm == 0) return MPB_OK;
     if (!fft_len_ok(fft_len)) return fail(MPB_ERR_FFT_LEN, "fft_len must be 1024, 2048 or 4096");
@@ -201,7 +203,8 @@ static int frames_host(mpb_ctx* ctx, const double* sig, int64_t n_sig, const int
     CU(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> lk(ctx->mu);
     const int64_t H = fft_len / 2 + 1;
-    const size_t osz = sizeof(double) * (size_t)nfrm * H * (mode == MODE_FFT ? 2 : 1);
+    if (!sig_dtype_ok(sig_in_dtype) || !dtype_ok(out_dtype)) return fail(MPB_ERR_BAD_ARG, "unknown dtype");
+    const size_t osz = (out_dtype == MPB_F64 ? 8 : 4) * (size_t)nfrm * H * (mode == MODE_FFT ? 2 : 1);
     DevBuf* b = ctx->scratch;
     CU(b[0].need(sizeof(double) * n_sig));
     CU(b[1].need(sizeof(int64_t) * nfrm));
@@ -212,7 +215,16 @@ static int frames_host(mpb_ctx* ctx, const double* sig, int64_t n_sig, const int
     if (mode == MODE_FEATS) { CU(b[6].need(osz)); CU(b[7].need(osz)); }
     cudaStream_t st = ctx->stream;
     int sig_dtype = MPB_F64;
-    rc = upload_signals(ctx, st, &sig, &n_sig, 1, b[0].p, &sig_dtype);
+    if (sig_in_dtype == MPB_F64) {
+        const double* sd = (const double*)sig;
+        rc = upload_signals(ctx, st, &sd, &n_sig, 1, b[0].p, &sig_dtype);
+    } else {
+        // narrow element types: staged as they are; int16 lands in the upper half of the buffer and is converted in front
+        const int32_t end = 1;
+        sig_dtype = MPB_F32;
+        rc = upload_signal_groups_narrow(ctx, st, &sig, sig_in_dtype, &n_sig, 1, &end, 1, b[0].p, (char*)b[0].p + 4 * (size_t)n_sig,
+                                         [](int32_t, int) { return (int)MPB_OK; });
+    }
     if (rc != MPB_OK) return rc;
     CU(cudaMemcpyAsync(b[1].p, centre, sizeof(int64_t) * nfrm, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b[2].p, left, sizeof(int32_t) * nfrm, cudaMemcpyHostToDevice, st));
@@ -220,7 +232,7 @@ static int frames_host(mpb_ctx* ctx, const double* sig, int64_t n_sig, const int
     if (win) CU(cudaMemcpyAsync(b[4].p, win, (size_t)nfrm, cudaMemcpyHostToDevice, st));
     rc = analysis_common(ctx, st, b[0].p, sig_dtype, n_sig, (const int64_t*)b[1].p, (const int32_t*)b[2].p,
                          (const int32_t*)b[3].p, win ? (const uint8_t*)b[4].p : nullptr, nfrm, fft_len, compute_dtype,
-                         b[5].p, b[6].p, b[7].p, MPB_F64, mode);
+                         b[5].p, b[6].p, b[7].p, out_dtype, mode);
     if (rc != MPB_OK) return rc;
     CU(cudaMemcpyAsync(o0, b[5].p, osz, cudaMemcpyDeviceToHost, st));
     if (mode == MODE_FEATS) {
@@ -235,15 +247,25 @@ int mpb_analysis_lossless_host(mpb_ctx* ctx, const double* sig, int64_t n_sig, c
                                const int32_t* left, const int32_t* right, const uint8_t* win, int64_t nfrm,
                                int fft_len, int compute_dtype, double* out_mag, double* out_real, double* out_imag) {
     if (nfrm > 0 && (!out_real || !out_imag)) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
-    return frames_host(ctx, sig, n_sig, centre, left, right, win, nfrm, fft_len, compute_dtype, out_mag, out_real,
-                       out_imag, MODE_FEATS);
+    return frames_host(ctx, sig, MPB_F64, n_sig, centre, left, right, win, nfrm, fft_len, compute_dtype, out_mag, out_real,
+                       out_imag, MPB_F64, MODE_FEATS);
+}
+
+// mpb_analysis_lossless_host with the caller's element types: signal float64 / float32 / int16 PCM (sig_dtype), feature
+// matrices float64 or float32 (out_dtype; the reference's .mag/.real/.imag files are float32, src/libutils.py:122-127).
+int mpb_analysis_lossless_host2(mpb_ctx* ctx, const void* sig, int sig_dtype, int64_t n_sig, const int64_t* centre,
+                                const int32_t* left, const int32_t* right, const uint8_t* win, int64_t nfrm, int fft_len,
+                                int compute_dtype, void* out_mag, void* out_real, void* out_imag, int out_dtype) {
+    if (nfrm > 0 && (!out_real || !out_imag)) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    return frames_host(ctx, sig, sig_dtype, n_sig, centre, left, right, win, nfrm, fft_len, compute_dtype, out_mag, out_real,
+                       out_imag, out_dtype, MODE_FEATS);
 }
 
 int mpb_frames_fft_host(mpb_ctx* ctx, const double* sig, int64_t n_sig, const int64_t* centre, const int32_t* left,
                         const int32_t* right, const uint8_t* win, int64_t nfrm, int fft_len, int compute_dtype,
                         double* out_fft) {
-    return frames_host(ctx, sig, n_sig, centre, left, right, win, nfrm, fft_len, compute_dtype, out_fft, nullptr,
-                       nullptr, MODE_FFT);
+    return frames_host(ctx, sig, MPB_F64, n_sig, centre, left, right, win, nfrm, fft_len, compute_dtype, out_fft, nullptr,
+                       nullptr, MPB_F64, MODE_FFT);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -312,7 +334,18 @@ int mpb_synthesis_lossless_host(mpb_ctx* ctx, const double* mag, const double* r
                                 const int32_t* pm, int64_t nfrm_total, const int64_t* utt_frm_off,
                                 const int64_t* utt_out_off, const int32_t* utt_t0, int32_t n_utt, int fft_len,
                                 int compute_dtype, double* out, int64_t n_out) {
+    return mpb_synthesis_lossless_host2(ctx, mag, real, imag, MPB_F64, pm, nfrm_total, utt_frm_off, utt_out_off, utt_t0, n_utt,
+                                        fft_len, compute_dtype, out, MPB_F64, n_out);
+}
+
+// mpb_synthesis_lossless_host with float64 or float32 feature matrices (feat_dtype) and waveform (out_dtype).
+int mpb_synthesis_lossless_host2(mpb_ctx* ctx, const void* mag, const void* real, const void* imag, int feat_dtype,
+                                 const int32_t* pm, int64_t nfrm_total, const int64_t* utt_frm_off,
+                                 const int64_t* utt_out_off, const int32_t* utt_t0, int32_t n_utt, int fft_len,
+                                 int compute_dtype, void* out, int out_dtype, int64_t n_out) {
     if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (!dtype_ok(feat_dtype) || !dtype_ok(out_dtype)) return fail(MPB_ERR_BAD_ARG, "unknown dtype");
+    const size_t fes = feat_dtype == MPB_F64 ? 8 : 4, oes = out_dtype == MPB_F64 ? 8 : 4;
     if (!fft_len_ok(fft_len)) return fail(MPB_ERR_FFT_LEN, "fft_len must be 1024, 2048 or 4096");
     if (n_out == 0) return MPB_OK;
     if (!mag || !real || !imag || !pm || !utt_frm_off || !utt_out_off || !utt_t0 || !out)
@@ -331,14 +364,14 @@ int mpb_synthesis_lossless_host(mpb_ctx* ctx, const double* mag, const double* r
     CU(cudaSetDevice(ctx->device));
     std::unique_lock<std::mutex> lk(ctx->mu);
     const int64_t H = fft_len / 2 + 1;
-    const size_t fsz = sizeof(double) * (size_t)nfrm_total * H;
+    const size_t fsz = fes * (size_t)nfrm_total * H;
     DevBuf* b = ctx->scratch;
     CU(b[5].need(fsz)); CU(b[6].need(fsz)); CU(b[7].need(fsz));
     CU(b[1].need(sizeof(int32_t) * nfrm_total));
     CU(b[2].need(sizeof(int64_t) * (n_utt + 1)));
     CU(b[3].need(sizeof(int32_t) * (n_utt + 1)));
     CU(b[8].need(sizeof(int32_t) * 4 * (size_t)n_runs));
-    CU(b[0].need(sizeof(double) * n_out));
+    CU(b[0].need(oes * n_out));
     cudaStream_t st = ctx->stream;
     CU(cudaMemcpyAsync(b[5].p, mag, fsz, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b[6].p, real, fsz, cudaMemcpyHostToDevice, st));
@@ -347,11 +380,11 @@ int mpb_synthesis_lossless_host(mpb_ctx* ctx, const double* mag, const double* r
     CU(cudaMemcpyAsync(b[2].p, utt_out_off, sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b[3].p, utt_t0, sizeof(int32_t) * n_utt, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b[8].p, runs.data(), sizeof(int32_t) * 4 * (size_t)n_runs, cudaMemcpyHostToDevice, st));
-    rc = mpb_synthesis_lossless_dev(ctx, st, b[5].p, b[6].p, b[7].p, MPB_F64, (const int32_t*)b[1].p, nfrm_total,
+    rc = mpb_synthesis_lossless_dev(ctx, st, b[5].p, b[6].p, b[7].p, feat_dtype, (const int32_t*)b[1].p, nfrm_total,
                                     (const int64_t*)b[2].p, (const int32_t*)b[3].p, n_utt, (const int32_t*)b[8].p,
-                                    (int32_t)n_runs, fft_len, compute_dtype, b[0].p, MPB_F64, n_out);
+                                    (int32_t)n_runs, fft_len, compute_dtype, b[0].p, out_dtype, n_out);
     if (rc != MPB_OK) return rc;
-    CU(cudaMemcpyAsync(out, b[0].p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out, b[0].p, oes * n_out, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return MPB_OK;
 }

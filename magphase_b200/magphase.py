@@ -210,9 +210,13 @@ def _analysis_geometry_c(l_pm_smpls, l_n_smpls, l_voi, fs):
 # ----------------------------------------------------------------------------------------------
 # analysis
 # ----------------------------------------------------------------------------------------------
-def _frames_call(l_sig, l_pm, fft_len, l_win, mode, compute=None):
-    """Shared driver of the analysis kernels for a list of utterances (host buffers in, host buffers out)."""
+def _frames_call(l_sig, l_pm, fft_len, l_win, mode, compute=None, out_dtype=np.float64):
+    """Shared driver of the analysis kernels for a list of utterances (host buffers in, host buffers out).  Signals that
+    are ALL int16 (PCM as the wav file holds it) or ALL float32 travel as they are; out_dtype float32 halves the feature bytes."""
     compute = ANALYSIS_COMPUTE if compute is None else compute
+    out_dtype = np.dtype(out_dtype)
+    if out_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+        raise ValueError('out_dtype must be float64 or float32')
     H = fft_len // 2 + 1
     sig_off = _seg_offsets([s.size for s in l_sig])
     pm, left64, right64, frm_off = batch_frame_geometry(l_pm, [s.size for s in l_sig])
@@ -227,19 +231,25 @@ def _frames_call(l_sig, l_pm, fft_len, l_win, mode, compute=None):
     if any(w is not None for w in wins):
         win = np.ascontiguousarray(np.concatenate([w if w is not None else np.zeros(int(k), np.uint8)
                                                    for w, k in zip(wins, nfr)]), dtype=np.uint8)
-    sig_all = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.float64) for s in l_sig]))
+    kinds = {np.asarray(s).dtype for s in l_sig}
+    sig_np = kinds.pop() if len(kinds) == 1 and next(iter(kinds)) in (np.dtype(np.int16), np.dtype(np.float32)) else np.dtype(np.float64)
+    sig_code = {np.dtype(np.float64): MPB_F64, np.dtype(np.float32): MPB_F32, np.dtype(np.int16): _lib.MPB_I16}[sig_np]
+    sig_all = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=sig_np) for s in l_sig]))
     nfrm = centre.size
     l = _lib.lib()
     if mode == 'fft':
+        sig_all = np.ascontiguousarray(sig_all if sig_np == np.dtype(np.float64) else
+                                       (sig_all.astype(np.float64) / 32768.0 if sig_np == np.dtype(np.int16) else sig_all), dtype=np.float64)
         out = np.empty((nfrm, H), dtype=np.complex128)
         _lib.check(l.mpb_frames_fft_host(_lib.ctx(), _lib.ptr(sig_all), sig_all.size, _lib.ptr(centre), _lib.ptr(left),
                                          _lib.ptr(right), _lib.ptr(win), nfrm, fft_len, compute, _lib.ptr(out)))
         outs = (out,)
     else:
-        outs = tuple(_lib.pinned.empty((nfrm, H)) for _ in range(3))
-        _lib.check(l.mpb_analysis_lossless_host(_lib.ctx(), _lib.ptr(sig_all), sig_all.size, _lib.ptr(centre),
-                                                _lib.ptr(left), _lib.ptr(right), _lib.ptr(win), nfrm, fft_len, compute,
-                                                _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2])))
+        outs = tuple(_lib.pinned.empty((nfrm, H), dtype=out_dtype) for _ in range(3))
+        _lib.check(l.mpb_analysis_lossless_host2(_lib.ctx(), _lib.ptr(sig_all), sig_code, sig_all.size, _lib.ptr(centre),
+                                                 _lib.ptr(left), _lib.ptr(right), _lib.ptr(win), nfrm, fft_len, compute,
+                                                 _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]),
+                                                 MPB_F32 if out_dtype == np.dtype(np.float32) else MPB_F64))
     return outs, shifts, frm_off
 
 
@@ -275,13 +285,16 @@ def analysis_lossless_from_pm(v_sig, fs, v_pm_smpls, v_voi, fft_len=None):
     return m_mag, m_real, m_imag, v_f0, fs, v_shift
 
 
-def analysis_lossless_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None):
+def analysis_lossless_batch(l_sig, fs, l_pm_smpls, l_voi, fft_len=None, out_dtype=np.float64):
     """Batched analysis_lossless_from_pm: one kernel launch for all utterances.
-    Returns a list of (m_mag, m_real, m_imag, v_f0, fs, v_shift), the arrays being views into three batch matrices."""
+    Returns a list of (m_mag, m_real, m_imag, v_f0, fs, v_shift), the arrays being views into three batch matrices.
+    Element types on request, as for the compressed chain: int16 (PCM16 of the wav file) or float32 signals are uploaded as
+    they are, ``out_dtype=np.float32`` returns float32 feature matrices -- the precision of the reference's own feature files
+    (src/libutils.py:122-127) and half of the 98 KB per frame that otherwise cross PCIe.  The butterflies stay float64."""
     if fft_len is None:
         fft_len = define_fft_len(fs)
     (mag, real, imag), shifts, off = _frames_call([np.asarray(s) for s in l_sig], l_pm_smpls, fft_len,
-                                                  [np.hanning] * len(l_sig), 'feats')
+                                                  [np.hanning] * len(l_sig), 'feats', out_dtype=out_dtype)
     out = []
     for u in range(len(l_sig)):
         a, b = off[u], off[u + 1]
@@ -349,8 +362,12 @@ def ola_geometry(v_pm, fft_len):
     return v_pm.astype(np.int32), t0, n_out
 
 
-def _synthesis_lossless_call(l_feats, l_pm_int, l_t0, l_nout, fft_len, compute=None):
+def _synthesis_lossless_call(l_feats, l_pm_int, l_t0, l_nout, fft_len, compute=None, out_dtype=np.float64):
     compute = SYNTHESIS_COMPUTE if compute is None else compute
+    out_dtype = np.dtype(out_dtype)
+    if out_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+        raise ValueError('out_dtype must be float64 or float32')
+    feat_np = np.float32 if all(np.asarray(f[i]).dtype == np.float32 for f in l_feats for i in range(3)) else np.float64
     n_utt = len(l_feats)
     frm_off = np.zeros(n_utt + 1, dtype=np.int64)
     out_off = np.zeros(n_utt + 1, dtype=np.int64)
@@ -358,16 +375,17 @@ def _synthesis_lossless_call(l_feats, l_pm_int, l_t0, l_nout, fft_len, compute=N
         frm_off[u + 1] = frm_off[u] + l_pm_int[u].size
         out_off[u + 1] = out_off[u] + l_nout[u]
     # zero-copy when the rows already sit back to back (the blocks analysis_lossless_batch returns live in pinned memory)
-    mag, real, imag = (_stack_rows([f[i] for f in l_feats]) for i in range(3))
+    mag, real, imag = (_stack_rows([f[i] for f in l_feats], feat_np) for i in range(3))
     H = fft_len // 2 + 1
     if mag.shape[1] != H or real.shape != mag.shape or imag.shape != mag.shape:
         raise ValueError('feature matrices must be nfrms x %d' % H)
     pm = np.ascontiguousarray(np.concatenate(l_pm_int), dtype=np.int32)
     t0 = np.ascontiguousarray(l_t0, dtype=np.int32)
-    out = _lib.pinned.empty(int(out_off[-1]))
-    _lib.check(_lib.lib().mpb_synthesis_lossless_host(
-        _lib.ctx(), _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), _lib.ptr(pm), pm.size, _lib.ptr(frm_off),
-        _lib.ptr(out_off), _lib.ptr(t0), n_utt, fft_len, compute, _lib.ptr(out), out.size))
+    out = _lib.pinned.empty(int(out_off[-1]), dtype=out_dtype)
+    code = lambda dt: MPB_F32 if np.dtype(dt) == np.dtype(np.float32) else MPB_F64
+    _lib.check(_lib.lib().mpb_synthesis_lossless_host2(
+        _lib.ctx(), _lib.ptr(mag), _lib.ptr(real), _lib.ptr(imag), code(feat_np), _lib.ptr(pm), pm.size, _lib.ptr(frm_off),
+        _lib.ptr(out_off), _lib.ptr(t0), n_utt, fft_len, compute, _lib.ptr(out), code(out_dtype), out.size))
     return [out[out_off[u]:out_off[u + 1]] for u in range(n_utt)]
 
 
@@ -376,8 +394,9 @@ def synthesis_from_lossless(m_mag, m_real, m_imag, v_f0, fs):
     return synthesis_from_lossless_batch([(m_mag, m_real, m_imag, v_f0)], fs)[0]
 
 
-def synthesis_from_lossless_batch(l_feats, fs):
-    """Batched synthesis_from_lossless; l_feats is a list of (m_mag, m_real, m_imag, v_f0)."""
+def synthesis_from_lossless_batch(l_feats, fs, out_dtype=np.float64):
+    """Batched synthesis_from_lossless; l_feats is a list of (m_mag, m_real, m_imag, v_f0).  Feature matrices that are
+    ALL float32 cross PCIe as float32; ``out_dtype=np.float32`` returns float32 waveforms."""
     l_pm, l_t0, l_n = [], [], []
     fft_len = None
     for (m_mag, m_real, m_imag, v_f0) in l_feats:
@@ -392,7 +411,7 @@ def synthesis_from_lossless_batch(l_feats, fs):
         l_pm.append(pm_int)
         l_t0.append(t0)
         l_n.append(n_out)
-    return _synthesis_lossless_call(l_feats, l_pm, l_t0, l_n, fft_len)
+    return _synthesis_lossless_call(l_feats, l_pm, l_t0, l_n, fft_len, out_dtype=out_dtype)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -113,3 +113,29 @@ def test_narrow_element_types_on_request(mp):
     z32 = mp.synthesis_from_compressed_batch(feats32, 48000, b_out_hpf=True, out_dtype=np.float32)
     for a, b in zip(z32, z64):
         assert rms(a, b) < 1e-6
+
+
+def test_lossless_narrow_element_types_on_request(mp):
+    """The lossless chain with the reference's file formats: PCM16 / float32 signals in, float32 feature matrices out
+    (.mag/.real/.imag are float32 files), float32 features in, float32 waveform out.  Same kernels and float64 butterflies:
+    the features equal the float64 API's within float32 rounding, and so does the waveform of float32 features."""
+    utts = _batch(n=3, dur=0.5)[:3]
+    utts = [(np.round(s * 32768.0) / 32768.0, pm, voi) for s, pm, voi in utts]          # PCM16-exact samples
+    pcm = [np.round(u[0] * 32768.0).astype(np.int16) for u in utts]
+    pms, vois = [u[1] for u in utts], [u[2] for u in utts]
+    ref = mp.analysis_lossless_batch([u[0] for u in utts], 48000, pms, vois)
+    for sigs in (pcm, [u[0].astype(np.float32) for u in utts]):
+        got = mp.analysis_lossless_batch(sigs, 48000, pms, vois, out_dtype=np.float32)
+        for g, r in zip(got, ref):
+            for a, b in zip(g[:3], r[:3]):
+                # (float32 rows are normalised in float32 arithmetic after the float64 butterflies: within an ulp or two of
+                #  the float64 rows, not their rounding)
+                assert a.dtype == np.float32 and a.shape == b.shape
+                assert np.max(np.abs(a - b)) <= 4e-7 * max(1.0, float(np.max(np.abs(b)))) and rms(a, b) < 1e-7 * max(1.0, rms(b, 0 * b))
+            assert np.array_equal(g[3], r[3]) and np.array_equal(g[5], r[5]) and g[3].dtype == np.float64
+    y64 = mp.synthesis_from_lossless_batch([r[:4] for r in ref], 48000)
+    y32 = mp.synthesis_from_lossless_batch([g[:4] for g in got], 48000, out_dtype=np.float32)
+    for a, b in zip(y32, y64):
+        assert a.dtype == np.float32 and a.shape == b.shape and rms(a, b) < 2e-7
+    with pytest.raises(ValueError):
+        mp.analysis_lossless_batch(pcm, 48000, pms, vois, out_dtype=np.int16)
