@@ -44,6 +44,10 @@ extern "C" {
 /* window applied to each side of a pitch-synchronous frame (mpb_frames_*) */
 #define MPB_WIN_HANN 0            /* np.hanning halves               src/libaudio.py:70-84 */
 #define MPB_WIN_BARTLETT25 1      /* np.bartlett(.)**2.5 halves      src/magphase.py:67-69 */
+#define MPB_WIN_RECT 2            /* weight 1: the frame's samples already carry their window.  How an arbitrary win_func
+                                     callable (src/magphase.py:102-108) reaches the kernels: the caller lays the windowed
+                                     frames sig[P[f] .. P[f+2]] * gen_non_symmetric_win(l, r, win_func) back to back in
+                                     `sig` and points centre[f] at the frame's own mark inside that buffer */
 
 typedef struct mpb_ctx mpb_ctx;
 

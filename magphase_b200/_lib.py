@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libmagphase_b200.so')
 
 MPB_F32, MPB_F64, MPB_I16 = 0, 1, 2
-WIN_HANN, WIN_BARTLETT25 = 0, 1
+WIN_HANN, WIN_BARTLETT25, WIN_RECT = 0, 1, 2
 _VALUE_ERRORS = (-1, -2, -3, -6)
 
 _lib = None

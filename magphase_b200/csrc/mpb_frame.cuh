@@ -43,6 +43,8 @@ __device__ __forceinline__ float hann_side_f32(float x) {
 // value of the side window at distance j from the peak; inv_s = 1 / side length (j <= side length):
 //   Hann       : 0.5 + 0.5 cos(pi j / S) = 0.5 - 0.5 sin(pi (j/S - 0.5))   (np.hanning(2S+1) halves; hanning(1) = [1])
 //   Bartlett2.5: (1 - j/S)^2.5                                           (np.bartlett(2S+1)**2.5 halves)
+//   Rect       : 1 -- the caller's samples already carry the window (arbitrary win_func callables, evaluated on the
+//                host and multiplied in by the mirror module: src/magphase.py:102-108)
 template <typename T>
 __device__ __forceinline__ T side_window(int j, double inv_s, int kind) {
     if (j == 0) return (T)1;
@@ -50,11 +52,13 @@ __device__ __forceinline__ T side_window(int j, double inv_s, int kind) {
         // float32 frames (the noise branch of compressed synthesis): float32 window arithmetic is enough
         const float x = (float)j * (float)inv_s;
         if (kind == MPB_WIN_HANN) return (T)hann_side_f32(x);
+        if (kind == MPB_WIN_RECT) return (T)1;
         const float b = 1.0f - x;
         return (T)(b * b * sqrtf(b));
     }
     const double x = (double)j * inv_s;
     if (kind == MPB_WIN_HANN) return (T)(0.5 - 0.5 * sinpi_half(x - 0.5));
+    if (kind == MPB_WIN_RECT) return (T)1;
     const double b = 1.0 - x;
     return (T)(b * b * sqrt(b));
 }

@@ -262,7 +262,8 @@ def griffin_lim(m_mag, v_shift, win_func=np.hanning, phase_init='random', niters
     P, left, right = mp.frame_geometry(v_pm, n_out)
     if np.any(left > N // 2) or np.any(right >= N // 2):          # la.frame_shift gets a negative pad (src/libaudio.py:137-140)
         raise ValueError('negative dimensions are not allowed')
-    kinds = mp._win_codes(win_func, nfrms)
+    custom = mp._has_custom_window(win_func)
+    kinds = None if custom else mp._win_codes(win_func, nfrms)
 
     # ---- initial spectrum, as the first synthesis sees it (src/magphase.py:3330-3347, :3356-3357) ----
     sgn = np.where(np.arange(H) % 2 == 0, 1.0, -1.0)
@@ -307,6 +308,16 @@ def griffin_lim(m_mag, v_shift, win_func=np.hanning, phase_init='random', niters
     d_out_off, d_t0 = up(np.array([0, n_out]), np.int64), up(np.array([t0]), np.int32)
     d_centre, d_left, d_right = up(P[1:-1], np.int64), up(left, np.int32), up(right, np.int32)
     d_win = up(kinds, np.uint8) if kinds is not None else None
+    n_ana = n_out
+    if custom:
+        # a window the kernels do not evaluate themselves (any callable, src/magphase.py:102-108): its weights and the
+        # gather indices of the frames are fixed over the iterations; every analysis half runs on sig[idx] * w with weight 1
+        w_all, w_off = mp.window_weights(mp._win_list(win_func, nfrms), left, right)
+        idx = np.repeat(P[1:-1] - left - w_off[:-1], np.diff(w_off)) + np.arange(w_all.size, dtype=np.int64)
+        d_idx, d_w = up(idx, np.int64), up(w_all, np.float64)
+        d_centre = up(w_off[:-1] + left, np.int64)
+        d_win = up(np.full(nfrms, _lib.WIN_RECT), np.uint8)
+        n_ana = int(w_all.size)
     d_mag_t, d_mag0 = up(m_mag, np.float64), up(mag0, np.float64)
     d_re, d_im = up(u0.real, np.float64), up(u0.imag, np.float64)
     d_mag_w = torch.empty_like(d_mag_t)
@@ -320,7 +331,8 @@ def griffin_lim(m_mag, v_shift, win_func=np.hanning, phase_init='random', niters
                                                       _dp(d_sig), MPB_F64, n_out))
             if it == niters - 1:
                 break
-            _lib.check(lib.mpb_analysis_lossless_dev(ctx, st, _dp(d_sig), MPB_F64, n_out, _dp(d_centre), _dp(d_left),
+            d_ana = (d_sig[:n_out][d_idx] * d_w) if custom else d_sig
+            _lib.check(lib.mpb_analysis_lossless_dev(ctx, st, _dp(d_ana), MPB_F64, n_ana, _dp(d_centre), _dp(d_left),
                                                      _dp(d_right), _dp(d_win), nfrms, N, MPB_F64, _dp(d_mag_w), _dp(d_re),
                                                      _dp(d_im), MPB_F64))
         v_sig = d_sig[:n_out].cpu().numpy()

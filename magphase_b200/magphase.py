@@ -22,7 +22,7 @@ import numpy as np
 
 from . import _lib
 from . import hostio as io
-from ._lib import MPB_F32, MPB_F64, WIN_BARTLETT25, WIN_HANN
+from ._lib import MPB_F32, MPB_F64, WIN_BARTLETT25, WIN_HANN, WIN_RECT
 
 MAGIC = -1.0e10   # src/libaudio.py:17
 
@@ -105,20 +105,78 @@ def frame_geometry(v_pm_smpls, n_smpls):
     return P, (P[1:-1] - P[:-2]), (P[2:] - P[1:-1])
 
 
-def _win_codes(win_func, n):
-    """Map the reference's win_func argument (a function or a per-frame list) to per-frame kernel codes."""
-    def one(f):
-        if f is np.hanning or f == 'hann':
-            return WIN_HANN
-        if f is voi_noise_window or f == 'bartlett2.5':
-            return WIN_BARTLETT25
-        raise ValueError('win_func %r is not available on the CUDA path (np.hanning / voi_noise_window only)' % (f,))
+def _win_builtin(f):
+    """Kernel code of a window the kernels evaluate in closed form, None for any other callable."""
+    if f is np.hanning or (isinstance(f, str) and f == 'hann'):
+        return WIN_HANN
+    if f is voi_noise_window or (isinstance(f, str) and f == 'bartlett2.5'):
+        return WIN_BARTLETT25
+    if callable(f):
+        return None
+    raise ValueError('win_func %r is neither a window function nor a list of window functions' % (f,))
+
+
+def _win_list(win_func, n):
     if isinstance(win_func, (list, tuple)):
         if len(win_func) != n:
             raise ValueError('win_func list length must equal the number of frames')
-        return np.array([one(f) for f in win_func], dtype=np.uint8)
-    code = one(win_func)
-    return None if code == WIN_HANN else np.full(n, code, dtype=np.uint8)
+        return list(win_func)
+    return [win_func] * n
+
+
+def _has_custom_window(win_func):
+    """True when win_func (a function or a per-frame list, src/magphase.py:102-108) names a window the kernels do not
+    evaluate themselves."""
+    fs = win_func if isinstance(win_func, (list, tuple)) else (win_func,)
+    return any(_win_builtin(f) is None for f in fs)
+
+
+def _win_codes(win_func, n):
+    """Map the reference's win_func argument (a function or a per-frame list) to per-frame kernel codes; None = all Hann.
+    Only for the two windows the kernels evaluate in closed form (see _has_custom_window / window_weights for the rest)."""
+    codes = [_win_builtin(f) for f in _win_list(win_func, n)]
+    if any(c is None for c in codes):
+        raise ValueError('arbitrary window callables go through window_weights(), not through kernel codes')
+    if all(c == WIN_HANN for c in codes):
+        return None
+    return np.array(codes, dtype=np.uint8)
+
+
+def window_weights(l_fns, left, right):
+    """The windows la.gen_non_symmetric_win(left[f], right[f], l_fns[f]) of all frames back to back (float64) and their
+    offsets: hstack(w(1+2l)[0:l+1], flipud(w(1+2r)[0:r+1])[1:]) per frame (src/libaudio.py:70-84), evaluated by the
+    caller's own callables once per distinct (function, side length).  This is how arbitrary ``win_func`` arguments reach
+    the kernels: the mirror multiplies the weights into the frames' samples and launches with MPB_WIN_RECT."""
+    left = np.asarray(left, dtype=np.int64)
+    right = np.asarray(right, dtype=np.int64)
+    off = _seg_offsets(left + right + 1)
+    w_all = np.empty(int(off[-1]), dtype=np.float64)
+    halves = {}
+
+    def half(fn, s):
+        key = (id(fn), s)
+        h = halves.get(key)
+        if h is None:
+            fn_ = {WIN_HANN: np.hanning, WIN_BARTLETT25: voi_noise_window}.get(_win_builtin(fn), fn)
+            h = np.asarray(fn_(1 + 2 * s), dtype=np.float64)
+            if h.shape != (1 + 2 * s,):
+                raise ValueError('win_func(%d) must return %d values' % (1 + 2 * s, 1 + 2 * s))
+            h = halves[key] = h[:s + 1]
+        return h
+    for f in range(left.size):
+        l, r, a = int(left[f]), int(right[f]), int(off[f])
+        w_all[a:a + l + 1] = half(l_fns[f], l)
+        w_all[a + l + 1:a + l + 1 + r] = half(l_fns[f], r)[::-1][1:]
+    return w_all, off
+
+
+def prewindowed_frames(sig_all, centre, left, right, l_fns):
+    """Frames sig[c-l .. c+r] * window laid back to back, and the marks' positions inside that buffer (centre[f] must be
+    the absolute index of frame f's mark in sig_all).  Launch the analysis kernels on the result with MPB_WIN_RECT."""
+    w_all, off = window_weights(l_fns, left, right)
+    lens = np.diff(off)
+    idx = np.repeat(np.asarray(centre, dtype=np.int64) - left - off[:-1], lens) + np.arange(int(off[-1]), dtype=np.int64)
+    return np.asarray(sig_all, dtype=np.float64)[idx] * w_all, np.ascontiguousarray(off[:-1] + left), idx, w_all
 
 
 def voi_noise_window(length):
@@ -226,16 +284,25 @@ def _frames_call(l_sig, l_pm, fft_len, l_win, mode, compute=None, out_dtype=np.f
     left = left64.astype(np.int32)
     right = right64.astype(np.int32)
     shifts = [left64[frm_off[u]:frm_off[u + 1]] for u in range(len(l_sig))]
-    wins = [_win_codes(l_win[u], int(nfr[u])) for u in range(len(l_sig))]
-    win = None
-    if any(w is not None for w in wins):
-        win = np.ascontiguousarray(np.concatenate([w if w is not None else np.zeros(int(k), np.uint8)
-                                                   for w, k in zip(wins, nfr)]), dtype=np.uint8)
     kinds = {np.asarray(s).dtype for s in l_sig}
     sig_np = kinds.pop() if len(kinds) == 1 and next(iter(kinds)) in (np.dtype(np.int16), np.dtype(np.float32)) else np.dtype(np.float64)
-    sig_code = {np.dtype(np.float64): MPB_F64, np.dtype(np.float32): MPB_F32, np.dtype(np.int16): _lib.MPB_I16}[sig_np]
     sig_all = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=sig_np) for s in l_sig]))
     nfrm = centre.size
+    win = None
+    if any(_has_custom_window(w) for w in l_win):
+        # a window the kernels do not know in closed form: evaluate the caller's callables on the host, multiply them into
+        # the frames' samples (float64) and run the kernels with weight 1 on that buffer
+        fns = [f for u in range(len(l_sig)) for f in _win_list(l_win[u], int(nfr[u]))]
+        scale = 1.0 / 32768.0 if sig_np == np.dtype(np.int16) else 1.0
+        sig_all, centre, _, _ = prewindowed_frames(sig_all.astype(np.float64) * scale, centre, left64, right64, fns)
+        sig_np = np.dtype(np.float64)
+        win = np.full(nfrm, WIN_RECT, dtype=np.uint8)
+    else:
+        wins = [_win_codes(l_win[u], int(nfr[u])) for u in range(len(l_sig))]
+        if any(w is not None for w in wins):
+            win = np.ascontiguousarray(np.concatenate([w if w is not None else np.zeros(int(k), np.uint8)
+                                                       for w, k in zip(wins, nfr)]), dtype=np.uint8)
+    sig_code = {np.dtype(np.float64): MPB_F64, np.dtype(np.float32): MPB_F32, np.dtype(np.int16): _lib.MPB_I16}[sig_np]
     l = _lib.lib()
     if mode == 'fft':
         sig_all = np.ascontiguousarray(sig_all if sig_np == np.dtype(np.float64) else

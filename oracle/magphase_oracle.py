@@ -119,8 +119,11 @@ def side_window(length, kind):
 
     kind 'hann'        -> np.hanning              (src/libaudio.py:70-84)
     kind 'bartlett2.5' -> np.bartlett(.)**2.5     (src/magphase.py:67-69)
+    kind callable      -> kind(1 + 2*length)      (any win_func, src/libaudio.py:72-78)
     """
-    if kind == 'hann':
+    if callable(kind):
+        w = np.asarray(kind(1 + 2 * length), dtype=np.float64)
+    elif kind == 'hann':
         w = np.hanning(1 + 2 * length)
     elif kind == 'bartlett2.5':
         w = np.bartlett(1 + 2 * length) ** 2.5
@@ -178,11 +181,15 @@ def analysis_frames(v_sig, v_pm_smpls, fft_len, kinds=None):
     return m, v_shift, P
 
 
-def analysis_fft_from_pm(v_sig, fs, v_pm_smpls, fft_len=None):
-    """Half spectrum of every pitch-synchronous frame.  src/magphase.py:266-334"""
+def analysis_fft_from_pm(v_sig, fs, v_pm_smpls, fft_len=None, win_func=None):
+    """Half spectrum of every pitch-synchronous frame.  src/magphase.py:266-334
+    win_func: None (np.hanning), a callable or a per-frame list of callables / kind names (src/magphase.py:102-108)."""
     if fft_len is None:
         fft_len = define_fft_len(fs)
-    m_frms, v_shift, _ = analysis_frames(v_sig, v_pm_smpls, fft_len)
+    kinds = None
+    if win_func is not None:
+        kinds = list(win_func) if isinstance(win_func, (list, tuple)) else [win_func] * np.size(v_pm_smpls)
+    m_frms, v_shift, _ = analysis_frames(v_sig, v_pm_smpls, fft_len, kinds)
     m_fft = np.fft.fft(m_frms)[:, :fft_len // 2 + 1].copy()
     return m_fft, v_shift
 
@@ -614,8 +621,8 @@ def griffin_lim_initial_phase(m_mag, phase_init='random'):
     return herm(np.asarray(phase_init, dtype=np.float64))
 
 
-def griffin_lim(m_mag, v_shift, phase_init='random', niters=30):
-    """Pitch synchronous Griffin-Lim (win_func=np.hanning).  src/magphase.py:3318-3373.
+def griffin_lim(m_mag, v_shift, phase_init='random', niters=30, win_func='hann'):
+    """Pitch synchronous Griffin-Lim (win_func: np.hanning unless a callable is given).  src/magphase.py:3318-3373.
     Synthesis: ifft(mag * exp(j phase)).real rows overlap-added with the frame centre (column N/2) on the pitch marks,
     NO fftshift (:3356-3358).  Analysis: windowing() around the marks, frame placed with its mark at column N/2
     (la.frm_list_to_matrix, src/libaudio.py:122-140), fft, np.angle (:3364-3369).  Returns (v_sig, half phase)."""
@@ -636,7 +643,7 @@ def griffin_lim(m_mag, v_shift, phase_init='random', niters=30):
         m_frms = np.zeros((nfrms, N))
         for f in range(nfrms):
             l, r = int(v_l[f]), int(v_r[f])
-            frm = v_sig[P[f]:P[f + 2] + 1] * asym_window(l, r, 'hann')
+            frm = v_sig[P[f]:P[f + 2] + 1] * asym_window(l, r, win_func)
             a = N // 2 - l                                                 # rel_shift of la.frame_shift
             if a < 0 or a + frm.size > N:
                 raise ValueError('negative dimensions are not allowed')

@@ -41,6 +41,20 @@ def test_griffin_lim_vs_oracle(feats, init):
         assert np.max(phase_dist(ph, ph_ref)[strong]) < 1e-5, (init, niters)
 
 
+def test_griffin_lim_with_arbitrary_window(feats):
+    """win_func other than np.hanning (src/magphase.py:3318, :3362): the weights and gather indices are built once on the
+    host, every analysis half runs on sig[idx] * w with MPB_WIN_RECT."""
+    import magphase_b200.magphase as mp
+    mag, real, imag, shift = feats
+    for fn in (np.hamming, np.blackman):
+        y_ref, ph_ref = orc.griffin_lim(mag.copy(), shift, phase_init='linear', niters=5, win_func=fn)
+        y, ph = mp.griffin_lim(mag.copy(), shift, win_func=fn, phase_init='linear', niters=5)
+        assert y.shape == y_ref.shape
+        assert rms(y, y_ref) < 1e-9 * max(1.0, float(np.abs(y_ref).max())), rms(y, y_ref)
+        strong = mag > 1e-6 * mag.max()
+        assert np.max(phase_dist(ph, ph_ref)[strong]) < 1e-5
+
+
 def test_griffin_lim_reduces_inconsistency(feats):
     """The point of the algorithm: the spectrogram of the output gets closer to the target magnitude."""
     import magphase_b200.magphase as mp

@@ -111,6 +111,37 @@ def test_noise_window_kind(mp):
     assert rms(got, ref) < 1e-9
 
 
+def _offpeak_window(n):
+    """Neither of the two closed-form windows, and its centre value is not 1."""
+    return 0.9 * np.hamming(n) ** 1.5
+
+
+@pytest.mark.parametrize('win', ['hamming', 'blackman', 'offpeak', 'list'])
+def test_arbitrary_win_func(mp, win):
+    """win_func as any callable, or a per-frame list mixing callables with the built-ins (src/magphase.py:102-108): the
+    mirror evaluates the callables on the host and the kernels run with MPB_WIN_RECT on the weighted frames.  The marks
+    include a frame longer than fft_len (truncation branch) and a mark at sample 0."""
+    rng = np.random.default_rng(12)
+    sig = rng.uniform(-1, 1, 30000)
+    pm = np.concatenate(([0.0], np.cumsum(rng.integers(150, 700, 24)).astype(float), [16000.0, 21000.5, 29000.0]))
+    n = pm.size
+    fn = {'hamming': np.hamming, 'blackman': np.blackman, 'offpeak': _offpeak_window,
+          'list': [(np.hanning, np.hamming, _offpeak_window, mp.voi_noise_window)[f % 4] for f in range(n)]}[win]
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref, shift_ref = orc.analysis_fft_from_pm(sig, 48000, pm, win_func=fn)
+        got, shift = mp.analysis_with_del_comp_from_pm(sig, 48000, pm, win_func=fn)
+    assert np.array_equal(shift, shift_ref)
+    assert rms(got, ref) < 1e-9, rms(got, ref)
+    # PCM16 input takes the same route (scaled by 1/32768 on the host before the weights)
+    pcm = np.round(sig * 20000).astype(np.int16)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref16, _ = orc.analysis_fft_from_pm(pcm / 32768.0, 48000, pm, win_func=fn)
+        got16, _ = mp.analysis_with_del_comp_from_pm(pcm, 48000, pm, win_func=fn)
+    assert rms(got16, ref16) < 1e-9
+
+
 def test_synthesis_vs_oracle(mp):
     sig, pm, voi = synth_utterance(2, fs=48000, dur_s=1.0)
     mag, real, imag, f0, fs, _ = orc.analysis_lossless_from_pm(sig, 48000, pm, voi)

@@ -268,3 +268,46 @@ def test_intermediate_epochs_match_reference(ref_modules):
         v_pm = host._expand_epochs(np.asarray(pm, dtype=np.float64), nwin)
         _, v_shift, _ = host.frame_geometry(v_pm, sig.size)
         assert np.array_equal(v_shift, v_shift_ref), nwin
+
+
+def _tukeyish(n):
+    """A window that is neither symmetric-peaked at 1 nor one of the two built-ins (centre value 0.9)."""
+    return 0.9 * np.hamming(n) ** 1.5
+
+
+@pytest.mark.parametrize('win', ['hamming', 'blackman', 'custom', 'list'])
+def test_arbitrary_win_func_matches_reference(ref_modules, win):
+    """win_func as any callable or a per-frame list (src/magphase.py:102-108, src/libaudio.py:70-84): the oracle's
+    restatement and the mirror's host-side weights (window_weights / prewindowed_frames, which feed the kernels their
+    samples under MPB_WIN_RECT) against the reference's own windowing() and analysis."""
+    mp, la, lu = ref_modules
+    import magphase_b200.magphase as mpb
+    sig, pm, voi = synth_utterance(4, dur_s=0.5)
+    n = pm.size
+    fn = {'hamming': np.hamming, 'blackman': np.blackman, 'custom': _tukeyish,
+          'list': [(np.hanning, np.hamming, _tukeyish, mp.voi_noise_window)[f % 4] for f in range(n)]}[win]
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m_fft_r, v_shift_r = mp.analysis_with_del_comp_from_pm(sig, 48000, pm, win_func=fn)
+        m_fft, v_shift = orc.analysis_fft_from_pm(sig, 48000, pm, win_func=fn)
+    assert np.array_equal(v_shift, v_shift_r)
+    np.testing.assert_allclose(m_fft, m_fft_r, rtol=0, atol=1e-11)
+    # the host half of the CUDA path: frames times weights, laid back to back
+    l_frames, v_lens, P, v_shift_w, v_rights = mp.windowing(sig, pm, win_func=fn)
+    fns = mpb._win_list(fn, n)
+    pre, centre, idx, w_all = mpb.prewindowed_frames(sig, P[1:-1], v_shift_w, v_rights, fns)
+    assert pre.size == int(np.sum(v_lens))
+    np.testing.assert_array_equal(pre, np.concatenate(l_frames))
+    assert np.array_equal(centre, np.concatenate(([0], np.cumsum(v_lens)[:-1])) + v_shift_w)
+    assert np.array_equal(sig[idx] * w_all, pre)
+
+
+def test_griffin_lim_with_arbitrary_window_matches_reference(ref_modules):
+    mp, la, lu = ref_modules
+    sig, pm, voi = synth_utterance(8, dur_s=0.5)
+    mag, real, imag, f0, fs, shift = orc.analysis_lossless_from_pm(sig, 48000, pm, voi)
+    y_ref, ph_ref = mp.griffin_lim(mag.copy(), shift, win_func=np.hamming, phase_init='linear', niters=4)
+    y, ph = orc.griffin_lim(mag.copy(), shift, phase_init='linear', niters=4, win_func=np.hamming)
+    np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-12)
+    strong = mag > 1e-6 * mag.max()
+    assert np.max(np.abs(np.angle(np.exp(1j * (ph - ph_ref))))[strong]) < 1e-8
