@@ -13,13 +13,23 @@ Results are the same files the per-utterance wrappers write (``analysis_for_acou
 ``synthesis_from_acoustic_modelling``): feature files byte for byte; waveforms from the same NumPy noise stream, consumed
 in list order exactly like the reference's sequential loop (``b_multiproc = False``, its default for synthesis).
 
-    python -m magphase_b200.batch extract  --scp file_id.scp --wav-dir wavs --out-dir feats [--est-dir est]
-    python -m magphase_b200.batch generate --scp file_id.scp --feats-dir feats --out-dir wavs_syn --fs 48000
+Two things a 100k-utterance job needs that the reference's scripts leave to the operator (failure
+detection / checkpoint-resume rows): ``on_error='skip'`` isolates a token whose files cannot be read or whose marks are
+unusable -- it is appended to ``crash_file_list_<host>_<pid>.scp`` in the output directory (the convention of
+scripts/batch_convert_label_state_aligned_to_variable_frame_rate.py:48, 59-70) and the batch goes on without it; and
+``resume=True`` skips tokens whose output files are already complete (outputs are written under a temporary name and
+renamed, so a killed job never leaves a half-written file that looks finished).  A resumed generation run still draws the
+skipped utterances' share of the NumPy noise stream, so its waveforms are the ones an uninterrupted run writes.
+
+    python -m magphase_b200.batch extract  --scp file_id.scp --wav-dir wavs --out-dir feats [--est-dir est] [--resume] [--skip-errors]
+    python -m magphase_b200.batch generate --scp file_id.scp --feats-dir feats --out-dir wavs_syn --fs 48000 [--resume] [--skip-errors]
 """
 import argparse
 import concurrent.futures as cf
 import os
+import socket
 import time
+import warnings
 
 import numpy as np
 
@@ -46,50 +56,130 @@ def _load_utterance(in_wav_dir, est_dir, token):
     return v_sig, fs, v_pm_sec, v_voi
 
 
+def _feature_exts(b_const_rate):
+    return ('.mag', '.real', '.imag', '.lf0') + (() if b_const_rate else ('.shift',))
+
+
+def _atomically(write, path, *args):
+    """write(..., tmp) then rename: the final name only ever holds a complete file (what ``resume`` relies on).  The
+    temporary name keeps the extension (sf.write / wavfile pick the container from it)."""
+    d, base = os.path.split(path)
+    tmp = os.path.join(d, '.tmp%d_%s' % (os.getpid(), base))
+    try:
+        write(*args, tmp)
+        os.replace(tmp, path)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+
+
 def _write_features(out_dir, token, feats, b_const_rate):
-    m_mag_mel_log, m_real_mel, m_imag_mel, v_lf0, v_shift = feats[:5]
-    io.write_binfile(m_mag_mel_log, os.path.join(out_dir, token + '.mag'))
-    io.write_binfile(m_real_mel, os.path.join(out_dir, token + '.real'))
-    io.write_binfile(m_imag_mel, os.path.join(out_dir, token + '.imag'))
-    io.write_binfile(v_lf0, os.path.join(out_dir, token + '.lf0'))
-    if not b_const_rate:
-        io.write_binfile(v_shift, os.path.join(out_dir, token + '.shift'))
+    for ext, arr in zip(_feature_exts(b_const_rate), feats[:5]):
+        _atomically(io.write_binfile, os.path.join(out_dir, token + ext), arr)
+
+
+def _write_wav(path, y, fs):
+    _atomically(lambda y_, fs_, tmp: io.write_audio_file(tmp, y_, fs_), path, y, fs)
+
+
+def _complete(paths):
+    return all(os.path.isfile(p) and os.path.getsize(p) > 0 for p in paths)
+
+
+class _CrashList:
+    """Tokens that failed, appended (and flushed) one per line to crash_file_list_<host>_<pid>.scp as they happen."""
+
+    def __init__(self, out_dir):
+        self.path = os.path.join(out_dir, 'crash_file_list_%s_%d.scp' % (socket.gethostname(), os.getpid()))
+        self.tokens = []
+
+    def add(self, token, err):
+        self.tokens.append(token)
+        warnings.warn('%s: %s: %s (skipped, listed in %s)' % (token, type(err).__name__, err, self.path))
+        with open(self.path, 'a') as f:
+            f.write('%s # %s: %s\n' % (token, type(err).__name__, str(err).replace('\n', ' ')))
+
+
+def _collect(futures, tokens, on_error, crashes):
+    """Results of the per-token loader futures; with on_error='skip' a failing token goes to the crash list instead."""
+    ok_tokens, items = [], []
+    for t, f in zip(tokens, futures):
+        try:
+            items.append(f.result())
+            ok_tokens.append(t)
+        except Exception as e:                      # noqa: BLE001 -- any per-utterance failure is isolated, as the reference's label script does
+            if on_error != 'skip':
+                raise
+            crashes.add(t, e)
+    return ok_tokens, items
+
+
+def _check_on_error(on_error):
+    if on_error not in ('raise', 'skip'):
+        raise ValueError("on_error must be 'raise' or 'skip'")
 
 
 def run_feature_extraction(tokens, in_wav_dir, out_feats_dir, est_dir=None, fft_len=None, mag_dim=60, phase_dim=45,
-                           b_const_rate=False, batch_utts=64, io_threads=8, verbose=False):
+                           b_const_rate=False, batch_utts=64, io_threads=8, verbose=False, resume=False, on_error='raise'):
     """analysis_for_acoustic_modelling (src/magphase.py:2992-3022) for a list of file tokens (or an .scp path).
     Pitch marks come from ``<est_dir>/<token>.est`` when est_dir is given, else from the REAPER binary (as the reference).
-    Returns {'utterances', 'frames', 'seconds'}."""
+    resume / on_error: module docstring.  Returns {'utterances', 'frames', 'seconds', 'skipped', 'failed'}."""
+    _check_on_error(on_error)
     if isinstance(tokens, str):
         tokens = read_tokens(tokens)
+    tokens = list(tokens)
     os.makedirs(out_feats_dir, exist_ok=True)
+    skipped = []
+    if resume:
+        done = lambda t: _complete([os.path.join(out_feats_dir, t + e) for e in _feature_exts(b_const_rate)])
+        skipped = [t for t in tokens if done(t)]
+        gone = set(skipped)
+        tokens = [t for t in tokens if t not in gone]
+    crashes = _CrashList(out_feats_dir)
     t0 = time.perf_counter()
-    n_frames = 0
+    n_frames = n_done = 0
     with cf.ThreadPoolExecutor(max_workers=io_threads) as pool:
-        groups = list(_batches(list(tokens), batch_utts))
+        groups = list(_batches(tokens, batch_utts))
         load = lambda g: [pool.submit(_load_utterance, in_wav_dir, est_dir, t) for t in g]
         pending = load(groups[0]) if groups else []
         writes = []
         for k, g in enumerate(groups):
-            utts = [f.result() for f in pending]
+            g, utts = _collect(pending, g, on_error, crashes)
             pending = load(groups[k + 1]) if k + 1 < len(groups) else []      # disk reads overlap the GPU call below
+            if not utts:
+                continue
             fs = utts[0][1]
             if any(u[1] != fs for u in utts):
                 raise ValueError('all utterances of a batch must share the sample rate')
-            # the reference passes alpha_phase=b_mag_fbank_mel (= False, i.e. 0.0) at src/magphase.py:3010 -- replicated
-            outs = mp.analysis_compressed_batch([u[0] for u in utts], fs, [u[2] * fs for u in utts], [u[3] for u in utts],
-                                                fft_len=fft_len, mag_dim=mag_dim, phase_dim=phase_dim,
-                                                b_const_rate=b_const_rate, alpha_phase=False)
+            call = lambda uu: mp.analysis_compressed_batch(
+                [u[0] for u in uu], fs, [u[2] * fs for u in uu], [u[3] for u in uu], fft_len=fft_len, mag_dim=mag_dim,
+                phase_dim=phase_dim, b_const_rate=b_const_rate,
+                alpha_phase=False)     # the reference passes alpha_phase=b_mag_fbank_mel (= False, i.e. 0.0) at src/magphase.py:3010 -- replicated
+            try:
+                outs = call(utts)
+            except (ValueError, IndexError):
+                if on_error != 'skip':
+                    raise
+                # an utterance with unusable marks fails the argument checks of the whole batch: find it one by one
+                g2, outs = [], []
+                for t, u in zip(g, utts):
+                    try:
+                        outs.extend(call([u]))
+                        g2.append(t)
+                    except (ValueError, IndexError) as e:
+                        crashes.add(t, e)
+                g = g2
             for f in writes:
                 f.result()                                                    # surface write errors of batch k-1
             writes = [pool.submit(_write_features, out_feats_dir, t, o, b_const_rate) for t, o in zip(g, outs)]
             n_frames += sum(o[0].shape[0] for o in outs)
+            n_done += len(g)
             if verbose:
-                print('analysed %d / %d utterances' % (min((k + 1) * batch_utts, len(tokens)), len(tokens)))
+                print('analysed %d / %d utterances' % (n_done, len(tokens)))
         for f in writes:
             f.result()
-    return dict(utterances=len(tokens), frames=n_frames, seconds=time.perf_counter() - t0)
+    return dict(utterances=n_done, frames=n_frames, seconds=time.perf_counter() - t0, skipped=skipped,
+                failed=crashes.tokens)
 
 
 def _load_features(in_feats_dir, token, mag_dim, phase_dim):
@@ -97,43 +187,86 @@ def _load_features(in_feats_dir, token, mag_dim, phase_dim):
     return rd('.mag', mag_dim), rd('.real', phase_dim), rd('.imag', phase_dim), rd('.lf0', 1)
 
 
+def _noise_draws(v_lf0, fs, fft_len, b_const_rate):
+    """How many np.random.uniform draws synthesis_from_compressed takes for this utterance (src/magphase.py:879-883)."""
+    v_lf0 = np.asarray(v_lf0, dtype=np.float64).reshape(-1)
+    _, ns_lens = mp.compressed_synthesis_geometry([v_lf0], [v_lf0.size], fs, fft_len if fft_len else mp.define_fft_len(fs),
+                                                  b_const_rate=b_const_rate)
+    return int(ns_lens[0])
+
+
 def run_waveform_generation(tokens, in_feats_dir, out_syn_dir, mag_dim, phase_dim, fs, fft_len=None, pf_type='magphase',
-                            b_const_rate=False, batch_utts=64, io_threads=8, verbose=False):
+                            b_const_rate=False, batch_utts=64, io_threads=8, verbose=False, resume=False, on_error='raise'):
     """synthesis_from_acoustic_modelling (src/magphase.py:3229-3275) for a list of file tokens (or an .scp path).
-    The aperiodic noise is drawn from NumPy's global stream in list order (seed it for reproducible output)."""
+    The aperiodic noise is drawn from NumPy's global stream in list order (seed it for reproducible output); with
+    ``resume`` the draws of the tokens whose wav already exists are consumed all the same, so a resumed run writes the
+    files of an uninterrupted one.  resume / on_error: module docstring.
+    Returns {'utterances', 'frames', 'seconds', 'skipped', 'failed'}."""
+    _check_on_error(on_error)
     if isinstance(tokens, str):
         tokens = read_tokens(tokens)
+    tokens = list(tokens)
     if pf_type not in ('magphase', 'merlin', 'no'):
         raise ValueError("pf_type must be 'magphase', 'merlin' or 'no'")
     os.makedirs(out_syn_dir, exist_ok=True)
+    have = set(t for t in tokens if resume and _complete([os.path.join(out_syn_dir, t + '.wav')]))
+    crashes = _CrashList(out_syn_dir)
     t0 = time.perf_counter()
-    n_frames = 0
+    n_frames = n_done = 0
     with cf.ThreadPoolExecutor(max_workers=io_threads) as pool:
-        groups = list(_batches(list(tokens), batch_utts))
+        groups = list(_batches(tokens, batch_utts))
         load = lambda g: [pool.submit(_load_features, in_feats_dir, t, mag_dim, phase_dim) for t in g]
         pending = load(groups[0]) if groups else []
         writes = []
         for k, g in enumerate(groups):
-            feats = [f.result() for f in pending]
+            g, feats = _collect(pending, g, on_error, crashes)
             pending = load(groups[k + 1]) if k + 1 < len(groups) else []
-            if pf_type in ('magphase', 'merlin'):
+            if pf_type in ('magphase', 'merlin') and feats:
                 # both post-filters work frame by frame (src/magphase.py:2300-2378, 3375-3465): one call over the stacked rows
                 rows = np.concatenate([np.atleast_2d(f[0]) for f in feats], axis=0)
                 rows = mp.post_filter(rows, fs) if pf_type == 'magphase' else mp.post_filter_merlin(rows, fs)
                 off = np.concatenate(([0], np.cumsum([np.atleast_2d(f[0]).shape[0] for f in feats])))
                 feats = [(rows[off[i]:off[i + 1]],) + f[1:] for i, f in enumerate(feats)]
-            ys = mp.synthesis_from_compressed_batch(feats, fs, fft_len=fft_len, b_const_rate=b_const_rate)
-            for f in writes:
-                f.result()
-            # (copies: the batch result is a view into a pooled page-locked block that the next batch reuses)
-            writes = [pool.submit(io.write_audio_file, os.path.join(out_syn_dir, t + '.wav'), np.array(y), fs)
-                      for t, y in zip(g, ys)]
-            n_frames += sum(np.atleast_2d(f[0]).shape[0] for f in feats)
+            # maximal stretches of tokens still to do, in list order; the finished ones in between only advance the stream
+            i = 0
+            while i < len(g):
+                if g[i] in have:
+                    np.random.uniform(-1, 1, _noise_draws(feats[i][3], fs, fft_len, b_const_rate))
+                    i += 1
+                    continue
+                j = i
+                while j < len(g) and g[j] not in have:
+                    j += 1
+                run_t, run_f = g[i:j], feats[i:j]
+                i = j
+                try:
+                    ys = mp.synthesis_from_compressed_batch(run_f, fs, fft_len=fft_len, b_const_rate=b_const_rate)
+                except (ValueError, IndexError):
+                    if on_error != 'skip':
+                        raise
+                    # the argument checks run before any noise is drawn: retry utterance by utterance to find the bad one
+                    ys, ok = [], []
+                    for t, f in zip(run_t, run_f):
+                        try:
+                            ys.append(np.array(mp.synthesis_from_compressed_batch([f], fs, fft_len=fft_len,
+                                                                                  b_const_rate=b_const_rate)[0]))
+                            ok.append(t)
+                        except (ValueError, IndexError) as e:
+                            crashes.add(t, e)
+                    run_t = ok
+                for f in writes:
+                    f.result()
+                # (copies: the batch result is a view into a pooled page-locked block that the next batch reuses)
+                writes = [pool.submit(_write_wav, os.path.join(out_syn_dir, t + '.wav'), np.array(y), fs)
+                          for t, y in zip(run_t, ys)]
+                n_done += len(run_t)
+                n_frames += sum(np.atleast_2d(f[0]).shape[0] for t, f in zip(g, feats) if t in set(run_t))
             if verbose:
-                print('synthesised %d / %d utterances' % (min((k + 1) * batch_utts, len(tokens)), len(tokens)))
+                print('synthesised %d / %d utterances' % (n_done, len(tokens) - len(have)))
         for f in writes:
             f.result()
-    return dict(utterances=len(tokens), frames=n_frames, seconds=time.perf_counter() - t0)
+    return dict(utterances=n_done, frames=n_frames, seconds=time.perf_counter() - t0,
+                skipped=[t for t in tokens if t in have], failed=crashes.tokens)
 
 
 def run_chain_stream(batches, fs, fft_len=None, mag_dim=60, phase_dim=45, b_out_hpf=False, n_workers=2, seed=0,
@@ -207,15 +340,22 @@ def main(argv=None):
         p.add_argument('--const-rate', action='store_true')
         p.add_argument('--batch-utts', type=int, default=64)
         p.add_argument('--io-threads', type=int, default=8)
+        p.add_argument('--resume', action='store_true', help='skip tokens whose output files are already complete')
+        p.add_argument('--skip-errors', action='store_true',
+                       help='list failing tokens in crash_file_list_<host>_<pid>.scp and go on')
     a = ap.parse_args(argv)
     if a.cmd == 'extract':
         r = run_feature_extraction(a.scp, a.wav_dir, a.out_dir, est_dir=a.est_dir, mag_dim=a.mag_dim, phase_dim=a.phase_dim,
-                                   b_const_rate=a.const_rate, batch_utts=a.batch_utts, io_threads=a.io_threads, verbose=True)
+                                   b_const_rate=a.const_rate, batch_utts=a.batch_utts, io_threads=a.io_threads, verbose=True,
+                                   resume=a.resume, on_error='skip' if a.skip_errors else 'raise')
     else:
         if a.seed is not None:
             np.random.seed(a.seed)
         r = run_waveform_generation(a.scp, a.feats_dir, a.out_dir, a.mag_dim, a.phase_dim, a.fs, pf_type=a.pf_type,
-                                    b_const_rate=a.const_rate, batch_utts=a.batch_utts, io_threads=a.io_threads, verbose=True)
+                                    b_const_rate=a.const_rate, batch_utts=a.batch_utts, io_threads=a.io_threads, verbose=True,
+                                    resume=a.resume, on_error='skip' if a.skip_errors else 'raise')
+    if r['skipped'] or r['failed']:
+        print('%d tokens already done, %d failed' % (len(r['skipped']), len(r['failed'])))
     print('Done! %d utterances, %d frames in %.2f s (%.0f frames/s incl. file IO)'
           % (r['utterances'], r['frames'], r['seconds'], r['frames'] / max(r['seconds'], 1e-9)))
 

@@ -88,3 +88,46 @@ def test_batch_cli_and_errors(corpus, capsys):
     assert r['utterances'] == len(tokens) and sorted(os.listdir(str(d / 'x'))) == sorted(t + '.wav' for t in tokens)
     with pytest.raises(FileNotFoundError):
         batch.run_feature_extraction(['missing'], wav_dir, str(d / 'y'), est_dir=est_dir)
+
+
+def test_resume_and_skip_errors_on_the_device(corpus):
+    """resume / on_error='skip' with the real device calls (the CPU suite covers the logic with stand-ins): a resumed
+    generation run writes the files of an uninterrupted one because the finished tokens' noise draws are still consumed;
+    a one-frame feature set fails the argument checks of its batch and is isolated."""
+    from magphase_b200 import batch, hostio
+    d, scp, wav_dir, est_dir, tokens = corpus
+    feats = str(d / 'feats_resume')
+    r = batch.run_feature_extraction(tokens[:2], wav_dir, feats, est_dir=est_dir)
+    first = {t: open(os.path.join(feats, t + '.mag'), 'rb').read() for t in tokens[:2]}
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        r = batch.run_feature_extraction(tokens + ['absent'], wav_dir, feats, est_dir=est_dir, batch_utts=4, resume=True,
+                                         on_error='skip')
+    assert r['skipped'] == tokens[:2] and r['failed'] == ['absent'] and r['utterances'] == len(tokens) - 2
+    assert all(open(os.path.join(feats, t + '.mag'), 'rb').read() == first[t] for t in tokens[:2])
+    ref = str(d / 'feats_batch')
+    if os.path.isdir(ref):
+        for t in tokens:
+            assert open(os.path.join(feats, t + '.real'), 'rb').read() == open(os.path.join(ref, t + '.real'), 'rb').read()
+    for ext, dim in (('.mag', 60), ('.real', 45), ('.imag', 45), ('.lf0', 1)):
+        hostio.write_binfile(np.zeros((1, dim)), os.path.join(feats, 'short' + ext))
+    full, part = str(d / 'syn_full'), str(d / 'syn_part')
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        np.random.seed(21)
+        batch.run_waveform_generation(tokens, feats, full, 60, 45, 48000, batch_utts=3)
+        state_full = np.random.get_state()
+        np.random.seed(21)
+        batch.run_waveform_generation(tokens[:4], feats, part, 60, 45, 48000, batch_utts=3)
+        os.remove(os.path.join(part, tokens[0] + '.wav'))
+        os.remove(os.path.join(part, tokens[2] + '.wav'))
+        np.random.seed(21)
+        r = batch.run_waveform_generation(tokens[:3] + ['short'] + tokens[3:], feats, part, 60, 45, 48000, batch_utts=3,
+                                          resume=True, on_error='skip')
+    assert r['skipped'] == [tokens[1], tokens[3]] and r['failed'] == ['short'] and r['utterances'] == 3
+    st = np.random.get_state()
+    assert st[2] == state_full[2] and np.array_equal(st[1], state_full[1])
+    for t in tokens:
+        a, _ = hostio.read_audio_file(os.path.join(part, t + '.wav'))
+        b, _ = hostio.read_audio_file(os.path.join(full, t + '.wav'))
+        assert a.shape == b.shape and np.max(np.abs(a - b)) <= 1.0 / 32768 + 1e-12 and np.mean(a != b) < 0.01, t
