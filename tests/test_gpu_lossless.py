@@ -91,6 +91,40 @@ def test_analysis_edge_marks(mp):
     assert got[0].dtype == np.complex128 and rms(got[0], ref[0]) < 1e-9
 
 
+@pytest.mark.parametrize('style', ['speech', 'tiny', 'long', 'fractional'])
+def test_random_mark_patterns(mp, style):
+    """Generated mark patterns (the generator tests/test_mark_patterns_cpu.py pins the oracle to the reference with):
+    a mark at sample 0, shifts of 1-3 samples, half-integer marks, periods beyond fft_len, a mark on the last sample --
+    at all three FFT lengths, spectra and shifts against the oracle, then lossless resynthesis of the analysed features."""
+    from test_mark_patterns_cpu import mark_pattern
+    for seed in range(6):
+        rng = np.random.default_rng(1000 + seed)
+        fft_len = (1024, 2048, 4096)[seed % 3]
+        n = int(rng.integers(3000, 40000))
+        sig = rng.uniform(-1, 1, n)
+        pm = mark_pattern(rng, n, int(rng.integers(3, 40)), style)
+        if pm.size < 2:
+            continue
+        voi = (rng.random(pm.size) < 0.6).astype(float)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ref, shift_ref = orc.analysis_fft_from_pm(sig, 48000, pm, fft_len=fft_len)
+            got, shift = mp.analysis_with_del_comp_from_pm(sig, 48000, pm, fft_len=fft_len)
+        assert np.array_equal(shift, shift_ref), (style, seed)
+        assert rms(got, ref) < 1e-9, (style, seed, rms(got, ref))
+        if shift_ref[0] == 0:
+            continue                                   # f0 = voi * fs / 0: no resynthesis in the reference either
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            f_ref = orc.analysis_lossless_from_pm(sig, 48000, pm, voi, fft_len=fft_len)
+            f_got = mp.analysis_lossless_from_pm(sig, 48000, pm, voi, fft_len=fft_len)
+            y_ref = orc.synthesis_from_lossless(*f_ref[:4], 48000)
+            y = mp.synthesis_from_lossless(*f_got[:4], 48000)
+        assert np.array_equal(f_got[3], f_ref[3])
+        assert y.shape == y_ref.shape, (style, seed)
+        assert rms(y, y_ref) < TOL, (style, seed, rms(y, y_ref))
+
+
 def test_analysis_all_zero_signal(mp):
     sig = np.zeros(5000)
     pm = np.array([500.0, 900.0, 1500.0, 2500.0])
