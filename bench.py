@@ -616,6 +616,9 @@ def main():
                      'algorithmic_bytes_per_launch': int(dom['algorithmic_bytes_per_step'] / max(dom['launches_per_step'], 1)),
                      'ms_per_launch': dom['ms_per_step'] / max(dom['launches_per_step'], 1),
                      'compute': dom.get('compute'),
+                     'limiter': 'ncu (profiles/r2/c_k_analysis_logp.txt): FP64 pipe 44 % active, issue slots 56 %, warps active '
+                                '28 % (96 registers x 128 threads, 5 CTAs/SM) -- latency / FP64-pipe bound, NOT HBM-bound; '
+                                '"bound" names the nearer of the two rooflines the line format knows',
                      'note': 'the dominant kernels are the three FFT kernels: their contract is HBM bytes (this fraction), their '
                              'practical limit is instruction issue / the FP64 pipe (see compute.frac against the measured FMA '
                              'peak and profiles/); the tensor-core tile products are HBM-bound (their own frac in kernels[])'},
