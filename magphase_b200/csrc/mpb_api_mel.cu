@@ -218,7 +218,7 @@ int mpb_analysis_compressed_dev(mpb_mel* m, void* stream, const void* sig, int s
         a.mode = MODE_LOGP; a.num_sms = ctx->num_sms; a.ph_mask = voi + f0;
         if (use_tc) {
             // tensor-core product with the finish step in its epilogue: 16-byte pitched rows, the phase rows compacted to the
-            // voiced frames (rank from the one-CTA scan), nothing but the low-dimensional features leaves the second kernel
+            // voiced frames (rank from k_voiced_compact), nothing but the low-dimensional features leaves the second kernel
             std::lock_guard<std::mutex> lk(m->mu);
             int32_t* d_vidx = (int32_t*)m->compact.p;
             int32_t* d_cidx = d_vidx + ((chunk + 3) & ~(int64_t)3);          // 16-byte aligned: vector stores in the scan
