@@ -179,6 +179,20 @@ def prewindowed_frames(sig_all, centre, left, right, l_fns):
     return np.asarray(sig_all, dtype=np.float64)[idx] * w_all, np.ascontiguousarray(off[:-1] + left), idx, w_all
 
 
+def windowing(v_sig, v_pm, win_func=np.hanning):
+    """The reference's frame extractor as a callable (src/magphase.py:74-119): the list of windowed frames
+    sig[P[f] : P[f+2]+1] * gen_non_symmetric_win(left, right, win_func[f]) and the integer bookkeeping
+    (v_lens, v_pm_plus, v_shift, v_rights).  Host NumPy, for callers of the reference's helper: the analysis kernels never
+    materialise this list -- they gather and window the samples on the fly (mpb_frame.cuh:load_frame)."""
+    v_sig = np.asarray(v_sig)
+    P, left, right = frame_geometry(v_pm, v_sig.size)
+    n = left.size
+    pre, _, _, _ = prewindowed_frames(v_sig, P[1:-1], left, right, _win_list(win_func, n))
+    off = _seg_offsets(left + right + 1)
+    l_frames = [pre[off[f]:off[f + 1]] for f in range(n)]
+    return l_frames, (left + right + 1).astype(int), P.astype(int), left.astype(int), right.astype(int)
+
+
 def voi_noise_window(length):
     """Host definition kept for API compatibility (src/magphase.py:67-69); the kernels evaluate it in closed form."""
     return np.bartlett(length) ** 2.5

@@ -311,3 +311,20 @@ def test_griffin_lim_with_arbitrary_window_matches_reference(ref_modules):
     np.testing.assert_allclose(y, y_ref, rtol=0, atol=1e-12)
     strong = mag > 1e-6 * mag.max()
     assert np.max(np.abs(np.angle(np.exp(1j * (ph - ph_ref))))[strong]) < 1e-8
+
+
+def test_windowing_helper_matches_reference(ref_modules):
+    """mirror.windowing() (host helper with the reference's signature, src/magphase.py:74-119) against the reference."""
+    mp, la, lu = ref_modules
+    import magphase_b200.magphase as mpb
+    sig, pm, voi = synth_utterance(6, dur_s=0.4)
+    for fn_ref, fn in ((np.hanning, np.hanning), (np.hamming, np.hamming),
+                       ([mp.voi_noise_window if i % 2 else np.hanning for i in range(pm.size)],
+                        [mpb.voi_noise_window if i % 2 else np.hanning for i in range(pm.size)])):
+        l_r, lens_r, P_r, shift_r, rights_r = mp.windowing(sig, pm, win_func=fn_ref)
+        l_m, lens_m, P_m, shift_m, rights_m = mpb.windowing(sig, pm, win_func=fn)
+        assert np.array_equal(lens_r, lens_m) and np.array_equal(P_r, P_m)
+        assert np.array_equal(shift_r, shift_m) and np.array_equal(rights_r, rights_m)
+        assert len(l_r) == len(l_m)
+        for a, b in zip(l_r, l_m):
+            np.testing.assert_array_equal(a, b)
