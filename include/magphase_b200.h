@@ -331,6 +331,19 @@ int mpb_synthesis_compressed_hostv2(mpb_syn* plan,
                                     const mpb_syn_frames* frames, int per_linear, const double* hpf_sos,
                                     void* out, int out_dtype, int64_t n_out);
 
+/*
+ * ola (src/magphase.py:34-62) as a function of its own: overlap-add of nfrm ready-made time-domain frames
+ * frames[nfrm][frmlen] (float64, frame centre = column frmlen/2) at the integer pitch marks pm (non-decreasing).
+ * out[j] = sum over i, in frame order, of frames[i][j + t0 - pm[i] + frmlen/2] where that column exists; t0 and n_out are
+ * the cut of :58-60 as computed by the host mirror (magphase.ola_geometry, Python slice semantics included).  The sums
+ * are bit-identical to the reference's loop.  (The synthesis entry points above overlap-add inside their inverse-FFT
+ * kernels; this is the standalone operator.)
+ */
+int mpb_ola_dev(mpb_ctx* ctx, void* stream, const double* frames, const int32_t* pm, int64_t nfrm, int frmlen,
+                int32_t t0, double* out, int64_t n_out);
+int mpb_ola_host(mpb_ctx* ctx, const double* frames, const int32_t* pm, int64_t nfrm, int frmlen,
+                 int32_t t0, double* out, int64_t n_out);
+
 /* ---- post-filter and minimum phase ---------------------------------------------------------- */
 /*
  * post_filter (src/magphase.py:2300-2378): ave[b] = mean(x[centre[b]-half[b] .. centre[b]+half[b]]),

@@ -423,6 +423,43 @@ int mpb_cep_energy_host(mpb_ctx* ctx, const double* c, int64_t nfrm, int n, cons
     return MPB_OK;
 }
 
+int mpb_ola_dev(mpb_ctx* ctx, void* stream, const double* frames, const int32_t* pm, int64_t nfrm, int frmlen,
+                int32_t t0, double* out, int64_t n_out) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (nfrm < 0 || n_out < 0 || frmlen < 1) return fail(MPB_ERR_BAD_ARG, "bad size");
+    if (n_out == 0) return MPB_OK;
+    if (!out || (nfrm > 0 && (!frames || !pm))) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    LAUNCH(ctx, (cudaStream_t)stream, "k_ola_gather",
+           launch_ola_gather(frames, pm, nfrm, frmlen, t0, out, n_out, (cudaStream_t)stream));
+    return MPB_OK;
+}
+
+int mpb_ola_host(mpb_ctx* ctx, const double* frames, const int32_t* pm, int64_t nfrm, int frmlen,
+                 int32_t t0, double* out, int64_t n_out) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (nfrm < 0 || n_out < 0 || frmlen < 1) return fail(MPB_ERR_BAD_ARG, "bad size");
+    if (n_out == 0) return MPB_OK;
+    if (!out || (nfrm > 0 && (!frames || !pm))) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    for (int64_t i = 1; i < nfrm; ++i)
+        if (pm[i] < pm[i - 1]) return fail(MPB_ERR_BAD_ARG, "pitch marks must be non-decreasing");
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevBuf* b = ctx->scratch;
+    cudaStream_t st = ctx->stream;
+    const size_t fsz = sizeof(double) * (size_t)nfrm * (size_t)frmlen, osz = sizeof(double) * (size_t)n_out;
+    CU(b[0].need(fsz ? fsz : 8)); CU(b[2].need(nfrm ? sizeof(int32_t) * (size_t)nfrm : 4)); CU(b[5].need(osz));
+    if (nfrm > 0) {
+        CU(cudaMemcpyAsync(b[0].p, frames, fsz, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(b[2].p, pm, sizeof(int32_t) * (size_t)nfrm, cudaMemcpyHostToDevice, st));
+    }
+    int rc = mpb_ola_dev(ctx, st, (const double*)b[0].p, (const int32_t*)b[2].p, nfrm, frmlen, t0, (double*)b[5].p, n_out);
+    if (rc != MPB_OK) { cudaStreamSynchronize(st); return rc; }
+    CU(cudaMemcpyAsync(out, b[5].p, osz, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MPB_OK;
+}
+
 int mpb_post_filter_host(mpb_ctx* ctx, const double* x, int64_t nfrm, int dim, const int32_t* centre,
                          const int32_t* half, const double* tilt, double* out) {
     if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");

@@ -303,4 +303,37 @@ cudaError_t launch_sos2(void* x, int dtype, const int64_t* utt_off, const int64_
     return cudaGetLastError();
 }
 
+// ---- ola(): overlap-add of ready-made time-domain frames (src/magphase.py:34-62) ------------------------------------
+// One thread per output sample gathers the frames that cover it, in frame order -- the order in which the reference's loop
+// adds them into its zero-initialised buffer, so the float64 sums are bit-identical.  Frame i (frmlen columns, centre at
+// column frmlen/2) covers the positions [pm[i] - frmlen/2, pm[i] - frmlen/2 + frmlen) of the pitch-mark axis; output sample
+// j sits at position j + t0 (magphase.ola_geometry).  pm is non-decreasing (checked on the host): the first covering frame
+// is found by bisection.  Reads of one frame are coalesced across the threads of a warp.
+__global__ void __launch_bounds__(256)
+k_ola_gather(const double* __restrict__ frames, const int32_t* __restrict__ pm, int64_t nfrm, int frmlen, int32_t t0,
+             double* __restrict__ out, int64_t n_out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    const int64_t pos = j + t0;
+    const int half = frmlen / 2;
+    const int64_t lo_val = pos + half - frmlen;          // frames with pm[i] > lo_val and pm[i] <= pos + half cover pos
+    int64_t a = 0, b = nfrm;
+    while (a < b) {                                      // first i with pm[i] > lo_val
+        const int64_t m = (a + b) >> 1;
+        if ((int64_t)pm[m] > lo_val) b = m; else a = m + 1;
+    }
+    double acc = 0.0;
+    for (int64_t i = a; i < nfrm && (int64_t)pm[i] <= pos + half; ++i)
+        acc += frames[i * frmlen + (pos - (int64_t)pm[i] + half)];
+    out[j] = acc;
+}
+
+cudaError_t launch_ola_gather(const double* frames, const int32_t* pm, int64_t nfrm, int frmlen, int32_t t0, double* out,
+                              int64_t n_out, cudaStream_t st) {
+    if (n_out < 1) return cudaSuccess;
+    k_ola_gather<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(frames, pm, nfrm, frmlen, t0, out, n_out);
+    return cudaGetLastError();
+}
+
+
 }  // namespace mpb

@@ -443,6 +443,44 @@ def ola_geometry(v_pm, fft_len):
     return v_pm.astype(np.int32), t0, n_out
 
 
+def raised_hanning(length, att=1.0):
+    """src/magphase.py:25-31"""
+    return (1 - att) + att * np.hanning(length)
+
+
+def ola(m_frm, v_pm, win_func=None):
+    """Pitch-synchronous overlap-add of ready-made frames (src/magphase.py:34-62) on the device: the frame centre (column
+    frmlen/2) of frame i lands on int(v_pm[i]); the sums are taken in frame order like the reference's loop, so the result is
+    bit-identical to it.  ``win_func``: optional per-frame centred window la.gen_centr_win(shift[i], shift[i+1], frmlen,
+    win_func) (src/libaudio.py:90-103), evaluated on the host; unlike the reference the caller's m_frm is NOT modified.
+    (synthesis_from_lossless / synthesis_from_compressed do their overlap-add inside the inverse-FFT kernels; this is the
+    standalone operator.)"""
+    m_frm = np.asarray(m_frm, dtype=np.float64)
+    if m_frm.ndim != 2:
+        raise ValueError('m_frm must be nfrms x frmlen')
+    nfrms, frmlen = m_frm.shape
+    v_pm_i = np.asarray(v_pm).astype(int)
+    if v_pm_i.size != nfrms or nfrms < 1:
+        raise ValueError('one pitch mark per frame')
+    if np.any(np.diff(v_pm_i) < 0):
+        raise ValueError('pitch marks must be non-decreasing')
+    pm32, t0, n_out = ola_geometry(v_pm_i, frmlen)
+    if win_func is not None:
+        v_shift = np.diff(np.hstack((0, v_pm_i)))
+        v_shift = np.append(v_shift, v_shift[-1])
+        w_all, off = window_weights([win_func] * nfrms, v_shift[:-1], v_shift[1:])
+        m_frm = m_frm.copy()
+        for i in range(nfrms):
+            v_win = np.zeros(frmlen)
+            z = frmlen // 2 - int(v_shift[i])
+            v_win[z:z + int(off[i + 1] - off[i])] = w_all[off[i]:off[i + 1]]     # same ValueError as the reference when it does not fit
+            m_frm[i] *= v_win
+    m_frm = np.ascontiguousarray(m_frm)
+    out = np.empty(n_out, dtype=np.float64)
+    _lib.check(_lib.lib().mpb_ola_host(_lib.ctx(), _lib.ptr(m_frm), _lib.ptr(pm32), nfrms, frmlen, int(t0), _lib.ptr(out), n_out))
+    return out
+
+
 def _synthesis_lossless_call(l_feats, l_pm_int, l_t0, l_nout, fft_len, compute=None, out_dtype=np.float64):
     compute = SYNTHESIS_COMPUTE if compute is None else compute
     out_dtype = np.dtype(out_dtype)

@@ -176,6 +176,40 @@ def test_arbitrary_win_func(mp, win):
     assert rms(got16, ref16) < 1e-9
 
 
+def test_standalone_ola(mp):
+    """mp.ola() (src/magphase.py:34-62) on the device: bit-identical to the loop (same float64 adds in the same order), on
+    the index cases tests/test_ola_cpu.py pins to the reference, at a realistic size, and with the optional centred window."""
+    from test_ola_cpu import CASES
+    rng = np.random.default_rng(3)
+    for case in CASES:
+        pm = np.array(case['pm'], dtype=np.float64) + 0.4
+        m_frm = rng.standard_normal((pm.size, case['frmlen']))
+        ref = orc.ola(m_frm.copy(), pm)
+        got = mp.ola(m_frm, pm)
+        assert got.shape == ref.shape and np.array_equal(got, ref), case
+    pm = np.cumsum(rng.integers(120, 700, 400)).astype(float)
+    m_frm = rng.standard_normal((pm.size, 4096))
+    keep = m_frm.copy()
+    assert np.array_equal(mp.ola(m_frm, pm), orc.ola(m_frm.copy(), pm))
+    # centred per-frame window (:45-48), the reference's loop restated on the host; the caller's frames stay untouched
+    got = mp.ola(m_frm, pm, win_func=mp.raised_hanning)
+    assert np.array_equal(m_frm, keep)
+    v_pm = pm.astype(int)
+    shift = np.diff(np.hstack((0, v_pm)))
+    shift = np.append(shift, shift[-1])
+    w = m_frm.copy()
+    for i in range(pm.size):
+        v_win = np.zeros(4096)
+        short = orc.asym_window(shift[i], shift[i + 1], mp.raised_hanning)
+        v_win[2048 - shift[i]:2048 - shift[i] + short.size] = short
+        w[i] *= v_win
+    assert np.array_equal(got, orc.ola(w, pm))
+    with pytest.raises(ValueError):
+        mp.ola(m_frm[:3], np.array([100.0, 50.0, 200.0]))          # marks must be non-decreasing
+    with pytest.raises(ValueError):
+        mp.ola(m_frm[:3], pm[:2])
+
+
 def test_synthesis_vs_oracle(mp):
     sig, pm, voi = synth_utterance(2, fs=48000, dur_s=1.0)
     mag, real, imag, f0, fs, _ = orc.analysis_lossless_from_pm(sig, 48000, pm, voi)
