@@ -1393,6 +1393,19 @@ def sp_to_mcep(m_sp, n_coeffs=60, alpha=0.77, in_type=3, fft_len=0):
     return outs[0] if in_type == 3 else outs[1]
 
 
+def sp_mel_warp(m_sp, nbins_out, alpha=0.77, in_type=3):
+    """la.sp_mel_warp (src/libaudio.py:643-661) as a function of its own: sp_to_mcep on the device, then the nbins_out x
+    nbins_out cosine matrix of la.mcep_to_sp_cosmat(alpha=0.0) (:605-631) on the host (a few thousand multiplies per frame;
+    format_for_modelling runs the same product inside its kernels).  Output type follows in_type: 3 -> |.|, 2 -> ln, 1 -> dB."""
+    m_mcep = sp_to_mcep(m_sp, n_coeffs=nbins_out, alpha=alpha, in_type=in_type)
+    m_sp_wrp = np.dot(m_mcep, np.cos(np.arange(nbins_out)[:, None] * warped_axis(0.0, nbins_out)[None, :]))
+    if in_type == 3:
+        return np.exp(m_sp_wrp)
+    if in_type == 1:
+        return m_sp_wrp * (20 / np.log(10))
+    return m_sp_wrp
+
+
 def analysis_with_del_comp_and_ph_encoding(v_in_sig, nFFT, fs, mvf, pm=None):
     """Legacy v1 analysis (src/magphase.py:573-598 over analysis_with_del_comp :338-368): spectral envelope and the
     sine / cosine of the phase up to `mvf` Hz, each as 60 mel-cepstral coefficients.

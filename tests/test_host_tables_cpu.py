@@ -70,3 +70,20 @@ def test_output_hpf_sections_reproduce_the_reference_design(fs):
 def test_post_filter_argument_errors_come_before_device_work():
     with pytest.raises(ValueError):
         mp.post_filter(np.zeros((4, 60)), 22050)           # no defaults for this rate (src/magphase.py:2330-2334)
+
+
+def test_sp_mel_warp_host_half_against_the_oracle(monkeypatch):
+    """mp.sp_mel_warp = sp_to_mcep (device, tests/test_gpu_compressed_analysis.py) + the cosine matrix of
+    la.mcep_to_sp_cosmat(alpha=0) on the host: with the oracle's mcep_j0 standing in for the device half, the composition
+    must equal the oracle's sp_mel_warp for all three input types (src/libaudio.py:643-661)."""
+    import numpy as np
+    import magphase_oracle as orc
+    import magphase_b200.magphase as mp
+    monkeypatch.setattr(mp, 'sp_to_mcep', lambda m_sp, n_coeffs=60, alpha=0.77, in_type=3, fft_len=0:
+                        orc.mcep_j0(m_sp, n_coeffs=n_coeffs, alpha=alpha, in_type=in_type))
+    rng = np.random.default_rng(0)
+    mag = np.abs(rng.standard_normal((5, 1025))) + 0.01
+    for in_type, x in ((3, mag), (2, np.log(mag)), (1, 20 * np.log10(mag))):
+        got = mp.sp_mel_warp(x, 40, alpha=0.58, in_type=in_type)
+        ref = orc.sp_mel_warp(x, 40, alpha=0.58, in_type=in_type)
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12)
