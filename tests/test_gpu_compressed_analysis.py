@@ -140,3 +140,9 @@ def test_legacy_analysis_with_del_comp_and_ph_encoding(mp):
     mag = orc.analysis_lossless_from_pm(sig, 48000, pm, voi)[0]
     for it, x in ((3, mag), (2, np.log(mag + 1e-3)), (1, 20 * np.log10(mag + 1e-3))):
         assert rms(mp.sp_to_mcep(x, in_type=it), orc.mcep_j0(x, in_type=it)) < TOL
+        # la.sp_mel_warp on top of it (src/libaudio.py:643-661): compared in the log domain for in_type 3 (output is |.|)
+        w_got, w_ref = mp.sp_mel_warp(x, 60, alpha=0.77, in_type=it), orc.sp_mel_warp(x, 60, alpha=0.77, in_type=it)
+        assert w_got.shape == w_ref.shape == (pm.size, 60)
+        if it == 3:
+            w_got, w_ref = np.log(w_got), np.log(w_ref)
+        assert rms(w_got, w_ref) < (1e-4 if it == 1 else TOL), (it, rms(w_got, w_ref))      # dB scale: 8.7 x the log error
