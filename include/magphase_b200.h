@@ -332,6 +332,13 @@ int mpb_synthesis_compressed_hostv2(mpb_syn* plan,
                                     void* out, int out_dtype, int64_t n_out);
 
 /*
+ * compute_lossless_feats (src/magphase.py:457-476) on ready-made half spectra: fft holds n complex128 values (the output
+ * of mpb_frames_fft_host, any shape), mag = |X|, real = Re X/|X|, imag = Im X/|X|, all 0 where |X| == 0; float64.
+ * (mpb_analysis_lossless_* fuse this into the analysis kernel.)
+ */
+int mpb_lossless_feats_host(mpb_ctx* ctx, const double* fft, int64_t n, double* mag, double* real, double* imag);
+
+/*
  * ola (src/magphase.py:34-62) as a function of its own: overlap-add of nfrm ready-made time-domain frames
  * frames[nfrm][frmlen] (float64, frame centre = column frmlen/2) at the integer pitch marks pm (non-decreasing).
  * out[j] = sum over i, in frame order, of frames[i][j + t0 - pm[i] + frmlen/2] where that column exists; t0 and n_out are

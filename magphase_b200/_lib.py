@@ -68,6 +68,7 @@ SIGNATURES = {
     'mpb_synthesis_compressed_hostv2': [_vp, _vp, _vp, _vp, _vp, _i32, C.c_int, _vp, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp, _vp,
                                         C.c_int, _i64],
     'mpb_post_filter_dev': [_vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp],
+    'mpb_lossless_feats_host': [_vp, _vp, _i64, _vp, _vp, _vp],
     'mpb_ola_dev': [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int32, _vp, _i64],
     'mpb_ola_host': [_vp, _vp, _vp, _i64, C.c_int, C.c_int32, _vp, _i64],
     'mpb_post_filter_host': [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _vp],

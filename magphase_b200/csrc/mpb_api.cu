@@ -423,6 +423,32 @@ int mpb_cep_energy_host(mpb_ctx* ctx, const double* c, int64_t nfrm, int n, cons
     return MPB_OK;
 }
 
+int mpb_lossless_feats_host(mpb_ctx* ctx, const double* fft, int64_t n, double* mag, double* real, double* imag) {
+    if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");
+    if (n < 0) return fail(MPB_ERR_BAD_ARG, "bad size");
+    if (n == 0) return MPB_OK;
+    if (!fft || !mag || !real || !imag) return fail(MPB_ERR_BAD_ARG, "NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevBuf* b = ctx->scratch;
+    cudaStream_t st = ctx->stream;
+    // chunks of at most 16 M values: 256 MB in, 384 MB out of scratch whatever the size of the call
+    const int64_t CH = (int64_t)1 << 24;
+    const int64_t c0 = n < CH ? n : CH;
+    CU(b[0].need(sizeof(double) * 2 * (size_t)c0)); CU(b[5].need(sizeof(double) * 3 * (size_t)c0));
+    for (int64_t a = 0; a < n; a += CH) {
+        const int64_t c = n - a < CH ? n - a : CH;
+        double* o = (double*)b[5].p;
+        CU(cudaMemcpyAsync(b[0].p, fft + 2 * a, sizeof(double) * 2 * (size_t)c, cudaMemcpyHostToDevice, st));
+        LAUNCH(ctx, st, "k_lossless_feats", launch_lossless_feats(b[0].p, c, o, o + c, o + 2 * c, ctx->num_sms, st));
+        CU(cudaMemcpyAsync(mag + a, o, sizeof(double) * (size_t)c, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(real + a, o + c, sizeof(double) * (size_t)c, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(imag + a, o + 2 * c, sizeof(double) * (size_t)c, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return MPB_OK;
+}
+
 int mpb_ola_dev(mpb_ctx* ctx, void* stream, const double* frames, const int32_t* pm, int64_t nfrm, int frmlen,
                 int32_t t0, double* out, int64_t n_out) {
     if (!ctx) return fail(MPB_ERR_BAD_ARG, "ctx is NULL");

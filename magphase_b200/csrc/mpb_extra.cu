@@ -336,4 +336,27 @@ cudaError_t launch_ola_gather(const double* frames, const int32_t* pm, int64_t n
 }
 
 
+// ---- compute_lossless_feats() on ready-made spectra (src/magphase.py:457-476) ----------------------------------------
+// mag = |X|, real = Re X / |X|, imag = Im X / |X| (0 where |X| == 0), elementwise over n complex128 values.  The analysis
+// kernels apply the same normalise() to the spectrum they have just computed; this is the operator for callers that hold
+// the output of analysis_with_del_comp_from_pm.
+__global__ void __launch_bounds__(256)
+k_lossless_feats(const double2* __restrict__ x, int64_t n, double* __restrict__ mag, double* __restrict__ re,
+                 double* __restrict__ im) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 v = x[i];
+        double m, a, b;
+        normalise(v.x, v.y, m, a, b);
+        mag[i] = m; re[i] = a; im[i] = b;
+    }
+}
+
+cudaError_t launch_lossless_feats(const void* x, int64_t n, double* mag, double* re, double* im, int num_sms, cudaStream_t st) {
+    if (n < 1) return cudaSuccess;
+    int64_t grid = (n + 255) / 256;
+    if (grid > (int64_t)num_sms * 8) grid = (int64_t)num_sms * 8;
+    k_lossless_feats<<<(unsigned)grid, 256, 0, st>>>((const double2*)x, n, mag, re, im);
+    return cudaGetLastError();
+}
+
 }  // namespace mpb

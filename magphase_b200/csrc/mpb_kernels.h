@@ -132,6 +132,7 @@ cudaError_t launch_synthesis_compressed(const SynthCompArgs& a, cudaStream_t st)
 // ---- post-filter and minimum phase (mpb_extra.cu) ----
 cudaError_t launch_post_filter(const void* x, int dtype, int64_t nfrm, int dim, const int32_t* centre, const int32_t* half,
                                const double* tilt, void* out, cudaStream_t st);
+cudaError_t launch_lossless_feats(const void* x, int64_t n, double* mag, double* re, double* im, int num_sms, cudaStream_t st);
 cudaError_t launch_ola_gather(const double* frames, const int32_t* pm, int64_t nfrm, int frmlen, int32_t t0, double* out,
                               int64_t n_out, cudaStream_t st);
 cudaError_t launch_cep_energy(const double* c, int64_t nfrm, int n, const double* G, int K, int L, double* r0, int num_sms,

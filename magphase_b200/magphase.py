@@ -355,6 +355,18 @@ def analysis_with_del_comp_from_pm(v_in_sig, fs, v_pm_smpls, fft_len=None, win_f
     return m_fft, shifts[0].astype(int)
 
 
+def compute_lossless_feats(m_fft, v_shift, v_voi, fs):
+    """mag, real / |X|, imag / |X| (0 where |X| == 0) and f0 from ready-made half spectra -- the second step of the
+    reference's analysis as a function of its own (src/magphase.py:457-476), for callers that hold the output of
+    analysis_with_del_comp_from_pm.  Elementwise on the device; analysis_lossless* fuse it into the analysis kernel."""
+    m_fft = np.ascontiguousarray(m_fft, dtype=np.complex128)
+    m_mag, m_real, m_imag = (np.empty(m_fft.shape, dtype=np.float64) for _ in range(3))
+    _lib.check(_lib.lib().mpb_lossless_feats_host(_lib.ctx(), _lib.ptr(m_fft), m_fft.size, _lib.ptr(m_mag), _lib.ptr(m_real),
+                                                  _lib.ptr(m_imag)))
+    v_f0 = shift_to_f0(np.asarray(v_shift), np.asarray(v_voi, dtype=np.float64), fs, out='f0', b_smooth=False)
+    return m_mag, m_real, m_imag, v_f0
+
+
 def analysis_lossless_from_pm(v_sig, fs, v_pm_smpls, v_voi, fft_len=None):
     """analysis_lossless minus file reading and epoch detection (pitch marks in samples + voicing given)."""
     if fft_len is None:

@@ -176,6 +176,29 @@ def test_arbitrary_win_func(mp, win):
     assert rms(got16, ref16) < 1e-9
 
 
+def test_compute_lossless_feats_on_ready_made_spectra(mp):
+    """The reference's two-step analysis (analysis_with_del_comp_from_pm -> compute_lossless_feats, src/magphase.py:266-334,
+    :457-476) gives what the fused analysis_lossless_from_pm gives; exact zeros stay zeros; huge / tiny magnitudes take the
+    exact path."""
+    sig, pm, voi = synth_utterance(2, fs=48000, dur_s=0.4)
+    m_fft, v_shift = mp.analysis_with_del_comp_from_pm(sig, 48000, pm)
+    got = mp.compute_lossless_feats(m_fft, v_shift, voi, 48000)
+    ref = orc.compute_lossless_feats(m_fft, v_shift, voi, 48000)
+    fused = mp.analysis_lossless_from_pm(sig, 48000, pm, voi)
+    assert np.array_equal(got[3], ref[3])
+    for a, b, c in zip(got[:3], ref[:3], fused[:3]):
+        assert a.shape == b.shape and a.dtype == np.float64
+        assert np.max(np.abs(a - b)) < 1e-12 * max(1.0, float(np.abs(b).max()))
+        assert rms(a, c) < 1e-10
+    x = np.array([[0.0 + 0.0j, 3.0 - 4.0j, 1e-200 + 1e-200j, 1e160 - 1e160j, -2.0 + 0.0j]])
+    m, r, i, _ = mp.compute_lossless_feats(x, np.array([100]), np.array([1.0]), 48000)
+    mr, rr, ir, _ = orc.compute_lossless_feats(x, np.array([100]), np.array([1.0]), 48000)
+    assert m[0, 0] == 0.0 and r[0, 0] == 0.0 and i[0, 0] == 0.0
+    np.testing.assert_allclose(m, mr, rtol=1e-14)
+    np.testing.assert_allclose(r, rr, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(i, ir, rtol=0, atol=1e-14)
+
+
 def test_standalone_ola(mp):
     """mp.ola() (src/magphase.py:34-62) on the device: bit-identical to the loop (same float64 adds in the same order), on
     the index cases tests/test_ola_cpu.py pins to the reference, at a realistic size, and with the optional centred window."""
