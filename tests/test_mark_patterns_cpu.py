@@ -27,11 +27,12 @@ def mark_pattern(rng, n_smpls, n_marks, style):
     pm = pm[pm <= n_smpls - 1]
     if rng.random() < 0.5 and pm.size and pm[-1] < n_smpls - 1:
         pm = np.concatenate((pm, [float(n_smpls - 1)]))      # last mark on the last sample: empty right side
-    pm = pm[np.concatenate(([True], np.diff(np.round(pm)) > 0))]
+    if pm.size:
+        pm = pm[np.concatenate(([True], np.diff(np.round(pm)) > 0))]
     return pm
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(max_examples=40, deadline=None, derandomize=True, database=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(seed=st.integers(0, 2 ** 31 - 1), style=st.sampled_from(['speech', 'tiny', 'long', 'fractional']),
        fft_len=st.sampled_from([1024, 2048, 4096]))
 def test_oracle_equals_reference_on_generated_marks(ref_modules, seed, style, fft_len):
