@@ -417,11 +417,16 @@ def get_pitch_marks_and_voicing(wav_file, n_smpls, fs, est_file=None, pm=None):
         return v_pm_sec[ok], v_voi[ok]
     tmp_est = io.ins_pid('temp.est')
     print("Extracting epochs with REAPER...")
-    call(reaper + " -s -x 400 -m 50 -a -u 0.005 -i %s -p %s" % (wav_file, tmp_est), shell=True)
+    # the reference's command line (src/libaudio.py:452), as an argument list: file names with blanks or shell characters
+    # are passed through untouched
+    rc = call([reaper, '-s', '-x', '400', '-m', '50', '-a', '-u', '0.005', '-i', str(wav_file), '-p', tmp_est])
     try:
+        if rc != 0 or not os.path.isfile(tmp_est):
+            raise RuntimeError('REAPER failed on %s (exit status %s)' % (wav_file, rc))
         return io.read_reaper_est_file(tmp_est, check_len_smpls=n_smpls, fs=fs)
     finally:
-        os.remove(tmp_est)
+        if os.path.exists(tmp_est):
+            os.remove(tmp_est)
 
 
 def analysis_lossless(wav_file, fft_len=None, out_dir=None, est_file=None, pm=None):

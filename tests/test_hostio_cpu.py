@@ -62,3 +62,33 @@ def test_band_limited_synthetic_utterance():
     f = np.fft.rfftfreq(b[0].size, 1.0 / 48000)
     lo, hi = spec[(f > 300) & (f < 3000)].max(), spec[f > 10000].max()
     assert 20 * np.log10(hi / lo) < -50.0
+
+
+def test_reaper_shell_out_with_a_fake_binary(tmp_path, monkeypatch):
+    """The REAPER call of analysis_lossless (src/libaudio.py:450-455) with a stand-in executable: same flags, file names
+    with blanks survive (argument list, no shell), the temporary .est is removed, a failing binary raises instead of leaving
+    a FileNotFoundError from the clean-up."""
+    import os
+    import stat
+    import numpy as np
+    import pytest
+    import magphase_b200.magphase as mp
+    from magphase_b200 import hostio
+    log = tmp_path / 'args.txt'
+    fake = tmp_path / 'reaper'
+    fake.write_text('#!/bin/bash\nprintf "%s\\n" "$@" > "' + str(log) + '"\n'
+                    'while [ $# -gt 0 ]; do if [ "$1" = "-p" ]; then out="$2"; fi; shift; done\n'
+                    'printf "EST_File Track\\nDataType ascii\\nNumFrames 3\\nNumChannels 1\\nFrameShift 0.0\\nVoicingEnabled true\\n'
+                    'EST_Header_End\\n0.010000 1\\n0.020000 0\\n0.500000 1\\n" > "$out"\n')
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setattr(hostio, 'find_tool', lambda name: str(fake))
+    monkeypatch.chdir(tmp_path)
+    wav = str(tmp_path / 'my utterance.wav')
+    v_pm, v_voi = mp.get_pitch_marks_and_voicing(wav, 4800, 48000)          # 0.5 s lies beyond the 0.1 s signal: dropped
+    assert np.allclose(v_pm, [0.01, 0.02]) and v_voi.tolist() == [1.0, 0.0]
+    args = log.read_text().split('\n')
+    assert args[:9] == ['-s', '-x', '400', '-m', '50', '-a', '-u', '0.005', '-i'] and args[9] == wav and args[10] == '-p'
+    assert not [f for f in os.listdir(tmp_path) if f.startswith('temp_') and f.endswith('.est')]
+    fake.write_text('#!/bin/bash\nexit 3\n')
+    with pytest.raises(RuntimeError):
+        mp.get_pitch_marks_and_voicing(wav, 4800, 48000)
