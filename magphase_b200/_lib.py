@@ -170,11 +170,22 @@ def device_gate():
     return _gate
 
 
+_ctx_pid = None
+
+
 def ctx(device=None):
-    """Context handle of (device, current_slot()) (created on first use)."""
+    """Context handle of (device, current_slot()) (created on first use).
+    CUDA contexts do not survive fork(): a child forked after the first context was created (what the reference's
+    ``lu.run_multithreaded`` would do, src/libutils.py:32-63) gets a clear error here instead of a hang or a corrupted
+    device state -- the ``*_batch`` functions and ``batch.run_*`` replace that fan-out."""
+    global _ctx_pid
     device = default_device() if device is None else int(device)
     key = (device, current_slot())
     with _lock:
+        if _ctx and _ctx_pid != os.getpid():
+            raise RuntimeError('magphase_b200: this process (pid %d) was forked after the library had initialised CUDA in pid %s; '
+                               'CUDA contexts do not survive fork().  Use the *_batch functions / magphase_b200.batch instead of a '
+                               'forking pool, or start the workers with the "spawn" method.' % (os.getpid(), _ctx_pid))
         h = _ctx.get(key)
     if h is None:
         l = lib()
@@ -182,6 +193,7 @@ def ctx(device=None):
         check(l.mpb_create(device, C.byref(p)))
         with _lock:
             _ctx.setdefault(key, p)
+            _ctx_pid = os.getpid()
             h = _ctx[key]
     return h
 

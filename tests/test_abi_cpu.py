@@ -137,3 +137,27 @@ def test_const_rate_scan_argument_checks_and_edge_cases():
     rs, rl = mp.get_shifts_and_frm_locs_from_const_shifts(nan, 5.0, 16000)      # the NumPy loop: NaN is handed through to the cap
     assert cnt[0] == rs.size == 5
     assert np.array_equal(o_s[:5][::-1], rs, equal_nan=True) and np.array_equal(o_l[:5][::-1], rl, equal_nan=True)
+
+
+def test_fork_after_initialisation_is_refused(monkeypatch):
+    """the reference fans out with a forking Pool (src/libutils.py:32-63); a CUDA context does not survive
+    fork(), so a child that inherited an initialised library must get an error, not a hang."""
+    import os
+    from magphase_b200 import _lib
+    monkeypatch.setattr(_lib, '_ctx', {(0, 0): object()})        # as if the parent had created a context
+    monkeypatch.setattr(_lib, '_ctx_pid', os.getpid())
+    assert _lib.ctx(0) is _lib._ctx[(0, 0)]                      # the parent itself keeps working
+    r, w = os.pipe()
+    pid = os.fork()
+    if pid == 0:                                                 # child
+        try:
+            _lib.ctx(0)
+            os.write(w, b'no error')
+        except RuntimeError as e:
+            os.write(w, b'refused' if 'fork' in str(e) else b'other')
+        finally:
+            os._exit(0)
+    os.close(w)
+    os.waitpid(pid, 0)
+    assert os.read(r, 64) == b'refused'
+    os.close(r)
