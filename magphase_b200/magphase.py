@@ -306,6 +306,8 @@ def _frames_call(l_sig, l_pm, fft_len, l_win, mode, compute=None, out_dtype=np.f
     if any(_has_custom_window(w) for w in l_win):
         # a window the kernels do not know in closed form: evaluate the caller's callables on the host, multiply them into
         # the frames' samples (float64) and run the kernels with weight 1 on that buffer
+        if np.any(left64 < 0) or np.any(right64 < 0):
+            raise ValueError('magphase_b200: frame reaches outside the signal (pitch marks must increase and lie inside it)')
         fns = [f for u in range(len(l_sig)) for f in _win_list(l_win[u], int(nfr[u]))]
         scale = 1.0 / 32768.0 if sig_np == np.dtype(np.int16) else 1.0
         sig_all, centre, _, _ = prewindowed_frames(sig_all.astype(np.float64) * scale, centre, left64, right64, fns)

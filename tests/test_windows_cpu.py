@@ -69,3 +69,11 @@ def test_window_classification_and_errors():
     assert off.tolist() == [0, 4, 7]
     np.testing.assert_allclose(w[:4], np.concatenate(([1.0], np.hanning(7)[:4][::-1][1:])))
     np.testing.assert_allclose(w[4:], np.hamming(5)[:3])
+
+
+def test_custom_window_path_rejects_marks_outside_the_signal():
+    """The host half validates the geometry before it gathers (the closed-form path leaves that to the C entry point)."""
+    sig = np.zeros(1000)
+    for pm in ([100.0, 50.0, 300.0], [100.0, 400.0, 2000.0]):
+        with pytest.raises(ValueError):
+            mp.analysis_with_del_comp_from_pm(sig, 48000, np.array(pm), win_func=np.hamming)
