@@ -140,3 +140,24 @@ def test_griffin_lim_golden():
         np.testing.assert_allclose(y, gl['syn_' + init], rtol=0, atol=1e-11)
         d = np.abs(np.angle(np.exp(1j * (ph[rows] - gl['phase_rows_' + init]))))
         assert np.max(d[strong]) < 1e-7
+
+
+def test_freqt_matrix_equals_the_all_pass_series_expansion():
+    """SPTK's `freqt` is absent here (parity unpinned), but what it computes is defined in print: the frequency
+    transformation of Oppenheim & Johnson (1972) that SPTK's manual cites -- C~(z~) = C(z) under the first-order all-pass
+    substitution z~^-1 = (z^-1 - a) / (1 - a z^-1), i.e. z^-1 = (x + a) / (1 + a x) with x = z~^-1.  So row m, column n of the
+    transform is the coefficient of x^m in ((x + a) / (1 + a x))^n.  Those coefficients are computed here by plain power-series
+    arithmetic (no recursion of SPTK's shape involved) and must equal the oracle's freqt matrix, which follows the published
+    recursion -- an independent derivation of the same linear map."""
+    for alpha, n_out, n_in in ((0.77, 60, 400), (0.58, 45, 257), (0.0, 10, 30), (-0.3, 12, 64)):
+        base = np.zeros(n_out, dtype=np.longdouble)                 # series of (x + a) / (1 + a x), truncated at x^(n_out-1)
+        geo = (-np.longdouble(alpha)) ** np.arange(n_out)           # 1 / (1 + a x) = sum (-a)^k x^k
+        base += alpha * geo
+        base[1:] += geo[:-1]
+        A = np.zeros((n_out, n_in), dtype=np.longdouble)
+        p = np.zeros(n_out, dtype=np.longdouble)
+        p[0] = 1.0                                                  # ((x + a) / (1 + a x))^0
+        for n in range(n_in):
+            A[:, n] = p
+            p = np.convolve(p, base)[:n_out]                        # next power, truncated
+        np.testing.assert_allclose(orc.freqt_matrix(n_out, n_in, alpha), A.astype(np.float64), rtol=0, atol=1e-11)

@@ -328,3 +328,30 @@ def test_windowing_helper_matches_reference(ref_modules):
         assert len(l_r) == len(l_m)
         for a, b in zip(l_r, l_m):
             np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize('alpha,fft_len', [(0.77, 4096), (0.58, 2048)])
+def test_restated_mcep_inverts_the_references_own_cosine_map(ref_modules, alpha, fft_len):
+    """SPTK's `mcep -j 0` is a third-party binary that is not available (parity unpinned).  What CAN be anchored
+    on the reference itself: its own la.mcep_to_sp_cosmat (src/libaudio.py:605-631) is the synthesis-side inverse of the
+    analysis-side `mcep`: a spectrum built from mel-cepstral coefficients by the REFERENCE's function must give those
+    coefficients back through the restated analysis step (to the float32 rounding SPTK's file interface applies and the
+    1e-8 floor of `-e`).  A wrong factor (the halved c[0] / c[N/2], power vs. amplitude), a wrong sign of alpha or a wrong
+    frequency transformation all break this identity at the 1e-1 level."""
+    mp, la, lu = ref_modules
+    rng = np.random.default_rng(0)
+    H = fft_len // 2 + 1
+    mc = np.zeros((6, 60))
+    mc[:, :25] = rng.standard_normal((6, 25)) * np.exp(-0.25 * np.arange(25))[None, :]
+    mc[:, 0] = rng.uniform(-3, 1, 6)
+    sp = la.mcep_to_sp_cosmat(mc, H, alpha=alpha, out_type='abs')
+    assert sp.min() > 1e-3                                                   # far above the 1e-8 floor of `-e`
+    for in_type, x in ((3, sp), (2, np.log(sp)), (1, 20 * np.log10(sp))):
+        back = orc.mcep_j0(x, n_coeffs=60, alpha=alpha, in_type=in_type)
+        assert np.sqrt(np.mean((back - mc) ** 2)) < 3e-6, in_type
+        assert np.abs(back - mc).max() < 3e-5, in_type
+    # ... and the whole warp of format_for_modelling: la.sp_mel_warp's output is the log spectrum on the alpha=0 axis of the
+    # same coefficients (src/libaudio.py:643-661)
+    warped = orc.sp_mel_warp(sp, 60, alpha=alpha, in_type=3)
+    direct = la.mcep_to_sp_cosmat(mc, 60, alpha=0.0, out_type='abs')
+    np.testing.assert_allclose(np.log(warped), np.log(direct), rtol=0, atol=2e-4)
