@@ -161,3 +161,29 @@ def test_freqt_matrix_equals_the_all_pass_series_expansion():
             A[:, n] = p
             p = np.convolve(p, base)[:n_out]                        # next power, truncated
         np.testing.assert_allclose(orc.freqt_matrix(n_out, n_in, alpha), A.astype(np.float64), rtol=0, atol=1e-11)
+
+
+def test_restated_merlin_post_filter_preserves_frame_energy():
+    """pf_type='merlin' (src/magphase.py:3375-3465) pipes the cepstrum through SPTK binaries that are absent here (parity
+    unpinned).  The pipeline's documented purpose is checkable without them: it sharpens the formants with a cepstral lifter
+    and then resets c0 so that every frame keeps its energy (the r[0] of `c2acr`).  The restatement must therefore change the
+    spectrum (it is not a no-op) while the autocorrelation r[0] of every frame, recomputed here from the OUTPUT, stays
+    where it was -- to the float32 round-off of the pipe and the 60-coefficient truncation."""
+    g = np.load(os.path.join(GOLD, 'compressed_hvd704.npz'))
+    mag = g['mag'].astype(np.float64)
+    out = orc.post_filter_merlin(mag, 48000)
+
+    def r0_of(m):
+        n = m.shape[1]
+        ext = np.hstack((m, m[:, -2:0:-1]))
+        ceps = np.fft.ifft(ext, axis=1).real
+        ceps[:, 1:(n - 2)] *= 2
+        F = orc.freqt_matrix(2048, n, -orc.define_alpha(48000))
+        return orc.sptk_c2acr_r0(ceps[:, :n] @ F.T, 4096)
+
+    ratio = r0_of(out) / r0_of(mag)
+    assert np.all(np.abs(ratio - 1.0) < 5e-3), (ratio.min(), ratio.max())
+    assert np.abs(out - mag).mean() > 0.1                            # the formant enhancement itself
+    # mc2b / b2mc are exact inverses of each other (their definition), whatever alpha
+    x = np.random.default_rng(0).standard_normal((5, 60))
+    np.testing.assert_allclose(orc.sptk_b2mc(orc.sptk_mc2b(x, 0.77), 0.77), x, rtol=0, atol=1e-12)
