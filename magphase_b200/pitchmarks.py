@@ -61,6 +61,7 @@ def estimate_pitch_marks(v_sig, fs, f0_min=50.0, f0_max=400.0, unv_step=0.005, v
     voi_smp = np.interp(np.arange(n), centre, voiced.astype(np.float64)) > 0.5
     marks, flags = [], []
     unv = int(round(unv_step * fs))
+    min_gap = max(1, int(0.7 * fs / f0_max))                                       # = the lower end of the epoch search below
     pos = 0
     while pos < n - 1:
         if not voi_smp[pos]:
@@ -83,8 +84,12 @@ def estimate_pitch_marks(v_sig, fs, f0_min=50.0, f0_max=400.0, unv_step=0.005, v
             continue
         sign = 1.0 if seg.max() >= -seg.min() else -1.0
         m = pos + int(np.argmax(sign * seg[:T0 + 1]))
-        if marks and m <= marks[-1]:
-            m = marks[-1] + 1
+        # no two marks closer than the shortest period searched for: an unvoiced filler mark that would sit right in front
+        # of the stretch's first epoch gives way to it (a one-sample frame would read as f0 = fs there)
+        while marks and flags[-1] == 0.0 and m - marks[-1] < min_gap:
+            marks.pop(); flags.pop()
+        if marks and m - marks[-1] < min_gap:
+            m = marks[-1] + min_gap
         while m < min(end, n - 1):
             marks.append(m); flags.append(1.0)
             T = per_smp[m]

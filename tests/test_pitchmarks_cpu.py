@@ -43,3 +43,21 @@ def test_est_file_round_trip_and_short_signals(tmp_path):
     assert t.size == 0 or np.all(v == 0)
     t, v = estimate_pitch_marks(np.zeros(48000), 48000)                         # silence: unvoiced marks every 5 ms
     assert np.all(v == 0) and np.allclose(np.diff(t), 0.005)
+
+
+def test_no_two_marks_closer_than_the_shortest_period():
+    """An unvoiced filler mark right in front of a voiced stretch's first epoch used to leave frames of 1-40 samples (read
+    as f0 = fs / 1 by shift_to_f0): consecutive marks now keep at least 0.7 / f0_max seconds, on synthetic speech and -- where
+    the reference's recordings are present -- on natural speech."""
+    cases = [synth_utterance(u, fs=48000, dur_s=1.5)[0] for u in (2, 5, 9)]
+    d = '/root/reference/demos/data_48k/wavs_nat'
+    if os.path.isdir(d):
+        from scipy.io import wavfile
+        for name in sorted(os.listdir(d))[:4]:
+            cases.append(wavfile.read(os.path.join(d, name))[1].astype(np.float64) / 32768.0)
+    for sig in cases:
+        pm_s, vv = estimate_pitch_marks(sig, 48000)
+        gaps = np.diff(np.round(pm_s * 48000))
+        assert gaps.min() >= int(0.7 * 48000 / 400.0), gaps.min()
+        assert gaps.max() <= 0.03 * 48000                               # never more than 1.3 periods of 50 Hz + one filler step
+        assert 0.1 < vv.mean() < 0.9
