@@ -203,3 +203,23 @@ def test_generation_resume_writes_the_files_of_an_uninterrupted_run(tmp_path, mo
     for t in tokens:
         assert open(os.path.join(part, t + '.wav'), 'rb').read() == open(os.path.join(full, t + '.wav'), 'rb').read(), t
     assert not [f for f in os.listdir(part) if f.startswith('.tmp')]
+
+
+def test_cli_passes_resume_and_skip_errors(monkeypatch, capsys):
+    seen = {}
+
+    def fake_extract(scp, wav_dir, out_dir, **kw):
+        seen['extract'] = kw
+        return dict(utterances=3, frames=30, seconds=1.0, skipped=['a'], failed=[])
+
+    def fake_generate(scp, feats_dir, out_dir, mag_dim, phase_dim, fs, **kw):
+        seen['generate'] = kw
+        return dict(utterances=2, frames=20, seconds=1.0, skipped=[], failed=['b'])
+    monkeypatch.setattr(batch, 'run_feature_extraction', fake_extract)
+    monkeypatch.setattr(batch, 'run_waveform_generation', fake_generate)
+    batch.main(['extract', '--scp', 's', '--wav-dir', 'w', '--out-dir', 'o', '--resume', '--skip-errors'])
+    assert seen['extract']['resume'] is True and seen['extract']['on_error'] == 'skip'
+    batch.main(['generate', '--scp', 's', '--feats-dir', 'f', '--out-dir', 'o'])
+    assert seen['generate']['resume'] is False and seen['generate']['on_error'] == 'raise'
+    out = capsys.readouterr().out
+    assert '1 tokens already done, 0 failed' in out and '0 tokens already done, 1 failed' in out and out.count('Done!') == 2
