@@ -83,7 +83,7 @@ def estimate_pitch_marks(v_sig, fs, f0_min=50.0, f0_max=400.0, unv_step=0.005, v
             pos = end
             continue
         sign = 1.0 if seg.max() >= -seg.min() else -1.0
-        m = pos + int(np.argmax(sign * seg[:T0 + 1]))
+        m = max(1, pos + int(np.argmax(sign * seg[:T0 + 1])))          # never on sample 0: a zero-length first frame reads as f0 = inf
         # no two marks closer than the shortest period searched for: an unvoiced filler mark that would sit right in front
         # of the stretch's first epoch gives way to it (a one-sample frame would read as f0 = fs there)
         while marks and flags[-1] == 0.0 and m - marks[-1] < min_gap:

@@ -61,3 +61,15 @@ def test_no_two_marks_closer_than_the_shortest_period():
         assert gaps.min() >= int(0.7 * 48000 / 400.0), gaps.min()
         assert gaps.max() <= 0.03 * 48000                               # never more than 1.3 periods of 50 Hz + one filler step
         assert 0.1 < vv.mean() < 0.9
+
+
+def test_no_mark_on_sample_zero():
+    """A recording that starts inside a voiced sound with its strongest peak on the very first sample: the first mark must not
+    be sample 0 (shift 0 -> f0 = voi * fs / 0 in shift_to_f0, src/magphase.py:2198-2207)."""
+    fs = 48000
+    t = np.arange(int(0.4 * fs)) / fs
+    sig = 0.5 * np.cos(2 * np.pi * 120.0 * t) + 0.25 * np.cos(2 * np.pi * 240.0 * t)      # peaks at t = 0, 1/120, ...
+    pm_s, vv = estimate_pitch_marks(sig, fs)
+    est = np.round(pm_s * fs)
+    assert est.size > 20 and est[0] >= 1 and np.all(np.diff(est) > 0)
+    assert vv.mean() > 0.8 and abs(np.median(fs / np.diff(est)[(vv[1:] > 0) & (vv[:-1] > 0)]) - 120.0) < 3.0
